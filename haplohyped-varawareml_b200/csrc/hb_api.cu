@@ -1,0 +1,752 @@
+// hb_api.cu -- host side of libhaplo_b200: the C ABI of include/haplo_b200.h sections A and B.
+//
+// Mirrors the reference's native layer (cpp/parse_vcf.cpp + the BcfReader of cpp/vcfpp.h) above
+// the kernels: open a .vcf / .vcf.gz (BGZF or plain gzip), read the header (sample names,
+// INFO/END type; vcfpp.h:1378-1385), ship the decompressed body to HBM, run tokenize -> sites ->
+// GT decode once for ALL samples, and answer load_vcf(sample) / load_vcf_without_sample calls
+// from that device-resident result.  No CPU parsing path exists: without a CUDA device every
+// entry point fails with HB_ERR_CUDA.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/haplo_b200.h"
+#include "hb_internal.h"
+
+namespace hb {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(uint64_t n) { g_launches += n; }
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e_) + " at " #expr); \
+    } while (0)
+
+static int ensure_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(HB_ERR_CUDA, "no CUDA device: libhaplo_b200 has no CPU fallback (" +
+                                     std::string(e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) + ")");
+    if (device < 0 || device >= n) return fail(HB_ERR_ARG, "bad device ordinal");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return fail(HB_ERR_CUDA, "libhaplo_b200 is built for sm_100a only; device is sm_" +
+                                                    std::to_string(p.major) + std::to_string(p.minor));
+    return HB_OK;
+}
+
+static void parse_region(const char *s, RegionArg &rg) {
+    memset(&rg, 0, sizeof rg);
+    rg.beg0 = 0;
+    rg.end0 = INT64_MAX;
+    if (!s || !*s) return;
+    rg.has_region = 1;
+    const char *colon = strrchr(s, ':');
+    size_t nlen = colon ? (size_t)(colon - s) : strlen(s);
+    if (nlen >= sizeof rg.chrom) nlen = sizeof rg.chrom - 1;
+    memcpy(rg.chrom, s, nlen);
+    rg.chrom_len = (uint32_t)nlen;
+    if (colon) {
+        long long v = 0;
+        bool any = false;
+        const char *p = colon + 1;
+        for (; *p && *p != '-'; ++p)
+            if (*p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); any = true; }
+        if (any && v > 0) rg.beg0 = v - 1;
+        if (*p == '-') {
+            v = 0; any = false;
+            for (++p; *p; ++p)
+                if (*p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); any = true; }
+            if (any) rg.end0 = v;
+        }
+    }
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+// =============================================================================================
+// hb_parse: one device-resident parse
+// =============================================================================================
+struct hb_parse {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    const uint8_t *d_text = nullptr;
+    uint8_t *d_text_owned = nullptr;
+    uint64_t nbytes = 0;
+    uint32_t n_samples = 0;
+    RegionArg rg;
+    int end_is_int = 0, want_gt = 1, tokenizer = 0;
+    bool with_tabs = false;
+    uint32_t ncp = 0;
+
+    uint64_t *d_tile_state = nullptr; uint64_t tile_cap = 0;
+    uint64_t *d_line_start = nullptr; uint64_t line_cap = 0;
+    uint64_t *d_cp = nullptr; uint64_t cp_rows = 0;
+    DevStatus *d_st = nullptr;
+    DevStatus h_st;
+    uint32_t *d_start = nullptr, *d_stop = nullptr;
+    uint8_t *d_ref = nullptr, *d_alt = nullptr, *d_chrom_len = nullptr;
+    uint64_t *d_chrom_abs = nullptr;
+    RowInfo *d_rowinfo = nullptr;
+    uint32_t *d_nu_rows = nullptr;
+    uint64_t *d_sites_state = nullptr;
+    uint64_t row_cap = 0;
+    int8_t *d_gt[2] = {nullptr, nullptr};
+    uint64_t gt_stride = 0, gt_bytes = 0;
+    uint32_t *d_ploidy = nullptr, *d_badgt = nullptr;
+    uint64_t *d_run_rows = nullptr;
+    static constexpr uint64_t kMaxRuns = 4096;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms_tok = 0, ms_sites = 0, ms_decode = 0;
+    // chrom runs (host)
+    std::vector<uint64_t> run_rows;
+    std::vector<std::string> run_names;
+};
+
+static void free_dev(void *p) { if (p) cudaFree(p); }
+
+void hb_parse_free(hb_parse *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    free_dev(p->d_text_owned); free_dev(p->d_tile_state); free_dev(p->d_line_start); free_dev(p->d_cp);
+    free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
+    free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
+    free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_ploidy);
+    free_dev(p->d_badgt); free_dev(p->d_run_rows);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    delete p;
+}
+
+template <typename T>
+static int dev_alloc(T **p, uint64_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(HB_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return HB_OK;
+}
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != HB_OK) return rc_; } while (0)
+
+// look at the first record of the body: FORMAT == "GT" -> newline-only tokenizer is enough
+static void probe_head(const uint8_t *h, size_t n, bool &gt_only, uint64_t &first_line_len) {
+    gt_only = false;
+    first_line_len = 0;
+    size_t i = 0;
+    int f = 0;
+    size_t fs = 0;
+    for (; i < n; ++i) {
+        if (h[i] == '\t' || h[i] == '\n') {
+            if (f == 8) gt_only = (i - fs == 2 && h[fs] == 'G' && h[fs + 1] == 'T');
+            if (h[i] == '\n') break;
+            ++f;
+            fs = i + 1;
+        }
+    }
+    if (i < n) first_line_len = i + 1;
+}
+
+static int run_parse(hb_parse *p) {
+    CU(cudaSetDevice(p->device));
+    Launch L{p->stream, p->sm_count};
+    const uint64_t tile = tokenize_tile_bytes();
+    const uint64_t n_tiles = (p->nbytes + tile - 1) / tile;
+    if (!p->d_st) TRY(dev_alloc(&p->d_st, 1));
+    CU(cudaMemsetAsync(p->d_st, 0, sizeof(DevStatus), p->stream));
+    memset(&p->h_st, 0, sizeof p->h_st);
+    p->ncp = (p->n_samples + kCP - 1) / kCP;
+    if (p->nbytes == 0) return HB_OK;
+
+    // ---- tokenizer mode + capacity estimate from the first record
+    if (p->line_cap == 0) {
+        uint8_t head[65536];
+        size_t hn = (size_t)std::min<uint64_t>(sizeof head, p->nbytes);
+        CU(cudaMemcpyAsync(head, p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        bool gt_only; uint64_t l0;
+        probe_head(head, hn, gt_only, l0);
+        p->with_tabs = p->tokenizer == 2 || (p->tokenizer == 0 && !gt_only);
+        if (!p->want_gt) p->with_tabs = false;
+        uint64_t est = l0 ? p->nbytes / l0 : p->nbytes / hn;
+        p->line_cap = est + est / 4 + 1024;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (!p->d_line_start) TRY(dev_alloc(&p->d_line_start, p->line_cap));
+        if (p->tile_cap < n_tiles) { TRY(dev_alloc(&p->d_tile_state, n_tiles)); p->tile_cap = n_tiles; }
+        if (p->with_tabs) {
+            if (p->cp_rows < p->line_cap) { TRY(dev_alloc(&p->d_cp, p->line_cap * p->ncp)); p->cp_rows = p->line_cap; }
+            CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
+        }
+        CU(cudaEventRecord(p->ev[0], p->stream));
+        launch_tokenize(p->with_tabs, p->d_text, p->nbytes, p->d_tile_state, n_tiles, p->d_line_start, p->line_cap,
+                        p->d_cp, p->ncp, p->d_st, L);
+        CU(cudaEventRecord(p->ev[1], p->stream));
+        CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        CU(cudaGetLastError());
+        if (!p->h_st.line_overflow) break;
+        if (attempt == 1) return fail(HB_ERR_MEM, "line index overflow");
+        p->line_cap = p->h_st.n_lines + 2;     // exact count is known even when the index overflowed
+        free_dev(p->d_line_start); p->d_line_start = nullptr;
+        free_dev(p->d_cp); p->d_cp = nullptr; p->cp_rows = 0;
+        CU(cudaMemsetAsync(p->d_st, 0, sizeof(DevStatus), p->stream));
+    }
+    const uint64_t n_lines = p->h_st.n_lines;
+
+    // ---- sites
+    if (p->row_cap < n_lines || !p->d_start) {
+        uint64_t cap = n_lines;
+        TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
+        TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
+        TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap));
+        TRY(dev_alloc(&p->d_rowinfo, cap)); TRY(dev_alloc(&p->d_nu_rows, cap));
+        TRY(dev_alloc(&p->d_sites_state, (cap + 255) / 256 + 1));
+        p->row_cap = cap;
+    }
+    if (!p->d_ploidy) {
+        TRY(dev_alloc(&p->d_ploidy, p->n_samples)); TRY(dev_alloc(&p->d_badgt, p->n_samples));
+        TRY(dev_alloc(&p->d_run_rows, hb_parse::kMaxRuns));
+    }
+    CU(cudaMemsetAsync(p->d_ploidy, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
+    CU(cudaMemsetAsync(p->d_badgt, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
+    launch_sites(p->d_text, p->d_line_start, n_lines, p->n_samples, p->rg, p->end_is_int, p->want_gt, p->with_tabs,
+                 p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_rowinfo,
+                 p->d_nu_rows, p->d_sites_state, p->d_st, L);
+    CU(cudaEventRecord(p->ev[2], p->stream));
+    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    const uint64_t n_rec = p->h_st.n_records;
+
+    // ---- GT decode
+    if (p->want_gt && n_rec && p->n_samples) {
+        if (!p->with_tabs && p->h_st.n_nonuniform) {
+            uint64_t n_nu = p->h_st.n_nonuniform;
+            if (p->cp_rows < n_nu) { TRY(dev_alloc(&p->d_cp, n_nu * p->ncp)); p->cp_rows = n_nu; }
+            CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
+            launch_index_columns(p->d_text, p->d_rowinfo, p->d_nu_rows, n_nu, p->d_cp, p->ncp, L);
+        }
+        uint64_t stride = (n_rec + kTV - 1) / kTV * kTV;
+        uint64_t bytes = stride * p->n_samples;
+        if (p->gt_bytes < bytes || p->gt_stride != stride) {
+            TRY(dev_alloc(&p->d_gt[0], bytes)); TRY(dev_alloc(&p->d_gt[1], bytes));
+            p->gt_bytes = bytes; p->gt_stride = stride;
+        }
+        launch_decode_gt(p->d_text, p->d_rowinfo, n_rec, p->n_samples, p->d_cp, p->ncp, p->d_gt[0], p->d_gt[1],
+                         p->gt_stride, p->d_ploidy, p->d_badgt, p->d_st, L);
+    }
+    CU(cudaEventRecord(p->ev[3], p->stream));
+    launch_chrom_runs(p->d_text, p->d_chrom_abs, p->d_chrom_len, n_rec, p->d_run_rows, hb_parse::kMaxRuns, p->d_st, L);
+    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    cudaEventElapsedTime(&p->ms_tok, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&p->ms_sites, p->ev[1], p->ev[2]);
+    cudaEventElapsedTime(&p->ms_decode, p->ev[2], p->ev[3]);
+
+    // ---- CHROM runs -> names (a handful of tiny D2H copies)
+    p->run_rows.clear(); p->run_names.clear();
+    uint64_t n_runs = std::min<uint64_t>(p->h_st.n_chrom_runs, hb_parse::kMaxRuns);
+    if (p->h_st.n_chrom_runs > hb_parse::kMaxRuns) return fail(HB_ERR_FORMAT, "more than 4096 CHROM runs (unsorted VCF?)");
+    if (n_runs) {
+        p->run_rows.resize(n_runs);
+        CU(cudaMemcpy(p->run_rows.data(), p->d_run_rows, n_runs * 8, cudaMemcpyDeviceToHost));
+        std::sort(p->run_rows.begin(), p->run_rows.end());
+        for (uint64_t r : p->run_rows) {
+            uint64_t abs; uint8_t len; char name[256];
+            CU(cudaMemcpy(&abs, p->d_chrom_abs + r, 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&len, p->d_chrom_len + r, 1, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(name, p->d_text + abs, len, cudaMemcpyDeviceToHost));
+            p->run_names.emplace_back(name, name + len);
+        }
+    }
+    if (p->h_st.n_bad_cols)
+        return fail(HB_ERR_FORMAT, "Number of columns does not match the number of samples (" +
+                                       std::to_string(p->h_st.n_bad_cols) + " records)");
+    return HB_OK;
+}
+
+static int new_parse(const hb_parse_opts *o, hb_parse **out) {
+    if (!o || !out) return fail(HB_ERR_ARG, "null argument");
+    TRY(ensure_device(o->device));
+    hb_parse *p = new hb_parse();
+    p->device = o->device;
+    p->stream = (cudaStream_t)o->stream;
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, o->device);
+    p->n_samples = o->n_samples;
+    parse_region(o->region, p->rg);
+    p->end_is_int = o->end_is_int;
+    p->want_gt = o->want_gt;
+    p->tokenizer = o->tokenizer;
+    for (auto &e : p->ev) cudaEventCreate(&e);
+    *out = p;
+    return HB_OK;
+}
+
+int hb_parse_device_text(const uint8_t *d_text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out) {
+    hb_parse *p = nullptr;
+    TRY(new_parse(opts, &p));
+    if (((uintptr_t)d_text & 15) != 0) { hb_parse_free(p); return fail(HB_ERR_ARG, "d_text must be 16-byte aligned"); }
+    p->d_text = d_text;
+    p->nbytes = nbytes;
+    int rc = run_parse(p);
+    if (rc != HB_OK) { hb_parse_free(p); return rc; }
+    *out = p;
+    return HB_OK;
+}
+
+int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out) {
+    hb_parse *p = nullptr;
+    TRY(new_parse(opts, &p));
+    bool add_nl = nbytes && text[nbytes - 1] != '\n';
+    uint64_t total = nbytes + (add_nl ? 1 : 0);
+    int rc = dev_alloc(&p->d_text_owned, total + 256);
+    if (rc != HB_OK) { hb_parse_free(p); return rc; }
+    cudaError_t e = cudaMemcpyAsync(p->d_text_owned, text, nbytes, cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess && add_nl) e = cudaMemsetAsync(p->d_text_owned + nbytes, '\n', 1, p->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_text_owned + total, 0, 256, p->stream);
+    if (e != cudaSuccess) { hb_parse_free(p); return fail(HB_ERR_CUDA, cudaGetErrorString(e)); }
+    p->d_text = p->d_text_owned;
+    p->nbytes = total;
+    rc = run_parse(p);
+    if (rc != HB_OK) { hb_parse_free(p); return rc; }
+    *out = p;
+    return HB_OK;
+}
+
+int hb_parse_rerun(hb_parse *p) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    return run_parse(p);
+}
+
+int hb_parse_get_info(const hb_parse *p, hb_parse_info *info) {
+    if (!p || !info) return fail(HB_ERR_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    info->text_bytes = p->nbytes;
+    info->n_lines = p->h_st.n_lines;
+    info->n_records = p->h_st.n_records;
+    info->n_samples = p->n_samples;
+    info->gt_stride = p->gt_stride;
+    info->d_gt[0] = p->d_gt[0];
+    info->d_gt[1] = p->d_gt[1];
+    info->d_start = p->d_start; info->d_stop = p->d_stop; info->d_ref = p->d_ref; info->d_alt = p->d_alt;
+    info->n_nonuniform = p->h_st.n_nonuniform;
+    info->n_bad_gt = p->h_st.n_bad_gt;
+    info->n_bad_cols = p->h_st.n_bad_cols;
+    info->n_nogt = p->h_st.n_nogt;
+    info->tokenizer_used = p->with_tabs ? 2 : 1;
+    info->ms_tokenize = p->ms_tok; info->ms_sites = p->ms_sites; info->ms_decode = p->ms_decode;
+    return HB_OK;
+}
+
+int hb_parse_fetch_sites(hb_parse *p, uint32_t *start, uint32_t *stop, char *ref, char *alt) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(p->device));
+    uint64_t n = p->h_st.n_records;
+    if (!n) return HB_OK;
+    if (start) CU(cudaMemcpyAsync(start, p->d_start, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (stop) CU(cudaMemcpyAsync(stop, p->d_stop, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    if (ref) CU(cudaMemcpyAsync(ref, p->d_ref, n, cudaMemcpyDeviceToHost, p->stream));
+    if (alt) CU(cudaMemcpyAsync(alt, p->d_alt, n, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return HB_OK;
+}
+
+int hb_parse_fetch_sample(hb_parse *p, uint32_t s, int8_t *gt0, int8_t *gt1) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    if (s >= p->n_samples) return fail(HB_ERR_SAMPLE, "sample index out of range");
+    CU(cudaSetDevice(p->device));
+    uint64_t n = p->h_st.n_records;
+    if (!n) return HB_OK;
+    if (!p->d_gt[0]) return fail(HB_ERR_NOGT, "parse was made without genotypes");
+    if (gt0) CU(cudaMemcpyAsync(gt0, p->d_gt[0] + (uint64_t)s * p->gt_stride, n, cudaMemcpyDeviceToHost, p->stream));
+    if (gt1) CU(cudaMemcpyAsync(gt1, p->d_gt[1] + (uint64_t)s * p->gt_stride, n, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return HB_OK;
+}
+
+int hb_parse_fetch_matrix(hb_parse *p, int8_t *gt0, int8_t *gt1) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(p->device));
+    uint64_t n = p->h_st.n_records;
+    if (!n || !p->n_samples) return HB_OK;
+    if (!p->d_gt[0]) return fail(HB_ERR_NOGT, "parse was made without genotypes");
+    if (gt0) CU(cudaMemcpy2DAsync(gt0, n, p->d_gt[0], p->gt_stride, n, p->n_samples, cudaMemcpyDeviceToHost, p->stream));
+    if (gt1) CU(cudaMemcpy2DAsync(gt1, n, p->d_gt[1], p->gt_stride, n, p->n_samples, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return HB_OK;
+}
+
+int hb_parse_fetch_sample_errors(hb_parse *p, uint32_t *ploidy, uint32_t *badgt) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(p->device));
+    if (!p->n_samples || !p->d_ploidy) return HB_OK;
+    if (ploidy) CU(cudaMemcpy(ploidy, p->d_ploidy, p->n_samples * 4ull, cudaMemcpyDeviceToHost));
+    if (badgt) CU(cudaMemcpy(badgt, p->d_badgt, p->n_samples * 4ull, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint64_t max_runs, char *names,
+                        uint64_t names_cap, uint64_t *names_len) {
+    if (!p || !n_runs) return fail(HB_ERR_ARG, "null argument");
+    *n_runs = p->run_rows.size();
+    uint64_t used = 0;
+    for (size_t i = 0; i < p->run_rows.size(); ++i) {
+        if (row_begin && i < max_runs) row_begin[i] = p->run_rows[i];
+        const std::string &s = p->run_names[i];
+        if (names && used + s.size() + 1 <= names_cap) memcpy(names + used, s.c_str(), s.size() + 1);
+        used += s.size() + 1;
+    }
+    if (names_len) *names_len = used;
+    return HB_OK;
+}
+
+// =============================================================================================
+// File level: .vcf / .vcf.gz reader (BGZF blocks inflate in parallel) + per-(file, region) cache
+// =============================================================================================
+namespace {
+
+struct FileText {
+    std::vector<uint8_t> data;   // whole decompressed file
+    uint64_t body = 0;           // offset of the first record
+    std::vector<std::string> samples;
+    int end_is_int = 0;
+};
+
+int read_all(const char *path, std::vector<uint8_t> &raw) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(HB_ERR_IO, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    raw.resize((size_t)sz);
+    size_t got = sz ? fread(raw.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    if (got != (size_t)sz) return fail(HB_ERR_IO, std::string("short read on ") + path);
+    return HB_OK;
+}
+
+// BGZF: every gzip member carries a 'BC' extra subfield with the block size (htslib bgzf.c)
+bool bgzf_blocks(const std::vector<uint8_t> &raw, std::vector<std::pair<uint64_t, uint32_t>> &blocks,
+                 std::vector<uint64_t> &out_off, uint64_t &total) {
+    uint64_t p = 0;
+    total = 0;
+    while (p < raw.size()) {
+        if (p + 18 > raw.size()) return false;
+        const uint8_t *h = raw.data() + p;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+        uint32_t xlen = h[10] | (h[11] << 8);
+        uint32_t bsize = 0;
+        bool found = false;
+        uint64_t q = p + 12, xe = p + 12 + xlen;
+        if (xe > raw.size()) return false;
+        while (q + 4 <= xe) {
+            uint32_t slen = raw[q + 2] | (raw[q + 3] << 8);
+            if (raw[q] == 'B' && raw[q + 1] == 'C' && slen == 2) { bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1; found = true; }
+            q += 4 + slen;
+        }
+        if (!found || p + bsize > raw.size() || bsize < 12 + xlen + 8) return false;
+        const uint8_t *tr = raw.data() + p + bsize - 4;
+        uint32_t isize = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        blocks.emplace_back(p, bsize);
+        out_off.push_back(total);
+        total += isize;
+        p += bsize;
+    }
+    return !blocks.empty();
+}
+
+int inflate_all(const std::vector<uint8_t> &raw, std::vector<uint8_t> &out) {
+    if (raw.size() < 2 || raw[0] != 0x1f || raw[1] != 0x8b) { out = raw; return HB_OK; }   // plain text
+    std::vector<std::pair<uint64_t, uint32_t>> blocks;
+    std::vector<uint64_t> off;
+    uint64_t total = 0;
+    if (bgzf_blocks(raw, blocks, off, total)) {
+        out.resize(total);
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+        nt = (unsigned)std::min<size_t>(nt, blocks.size());
+        std::atomic<size_t> next{0};
+        std::atomic<int> bad{0};
+        auto work = [&]() {
+            z_stream zs;
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= blocks.size()) break;
+                const uint8_t *h = raw.data() + blocks[i].first;
+                uint32_t xlen = h[10] | (h[11] << 8);
+                uint64_t outlen = (i + 1 < blocks.size() ? off[i + 1] : total) - off[i];
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; break; }
+                zs.next_in = const_cast<Bytef *>(h + 12 + xlen);
+                zs.avail_in = blocks[i].second - 12 - xlen - 8;
+                zs.next_out = out.data() + off[i];
+                zs.avail_out = (uInt)outlen;
+                int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (bad) return fail(HB_ERR_IO, "BGZF inflate failed");
+        return HB_OK;
+    }
+    // plain (possibly multi-member) gzip, e.g. the reference's own test fixture
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) return fail(HB_ERR_IO, "inflateInit2 failed");
+    zs.next_in = const_cast<Bytef *>(raw.data());
+    uint64_t in_left = raw.size();
+    out.resize(std::max<size_t>(raw.size() * 4, 1 << 16));
+    uint64_t produced = 0;
+    for (;;) {
+        if (out.size() - produced < (1 << 16)) out.resize(out.size() * 2);
+        zs.avail_in = (uInt)std::min<uint64_t>(in_left, 1u << 30);
+        uInt ain = zs.avail_in;
+        zs.next_out = out.data() + produced;
+        zs.avail_out = (uInt)std::min<uint64_t>(out.size() - produced, 1u << 30);
+        uInt aout = zs.avail_out;
+        int rc = inflate(&zs, Z_NO_FLUSH);
+        produced += aout - zs.avail_out;
+        in_left -= ain - zs.avail_in;
+        if (rc == Z_STREAM_END) {
+            if (in_left == 0) break;
+            if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); return fail(HB_ERR_IO, "gzip member reset failed"); }
+            continue;
+        }
+        if (rc != Z_OK && rc != Z_BUF_ERROR) { inflateEnd(&zs); return fail(HB_ERR_IO, "gzip inflate failed"); }
+        if (rc == Z_BUF_ERROR && in_left == 0 && zs.avail_out != 0) { inflateEnd(&zs); return fail(HB_ERR_IO, "truncated gzip"); }
+    }
+    inflateEnd(&zs);
+    out.resize(produced);
+    return HB_OK;
+}
+
+int read_vcf(const char *path, FileText &ft) {
+    std::vector<uint8_t> raw;
+    TRY(read_all(path, raw));
+    TRY(inflate_all(raw, ft.data));
+    raw.clear(); raw.shrink_to_fit();
+    if (!ft.data.empty() && ft.data.back() != '\n') ft.data.push_back('\n');
+    // header
+    uint64_t p = 0, n = ft.data.size();
+    const uint8_t *d = ft.data.data();
+    bool have = false;
+    while (p < n && d[p] == '#') {
+        const uint8_t *e = (const uint8_t *)memchr(d + p, '\n', n - p);
+        uint64_t le = e ? (uint64_t)(e - d) : n;
+        if (p + 1 < n && d[p + 1] == '#') {
+            std::string line((const char *)d + p, (const char *)d + le);
+            if (line.compare(0, 15, "##INFO=<ID=END,") == 0 && line.find("Type=Integer") != std::string::npos) ft.end_is_int = 1;
+        } else {
+            uint64_t ce = le;
+            if (ce > p && d[ce - 1] == '\r') --ce;
+            uint64_t q = p; int col = 0;
+            while (q <= ce) {
+                const uint8_t *t = (const uint8_t *)memchr(d + q, '\t', ce - q);
+                uint64_t te = t ? (uint64_t)(t - d) : ce;
+                if (col >= 9) ft.samples.emplace_back((const char *)d + q, (const char *)d + te);
+                ++col;
+                if (!t) break;
+                q = te + 1;
+            }
+            have = true;
+        }
+        p = e ? le + 1 : n;
+        if (have) break;
+    }
+    if (!have) return fail(HB_ERR_HEADER, "no #CHROM header line");
+    ft.body = p;
+    return HB_OK;
+}
+
+struct CacheEntry {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    int rc = HB_OK;
+    std::string err;
+    hb_parse *parse = nullptr;
+    std::vector<std::string> samples;
+    std::vector<uint32_t> start, stop, chrom_off;
+    std::vector<char> ref, alt;
+    std::string chrom_pool;
+    std::vector<uint32_t> ploidy_err, badgt_err;
+    bool want_gt = true;
+    ~CacheEntry() { if (parse) hb_parse_free(parse); }
+};
+
+std::mutex g_cache_mu;
+std::map<std::string, std::shared_ptr<CacheEntry>> g_cache;
+
+int env_device() {
+    const char *e = getenv("HB_DEVICE");
+    if (e && *e) return atoi(e);
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    return d;
+}
+
+int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_gt) {
+    FileText ft;
+    TRY(read_vcf(path, ft));
+    ce.samples = ft.samples;
+    ce.want_gt = want_gt;
+    hb_parse_opts o;
+    memset(&o, 0, sizeof o);
+    o.n_samples = (uint32_t)ft.samples.size();
+    o.region = region;
+    o.end_is_int = ft.end_is_int;
+    o.want_gt = want_gt ? 1 : 0;
+    o.device = env_device();
+    TRY(hb_parse_host_text(ft.data.data() + ft.body, ft.data.size() - ft.body, &o, &ce.parse));
+    hb_parse *p = ce.parse;
+    uint64_t n = p->h_st.n_records;
+    ce.start.resize(n); ce.stop.resize(n); ce.ref.resize(n); ce.alt.resize(n); ce.chrom_off.resize(n);
+    TRY(hb_parse_fetch_sites(p, ce.start.data(), ce.stop.data(), ce.ref.data(), ce.alt.data()));
+    for (size_t i = 0; i < p->run_rows.size(); ++i) {
+        uint32_t off = (uint32_t)ce.chrom_pool.size();
+        ce.chrom_pool.append(p->run_names[i]);
+        ce.chrom_pool.push_back('\0');
+        uint64_t b = p->run_rows[i], e = i + 1 < p->run_rows.size() ? p->run_rows[i + 1] : n;
+        for (uint64_t r = b; r < e; ++r) ce.chrom_off[r] = off;
+    }
+    if (want_gt) {
+        ce.ploidy_err.resize(o.n_samples); ce.badgt_err.resize(o.n_samples);
+        TRY(hb_parse_fetch_sample_errors(p, ce.ploidy_err.data(), ce.badgt_err.data()));
+    }
+    // the text is no longer needed once names are resolved: give the HBM back
+    if (p->d_text_owned) { cudaFree(p->d_text_owned); p->d_text_owned = nullptr; p->d_text = nullptr; }
+    return HB_OK;
+}
+
+std::shared_ptr<CacheEntry> get_entry(const char *path, const char *region, bool want_gt, int &rc) {
+    std::string key = std::string(path) + "\x01" + (region ? region : "") + (want_gt ? "\x01g" : "\x01s");
+    std::shared_ptr<CacheEntry> ce;
+    bool builder = false;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache.find(key);
+        if (it == g_cache.end() && !want_gt) {   // a genotype parse also answers site queries
+            auto it2 = g_cache.find(std::string(path) + "\x01" + (region ? region : "") + "\x01g");
+            if (it2 != g_cache.end()) it = it2;
+        }
+        if (it == g_cache.end()) { ce = std::make_shared<CacheEntry>(); g_cache[key] = ce; builder = true; }
+        else ce = it->second;
+    }
+    if (builder) {
+        int r = build_entry(*ce, path, region, want_gt);
+        {
+            std::lock_guard<std::mutex> lk(ce->mu);
+            ce->rc = r; ce->err = g_err; ce->done = true;
+        }
+        ce->cv.notify_all();
+        if (r != HB_OK) { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache.erase(key); }
+    } else {
+        std::unique_lock<std::mutex> lk(ce->mu);
+        ce->cv.wait(lk, [&] { return ce->done; });
+    }
+    rc = ce->rc;
+    if (rc != HB_OK) g_err = ce->err;
+    return ce;
+}
+
+struct RecOwner {
+    std::shared_ptr<CacheEntry> ce;
+    std::vector<int8_t> gt0, gt1;
+};
+
+void fill_records(hb_records *out, RecOwner *ow) {
+    CacheEntry &ce = *ow->ce;
+    out->n = ce.start.size();
+    out->n_samples = (uint32_t)ce.samples.size();
+    out->start = ce.start.data(); out->stop = ce.stop.data();
+    out->ref = ce.ref.data(); out->alt = ce.alt.data();
+    out->chrom_off = ce.chrom_off.data();
+    out->chrom_pool = ce.chrom_pool.data();
+    out->chrom_pool_len = ce.chrom_pool.size();
+    out->gt0 = ow->gt0.empty() ? nullptr : ow->gt0.data();
+    out->gt1 = ow->gt1.empty() ? nullptr : ow->gt1.data();
+    out->owner_ = ow;
+}
+
+}  // namespace
+
+int hb_load_vcf(const char *in_vcf, const char *sample, const char *chrom, hb_records *out) {
+    if (!in_vcf || !sample || !out) return fail(HB_ERR_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    if (!*sample) return hb_load_vcf_without_sample(in_vcf, chrom, out);
+    int rc;
+    auto ce = get_entry(in_vcf, chrom, true, rc);
+    if (rc != HB_OK) return rc;
+    auto it = std::find(ce->samples.begin(), ce->samples.end(), std::string(sample));
+    if (it == ce->samples.end())
+        return fail(HB_ERR_SAMPLE, "the 1-th sample are not in the VCF.\nparameter samples:" + std::string(sample));
+    uint32_t s = (uint32_t)(it - ce->samples.begin());
+    uint64_t n = ce->start.size();
+    if (n && ce->parse->h_st.n_nogt)
+        return fail(HB_ERR_NOGT, "genotypes not present. make sure you initilized the variant object first\n");
+    if (ce->badgt_err[s]) return fail(HB_ERR_GT, "Couldn't read GT data: value not a number or '.'");
+    if (ce->ploidy_err[s])
+        return fail(HB_ERR_PLOIDY, "ploidy != 2 (reference: assert(var.ploidy() == 2), parse_vcf.cpp:46)");
+    auto *ow = new RecOwner();
+    ow->ce = ce;
+    ow->gt0.resize(n ? n : 1); ow->gt1.resize(n ? n : 1);
+    rc = hb_parse_fetch_sample(ce->parse, s, ow->gt0.data(), ow->gt1.data());
+    if (rc != HB_OK) { delete ow; return rc; }
+    fill_records(out, ow);
+    return HB_OK;
+}
+
+int hb_load_vcf_without_sample(const char *in_vcf, const char *chrom, hb_records *out) {
+    if (!in_vcf || !out) return fail(HB_ERR_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    int rc;
+    auto ce = get_entry(in_vcf, chrom, false, rc);
+    if (rc != HB_OK) return rc;
+    auto *ow = new RecOwner();
+    ow->ce = ce;
+    fill_records(out, ow);
+    out->gt0 = out->gt1 = nullptr;
+    return HB_OK;
+}
+
+void hb_records_free(hb_records *r) {
+    if (!r || !r->owner_) return;
+    delete static_cast<RecOwner *>(r->owner_);
+    memset(r, 0, sizeof *r);
+}
+
+void hb_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.clear();
+}
+
+const char *hb_last_error(void) { return g_err.c_str(); }
+const char *hb_version(void) { return "haplo_b200 0.1 (sm_100a)"; }
+uint64_t hb_kernel_launches(void) { return g_launches.load(); }

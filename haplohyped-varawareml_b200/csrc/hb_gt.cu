@@ -1,0 +1,288 @@
+// hb_gt.cu -- kernel 3: GT-field decode into phased int8 allele planes, sample-major.
+//
+// Replaces BcfRecord::getGenotypes (reference cpp/vcfpp.h:546-588, over htslib's GT branch of
+// vcf_parse_format) plus the int8 narrowing of cpp/parse_vcf.cpp:51-52 -- for ALL samples of a
+// record at once instead of one sample per whole-file pass.
+//
+// Work unit: a 2-D tile of kTV records x kTS samples.  Variant-major text goes in, sample-major
+// bytes come out, so every tile is a transpose:
+//   * the per-record byte range of the tile's sample columns is known from the site kernel
+//     (uniform "\tX|Y" records: arithmetic) or from the tokenizer's column checkpoints;
+//   * uniform segments are staged into shared memory with one TMA bulk copy per record
+//     (cp.async.bulk, mbarrier completion), decoded 4 records x 1 sample per thread with a SWAR
+//     compare, and packed into the transposed tile;
+//   * anything else (GT:GQ:DP columns, multi-digit alleles, malformed text) is decoded by a
+//     warp that streams the segment, ranks its tabs with popc + a warp scan, and parses each field;
+//   * the tile is written out as 16-byte vectors, 128 contiguous bytes per (plane, sample).
+// Output layout = the Blosc2 byte-shuffled layout of the reference's 35-byte records
+// (planes 33 and 34 of every chunk), see DESIGN.md.
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+namespace hb {
+
+constexpr int GT_THREADS = 256;
+constexpr int GT_WARPS = GT_THREADS / 32;
+constexpr int SEG_PITCH = 4 * kTS + 32;   // staged bytes per record (16-byte slop either side)
+constexpr int OUT_PITCH = kTV + 4;        // bytes; 33 words => conflict-free transposed stores
+
+struct GtSmem {
+    alignas(128) uint8_t text[kTV][SEG_PITCH];
+    alignas(16) uint8_t out[2][kTS][OUT_PITCH];
+    uint64_t seg_begin[kTV];
+    uint32_t seg_len[kTV];
+    uint32_t seg_g[kTV];
+    int mode[kTV];              // 0 nothing to decode (zeros), 1 staged fast path, 2 general path
+    alignas(8) uint64_t bar;
+    uint32_t tx_total;
+};
+
+// One sample column starting at p (first byte after the TAB).  Restates htslib's GT parse:
+// '.' -> missing (-9), digits -> allele index (int8-narrowed), '|' or '/' continue.
+// Returns ploidy, or -1 when an allele is neither digits nor '.'.
+__device__ __forceinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t p, int g, int &a0, int &a1) {
+    for (int k = 0; k < g; ++k) {
+        for (;;) {
+            uint8_t c = t[p];
+            if (c == '\t' || c == '\n' || c == '\r') { a0 = -9; a1 = -9; return 0; }
+            ++p;
+            if (c == ':') break;
+        }
+    }
+    int l = 0;
+    a0 = 0; a1 = -128;
+    for (;;) {
+        uint8_t c = t[p];
+        int val;
+        if (c == '.') { ++p; val = -9; }
+        else {
+            uint32_t v = 0; int nd = 0;
+            while (c >= '0' && c <= '9') { v = v * 10u + (uint32_t)(c - '0'); ++nd; c = t[++p]; }
+            if (nd == 0) {
+                if (l == 0 && (c == '\t' || c == '\n' || c == '\r' || c == ':')) { a0 = -9; a1 = -9; return 1; }
+                return -1;
+            }
+            val = (int)(int8_t)(uint8_t)v;
+        }
+        if (l == 0) a0 = val; else if (l == 1) a1 = val;
+        ++l;
+        c = t[p];
+        if (c == '|' || c == '/') { ++p; continue; }
+        break;
+    }
+    return l;
+}
+
+__device__ __forceinline__ int allele_of(uint32_t c, bool &ok) {
+    if (c == '.') return -9;
+    uint32_t d = c - '0';
+    if (d > 9) ok = false;
+    return (int)d;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
+decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ rowinfo, uint64_t n_rows,
+                 uint32_t n_samples, uint32_t n_stiles, const uint64_t *__restrict__ cp, uint32_t ncp,
+                 int8_t *__restrict__ gt0, int8_t *__restrict__ gt1, uint64_t gt_stride,
+                 uint32_t *__restrict__ ploidy_err, uint32_t *__restrict__ badgt_err,
+                 DevStatus *__restrict__ st) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    GtSmem &sm = *reinterpret_cast<GtSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t tile = blockIdx.x;
+    const uint32_t tile_s = (uint32_t)(tile % n_stiles);
+    const uint64_t tile_r = tile / n_stiles;
+    const uint32_t s0 = tile_s * kTS;
+    const uint32_t ns = min((uint32_t)kTS, n_samples - s0);
+    const uint64_t r0 = tile_r * kTV;
+    const uint32_t nr = (uint32_t)min((uint64_t)kTV, n_rows - r0);
+
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+        sm.tx_total = 0;
+    }
+    __syncthreads();
+
+    // ---- phase 0: locate each record's segment; stage uniform ones with TMA
+    if (tid < kTV) {
+        int mode = 0;
+        uint64_t b = 0;
+        uint32_t len = 0, g = 0;
+        if ((uint32_t)tid < nr) {
+            const RowInfo ri = rowinfo[r0 + tid];
+            g = ri.misc & 0xffu;
+            if ((ri.misc & kRowHasSamples) && g != 255u) {
+                if (ri.misc & kRowUniform) {
+                    b = ri.samp_abs + 4ull * s0;
+                    len = 4u * ns;
+                    mode = 1;
+                } else {
+                    const uint64_t *row = cp + (uint64_t)ri.cp_row * ncp;
+                    uint64_t bb = row[tile_s];
+                    uint64_t ee = (tile_s + 1 < n_stiles) ? row[tile_s + 1] : ri.samp_abs + ri.samp_len;
+                    if (bb == kNoCp || ee == kNoCp || ee < bb || ee - bb > 0xffffffffull) {
+                        atomicAdd(&st->n_bad_cols, 1ull);     // too few columns in this record
+                    } else {
+                        b = bb;
+                        len = (uint32_t)(ee - bb);
+                        mode = (len == 4u * ns && g == 0) ? 1 : 2;
+                    }
+                }
+            }
+        }
+        sm.seg_begin[tid] = b;
+        sm.seg_len[tid] = len;
+        sm.seg_g[tid] = g;
+        sm.mode[tid] = mode;
+        if (mode == 1) {
+            uint32_t bytes = (uint32_t)(((b & 15ull) + len + 15ull) & ~15ull);
+            atomicAdd(&sm.tx_total, bytes);
+        }
+    }
+    __syncthreads();
+    const uint32_t tx_total = sm.tx_total;
+    if (tx_total) {
+        if (tid == 0) mbar_expect_tx(&sm.bar, tx_total);
+        if (tid < kTV && sm.mode[tid] == 1) {
+            uint64_t b = sm.seg_begin[tid];
+            uint32_t bytes = (uint32_t)(((b & 15ull) + sm.seg_len[tid] + 15ull) & ~15ull);
+            tma_load_1d(sm.text[tid], text + (b & ~15ull), bytes, &sm.bar);
+        }
+        mbar_wait(&sm.bar, 0);
+    }
+
+    // ---- phase 1: fast path, 4 records x 1 sample per thread, transposed pack
+    {
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(&sm.out[0][0][0]);
+        constexpr int OUT_PITCH_W = OUT_PITCH / 4;
+        for (int item = tid; item < kTS * (kTV / 4); item += GT_THREADS) {
+            const int s = item % kTS, r4 = item / kTS;
+            uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = 4 * r4 + k;
+                if (sm.mode[r] == 1 && (uint32_t)s < ns) {
+                    const uint32_t off = (uint32_t)(sm.seg_begin[r] & 15ull) + 4u * s;
+                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm.text[r]);
+                    const uint32_t w0 = rowp[off >> 2], w1 = rowp[(off >> 2) + 1];
+                    const uint32_t w = __funnelshift_r(w0, w1, (off & 3u) * 8u);
+                    int a0, a1;
+                    if (((w ^ 0x307C3009u) & 0xFEFFFEFFu) == 0) {   // "\t0|0" .. "\t1|1"
+                        a0 = (w >> 8) & 1;
+                        a1 = (w >> 24) & 1;
+                    } else {
+                        bool ok = (w & 0xffu) == '\t';
+                        const uint32_t sep = (w >> 16) & 0xffu;
+                        ok = ok && (sep == '|' || sep == '/');
+                        a0 = allele_of((w >> 8) & 0xffu, ok);
+                        a1 = allele_of(w >> 24, ok);
+                        if (!ok) { sm.mode[r] = 2; a0 = 0; a1 = 0; }   // demote the record to the general path
+                    }
+                    p0 |= (uint32_t)(a0 & 0xff) << (8 * k);
+                    p1 |= (uint32_t)(a1 & 0xff) << (8 * k);
+                }
+            }
+            out32[(0 * kTS + s) * OUT_PITCH_W + r4] = p0;
+            out32[(1 * kTS + s) * OUT_PITCH_W + r4] = p1;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: general path, one warp per record segment
+    for (uint32_t r = warp; r < nr; r += GT_WARPS) {
+        if (sm.mode[r] != 2) continue;
+        const uint64_t b = sm.seg_begin[r], e = b + sm.seg_len[r];
+        const int g = (int)sm.seg_g[r];
+        uint32_t seen = 0;
+        for (uint64_t base = b & ~15ull; base < e; base += 512) {
+            const uint64_t o = base + 16ull * lane;
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (o < e) {
+                uint4 v = *reinterpret_cast<const uint4 *>(text + o);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            }
+            uint32_t m[4], cnt = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                m[q] = eq_mask(w[q], kTab4);
+                const uint64_t wo = o + 4ull * q;
+                if (wo < b || wo + 4 > e) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (wo + k < b || wo + k >= e) m[q] &= ~(0x80u << (8 * k));
+                }
+                cnt += __popc(m[q]);
+            }
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            uint32_t k = seen + inc - cnt;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t mm = m[q];
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (k < ns) {
+                        int a0, a1;
+                        const int pl = decode_field(text, o + 4ull * q + (bit >> 3) + 1, g, a0, a1);
+                        if (pl < 0) { atomicAdd(&st->n_bad_gt, 1ull); atomicAdd(&badgt_err[s0 + k], 1u); a0 = 0; a1 = 0; }
+                        else if (pl != 2) atomicAdd(&ploidy_err[s0 + k], 1u);
+                        sm.out[0][k][r] = (uint8_t)a0;
+                        sm.out[1][k][r] = (uint8_t)a1;
+                    }
+                    ++k;
+                }
+            }
+            seen += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (seen != ns) {
+            if (lane == 0) atomicAdd(&st->n_bad_cols, 1ull);
+            for (uint32_t k = seen + lane; k < ns; k += 32) { sm.out[0][k][r] = 0; sm.out[1][k][r] = 0; }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: 128 contiguous bytes per (plane, sample), 16-byte vector stores
+    {
+        const uint32_t *out32 = reinterpret_cast<const uint32_t *>(&sm.out[0][0][0]);
+        constexpr int OUT_PITCH_W = OUT_PITCH / 4;
+        constexpr int PIECES = kTV / 16;
+        for (int item = tid; item < 2 * kTS * PIECES; item += GT_THREADS) {
+            const int piece = item % PIECES;
+            const int ps = item / PIECES;       // plane * kTS + s
+            const int s = ps % kTS, p = ps / kTS;
+            if ((uint32_t)s >= ns) continue;
+            const uint32_t *src = out32 + ps * OUT_PITCH_W + 4 * piece;
+            uint4 v;
+            v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+            int8_t *dst = (p ? gt1 : gt0) + (uint64_t)(s0 + s) * gt_stride + r0 + 16ull * piece;
+            stg_stream(reinterpret_cast<uint4 *>(dst), v);
+        }
+    }
+}
+
+void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t n_rows, uint32_t n_samples,
+                      const uint64_t *d_cp, uint32_t ncp, int8_t *d_gt0, int8_t *d_gt1, uint64_t gt_stride,
+                      uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st, const Launch &L) {
+    if (!n_rows || !n_samples) return;
+    static bool attr_set = false;
+    size_t smem = sizeof(GtSmem);
+    if (!attr_set) {
+        cudaFuncSetAttribute(decode_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    uint32_t n_stiles = (n_samples + kTS - 1) / kTS;
+    uint64_t n_rtiles = (n_rows + kTV - 1) / kTV;
+    uint64_t tiles = n_rtiles * n_stiles;
+    decode_gt_kernel<<<(unsigned)tiles, GT_THREADS, smem, L.stream>>>(d_text, d_rowinfo, n_rows, n_samples, n_stiles,
+                                                                      d_cp, ncp, d_gt0, d_gt1, gt_stride,
+                                                                      d_ploidy_err, d_badgt_err, d_st);
+    count_launch();
+}
+
+}  // namespace hb

@@ -1,0 +1,131 @@
+// hb_hap.cu -- kernel 5: batched on-the-fly haplotype construction for the dataset.
+//
+// Replaces, for a whole batch in one launch, RandomHaplotypeDataset.encode_haplotypes
+// (reference src/datasets/haplotype_dataset.py:86-110) and encode_sequence / array_to_onehot
+// (src/utils/common_utils.py:84-103), with the documented repairs R1-R3:
+//   R1 both haplotypes start from the index-encoded reference window;
+//   R2 only records with window_start <= start < window_start + len are applied;
+//   R3 one-hot out[i, c] = float(c == idx[i]), columns in encode_spec order.
+// Kept literally: phase == 1 selects the ALT index, anything else the record's REF index
+// (:99-100); duplicate positions -> the last record in file order wins (np.put_along_axis).
+//
+// One CTA builds 1024 window positions of one batch item: index bytes for both haplotypes are
+// composed in shared memory (window gather through a 256-entry LUT, then the item's records in
+// range -- found by binary search in the sorted start column -- scattered on top), and the
+// float32 one-hot rows are streamed out as 16-byte vectors.  HBM-write bound: 2*B*L*C*4 bytes.
+#include "../../include/haplo_b200.h"
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+namespace hb {
+
+constexpr int HP_THREADS = 256;
+constexpr int HP_TILE = 1024;
+
+__device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t *a, uint64_t lo, uint64_t hi, uint32_t key) {
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int CC>   // CC > 0: compile-time class count; 0: runtime
+__global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
+    __shared__ int8_t s_idx[2][HP_TILE];
+    __shared__ int8_t s_lut[256];
+    const int tid = threadIdx.x;
+    const uint32_t b = blockIdx.y;
+    const uint32_t tile0 = blockIdx.x * HP_TILE;
+    const uint32_t C = CC > 0 ? (uint32_t)CC : a.C;
+    const uint32_t L = a.L;
+    const uint32_t tn = min((uint32_t)HP_TILE, L - tile0);       // positions of this tile inside [0, L)
+    const uint32_t len = a.item_len[b];
+    const uint32_t ws = a.item_win_start[b];
+    s_lut[tid] = a.lut[tid];
+    __syncthreads();
+
+    // ---- reference window -> class index (R1); beyond the window: -1 => all-zero row
+    const uint8_t *seq = a.ref_seq + a.item_ref_off[b];
+    for (uint32_t k = tid; k < tn; k += HP_THREADS) {
+        uint32_t p = tile0 + k;
+        int8_t v = -1;
+        if (p < len) v = s_lut[seq[p]];
+        s_idx[0][k] = v;
+        s_idx[1][k] = v;
+    }
+    __syncthreads();
+
+    // ---- records inside this tile (R2), last duplicate wins
+    {
+        const uint64_t lo = a.item_row_lo[b], hi = a.item_row_hi[b];
+        const uint32_t wend = min(len, tile0 + tn);              // exclusive, window-relative
+        if (lo < hi && tile0 < wend) {
+            // genomic range [ws + tile0, ws + wend)
+            const uint64_t g0 = (uint64_t)ws + tile0, g1 = (uint64_t)ws + wend;
+            const uint32_t k0 = g0 > 0xffffffffull ? 0xffffffffu : (uint32_t)g0;
+            const uint64_t rb = lower_bound_u32(a.start, lo, hi, k0);
+            const uint64_t re = g1 > 0xffffffffull ? hi : lower_bound_u32(a.start, rb, hi, (uint32_t)g1);
+            const uint64_t go = a.item_gt_off[b];
+            for (uint64_t r = rb + tid; r < re; r += HP_THREADS) {
+                const uint32_t st = a.start[r];
+                if (r + 1 < hi && a.start[r + 1] == st) continue;   // a later record at the same position wins
+                const uint32_t k = st - ws - tile0;
+                const int8_t ri = s_lut[a.ref[r]], ai = s_lut[a.alt[r]];
+                s_idx[0][k] = a.p1[go + r] == 1 ? ai : ri;
+                s_idx[1][k] = a.p2[go + r] == 1 ? ai : ri;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- one-hot rows (R3), 16-byte stores
+    const uint64_t base_el = ((uint64_t)b * L + tile0) * C;      // first float of this tile
+    const uint32_t n_el = tn * C;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float *out = (h ? a.hap2 : a.hap1) + base_el;
+        const int8_t *idx = s_idx[h];
+        if ((base_el & 3) == 0) {
+            const uint32_t n4 = n_el >> 2;
+            for (uint32_t q = tid; q < n4; q += HP_THREADS) {
+                uint32_t e = 4 * q;
+                uint32_t p = e / C, c = e - p * C;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = (idx[p] == (int)c) ? 1.0f : 0.0f;
+                    if (++c == C) { c = 0; ++p; }
+                }
+                uint4 w;
+                w.x = __float_as_uint(v[0]); w.y = __float_as_uint(v[1]);
+                w.z = __float_as_uint(v[2]); w.w = __float_as_uint(v[3]);
+                stg_stream(reinterpret_cast<uint4 *>(out) + q, w);
+            }
+            for (uint32_t e = (n4 << 2) + tid; e < n_el; e += HP_THREADS) {
+                uint32_t p = e / C, c = e - p * C;
+                out[e] = (idx[p] == (int)c) ? 1.0f : 0.0f;
+            }
+        } else {
+            for (uint32_t e = tid; e < n_el; e += HP_THREADS) {
+                uint32_t p = e / C, c = e - p * C;
+                out[e] = (idx[p] == (int)c) ? 1.0f : 0.0f;
+            }
+        }
+    }
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_encode_haplotypes(const hb_hap_batch *batch) {
+    if (!batch || !batch->B || !batch->L || !batch->C) return HB_OK;
+    dim3 grid((batch->L + HP_TILE - 1) / HP_TILE, batch->B);
+    cudaStream_t st = (cudaStream_t)batch->stream;
+    if (batch->C == 5) hap_kernel<5><<<grid, HP_THREADS, 0, st>>>(*batch);
+    else if (batch->C == 4) hap_kernel<4><<<grid, HP_THREADS, 0, st>>>(*batch);
+    else hap_kernel<0><<<grid, HP_THREADS, 0, st>>>(*batch);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}

@@ -1,0 +1,71 @@
+// hb_internal.h -- structures shared by the kernels and the host side of libhaplo_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+// Tile geometry shared by the tokenizer (checkpoints) and the GT decoder (sample tiles).
+constexpr int kCP = 128;          // one column checkpoint every kCP samples
+constexpr int kTS = 128;          // samples per decode tile (== kCP)
+constexpr int kTV = 128;          // records (rows) per decode tile
+constexpr uint64_t kNoCp = ~0ull; // "no checkpoint written"
+
+// Per kept record, produced by the site kernel, consumed by the GT decoder.
+struct RowInfo {
+    uint64_t samp_abs;   // offset of the TAB that precedes sample 0
+    uint32_t samp_len;   // bytes from samp_abs to end of line (exclusive of '\n' / "\r\n")
+    uint32_t cp_row;     // row of the checkpoint table (general path only)
+    uint32_t misc;       // [7:0] GT index in FORMAT, bit 8 uniform ("\tX|Y" x n_samples), bit 9 has samples
+    uint32_t pad;
+};
+constexpr uint32_t kRowUniform = 1u << 8;
+constexpr uint32_t kRowHasSamples = 1u << 9;
+
+// Device-side counters / results, one per parse handle.
+struct DevStatus {
+    unsigned long long n_lines;        // tokenizer: number of '\n'
+    unsigned long long n_records;      // site kernel: rows kept
+    unsigned long long n_nonuniform;   // kept rows that need the general decode path
+    unsigned long long n_bad_gt;       // alleles neither digits nor '.'
+    unsigned long long n_bad_cols;     // records whose column count != 9 + n_samples (or < 8 fields)
+    unsigned long long n_nogt;         // kept records without a GT key / sample columns
+    unsigned long long n_chrom_runs;
+    unsigned int line_overflow;        // more lines than line_cap
+    unsigned int ticket;               // tile tickets of the site kernel
+};
+
+struct RegionArg {
+    char chrom[240];
+    uint32_t chrom_len;
+    int has_region;
+    long long beg0, end0;
+};
+
+struct Launch {   // filled by the host, one per parse
+    cudaStream_t stream;
+    int sm_count;
+};
+
+// ---- launchers (definitions in the .cu files) ----
+void launch_tokenize(bool with_tabs, const uint8_t *d_text, uint64_t nbytes, uint64_t *d_tile_state,
+                     uint64_t n_tiles, uint64_t *d_line_start, uint64_t line_cap, uint64_t *d_cp, uint32_t ncp,
+                     DevStatus *d_st, const Launch &L);
+uint64_t tokenize_tile_bytes();
+void launch_index_columns(const uint8_t *d_text, const RowInfo *d_rowinfo, const uint32_t *d_nu_rows,
+                          uint64_t n_nu, uint64_t *d_cp, uint32_t ncp, const Launch &L);
+void launch_sites(const uint8_t *d_text, const uint64_t *d_line_start, uint64_t n_lines, uint32_t n_samples,
+                  const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
+                  uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
+                  RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
+                  const Launch &L);
+void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const uint8_t *d_chrom_len,
+                       uint64_t n_rows, uint64_t *d_run_rows, uint64_t max_runs, DevStatus *d_st,
+                       const Launch &L);
+void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t n_rows, uint32_t n_samples,
+                      const uint64_t *d_cp, uint32_t ncp, int8_t *d_gt0, int8_t *d_gt1, uint64_t gt_stride,
+                      uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st, const Launch &L);
+
+void count_launch(uint64_t n = 1);
+
+}  // namespace hb

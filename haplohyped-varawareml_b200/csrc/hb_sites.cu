@@ -1,0 +1,263 @@
+// hb_sites.cu -- kernel 2: CHROM / POS / REF / ALT extraction, the biallelic-SNP predicate,
+// the region filter, and stream compaction of the records that pass.
+//
+// Replaces, per record, what the reference reaches through vcfpp accessors after vcf_parse1:
+//   isSNP   cpp/vcfpp.h:990-1000      CHROM :1076   Start/End :1118-1127   REF :1130   ALT :1142-1151
+// and the loop body of VCFLoader::load_vcf (cpp/parse_vcf.cpp:41-61) up to the genotype read.
+// One thread per line walks the nine fixed columns as a small state machine (a record head is
+// 50-100 bytes; the sample columns -- kilobytes -- are never touched here).  Kept records get a
+// dense row index from a ticketed single-pass decoupled look-back scan, so outputs are written
+// directly in row order (file order), ready for the decoder and for the shuffle stage.
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+namespace hb {
+
+constexpr int ST_THREADS = 256;
+
+struct SiteArgs {
+    const uint8_t *text;
+    const uint64_t *line_start;
+    uint64_t n_lines;
+    uint32_t n_samples;
+    RegionArg rg;
+    int end_is_int, want_gt, cp_by_line;
+    uint32_t *start, *stop;
+    uint8_t *ref, *alt;
+    uint64_t *chrom_abs;
+    uint8_t *chrom_len;
+    RowInfo *rowinfo;
+    uint32_t *nu_rows;
+    uint64_t *tile_state;
+    DevStatus *st;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[ST_THREADS / 32];
+    __shared__ uint64_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&a.st->ticket, 1u);
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t line = tile * ST_THREADS + tid;
+
+    bool keep = false, uniform = false, has_samples = false, malformed = false;
+    uint32_t pos = 0, ref_len = 0, alt_len = 0, n_comma = 0, fmt_len = 0, chrom_len = 0;
+    uint8_t ref0 = 0, alt0 = 0;
+    int g = -1;
+    uint64_t ls = 0, le = 0, samp_abs = 0;
+    long long endval = -1;
+
+    if (line < a.n_lines) {
+        ls = a.line_start[line];
+        le = a.line_start[line + 1] - 1;                       // position of '\n'
+        const uint8_t *t = a.text;
+        if (le > ls && t[le - 1] == '\r') --le;
+        if (le > ls && t[ls] != '#') {
+            int f = 0;
+            bool chrom_ok = true, pos_digits = true;
+            // INFO END= state: 0 matching key, 1 in value, 2 skip to ';'
+            int ist = 0, kpos = 0;
+            long long ev = 0;
+            bool ev_any = false, end_seen = false;   // only the first END= key counts
+            // FORMAT key state
+            int ki = 0, kl = 0;
+            uint8_t k0 = 0, k1 = 0;
+            uint64_t q = ls;
+            for (; q < le; ++q) {
+                uint8_t c = t[q];
+                if (c == '\t') {
+                    if (f == 7 && ist == 1 && ev_any) endval = ev;
+                    if (f == 8) { if (kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki; }
+                    ++f;
+                    if (f == 9) { samp_abs = q; has_samples = true; break; }
+                    continue;
+                }
+                switch (f) {
+                    case 0:
+                        if (a.rg.has_region) {
+                            if (chrom_len >= a.rg.chrom_len || (uint8_t)a.rg.chrom[chrom_len] != c) chrom_ok = false;
+                        }
+                        ++chrom_len;
+                        break;
+                    case 1:
+                        if (pos_digits && c >= '0' && c <= '9') pos = pos * 10u + (uint32_t)(c - '0');
+                        else pos_digits = false;
+                        break;
+                    case 3:
+                        if (ref_len == 0) ref0 = c;
+                        ++ref_len;
+                        break;
+                    case 4:
+                        if (alt_len == 0) alt0 = c;
+                        if (c == ',') ++n_comma;
+                        ++alt_len;
+                        break;
+                    case 7:
+                        if (c == ';') {
+                            if (ist == 1 && ev_any) endval = ev;
+                            ist = 0; kpos = 0; ev = 0; ev_any = false;
+                        } else if (ist == 0) {
+                            const char key[4] = {'E', 'N', 'D', '='};
+                            if (c == (uint8_t)key[kpos]) {
+                                if (++kpos == 4) { ist = end_seen ? 2 : 1; end_seen = true; }
+                            } else ist = 2;
+                        } else if (ist == 1) {
+                            if (c >= '0' && c <= '9') { ev = ev * 10 + (c - '0'); ev_any = true; }
+                            else { ist = 2; ev_any = false; }
+                        }
+                        break;
+                    case 8:
+                        ++fmt_len;
+                        if (c == ':') {
+                            if (kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki;
+                            ++ki; kl = 0;
+                        } else {
+                            if (kl == 0) k0 = c; else if (kl == 1) k1 = c;
+                            ++kl;
+                        }
+                        break;
+                    default: break;
+                }
+            }
+            if (!has_samples) {   // line ended inside field f
+                if (f == 7 && ist == 1 && ev_any) endval = ev;
+                if (f == 8 && kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki;
+            }
+            if (f < 7) malformed = true;
+            else {
+                long long pos0 = (long long)pos - 1;
+                long long rlen = ref_len;
+                if (a.end_is_int && endval > pos0) rlen = endval - pos0;
+                bool in_region = true;
+                if (a.rg.has_region)
+                    in_region = chrom_ok && chrom_len == a.rg.chrom_len && pos0 < a.rg.end0 && pos0 + rlen > a.rg.beg0;
+                bool snp = ref_len <= 1 && n_comma == 0 && alt_len == 1 &&
+                           (alt0 == 'A' || alt0 == 'C' || alt0 == 'G' || alt0 == 'T');
+                keep = in_region && snp;
+                endval = pos0 + rlen;       // reuse: stop
+                if (has_samples)
+                    uniform = fmt_len == 2 && g == 0 && (le - samp_abs) == 4ull * a.n_samples;
+            }
+        }
+    }
+
+    // ---- row index: CTA exclusive scan of keep + ticketed look-back across tiles
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    uint32_t wcount = __popc(bal);
+    if (lane == 0) s_warp[warp] = wcount;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < ST_THREADS / 32; ++w) {
+        uint32_t c = s_warp[w];
+        if (w < warp) before += c;
+        total += c;
+    }
+    if (warp == 0) {
+        uint64_t excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed(&a.tile_state[0], kFlagPre | total);
+        } else {
+            if (lane == 0) st_relaxed(&a.tile_state[tile], kFlagAgg | total);
+            int64_t base = (int64_t)tile - 1;
+            for (;;) {
+                int64_t idx = base - lane;
+                uint64_t w = kFlagPre;
+                if (idx >= 0) { do { w = ld_relaxed(&a.tile_state[idx]); } while ((w >> 62) == 0); }
+                unsigned pre = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                int P = pre ? (__ffs(pre) - 1) : 31;
+                uint64_t v = lane <= P ? (w & kPayload) : 0;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+                excl += __shfl_sync(0xffffffffu, v, 0);
+                if (pre) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed(&a.tile_state[tile], kFlagPre | (excl + total));
+        }
+        if (lane == 0) {
+            s_base = excl;
+            if ((tile + 1) * ST_THREADS >= a.n_lines) a.st->n_records = excl + total;
+        }
+    }
+    __syncthreads();
+    if (malformed) atomicAdd(&a.st->n_bad_cols, 1ull);
+    if (!keep) return;
+    const uint64_t row = s_base + before + __popc(bal & ((1u << lane) - 1u));
+    a.start[row] = (uint32_t)((long long)pos - 1);
+    a.stop[row] = (uint32_t)endval;
+    a.ref[row] = ref0;
+    a.alt[row] = alt0;
+    a.chrom_abs[row] = ls;
+    a.chrom_len[row] = (uint8_t)(chrom_len > 255 ? 255 : chrom_len);
+    RowInfo ri;
+    ri.samp_abs = samp_abs;
+    ri.samp_len = has_samples ? (uint32_t)(le - samp_abs) : 0u;
+    ri.cp_row = 0;
+    ri.pad = 0;
+    uint32_t gi = g < 0 ? 255u : (uint32_t)(g > 254 ? 254 : g);
+    ri.misc = gi | (uniform ? kRowUniform : 0u) | (has_samples ? kRowHasSamples : 0u);
+    if (a.want_gt) {
+        if (!has_samples || g < 0) atomicAdd(&a.st->n_nogt, 1ull);
+        else if (!uniform) {
+            unsigned long long slot = atomicAdd(&a.st->n_nonuniform, 1ull);
+            if (a.cp_by_line) ri.cp_row = (uint32_t)line;
+            else { ri.cp_row = (uint32_t)slot; a.nu_rows[slot] = (uint32_t)row; }
+        }
+    }
+    a.rowinfo[row] = ri;
+}
+
+void launch_sites(const uint8_t *d_text, const uint64_t *d_line_start, uint64_t n_lines, uint32_t n_samples,
+                  const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
+                  uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
+                  RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
+                  const Launch &L) {
+    if (!n_lines) return;
+    uint64_t tiles = (n_lines + ST_THREADS - 1) / ST_THREADS;
+    cudaMemsetAsync(d_tile_state, 0, tiles * sizeof(uint64_t), L.stream);
+    SiteArgs a;
+    a.text = d_text; a.line_start = d_line_start; a.n_lines = n_lines; a.n_samples = n_samples;
+    a.rg = rg; a.end_is_int = end_is_int; a.want_gt = want_gt; a.cp_by_line = cp_by_line ? 1 : 0;
+    a.start = d_start; a.stop = d_stop; a.ref = d_ref; a.alt = d_alt;
+    a.chrom_abs = d_chrom_abs; a.chrom_len = d_chrom_len; a.rowinfo = d_rowinfo; a.nu_rows = d_nu_rows;
+    a.tile_state = d_tile_state; a.st = d_st;
+    sites_kernel<<<(unsigned)tiles, ST_THREADS, 0, L.stream>>>(a);
+    count_launch();
+}
+
+// rows whose CHROM differs from the previous row's start a new run (row 0 always does)
+__global__ void chrom_runs_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ chrom_abs,
+                                  const uint8_t *__restrict__ chrom_len, uint64_t n_rows,
+                                  uint64_t *__restrict__ run_rows, uint64_t max_runs, DevStatus *st) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    bool is_new = r == 0;
+    if (!is_new) {
+        uint32_t la = chrom_len[r], lb = chrom_len[r - 1];
+        if (la != lb) is_new = true;
+        else {
+            const uint8_t *pa = text + chrom_abs[r], *pb = text + chrom_abs[r - 1];
+            for (uint32_t i = 0; i < la; ++i)
+                if (pa[i] != pb[i]) { is_new = true; break; }
+        }
+    }
+    if (is_new) {
+        unsigned long long k = atomicAdd(&st->n_chrom_runs, 1ull);
+        if (k < max_runs) run_rows[k] = r;
+    }
+}
+
+void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const uint8_t *d_chrom_len,
+                       uint64_t n_rows, uint64_t *d_run_rows, uint64_t max_runs, DevStatus *d_st,
+                       const Launch &L) {
+    if (!n_rows) return;
+    uint64_t blocks = (n_rows + 255) / 256;
+    chrom_runs_kernel<<<(unsigned)blocks, 256, 0, L.stream>>>(d_text, d_chrom_abs, d_chrom_len, n_rows, d_run_rows,
+                                                              max_runs, d_st);
+    count_launch();
+}
+
+}  // namespace hb

@@ -1,0 +1,196 @@
+/*
+ * haplo_b200.h -- C ABI of libhaplo_b200.so: the B200-native VCF -> tensor hot path.
+ *
+ * Plain pointers and sizes only (no torch / pybind types).  Every entry point names the
+ * reference interface it replaces (paths relative to the HaploHyped-VarAwareML checkout).
+ * All functions return HB_OK (0) or an HB_ERR_* code; hb_last_error() gives the thread-local
+ * message.  There is NO CPU fallback: every compute entry point needs a CUDA device of
+ * compute capability 10.x and fails with HB_ERR_CUDA otherwise.
+ */
+#ifndef HAPLO_B200_H
+#define HAPLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_IO 1        /* cannot open / read / inflate the input */
+#define HB_ERR_HEADER 2    /* no #CHROM line */
+#define HB_ERR_SAMPLE 3    /* unknown sample (vcfpp.h:369-378 runtime_error) */
+#define HB_ERR_PLOIDY 4    /* GT of the requested sample is not diploid (parse_vcf.cpp:46 assert) */
+#define HB_ERR_GT 5        /* allele neither digits nor '.' (htslib "Couldn't read GT data") */
+#define HB_ERR_FORMAT 6    /* wrong number of columns */
+#define HB_ERR_NOGT 7      /* FORMAT has no GT (vcfpp.h:550-552 "genotypes not present") */
+#define HB_ERR_MEM 8
+#define HB_ERR_CUDA 9      /* no usable device / CUDA failure: the product never falls back to CPU */
+#define HB_ERR_ARG 10
+
+const char *hb_last_error(void);
+const char *hb_version(void);
+/* number of this library's kernels launched by the calling process so far (bench "gpu_launches") */
+uint64_t hb_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A. Reference-facing entry points.  These are what the reference's pybind11 module binds:
+ *      VCFLoader::load_vcf                cpp/parse_vcf.cpp:30-71   (bound at :120-121)
+ *      VCFLoader::load_vcf_without_sample cpp/parse_vcf.cpp:80-113  (bound at :122-123)
+ *    Same argument meaning (path, sample id, region string; "" = whole file), same filter
+ *    (biallelic SNP, vcfpp.h:990-1000), same values (POS-1, POS-1+rlen, REF, ALT, int8 alleles,
+ *    -9 = missing).  Results are columnar; the pybind11 shim turns them into the list of tuples.
+ *    One (file, region) is parsed ONCE on the GPU for all samples and cached, so the reference's
+ *    per-donor call pattern (vcf_to_h5.py:150-152) costs one parse, not n_samples parses.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hb_records {
+    uint64_t n;                 /* records kept */
+    uint32_t n_samples;         /* samples in the file header */
+    const uint32_t *start;      /* [n] POS-1                       (vcfpp.h:1118-1121) */
+    const uint32_t *stop;       /* [n] POS-1+rlen                  (vcfpp.h:1124-1127) */
+    const char *ref;            /* [n] one char per record         (vcfpp.h:1130-1133) */
+    const char *alt;            /* [n] one char per record         (vcfpp.h:1142-1151) */
+    const uint32_t *chrom_off;  /* [n] offset of the NUL-terminated CHROM in chrom_pool (vcfpp.h:1076) */
+    const char *chrom_pool;
+    uint64_t chrom_pool_len;
+    const int8_t *gt0;          /* [n] first allele index or -9; NULL without sample (parse_vcf.cpp:51) */
+    const int8_t *gt1;          /* [n] second allele                                   (parse_vcf.cpp:52) */
+    void *owner_;               /* private */
+} hb_records;
+
+int hb_load_vcf(const char *in_vcf, const char *sample, const char *chrom, hb_records *out);
+int hb_load_vcf_without_sample(const char *in_vcf, const char *chrom, hb_records *out);
+void hb_records_free(hb_records *r);
+void hb_cache_clear(void);      /* drop the per-(file, region) device-resident parse cache */
+
+/* ------------------------------------------------------------------------------------------
+ * B. Text-level entry points: the kernels behind A, on a caller-supplied buffer of decompressed
+ *    VCF *body* text (no header lines).  Replaces the hot loop parse_vcf.cpp:41-62 /
+ *    vcfpp.h:1455-1484 (tokenise), :1076-1151 (site columns), :546-588 (GT decode) for ALL
+ *    samples at once.  Output stays in HBM in the byte-shuffled (planar) layout:
+ *        gt[plane][sample][row]  int8, row stride = gt_stride, plane 0 = phase1, 1 = phase2.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hb_parse hb_parse;
+
+typedef struct hb_parse_opts {
+    uint32_t n_samples;     /* sample columns per record (from the #CHROM line) */
+    const char *region;     /* "" / NULL, "chr22" or "chr22:beg-end" (tabix syntax, vcfpp.h:1424-1451) */
+    int end_is_int;         /* header declares INFO/END as Integer: END overrides rlen */
+    int want_gt;            /* 0: sites only (load_vcf_without_sample) */
+    int device;             /* CUDA device ordinal */
+    int tokenizer;          /* 0 auto, 1 newline-only (GT-only text), 2 newline+tab checkpoints */
+    void *stream;           /* cudaStream_t or NULL */
+} hb_parse_opts;
+
+typedef struct hb_parse_info {
+    uint64_t text_bytes, n_lines, n_records;
+    uint32_t n_samples;
+    uint64_t gt_stride;             /* bytes between consecutive samples in a plane */
+    const int8_t *d_gt[2];          /* device: plane base pointers */
+    const uint32_t *d_start, *d_stop;
+    const uint8_t *d_ref, *d_alt;
+    uint64_t n_nonuniform;          /* records that took the general (tab-scan) decode path */
+    uint64_t n_bad_gt, n_bad_cols;  /* malformed alleles / column-count mismatches */
+    uint64_t n_nogt;                /* kept records without a GT key or without sample columns */
+    int tokenizer_used;             /* 1 newline-only, 2 newline + tab checkpoints */
+    float ms_tokenize, ms_sites, ms_decode;   /* CUDA-event kernel times of the last parse */
+} hb_parse_info;
+
+/* text on the HOST (pageable or pinned): H2D copy + kernels.  body must end with '\n'. */
+int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
+/* text already in HBM.  d_text must be 16-byte aligned with >= 64 readable bytes of slack after nbytes. */
+int hb_parse_device_text(const uint8_t *d_text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
+/* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */
+int hb_parse_rerun(hb_parse *p);
+int hb_parse_get_info(const hb_parse *p, hb_parse_info *info);
+/* host copies.  Any pointer may be NULL.  chrom names: see hb_parse_chrom_runs. */
+int hb_parse_fetch_sites(hb_parse *p, uint32_t *start, uint32_t *stop, char *ref, char *alt);
+int hb_parse_fetch_sample(hb_parse *p, uint32_t sample_index, int8_t *gt0, int8_t *gt1);
+int hb_parse_fetch_matrix(hb_parse *p, int8_t *gt0, int8_t *gt1); /* [n_samples][n_records] each */
+/* per-sample counts [n_samples]: records whose GT was not diploid (the reference aborts there,
+ * parse_vcf.cpp:46) and records whose GT had an unreadable allele (htslib "Couldn't read GT data") */
+int hb_parse_fetch_sample_errors(hb_parse *p, uint32_t *ploidy, uint32_t *badgt);
+/* CHROM runs: rows [row_begin[i], row_begin[i+1]) share names[i]; names are written NUL-separated */
+int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint64_t max_runs,
+                        char *names, uint64_t names_cap, uint64_t *names_len);
+void hb_parse_free(hb_parse *p);
+
+/* ------------------------------------------------------------------------------------------
+ * C. Storage: Blosc2 byte-shuffle (typesize 35) + LZ4 block encoder + Blosc2 chunk / cframe
+ *    framing, one frame per (sample, HDF5 chunk) -- what h5py + hdf5plugin produce for
+ *    create_dataset('snp_data', compression=32001, compression_opts=(2,2,0,0,5,1,2), chunks=True)
+ *    (src/haplohyped/vcf_to_h5.py:119-135).  Frames stay in HBM until fetched.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hb_frames hb_frames;
+
+typedef struct hb_frames_info {
+    uint64_t n_records, n_chunks, chunk_records;
+    uint32_t n_samples;
+    uint64_t total_bytes;           /* all frames of all samples */
+    uint64_t raw_bytes;             /* 35 * n_records * n_samples */
+    float ms_site, ms_gt;           /* kernel times */
+} hb_frames_info;
+
+/* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items.
+ * chrom5: the 5 bytes stored in the S5 field for every record (single-CHROM parses). */
+int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out);
+int hb_frames_get_info(const hb_frames *f, hb_frames_info *info);
+/* sizes[n_chunks] of one sample's frames; then the frames themselves, concatenated */
+int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes, uint8_t *buf, uint64_t cap,
+                           uint64_t *total);
+void hb_frames_free(hb_frames *f);
+uint64_t hb_guess_chunk_records(uint64_t n_records);   /* h5py guess_chunk restated for 35-byte items */
+
+/* ------------------------------------------------------------------------------------------
+ * D. Dataset: batched on-the-fly haplotype construction, replacing
+ *    RandomHaplotypeDataset.encode_haplotypes + encode_sequence
+ *    (src/datasets/haplotype_dataset.py:86-110, src/utils/common_utils.py:84-103).
+ *    All pointers are DEVICE pointers.  For batch item b:
+ *      window  = ref_seq[item_ref_off[b] + (0 .. item_len[b]))   ASCII bases (any case)
+ *      records = rows [item_row_lo[b], item_row_hi[b]) of (start, ref, alt) -- sorted by start --
+ *                with phases p1/p2 read at item_gt_off[b] + row
+ *      out     = hap1/hap2 [B][L][C] float32 one-hot; positions >= item_len[b] are all-zero rows
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hb_hap_batch {
+    uint32_t B, L, C;
+    const uint8_t *ref_seq;          /* concatenated reference bases */
+    const uint64_t *item_ref_off;    /* [B] */
+    const uint32_t *item_len;        /* [B] window length (<= L) */
+    const uint32_t *item_win_start;  /* [B] genomic coordinate of window position 0 */
+    const uint32_t *start;           /* record columns (device) */
+    const uint8_t *ref, *alt;
+    const uint64_t *item_row_lo, *item_row_hi;  /* [B] record range of the item's (donor, chrom) */
+    const int8_t *p1, *p2;           /* phase planes */
+    const uint64_t *item_gt_off;     /* [B] offset added to the row index when reading p1/p2 */
+    const int8_t *lut;               /* [256] base byte -> class index (encode_spec order) */
+    float *hap1, *hap2;              /* [B][L][C] */
+    void *stream;
+} hb_hap_batch;
+
+int hb_encode_haplotypes(const hb_hap_batch *batch);
+
+/* ------------------------------------------------------------------------------------------
+ * E. Synthetic input (bench / tests): seeded, counter-based, identical bytes from the CUDA
+ *    generator and from hb_synth_host.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hb_synth_spec {
+    uint64_t n_variants;
+    uint32_t n_samples;
+    uint64_t seed;
+    uint32_t first_pos, pos_step;   /* POS_i = first_pos + i*pos_step + hash(i) % pos_step */
+    uint32_t mix;                   /* 0: config 2/3 (biallelic SNP, a|b); 1: config 4 (multiallelic,
+                                       indel, a/b, missing) */
+    char chrom[16];
+} hb_synth_spec;
+
+uint64_t hb_synth_body_bytes(const hb_synth_spec *s);
+int hb_synth_header(const hb_synth_spec *s, char *buf, uint64_t cap, uint64_t *len);
+int hb_synth_device(const hb_synth_spec *s, uint8_t *d_text, uint64_t cap, int device, void *stream);
+int hb_synth_host(const hb_synth_spec *s, uint64_t first_variant, uint64_t n, uint8_t *buf, uint64_t cap,
+                  uint64_t *len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
