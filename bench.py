@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- genotype calls/sec of the VCF -> tensor hot path on B200.
+
+A "step" = one pass of tokenize -> site extraction -> GT decode (kernels 1-3, output in the
+byte-shuffled planar layout) over one synthetic VCF body resident in HBM.  N=1 workload:
+BASELINE.json configs[1] (synthetic chr22-like, 1.1M biallelic variants x 2504 phased samples,
+~11.1 GB of text).  N>1: every rank parses its own chromosome-sized shard of that shape (the
+path shards by chromosome / BGZF range with no collective on the data path); a 6-int64
+all_gather of per-shard index metadata is the only exchange.
+
+Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]; rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NOMINAL_HBM_GBS = 7700.0
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(text_with_header: bytes, sample_names, n_variants_sample: int, threads: int, passes_per_thread: int = 1):
+    """The reference's driving pattern (vcf_to_h5.py:150-152,191-192): one whole-text load_vcf pass per
+    donor, `threads` donors in parallel.  Runs the C oracle (kind "port": the reference parser needs
+    htslib and cannot be built here).  Returns genotype calls/s = donor passes * variants / wall."""
+    import oracle
+    oracle.lib()
+    donors = [sample_names[(k * 7919) % len(sample_names)] for k in range(threads * passes_per_thread)]
+    done = []
+
+    def work(k):
+        for j in range(passes_per_thread):
+            r = oracle.parse_text(text_with_header, donors[k * passes_per_thread + j], "")
+            done.append(r["n"])
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    calls = sum(done)
+    return calls / dt, dt, len(donors)
+
+
+def run_reference(args):
+    """--impl reference: the reference path's CPU implementation (oracle port) on the host cores, on a
+    bounded sample of the same workload.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from haplohyped_varawareml_b200 import capi
+    cores = os.cpu_count() or 1
+    nv = args.cpu_sample_variants
+    spec = capi.synth_spec(nv, args.samples, seed=args.seed)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    names = capi.synth_sample_names(spec)
+    for _ in range(args.warmup):
+        cpu_baseline(text, names, nv, cores)
+    t_tot, calls_tot = 0.0, 0.0
+    for _ in range(args.steps):
+        v, dt, nd = cpu_baseline(text, names, nv, cores)
+        t_tot += dt
+        calls_tot += v * dt
+    value = calls_tot / t_tot
+    sample = (f"first {nv} variants x {args.samples} samples of the workload text ({len(text) / 1e6:.0f} MB); per step "
+              f"{cores} donors parsed in parallel, one whole-text load_vcf pass per donor (reference driving pattern)")
+    line = {"impl": "reference", "metric": "genotype calls/sec", "value": value, "unit": "calls/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "calls/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "calls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle C port of parse_vcf.cpp:30-71 semantics; the reference binary needs htslib (absent)"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"synthetic chr22-like VCF body: {args.variants} biallelic SNPs x {args.samples} phased samples, "
+                        f"FORMAT=GT, seed {args.seed} (BASELINE.json configs[1])",
+            "variants": args.variants, "samples": args.samples,
+            "l2": "inputs (GBs of text) are far larger than the 126 MB L2; no flush needed",
+            "per_rank": "each rank parses its own shard of this shape (seed + rank)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--variants", type=int, default=1_100_000)
+    ap.add_argument("--samples", type=int, default=2504)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-sample-variants", type=int, default=60000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from haplohyped_varawareml_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    V, S = args.variants, args.samples
+    spec = capi.synth_spec(V, S, seed=args.seed + rank, chrom="chr22")
+    T = int(capi.lib().hb_synth_body_bytes(spec))
+    text = torch.empty(T + 256, dtype=torch.uint8, device=dev)
+    text[T:].zero_()
+    capi.check(capi.lib().hb_synth_device(spec, text.data_ptr(), T, local, None))
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    meta = torch.zeros(6, dtype=torch.int64, device=dev)
+    gathered = [torch.zeros(6, dtype=torch.int64, device=dev) for _ in range(world)]
+
+    def step(p):
+        p.rerun()
+        if world > 1:            # the path's only exchange: per-shard index metadata
+            i = p.info
+            meta[0], meta[1], meta[2] = int(i.n_records), int(i.n_lines), int(i.text_bytes)
+            dist.all_gather(gathered, meta)
+
+    # first parse allocates; it is warm-up step 1
+    p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr22", device=local, stream=stream)
+    for _ in range(args.warmup - 1):
+        step(p)
+    info = p.info
+    Vk = int(info.n_records)
+
+    barrier()
+    launches0 = capi.kernel_launches()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tok, sit, dec = [], [], []
+    ev0.record()
+    for _ in range(args.steps):
+        step(p)
+        i = p.info
+        tok.append(i.ms_tokenize); sit.append(i.ms_sites); dec.append(i.ms_decode)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    launches = capi.kernel_launches() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    calls_total = float(V) * S * world
+    value = calls_total / (ms / 1e3 / args.steps)
+
+    # ---- parity spot check of what was just measured (oracle as the checker, small sample)
+    parity = None
+    if rank == 0:
+        import oracle
+        nchk = 64
+        head = capi.synth_header(spec) + capi.synth_host(spec, 0, nchk)
+        ora = oracle.parse_text(head, "*", "chr22")
+        start, stop, ref, alt = p.sites()
+        ok = np.array_equal(start[:ora["n"]], ora["start"])
+        for s in (0, S // 2, S - 1):
+            g0, g1 = p.sample(s)
+            ok = ok and np.array_equal(g0[:ora["n"]], ora["gt0"][s]) and np.array_equal(g1[:ora["n"]], ora["gt1"][s])
+        parity = bool(ok)
+
+    # ---- e2e: host (pinned) text -> C ABI -> genotype matrix back in host memory
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(T, dtype=torch.uint8).pin_memory()
+        host.copy_(text[:T])
+        out0 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
+        out1 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
+        sites = [np.empty(Vk, np.uint32), np.empty(Vk, np.uint32), np.empty(Vk, "S1"), np.empty(Vk, "S1")]
+
+        def e2e_step():
+            q = capi.Parse.from_host(host.data_ptr(), S, region="chr22", device=local, stream=stream, nbytes=T)
+            capi.check(capi.lib().hb_parse_fetch_matrix(q._h, out0.data_ptr(), out1.data_ptr()))
+            capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.ctypes.data for a in sites]))
+            q.close()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T,
+               "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk, "steps": args.e2e_steps,
+               "api": "hb_parse_host_text + hb_parse_fetch_matrix + hb_parse_fetch_sites (pinned host buffers)"}
+        del host, out0, out1
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        med = lambda a: float(sorted(a)[len(a) // 2])
+        alg_tok = T
+        alg_dec = 4.0 * Vk * S + 2.0 * Vk * S
+        alg_all = T + 2.0 * Vk * S + 33.0 * Vk
+        step_s = ms / 1e3 / args.steps
+        dec_gbs = alg_dec / (med(dec) / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "decode_gt_kernel", "achieved": dec_gbs, "peak": peak, "unit": "GB/s",
+                "frac": dec_gbs / peak, "traffic": None, "peak_source": peak_src, "nominal_peak": NOMINAL_HBM_GBS,
+                "algorithmic_bytes_per_launch": alg_dec, "ms_per_launch": med(dec),
+                "path": {"algorithmic_bytes": alg_all, "gbs": alg_all / step_s / 1e9, "frac": alg_all / step_s / 1e9 / peak,
+                         "definition": "T + 2*V'*S + 33*V' per step (SURVEY.md 8d), whole step incl. host syncs"},
+                "stages": {"tokenize": {"ms": med(tok), "gbs": alg_tok / (med(tok) / 1e3) / 1e9, "bytes": alg_tok},
+                           "sites": {"ms": med(sit)},
+                           "decode_gt": {"ms": med(dec), "gbs": dec_gbs, "bytes": alg_dec}}}
+        cpu = None
+        if not args.no_cpu:
+            nv = args.cpu_sample_variants
+            cs = capi.synth_spec(nv, S, seed=args.seed)
+            ctext = capi.synth_header(cs) + capi.synth_host(cs)
+            cores = os.cpu_count() or 1
+            v, dt, nd = cpu_baseline(ctext, capi.synth_sample_names(cs), nv, cores)
+            cpu = {"value": v, "unit": "calls/s", "cores": cores, "kind": "port",
+                   "sample": f"first {nv} variants x {S} samples ({len(ctext) / 1e6:.0f} MB); {nd} donors in parallel, one "
+                             f"whole-text load_vcf pass per donor (reference driving pattern); {dt:.1f} s"}
+        line = {"metric": "genotype calls/sec", "value": value, "unit": "calls/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+                "variants_per_s": float(V) * world / step_s, "records_kept": Vk, "text_bytes_per_rank": T,
+                "tokenizer": int(info.tokenizer_used), "parity_spot_check": parity,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    p.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,8 +110,8 @@ def test_crlf_info_end_and_regions(capi):
     text, samples = synth.random_vcf(500, 40, seed=10, fmt="GT", kinds="mixed", info_end=True)
     _check_matrix(capi, text, len(samples), "chr22", end_is_int=True)
     _check_matrix(capi, text, len(samples), "chr22:10020000-10060000", end_is_int=True)
-    _check_matrix(capi, text, len(samples), "chr22_KI270731v1_random")
-    p, info = _check_matrix(capi, text, len(samples), "chrNope")
+    _check_matrix(capi, text, len(samples), "chr22_KI270731v1_random", end_is_int=True)
+    p, info = _check_matrix(capi, text, len(samples), "chrNope", end_is_int=True)
     assert info.n_records == 0
 
 
