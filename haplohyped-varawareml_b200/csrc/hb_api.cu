@@ -103,8 +103,14 @@ struct hb_parse {
     bool with_tabs = false;
     uint32_t ncp = 0;
 
-    uint64_t *d_tile_state = nullptr; uint64_t tile_cap = 0;
-    uint64_t *d_line_start = nullptr; uint64_t line_cap = 0;
+    uint64_t *d_nl_after = nullptr; uint64_t nl_after_cap = 0;
+    uint32_t stage_cap = 0, n_cta = 0;
+    uint64_t tiles_per_cta = 0;
+    bool probed = false;
+    uint64_t n_lines = 0;
+    uint64_t first_line_len = 0;
+    CtaTok *d_cta = nullptr;
+    uint64_t *d_cbase = nullptr;
     uint64_t *d_cp = nullptr; uint64_t cp_rows = 0;
     DevStatus *d_st = nullptr;
     DevStatus h_st;
@@ -132,7 +138,7 @@ static void free_dev(void *p) { if (p) cudaFree(p); }
 void hb_parse_free(hb_parse *p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    free_dev(p->d_text_owned); free_dev(p->d_tile_state); free_dev(p->d_line_start); free_dev(p->d_cp);
+    free_dev(p->d_text_owned); free_dev(p->d_nl_after); free_dev(p->d_cta); free_dev(p->d_cbase); free_dev(p->d_cp);
     free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
     free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
     free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_ploidy);
@@ -181,7 +187,7 @@ static int run_parse(hb_parse *p) {
     if (p->nbytes == 0) return HB_OK;
 
     // ---- tokenizer mode + capacity estimate from the first record
-    if (p->line_cap == 0) {
+    if (!p->probed) {
         uint8_t head[65536];
         size_t hn = (size_t)std::min<uint64_t>(sizeof head, p->nbytes);
         CU(cudaMemcpyAsync(head, p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
@@ -190,31 +196,48 @@ static int run_parse(hb_parse *p) {
         probe_head(head, hn, gt_only, l0);
         p->with_tabs = p->tokenizer == 2 || (p->tokenizer == 0 && !gt_only);
         if (!p->want_gt) p->with_tabs = false;
-        uint64_t est = l0 ? p->nbytes / l0 : p->nbytes / hn;
-        p->line_cap = est + est / 4 + 1024;
+        p->first_line_len = l0 ? l0 : hn;
+        p->probed = true;
+        // one contiguous range of tiles per persistent CTA, 2 CTAs per SM
+        uint64_t want = std::min<uint64_t>((uint64_t)p->sm_count * 2, n_tiles);
+        if (want > 1024) want = 1024;
+        p->tiles_per_cta = (n_tiles + want - 1) / want;
+        p->n_cta = (uint32_t)((n_tiles + p->tiles_per_cta - 1) / p->tiles_per_cta);
+        uint64_t est = p->tiles_per_cta * tile / p->first_line_len;
+        p->stage_cap = (uint32_t)std::min<uint64_t>(est + est / 2 + 64, 0x7fffffffull);
+        TRY(dev_alloc(&p->d_cta, p->n_cta));
+        TRY(dev_alloc(&p->d_cbase, p->n_cta + 1));
     }
+    std::vector<CtaTok> h_cta(p->n_cta);
+    std::vector<uint64_t> h_base(p->n_cta + 1);
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (!p->d_line_start) TRY(dev_alloc(&p->d_line_start, p->line_cap));
-        if (p->tile_cap < n_tiles) { TRY(dev_alloc(&p->d_tile_state, n_tiles)); p->tile_cap = n_tiles; }
+        uint64_t need = (uint64_t)p->n_cta * p->stage_cap;
+        if (p->nl_after_cap < need) { TRY(dev_alloc(&p->d_nl_after, need)); p->nl_after_cap = need; }
         if (p->with_tabs) {
-            if (p->cp_rows < p->line_cap) { TRY(dev_alloc(&p->d_cp, p->line_cap * p->ncp)); p->cp_rows = p->line_cap; }
+            if (p->cp_rows < need) { TRY(dev_alloc(&p->d_cp, need * p->ncp)); p->cp_rows = need; }
             CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
         }
         CU(cudaEventRecord(p->ev[0], p->stream));
-        launch_tokenize(p->with_tabs, p->d_text, p->nbytes, p->d_tile_state, n_tiles, p->d_line_start, p->line_cap,
-                        p->d_cp, p->ncp, p->d_st, L);
+        launch_tokenize(p->with_tabs, p->d_text, p->nbytes, p->n_cta, p->tiles_per_cta, p->d_nl_after, p->stage_cap,
+                        p->d_cp, p->ncp, p->d_cta, L);
         CU(cudaEventRecord(p->ev[1], p->stream));
-        CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(h_cta.data(), p->d_cta, p->n_cta * sizeof(CtaTok), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         CU(cudaGetLastError());
-        if (!p->h_st.line_overflow) break;
+        uint32_t mx = 0;
+        h_base[0] = 0;
+        for (uint32_t c = 0; c < p->n_cta; ++c) {
+            mx = std::max(mx, h_cta[c].n_newlines);
+            h_base[c + 1] = h_base[c] + h_cta[c].n_newlines;
+        }
+        if ((uint64_t)mx + 1 <= p->stage_cap) break;
         if (attempt == 1) return fail(HB_ERR_MEM, "line index overflow");
-        p->line_cap = p->h_st.n_lines + 2;     // exact count is known even when the index overflowed
-        free_dev(p->d_line_start); p->d_line_start = nullptr;
-        free_dev(p->d_cp); p->d_cp = nullptr; p->cp_rows = 0;
-        CU(cudaMemsetAsync(p->d_st, 0, sizeof(DevStatus), p->stream));
+        p->stage_cap = mx + 2;                 // exact counts are known even when the index overflowed
     }
-    const uint64_t n_lines = p->h_st.n_lines;
+    CU(cudaMemcpyAsync(p->d_cbase, h_base.data(), (p->n_cta + 1) * 8ull, cudaMemcpyHostToDevice, p->stream));
+    const uint64_t n_lines = h_base[p->n_cta];
+    p->n_lines = n_lines;
+    LineIndex li{p->d_nl_after, p->d_cbase, p->n_cta, p->stage_cap};
 
     // ---- sites
     if (p->row_cap < n_lines || !p->d_start) {
@@ -232,7 +255,7 @@ static int run_parse(hb_parse *p) {
     }
     CU(cudaMemsetAsync(p->d_ploidy, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
     CU(cudaMemsetAsync(p->d_badgt, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
-    launch_sites(p->d_text, p->d_line_start, n_lines, p->n_samples, p->rg, p->end_is_int, p->want_gt, p->with_tabs,
+    launch_sites(p->d_text, li, n_lines, p->n_samples, p->rg, p->end_is_int, p->want_gt, p->with_tabs,
                  p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_rowinfo,
                  p->d_nu_rows, p->d_sites_state, p->d_st, L);
     CU(cudaEventRecord(p->ev[2], p->stream));
@@ -346,7 +369,7 @@ int hb_parse_get_info(const hb_parse *p, hb_parse_info *info) {
     if (!p || !info) return fail(HB_ERR_ARG, "null argument");
     memset(info, 0, sizeof *info);
     info->text_bytes = p->nbytes;
-    info->n_lines = p->h_st.n_lines;
+    info->n_lines = p->n_lines;
     info->n_records = p->h_st.n_records;
     info->n_samples = p->n_samples;
     info->gt_stride = p->gt_stride;

@@ -9,11 +9,12 @@
 //   * the per-record byte range of the tile's sample columns is known from the site kernel
 //     (uniform "\tX|Y" records: arithmetic) or from the tokenizer's column checkpoints;
 //   * uniform segments are staged into shared memory with one TMA bulk copy per record
-//     (cp.async.bulk, mbarrier completion), decoded 4 records x 1 sample per thread with a SWAR
-//     compare, and packed into the transposed tile;
+//     (cp.async.bulk, mbarrier completion); each thread then decodes 1 sample x 16 records with
+//     a SWAR compare per call and packs the 16 alleles of each plane into one 16-byte
+//     shared-memory store of the transposed tile;
 //   * anything else (GT:GQ:DP columns, multi-digit alleles, malformed text) is decoded by a
 //     warp that streams the segment, ranks its tabs with popc + a warp scan, and parses each field;
-//   * the tile is written out as 16-byte vectors, 128 contiguous bytes per (plane, sample).
+//   * the tile is written out as 16-byte vectors, kTV contiguous bytes per (plane, sample).
 // Output layout = the Blosc2 byte-shuffled layout of the reference's 35-byte records
 // (planes 33 and 34 of every chunk), see DESIGN.md.
 #include "hb_common.cuh"
@@ -23,24 +24,27 @@ namespace hb {
 
 constexpr int GT_THREADS = 256;
 constexpr int GT_WARPS = GT_THREADS / 32;
-constexpr int SEG_PITCH = 4 * kTS + 32;   // staged bytes per record (16-byte slop either side)
-constexpr int OUT_PITCH = kTV + 4;        // bytes; 33 words => conflict-free transposed stores
+constexpr int SEG_PITCH = 4 * kTS + 16;   // staged bytes per record: 4*kTS + up to 15 bytes of misalignment
+constexpr int OUT_PITCH = kTV + 16;       // bytes; (kTV+16)/16 odd => conflict-free 16-byte transposed stores
+static_assert(kTV % 16 == 0 && ((OUT_PITCH / 16) & 1) == 1, "tile geometry");
 
 struct GtSmem {
     alignas(128) uint8_t text[kTV][SEG_PITCH];
     alignas(16) uint8_t out[2][kTS][OUT_PITCH];
+    alignas(16) uint32_t meta[kTV];       // fast rows: byte offset of sample 0's TAB inside text[r]; else 0xffffffff
     uint64_t seg_begin[kTV];
     uint32_t seg_len[kTV];
     uint32_t seg_g[kTV];
-    int mode[kTV];              // 0 nothing to decode (zeros), 1 staged fast path, 2 general path
+    int mode[kTV];                        // 0 nothing to decode (zeros), 1 staged fast path, 2 general path
     alignas(8) uint64_t bar;
     uint32_t tx_total;
 };
+constexpr uint32_t kMetaSlow = 0xffffffffu;
 
 // One sample column starting at p (first byte after the TAB).  Restates htslib's GT parse:
 // '.' -> missing (-9), digits -> allele index (int8-narrowed), '|' or '/' continue.
 // Returns ploidy, or -1 when an allele is neither digits nor '.'.
-__device__ __forceinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t p, int g, int &a0, int &a1) {
+__device__ __noinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t p, int g, int &a0, int &a1) {
     for (int k = 0; k < g; ++k) {
         for (;;) {
             uint8_t c = t[p];
@@ -73,14 +77,18 @@ __device__ __forceinline__ int decode_field(const uint8_t *__restrict__ t, uint6
     return l;
 }
 
-__device__ __forceinline__ int allele_of(uint32_t c, bool &ok) {
-    if (c == '.') return -9;
-    uint32_t d = c - '0';
-    if (d > 9) ok = false;
-    return (int)d;
+// "\tXsY" with X,Y in [0-9.] and s in [|/] that is not the common "\t[01]|[01]".
+// Returns (a0 & 0xff) << 8 | (a1 & 0xff) << 24, or 0xffffffff when the group is not of that shape.
+__device__ __noinline__ uint32_t decode_group_slow(uint32_t w) {
+    const uint32_t sep = (w >> 16) & 0xffu, x = (w >> 8) & 0xffu, y = w >> 24;
+    if ((w & 0xffu) != '\t' || !(sep == '|' || sep == '/')) return 0xffffffffu;
+    uint32_t a0, a1;
+    if (x == '.') a0 = (uint32_t)(-9) & 0xffu; else { a0 = x - '0'; if (a0 > 9) return 0xffffffffu; }
+    if (y == '.') a1 = (uint32_t)(-9) & 0xffu; else { a1 = y - '0'; if (a1 > 9) return 0xffffffffu; }
+    return (a0 << 8) | (a1 << 24);
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 2)
+__global__ void __launch_bounds__(GT_THREADS, 4)
 decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ rowinfo, uint64_t n_rows,
                  uint32_t n_samples, uint32_t n_stiles, const uint64_t *__restrict__ cp, uint32_t ncp,
                  int8_t *__restrict__ gt0, int8_t *__restrict__ gt1, uint64_t gt_stride,
@@ -135,6 +143,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         sm.seg_len[tid] = len;
         sm.seg_g[tid] = g;
         sm.mode[tid] = mode;
+        sm.meta[tid] = mode == 1 ? (uint32_t)(b & 15ull) : kMetaSlow;
         if (mode == 1) {
             uint32_t bytes = (uint32_t)(((b & 15ull) + len + 15ull) & ~15ull);
             atomicAdd(&sm.tx_total, bytes);
@@ -152,40 +161,37 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         mbar_wait(&sm.bar, 0);
     }
 
-    // ---- phase 1: fast path, 4 records x 1 sample per thread, transposed pack
-    {
-        uint32_t *out32 = reinterpret_cast<uint32_t *>(&sm.out[0][0][0]);
-        constexpr int OUT_PITCH_W = OUT_PITCH / 4;
-        for (int item = tid; item < kTS * (kTV / 4); item += GT_THREADS) {
-            const int s = item % kTS, r4 = item / kTS;
-            uint32_t p0 = 0, p1 = 0;
+    // ---- phase 1: fast path.  One thread = 1 sample x 16 records; lanes run along samples, so the
+    //      two 4-byte loads per call and the 16-byte transposed stores are bank-conflict free.
+    for (int item = tid; item < kTS * (kTV / 16); item += GT_THREADS) {
+        const int s = item % kTS, rg = item / kTS;
+        uint32_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        if ((uint32_t)s < ns) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int r = 4 * r4 + k;
-                if (sm.mode[r] == 1 && (uint32_t)s < ns) {
-                    const uint32_t off = (uint32_t)(sm.seg_begin[r] & 15ull) + 4u * s;
-                    const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm.text[r]);
-                    const uint32_t w0 = rowp[off >> 2], w1 = rowp[(off >> 2) + 1];
-                    const uint32_t w = __funnelshift_r(w0, w1, (off & 3u) * 8u);
-                    int a0, a1;
-                    if (((w ^ 0x307C3009u) & 0xFEFFFEFFu) == 0) {   // "\t0|0" .. "\t1|1"
-                        a0 = (w >> 8) & 1;
-                        a1 = (w >> 24) & 1;
-                    } else {
-                        bool ok = (w & 0xffu) == '\t';
-                        const uint32_t sep = (w >> 16) & 0xffu;
-                        ok = ok && (sep == '|' || sep == '/');
-                        a0 = allele_of((w >> 8) & 0xffu, ok);
-                        a1 = allele_of(w >> 24, ok);
-                        if (!ok) { sm.mode[r] = 2; a0 = 0; a1 = 0; }   // demote the record to the general path
+            for (int q = 0; q < 4; ++q) {
+                const uint4 m4 = *reinterpret_cast<const uint4 *>(&sm.meta[16 * rg + 4 * q]);
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = 16 * rg + 4 * q + k;
+                    if (mm[k] != kMetaSlow) {                 // warp-uniform
+                        const uint32_t off = mm[k] + 4u * s;
+                        const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm.text[r]) + (off >> 2);
+                        const uint32_t w = __funnelshift_r(rowp[0], rowp[1], (off & 3u) * 8u);
+                        uint32_t x = w ^ 0x307C3009u;         // "\t0|0": leaves the two allele bits
+                        if (x & 0xFEFFFEFFu) {
+                            x = decode_group_slow(w);
+                            if (x == 0xffffffffu) { sm.mode[r] = 2; x = 0; }   // demote the record to the general path
+                        }
+                        // byte k of acc0 <- byte 1 of x, byte k of acc1 <- byte 3 of x
+                        acc0[q] = __byte_perm(acc0[q], x, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
+                        acc1[q] = __byte_perm(acc1[q], x, k == 0 ? 0x3217 : k == 1 ? 0x3270 : k == 2 ? 0x3710 : 0x7210);
                     }
-                    p0 |= (uint32_t)(a0 & 0xff) << (8 * k);
-                    p1 |= (uint32_t)(a1 & 0xff) << (8 * k);
                 }
             }
-            out32[(0 * kTS + s) * OUT_PITCH_W + r4] = p0;
-            out32[(1 * kTS + s) * OUT_PITCH_W + r4] = p1;
         }
+        *reinterpret_cast<uint4 *>(&sm.out[0][s][16 * rg]) = make_uint4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        *reinterpret_cast<uint4 *>(&sm.out[1][s][16 * rg]) = make_uint4(acc1[0], acc1[1], acc1[2], acc1[3]);
     }
     __syncthreads();
 
@@ -247,19 +253,15 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     }
     __syncthreads();
 
-    // ---- phase 3: 128 contiguous bytes per (plane, sample), 16-byte vector stores
+    // ---- phase 3: kTV contiguous bytes per (plane, sample), 16-byte vector stores
     {
-        const uint32_t *out32 = reinterpret_cast<const uint32_t *>(&sm.out[0][0][0]);
-        constexpr int OUT_PITCH_W = OUT_PITCH / 4;
         constexpr int PIECES = kTV / 16;
         for (int item = tid; item < 2 * kTS * PIECES; item += GT_THREADS) {
             const int piece = item % PIECES;
             const int ps = item / PIECES;       // plane * kTS + s
             const int s = ps % kTS, p = ps / kTS;
             if ((uint32_t)s >= ns) continue;
-            const uint32_t *src = out32 + ps * OUT_PITCH_W + 4 * piece;
-            uint4 v;
-            v.x = src[0]; v.y = src[1]; v.z = src[2]; v.w = src[3];
+            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.out[p][s][16 * piece]);
             int8_t *dst = (p ? gt1 : gt0) + (uint64_t)(s0 + s) * gt_stride + r0 + 16ull * piece;
             stg_stream(reinterpret_cast<uint4 *>(dst), v);
         }

@@ -8,7 +8,7 @@ namespace hb {
 // Tile geometry shared by the tokenizer (checkpoints) and the GT decoder (sample tiles).
 constexpr int kCP = 128;          // one column checkpoint every kCP samples
 constexpr int kTS = 128;          // samples per decode tile (== kCP)
-constexpr int kTV = 128;          // records (rows) per decode tile
+constexpr int kTV = 64;           // records (rows) per decode tile
 constexpr uint64_t kNoCp = ~0ull; // "no checkpoint written"
 
 // Per kept record, produced by the site kernel, consumed by the GT decoder.
@@ -31,8 +31,20 @@ struct DevStatus {
     unsigned long long n_bad_cols;     // records whose column count != 9 + n_samples (or < 8 fields)
     unsigned long long n_nogt;         // kept records without a GT key / sample columns
     unsigned long long n_chrom_runs;
-    unsigned int line_overflow;        // more lines than line_cap
     unsigned int ticket;               // tile tickets of the site kernel
+};
+
+// Per tokenizer CTA (one contiguous byte range each).
+struct CtaTok {
+    uint32_t n_newlines;   // '\n' bytes in the range
+    uint32_t tail_tabs;    // tabs after the last newline of the range (all tabs if it has none)
+};
+
+// Staged line index: record starts as written by the tokenizer CTAs + prefix sums of their counts.
+struct LineIndex {
+    const uint64_t *nl_after;   // [n_cta * stage_cap]
+    const uint64_t *base;       // [n_cta + 1] exclusive prefix sum of CtaTok::n_newlines
+    uint32_t n_cta, stage_cap;
 };
 
 struct RegionArg {
@@ -48,13 +60,13 @@ struct Launch {   // filled by the host, one per parse
 };
 
 // ---- launchers (definitions in the .cu files) ----
-void launch_tokenize(bool with_tabs, const uint8_t *d_text, uint64_t nbytes, uint64_t *d_tile_state,
-                     uint64_t n_tiles, uint64_t *d_line_start, uint64_t line_cap, uint64_t *d_cp, uint32_t ncp,
-                     DevStatus *d_st, const Launch &L);
+void launch_tokenize(bool with_tabs, const uint8_t *d_text, uint64_t nbytes, uint32_t n_cta, uint64_t tiles_per_cta,
+                     uint64_t *d_nl_after, uint32_t stage_cap, uint64_t *d_cp, uint32_t ncp, CtaTok *d_cta,
+                     const Launch &L);
 uint64_t tokenize_tile_bytes();
 void launch_index_columns(const uint8_t *d_text, const RowInfo *d_rowinfo, const uint32_t *d_nu_rows,
                           uint64_t n_nu, uint64_t *d_cp, uint32_t ncp, const Launch &L);
-void launch_sites(const uint8_t *d_text, const uint64_t *d_line_start, uint64_t n_lines, uint32_t n_samples,
+void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, uint32_t n_samples,
                   const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
                   uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
                   RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,

@@ -17,7 +17,7 @@ constexpr int ST_THREADS = 256;
 
 struct SiteArgs {
     const uint8_t *text;
-    const uint64_t *line_start;
+    LineIndex li;
     uint64_t n_lines;
     uint32_t n_samples;
     RegionArg rg;
@@ -32,12 +32,26 @@ struct SiteArgs {
     DevStatus *st;
 };
 
+// offset of the byte after the k-th newline of the text (k = global newline ordinal)
+__device__ __forceinline__ uint64_t nl_after_global(const LineIndex &li, const uint64_t *s_base, uint64_t k) {
+    uint32_t lo = 0, hi = li.n_cta;          // find b with base[b] <= k < base[b+1]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (s_base[mid] <= k) lo = mid; else hi = mid;
+    }
+    return li.nl_after[(uint64_t)lo * li.stage_cap + (k - s_base[lo])];
+}
+
+constexpr int kMaxTokCta = 1024;
+
 __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
+    __shared__ uint64_t s_cbase[kMaxTokCta + 1];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[ST_THREADS / 32];
     __shared__ uint64_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(&a.st->ticket, 1u);
+    for (uint32_t k = tid; k <= a.li.n_cta; k += ST_THREADS) s_cbase[k] = a.li.base[k];
     __syncthreads();
     const uint64_t tile = s_tile;
     const uint64_t line = tile * ST_THREADS + tid;
@@ -50,8 +64,8 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
     long long endval = -1;
 
     if (line < a.n_lines) {
-        ls = a.line_start[line];
-        le = a.line_start[line + 1] - 1;                       // position of '\n'
+        ls = line ? nl_after_global(a.li, s_cbase, line - 1) : 0;
+        le = nl_after_global(a.li, s_cbase, line) - 1;         // position of '\n'
         const uint8_t *t = a.text;
         if (le > ls && t[le - 1] == '\r') --le;
         if (le > ls && t[ls] != '#') {
@@ -203,14 +217,22 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
         if (!has_samples || g < 0) atomicAdd(&a.st->n_nogt, 1ull);
         else if (!uniform) {
             unsigned long long slot = atomicAdd(&a.st->n_nonuniform, 1ull);
-            if (a.cp_by_line) ri.cp_row = (uint32_t)line;
+            if (a.cp_by_line) {   // staged id of the line: (tokenizer CTA, local line) -- see hb_tokenize.cu
+                uint32_t cb = 0, jl = 0;
+                if (line) {
+                    uint32_t lo = 0, hi = a.li.n_cta;
+                    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= line - 1) lo = mid; else hi = mid; }
+                    cb = lo; jl = (uint32_t)(line - 1 - s_cbase[lo]) + 1;
+                }
+                ri.cp_row = cb * a.li.stage_cap + jl;
+            }
             else { ri.cp_row = (uint32_t)slot; a.nu_rows[slot] = (uint32_t)row; }
         }
     }
     a.rowinfo[row] = ri;
 }
 
-void launch_sites(const uint8_t *d_text, const uint64_t *d_line_start, uint64_t n_lines, uint32_t n_samples,
+void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, uint32_t n_samples,
                   const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
                   uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
                   RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
@@ -219,7 +241,7 @@ void launch_sites(const uint8_t *d_text, const uint64_t *d_line_start, uint64_t 
     uint64_t tiles = (n_lines + ST_THREADS - 1) / ST_THREADS;
     cudaMemsetAsync(d_tile_state, 0, tiles * sizeof(uint64_t), L.stream);
     SiteArgs a;
-    a.text = d_text; a.line_start = d_line_start; a.n_lines = n_lines; a.n_samples = n_samples;
+    a.text = d_text; a.li = li; a.n_lines = n_lines; a.n_samples = n_samples;
     a.rg = rg; a.end_is_int = end_is_int; a.want_gt = want_gt; a.cp_by_line = cp_by_line ? 1 : 0;
     a.start = d_start; a.stop = d_stop; a.ref = d_ref; a.alt = d_alt;
     a.chrom_abs = d_chrom_abs; a.chrom_len = d_chrom_len; a.rowinfo = d_rowinfo; a.nu_rows = d_nu_rows;
