@@ -31,7 +31,9 @@ static_assert(kTV % 16 == 0 && ((OUT_PITCH / 16) & 1) == 1, "tile geometry");
 struct GtSmem {
     alignas(128) uint8_t text[kTV][SEG_PITCH];
     alignas(16) uint8_t out[2][kTS][OUT_PITCH];
-    alignas(16) uint32_t meta[kTV];       // fast rows: byte offset of sample 0's TAB inside text[r]; else 0xffffffff
+    alignas(16) uint32_t addr[kTV];       // byte offset (multiple of 4) of sample 0's column word inside text[][]
+    alignas(16) uint32_t shft[kTV];       // 8 * (misalignment of that column, 0..3)
+    alignas(16) uint32_t dummy[kTS + 4];  // "\t0|0" x kTS: what records off the fast path decode
     uint64_t seg_begin[kTV];
     uint32_t seg_len[kTV];
     uint32_t seg_g[kTV];
@@ -39,7 +41,6 @@ struct GtSmem {
     alignas(8) uint64_t bar;
     uint32_t tx_total;
 };
-constexpr uint32_t kMetaSlow = 0xffffffffu;
 
 // One sample column starting at p (first byte after the TAB).  Restates htslib's GT parse:
 // '.' -> missing (-9), digits -> allele index (int8-narrowed), '|' or '/' continue.
@@ -78,13 +79,17 @@ __device__ __noinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t
 }
 
 // "\tXsY" with X,Y in [0-9.] and s in [|/] that is not the common "\t[01]|[01]".
-// Returns (a0 & 0xff) << 8 | (a1 & 0xff) << 24, or 0xffffffff when the group is not of that shape.
-__device__ __noinline__ uint32_t decode_group_slow(uint32_t w) {
+// Returns (a0 & 0xff) << 8 | (a1 & 0xff) << 24.  A group that is not of that shape demotes its record
+// (*mode = 2) to the general path, which redoes the whole segment; records that were never on the
+// fast path (*mode != 1) just yield 0.
+__device__ __noinline__ uint32_t decode_group_slow(uint32_t w, int *mode) {
+    if (*mode != 1) return 0;
     const uint32_t sep = (w >> 16) & 0xffu, x = (w >> 8) & 0xffu, y = w >> 24;
-    if ((w & 0xffu) != '\t' || !(sep == '|' || sep == '/')) return 0xffffffffu;
-    uint32_t a0, a1;
-    if (x == '.') a0 = (uint32_t)(-9) & 0xffu; else { a0 = x - '0'; if (a0 > 9) return 0xffffffffu; }
-    if (y == '.') a1 = (uint32_t)(-9) & 0xffu; else { a1 = y - '0'; if (a1 > 9) return 0xffffffffu; }
+    bool ok = (w & 0xffu) == '\t' && (sep == '|' || sep == '/');
+    uint32_t a0 = x - '0', a1 = y - '0';
+    if (x == '.') a0 = (uint32_t)(-9) & 0xffu; else if (a0 > 9) ok = false;
+    if (y == '.') a1 = (uint32_t)(-9) & 0xffu; else if (a1 > 9) ok = false;
+    if (!ok) { *mode = 2; return 0; }
     return (a0 << 8) | (a1 << 24);
 }
 
@@ -110,6 +115,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         mbar_fence_init();
         sm.tx_total = 0;
     }
+    if (tid < kTS + 4) sm.dummy[tid] = 0x307C3009u;
     __syncthreads();
 
     // ---- phase 0: locate each record's segment; stage uniform ones with TMA
@@ -143,7 +149,13 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         sm.seg_len[tid] = len;
         sm.seg_g[tid] = g;
         sm.mode[tid] = mode;
-        sm.meta[tid] = mode == 1 ? (uint32_t)(b & 15ull) : kMetaSlow;
+        if (mode == 1) {
+            sm.addr[tid] = (uint32_t)tid * SEG_PITCH + ((uint32_t)(b & 15ull) & ~3u);
+            sm.shft[tid] = 8u * ((uint32_t)b & 3u);
+        } else {
+            sm.addr[tid] = (uint32_t)(reinterpret_cast<const uint8_t *>(sm.dummy) - &sm.text[0][0]);
+            sm.shft[tid] = 0;
+        }
         if (mode == 1) {
             uint32_t bytes = (uint32_t)(((b & 15ull) + len + 15ull) & ~15ull);
             atomicAdd(&sm.tx_total, bytes);
@@ -163,35 +175,46 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
 
     // ---- phase 1: fast path.  One thread = 1 sample x 16 records; lanes run along samples, so the
     //      two 4-byte loads per call and the 16-byte transposed stores are bank-conflict free.
+    //      Records that are not on the fast path read a dummy row of "\t0|0" instead (-> zeros), and
+    //      anything that is not "\t[01]|[01]" only raises a flag, so the hot loop has no branches;
+    //      flagged threads then redo their few odd calls one by one.
     for (int item = tid; item < kTS * (kTV / 16); item += GT_THREADS) {
         const int s = item % kTS, rg = item / kTS;
         uint32_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+        uint32_t bad = 0;
+        const uint8_t *tbase = &sm.text[0][0] + 4 * s;
         if ((uint32_t)s < ns) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 m4 = *reinterpret_cast<const uint4 *>(&sm.meta[16 * rg + 4 * q]);
-                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const uint4 a4 = *reinterpret_cast<const uint4 *>(&sm.addr[16 * rg + 4 * q]);
+                const uint4 h4 = *reinterpret_cast<const uint4 *>(&sm.shft[16 * rg + 4 * q]);
+                const uint32_t aa[4] = {a4.x, a4.y, a4.z, a4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int r = 16 * rg + 4 * q + k;
-                    if (mm[k] != kMetaSlow) {                 // warp-uniform
-                        const uint32_t off = mm[k] + 4u * s;
-                        const uint32_t *rowp = reinterpret_cast<const uint32_t *>(sm.text[r]) + (off >> 2);
-                        const uint32_t w = __funnelshift_r(rowp[0], rowp[1], (off & 3u) * 8u);
-                        uint32_t x = w ^ 0x307C3009u;         // "\t0|0": leaves the two allele bits
-                        if (x & 0xFEFFFEFFu) {
-                            x = decode_group_slow(w);
-                            if (x == 0xffffffffu) { sm.mode[r] = 2; x = 0; }   // demote the record to the general path
-                        }
-                        // byte k of acc0 <- byte 1 of x, byte k of acc1 <- byte 3 of x
-                        acc0[q] = __byte_perm(acc0[q], x, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
-                        acc1[q] = __byte_perm(acc1[q], x, k == 0 ? 0x3217 : k == 1 ? 0x3270 : k == 2 ? 0x3710 : 0x7210);
-                    }
+                    const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + aa[k]);
+                    const uint32_t x = __funnelshift_r(colp[0], colp[1], hh[k]) ^ 0x307C3009u;   // "\t0|0"
+                    bad |= x & 0xFEFFFEFFu;                   // anything but the two allele bits left?
+                    // byte k of acc0 <- byte 1 of x, byte k of acc1 <- byte 3 of x
+                    acc0[q] = __byte_perm(acc0[q], x, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
+                    acc1[q] = __byte_perm(acc1[q], x, k == 0 ? 0x3217 : k == 1 ? 0x3270 : k == 2 ? 0x3710 : 0x7210);
                 }
             }
         }
         *reinterpret_cast<uint4 *>(&sm.out[0][s][16 * rg]) = make_uint4(acc0[0], acc0[1], acc0[2], acc0[3]);
         *reinterpret_cast<uint4 *>(&sm.out[1][s][16 * rg]) = make_uint4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        if (bad) {
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {
+                const int r = 16 * rg + i;
+                const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + sm.addr[r]);
+                const uint32_t w = __funnelshift_r(colp[0], colp[1], sm.shft[r]);
+                if ((w ^ 0x307C3009u) & 0xFEFFFEFFu) {
+                    const uint32_t x = decode_group_slow(w, &sm.mode[r]);
+                    sm.out[0][s][r] = (uint8_t)(x >> 8);
+                    sm.out[1][s][r] = (uint8_t)(x >> 24);
+                }
+            }
+        }
     }
     __syncthreads();
 
