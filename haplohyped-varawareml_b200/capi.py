@@ -52,11 +52,10 @@ class FramesInfo(C.Structure):
 
 class HapBatch(C.Structure):
     _fields_ = [("B", C.c_uint32), ("L", C.c_uint32), ("C", C.c_uint32),
-                ("ref_seq", C.c_void_p), ("item_ref_off", C.c_void_p), ("item_len", C.c_void_p),
-                ("item_win_start", C.c_void_p), ("start", C.c_void_p), ("ref", C.c_void_p), ("alt", C.c_void_p),
-                ("item_row_lo", C.c_void_p), ("item_row_hi", C.c_void_p), ("p1", C.c_void_p), ("p2", C.c_void_p),
-                ("item_gt_off", C.c_void_p), ("lut", C.c_void_p), ("hap1", C.c_void_p), ("hap2", C.c_void_p),
-                ("stream", C.c_void_p)]
+                ("item_seq", C.c_void_p), ("item_len", C.c_void_p), ("item_win_start", C.c_void_p),
+                ("item_start", C.c_void_p), ("item_ref", C.c_void_p), ("item_alt", C.c_void_p),
+                ("item_p1", C.c_void_p), ("item_p2", C.c_void_p), ("item_nrec", C.c_void_p),
+                ("lut", C.c_void_p), ("hap1", C.c_void_p), ("hap2", C.c_void_p), ("stream", C.c_void_p)]
 
 
 class SynthSpec(C.Structure):

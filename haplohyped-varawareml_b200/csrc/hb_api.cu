@@ -23,6 +23,7 @@
 
 #include "../../include/haplo_b200.h"
 #include "hb_internal.h"
+#include "hb_parse_struct.h"
 
 namespace hb {
 
@@ -34,6 +35,7 @@ static int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+int api_fail(int code, const std::string &msg) { return fail(code, msg); }
 #define CU(expr)                                                                                      \
     do {                                                                                              \
         cudaError_t e_ = (expr);                                                                      \
@@ -90,48 +92,7 @@ using namespace hb;
 // =============================================================================================
 // hb_parse: one device-resident parse
 // =============================================================================================
-struct hb_parse {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    int sm_count = 148;
-    const uint8_t *d_text = nullptr;
-    uint8_t *d_text_owned = nullptr;
-    uint64_t nbytes = 0;
-    uint32_t n_samples = 0;
-    RegionArg rg;
-    int end_is_int = 0, want_gt = 1, tokenizer = 0;
-    bool with_tabs = false;
-    uint32_t ncp = 0;
-
-    uint64_t *d_nl_after = nullptr; uint64_t nl_after_cap = 0;
-    uint32_t stage_cap = 0, n_cta = 0;
-    uint64_t tiles_per_cta = 0;
-    bool probed = false;
-    uint64_t n_lines = 0;
-    uint64_t first_line_len = 0;
-    CtaTok *d_cta = nullptr;
-    uint64_t *d_cbase = nullptr;
-    uint64_t *d_cp = nullptr; uint64_t cp_rows = 0;
-    DevStatus *d_st = nullptr;
-    DevStatus h_st;
-    uint32_t *d_start = nullptr, *d_stop = nullptr;
-    uint8_t *d_ref = nullptr, *d_alt = nullptr, *d_chrom_len = nullptr;
-    uint64_t *d_chrom_abs = nullptr;
-    RowInfo *d_rowinfo = nullptr;
-    uint32_t *d_nu_rows = nullptr;
-    uint64_t *d_sites_state = nullptr;
-    uint64_t row_cap = 0;
-    int8_t *d_gt[2] = {nullptr, nullptr};
-    uint64_t gt_stride = 0, gt_bytes = 0;
-    uint32_t *d_ploidy = nullptr, *d_badgt = nullptr;
-    uint64_t *d_run_rows = nullptr;
-    static constexpr uint64_t kMaxRuns = 4096;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float ms_tok = 0, ms_sites = 0, ms_decode = 0;
-    // chrom runs (host)
-    std::vector<uint64_t> run_rows;
-    std::vector<std::string> run_names;
-};
+#include "hb_parse_struct.h"
 
 static void free_dev(void *p) { if (p) cudaFree(p); }
 
@@ -140,7 +101,7 @@ void hb_parse_free(hb_parse *p) {
     cudaSetDevice(p->device);
     free_dev(p->d_text_owned); free_dev(p->d_nl_after); free_dev(p->d_cta); free_dev(p->d_cbase); free_dev(p->d_cp);
     free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
-    free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
+    free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_chrom5); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
     free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_ploidy);
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
@@ -244,7 +205,7 @@ static int run_parse(hb_parse *p) {
         uint64_t cap = n_lines;
         TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
         TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
-        TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap));
+        TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
         TRY(dev_alloc(&p->d_rowinfo, cap)); TRY(dev_alloc(&p->d_nu_rows, cap));
         TRY(dev_alloc(&p->d_sites_state, (cap + 255) / 256 + 1));
         p->row_cap = cap;
@@ -256,7 +217,7 @@ static int run_parse(hb_parse *p) {
     CU(cudaMemsetAsync(p->d_ploidy, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
     CU(cudaMemsetAsync(p->d_badgt, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
     launch_sites(p->d_text, li, n_lines, p->n_samples, p->rg, p->end_is_int, p->want_gt, p->with_tabs,
-                 p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_rowinfo,
+                 p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_chrom5, p->d_rowinfo,
                  p->d_nu_rows, p->d_sites_state, p->d_st, L);
     CU(cudaEventRecord(p->ev[2], p->stream));
     CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));

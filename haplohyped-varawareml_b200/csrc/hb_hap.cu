@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
     __syncthreads();
 
     // ---- reference window -> class index (R1); beyond the window: -1 => all-zero row
-    const uint8_t *seq = a.ref_seq + a.item_ref_off[b];
+    const uint8_t *seq = reinterpret_cast<const uint8_t *>(a.item_seq[b]);
     for (uint32_t k = tid; k < tn; k += HP_THREADS) {
         uint32_t p = tile0 + k;
         int8_t v = -1;
@@ -58,22 +58,25 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
 
     // ---- records inside this tile (R2), last duplicate wins
     {
-        const uint64_t lo = a.item_row_lo[b], hi = a.item_row_hi[b];
+        const uint64_t nrec = a.item_nrec[b];
         const uint32_t wend = min(len, tile0 + tn);              // exclusive, window-relative
-        if (lo < hi && tile0 < wend) {
+        if (nrec && tile0 < wend) {
+            const uint32_t *start = reinterpret_cast<const uint32_t *>(a.item_start[b]);
+            const uint8_t *ref = reinterpret_cast<const uint8_t *>(a.item_ref[b]);
+            const uint8_t *alt = reinterpret_cast<const uint8_t *>(a.item_alt[b]);
+            const int8_t *p1 = reinterpret_cast<const int8_t *>(a.item_p1[b]);
+            const int8_t *p2 = reinterpret_cast<const int8_t *>(a.item_p2[b]);
             // genomic range [ws + tile0, ws + wend)
             const uint64_t g0 = (uint64_t)ws + tile0, g1 = (uint64_t)ws + wend;
-            const uint32_t k0 = g0 > 0xffffffffull ? 0xffffffffu : (uint32_t)g0;
-            const uint64_t rb = lower_bound_u32(a.start, lo, hi, k0);
-            const uint64_t re = g1 > 0xffffffffull ? hi : lower_bound_u32(a.start, rb, hi, (uint32_t)g1);
-            const uint64_t go = a.item_gt_off[b];
+            const uint64_t rb = g0 > 0xffffffffull ? nrec : lower_bound_u32(start, 0, nrec, (uint32_t)g0);
+            const uint64_t re = g1 > 0xffffffffull ? nrec : lower_bound_u32(start, rb, nrec, (uint32_t)g1);
             for (uint64_t r = rb + tid; r < re; r += HP_THREADS) {
-                const uint32_t st = a.start[r];
-                if (r + 1 < hi && a.start[r + 1] == st) continue;   // a later record at the same position wins
+                const uint32_t st = start[r];
+                if (r + 1 < nrec && start[r + 1] == st) continue;   // a later record at the same position wins
                 const uint32_t k = st - ws - tile0;
-                const int8_t ri = s_lut[a.ref[r]], ai = s_lut[a.alt[r]];
-                s_idx[0][k] = a.p1[go + r] == 1 ? ai : ri;
-                s_idx[1][k] = a.p2[go + r] == 1 ? ai : ri;
+                const int8_t ri = s_lut[ref[r]], ai = s_lut[alt[r]];
+                s_idx[0][k] = p1[r] == 1 ? ai : ri;
+                s_idx[1][k] = p2[r] == 1 ? ai : ri;
             }
         }
     }

@@ -69,7 +69,7 @@ void launch_index_columns(const uint8_t *d_text, const RowInfo *d_rowinfo, const
 void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, uint32_t n_samples,
                   const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
                   uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
-                  RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
+                  uint64_t *d_chrom5, RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
                   const Launch &L);
 void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const uint8_t *d_chrom_len,
                        uint64_t n_rows, uint64_t *d_run_rows, uint64_t max_runs, DevStatus *d_st,

@@ -1,0 +1,55 @@
+// hb_parse_struct.h -- the device-resident parse handle, shared by hb_api.cu and hb_store.cu.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "hb_internal.h"
+
+namespace hb {
+int api_fail(int code, const std::string &msg);    // sets the thread-local hb_last_error() text
+}
+
+struct hb_parse {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    const uint8_t *d_text = nullptr;
+    uint8_t *d_text_owned = nullptr;
+    uint64_t nbytes = 0;
+    uint32_t n_samples = 0;
+    hb::RegionArg rg;
+    int end_is_int = 0, want_gt = 1, tokenizer = 0;
+    bool with_tabs = false;
+    uint32_t ncp = 0;
+
+    uint64_t *d_nl_after = nullptr; uint64_t nl_after_cap = 0;
+    uint32_t stage_cap = 0, n_cta = 0;
+    uint64_t tiles_per_cta = 0;
+    bool probed = false;
+    uint64_t n_lines = 0;
+    uint64_t first_line_len = 0;
+    hb::CtaTok *d_cta = nullptr;
+    uint64_t *d_cbase = nullptr;
+    uint64_t *d_cp = nullptr; uint64_t cp_rows = 0;
+    hb::DevStatus *d_st = nullptr;
+    hb::DevStatus h_st;
+    uint32_t *d_start = nullptr, *d_stop = nullptr;
+    uint8_t *d_ref = nullptr, *d_alt = nullptr, *d_chrom_len = nullptr;
+    uint64_t *d_chrom_abs = nullptr;
+    uint64_t *d_chrom5 = nullptr;       // first 5 CHROM bytes per record (the S5 field of the 35-byte record)
+    hb::RowInfo *d_rowinfo = nullptr;
+    uint32_t *d_nu_rows = nullptr;
+    uint64_t *d_sites_state = nullptr;
+    uint64_t row_cap = 0;
+    int8_t *d_gt[2] = {nullptr, nullptr};
+    uint64_t gt_stride = 0, gt_bytes = 0;
+    uint32_t *d_ploidy = nullptr, *d_badgt = nullptr;
+    uint64_t *d_run_rows = nullptr;
+    static constexpr uint64_t kMaxRuns = 4096;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms_tok = 0, ms_sites = 0, ms_decode = 0;
+    // chrom runs (host)
+    std::vector<uint64_t> run_rows;
+    std::vector<std::string> run_names;
+};
+

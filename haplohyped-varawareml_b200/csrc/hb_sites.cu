@@ -26,6 +26,7 @@ struct SiteArgs {
     uint8_t *ref, *alt;
     uint64_t *chrom_abs;
     uint8_t *chrom_len;
+    uint64_t *chrom5;
     RowInfo *rowinfo;
     uint32_t *nu_rows;
     uint64_t *tile_state;
@@ -206,6 +207,11 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
     a.alt[row] = alt0;
     a.chrom_abs[row] = ls;
     a.chrom_len[row] = (uint8_t)(chrom_len > 255 ? 255 : chrom_len);
+    {   // S5 field of the 35-byte record: first 5 CHROM bytes, NUL padded (silent truncation, vcf_to_h5.py:120)
+        uint64_t c5 = 0;
+        for (uint32_t k = 0; k < 5 && k < chrom_len; ++k) c5 |= (uint64_t)a.text[ls + k] << (8 * k);
+        a.chrom5[row] = c5;
+    }
     RowInfo ri;
     ri.samp_abs = samp_abs;
     ri.samp_len = has_samples ? (uint32_t)(le - samp_abs) : 0u;
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
 void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, uint32_t n_samples,
                   const RegionArg &rg, int end_is_int, int want_gt, bool cp_by_line, uint32_t *d_start,
                   uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
-                  RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
+                  uint64_t *d_chrom5, RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
                   const Launch &L) {
     if (!n_lines) return;
     uint64_t tiles = (n_lines + ST_THREADS - 1) / ST_THREADS;
@@ -244,7 +250,7 @@ void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, 
     a.text = d_text; a.li = li; a.n_lines = n_lines; a.n_samples = n_samples;
     a.rg = rg; a.end_is_int = end_is_int; a.want_gt = want_gt; a.cp_by_line = cp_by_line ? 1 : 0;
     a.start = d_start; a.stop = d_stop; a.ref = d_ref; a.alt = d_alt;
-    a.chrom_abs = d_chrom_abs; a.chrom_len = d_chrom_len; a.rowinfo = d_rowinfo; a.nu_rows = d_nu_rows;
+    a.chrom_abs = d_chrom_abs; a.chrom_len = d_chrom_len; a.chrom5 = d_chrom5; a.rowinfo = d_rowinfo; a.nu_rows = d_nu_rows;
     a.tile_state = d_tile_state; a.st = d_st;
     sites_kernel<<<(unsigned)tiles, ST_THREADS, 0, L.stream>>>(a);
     count_launch();

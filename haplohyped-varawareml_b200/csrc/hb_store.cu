@@ -1,0 +1,468 @@
+// hb_store.cu -- kernel 4: Blosc2 byte-shuffle + LZ4 block encoder + Blosc2 chunk / cframe framing.
+//
+// Replaces what h5py + hdf5plugin do for every HDF5 chunk of
+//   create_dataset('snp_data', data=<35-byte records>, compression=32001,
+//                  compression_opts=(2,2,0,0,5,1,2), chunks=True)        (vcf_to_h5.py:119-135)
+// i.e. c-blosc2's shuffle(typesize 35) + LZ4-family codec, wrapped by the hdf5-blosc2 filter as a
+// contiguous frame holding one Blosc2 chunk.  The reference asks for LZ4HC (compcode 2); LZ4 and
+// LZ4HC share one block format and one Blosc codec-format id, so a stock decoder cannot tell.
+//
+// The byte-shuffled image of one (sample, chunk) is 35 planes of `cr` bytes.  Planes 0..32 hold
+// site bytes and are IDENTICAL for every sample; only planes 33/34 (the two allele planes, which
+// the GT decoder already wrote in exactly this planar layout) differ.  So:
+//   site_prefix_kernel   one CTA per chunk: builds the 33 site planes in shared memory straight
+//                        from the SoA columns (the 35-byte AoS records are never materialised) and
+//                        LZ4-encodes them once, as the head of a no-split LZ4 block;
+//   donor_frames_kernel  one warp per (chunk, sample): LZ4-encodes the 2*cr allele bytes as the
+//                        continuation of that block (history = tail of the site planes), then
+//                        writes cframe header + chunk header + shared prefix + own sequences +
+//                        offsets chunk + trailer.
+// The encoder is a warp-cooperative greedy matcher: 32 candidate positions per step are hashed in
+// parallel, the first hit is extended with ballots, literals are copied 32 bytes per step.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/haplo_b200.h"
+#include "hb_common.cuh"
+#include "hb_internal.h"
+#include "hb_parse_struct.h"
+
+namespace hb {
+
+constexpr int kHist = 64;                 // bytes of history kept in front of the donor planes
+constexpr int FRAME_HDR = 97, CHUNK_HDR = 32, OFFS_CHUNK = 40, FRAME_TRAILER = 35;
+constexpr int FRAME_FIXED = FRAME_HDR + CHUNK_HDR + 4 + 4 + OFFS_CHUNK + FRAME_TRAILER;   // + LZ4 bytes
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t *p) {     // unaligned 4-byte read (shared memory)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8u);
+}
+
+// Warp-cooperative LZ4 block encoder over src[0..n) with `hist` readable bytes before src.
+//   anchor0 <= 0: literals still pending from the previous part of the block (src[anchor0..0)).
+//   final: obey the end-of-block rules (last 5 bytes literal, last match starts <= n-12) and flush
+//          the trailing literals; otherwise stop after the last match and report the pending
+//          literal count through *pending.
+// table: 1 << hashlog uint16 entries (position + 1; 0 = empty), cleared here.  n < 65535.
+// Returns the number of bytes written to dst.  All lanes return the same value.
+__device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool final, uint8_t *dst,
+                        uint16_t *table, int hashlog, int *pending) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < (1 << hashlog); i += 32) table[i] = 0;
+    __syncwarp();
+    int op = 0, anchor = anchor0, pos = 0;
+    const int mflimit = final ? n - 12 : n - 4;      // last position a match may start at
+    const int mend = final ? n - 5 : n;              // matches end at or before this
+    while (pos <= mflimit) {
+        const int p = pos + lane;
+        const bool valid = p <= mflimit;
+        uint32_t v = 0, h = 0;
+        int cand = -0x40000000;
+        if (valid) {
+            v = rd32(src + p);
+            h = (v * 2654435761u) >> (32 - hashlog);
+            const int c = (int)table[h] - 1;
+            if (c >= 0 && c < p && rd32(src + c) == v) cand = c;   // c == p: left by a re-examined window
+            else if (p - 1 >= -hist && rd32(src + p - 1) == v) cand = p - 1;     // run of one byte
+        }
+        __syncwarp();
+        if (valid) table[h] = (uint16_t)(p + 1);
+        __syncwarp();
+        const unsigned hit = __ballot_sync(0xffffffffu, cand > -0x40000000);
+        if (!hit) { pos += 32; continue; }
+        const int f = __ffs(hit) - 1;
+        const int m = pos + f;
+        const int c = __shfl_sync(0xffffffffu, cand, f);
+        int ml = 4;
+        for (;;) {
+            const int i = ml + lane;
+            const bool same = (m + i < mend) && src[m + i] == src[c + i];
+            const unsigned bal = __ballot_sync(0xffffffffu, same);
+            if (bal == 0xffffffffu) { ml += 32; continue; }
+            ml += __ffs(~bal) - 1;
+            break;
+        }
+        if (m + ml > mend) ml = mend - m;             // (cannot happen: guarded above)
+        if (ml < 4) { pos = m + 1; continue; }        // match would cross the end-of-block limit
+        const int litlen = m - anchor;
+        int o = op;
+        if (lane == 0) {
+            dst[o] = (uint8_t)((min(litlen, 15) << 4) | min(ml - 4, 15));
+        }
+        ++o;
+        if (litlen >= 15) {
+            int rem = litlen - 15;
+            while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
+            if (lane == 0) dst[o] = (uint8_t)rem;
+            ++o;
+        }
+        for (int i = lane; i < litlen; i += 32) dst[o + i] = src[anchor + i];
+        o += litlen;
+        const int off = m - c;
+        if (lane == 0) { dst[o] = (uint8_t)off; dst[o + 1] = (uint8_t)(off >> 8); }
+        o += 2;
+        if (ml - 4 >= 15) {
+            int rem = ml - 19;
+            while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
+            if (lane == 0) dst[o] = (uint8_t)rem;
+            ++o;
+        }
+        op = o;
+        anchor = pos = m + ml;
+    }
+    if (final) {
+        const int litlen = n - anchor;
+        int o = op;
+        if (lane == 0) dst[o] = (uint8_t)(min(litlen, 15) << 4);
+        ++o;
+        if (litlen >= 15) {
+            int rem = litlen - 15;
+            while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
+            if (lane == 0) dst[o] = (uint8_t)rem;
+            ++o;
+        }
+        for (int i = lane; i < litlen; i += 32) dst[o + i] = src[anchor + i];
+        op = o + litlen;
+        if (pending) *pending = 0;
+    } else if (pending) {
+        *pending = n - anchor;
+    }
+    __syncwarp();
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------
+// site planes 0..32 of one chunk -> LZ4 head of the block
+// ------------------------------------------------------------------------------------------
+struct SiteArgs4 {
+    const uint64_t *chrom5;      // per record: first 5 CHROM bytes, NUL padded, in the low 40 bits
+    const uint32_t *start, *stop;
+    const uint8_t *ref, *alt;
+    uint64_t n_records;
+    uint32_t cr;                 // records per chunk
+    uint8_t *prefix;             // [n_chunks][prefix_cap]
+    uint32_t prefix_cap;
+    uint32_t *prefix_len;        // [n_chunks]
+    uint32_t *prefix_pending;    // [n_chunks] literals left pending at the end of the site planes
+    uint8_t *tail;               // [n_chunks][kHist] last bytes of the site planes
+};
+
+__global__ void __launch_bounds__(256) site_prefix_kernel(const SiteArgs4 a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t cr = a.cr;
+    const uint32_t n = 33u * cr;
+    uint8_t *planes = smem + 16;                            // 16 bytes of (unused) history in front
+    uint8_t *outb = planes + ((n + 19) & ~15u);
+    uint16_t *table = reinterpret_cast<uint16_t *>(outb + ((n + n / 255 + 64 + 15) & ~15u));
+    const uint64_t c = blockIdx.x;
+    const uint64_t r0 = c * cr;
+    for (uint32_t i = threadIdx.x; i < cr; i += blockDim.x) {
+        const uint64_t r = r0 + i;
+        uint64_t ch = 0;
+        uint32_t st = 0, sp = 0;
+        uint8_t rf = 0, al = 0;
+        if (r < a.n_records) { ch = a.chrom5[r]; st = a.start[r]; sp = a.stop[r]; rf = a.ref[r]; al = a.alt[r]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) planes[k * cr + i] = (uint8_t)(ch >> (8 * k));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            planes[(5 + k) * cr + i] = (uint8_t)(st >> (8 * k));
+            planes[(9 + k) * cr + i] = (uint8_t)(sp >> (8 * k));
+        }
+        planes[13 * cr + i] = rf;
+        planes[23 * cr + i] = al;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { planes[(14 + k) * cr + i] = 0; planes[(24 + k) * cr + i] = 0; }
+    }
+    if (threadIdx.x < 16) smem[threadIdx.x] = 0;
+    __syncthreads();
+    // Chunks of fewer than 6 records cannot honour LZ4's end-of-block rules (last match >= 12 bytes
+    // before the end) once the 2*cr allele bytes follow: such blocks are stored raw (csize == size).
+    const bool raw = cr < 6;
+    if (raw) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) outb[i] = planes[i];
+        if (threadIdx.x == 0) { a.prefix_len[c] = n; a.prefix_pending[c] = 0; }
+    } else if (threadIdx.x < 32) {
+        int pending = 0;
+        const int len = warp_lz4(planes, (int)n, 0, 0, false, outb, table, 12, &pending);
+        if (threadIdx.x == 0) { a.prefix_len[c] = (uint32_t)len; a.prefix_pending[c] = (uint32_t)pending; }
+    }
+    __syncthreads();
+    const uint32_t len = a.prefix_len[c];
+    uint8_t *dstp = a.prefix + c * a.prefix_cap;
+    for (uint32_t i = threadIdx.x; i < len && i < a.prefix_cap; i += blockDim.x) dstp[i] = outb[i];
+    if (threadIdx.x < kHist) {
+        const int idx = (int)n - kHist + (int)threadIdx.x;
+        a.tail[c * kHist + threadIdx.x] = idx >= 0 ? planes[idx] : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// one warp per (chunk, sample): allele planes -> tail of the LZ4 block -> complete cframe
+// ------------------------------------------------------------------------------------------
+struct DonorArgs {
+    const int8_t *gt0, *gt1;
+    uint64_t gt_stride, n_records;
+    uint32_t cr, n_samples;
+    uint64_t n_chunks;
+    const uint8_t *prefix;
+    uint32_t prefix_cap;
+    const uint32_t *prefix_len, *prefix_pending;
+    const uint8_t *tail;
+    uint8_t *frames;             // [n_chunks][n_samples][slot]
+    uint32_t slot;
+    uint32_t *sizes;             // [n_samples][n_chunks]
+    uint32_t warp_smem;          // bytes of shared memory per warp
+};
+
+__device__ __forceinline__ void put_be(uint8_t *p, uint64_t v, int nb) {
+    for (int i = 0; i < nb; ++i) p[i] = (uint8_t)(v >> (8 * (nb - 1 - i)));
+}
+__device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+__global__ void __launch_bounds__(256) donor_frames_kernel(const DonorArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (wid >= a.n_chunks * a.n_samples) return;
+    const uint64_t c = wid / a.n_samples;
+    const uint32_t s = (uint32_t)(wid % a.n_samples);
+    const uint32_t cr = a.cr, n = 2u * cr;
+    uint8_t *base = smem + (size_t)warp * a.warp_smem;
+    uint8_t *src = base + kHist;                                   // history sits right in front
+    uint8_t *outb = src + ((n + 19) & ~15u);
+    uint16_t *table = reinterpret_cast<uint16_t *>(outb + ((n + n / 255 + 64 + 15) & ~15u));
+    // history + the two allele planes (zero-padded past n_records, like an HDF5 edge chunk)
+    for (int i = lane; i < kHist; i += 32) base[i] = a.tail[c * kHist + i];
+    const uint64_t r0 = c * cr;
+    const int8_t *g0 = a.gt0 + (uint64_t)s * a.gt_stride + r0, *g1 = a.gt1 + (uint64_t)s * a.gt_stride + r0;
+    for (uint32_t i = lane; i < cr; i += 32) {
+        const bool in = r0 + i < a.n_records;
+        src[i] = in ? (uint8_t)g0[i] : 0;
+        src[cr + i] = in ? (uint8_t)g1[i] : 0;
+    }
+    __syncwarp();
+    const int pend = (int)a.prefix_pending[c];
+    const int hist = min(kHist, (int)(33u * cr));
+    // pending literals of the site planes are re-emitted as the first literals here; they must lie in the history
+    int dlen;
+    if (cr < 6) {                                  // raw block, see site_prefix_kernel
+        for (uint32_t i = lane; i < n; i += 32) outb[i] = src[i];
+        dlen = (int)n;
+        __syncwarp();
+    } else {
+        dlen = warp_lz4(src, (int)n, hist, -min(pend, hist), true, outb, table, 10, nullptr);
+    }
+    const uint32_t plen = a.prefix_len[c];
+    const uint32_t lz = plen + (uint32_t)dlen;
+    const uint32_t nbytes = 35u * cr;
+    const uint32_t chunk_cb = CHUNK_HDR + 4 + 4 + lz;
+    const uint32_t frame_len = FRAME_HDR + chunk_cb + OFFS_CHUNK + FRAME_TRAILER;
+    uint8_t *f = a.frames + (c * a.n_samples + s) * (uint64_t)a.slot;
+    if (lane == 0) {
+        // ---- cframe header (c-blosc2 README_CFRAME_FORMAT; msgpack, big-endian)
+        uint8_t *h = f;
+        h[0] = 0x9e; h[1] = 0xa8;
+        const char magic[8] = {'b', '2', 'f', 'r', 'a', 'm', 'e', 0};
+        for (int i = 0; i < 8; ++i) h[2 + i] = (uint8_t)magic[i];
+        h[10] = 0xd2; put_be(h + 11, FRAME_HDR, 4);
+        h[15] = 0xcf; put_be(h + 16, frame_len, 8);
+        h[24] = 0xa4; h[25] = 0x12; h[26] = 0x00; h[27] = 0x51; h[28] = 0x03;   // v2 | 64-bit offs, contiguous, LZ4 | clevel 5, split mode
+        h[29] = 0xd3; put_be(h + 30, nbytes, 8);
+        h[38] = 0xd3; put_be(h + 39, chunk_cb, 8);
+        h[47] = 0xd2; put_be(h + 48, 35, 4);
+        h[52] = 0xd2; put_be(h + 53, nbytes, 4);
+        h[57] = 0xd2; put_be(h + 58, nbytes, 4);
+        h[62] = 0xd1; put_be(h + 63, 1, 2);
+        h[65] = 0xd1; put_be(h + 66, 1, 2);
+        h[68] = 0xc2;
+        h[69] = 0xd8; h[70] = 6;
+        for (int i = 0; i < 16; ++i) h[71 + i] = 0;
+        h[76] = 1;                                       // filters[5] = BLOSC_SHUFFLE
+        h[87] = 0x93; h[88] = 0xcd; put_be(h + 89, 5, 2);
+        h[91] = 0xde; h[92] = 0; h[93] = 0; h[94] = 0xdc; h[95] = 0; h[96] = 0;
+        // ---- Blosc2 chunk header (extended, 32 bytes, little-endian)
+        uint8_t *k = f + FRAME_HDR;
+        k[0] = 5; k[1] = 1; k[2] = 0x35; k[3] = 35;      // format 5, LZ4 format 1, shuffle|bitshuffle(=extended)|dont-split|LZ4
+        put_le32(k + 4, nbytes); put_le32(k + 8, nbytes); put_le32(k + 12, chunk_cb);
+        for (int i = 16; i < 32; ++i) k[i] = 0;
+        k[21] = 1;                                       // filters[5] = BLOSC_SHUFFLE
+        put_le32(k + 32, CHUNK_HDR + 4);                 // bstarts[0]
+        put_le32(k + 36, lz);                            // the single stream's compressed size
+        // ---- offsets chunk: one int64 (0), stored as a memcpyed Blosc2 chunk
+        uint8_t *o = f + FRAME_HDR + chunk_cb;
+        o[0] = 5; o[1] = 1; o[2] = 0x17; o[3] = 8;
+        put_le32(o + 4, 8); put_le32(o + 8, 8); put_le32(o + 12, OFFS_CHUNK);
+        for (int i = 16; i < 40; ++i) o[i] = 0;
+        o[21] = 1;
+        // ---- trailer
+        uint8_t *t = o + OFFS_CHUNK;
+        t[0] = 0x94; t[1] = 0x01; t[2] = 0x93; t[3] = 0xcd; put_be(t + 4, 5, 2);
+        t[6] = 0xde; t[7] = 0; t[8] = 0; t[9] = 0xdc; t[10] = 0; t[11] = 0;
+        t[12] = 0xce; put_be(t + 13, FRAME_TRAILER, 4);
+        t[17] = 0xd8; t[18] = 0;
+        for (int i = 0; i < 16; ++i) t[19 + i] = 0;
+        a.sizes[(uint64_t)s * a.n_chunks + c] = frame_len;
+    }
+    // ---- LZ4 block: shared site head, then this sample's sequences
+    uint8_t *lzp = f + FRAME_HDR + CHUNK_HDR + 8;
+    const uint8_t *pp = a.prefix + c * a.prefix_cap;
+    for (uint32_t i = lane; i < plen; i += 32) lzp[i] = pp[i];
+    for (int i = lane; i < dlen; i += 32) lzp[plen + i] = outb[i];
+}
+
+uint64_t guess_chunk_records(uint64_t n) {      // h5py/_hl/filters.py guess_chunk for shape (n,), 35-byte items
+    const double CHUNK_BASE = 16 * 1024, CHUNK_MIN = 8 * 1024, CHUNK_MAX = 1024 * 1024;
+    if (n == 0) return 1;
+    double chunk = (double)n;
+    const double dset_size = chunk * 35.0;
+    double target = CHUNK_BASE * std::pow(2.0, std::log10(dset_size / (1024.0 * 1024.0)));
+    if (target > CHUNK_MAX) target = CHUNK_MAX;
+    else if (target < CHUNK_MIN) target = CHUNK_MIN;
+    for (;;) {
+        const double bytes = chunk * 35.0;
+        if ((bytes < target || std::fabs(bytes - target) / target < 0.5) && bytes < CHUNK_MAX) break;
+        if (chunk == 1) break;
+        chunk = std::ceil(chunk / 2.0);
+    }
+    return (uint64_t)chunk;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+struct hb_frames {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t n_records = 0, n_chunks = 0, cr = 0;
+    uint32_t n_samples = 0, slot = 0, prefix_cap = 0;
+    uint8_t *d_prefix = nullptr, *d_tail = nullptr, *d_frames = nullptr;
+    uint32_t *d_prefix_len = nullptr, *d_prefix_pending = nullptr, *d_sizes = nullptr;
+    std::vector<uint32_t> h_sizes;       // [n_samples][n_chunks]
+    uint64_t total_bytes = 0;
+    float ms_site = 0, ms_gt = 0;
+};
+
+extern "C" {
+
+uint64_t hb_guess_chunk_records(uint64_t n_records) { return guess_chunk_records(n_records); }
+
+void hb_frames_free(hb_frames *f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->d_prefix); cudaFree(f->d_tail); cudaFree(f->d_frames);
+    cudaFree(f->d_prefix_len); cudaFree(f->d_prefix_pending); cudaFree(f->d_sizes);
+    delete f;
+}
+
+int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
+    if (!p || !out) return api_fail(HB_ERR_ARG, "null argument");
+    if (cudaSetDevice(p->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    const uint64_t n = p->h_st.n_records;
+    if (!p->d_gt[0] && n) return api_fail(HB_ERR_NOGT, "parse was made without genotypes");
+    hb_frames *f = new hb_frames();
+    f->device = p->device; f->stream = p->stream;
+    f->n_records = n; f->n_samples = p->n_samples;
+    f->cr = chunk_records ? chunk_records : guess_chunk_records(n);
+    f->n_chunks = n ? (n + f->cr - 1) / f->cr : 0;
+    *out = f;
+    if (!f->n_chunks || !f->n_samples) return HB_OK;
+    const uint32_t cr = (uint32_t)f->cr;
+    const uint32_t n_site = 33u * cr, n_gt = 2u * cr;
+    auto bound = [](uint32_t x) { return x + x / 255 + 64; };
+    const size_t smem_site = 16 + ((n_site + 19) & ~15u) + ((bound(n_site) + 15) & ~15u) + (2u << 12);
+    if (smem_site > 220 * 1024) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
+    f->prefix_cap = bound(n_site);
+    f->slot = (FRAME_FIXED + f->prefix_cap + bound(n_gt) + 15) & ~15u;
+    const uint32_t warp_smem = (kHist + ((n_gt + 19) & ~15u) + ((bound(n_gt) + 15) & ~15u) + (2u << 10) + 15) & ~15u;
+    int warps_per_cta = 8;
+    while (warps_per_cta > 1 && (size_t)warps_per_cta * warp_smem > 200 * 1024) warps_per_cta >>= 1;
+    if ((size_t)warps_per_cta * warp_smem > 220 * 1024) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
+    cudaError_t e;
+#define CUF(x) do { e = (x); if (e != cudaSuccess) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); } } while (0)
+    CUF(cudaMalloc(&f->d_prefix, f->n_chunks * (uint64_t)f->prefix_cap));
+    CUF(cudaMalloc(&f->d_tail, f->n_chunks * kHist));
+    CUF(cudaMalloc(&f->d_prefix_len, f->n_chunks * 4));
+    CUF(cudaMalloc(&f->d_prefix_pending, f->n_chunks * 4));
+    CUF(cudaMalloc(&f->d_sizes, f->n_chunks * (uint64_t)f->n_samples * 4));
+    CUF(cudaMalloc(&f->d_frames, f->n_chunks * (uint64_t)f->n_samples * f->slot));
+    cudaEvent_t ev[3];
+    for (auto &x : ev) cudaEventCreate(&x);
+    SiteArgs4 sa;
+    sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
+    sa.n_records = n; sa.cr = cr; sa.prefix = f->d_prefix; sa.prefix_cap = f->prefix_cap;
+    sa.prefix_len = f->d_prefix_len; sa.prefix_pending = f->d_prefix_pending; sa.tail = f->d_tail;
+    CUF(cudaFuncSetAttribute(site_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_site));
+    cudaEventRecord(ev[0], f->stream);
+    site_prefix_kernel<<<(unsigned)f->n_chunks, 256, smem_site, f->stream>>>(sa);
+    count_launch();
+    cudaEventRecord(ev[1], f->stream);
+    DonorArgs da;
+    da.gt0 = p->d_gt[0]; da.gt1 = p->d_gt[1]; da.gt_stride = p->gt_stride; da.n_records = n;
+    da.cr = cr; da.n_samples = f->n_samples; da.n_chunks = f->n_chunks;
+    da.prefix = f->d_prefix; da.prefix_cap = f->prefix_cap; da.prefix_len = f->d_prefix_len;
+    da.prefix_pending = f->d_prefix_pending; da.tail = f->d_tail;
+    da.frames = f->d_frames; da.slot = f->slot; da.sizes = f->d_sizes; da.warp_smem = warp_smem;
+    const size_t smem_donor = (size_t)warps_per_cta * warp_smem;
+    CUF(cudaFuncSetAttribute(donor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_donor));
+    const uint64_t warps = f->n_chunks * f->n_samples;
+    donor_frames_kernel<<<(unsigned)((warps + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, smem_donor,
+                          f->stream>>>(da);
+    count_launch();
+    cudaEventRecord(ev[2], f->stream);
+    f->h_sizes.resize(warps);
+    CUF(cudaMemcpyAsync(f->h_sizes.data(), f->d_sizes, warps * 4, cudaMemcpyDeviceToHost, f->stream));
+    CUF(cudaStreamSynchronize(f->stream));
+    CUF(cudaGetLastError());
+    cudaEventElapsedTime(&f->ms_site, ev[0], ev[1]);
+    cudaEventElapsedTime(&f->ms_gt, ev[1], ev[2]);
+    for (auto &x : ev) cudaEventDestroy(x);
+    f->total_bytes = 0;
+    for (uint32_t v : f->h_sizes) f->total_bytes += v;
+#undef CUF
+    return HB_OK;
+}
+
+int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
+    if (!f || !info) return api_fail(HB_ERR_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    info->n_records = f->n_records; info->n_chunks = f->n_chunks; info->chunk_records = f->cr;
+    info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
+    info->raw_bytes = 35ull * f->n_records * f->n_samples;
+    info->ms_site = f->ms_site; info->ms_gt = f->ms_gt;
+    return HB_OK;
+}
+
+int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *buf, uint64_t cap, uint64_t *total) {
+    if (!f) return api_fail(HB_ERR_ARG, "null handle");
+    if (s >= f->n_samples) return api_fail(HB_ERR_SAMPLE, "sample index out of range");
+    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    uint64_t tot = 0;
+    for (uint64_t c = 0; c < f->n_chunks; ++c) {
+        const uint32_t sz = f->h_sizes[(uint64_t)s * f->n_chunks + c];
+        if (sizes) sizes[c] = sz;
+        tot += sz;
+    }
+    if (total) *total = tot;
+    if (!buf) return HB_OK;
+    if (cap < tot) return api_fail(HB_ERR_ARG, "buffer too small");
+    uint64_t o = 0;
+    for (uint64_t c = 0; c < f->n_chunks; ++c) {
+        const uint32_t sz = f->h_sizes[(uint64_t)s * f->n_chunks + c];
+        cudaError_t e = cudaMemcpyAsync(buf + o, f->d_frames + (c * f->n_samples + s) * (uint64_t)f->slot, sz,
+                                        cudaMemcpyDeviceToHost, f->stream);
+        if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, cudaGetErrorString(e));
+        o += sz;
+    }
+    if (cudaStreamSynchronize(f->stream) != cudaSuccess) return api_fail(HB_ERR_CUDA, "D2H of frames failed");
+    return HB_OK;
+}
+
+}  // extern "C"

@@ -146,24 +146,22 @@ uint64_t hb_guess_chunk_records(uint64_t n_records);   /* h5py guess_chunk resta
  * D. Dataset: batched on-the-fly haplotype construction, replacing
  *    RandomHaplotypeDataset.encode_haplotypes + encode_sequence
  *    (src/datasets/haplotype_dataset.py:86-110, src/utils/common_utils.py:84-103).
- *    All pointers are DEVICE pointers.  For batch item b:
- *      window  = ref_seq[item_ref_off[b] + (0 .. item_len[b]))   ASCII bases (any case)
- *      records = rows [item_row_lo[b], item_row_hi[b]) of (start, ref, alt) -- sorted by start --
- *                with phases p1/p2 read at item_gt_off[b] + row
+ *    All pointers are DEVICE pointers; the per-item arrays hold DEVICE ADDRESSES, so the items of
+ *    one batch may come from different chromosomes and donors.  For batch item b:
+ *      window  = item_len[b] ASCII bases (any case) at address item_seq[b]
+ *      records = item_nrec[b] rows of the (donor, chrom) columns at item_start[b] (uint32, sorted),
+ *                item_ref[b] / item_alt[b] (uint8) and item_p1[b] / item_p2[b] (int8 phases)
  *      out     = hap1/hap2 [B][L][C] float32 one-hot; positions >= item_len[b] are all-zero rows
  * ------------------------------------------------------------------------------------------ */
 typedef struct hb_hap_batch {
     uint32_t B, L, C;
-    const uint8_t *ref_seq;          /* concatenated reference bases */
-    const uint64_t *item_ref_off;    /* [B] */
+    const uint64_t *item_seq;        /* [B] address of window position 0 in the reference sequence */
     const uint32_t *item_len;        /* [B] window length (<= L) */
     const uint32_t *item_win_start;  /* [B] genomic coordinate of window position 0 */
-    const uint32_t *start;           /* record columns (device) */
-    const uint8_t *ref, *alt;
-    const uint64_t *item_row_lo, *item_row_hi;  /* [B] record range of the item's (donor, chrom) */
-    const int8_t *p1, *p2;           /* phase planes */
-    const uint64_t *item_gt_off;     /* [B] offset added to the row index when reading p1/p2 */
-    const int8_t *lut;               /* [256] base byte -> class index (encode_spec order) */
+    const uint64_t *item_start;      /* [B] address of the record start column */
+    const uint64_t *item_ref, *item_alt, *item_p1, *item_p2;   /* [B] addresses of the other columns */
+    const uint64_t *item_nrec;       /* [B] records in those columns */
+    const int8_t *lut;               /* [256] base byte -> class index (encode_spec order), -1 = none */
     float *hap1, *hap2;              /* [B][L][C] */
     void *stream;
 } hb_hap_batch;

@@ -239,9 +239,11 @@ def calculate_midpoint_region(start, end, seq_length):
 
 def base_to_index(seq: np.ndarray, encode_spec) -> np.ndarray:
     """Intent of common_utils.py:84-103: upper-case, anything outside ACGT -> N, index in
-    encode_spec key order (repair R3; the reference code returns all zeros)."""
+    encode_spec key order (repair R3; the reference code returns all zeros).  A spec
+    without an "N" key gives -1 = an all-zero one-hot row, which is what reindex(columns=base_list)
+    at :86 produces for a category that is not a column."""
     spec = parse_encode_dict(encode_spec)
-    lut = np.full(256, spec.get("N", len(spec) - 1), dtype=np.int8)
+    lut = np.full(256, spec.get("N", -1), dtype=np.int8)
     for b in "ACGT":
         if b in spec:
             lut[ord(b)] = spec[b]

@@ -1,0 +1,112 @@
+"""GPU parity tests for kernel 4: byte-shuffle + LZ4 + Blosc2 chunk/cframe framing.
+
+north_star bar: decompressed chunks bit-exact.  Each frame produced on the GPU is decoded by the
+oracle's independent cframe -> chunk -> LZ4 -> unshuffle path and compared with the 35-byte record
+array the reference would have handed to h5py (vcf_to_h5.py:119-129); the LZ4 payload is also fed
+to the stock liblz4 (ctypes) when the shared library is present."""
+import ctypes
+import ctypes.util
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(built):
+    from haplohyped_varawareml_b200 import capi as c
+    return c
+
+
+def _stock_lz4():
+    for name in ("liblz4.so.1", ctypes.util.find_library("lz4")):
+        if not name:
+            continue
+        try:
+            L = ctypes.CDLL(name)
+            L.LZ4_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+            return L
+        except OSError:
+            continue
+    return None
+
+
+def _expected_chunks(ora, s, cr):
+    rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"],
+                                      ora["gt0"][s], ora["gt1"][s])
+    raw = rec.tobytes()
+    n_chunks = (ora["n"] + cr - 1) // cr
+    raw += b"\0" * (n_chunks * cr * 35 - len(raw))          # HDF5 edge chunks are zero-filled to full size
+    return [raw[k * cr * 35:(k + 1) * cr * 35] for k in range(n_chunks)]
+
+
+def _check(capi, text, n_samples, region, chunk_records, samples_to_check):
+    ora = oracle.parse_text(text, "*", region)
+    p = capi.Parse.from_host(synth.body_of(text), n_samples, region=region)
+    fr = p.compress(chunk_records)
+    info = fr.info
+    cr = int(info.chunk_records)
+    if chunk_records == 0:
+        assert cr == oracle.guess_chunk_1d(ora["n"])
+    assert info.n_chunks == (ora["n"] + cr - 1) // cr
+    lz4 = _stock_lz4()
+    total = 0
+    for s in samples_to_check:
+        frames = fr.sample(s)
+        exp = _expected_chunks(ora, s, cr)
+        assert len(frames) == len(exp)
+        for f, e in zip(frames, exp):
+            got = oracle.cframe_decode(f, len(e)).tobytes()
+            assert got == e, "decompressed chunk differs"
+            total += len(f)
+            # header fields a stock reader relies on
+            assert f[1:10] == b"\xa8b2frame\0" and struct.unpack(">q", f[16:24])[0] == len(f)
+            assert struct.unpack(">i", f[48:52])[0] == 35 and f[97] == 5 and f[99] & 0x10
+            if lz4 is not None:
+                csize = struct.unpack("<i", f[97 + 36:97 + 40])[0]
+                payload = f[97 + 40:97 + 40 + csize]
+                if csize == len(e):                      # Blosc convention: csize == size means stored raw
+                    assert payload == oracle.shuffle(e, 35).tobytes()
+                    continue
+                out = ctypes.create_string_buffer(len(e))
+                n = lz4.LZ4_decompress_safe(payload, out, len(payload), len(e))
+                assert n == len(e), "stock liblz4 rejected the block"
+                assert out.raw == oracle.shuffle(e, 35).tobytes()
+    return info, total
+
+
+def test_fixture_chunks_roundtrip(capi, golden_dir):
+    import gzip, os
+    text = gzip.open(os.path.join(golden_dir, "chr22.filtered.vcf.gz")).read()
+    info, total = _check(capi, text, 3, "chr22", 0, [0, 1, 2])
+    assert info.chunk_records == 250 and info.n_chunks == 4       # h5py auto-chunk for 1000 x 35 B
+    assert total < 3 * 35 * 1000                                    # it does compress
+
+
+@pytest.mark.parametrize("chunk_records", [0, 64, 100, 1075])
+def test_random_vcf_chunks_roundtrip(capi, chunk_records):
+    text, samples = synth.random_vcf(900, 37, seed=21, fmt="GT", kinds="mixed", multidigit=False)
+    _check(capi, text, len(samples), "chr22", chunk_records, [0, 5, 36])
+    _check(capi, text, len(samples), "", chunk_records, [1])         # several CHROM values, long contig name truncated to S5
+
+
+def test_synthetic_shapes_chunks_roundtrip(capi):
+    for mix in (0, 1):
+        spec = capi.synth_spec(6000, 130, seed=5 + mix, mix=mix)
+        text = capi.synth_header(spec) + capi.synth_host(spec)
+        info, total = _check(capi, text, spec.n_samples, "chr22", 0, [0, 64, 129])
+        assert info.total_bytes < info.raw_bytes
+
+
+def test_tiny_and_empty(capi):
+    S = ["a", "b"]
+    one = (synth.header(S) + "chr22\t5\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1|1\n").encode()
+    _check(capi, one, 2, "chr22", 0, [0, 1])
+    p = capi.Parse.from_host(synth.body_of(one), 2, region="chrNope")
+    fr = p.compress(0)
+    assert fr.info.n_chunks == 0 and fr.info.total_bytes == 0
