@@ -66,11 +66,11 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
-    "hb_parse_host_text", "hb_parse_device_text", "hb_parse_rerun", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_compress_records", "hb_frames_get_info", "hb_frames_fetch_sample", "hb_frames_free",
-    "hb_guess_chunk_records",
+    "hb_guess_chunk_records", "hb_decode_frames",
     "hb_encode_haplotypes",
     "hb_synth_body_bytes", "hb_synth_header", "hb_synth_device", "hb_synth_host",
 ]
@@ -92,6 +92,8 @@ def lib():
         L.hb_records_free.argtypes = [C.POINTER(Records)]
         L.hb_parse_host_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_device_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
+        L.hb_parse_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.hb_parse_samples.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_parse_rerun.argtypes = [C.c_void_p]
         L.hb_parse_get_info.argtypes = [C.c_void_p, C.POINTER(ParseInfo)]
         L.hb_parse_fetch_sites.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -109,6 +111,7 @@ def lib():
             L.hb_frames_free.argtypes = [C.c_void_p]
             L.hb_guess_chunk_records.argtypes = [C.c_uint64]
             L.hb_guess_chunk_records.restype = C.c_uint64
+            L.hb_decode_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
         L.hb_encode_haplotypes.argtypes = [C.POINTER(HapBatch)]
         L.hb_synth_body_bytes.argtypes = [C.POINTER(SynthSpec)]
         L.hb_synth_body_bytes.restype = C.c_uint64
@@ -172,6 +175,19 @@ class Parse:
         o = cls._opts(n_samples, region, end_is_int, want_gt, device, tokenizer, stream)
         check(lib().hb_parse_device_text(d_ptr, nbytes, C.byref(o), C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def from_file(cls, path: str, region="", want_gt=True, device=0):
+        h = C.c_void_p()
+        check(lib().hb_parse_file(path.encode(), (region or "").encode(), int(want_gt), device, C.byref(h)))
+        return cls(h)
+
+    def sample_names(self):
+        n, ln = C.c_uint32(), C.c_uint64()
+        check(lib().hb_parse_samples(self._h, C.byref(n), None, 0, C.byref(ln)))
+        buf = C.create_string_buffer(max(1, ln.value))
+        check(lib().hb_parse_samples(self._h, C.byref(n), buf, ln.value, C.byref(ln)))
+        return [x.decode() for x in buf.raw[:ln.value].split(b"\0")[:n.value]]
 
     def rerun(self):
         check(lib().hb_parse_rerun(self._h))
@@ -308,6 +324,19 @@ def load_vcf_columns(path: str, sample: str, chrom: str = ""):
         return d
     finally:
         lib().hb_records_free(C.byref(r))
+
+
+def decode_frames(frames, chunk_nbytes: int, planar: bool = False, device: int = 0) -> np.ndarray:
+    """Stored HDF5 chunks (Blosc2 cframes) -> uint8 [n_frames, chunk_nbytes], decoded on the GPU."""
+    n = len(frames)
+    out = np.empty((n, chunk_nbytes), np.uint8)
+    if n == 0:
+        return out
+    offs = np.zeros(n + 1, np.uint64)
+    offs[1:] = np.cumsum([len(f) for f in frames])
+    blob = np.frombuffer(b"".join(bytes(f) for f in frames), np.uint8)
+    check(lib().hb_decode_frames(blob.ctypes.data, offs.ctypes.data, n, chunk_nbytes, out.ctypes.data, int(planar), device))
+    return out
 
 
 def synth_spec(n_variants, n_samples, seed=42, chrom="chr22", first_pos=10_000_000, pos_step=35, mix=0) -> SynthSpec:

@@ -734,3 +734,34 @@ void hb_cache_clear(void) {
 const char *hb_last_error(void) { return g_err.c_str(); }
 const char *hb_version(void) { return "haplo_b200 0.1 (sm_100a)"; }
 uint64_t hb_kernel_launches(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------------
+// File-level parse without the per-sample cache: what the converter (vcf_to_h5 mirror) drives.
+// ---------------------------------------------------------------------------------------------
+int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int device, hb_parse **out) {
+    if (!in_vcf || !out) return fail(HB_ERR_ARG, "null argument");
+    FileText ft;
+    TRY(read_vcf(in_vcf, ft));
+    hb_parse_opts o;
+    memset(&o, 0, sizeof o);
+    o.n_samples = (uint32_t)ft.samples.size();
+    o.region = region;
+    o.end_is_int = ft.end_is_int;
+    o.want_gt = want_gt;
+    o.device = device;
+    TRY(hb_parse_host_text(ft.data.data() + ft.body, ft.data.size() - ft.body, &o, out));
+    (*out)->samples = ft.samples;
+    return HB_OK;
+}
+
+int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    if (n) *n = (uint32_t)p->samples.size();
+    uint64_t used = 0;
+    for (const std::string &s : p->samples) {
+        if (names && used + s.size() + 1 <= cap) memcpy(names + used, s.c_str(), s.size() + 1);
+        used += s.size() + 1;
+    }
+    if (len) *len = used;
+    return HB_OK;
+}

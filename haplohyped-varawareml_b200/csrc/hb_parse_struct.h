@@ -51,5 +51,6 @@ struct hb_parse {
     // chrom runs (host)
     std::vector<uint64_t> run_rows;
     std::vector<std::string> run_names;
+    std::vector<std::string> samples;   // sample names when the parse was made from a file
 };
 

@@ -466,3 +466,181 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *b
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// Read side: Blosc2 cframe -> chunk -> LZ4 -> un-shuffle, one warp per HDF5 chunk.
+// Replaces, for VCFH5Reader.fetch_genotypes (src/utils/h5_reader.py:37-41), what h5py + the Blosc2
+// filter do when a `snp_data` dataset is read.  Accepts what stock c-blosc2 writes for this path
+// too (several blocks per chunk, LZ4/LZ4HC streams, raw streams, zero-run streams, memcpyed chunks);
+// anything else sets the frame's status to non-zero.
+// =============================================================================================
+namespace hb {
+
+__device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
+    return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint64_t ld_be(const uint8_t *p, int nb) {
+    uint64_t v = 0;
+    for (int i = 0; i < nb; ++i) v = (v << 8) | p[i];
+    return v;
+}
+
+// LZ4 block decode by one warp: sequences are walked in lock-step, bytes are copied 32 per step.
+// dst is global memory written and re-read by different lanes: reads go through L2 (__ldcg).
+__device__ bool warp_lz4_decode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap) {
+    const int lane = threadIdx.x & 31;
+    uint32_t ip = 0, op = 0;
+    if (n == 0) return false;
+    for (;;) {
+        if (ip >= n) return false;
+        const uint32_t tok = src[ip++];
+        uint32_t ll = tok >> 4;
+        if (ll == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ll += b; } while (b == 255); }
+        if (ip + ll > n || op + ll > cap) return false;
+        for (uint32_t i = lane; i < ll; i += 32) dst[op + i] = src[ip + i];
+        ip += ll; op += ll;
+        if (ip == n) break;
+        if (ip + 2 > n) return false;
+        const uint32_t off = src[ip] | ((uint32_t)src[ip + 1] << 8);
+        ip += 2;
+        if (off == 0 || off > op) return false;
+        uint32_t ml = tok & 15;
+        if (ml == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ml += b; } while (b == 255); }
+        ml += 4;
+        if (op + ml > cap) return false;
+        __syncwarp();
+        // periodic copy: dst[op+i] = dst[op-off + i % off] only reads bytes written before this match
+        for (uint32_t i = lane; i < ml; i += 32) {
+            const uint32_t k = off >= ml ? i : i % off;
+            dst[op + i] = __ldcg(dst + op - off + k);
+        }
+        op += ml;
+        __syncwarp();
+    }
+    __syncwarp();
+    return op == cap;
+}
+
+__global__ void __launch_bounds__(256)
+decode_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restrict__ offsets, uint64_t n_frames,
+                     uint32_t chunk_nbytes, uint8_t *__restrict__ tmp, uint8_t *__restrict__ out, int planar,
+                     int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= n_frames) return;
+    const uint8_t *f = frames + offsets[wid];
+    const uint64_t flen = offsets[wid + 1] - offsets[wid];
+    uint8_t *t = tmp + wid * (uint64_t)chunk_nbytes;
+    uint8_t *o = out + wid * (uint64_t)chunk_nbytes;
+    int err = 0;
+    // ---- cframe header
+    if (flen < 87 + 35 || f[1] != 0xa8 || f[2] != 'b' || f[3] != '2' || f[4] != 'f' || f[10] != 0xd2) err = 1;
+    uint64_t hlen = 0, nbytes = 0, cbytes = 0;
+    if (!err) {
+        hlen = ld_be(f + 11, 4); nbytes = ld_be(f + 30, 8); cbytes = ld_be(f + 39, 8);
+        if (hlen < 87 || hlen + cbytes > flen || nbytes != chunk_nbytes) err = 2;
+    }
+    uint32_t typesize = 1;
+    if (!err) {
+        const uint8_t *c = f + hlen;                         // the (single) Blosc2 chunk
+        const uint32_t flags = c[2];
+        typesize = c[3];
+        const uint32_t cn = ld_le32(c + 4), bs = ld_le32(c + 8), ccb = ld_le32(c + 12);
+        const bool ext = (flags & 1) && (flags & 4);
+        const uint32_t hdr = ext ? 32 : 16;
+        bool shuffle = !ext && (flags & 1);
+        if (ext) for (int i = 0; i < 6; ++i) { if (c[16 + i] == 1) shuffle = true; else if (c[16 + i] != 0) err = 3; }
+        if (cn != chunk_nbytes || ccb > cbytes || bs == 0 || typesize == 0) err = 4;
+        if (!err && (flags & 2)) {                           // memcpyed
+            for (uint32_t i = lane; i < cn; i += 32) t[i] = c[hdr + i];
+            shuffle = false;
+        } else if (!err) {
+            if ((flags >> 5) != 1) err = 5;                  // LZ4 / LZ4HC codec format
+            if (ext && ((c[31] >> 4) & 7)) err = 6;          // special chunks
+            const bool dont_split = flags & 0x10;
+            const uint32_t nblocks = (cn + bs - 1) / bs;
+            for (uint32_t b = 0; b < nblocks && !err; ++b) {
+                const uint32_t bsize = (b == nblocks - 1 && cn % bs) ? cn % bs : bs;
+                const bool leftover = (b == nblocks - 1) && (cn % bs);
+                const uint32_t nstreams = (!dont_split && !leftover) ? typesize : 1;
+                const uint32_t ne = bsize / nstreams;
+                uint32_t ip = ld_le32(c + hdr + 4 * b);
+                for (uint32_t s = 0; s < nstreams && !err; ++s) {
+                    if (ip + 4 > ccb) { err = 7; break; }
+                    const int32_t cs = (int32_t)ld_le32(c + ip);
+                    ip += 4;
+                    uint8_t *d = t + (uint64_t)b * bs + (uint64_t)s * ne;
+                    if (cs == 0) { for (uint32_t i = lane; i < ne; i += 32) d[i] = 0; }
+                    else if (cs < 0 || ip + (uint32_t)cs > ccb) err = 8;
+                    else if ((uint32_t)cs == ne) { for (uint32_t i = lane; i < ne; i += 32) d[i] = c[ip + i]; ip += cs; }
+                    else { if (!warp_lz4_decode(c + ip, (uint32_t)cs, d, ne)) err = 9; ip += cs; }
+                    __syncwarp();
+                }
+            }
+            // Blosc shuffles per block; this path only un-shuffles the single-block layout planar -> AoS
+            if (!err && shuffle && nblocks != 1 && !planar) {
+                // several blocks: un-shuffle each block on its own
+                for (uint32_t b = 0; b < nblocks; ++b) {
+                    const uint32_t bsize = (b == nblocks - 1 && cn % bs) ? cn % bs : bs;
+                    const uint32_t ne = bsize / typesize;
+                    const uint8_t *sb = t + (uint64_t)b * bs;
+                    uint8_t *ob = o + (uint64_t)b * bs;
+                    for (uint32_t i = lane; i < ne * typesize; i += 32) ob[i] = __ldcg(sb + (i % typesize) * ne + i / typesize);
+                    for (uint32_t i = ne * typesize + lane; i < bsize; i += 32) ob[i] = __ldcg(sb + i);
+                }
+                if (lane == 0) status[wid] = 0;
+                return;
+            }
+            if (!err && !shuffle) planar = 1;                // nothing to undo
+        }
+    }
+    __syncwarp();
+    if (!err) {
+        if (planar) { for (uint32_t i = lane; i < chunk_nbytes; i += 32) o[i] = __ldcg(t + i); }
+        else {
+            const uint32_t ne = chunk_nbytes / typesize;
+            for (uint32_t i = lane; i < ne * typesize; i += 32) o[i] = __ldcg(t + (i % typesize) * ne + i / typesize);
+            for (uint32_t i = ne * typesize + lane; i < chunk_nbytes; i += 32) o[i] = __ldcg(t + i);
+        }
+    }
+    if (lane == 0) status[wid] = err;
+}
+
+}  // namespace hb
+
+extern "C" int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, uint64_t n_frames,
+                                uint64_t chunk_nbytes, uint8_t *out, int planar, int device) {
+    if (!n_frames) return HB_OK;
+    if (!frames || !offsets || !out || chunk_nbytes == 0 || chunk_nbytes > 0x7fffffffull) return api_fail(HB_ERR_ARG, "bad argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return api_fail(HB_ERR_CUDA, "no CUDA device: libhaplo_b200 has no CPU fallback");
+    if (cudaSetDevice(device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    const uint64_t total = offsets[n_frames];
+    uint8_t *d_frames = nullptr, *d_tmp = nullptr, *d_out = nullptr;
+    uint64_t *d_off = nullptr;
+    int *d_status = nullptr;
+    std::vector<int> status(n_frames);
+    int rc = HB_OK;
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cudaMalloc(&d_frames, total + 64));
+    ck(cudaMalloc(&d_off, (n_frames + 1) * 8));
+    ck(cudaMalloc(&d_tmp, n_frames * chunk_nbytes));
+    ck(cudaMalloc(&d_out, n_frames * chunk_nbytes));
+    ck(cudaMalloc(&d_status, n_frames * sizeof(int)));
+    if (e == cudaSuccess) {
+        ck(cudaMemcpy(d_frames, frames, total, cudaMemcpyHostToDevice));
+        ck(cudaMemcpy(d_off, offsets, (n_frames + 1) * 8, cudaMemcpyHostToDevice));
+        decode_frames_kernel<<<(unsigned)((n_frames + 7) / 8), 256>>>(d_frames, d_off, n_frames, (uint32_t)chunk_nbytes,
+                                                                     d_tmp, d_out, planar, d_status);
+        count_launch();
+        ck(cudaGetLastError());
+        ck(cudaMemcpy(out, d_out, n_frames * chunk_nbytes, cudaMemcpyDeviceToHost));
+        ck(cudaMemcpy(status.data(), d_status, n_frames * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_frames); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_out); cudaFree(d_status);
+    if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    for (uint64_t i = 0; i < n_frames; ++i)
+        if (status[i]) { rc = api_fail(HB_ERR_IO, "corrupt or unsupported Blosc2 frame (chunk " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")"); break; }
+    return rc;
+}

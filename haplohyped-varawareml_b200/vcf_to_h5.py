@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's conversion driver and CLI (src/haplohyped/vcf_to_h5.py).
+
+Same class, constructor arguments, method names, click options, input naming
+(`{vcf}/chr{N}.filtered.vcf.gz`, N = 1..22, :51,:151), output path (`{outdir}/{cohort}.h5`, :161),
+group / dataset names (`donor_{id}/chr_{N}/snp_data`, :132-134), record dtype (:119-127) and filter
+(32001 with opts (2,2,0,0,5,1,2), :135).
+
+What changes is the shape of the work.  The reference calls `parse_vcf.load_vcf` once per (donor,
+chromosome) -- S whole-file scans per chromosome -- then builds records in two per-record Python
+loops, lets h5py/hdf5plugin compress them on the CPU into one temporary file each and copies every
+temporary file into the final one (:98-135,:154-180).  Here one chromosome file is parsed ONCE on the
+GPU for all donors (`hb_parse_file`), kernel 4 emits the Blosc2 frames of every donor's chunks
+(`hb_compress_records`), and the frames are stored as-is (HDF5 direct chunk write) straight into the
+final file; the 35-byte records are never materialised on the host.
+
+Documented deviations (each replaces a crash or a silent loss in the reference):
+a chromosome file that does not exist is skipped with a warning (the reference dereferences NULL);
+a donor that is not in the VCF header is reported and skipped (the reference's worker exception
+vanishes inside `executor.map`); `tmp_files/` is still created and removed but never used.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import shutil
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import capi
+from .container import open_h5
+from .h5_reader import RECORD_DTYPE
+
+logger = logging.getLogger(__name__)
+
+
+def _configure_logging():
+    """The reference configures this at import (vcf_to_h5.py:17-25); here only the CLI does."""
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(name)s - %(levelname)s - %(message)s",
+                        handlers=[logging.FileHandler("haplohyped.log"), logging.StreamHandler()])
+
+
+class _ChromParse:
+    """One chromosome file: device-resident parse + Blosc2 frames of every donor's chunks."""
+
+    def __init__(self, data_path: str, chromosome: int, device: int):
+        self.parse = capi.Parse.from_file(data_path, region=f"chr{chromosome}", want_gt=True, device=device)
+        self.samples = self.parse.sample_names()
+        self.index = {s: i for i, s in enumerate(self.samples)}
+        info = self.parse.info
+        self.n_records = int(info.n_records)
+        self.ploidy_err, self.badgt_err = self.parse.sample_errors()
+        self.frames = self.parse.compress(0) if self.n_records else None
+        self.chunk_records = int(self.frames.info.chunk_records) if self.frames else 0
+
+    def donor_frames(self, donor_id: str):
+        if donor_id not in self.index:
+            raise RuntimeError("Error parsing VCF file: the 1-th sample are not in the VCF.\nparameter samples:" + donor_id)
+        s = self.index[donor_id]
+        if self.badgt_err[s]:
+            raise RuntimeError("Error parsing VCF file: Couldn't read GT data: value not a number or '.'")
+        if self.ploidy_err[s]:
+            raise RuntimeError("Error parsing VCF file: ploidy != 2 (reference: assert(var.ploidy() == 2), parse_vcf.cpp:46)")
+        return self.frames.sample(s) if self.frames else []
+
+    def close(self):
+        if self.frames:
+            self.frames.close()
+        self.parse.close()
+
+
+class VCFtoHDF5Converter:
+    def __init__(self, cohort_name: str, vcf_dir: str, out_dir: str, sample_list_path: str, cores: int,
+                 cxx_threads: int, device: int = 0, chromosomes=None, backend: Optional[str] = None):
+        self.cohort_name = cohort_name
+        self.vcf_dir = vcf_dir
+        self.out_dir = out_dir
+        self.sample_list_path = sample_list_path
+        self.cores = cores
+        self.cxx_threads = cxx_threads            # kept for interface parity; a no-op in the reference too
+        self.device = device
+        self.backend = backend
+        self.donor_ids = self.read_sample_list(sample_list_path)
+        self.chromosomes = range(1, 23) if chromosomes is None else chromosomes
+        self.tmp_dir = os.path.join(out_dir, "tmp_files")
+        os.makedirs(self.tmp_dir, exist_ok=True)
+        self._out = None
+        self._chrom: Dict[int, _ChromParse] = {}
+        self.stats = {"datasets": 0, "records": 0, "stored_bytes": 0, "skipped_files": 0, "skipped_donors": 0}
+
+    def read_sample_list(self, sample_list_path: str) -> List[str]:
+        try:
+            with open(sample_list_path, "r") as f:
+                return [line.strip() for line in f]
+        except FileNotFoundError as e:
+            logger.error(f"Sample list file not found: {e}")
+            raise
+        except Exception as e:
+            logger.error(f"An error occurred while reading the sample list: {e}")
+            raise
+
+    # -- output file, opened lazily so that single-call use of genotype_vcf_to_hdf5 works too
+    def _final(self):
+        if self._out is None:
+            os.makedirs(self.out_dir, exist_ok=True)
+            self._out = open_h5(os.path.join(self.out_dir, f"{self.cohort_name}.h5"), "w", backend=self.backend)
+        return self._out
+
+    def _chrom_parse(self, data_path: str, chromosome: int) -> _ChromParse:
+        cp = self._chrom.get(chromosome)
+        if cp is None:
+            cp = _ChromParse(data_path, chromosome, self.device)
+            self._chrom[chromosome] = cp
+        return cp
+
+    def genotype_vcf_to_hdf5(self, data_path: str, donor_id: str, chromosome: int) -> None:
+        """One (donor, chromosome) dataset -- the reference's unit of work (:79-140)."""
+        logger.info(f"Processing VCF file {data_path} for chromosome {chromosome} and donor {donor_id}")
+        try:
+            if donor_id:
+                cp = self._chrom_parse(data_path, chromosome)
+                frames = cp.donor_frames(donor_id)
+                chunk = cp.chunk_records or int(capi.lib().hb_guess_chunk_records(max(1, cp.n_records)))
+                self._final().write_chunked(f"donor_{donor_id}/chr_{chromosome}/snp_data", RECORD_DTYPE, cp.n_records,
+                                            chunk, frames)
+                self.stats["datasets"] += 1
+                self.stats["records"] += cp.n_records
+                self.stats["stored_bytes"] += sum(len(f) for f in frames)
+                logger.info(f"Finished processing VCF file for donor {donor_id} and chromosome {chromosome}")
+        except Exception as e:
+            logger.error(f"An error occurred while processing VCF file: {e}")
+            raise
+
+    def process_chromosome(self, chromosome: int) -> None:
+        """All donors of one chromosome file: one GPU parse + one compression pass."""
+        vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
+        if not os.path.exists(vcf_file):
+            logger.warning(f"{vcf_file} does not exist; chromosome {chromosome} skipped")
+            self.stats["skipped_files"] += 1
+            return
+        for donor_id in self.donor_ids:
+            try:
+                self.genotype_vcf_to_hdf5(vcf_file, donor_id, chromosome)
+            except capi.HaploError:
+                raise                                   # the file itself is unreadable / malformed
+            except RuntimeError:
+                self.stats["skipped_donors"] += 1       # this donor only (unknown, haploid, bad GT)
+        cp = self._chrom.pop(chromosome, None)
+        if cp is not None:
+            cp.close()
+
+    def process_donor(self, donor_id: str) -> None:
+        """The reference's per-donor loop (:142-152), kept for callers that drive it directly."""
+        logger.info(f"Processing donor {donor_id}")
+        for chromosome in self.chromosomes:
+            vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
+            if not os.path.exists(vcf_file):
+                logger.warning(f"{vcf_file} does not exist; chromosome {chromosome} skipped")
+                continue
+            self.genotype_vcf_to_hdf5(vcf_file, donor_id, chromosome)
+
+    def merge_h5_files(self) -> None:
+        """Nothing to merge: datasets were written into the final file directly.  Closes it."""
+        final_h5_file = os.path.join(self.out_dir, f"{self.cohort_name}.h5")
+        self._final().close()
+        self._out = None
+        logger.info(f"Finished writing {final_h5_file}")
+
+    def run(self):
+        start_time = time.time()
+        try:
+            # chromosome-major: one device-resident parse is shared by every donor.  `cores` host
+            # threads overlap the BGZF inflate of the next files with the GPU work of the current one.
+            present = [c for c in self.chromosomes
+                       if os.path.exists(os.path.join(self.vcf_dir, f"chr{c}.filtered.vcf.gz"))]
+            self.stats["skipped_files"] += len(list(self.chromosomes)) - len(present)
+            for c in self.chromosomes:
+                if c not in present:
+                    logger.warning(f"chr{c}.filtered.vcf.gz does not exist in {self.vcf_dir}; skipped")
+            with ThreadPoolExecutor(max_workers=max(1, min(int(self.cores or 1), 2))) as executor:
+                parses = executor.map(lambda c: (c, self._safe_parse(c)), present)
+                for c, cp in parses:
+                    if cp is None:
+                        continue
+                    self._chrom[c] = cp
+                    self.process_chromosome(c)
+            merge_start_time = time.time()
+            self.merge_h5_files()
+            end_time = time.time()
+            logger.info(f"Time taken to merge HDF5 files: {end_time - merge_start_time:.2f} seconds")
+            logger.info(f"Total time taken: {end_time - start_time:.2f} seconds")
+        except Exception as e:
+            logger.error(f"An error occurred: {e}")
+            raise
+        finally:
+            for cp in self._chrom.values():
+                cp.close()
+            self._chrom.clear()
+            if self._out is not None:
+                self._out.close()
+                self._out = None
+            shutil.rmtree(self.tmp_dir, ignore_errors=True)
+
+    def _safe_parse(self, chromosome: int):
+        vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
+        try:
+            return _ChromParse(vcf_file, chromosome, self.device)
+        except capi.HaploError as e:
+            logger.error(f"An error occurred while processing VCF file: Error parsing VCF file: {e}")
+            self.stats["skipped_files"] += 1
+            return None
+
+
+def main(argv=None):
+    import click
+
+    @click.command()
+    @click.option("--cohort_name", required=True, type=str, help="Cohort specific name")
+    @click.option("--vcf", required=True, type=str, help="Path to VCF files directory")
+    @click.option("--outdir", required=True, type=str, help="Path to results save folder")
+    @click.option("--sample_list", required=True, type=str, help="Path to sample list file")
+    @click.option("--cores", default=os.cpu_count(), type=int, help="Number of CPU cores to use")
+    @click.option("--cxx_threads", default=4, type=int, help="Number of threads to use in the C++ code")
+    @click.option("--device", default=0, type=int, help="CUDA device ordinal")
+    def _main(cohort_name, vcf, outdir, sample_list, cores, cxx_threads, device):
+        _configure_logging()
+        VCFtoHDF5Converter(cohort_name=cohort_name, vcf_dir=vcf, out_dir=outdir, sample_list_path=sample_list,
+                           cores=cores, cxx_threads=cxx_threads, device=device).run()
+
+    return _main(args=argv, standalone_mode=argv is None)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,11 @@ typedef struct hb_parse_info {
 int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
 /* text already in HBM.  d_text must be 16-byte aligned with >= 64 readable bytes of slack after nbytes. */
 int hb_parse_device_text(const uint8_t *d_text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
+/* a whole .vcf / .vcf.gz (BGZF or plain gzip): header + body, all samples, no per-sample cache.
+ * What the vcf_to_h5 converter drives (src/haplohyped/vcf_to_h5.py:98-101 without the per-donor re-scan). */
+int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int device, hb_parse **out);
+/* sample names of a file-level parse, NUL-separated */
+int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */
 int hb_parse_rerun(hb_parse *p);
 int hb_parse_get_info(const hb_parse *p, hb_parse_info *info);
@@ -141,6 +146,12 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes,
                            uint64_t *total);
 void hb_frames_free(hb_frames *f);
 uint64_t hb_guess_chunk_records(uint64_t n_records);   /* h5py guess_chunk restated for 35-byte items */
+/* Read side (VCFH5Reader.fetch_genotypes, src/utils/h5_reader.py:37-41): n_frames stored HDF5 chunks
+ * (Blosc2 cframes; frame i = frames[offsets[i] .. offsets[i+1])) -> out[i * chunk_nbytes ...], decoded on the
+ * GPU (cframe -> chunk -> LZ4 -> un-shuffle).  planar != 0 keeps the byte-shuffled plane layout.
+ * Host pointers. */
+int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, uint64_t n_frames, uint64_t chunk_nbytes,
+                     uint8_t *out, int planar, int device);
 
 /* ------------------------------------------------------------------------------------------
  * D. Dataset: batched on-the-fly haplotype construction, replacing

@@ -1,0 +1,148 @@
+"""GPU parity tests for the write side end to end (vcf_to_h5 mirror -> HDF5 container) and the read
+side (VCFH5Reader -> GPU Blosc2 decode -> RandomHaplotypeDataset).
+
+Bar (north_star): record arrays read back from the file are bit-exact with what the reference would
+have stored -- np.array([tuple(row) ...], dtype=35-byte struct) of load_vcf's tuples
+(vcf_to_h5.py:101-129), restated by the oracle."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    from haplohyped_varawareml_b200 import capi, container, h5_reader, haplotype_dataset, vcf_to_h5
+    return capi, container, h5_reader, haplotype_dataset, vcf_to_h5
+
+
+def _expected_records(path, donor, chrom):
+    rows = oracle.load_vcf(path, donor, chrom)
+    return oracle.records_from_tuples(rows)
+
+
+def test_decode_frames_matches_oracle(mods):
+    capi = mods[0]
+    text, samples = synth.random_vcf(2600, 7, seed=5, fmt="GT", kinds="mixed")
+    ora = oracle.parse_text(text, "*", "chr22")
+    p = capi.Parse.from_host(synth.body_of(text), len(samples), region="chr22")
+    fr = p.compress(0)
+    cr = int(fr.info.chunk_records)
+    for s in (0, 3, 6):
+        frames = fr.sample(s)
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"],
+                                          ora["gt0"][s], ora["gt1"][s])
+        raw = rec.tobytes() + b"\0" * (len(frames) * cr * 35 - rec.nbytes)
+        got = capi.decode_frames(frames, cr * 35)
+        assert got.tobytes() == raw
+        planar = capi.decode_frames(frames, cr * 35, planar=True)
+        for k in range(len(frames)):
+            assert planar[k].tobytes() == oracle.shuffle(raw[k * cr * 35:(k + 1) * cr * 35], 35).tobytes()
+            assert oracle.cframe_decode(frames[k], cr * 35).tobytes() == got[k].tobytes()
+    # corrupt frames are rejected, not decoded into garbage
+    bad = bytearray(fr.sample(0)[0])
+    bad[3] ^= 0xff
+    with pytest.raises(capi.HaploError):
+        capi.decode_frames([bytes(bad)], cr * 35)
+    assert capi.decode_frames([], cr * 35).shape == (0, cr * 35)
+
+
+def test_fixture_through_cli_and_reader(mods, tmp_path, golden_dir):
+    """configs[0]: the reference's own fixture through the converter (chr22 only; chr1-21 absent -> skipped)."""
+    capi, container, h5_reader, hd, v2h = mods
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    src = os.path.join(golden_dir, "chr22.filtered.vcf.gz")
+    os.symlink(src, vdir / "chr22.filtered.vcf.gz")
+    out = tmp_path / "out"
+    conv = v2h.VCFtoHDF5Converter("cohort", str(vdir), str(out), os.path.join(golden_dir, "ipscs_samples_test.txt"), 4, 4)
+    assert len(conv.donor_ids) == 3 and os.path.isdir(out / "tmp_files")
+    conv.run()
+    assert not os.path.exists(out / "tmp_files") and os.path.exists(out / "cohort.h5")
+    assert conv.stats["datasets"] == 3 and conv.stats["skipped_files"] == 21
+    rd = h5_reader.VCFH5Reader(str(out / "cohort.h5"))
+    for d in conv.donor_ids:
+        got = rd.fetch_genotypes(d, 22)
+        exp = _expected_records(src, d, "chr22")
+        assert got.dtype == oracle.RECORD_DTYPE and len(got) == 1000
+        assert got.tobytes() == exp.tobytes()
+    with pytest.raises(KeyError):
+        rd.fetch_genotypes(conv.donor_ids[0], 1)
+    with pytest.raises(KeyError):
+        rd.fetch_genotypes("nobody", 22)
+    rd.close()
+
+
+def test_multi_chromosome_cohort(mods, tmp_path):
+    capi, container, h5_reader, hd, v2h = mods
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    samples = None
+    files = {}
+    for c, (nv, fmt, kinds) in {1: (1500, "GT", "phased"), 7: (2300, "GT:GQ:DP", "mixed"), 22: (900, "GT", "mixed")}.items():
+        text, samples = synth.random_vcf(nv, 11, seed=c, fmt=fmt, kinds=kinds, chrom=f"chr{c}", site_mix=True)
+        path = vdir / f"chr{c}.filtered.vcf.gz"
+        with gzip.open(path, "wb") as f:
+            f.write(text)
+        files[c] = str(path)
+    (vdir / "chr5.filtered.vcf.gz").write_bytes(gzip.compress(synth.header(samples).encode()))    # no records at all
+    donors = [samples[0], samples[4], "not-in-the-vcf", samples[10]]
+    (tmp_path / "donors.txt").write_text("\n".join(donors))
+    conv = v2h.VCFtoHDF5Converter("c2", str(vdir), str(tmp_path / "o"), str(tmp_path / "donors.txt"), 2, 4)
+    conv.run()
+    assert conv.stats["skipped_donors"] == 4 and conv.stats["datasets"] == 3 * 4
+    f = container.open_h5(str(tmp_path / "o" / "c2.h5"))
+    assert f.keys() == sorted(f"donor_{d}" for d in donors if d != "not-in-the-vcf")
+    assert f.keys(f"donor_{samples[0]}") == sorted(["chr_1", "chr_5", "chr_7", "chr_22"])
+    f.close()
+    rd = h5_reader.VCFH5Reader(str(tmp_path / "o" / "c2.h5"))
+    for d in (samples[0], samples[4], samples[10]):
+        for c, path in files.items():
+            got = rd.fetch_genotypes(d, c)
+            exp = _expected_records(path, d, f"chr{c}")
+            assert len(exp) > 100 and got.tobytes() == exp.tobytes()
+        assert len(rd.fetch_genotypes(d, 5)) == 0
+    rd.close()
+
+
+def test_dataset_from_files(mods, tmp_path):
+    """RandomHaplotypeDataset constructed exactly as the reference constructs it: four paths."""
+    capi, container, h5_reader, hd, v2h = mods
+    rng = np.random.default_rng(3)
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    texts = {}
+    for c in range(1, 23):
+        text, samples = synth.random_vcf(400, 5, seed=100 + c, fmt="GT", kinds="mixed", chrom=f"chr{c}", site_mix=False)
+        texts[c] = text
+        with gzip.open(vdir / f"chr{c}.filtered.vcf.gz", "wb") as f:
+            f.write(text)
+    (tmp_path / "samples.txt").write_text("\n".join(samples))
+    v2h.VCFtoHDF5Converter("g", str(vdir), str(tmp_path), str(tmp_path / "samples.txt"), 2, 4).run()
+    # reference chromosomes long enough to cover the variant positions (10.0 Mb + ...)
+    hi = max(int(oracle.parse_text(texts[c], "*", f"chr{c}")["start"].max()) for c in texts) + 3000
+    lo = 10_000_000
+    seqs = {f"chr{c}": rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=hi) for c in range(1, 23)}
+    with container.open_h5(str(tmp_path / "ref.h5"), "w") as f:
+        for k, v in seqs.items():
+            f.write_array(k, v.view("S1"))
+    bed = tmp_path / "r.bed"
+    bed.write_text("".join(f"chr1\t{s}\t{s + 500}\n" for s in rng.integers(lo, hi - 3000, 12)))
+    ds = hd.RandomHaplotypeDataset(str(bed), str(tmp_path / "g.h5"), str(tmp_path / "ref.h5"), str(tmp_path / "samples.txt"),
+                                   batch_size=6, seq_length=1500)
+    items = ds.draw()
+    h1, h2 = ds.encode_items(items)
+    spec = oracle.parse_encode_dict(None)
+    for b, (chrom, donor, ns, ne) in enumerate(items):
+        ora = oracle.parse_text(texts[chrom], donor, f"chr{chrom}")
+        a, bb = oracle.encode_haplotypes(seqs[f"chr{chrom}"][ns:ne], ora["start"], ora["ref"], ora["alt"],
+                                         ora["gt0"], ora["gt1"], ns, ne, spec)
+        assert np.array_equal(h1[b].cpu().numpy(), oracle.onehot(a, 5))
+        assert np.array_equal(h2[b].cpu().numpy(), oracle.onehot(bb, 5))
+    ds.close()
