@@ -32,7 +32,8 @@ class ParseInfo(C.Structure):
                 ("d_start", C.c_void_p), ("d_stop", C.c_void_p), ("d_ref", C.c_void_p), ("d_alt", C.c_void_p),
                 ("n_nonuniform", C.c_uint64), ("n_bad_gt", C.c_uint64), ("n_bad_cols", C.c_uint64),
                 ("n_nogt", C.c_uint64), ("tokenizer_used", C.c_int),
-                ("ms_tokenize", C.c_float), ("ms_sites", C.c_float), ("ms_decode", C.c_float)]
+                ("ms_tokenize", C.c_float), ("ms_sites", C.c_float), ("ms_decode", C.c_float),
+                ("walker_fallbacks", C.c_int)]
 
 
 class Records(C.Structure):

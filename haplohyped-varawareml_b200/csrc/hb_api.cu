@@ -104,6 +104,7 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_chrom5); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
     free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_ploidy);
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
+    free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     delete p;
 }
@@ -118,47 +119,37 @@ static int dev_alloc(T **p, uint64_t n) {
 }
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != HB_OK) return rc_; } while (0)
 
-// look at the first record of the body: FORMAT == "GT" -> newline-only tokenizer is enough
-static void probe_head(const uint8_t *h, size_t n, bool &gt_only, uint64_t &first_line_len) {
+// look at the first record of the body: FORMAT == "GT" -> newline-only tokenizer is enough;
+// and exactly 4 bytes per sample after the 9th tab -> the walker (hb_walk.cu) applies
+static void probe_head(const uint8_t *h, size_t n, uint32_t n_samples, bool &gt_only, bool &uniform,
+                       uint64_t &first_line_len) {
     gt_only = false;
+    uniform = false;
     first_line_len = 0;
-    size_t i = 0;
+    size_t i = 0, tab9 = 0;
     int f = 0;
     size_t fs = 0;
     for (; i < n; ++i) {
         if (h[i] == '\t' || h[i] == '\n') {
-            if (f == 8) gt_only = (i - fs == 2 && h[fs] == 'G' && h[fs + 1] == 'T');
+            if (f == 8) { gt_only = (i - fs == 2 && h[fs] == 'G' && h[fs + 1] == 'T'); tab9 = i; }
             if (h[i] == '\n') break;
             ++f;
             fs = i + 1;
         }
     }
-    if (i < n) first_line_len = i + 1;
+    if (i < n) {
+        first_line_len = i + 1;
+        size_t e = i;
+        if (e > 0 && h[e - 1] == '\r') --e;
+        uniform = gt_only && f >= 9 && e - tab9 == 4ull * n_samples;
+    }
 }
 
-static int run_parse(hb_parse *p) {
-    CU(cudaSetDevice(p->device));
-    Launch L{p->stream, p->sm_count};
+// ---- records located by the tokenizer (any text): kernels 1 and 2
+static int index_by_tokenizer(hb_parse *p, const Launch &L) {
     const uint64_t tile = tokenize_tile_bytes();
     const uint64_t n_tiles = (p->nbytes + tile - 1) / tile;
-    if (!p->d_st) TRY(dev_alloc(&p->d_st, 1));
-    CU(cudaMemsetAsync(p->d_st, 0, sizeof(DevStatus), p->stream));
-    memset(&p->h_st, 0, sizeof p->h_st);
-    p->ncp = (p->n_samples + kCP - 1) / kCP;
-    if (p->nbytes == 0) return HB_OK;
-
-    // ---- tokenizer mode + capacity estimate from the first record
-    if (!p->probed) {
-        uint8_t head[65536];
-        size_t hn = (size_t)std::min<uint64_t>(sizeof head, p->nbytes);
-        CU(cudaMemcpyAsync(head, p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
-        CU(cudaStreamSynchronize(p->stream));
-        bool gt_only; uint64_t l0;
-        probe_head(head, hn, gt_only, l0);
-        p->with_tabs = p->tokenizer == 2 || (p->tokenizer == 0 && !gt_only);
-        if (!p->want_gt) p->with_tabs = false;
-        p->first_line_len = l0 ? l0 : hn;
-        p->probed = true;
+    if (!p->d_cta) {
         // one contiguous range of tiles per persistent CTA, 2 CTAs per SM
         uint64_t want = std::min<uint64_t>((uint64_t)p->sm_count * 2, n_tiles);
         if (want > 1024) want = 1024;
@@ -200,9 +191,8 @@ static int run_parse(hb_parse *p) {
     p->n_lines = n_lines;
     LineIndex li{p->d_nl_after, p->d_cbase, p->n_cta, p->stage_cap};
 
-    // ---- sites
-    if (p->row_cap < n_lines || !p->d_start) {
-        uint64_t cap = n_lines;
+    if (p->row_cap < n_lines || !p->d_start || !p->d_sites_state) {
+        uint64_t cap = std::max(n_lines, p->row_cap);
         TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
         TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
         TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
@@ -210,12 +200,6 @@ static int run_parse(hb_parse *p) {
         TRY(dev_alloc(&p->d_sites_state, (cap + 255) / 256 + 1));
         p->row_cap = cap;
     }
-    if (!p->d_ploidy) {
-        TRY(dev_alloc(&p->d_ploidy, p->n_samples)); TRY(dev_alloc(&p->d_badgt, p->n_samples));
-        TRY(dev_alloc(&p->d_run_rows, hb_parse::kMaxRuns));
-    }
-    CU(cudaMemsetAsync(p->d_ploidy, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
-    CU(cudaMemsetAsync(p->d_badgt, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
     launch_sites(p->d_text, li, n_lines, p->n_samples, p->rg, p->end_is_int, p->want_gt, p->with_tabs,
                  p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_chrom5, p->d_rowinfo,
                  p->d_nu_rows, p->d_sites_state, p->d_st, L);
@@ -223,11 +207,87 @@ static int run_parse(hb_parse *p) {
     CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     CU(cudaGetLastError());
+    p->index_used = p->with_tabs ? 2 : 1;
+    return HB_OK;
+}
+
+// ---- records located by walking heads (uniform GT-only text): hb_walk.cu
+static int index_by_walker(hb_parse *p, const Launch &L) {
+    if (!p->d_wstart) {
+        uint32_t k = 16;
+        if (const char *e = getenv("HB_WALK_LINES")) { int v = atoi(e); if (v > 0 && v < 65536) k = (uint32_t)v; }
+        p->n_walkers = walk_plan(p->nbytes, p->first_line_len, k, &p->walk_range);
+        TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
+        TRY(dev_alloc(&p->d_wrow, p->n_walkers));
+        uint64_t *wc = nullptr;
+        TRY(dev_alloc(&wc, p->n_walkers));
+        p->d_wcount = wc;
+    }
+    CU(cudaEventRecord(p->ev[0], p->stream));
+    launch_walk_count(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
+                      p->d_wstart, p->d_wcount, p->d_wrow, p->d_st, L);
+    CU(cudaEventRecord(p->ev[1], p->stream));
+    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaGetLastError());
+    const uint64_t n_lines = p->h_st.n_lines, n_rec = p->h_st.n_records;
+    p->n_lines = n_lines;
+    if (p->row_cap < n_rec || !p->d_start) {
+        uint64_t cap = std::max(n_rec, p->row_cap);
+        TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
+        TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
+        TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
+        TRY(dev_alloc(&p->d_rowinfo, cap)); TRY(dev_alloc(&p->d_nu_rows, cap));
+        if (p->d_sites_state) { cudaFree(p->d_sites_state); p->d_sites_state = nullptr; }
+        p->row_cap = cap;
+    }
+    if (p->verify_cap < n_lines || !p->d_verify) { TRY(dev_alloc(&p->d_verify, n_lines)); p->verify_cap = n_lines; }
+    launch_walk_write(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
+                      p->d_wstart, p->d_wcount, p->d_wrow, p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs,
+                      p->d_chrom_len, p->d_chrom5, p->d_rowinfo, p->d_nu_rows, p->d_verify, p->verify_cap, p->d_st, L);
+    CU(cudaEventRecord(p->ev[2], p->stream));
+    p->index_used = 3;
+    return HB_OK;
+}
+
+static int run_parse(hb_parse *p) {
+    CU(cudaSetDevice(p->device));
+    Launch L{p->stream, p->sm_count};
+    if (!p->d_st) TRY(dev_alloc(&p->d_st, 1));
+    CU(cudaMemsetAsync(p->d_st, 0, sizeof(DevStatus), p->stream));
+    memset(&p->h_st, 0, sizeof p->h_st);
+    p->ncp = (p->n_samples + kCP - 1) / kCP;
+    if (p->nbytes == 0) return HB_OK;
+
+    // ---- how to locate the records, from the first one
+    if (!p->probed) {
+        uint8_t head[65536];
+        size_t hn = (size_t)std::min<uint64_t>(sizeof head, p->nbytes);
+        CU(cudaMemcpyAsync(head, p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        bool gt_only, uniform; uint64_t l0;
+        probe_head(head, hn, p->n_samples, gt_only, uniform, l0);
+        p->with_tabs = p->tokenizer == 2 || ((p->tokenizer == 0 || p->tokenizer == 3) && !gt_only);
+        if (!p->want_gt) p->with_tabs = false;
+        // walking pays when a record is much longer than its head (and needs the decoder to validate the jumps)
+        p->use_walker = p->want_gt && p->n_samples > 0 &&
+                        (p->tokenizer == 3 || (p->tokenizer == 0 && uniform && p->n_samples >= 256));
+        p->first_line_len = l0 ? l0 : hn;
+        p->probed = true;
+    }
+    if (!p->d_ploidy) {
+        TRY(dev_alloc(&p->d_ploidy, p->n_samples)); TRY(dev_alloc(&p->d_badgt, p->n_samples));
+        TRY(dev_alloc(&p->d_run_rows, hb_parse::kMaxRuns));
+    }
+    CU(cudaMemsetAsync(p->d_ploidy, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
+    CU(cudaMemsetAsync(p->d_badgt, 0, std::max<uint64_t>(1, p->n_samples) * 4, p->stream));
+    if (p->use_walker) TRY(index_by_walker(p, L));
+    else TRY(index_by_tokenizer(p, L));
     const uint64_t n_rec = p->h_st.n_records;
 
     // ---- GT decode
     if (p->want_gt && n_rec && p->n_samples) {
-        if (!p->with_tabs && p->h_st.n_nonuniform) {
+        if (p->index_used == 1 && p->h_st.n_nonuniform) {
             uint64_t n_nu = p->h_st.n_nonuniform;
             if (p->cp_rows < n_nu) { TRY(dev_alloc(&p->d_cp, n_nu * p->ncp)); p->cp_rows = n_nu; }
             CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
@@ -238,6 +298,13 @@ static int run_parse(hb_parse *p) {
         if (p->gt_bytes < bytes || p->gt_stride != stride) {
             TRY(dev_alloc(&p->d_gt[0], bytes)); TRY(dev_alloc(&p->d_gt[1], bytes));
             p->gt_bytes = bytes; p->gt_stride = stride;
+        }
+        if (p->index_used == 3 && p->h_st.n_nu_count) {
+            // walker: the count pass told the host how many kept records are not plain "\tX|Y" columns
+            uint64_t n_nu = p->h_st.n_nu_count;
+            if (p->cp_rows < n_nu) { TRY(dev_alloc(&p->d_cp, n_nu * p->ncp)); p->cp_rows = n_nu; }
+            CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
+            launch_index_columns(p->d_text, p->d_rowinfo, p->d_nu_rows, n_nu, p->d_cp, p->ncp, L);
         }
         launch_decode_gt(p->d_text, p->d_rowinfo, n_rec, p->n_samples, p->d_cp, p->ncp, p->d_gt[0], p->d_gt[1],
                          p->gt_stride, p->d_ploidy, p->d_badgt, p->d_st, L);
@@ -250,6 +317,13 @@ static int run_parse(hb_parse *p) {
     cudaEventElapsedTime(&p->ms_tok, p->ev[0], p->ev[1]);
     cudaEventElapsedTime(&p->ms_sites, p->ev[1], p->ev[2]);
     cudaEventElapsedTime(&p->ms_decode, p->ev[2], p->ev[3]);
+
+    if (p->index_used == 3 && (p->h_st.walk_broken || p->h_st.index_invalid)) {
+        // the text is not what the walker can prove exact: locate the records the plain way
+        p->use_walker = false;
+        ++p->walker_fallbacks;
+        return run_parse(p);
+    }
 
     // ---- CHROM runs -> names (a handful of tiny D2H copies)
     p->run_rows.clear(); p->run_names.clear();
@@ -341,7 +415,8 @@ int hb_parse_get_info(const hb_parse *p, hb_parse_info *info) {
     info->n_bad_gt = p->h_st.n_bad_gt;
     info->n_bad_cols = p->h_st.n_bad_cols;
     info->n_nogt = p->h_st.n_nogt;
-    info->tokenizer_used = p->with_tabs ? 2 : 1;
+    info->tokenizer_used = p->index_used;
+    info->walker_fallbacks = p->walker_fallbacks;
     info->ms_tokenize = p->ms_tok; info->ms_sites = p->ms_sites; info->ms_decode = p->ms_decode;
     return HB_OK;
 }

@@ -82,8 +82,11 @@ __device__ __noinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t
 // Returns (a0 & 0xff) << 8 | (a1 & 0xff) << 24.  A group that is not of that shape demotes its record
 // (*mode = 2) to the general path, which redoes the whole segment; records that were never on the
 // fast path (*mode != 1) just yield 0.
-__device__ __noinline__ uint32_t decode_group_slow(uint32_t w, int *mode) {
+// A '\n' inside a group means the span was not one record's samples (possible only when the records
+// were located by the walker, hb_walk.cu): the whole index is void and the caller falls back.
+__device__ __noinline__ uint32_t decode_group_slow(uint32_t w, int *mode, DevStatus *st) {
     if (*mode != 1) return 0;
+    if (has_byte(w, kNl4)) st->index_invalid = 1u;
     const uint32_t sep = (w >> 16) & 0xffu, x = (w >> 8) & 0xffu, y = w >> 24;
     bool ok = (w & 0xffu) == '\t' && (sep == '|' || sep == '/');
     uint32_t a0 = x - '0', a1 = y - '0';
@@ -209,7 +212,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + sm.addr[r]);
                 const uint32_t w = __funnelshift_r(colp[0], colp[1], sm.shft[r]);
                 if ((w ^ 0x307C3009u) & 0xFEFFFEFFu) {
-                    const uint32_t x = decode_group_slow(w, &sm.mode[r]);
+                    const uint32_t x = decode_group_slow(w, &sm.mode[r], st);
                     sm.out[0][s][r] = (uint8_t)(x >> 8);
                     sm.out[1][s][r] = (uint8_t)(x >> 24);
                 }

@@ -31,7 +31,11 @@ struct DevStatus {
     unsigned long long n_bad_cols;     // records whose column count != 9 + n_samples (or < 8 fields)
     unsigned long long n_nogt;         // kept records without a GT key / sample columns
     unsigned long long n_chrom_runs;
+    unsigned long long n_nu_count;     // walker count pass: kept rows that will need the general decode path
+    unsigned long long n_verify;       // walker: jumped-over spans the decoder will not validate
     unsigned int ticket;               // tile tickets of the site kernel
+    unsigned int walk_broken;          // walker: a chain did not land on the next walker's start
+    unsigned int index_invalid;        // a newline was found inside a span taken for one record's samples
 };
 
 // Per tokenizer CTA (one contiguous byte range each).
@@ -71,6 +75,16 @@ void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, 
                   uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt, uint64_t *d_chrom_abs, uint8_t *d_chrom_len,
                   uint64_t *d_chrom5, RowInfo *d_rowinfo, uint32_t *d_nu_rows, uint64_t *d_tile_state, DevStatus *d_st,
                   const Launch &L);
+// index-free record location for GT-only text (hb_walk.cu)
+uint32_t walk_plan(uint64_t nbytes, uint64_t first_line_len, uint32_t lines_per_walker, uint64_t *range_bytes);
+void launch_walk_count(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
+                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
+                       uint64_t *d_wrow, DevStatus *d_st, const Launch &L);
+void launch_walk_write(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
+                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
+                       uint64_t *d_wrow, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt,
+                       uint64_t *d_chrom_abs, uint8_t *d_chrom_len, uint64_t *d_chrom5, RowInfo *d_rowinfo,
+                       uint32_t *d_nu_rows, uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L);
 void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const uint8_t *d_chrom_len,
                        uint64_t n_rows, uint64_t *d_run_rows, uint64_t max_runs, DevStatus *d_st,
                        const Launch &L);

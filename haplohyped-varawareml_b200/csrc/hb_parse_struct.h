@@ -20,6 +20,14 @@ struct hb_parse {
     hb::RegionArg rg;
     int end_is_int = 0, want_gt = 1, tokenizer = 0;
     bool with_tabs = false;
+    bool use_walker = false;            // records located by walking heads (hb_walk.cu) instead of tokenizing
+    uint32_t n_walkers = 0;
+    uint64_t walk_range = 0;
+    uint64_t *d_wstart = nullptr, *d_wrow = nullptr, *d_verify = nullptr;
+    void *d_wcount = nullptr;
+    uint64_t verify_cap = 0;
+    int walker_fallbacks = 0;
+    int index_used = 0;                 // 1 newline tokenizer, 2 newline+tab tokenizer, 3 walker
     uint32_t ncp = 0;
 
     uint64_t *d_nl_after = nullptr; uint64_t nl_after_cap = 0;

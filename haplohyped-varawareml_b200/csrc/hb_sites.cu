@@ -9,6 +9,7 @@
 // dense row index from a ticketed single-pass decoupled look-back scan, so outputs are written
 // directly in row order (file order), ready for the decoder and for the shuffle stage.
 #include "hb_common.cuh"
+#include "hb_head.cuh"
 #include "hb_internal.h"
 
 namespace hb {
@@ -22,13 +23,7 @@ struct SiteArgs {
     uint32_t n_samples;
     RegionArg rg;
     int end_is_int, want_gt, cp_by_line;
-    uint32_t *start, *stop;
-    uint8_t *ref, *alt;
-    uint64_t *chrom_abs;
-    uint8_t *chrom_len;
-    uint64_t *chrom5;
-    RowInfo *rowinfo;
-    uint32_t *nu_rows;
+    SiteOut out;
     uint64_t *tile_state;
     DevStatus *st;
 };
@@ -57,12 +52,13 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
     const uint64_t tile = s_tile;
     const uint64_t line = tile * ST_THREADS + tid;
 
-    bool keep = false, uniform = false, has_samples = false, malformed = false;
-    uint32_t pos = 0, ref_len = 0, alt_len = 0, n_comma = 0, fmt_len = 0, chrom_len = 0;
-    uint8_t ref0 = 0, alt0 = 0;
-    int g = -1;
-    uint64_t ls = 0, le = 0, samp_abs = 0;
-    long long endval = -1;
+    bool keep = false, malformed = false;
+    HeadState h;
+    HeadVerdict v;
+    h.init();
+    v.keep = v.uniform = v.malformed = false;
+    v.start = v.stop = 0;
+    uint64_t ls = 0, le = 0;
 
     if (line < a.n_lines) {
         ls = line ? nl_after_global(a.li, s_cbase, line - 1) : 0;
@@ -70,91 +66,13 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
         const uint8_t *t = a.text;
         if (le > ls && t[le - 1] == '\r') --le;
         if (le > ls && t[ls] != '#') {
-            int f = 0;
-            bool chrom_ok = true, pos_digits = true;
-            // INFO END= state: 0 matching key, 1 in value, 2 skip to ';'
-            int ist = 0, kpos = 0;
-            long long ev = 0;
-            bool ev_any = false, end_seen = false;   // only the first END= key counts
-            // FORMAT key state
-            int ki = 0, kl = 0;
-            uint8_t k0 = 0, k1 = 0;
             uint64_t q = ls;
-            for (; q < le; ++q) {
-                uint8_t c = t[q];
-                if (c == '\t') {
-                    if (f == 7 && ist == 1 && ev_any) endval = ev;
-                    if (f == 8) { if (kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki; }
-                    ++f;
-                    if (f == 9) { samp_abs = q; has_samples = true; break; }
-                    continue;
-                }
-                switch (f) {
-                    case 0:
-                        if (a.rg.has_region) {
-                            if (chrom_len >= a.rg.chrom_len || (uint8_t)a.rg.chrom[chrom_len] != c) chrom_ok = false;
-                        }
-                        ++chrom_len;
-                        break;
-                    case 1:
-                        if (pos_digits && c >= '0' && c <= '9') pos = pos * 10u + (uint32_t)(c - '0');
-                        else pos_digits = false;
-                        break;
-                    case 3:
-                        if (ref_len == 0) ref0 = c;
-                        ++ref_len;
-                        break;
-                    case 4:
-                        if (alt_len == 0) alt0 = c;
-                        if (c == ',') ++n_comma;
-                        ++alt_len;
-                        break;
-                    case 7:
-                        if (c == ';') {
-                            if (ist == 1 && ev_any) endval = ev;
-                            ist = 0; kpos = 0; ev = 0; ev_any = false;
-                        } else if (ist == 0) {
-                            const char key[4] = {'E', 'N', 'D', '='};
-                            if (c == (uint8_t)key[kpos]) {
-                                if (++kpos == 4) { ist = end_seen ? 2 : 1; end_seen = true; }
-                            } else ist = 2;
-                        } else if (ist == 1) {
-                            if (c >= '0' && c <= '9') { ev = ev * 10 + (c - '0'); ev_any = true; }
-                            else { ist = 2; ev_any = false; }
-                        }
-                        break;
-                    case 8:
-                        ++fmt_len;
-                        if (c == ':') {
-                            if (kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki;
-                            ++ki; kl = 0;
-                        } else {
-                            if (kl == 0) k0 = c; else if (kl == 1) k1 = c;
-                            ++kl;
-                        }
-                        break;
-                    default: break;
-                }
-            }
-            if (!has_samples) {   // line ended inside field f
-                if (f == 7 && ist == 1 && ev_any) endval = ev;
-                if (f == 8 && kl == 2 && k0 == 'G' && k1 == 'T' && g < 0) g = ki;
-            }
-            if (f < 7) malformed = true;
-            else {
-                long long pos0 = (long long)pos - 1;
-                long long rlen = ref_len;
-                if (a.end_is_int && endval > pos0) rlen = endval - pos0;
-                bool in_region = true;
-                if (a.rg.has_region)
-                    in_region = chrom_ok && chrom_len == a.rg.chrom_len && pos0 < a.rg.end0 && pos0 + rlen > a.rg.beg0;
-                bool snp = ref_len <= 1 && n_comma == 0 && alt_len == 1 &&
-                           (alt0 == 'A' || alt0 == 'C' || alt0 == 'G' || alt0 == 'T');
-                keep = in_region && snp;
-                endval = pos0 + rlen;       // reuse: stop
-                if (has_samples)
-                    uniform = fmt_len == 2 && g == 0 && (le - samp_abs) == 4ull * a.n_samples;
-            }
+            for (; q < le; ++q)
+                if (h.feed(t[q], q, a.rg)) break;
+            if (!h.has_samples) h.finish_short();
+            v = judge_head(h, le, a.n_samples, a.rg, a.end_is_int);
+            keep = v.keep;
+            malformed = v.malformed;
         }
     }
 
@@ -201,41 +119,18 @@ __global__ void __launch_bounds__(ST_THREADS) sites_kernel(const SiteArgs a) {
     if (malformed) atomicAdd(&a.st->n_bad_cols, 1ull);
     if (!keep) return;
     const uint64_t row = s_base + before + __popc(bal & ((1u << lane) - 1u));
-    a.start[row] = (uint32_t)((long long)pos - 1);
-    a.stop[row] = (uint32_t)endval;
-    a.ref[row] = ref0;
-    a.alt[row] = alt0;
-    a.chrom_abs[row] = ls;
-    a.chrom_len[row] = (uint8_t)(chrom_len > 255 ? 255 : chrom_len);
-    {   // S5 field of the 35-byte record: first 5 CHROM bytes, NUL padded (silent truncation, vcf_to_h5.py:120)
-        uint64_t c5 = 0;
-        for (uint32_t k = 0; k < 5 && k < chrom_len; ++k) c5 |= (uint64_t)a.text[ls + k] << (8 * k);
-        a.chrom5[row] = c5;
-    }
-    RowInfo ri;
-    ri.samp_abs = samp_abs;
-    ri.samp_len = has_samples ? (uint32_t)(le - samp_abs) : 0u;
-    ri.cp_row = 0;
-    ri.pad = 0;
-    uint32_t gi = g < 0 ? 255u : (uint32_t)(g > 254 ? 254 : g);
-    ri.misc = gi | (uniform ? kRowUniform : 0u) | (has_samples ? kRowHasSamples : 0u);
-    if (a.want_gt) {
-        if (!has_samples || g < 0) atomicAdd(&a.st->n_nogt, 1ull);
-        else if (!uniform) {
-            unsigned long long slot = atomicAdd(&a.st->n_nonuniform, 1ull);
-            if (a.cp_by_line) {   // staged id of the line: (tokenizer CTA, local line) -- see hb_tokenize.cu
-                uint32_t cb = 0, jl = 0;
-                if (line) {
-                    uint32_t lo = 0, hi = a.li.n_cta;
-                    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= line - 1) lo = mid; else hi = mid; }
-                    cb = lo; jl = (uint32_t)(line - 1 - s_cbase[lo]) + 1;
-                }
-                ri.cp_row = cb * a.li.stage_cap + jl;
-            }
-            else { ri.cp_row = (uint32_t)slot; a.nu_rows[slot] = (uint32_t)row; }
+    uint32_t cp_row = kNoCpRow;
+    if (a.cp_by_line && a.want_gt && h.has_samples && h.g >= 0 && !v.uniform) {
+        // staged id of the line: (tokenizer CTA, local line) -- see hb_tokenize.cu
+        uint32_t cb = 0, jl = 0;
+        if (line) {
+            uint32_t lo = 0, hi = a.li.n_cta;
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_cbase[mid] <= line - 1) lo = mid; else hi = mid; }
+            cb = lo; jl = (uint32_t)(line - 1 - s_cbase[lo]) + 1;
         }
+        cp_row = cb * a.li.stage_cap + jl;
     }
-    a.rowinfo[row] = ri;
+    write_site_row(a.out, a.text, row, ls, le, h, v, a.want_gt, cp_row);
 }
 
 void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, uint32_t n_samples,
@@ -249,8 +144,9 @@ void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, 
     SiteArgs a;
     a.text = d_text; a.li = li; a.n_lines = n_lines; a.n_samples = n_samples;
     a.rg = rg; a.end_is_int = end_is_int; a.want_gt = want_gt; a.cp_by_line = cp_by_line ? 1 : 0;
-    a.start = d_start; a.stop = d_stop; a.ref = d_ref; a.alt = d_alt;
-    a.chrom_abs = d_chrom_abs; a.chrom_len = d_chrom_len; a.chrom5 = d_chrom5; a.rowinfo = d_rowinfo; a.nu_rows = d_nu_rows;
+    a.out.start = d_start; a.out.stop = d_stop; a.out.ref = d_ref; a.out.alt = d_alt;
+    a.out.chrom_abs = d_chrom_abs; a.out.chrom_len = d_chrom_len; a.out.chrom5 = d_chrom5; a.out.rowinfo = d_rowinfo;
+    a.out.nu_rows = d_nu_rows; a.out.st = d_st;
     a.tile_state = d_tile_state; a.st = d_st;
     sites_kernel<<<(unsigned)tiles, ST_THREADS, 0, L.stream>>>(a);
     count_launch();

@@ -79,7 +79,8 @@ typedef struct hb_parse_opts {
     int end_is_int;         /* header declares INFO/END as Integer: END overrides rlen */
     int want_gt;            /* 0: sites only (load_vcf_without_sample) */
     int device;             /* CUDA device ordinal */
-    int tokenizer;          /* 0 auto, 1 newline-only (GT-only text), 2 newline+tab checkpoints */
+    int tokenizer;          /* 0 auto, 1 newline-only (GT-only text), 2 newline+tab checkpoints,
+                               3 head walker (uniform GT-only text; falls back to 1/2 when it cannot prove itself exact) */
     void *stream;           /* cudaStream_t or NULL */
 } hb_parse_opts;
 
@@ -93,8 +94,9 @@ typedef struct hb_parse_info {
     uint64_t n_nonuniform;          /* records that took the general (tab-scan) decode path */
     uint64_t n_bad_gt, n_bad_cols;  /* malformed alleles / column-count mismatches */
     uint64_t n_nogt;                /* kept records without a GT key or without sample columns */
-    int tokenizer_used;             /* 1 newline-only, 2 newline + tab checkpoints */
+    int tokenizer_used;             /* 1 newline-only, 2 newline + tab checkpoints, 3 head walker */
     float ms_tokenize, ms_sites, ms_decode;   /* CUDA-event kernel times of the last parse */
+    int walker_fallbacks;           /* times the head walker could not prove itself exact and the tokenizer re-ran */
 } hb_parse_info;
 
 /* text on the HOST (pageable or pinned): H2D copy + kernels.  body must end with '\n'. */

@@ -86,7 +86,7 @@ def test_errors_match_reference_contract(parse_vcf, golden_dir):
         os.unlink(f.name)
 
 
-@pytest.mark.parametrize("tokenizer", [0, 1, 2])
+@pytest.mark.parametrize("tokenizer", [0, 1, 2, 3])
 @pytest.mark.parametrize("fmt,kinds,multidigit", [("GT", "phased", False), ("GT", "mixed", False),
                                                    ("GT", "mixed", True), ("GT:GQ:DP", "mixed", True),
                                                    ("DP:GT", "mixed", False)])
@@ -168,3 +168,95 @@ def test_many_tiles_lookback(capi):
     assert len(text) > 40 * 1024 * 1024
     _check_matrix(capi, text, spec.n_samples, "chr22", tokenizer=1)
     _check_matrix(capi, text, spec.n_samples, "chr22", tokenizer=2)
+    p, info = _check_matrix(capi, text, spec.n_samples, "chr22", tokenizer=0)       # auto -> head walker
+    assert info.tokenizer_used == 3 and info.walker_fallbacks == 0 and info.n_lines == 40000
+
+
+# ------------------------------------------------------------------------------------------------
+# head walker (tokenizer 3): records located by jumping 4*S bytes from the 9th tab
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lines_per_walker", ["1", "3", "16", "500"])
+@pytest.mark.parametrize("mix", [0, 1])
+def test_walker_uniform_text(capi, monkeypatch, lines_per_walker, mix):
+    monkeypatch.setenv("HB_WALK_LINES", lines_per_walker)
+    spec = capi.synth_spec(6000, 300, seed=17 + mix, mix=mix)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    p, info = _check_matrix(capi, text, spec.n_samples, "chr22", tokenizer=0)
+    assert info.tokenizer_used == 3 and info.walker_fallbacks == 0 and info.n_lines == 6000
+    _check_matrix(capi, text, spec.n_samples, "chr22:10050000-10120000", tokenizer=3)
+    p.rerun()
+    assert p.info.tokenizer_used == 3 and p.info.n_records == info.n_records
+
+
+def test_walker_odd_lines_stay_exact(capi, monkeypatch):
+    """Comment lines, empty lines, CRLF, wide records, other FORMATs and a missing final newline inside
+    otherwise uniform text: the walker searches those newlines instead of jumping."""
+    monkeypatch.setenv("HB_WALK_LINES", "4")
+    S = synth.sample_names(260)
+    rng = np.random.default_rng(0)
+
+    def rec(pos, gts=None, fmt="GT", ref="A", alt="C", eol="\n"):
+        gts = gts if gts is not None else ["%d|%d" % (a, b) for a, b in rng.integers(0, 2, (260, 2))]
+        return "\t".join(["chr22", str(pos), ".", ref, alt, ".", "PASS", ".", fmt] + gts) + eol
+
+    lines = []
+    for i in range(400):
+        pos = 1000 + 10 * i
+        if i == 5:
+            lines.append("#late comment\twith\ttabs\n")
+        if i == 9:
+            lines.append("\n")
+        if i % 37 == 3:
+            lines.append(rec(pos, eol="\r\n"))
+        elif i % 41 == 4:
+            g = ["%d|%d" % (a, b) for a, b in rng.integers(0, 2, (260, 2))]
+            g[17] = "10|1"
+            lines.append(rec(pos, g))
+        elif i % 43 == 5:
+            lines.append(rec(pos, ["0|1:%d" % d for d in rng.integers(1, 99, 260)], fmt="GT:DP"))
+        elif i % 47 == 6:
+            lines.append(rec(pos, ref="AT"))                          # dropped: its span goes to the verify kernel
+        else:
+            lines.append(rec(pos))
+    text = (synth.header(S) + "".join(lines)).encode()
+    p, info = _check_matrix(capi, text, 260, "chr22", tokenizer=3)
+    assert info.tokenizer_used == 3 and info.walker_fallbacks == 0
+    assert info.n_lines == len(lines)
+    _check_matrix(capi, text[:-1], 260, "chr22", tokenizer=3)        # no final newline
+
+
+def test_walker_cannot_be_fooled_by_hidden_newlines(capi, monkeypatch):
+    """Two short records whose lengths add up so that (9th tab of the first) + 4*S lands exactly on the
+    second one's newline: the jump is accepted by the walker and must be caught afterwards -- by the
+    verify kernel when the merged record is dropped, by the GT decoder when it is kept."""
+    monkeypatch.setenv("HB_WALK_LINES", "2")
+    n = 300
+    S = synth.sample_names(n)
+    rng = np.random.default_rng(1)
+
+    def groups(k):
+        return "".join("\t%d|%d" % (a, b) for a, b in rng.integers(0, 2, (k, 2)))
+
+    def head(pos, ref, alt, rid="."):
+        return "\t".join(["chr22", str(pos), rid, ref, alt, ".", "PASS", ".", "GT"])
+
+    for ref, expect_error in (("AT", False), ("A", True)):
+        lines = [head(100 + i, "A", "C") + groups(n) + "\n" for i in range(50)]
+        h2 = head(7000, ref, "G")
+        h2 = head(7000, ref, "G", "r" * (1 + (3 - len(h2)) % 4))       # make 4*n - 4*m - 1 - len(h2) a multiple of 4
+        m = 100
+        k2 = (4 * n - 4 * m - 1 - len(h2))
+        assert k2 % 4 == 0 and k2 > 0, (k2, len(h2))
+        pair = head(6000, ref, "G") + groups(m) + "\n" + h2 + groups(k2 // 4) + "\n"
+        lines.insert(20, pair)
+        lines += [head(9000 + i, "A", "C") + groups(n) + "\n" for i in range(50)]
+        text = (synth.header(S) + "".join(lines)).encode()
+        body = synth.body_of(text)
+        if expect_error:
+            for tok in (1, 3):
+                with pytest.raises(capi.HaploError, match="Number of columns"):
+                    capi.Parse.from_host(body, n, region="chr22", tokenizer=tok)
+        else:
+            p, info = _check_matrix(capi, text, n, "chr22", tokenizer=3)
+            assert info.walker_fallbacks == 1 and info.tokenizer_used == 1 and info.n_lines == 102
+            assert info.n_records == 100
