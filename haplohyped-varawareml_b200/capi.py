@@ -48,7 +48,8 @@ class Records(C.Structure):
 class FramesInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_chunks", C.c_uint64), ("chunk_records", C.c_uint64),
                 ("n_samples", C.c_uint32), ("total_bytes", C.c_uint64), ("raw_bytes", C.c_uint64),
-                ("ms_site", C.c_float), ("ms_gt", C.c_float)]
+                ("ms_site", C.c_float), ("ms_gt", C.c_float), ("padded_bytes", C.c_uint64), ("d_frames", C.c_void_p),
+                ("ms_offsets", C.c_float), ("ms_assemble", C.c_float)]
 
 
 class HapBatch(C.Structure):
@@ -70,7 +71,8 @@ EXPORTS = [
     "hb_parse_host_text", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
-    "hb_compress_records", "hb_frames_get_info", "hb_frames_fetch_sample", "hb_frames_free",
+    "hb_compress_records", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
+    "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_decode_frames",
     "hb_encode_haplotypes",
     "hb_synth_body_bytes", "hb_synth_header", "hb_synth_device", "hb_synth_host",
@@ -107,6 +109,9 @@ def lib():
         if hasattr(L, "hb_compress_records"):
             L.hb_compress_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
             L.hb_frames_get_info.argtypes = [C.c_void_p, C.POINTER(FramesInfo)]
+            L.hb_frames_rerun.argtypes = [C.c_void_p, C.c_void_p]
+            L.hb_frames_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.hb_frames_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
             L.hb_frames_fetch_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
                                                  C.POINTER(C.c_uint64)]
             L.hb_frames_free.argtypes = [C.c_void_p]
@@ -272,6 +277,23 @@ class Frames:
         i = FramesInfo()
         check(lib().hb_frames_get_info(self._h, C.byref(i)))
         return i
+
+    def rerun(self, parse: "Parse"):
+        check(lib().hb_frames_rerun(self._h, parse._h))
+
+    def layout(self):
+        """(offsets uint64 [n_samples, n_chunks] into the frame buffer, sizes uint32 [n_samples, n_chunks])"""
+        i = self.info
+        offs = np.zeros((i.n_samples, i.n_chunks), np.uint64)
+        sizes = np.zeros((i.n_samples, i.n_chunks), np.uint32)
+        check(lib().hb_frames_layout(self._h, offs.ctypes.data, sizes.ctypes.data))
+        return offs, sizes
+
+    def fetch_all(self) -> np.ndarray:
+        """The whole device frame buffer (frames 16-byte aligned, [sample][chunk] order) in one D2H copy."""
+        buf = np.empty(max(1, self.info.padded_bytes), np.uint8)
+        check(lib().hb_frames_fetch_all(self._h, buf.ctypes.data, buf.size))
+        return buf[:self.info.padded_bytes]
 
     def sample(self, s: int):
         i = self.info

@@ -34,7 +34,6 @@ namespace hb {
 
 constexpr int kHist = 64;                 // bytes of history kept in front of the donor planes
 constexpr int FRAME_HDR = 97, CHUNK_HDR = 32, OFFS_CHUNK = 40, FRAME_TRAILER = 35;
-constexpr int FRAME_FIXED = FRAME_HDR + CHUNK_HDR + 4 + 4 + OFFS_CHUNK + FRAME_TRAILER;   // + LZ4 bytes
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {     // unaligned 4-byte read (shared memory)
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -136,28 +135,119 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
 }
 
 // ------------------------------------------------------------------------------------------
-// site planes 0..32 of one chunk -> LZ4 head of the block
+// Frame anatomy.  One HDF5 chunk of one donor = one Blosc2 contiguous frame holding one chunk:
+//   [0,97)     cframe header        frame_len @16 (BE64) and cbytes @39 (BE64) depend on the donor
+//   [97,129)   Blosc2 chunk header  cbytes @109 (LE32) depends on the donor
+//   [129,133)  bstarts[0] = 36
+//   [133,137)  csize of the single (no-split) stream, LE32: depends on the donor
+//   [137,137+plen)   LZ4 sequences of the 33 site planes    -- identical for every donor
+//   [.., +dlen)      LZ4 sequences of the 2 allele planes   -- the donor's own
+//   [.., +40)        offsets chunk (one int64 0, memcpyed)  -- constant
+//   [.., +35)        cframe trailer                          -- constant
+// Kernels:
+//   site_template_kernel   one CTA per chunk: site planes -> LZ4; writes the frame TEMPLATE (header with
+//                          the donor-dependent fields left zero + shared LZ4 head), 16-byte aligned.
+//   donor_encode_kernel    one warp per (sample, chunk): allele planes -> LZ4 tail of the same block;
+//                          writes [pad][sequences][offsets chunk][trailer] into a staging slot, shifted
+//                          so that it lines up with the template's end modulo 16.
+//   frame_offsets_kernel / row_base_kernel   frame sizes -> 16-byte aligned offsets, [sample][chunk] order.
+//   assemble_kernel        one warp per frame: 16-byte vector copy template + staged tail -> final
+//                          position, patching the four size fields in registers.  This is where the
+//                          bytes go: C_out is written exactly once, the templates stay in L2.
 // ------------------------------------------------------------------------------------------
+constexpr int TMPL_HDR = FRAME_HDR + CHUNK_HDR + 8;        // 137 bytes of a frame precede its LZ4 block
+constexpr int FRAME_TAIL = OFFS_CHUNK + FRAME_TRAILER;     // 75 bytes follow it
+
+__device__ const uint8_t kFrameTail[FRAME_TAIL] = {
+    // offsets chunk: Blosc2 chunk header (version 5, LZ4 format 1, flags memcpyed|shuffle|bitshuffle(=extended),
+    // typesize 8, nbytes 8, blocksize 8, cbytes 40, filters[5] = shuffle) + one int64 0
+    5, 1, 0x17, 8, 8, 0, 0, 0, 8, 0, 0, 0, OFFS_CHUNK, 0, 0, 0,
+    0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0,
+    // trailer: [version 1, vlmetalayers {index, map16 0, array16 0}, uint32 trailer_len, fixext16 fingerprint]
+    0x94, 0x01, 0x93, 0xcd, 0, 5, 0xde, 0, 0, 0xdc, 0, 0, 0xce, 0, 0, 0, FRAME_TRAILER, 0xd8, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+__device__ __forceinline__ void put_be(uint8_t *p, uint64_t v, int nb) {
+    for (int i = 0; i < nb; ++i) p[i] = (uint8_t)(v >> (8 * (nb - 1 - i)));
+}
+__device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+// the 137 header bytes of a frame for chunks of `nbytes` uncompressed bytes; donor-dependent fields are zero
+__device__ void write_frame_head(uint8_t *h, uint32_t nbytes) {
+    for (int i = 0; i < TMPL_HDR; ++i) h[i] = 0;
+    // ---- cframe header (c-blosc2 README_CFRAME_FORMAT; msgpack, big-endian)
+    h[0] = 0x9e; h[1] = 0xa8;
+    const char magic[8] = {'b', '2', 'f', 'r', 'a', 'm', 'e', 0};
+    for (int i = 0; i < 8; ++i) h[2 + i] = (uint8_t)magic[i];
+    h[10] = 0xd2; put_be(h + 11, FRAME_HDR, 4);
+    h[15] = 0xcf;                                            // frame_len: patched
+    h[24] = 0xa4; h[25] = 0x12; h[26] = 0x00; h[27] = 0x51; h[28] = 0x03;   // v2 | 64-bit offs, contiguous, LZ4 | clevel 5, split mode
+    h[29] = 0xd3; put_be(h + 30, nbytes, 8);
+    h[38] = 0xd3;                                            // cbytes: patched
+    h[47] = 0xd2; put_be(h + 48, 35, 4);
+    h[52] = 0xd2; put_be(h + 53, nbytes, 4);
+    h[57] = 0xd2; put_be(h + 58, nbytes, 4);
+    h[62] = 0xd1; put_be(h + 63, 1, 2);
+    h[65] = 0xd1; put_be(h + 66, 1, 2);
+    h[68] = 0xc2;
+    h[69] = 0xd8; h[70] = 6;
+    h[76] = 1;                                               // filters[5] = BLOSC_SHUFFLE
+    h[87] = 0x93; h[88] = 0xcd; put_be(h + 89, 5, 2);
+    h[91] = 0xde; h[94] = 0xdc;
+    // ---- Blosc2 chunk header (extended, 32 bytes, little-endian)
+    uint8_t *k = h + FRAME_HDR;
+    k[0] = 5; k[1] = 1; k[2] = 0x35; k[3] = 35;              // format 5, LZ4 format 1, shuffle|bitshuffle(=extended)|dont-split|LZ4
+    put_le32(k + 4, nbytes); put_le32(k + 8, nbytes);        // cbytes @12: patched
+    k[21] = 1;                                               // filters[5] = BLOSC_SHUFFLE
+    put_le32(k + 32, CHUNK_HDR + 4);                         // bstarts[0]
+}                                                            // csize @36: patched
+
+// one LZ4 sequence, written by the whole warp; returns the new output offset
+__device__ int warp_emit_seq(uint8_t *dst, int o, const uint8_t *lit, int litlen, int off, int ml) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) dst[o] = (uint8_t)((min(litlen, 15) << 4) | min(ml - 4, 15));
+    ++o;
+    if (litlen >= 15) {
+        int rem = litlen - 15;
+        while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
+        if (lane == 0) dst[o] = (uint8_t)rem;
+        ++o;
+    }
+    for (int i = lane; i < litlen; i += 32) dst[o + i] = lit[i];
+    o += litlen;
+    if (lane == 0) { dst[o] = (uint8_t)off; dst[o + 1] = (uint8_t)(off >> 8); }
+    o += 2;
+    if (ml - 4 >= 15) {
+        int rem = ml - 19;
+        while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
+        if (lane == 0) dst[o] = (uint8_t)rem;
+        ++o;
+    }
+    return o;
+}
+
 struct SiteArgs4 {
     const uint64_t *chrom5;      // per record: first 5 CHROM bytes, NUL padded, in the low 40 bits
     const uint32_t *start, *stop;
     const uint8_t *ref, *alt;
     uint64_t n_records;
     uint32_t cr;                 // records per chunk
-    uint8_t *prefix;             // [n_chunks][prefix_cap]
-    uint32_t prefix_cap;
-    uint32_t *prefix_len;        // [n_chunks]
-    uint32_t *prefix_pending;    // [n_chunks] literals left pending at the end of the site planes
-    uint8_t *tail;               // [n_chunks][kHist] last bytes of the site planes
+    uint8_t *tmpl;               // [n_chunks][tmpl_cap], 16-byte aligned rows
+    uint32_t tmpl_cap;
+    uint32_t *tmpl_len;          // [n_chunks] = TMPL_HDR + LZ4 bytes of the site planes
 };
 
-__global__ void __launch_bounds__(256) site_prefix_kernel(const SiteArgs4 a) {
+__global__ void __launch_bounds__(256) site_template_kernel(const SiteArgs4 a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t s_len;
     const uint32_t cr = a.cr;
     const uint32_t n = 33u * cr;
     uint8_t *planes = smem + 16;                            // 16 bytes of (unused) history in front
-    uint8_t *outb = planes + ((n + 19) & ~15u);
-    uint16_t *table = reinterpret_cast<uint16_t *>(outb + ((n + n / 255 + 64 + 15) & ~15u));
+    uint8_t *outb = planes + ((n + 19) & ~15u);             // the template: header, then LZ4 bytes
+    uint16_t *table = reinterpret_cast<uint16_t *>(outb + a.tmpl_cap);
     const uint64_t c = blockIdx.x;
     const uint64_t r0 = c * cr;
     for (uint32_t i = threadIdx.x; i < cr; i += blockDim.x) {
@@ -179,142 +269,202 @@ __global__ void __launch_bounds__(256) site_prefix_kernel(const SiteArgs4 a) {
         for (int k = 0; k < 9; ++k) { planes[(14 + k) * cr + i] = 0; planes[(24 + k) * cr + i] = 0; }
     }
     if (threadIdx.x < 16) smem[threadIdx.x] = 0;
+    for (uint32_t i = threadIdx.x; i < a.tmpl_cap / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(outb)[i] = 0;
     __syncthreads();
+    if (threadIdx.x == 0) write_frame_head(outb, 35u * cr);
     // Chunks of fewer than 6 records cannot honour LZ4's end-of-block rules (last match >= 12 bytes
     // before the end) once the 2*cr allele bytes follow: such blocks are stored raw (csize == size).
     const bool raw = cr < 6;
+    uint8_t *lz = outb + TMPL_HDR;
     if (raw) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) outb[i] = planes[i];
-        if (threadIdx.x == 0) { a.prefix_len[c] = n; a.prefix_pending[c] = 0; }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) lz[i] = planes[i];
+        if (threadIdx.x == 0) s_len = n;
     } else if (threadIdx.x < 32) {
+        // Planes 24..32 (ALT bytes 1..9) are all zero: the head is encoded up to the first of those
+        // zeros, then ONE offset-1 match covers the other 9*cr-1 -- so the site part always ends on a
+        // sequence boundary and every donor continues the block with nothing pending and zeros behind it.
+        const int n1 = 24 * (int)cr + 1;
         int pending = 0;
-        const int len = warp_lz4(planes, (int)n, 0, 0, false, outb, table, 12, &pending);
-        if (threadIdx.x == 0) { a.prefix_len[c] = (uint32_t)len; a.prefix_pending[c] = (uint32_t)pending; }
+        int len = warp_lz4(planes, n1, 0, 0, false, lz, table, 12, &pending);
+        len = warp_emit_seq(lz, len, planes + n1 - pending, pending, 1, (int)n - n1);
+        if (threadIdx.x == 0) s_len = (uint32_t)len;
     }
     __syncthreads();
-    const uint32_t len = a.prefix_len[c];
-    uint8_t *dstp = a.prefix + c * a.prefix_cap;
-    for (uint32_t i = threadIdx.x; i < len && i < a.prefix_cap; i += blockDim.x) dstp[i] = outb[i];
-    if (threadIdx.x < kHist) {
-        const int idx = (int)n - kHist + (int)threadIdx.x;
-        a.tail[c * kHist + threadIdx.x] = idx >= 0 ? planes[idx] : 0;
-    }
+    const uint32_t tl = TMPL_HDR + s_len;
+    if (threadIdx.x == 0) a.tmpl_len[c] = tl;
+    uint4 *dstp = reinterpret_cast<uint4 *>(a.tmpl + c * a.tmpl_cap);
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
+    for (uint32_t i = threadIdx.x; i < (tl + 15) / 16; i += blockDim.x) dstp[i] = srcp[i];
 }
 
 // ------------------------------------------------------------------------------------------
-// one warp per (chunk, sample): allele planes -> tail of the LZ4 block -> complete cframe
+// one warp per (sample, chunk): allele planes -> LZ4 tail of the block -> staging slot
 // ------------------------------------------------------------------------------------------
 struct DonorArgs {
     const int8_t *gt0, *gt1;
     uint64_t gt_stride, n_records;
-    uint32_t cr, n_samples;
+    uint32_t cr, n_samples, s0;  // samples [s0, s0 + n_samples)
     uint64_t n_chunks;
-    const uint8_t *prefix;
-    uint32_t prefix_cap;
-    const uint32_t *prefix_len, *prefix_pending;
-    const uint8_t *tail;
-    uint8_t *frames;             // [n_chunks][n_samples][slot]
-    uint32_t slot;
-    uint32_t *sizes;             // [n_samples][n_chunks]
+    const uint32_t *tmpl_len;
+    uint8_t *stage;              // [n_samples * n_chunks][dslot]
+    uint32_t dslot;
+    uint32_t *dlen;              // [n_samples * n_chunks] LZ4 bytes of the allele planes
     uint32_t warp_smem;          // bytes of shared memory per warp
 };
 
-__device__ __forceinline__ void put_be(uint8_t *p, uint64_t v, int nb) {
-    for (int i = 0; i < nb; ++i) p[i] = (uint8_t)(v >> (8 * (nb - 1 - i)));
-}
-__device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v) {
-    p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
-}
-
-__global__ void __launch_bounds__(256) donor_frames_kernel(const DonorArgs a) {
+__global__ void __launch_bounds__(256) donor_encode_kernel(const DonorArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (wid >= a.n_chunks * a.n_samples) return;
-    const uint64_t c = wid / a.n_samples;
-    const uint32_t s = (uint32_t)(wid % a.n_samples);
+    const uint32_t s = (uint32_t)(wid / a.n_chunks);
+    const uint64_t c = wid % a.n_chunks;
     const uint32_t cr = a.cr, n = 2u * cr;
     uint8_t *base = smem + (size_t)warp * a.warp_smem;
     uint8_t *src = base + kHist;                                   // history sits right in front
     uint8_t *outb = src + ((n + 19) & ~15u);
-    uint16_t *table = reinterpret_cast<uint16_t *>(outb + ((n + n / 255 + 64 + 15) & ~15u));
-    // history + the two allele planes (zero-padded past n_records, like an HDF5 edge chunk)
-    for (int i = lane; i < kHist; i += 32) base[i] = a.tail[c * kHist + i];
+    uint16_t *table = reinterpret_cast<uint16_t *>(outb + a.dslot);
+    // history (the zero tail of the site planes) + the two allele planes (zero-padded past n_records,
+    // like an HDF5 edge chunk)
+    for (int i = lane; i < kHist; i += 32) base[i] = 0;
     const uint64_t r0 = c * cr;
-    const int8_t *g0 = a.gt0 + (uint64_t)s * a.gt_stride + r0, *g1 = a.gt1 + (uint64_t)s * a.gt_stride + r0;
+    const int8_t *g0 = a.gt0 + (uint64_t)(a.s0 + s) * a.gt_stride + r0, *g1 = a.gt1 + (uint64_t)(a.s0 + s) * a.gt_stride + r0;
     for (uint32_t i = lane; i < cr; i += 32) {
         const bool in = r0 + i < a.n_records;
         src[i] = in ? (uint8_t)g0[i] : 0;
         src[cr + i] = in ? (uint8_t)g1[i] : 0;
     }
+    const uint32_t sh = a.tmpl_len[c] & 15u;                       // lines the slot up with the template's end
+    if (lane < 16) outb[lane] = 0;
     __syncwarp();
-    const int pend = (int)a.prefix_pending[c];
-    const int hist = min(kHist, (int)(33u * cr));
-    // pending literals of the site planes are re-emitted as the first literals here; they must lie in the history
+    uint8_t *seq = outb + sh;
     int dlen;
-    if (cr < 6) {                                  // raw block, see site_prefix_kernel
-        for (uint32_t i = lane; i < n; i += 32) outb[i] = src[i];
+    if (cr < 6) {                                  // raw block, see site_template_kernel
+        for (uint32_t i = lane; i < n; i += 32) seq[i] = src[i];
         dlen = (int)n;
-        __syncwarp();
     } else {
-        dlen = warp_lz4(src, (int)n, hist, -min(pend, hist), true, outb, table, 10, nullptr);
+        dlen = warp_lz4(src, (int)n, min(kHist, 9 * (int)cr - 1), 0, true, seq, table, 10, nullptr);
     }
-    const uint32_t plen = a.prefix_len[c];
-    const uint32_t lz = plen + (uint32_t)dlen;
-    const uint32_t nbytes = 35u * cr;
-    const uint32_t chunk_cb = CHUNK_HDR + 4 + 4 + lz;
-    const uint32_t frame_len = FRAME_HDR + chunk_cb + OFFS_CHUNK + FRAME_TRAILER;
-    uint8_t *f = a.frames + (c * a.n_samples + s) * (uint64_t)a.slot;
-    if (lane == 0) {
-        // ---- cframe header (c-blosc2 README_CFRAME_FORMAT; msgpack, big-endian)
-        uint8_t *h = f;
-        h[0] = 0x9e; h[1] = 0xa8;
-        const char magic[8] = {'b', '2', 'f', 'r', 'a', 'm', 'e', 0};
-        for (int i = 0; i < 8; ++i) h[2 + i] = (uint8_t)magic[i];
-        h[10] = 0xd2; put_be(h + 11, FRAME_HDR, 4);
-        h[15] = 0xcf; put_be(h + 16, frame_len, 8);
-        h[24] = 0xa4; h[25] = 0x12; h[26] = 0x00; h[27] = 0x51; h[28] = 0x03;   // v2 | 64-bit offs, contiguous, LZ4 | clevel 5, split mode
-        h[29] = 0xd3; put_be(h + 30, nbytes, 8);
-        h[38] = 0xd3; put_be(h + 39, chunk_cb, 8);
-        h[47] = 0xd2; put_be(h + 48, 35, 4);
-        h[52] = 0xd2; put_be(h + 53, nbytes, 4);
-        h[57] = 0xd2; put_be(h + 58, nbytes, 4);
-        h[62] = 0xd1; put_be(h + 63, 1, 2);
-        h[65] = 0xd1; put_be(h + 66, 1, 2);
-        h[68] = 0xc2;
-        h[69] = 0xd8; h[70] = 6;
-        for (int i = 0; i < 16; ++i) h[71 + i] = 0;
-        h[76] = 1;                                       // filters[5] = BLOSC_SHUFFLE
-        h[87] = 0x93; h[88] = 0xcd; put_be(h + 89, 5, 2);
-        h[91] = 0xde; h[92] = 0; h[93] = 0; h[94] = 0xdc; h[95] = 0; h[96] = 0;
-        // ---- Blosc2 chunk header (extended, 32 bytes, little-endian)
-        uint8_t *k = f + FRAME_HDR;
-        k[0] = 5; k[1] = 1; k[2] = 0x35; k[3] = 35;      // format 5, LZ4 format 1, shuffle|bitshuffle(=extended)|dont-split|LZ4
-        put_le32(k + 4, nbytes); put_le32(k + 8, nbytes); put_le32(k + 12, chunk_cb);
-        for (int i = 16; i < 32; ++i) k[i] = 0;
-        k[21] = 1;                                       // filters[5] = BLOSC_SHUFFLE
-        put_le32(k + 32, CHUNK_HDR + 4);                 // bstarts[0]
-        put_le32(k + 36, lz);                            // the single stream's compressed size
-        // ---- offsets chunk: one int64 (0), stored as a memcpyed Blosc2 chunk
-        uint8_t *o = f + FRAME_HDR + chunk_cb;
-        o[0] = 5; o[1] = 1; o[2] = 0x17; o[3] = 8;
-        put_le32(o + 4, 8); put_le32(o + 8, 8); put_le32(o + 12, OFFS_CHUNK);
-        for (int i = 16; i < 40; ++i) o[i] = 0;
-        o[21] = 1;
-        // ---- trailer
-        uint8_t *t = o + OFFS_CHUNK;
-        t[0] = 0x94; t[1] = 0x01; t[2] = 0x93; t[3] = 0xcd; put_be(t + 4, 5, 2);
-        t[6] = 0xde; t[7] = 0; t[8] = 0; t[9] = 0xdc; t[10] = 0; t[11] = 0;
-        t[12] = 0xce; put_be(t + 13, FRAME_TRAILER, 4);
-        t[17] = 0xd8; t[18] = 0;
-        for (int i = 0; i < 16; ++i) t[19 + i] = 0;
-        a.sizes[(uint64_t)s * a.n_chunks + c] = frame_len;
+    for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
+    const uint32_t used = sh + (uint32_t)dlen + FRAME_TAIL;
+    for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
+    __syncwarp();
+    uint4 *dstp = reinterpret_cast<uint4 *>(a.stage + wid * (uint64_t)a.dslot);
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
+    for (uint32_t i = lane; i < (used + 15) / 16; i += 32) dstp[i] = srcp[i];
+    if (lane == 0) a.dlen[wid] = (uint32_t)dlen;
+}
+
+// ------------------------------------------------------------------------------------------
+// frame sizes -> offsets.  Frames are laid out [sample][chunk], each starting on a 16-byte boundary.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_offsets_kernel(const uint32_t *__restrict__ tmpl_len, const uint32_t *__restrict__ dlen, uint32_t n_chunks,
+                     uint32_t *__restrict__ size, uint32_t *__restrict__ rowoff, uint64_t *__restrict__ rowtot,
+                     unsigned long long *__restrict__ sum_sizes) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint64_t carry;
+    const uint32_t s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (uint32_t base = 0; base < n_chunks; base += 256) {
+        const uint32_t c = base + threadIdx.x;
+        const uint64_t wid = (uint64_t)s * n_chunks + c;
+        uint32_t sz = 0;
+        if (c < n_chunks) { sz = FRAME_TAIL + tmpl_len[c] + dlen[wid]; size[wid] = sz; mine += sz; }
+        const uint32_t pad = (sz + 15u) & ~15u;
+        uint32_t inc = pad;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { if (w < (int)warp) wbase += wsum[w]; total += wsum[w]; }
+        if (c < n_chunks) rowoff[wid] = (uint32_t)(carry + wbase + inc - pad);
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
     }
-    // ---- LZ4 block: shared site head, then this sample's sequences
-    uint8_t *lzp = f + FRAME_HDR + CHUNK_HDR + 8;
-    const uint8_t *pp = a.prefix + c * a.prefix_cap;
-    for (uint32_t i = lane; i < plen; i += 32) lzp[i] = pp[i];
-    for (int i = lane; i < dlen; i += 32) lzp[plen + i] = outb[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+    if (lane == 0 && mine) atomicAdd(sum_sizes, mine);
+    if (threadIdx.x == 0) rowtot[s] = carry;
+}
+
+__global__ void __launch_bounds__(1024) row_base_kernel(const uint64_t *__restrict__ rowtot, uint32_t n, uint64_t *__restrict__ rowbase) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint64_t v = i < n ? rowtot[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint64_t wbase = 0, total = 0;
+        for (int w = 0; w < 32; ++w) { if (w < (int)warp) wbase += wsum[w]; total += wsum[w]; }
+        if (i < n) rowbase[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowbase[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------
+// one warp per frame: template + staged tail -> final position
+// ------------------------------------------------------------------------------------------
+struct AsmArgs {
+    const uint8_t *tmpl; uint32_t tmpl_cap; const uint32_t *tmpl_len;
+    const uint8_t *stage; uint32_t dslot; const uint32_t *dlen;
+    const uint32_t *rowoff; const uint64_t *rowbase;
+    uint8_t *frames;
+    uint32_t n_chunks, n_samples;
+};
+
+__device__ __forceinline__ uint4 ldg_nc(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) assemble_kernel(const AsmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (uint64_t)a.n_chunks * a.n_samples) return;
+    const uint32_t s = (uint32_t)(wid / a.n_chunks), c = (uint32_t)(wid % a.n_chunks);
+    const uint32_t tl = a.tmpl_len[c], dl = a.dlen[wid];
+    const uint32_t lz = tl - TMPL_HDR + dl, cb = CHUNK_HDR + 8 + lz, flen = tl + dl + FRAME_TAIL;
+    const uint32_t jb = tl >> 4, nvec = (flen + 15) >> 4;
+    const uint4 *T = reinterpret_cast<const uint4 *>(a.tmpl + (uint64_t)c * a.tmpl_cap);
+    const uint4 *G = reinterpret_cast<const uint4 *>(a.stage + wid * (uint64_t)a.dslot);
+    uint4 *D = reinterpret_cast<uint4 *>(a.frames + a.rowbase[s] + a.rowoff[wid]);
+#pragma unroll 4
+    for (uint32_t j = lane; j < nvec; j += 32) {
+        uint4 v;
+        if (j < jb) v = ldg_nc(T + j);
+        else {
+            v = ldg_stream(G + (j - jb));
+            if (j == jb && (tl & 15u)) {           // the template's last bytes and the slot's pad are zero where the other has data
+                const uint4 t = ldg_nc(T + j);
+                v.x |= t.x; v.y |= t.y; v.z |= t.z; v.w |= t.w;
+            }
+        }
+        if (j <= 8) {                              // the four donor-dependent size fields (all zero in the template)
+            if (j == 1) v.y |= __byte_perm(flen, 0, 0x0123);                               // frame_len, BE64 @16
+            else if (j == 2) { v.z |= (cb >> 24) << 24; v.w |= __byte_perm(cb, 0, 0x0123) >> 8; }   // cbytes, BE64 @39
+            else if (j == 6) v.w |= cb << 8;                                               // chunk cbytes, LE32 @109
+            else if (j == 7) v.x |= cb >> 24;
+            else if (j == 8) { v.y |= lz << 8; v.z |= lz >> 24; }                          // stream csize, LE32 @133
+        }
+        stg_stream(D + j, v);
+    }
 }
 
 uint64_t guess_chunk_records(uint64_t n) {      // h5py/_hl/filters.py guess_chunk for shape (n,), 35-byte items
@@ -342,13 +492,101 @@ struct hb_frames {
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t n_records = 0, n_chunks = 0, cr = 0;
-    uint32_t n_samples = 0, slot = 0, prefix_cap = 0;
-    uint8_t *d_prefix = nullptr, *d_tail = nullptr, *d_frames = nullptr;
-    uint32_t *d_prefix_len = nullptr, *d_prefix_pending = nullptr, *d_sizes = nullptr;
-    std::vector<uint32_t> h_sizes;       // [n_samples][n_chunks]
-    uint64_t total_bytes = 0;
-    float ms_site = 0, ms_gt = 0;
+    uint32_t n_samples = 0, tmpl_cap = 0, dslot = 0, warp_smem = 0;
+    int warps_per_cta = 8;
+    size_t smem_site = 0;
+    uint8_t *d_tmpl = nullptr, *d_stage = nullptr, *d_frames = nullptr;
+    uint32_t *d_tmpl_len = nullptr, *d_dlen = nullptr, *d_size = nullptr, *d_rowoff = nullptr;
+    uint64_t *d_rowtot = nullptr, *d_rowbase = nullptr;
+    unsigned long long *d_sum = nullptr;
+    uint64_t frames_cap = 0;
+    uint64_t total_bytes = 0, padded_bytes = 0;
+    // host copies of the layout, fetched on demand
+    bool layout_valid = false;
+    std::vector<uint32_t> h_size, h_rowoff;      // [n_samples][n_chunks]
+    std::vector<uint64_t> h_rowbase;             // [n_samples + 1]
+    std::vector<uint8_t> h_row;                  // scratch for hb_frames_fetch_sample
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms_site = 0, ms_gt = 0, ms_offsets = 0, ms_assemble = 0;
 };
+
+static int frames_run(hb_frames *f, hb_parse *p) {
+    cudaError_t e;
+#define CUF(x) do { e = (x); if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e) + " at " #x); } while (0)
+    CUF(cudaSetDevice(f->device));
+    const uint64_t n = f->n_records;
+    const uint32_t cr = (uint32_t)f->cr;
+    const uint64_t n_frames = f->n_chunks * f->n_samples;
+    f->layout_valid = false;
+    SiteArgs4 sa;
+    sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
+    sa.n_records = n; sa.cr = cr; sa.tmpl = f->d_tmpl; sa.tmpl_cap = f->tmpl_cap; sa.tmpl_len = f->d_tmpl_len;
+    CUF(cudaMemsetAsync(f->d_sum, 0, 8, f->stream));
+    CUF(cudaEventRecord(f->ev[0], f->stream));
+    site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, f->stream>>>(sa);
+    count_launch();
+    CUF(cudaEventRecord(f->ev[1], f->stream));
+    DonorArgs da;
+    da.gt0 = p->d_gt[0]; da.gt1 = p->d_gt[1]; da.gt_stride = p->gt_stride; da.n_records = n;
+    da.cr = cr; da.n_samples = f->n_samples; da.s0 = 0; da.n_chunks = f->n_chunks;
+    da.tmpl_len = f->d_tmpl_len; da.stage = f->d_stage; da.dslot = f->dslot; da.dlen = f->d_dlen;
+    da.warp_smem = f->warp_smem;
+    const int wpc = f->warps_per_cta;
+    donor_encode_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(da);
+    count_launch();
+    CUF(cudaEventRecord(f->ev[2], f->stream));
+    frame_offsets_kernel<<<f->n_samples, 256, 0, f->stream>>>(f->d_tmpl_len, f->d_dlen, (uint32_t)f->n_chunks, f->d_size,
+                                                              f->d_rowoff, f->d_rowtot, f->d_sum);
+    row_base_kernel<<<1, 1024, 0, f->stream>>>(f->d_rowtot, f->n_samples, f->d_rowbase);
+    count_launch(2);
+    CUF(cudaEventRecord(f->ev[3], f->stream));
+    uint64_t tot[2] = {0, 0};
+    CUF(cudaMemcpyAsync(&tot[0], f->d_rowbase + f->n_samples, 8, cudaMemcpyDeviceToHost, f->stream));
+    CUF(cudaMemcpyAsync(&tot[1], f->d_sum, 8, cudaMemcpyDeviceToHost, f->stream));
+    CUF(cudaStreamSynchronize(f->stream));
+    CUF(cudaGetLastError());
+    f->padded_bytes = tot[0];
+    f->total_bytes = tot[1];
+    if (f->frames_cap < f->padded_bytes) {
+        if (f->d_frames) { cudaFree(f->d_frames); f->d_frames = nullptr; f->frames_cap = 0; }
+        const uint64_t cap = f->padded_bytes + f->padded_bytes / 64 + 4096;     // head-room for re-runs on new data
+        e = cudaMalloc(&f->d_frames, cap);
+        if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
+        f->frames_cap = cap;
+    }
+    AsmArgs aa;
+    aa.tmpl = f->d_tmpl; aa.tmpl_cap = f->tmpl_cap; aa.tmpl_len = f->d_tmpl_len;
+    aa.stage = f->d_stage; aa.dslot = f->dslot; aa.dlen = f->d_dlen;
+    aa.rowoff = f->d_rowoff; aa.rowbase = f->d_rowbase; aa.frames = f->d_frames;
+    aa.n_chunks = (uint32_t)f->n_chunks; aa.n_samples = f->n_samples;
+    assemble_kernel<<<(unsigned)((n_frames + 7) / 8), 256, 0, f->stream>>>(aa);
+    count_launch();
+    CUF(cudaEventRecord(f->ev[4], f->stream));
+    CUF(cudaStreamSynchronize(f->stream));
+    CUF(cudaGetLastError());
+    cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
+    cudaEventElapsedTime(&f->ms_gt, f->ev[1], f->ev[2]);
+    cudaEventElapsedTime(&f->ms_offsets, f->ev[2], f->ev[3]);
+    cudaEventElapsedTime(&f->ms_assemble, f->ev[3], f->ev[4]);
+#undef CUF
+    return HB_OK;
+}
+
+static int frames_layout(hb_frames *f) {
+    if (f->layout_valid) return HB_OK;
+    const uint64_t n_frames = f->n_chunks * f->n_samples;
+    f->h_size.resize(n_frames); f->h_rowoff.resize(n_frames); f->h_rowbase.resize((size_t)f->n_samples + 1);
+    if (n_frames) {
+        if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+        cudaError_t e = cudaMemcpyAsync(f->h_size.data(), f->d_size, n_frames * 4, cudaMemcpyDeviceToHost, f->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_rowoff.data(), f->d_rowoff, n_frames * 4, cudaMemcpyDeviceToHost, f->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_rowbase.data(), f->d_rowbase, ((size_t)f->n_samples + 1) * 8, cudaMemcpyDeviceToHost, f->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+        if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    }
+    f->layout_valid = true;
+    return HB_OK;
+}
 
 extern "C" {
 
@@ -357,13 +595,16 @@ uint64_t hb_guess_chunk_records(uint64_t n_records) { return guess_chunk_records
 void hb_frames_free(hb_frames *f) {
     if (!f) return;
     cudaSetDevice(f->device);
-    cudaFree(f->d_prefix); cudaFree(f->d_tail); cudaFree(f->d_frames);
-    cudaFree(f->d_prefix_len); cudaFree(f->d_prefix_pending); cudaFree(f->d_sizes);
+    cudaFree(f->d_tmpl); cudaFree(f->d_stage); cudaFree(f->d_frames);
+    cudaFree(f->d_tmpl_len); cudaFree(f->d_dlen); cudaFree(f->d_size); cudaFree(f->d_rowoff);
+    cudaFree(f->d_rowtot); cudaFree(f->d_rowbase); cudaFree(f->d_sum);
+    for (auto &x : f->ev) if (x) cudaEventDestroy(x);
     delete f;
 }
 
 int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     if (!p || !out) return api_fail(HB_ERR_ARG, "null argument");
+    *out = nullptr;
     if (cudaSetDevice(p->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
     const uint64_t n = p->h_st.n_records;
     if (!p->d_gt[0] && n) return api_fail(HB_ERR_NOGT, "parse was made without genotypes");
@@ -372,62 +613,47 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     f->n_records = n; f->n_samples = p->n_samples;
     f->cr = chunk_records ? chunk_records : guess_chunk_records(n);
     f->n_chunks = n ? (n + f->cr - 1) / f->cr : 0;
-    *out = f;
-    if (!f->n_chunks || !f->n_samples) return HB_OK;
+    if (!f->n_chunks || !f->n_samples) { f->n_chunks = n ? f->n_chunks : 0; *out = f; f->layout_valid = false; return HB_OK; }
+    if (f->cr > 2730) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk_records too large (at most 2730: the site encoder indexes 24*chunk_records+1 positions with 16 bits)"); }
     const uint32_t cr = (uint32_t)f->cr;
     const uint32_t n_site = 33u * cr, n_gt = 2u * cr;
     auto bound = [](uint32_t x) { return x + x / 255 + 64; };
-    const size_t smem_site = 16 + ((n_site + 19) & ~15u) + ((bound(n_site) + 15) & ~15u) + (2u << 12);
-    if (smem_site > 220 * 1024) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
-    f->prefix_cap = bound(n_site);
-    f->slot = (FRAME_FIXED + f->prefix_cap + bound(n_gt) + 15) & ~15u;
-    const uint32_t warp_smem = (kHist + ((n_gt + 19) & ~15u) + ((bound(n_gt) + 15) & ~15u) + (2u << 10) + 15) & ~15u;
-    int warps_per_cta = 8;
-    while (warps_per_cta > 1 && (size_t)warps_per_cta * warp_smem > 200 * 1024) warps_per_cta >>= 1;
-    if ((size_t)warps_per_cta * warp_smem > 220 * 1024) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
-    cudaError_t e;
-#define CUF(x) do { e = (x); if (e != cudaSuccess) { hb_frames_free(f); *out = nullptr; return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); } } while (0)
-    CUF(cudaMalloc(&f->d_prefix, f->n_chunks * (uint64_t)f->prefix_cap));
-    CUF(cudaMalloc(&f->d_tail, f->n_chunks * kHist));
-    CUF(cudaMalloc(&f->d_prefix_len, f->n_chunks * 4));
-    CUF(cudaMalloc(&f->d_prefix_pending, f->n_chunks * 4));
-    CUF(cudaMalloc(&f->d_sizes, f->n_chunks * (uint64_t)f->n_samples * 4));
-    CUF(cudaMalloc(&f->d_frames, f->n_chunks * (uint64_t)f->n_samples * f->slot));
-    cudaEvent_t ev[3];
-    for (auto &x : ev) cudaEventCreate(&x);
-    SiteArgs4 sa;
-    sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
-    sa.n_records = n; sa.cr = cr; sa.prefix = f->d_prefix; sa.prefix_cap = f->prefix_cap;
-    sa.prefix_len = f->d_prefix_len; sa.prefix_pending = f->d_prefix_pending; sa.tail = f->d_tail;
-    CUF(cudaFuncSetAttribute(site_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_site));
-    cudaEventRecord(ev[0], f->stream);
-    site_prefix_kernel<<<(unsigned)f->n_chunks, 256, smem_site, f->stream>>>(sa);
-    count_launch();
-    cudaEventRecord(ev[1], f->stream);
-    DonorArgs da;
-    da.gt0 = p->d_gt[0]; da.gt1 = p->d_gt[1]; da.gt_stride = p->gt_stride; da.n_records = n;
-    da.cr = cr; da.n_samples = f->n_samples; da.n_chunks = f->n_chunks;
-    da.prefix = f->d_prefix; da.prefix_cap = f->prefix_cap; da.prefix_len = f->d_prefix_len;
-    da.prefix_pending = f->d_prefix_pending; da.tail = f->d_tail;
-    da.frames = f->d_frames; da.slot = f->slot; da.sizes = f->d_sizes; da.warp_smem = warp_smem;
-    const size_t smem_donor = (size_t)warps_per_cta * warp_smem;
-    CUF(cudaFuncSetAttribute(donor_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_donor));
-    const uint64_t warps = f->n_chunks * f->n_samples;
-    donor_frames_kernel<<<(unsigned)((warps + warps_per_cta - 1) / warps_per_cta), warps_per_cta * 32, smem_donor,
-                          f->stream>>>(da);
-    count_launch();
-    cudaEventRecord(ev[2], f->stream);
-    f->h_sizes.resize(warps);
-    CUF(cudaMemcpyAsync(f->h_sizes.data(), f->d_sizes, warps * 4, cudaMemcpyDeviceToHost, f->stream));
-    CUF(cudaStreamSynchronize(f->stream));
-    CUF(cudaGetLastError());
-    cudaEventElapsedTime(&f->ms_site, ev[0], ev[1]);
-    cudaEventElapsedTime(&f->ms_gt, ev[1], ev[2]);
-    for (auto &x : ev) cudaEventDestroy(x);
-    f->total_bytes = 0;
-    for (uint32_t v : f->h_sizes) f->total_bytes += v;
-#undef CUF
+    f->tmpl_cap = (TMPL_HDR + bound(n_site) + 15) & ~15u;
+    f->smem_site = 16 + ((n_site + 19) & ~15u) + f->tmpl_cap + (2u << 12);
+    if (f->smem_site > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
+    f->dslot = (16 + bound(n_gt) + FRAME_TAIL + 15) & ~15u;
+    f->warp_smem = (kHist + ((n_gt + 19) & ~15u) + f->dslot + (2u << 10) + 15) & ~15u;
+    f->warps_per_cta = 8;
+    while (f->warps_per_cta > 1 && (size_t)f->warps_per_cta * f->warp_smem > 200 * 1024) f->warps_per_cta >>= 1;
+    if ((size_t)f->warps_per_cta * f->warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
+    const uint64_t n_frames = f->n_chunks * f->n_samples;
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cudaMalloc(&f->d_tmpl, f->n_chunks * (uint64_t)f->tmpl_cap));
+    ck(cudaMalloc(&f->d_tmpl_len, f->n_chunks * 4));
+    ck(cudaMalloc(&f->d_stage, n_frames * (uint64_t)f->dslot));
+    ck(cudaMalloc(&f->d_dlen, n_frames * 4));
+    ck(cudaMalloc(&f->d_size, n_frames * 4));
+    ck(cudaMalloc(&f->d_rowoff, n_frames * 4));
+    ck(cudaMalloc(&f->d_rowtot, (uint64_t)f->n_samples * 8));
+    ck(cudaMalloc(&f->d_rowbase, ((uint64_t)f->n_samples + 1) * 8));
+    ck(cudaMalloc(&f->d_sum, 8));
+    for (auto &x : f->ev) ck(cudaEventCreate(&x));
+    ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_site));
+    ck(cudaFuncSetAttribute(donor_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
+    if (e != cudaSuccess) { hb_frames_free(f); return api_fail(HB_ERR_MEM, std::string("CUDA: ") + cudaGetErrorString(e)); }
+    int rc = frames_run(f, p);
+    if (rc != HB_OK) { hb_frames_free(f); return rc; }
+    *out = f;
     return HB_OK;
+}
+
+int hb_frames_rerun(hb_frames *f, hb_parse *p) {
+    if (!f || !p) return api_fail(HB_ERR_ARG, "null argument");
+    if (p->h_st.n_records != f->n_records || p->n_samples != f->n_samples || p->device != f->device)
+        return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
+    if (!f->n_chunks || !f->n_samples) return HB_OK;
+    return frames_run(f, p);
 }
 
 int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
@@ -437,31 +663,64 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
     info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
     info->raw_bytes = 35ull * f->n_records * f->n_samples;
     info->ms_site = f->ms_site; info->ms_gt = f->ms_gt;
+    info->padded_bytes = f->padded_bytes;
+    info->d_frames = f->d_frames;
+    info->ms_offsets = f->ms_offsets; info->ms_assemble = f->ms_assemble;
+    return HB_OK;
+}
+
+int hb_frames_layout(hb_frames *f, uint64_t *offsets, uint32_t *sizes) {
+    if (!f) return api_fail(HB_ERR_ARG, "null handle");
+    int rc = frames_layout(f);
+    if (rc != HB_OK) return rc;
+    const uint64_t nc = f->n_chunks;
+    for (uint32_t s = 0; s < f->n_samples; ++s)
+        for (uint64_t c = 0; c < nc; ++c) {
+            if (offsets) offsets[s * nc + c] = f->h_rowbase[s] + f->h_rowoff[s * nc + c];
+            if (sizes) sizes[s * nc + c] = f->h_size[s * nc + c];
+        }
+    return HB_OK;
+}
+
+int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap) {
+    if (!f || !buf) return api_fail(HB_ERR_ARG, "null argument");
+    if (cap < f->padded_bytes) return api_fail(HB_ERR_ARG, "buffer too small");
+    if (!f->padded_bytes) return HB_OK;
+    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    cudaError_t e = cudaMemcpyAsync(buf, f->d_frames, f->padded_bytes, cudaMemcpyDeviceToHost, f->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     return HB_OK;
 }
 
 int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *buf, uint64_t cap, uint64_t *total) {
     if (!f) return api_fail(HB_ERR_ARG, "null handle");
     if (s >= f->n_samples) return api_fail(HB_ERR_SAMPLE, "sample index out of range");
-    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    int rc = frames_layout(f);
+    if (rc != HB_OK) return rc;
+    const uint64_t nc = f->n_chunks;
     uint64_t tot = 0;
-    for (uint64_t c = 0; c < f->n_chunks; ++c) {
-        const uint32_t sz = f->h_sizes[(uint64_t)s * f->n_chunks + c];
+    for (uint64_t c = 0; c < nc; ++c) {
+        const uint32_t sz = f->h_size[s * nc + c];
         if (sizes) sizes[c] = sz;
         tot += sz;
     }
     if (total) *total = tot;
-    if (!buf) return HB_OK;
+    if (!buf || !nc) return HB_OK;
     if (cap < tot) return api_fail(HB_ERR_ARG, "buffer too small");
+    // one contiguous D2H of the sample's (16-byte padded) row, then the pads are squeezed out on the host
+    const uint64_t row = f->h_rowbase[s + 1] - f->h_rowbase[s];
+    f->h_row.resize(row);
+    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    cudaError_t e = cudaMemcpyAsync(f->h_row.data(), f->d_frames + f->h_rowbase[s], row, cudaMemcpyDeviceToHost, f->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("D2H of frames failed: ") + cudaGetErrorString(e));
     uint64_t o = 0;
-    for (uint64_t c = 0; c < f->n_chunks; ++c) {
-        const uint32_t sz = f->h_sizes[(uint64_t)s * f->n_chunks + c];
-        cudaError_t e = cudaMemcpyAsync(buf + o, f->d_frames + (c * f->n_samples + s) * (uint64_t)f->slot, sz,
-                                        cudaMemcpyDeviceToHost, f->stream);
-        if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, cudaGetErrorString(e));
+    for (uint64_t c = 0; c < nc; ++c) {
+        const uint32_t sz = f->h_size[s * nc + c];
+        memcpy(buf + o, f->h_row.data() + f->h_rowoff[s * nc + c], sz);
         o += sz;
     }
-    if (cudaStreamSynchronize(f->stream) != cudaSuccess) return api_fail(HB_ERR_CUDA, "D2H of frames failed");
     return HB_OK;
 }
 

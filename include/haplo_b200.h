@@ -134,16 +134,27 @@ typedef struct hb_frames hb_frames;
 typedef struct hb_frames_info {
     uint64_t n_records, n_chunks, chunk_records;
     uint32_t n_samples;
-    uint64_t total_bytes;           /* all frames of all samples */
+    uint64_t total_bytes;           /* all frames of all samples (C_out) */
     uint64_t raw_bytes;             /* 35 * n_records * n_samples */
-    float ms_site, ms_gt;           /* kernel times */
+    float ms_site, ms_gt;           /* kernel times: site templates, allele-plane encoder */
+    uint64_t padded_bytes;          /* size of the device frame buffer: frames start on 16-byte boundaries */
+    const uint8_t *d_frames;        /* device: frames in [sample][chunk] order, see hb_frames_layout */
+    float ms_offsets, ms_assemble;  /* kernel times: size scan, frame assembly (the C_out write) */
 } hb_frames_info;
 
-/* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items.
- * chrom5: the 5 bytes stored in the S5 field for every record (single-CHROM parses). */
+/* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items (at most 2730).
+ * All frames of all samples are produced in one pass and stay in HBM as ONE buffer, laid out
+ * [sample][chunk] with every frame starting on a 16-byte boundary: a sample's dataset is one contiguous
+ * byte range, and the whole buffer can be written to the HDF5 file with one write. */
 int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out);
+/* run the kernels again on the (re-parsed) handle the frames were made from: no allocation unless C_out grew */
+int hb_frames_rerun(hb_frames *f, hb_parse *p);
 int hb_frames_get_info(const hb_frames *f, hb_frames_info *info);
-/* sizes[n_chunks] of one sample's frames; then the frames themselves, concatenated */
+/* offsets (into the frame buffer) and true sizes of every frame, [n_samples][n_chunks]; either may be NULL */
+int hb_frames_layout(hb_frames *f, uint64_t *offsets, uint32_t *sizes);
+/* the whole frame buffer (padded_bytes) in one D2H copy */
+int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap);
+/* sizes[n_chunks] of one sample's frames; then the frames themselves, concatenated without padding */
 int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes, uint8_t *buf, uint64_t cap,
                            uint64_t *total);
 void hb_frames_free(hb_frames *f);
