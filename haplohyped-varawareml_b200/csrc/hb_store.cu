@@ -21,6 +21,7 @@
 // parallel, the first hit is extended with ballots, literals are copied 32 bytes per step.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -356,6 +357,218 @@ __global__ void __launch_bounds__(256) donor_encode_kernel(const DonorArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Allele-plane encoder, bit-parallel (the default).  After the SNP filter the allele bytes are 0 / 1
+// (rarely -9), so the two planes are packed to one bit per byte (B = bit 0, N = "any other bit set")
+// and LZ4 matches are found with word-wide logic instead of byte-wise hashing:
+//   offset 1   (run of equal bytes)                 m1 = ~(B ^ B<<1) & ~(N | N<<1)
+//   offset cr  (same record, the other haplotype;   mc = ~(B1 ^ B0) & ~(N1 | N0)
+//               for plane 0 the zero plane 32 of the site part: mc = ~B0 & ~N0)
+// A byte with N set never matches, so the stream is exact for ANY byte values; it just compresses
+// best on genotype data.  Lanes 0-15 parse 16 segments of plane 0, lanes 16-31 the same segments of
+// plane 1, greedily and independently (a match never crosses a segment); trailing literals of a
+// segment are carried into the next lane's first sequence, an exclusive scan of the encoded sizes
+// gives every lane its output offset, and each lane writes its own sequences.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_lsb4(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
+__device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {       // bit j = byte j has one of bits 1..7 set
+    const uint32_t t = w & 0xFEFEFEFEu;
+    const uint32_t nz = ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u) >> 7;
+    return (nz * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t low_mask(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)); }
+__device__ __forceinline__ int ctz32(uint32_t v) { return __clz(__brev(v)); }       // 32 for 0
+__device__ __forceinline__ int seq_bytes(int lit, int ml) {
+    return 3 + lit + (lit >= 15 ? 1 + (lit - 15) / 255 : 0) + (ml >= 19 ? 1 + (ml - 19) / 255 : 0);
+}
+
+struct DonorBitsArgs {
+    DonorArgs d;
+    uint32_t rb;        // bytes of one raw plane row in shared memory (multiple of 16)
+    uint32_t bww;       // words of one packed bit array (word 0 is a leading zero word)
+    uint32_t caps;      // sequence slots per lane
+};
+
+__global__ void __launch_bounds__(256) donor_encode_bits_kernel(const DonorBitsArgs A) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const DonorArgs &a = A.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (wid >= a.n_chunks * a.n_samples) return;
+    const uint32_t s = (uint32_t)(wid / a.n_chunks);
+    const uint64_t c = wid % a.n_chunks;
+    const int cr = (int)a.cr, n = 2 * cr;
+    uint8_t *base = smem + (size_t)warp * a.warp_smem;
+    uint8_t *raw0 = base, *raw1 = base + A.rb;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(base + 2 * A.rb);      // B0, N0, B1, N1
+    const int BWW = (int)A.bww;
+    uint16_t *seqs = reinterpret_cast<uint16_t *>(bits + 4 * BWW);       // [caps][32]
+    uint8_t *outb = reinterpret_cast<uint8_t *>(seqs + A.caps * 32);
+
+    // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
+    const uint64_t r0 = c * (uint64_t)cr;
+    const int alpha = (int)(r0 & 15);
+    const int valid = (int)min((uint64_t)cr, a.n_records - r0);          // rows past n_records read as zero (HDF5 edge chunk)
+    const int nvec = (alpha + cr + 15) >> 4;
+    for (int i = lane; i < 4 * BWW; i += 32) bits[i] = 0;
+    if (lane < 16) outb[lane] = 0;
+    __syncwarp();
+    const uint64_t rowbase = (uint64_t)(a.s0 + s) * a.gt_stride + (r0 & ~15ull);
+    for (int v = lane; v < 2 * nvec; v += 32) {
+        const int p = v >= nvec, k = v - p * nvec;
+        const int lo = alpha - 16 * k, hi = alpha + valid - 16 * k;      // bytes [lo, hi) of this vector belong to the chunk
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (hi > 0) x = ldg_stream(reinterpret_cast<const uint4 *>((p ? a.gt1 : a.gt0) + rowbase + 16 * k));
+        reinterpret_cast<uint4 *>(p ? raw1 : raw0)[k] = x;
+        uint32_t b16 = pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
+        uint32_t n16 = 0;
+        if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
+            n16 = pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
+        const uint32_t m = low_mask(hi) & ~low_mask(lo) & 0xFFFFu;
+        reinterpret_cast<uint16_t *>(bits + (2 * p) * BWW + 1)[k] = (uint16_t)(b16 & m);
+        reinterpret_cast<uint16_t *>(bits + (2 * p + 1) * BWW + 1)[k] = (uint16_t)(n16 & m);
+    }
+    __syncwarp();
+    if (valid < cr && lane < 16) {               // the vector that straddles n_records: bytes past it must read 0
+        const int idx = alpha + valid + lane;
+        if (idx < ((alpha + valid + 15) & ~15)) { raw0[idx] = 0; raw1[idx] = 0; }
+    }
+    const uint32_t sh16 = a.tmpl_len[c] & 15u;   // lines the slot up with the template's end
+    uint8_t *seq = outb + sh16;
+
+    // ---- 2. per-lane greedy parse of one segment
+    const int p = lane >> 4, q = lane & 15;
+    const int seg = (cr + 15) >> 4;
+    const int a0 = q * seg;
+    const int seglen = max(0, min(seg, cr - a0));
+    const int NW = (seg + 31) >> 5;
+    const uint32_t *B = bits + (2 * p) * BWW + 1, *N = B + BWW;
+    const uint32_t *B0 = bits + 1, *N0 = bits + BWW + 1;
+    const int bi = alpha + a0, j0 = bi >> 5, shb = bi & 31;
+    const int mlimit = (p ? min(seglen, cr - 5 - a0) : seglen);      // positions < mlimit may lie inside a match
+    const int slimit = p ? cr - 11 - a0 : 0x7fffffff;                // positions < slimit may start one
+    uint32_t cb = 0, cn = 0;                                         // the byte in front of the segment
+    if (a0 > 0 && seglen > 0) { const int i = bi - 1; cb = (B[i >> 5] >> (i & 31)) & 1u; cn = (N[i >> 5] >> (i & 31)) & 1u; }
+    else if (p && seglen > 0) { const int i = alpha + cr - 1; cb = (B0[i >> 5] >> (i & 31)) & 1u; cn = (N0[i >> 5] >> (i & 31)) & 1u; }
+
+    int m = 0, prev_end = 0, first_lit = 0, first_ml = 0, size_rest = 0;
+    unsigned long long offmask = 0;
+    bool open = false;
+    int open_off = 0, open_start = 0, open_len = 0;
+    auto record = [&](int st, int ml, int off) {
+        seqs[m * 32 + lane] = (uint16_t)((st << 8) | ml);
+        offmask |= (unsigned long long)off << m;
+        const int lit = st - prev_end;
+        if (m == 0) { first_lit = lit; first_ml = ml; }
+        else size_rest += seq_bytes(lit, ml);
+        prev_end = st + ml;
+        ++m;
+    };
+    uint32_t m1c = 0, mcc = 0, m1n, mcn;
+    auto masks = [&](int k, uint32_t &m1, uint32_t &mc) {
+        if (k >= NW) { m1 = mc = 0; return; }
+        const uint32_t bw = __funnelshift_r(B[j0 + k], B[j0 + k + 1], shb);
+        const uint32_t nw = __funnelshift_r(N[j0 + k], N[j0 + k + 1], shb);
+        const uint32_t bprev = (bw << 1) | cb, nprev = (nw << 1) | cn;
+        cb = bw >> 31; cn = nw >> 31;
+        const uint32_t vm = low_mask(mlimit - 32 * k);
+        m1 = ~(bw ^ bprev) & ~(nw | nprev) & vm;
+        if (p) {
+            const uint32_t b0w = __funnelshift_r(B0[j0 + k], B0[j0 + k + 1], shb);
+            const uint32_t n0w = __funnelshift_r(N0[j0 + k], N0[j0 + k + 1], shb);
+            mc = ~(bw ^ b0w) & ~(nw | n0w) & vm;
+        } else mc = ~bw & ~nw & vm;
+    };
+    masks(0, m1c, mcc);
+    for (int k = 0; k < NW; ++k) {
+        masks(k + 1, m1n, mcn);
+        const uint32_t r1 = m1c & __funnelshift_r(m1c, m1n, 1) & __funnelshift_r(m1c, m1n, 2) & __funnelshift_r(m1c, m1n, 3);
+        const uint32_t rc = mcc & __funnelshift_r(mcc, mcn, 1) & __funnelshift_r(mcc, mcn, 2) & __funnelshift_r(mcc, mcn, 3);
+        const uint32_t r = (r1 | rc) & low_mask(slimit - 32 * k);
+        int pos = 0;
+        if (open) {
+            const int cont = ctz32(~(open_off ? mcc : m1c));
+            open_len += cont;
+            pos = cont;
+            if (cont < 32) { record(open_start, open_len, open_off); open = false; }
+        }
+        while (pos < 32) {
+            const uint32_t x = r & (0xFFFFFFFFu << pos);
+            if (!x) break;
+            const int st = ctz32(x);
+            const int l1 = ctz32(~(m1c >> st)), lc = ctz32(~(mcc >> st));
+            // a run that reaches the end of this word is measured on into the next one, so that the
+            // offset chosen is the one whose run is really the longer (and >= 4, as r promises)
+            const int l1x = st + l1 == 32 ? l1 + ctz32(~m1n) : l1, lcx = st + lc == 32 ? lc + ctz32(~mcn) : lc;
+            const int off = lcx > l1x;
+            const int best = off ? lc : l1;
+            if (st + best >= 32) { open = true; open_off = off; open_start = 32 * k + st; open_len = 32 - st; break; }
+            record(32 * k + st, best, off);
+            pos = st + best;
+        }
+        m1c = m1n; mcc = mcn;
+    }
+    if (open) record(open_start, open_len, open_off);
+    const int trail = seglen - prev_end;
+
+    // ---- 3. carry trailing literals forward, size scan
+    int val = trail, flag = m > 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v2 = __shfl_up_sync(0xffffffffu, val, d), f2 = __shfl_up_sync(0xffffffffu, flag, d);
+        if (lane >= d && !flag) { val += v2; flag = f2; }
+    }
+    int carry = __shfl_up_sync(0xffffffffu, val, 1);
+    if (lane == 0) carry = 0;
+    const int final_lit = __shfl_sync(0xffffffffu, val, 31);
+    const int mysize = m > 0 ? seq_bytes(first_lit + carry, first_ml) + size_rest : 0;
+    int inc = mysize;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+
+    // ---- 4. every lane writes its own sequences
+    {
+        int o = inc - mysize;
+        int prev_abs = p * cr + a0 - carry;
+        for (int j = 0; j < m; ++j) {
+            const uint32_t e = seqs[j * 32 + lane];
+            const int st = p * cr + a0 + (int)(e >> 8), ml = (int)(e & 255u);
+            const int off = ((offmask >> j) & 1ull) ? cr : 1;
+            const int lit = st - prev_abs;
+            seq[o++] = (uint8_t)((min(lit, 15) << 4) | min(ml - 4, 15));
+            if (lit >= 15) { int rem = lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
+            for (int i = 0; i < lit; ++i) { const int P = prev_abs + i; seq[o++] = P < cr ? raw0[alpha + P] : raw1[alpha + P - cr]; }
+            seq[o++] = (uint8_t)off; seq[o++] = (uint8_t)(off >> 8);
+            if (ml >= 19) { int rem = ml - 19; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
+            prev_abs = st + ml;
+        }
+    }
+    // the last sequence of the block: literals only (at least the 5 bytes the format demands)
+    int o = total;
+    if (lane == 0) seq[o] = (uint8_t)(min(final_lit, 15) << 4);
+    ++o;
+    if (final_lit >= 15) {
+        int rem = final_lit - 15;
+        while (rem >= 255) { if (lane == 0) seq[o] = 255; ++o; rem -= 255; }
+        if (lane == 0) seq[o] = (uint8_t)rem;
+        ++o;
+    }
+    for (int i = lane; i < final_lit; i += 32) { const int P = n - final_lit + i; seq[o + i] = P < cr ? raw0[alpha + P] : raw1[alpha + P - cr]; }
+    const int dlen = o + final_lit;
+
+    // ---- 5. constant frame tail, pad, copy out
+    for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
+    const uint32_t used = sh16 + (uint32_t)dlen + FRAME_TAIL;
+    for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
+    __syncwarp();
+    uint4 *dstp = reinterpret_cast<uint4 *>(a.stage + wid * (uint64_t)a.dslot);
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
+    for (uint32_t i = lane; i < (used + 15) / 16; i += 32) dstp[i] = srcp[i];
+    if (lane == 0) a.dlen[wid] = (uint32_t)dlen;
+}
+
+// ------------------------------------------------------------------------------------------
 // frame sizes -> offsets.  Frames are laid out [sample][chunk], each starting on a 16-byte boundary.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -493,6 +706,8 @@ struct hb_frames {
     cudaStream_t stream = nullptr;
     uint64_t n_records = 0, n_chunks = 0, cr = 0;
     uint32_t n_samples = 0, tmpl_cap = 0, dslot = 0, warp_smem = 0;
+    uint32_t rb = 0, bww = 0, caps = 0;      // bit-parallel allele encoder geometry
+    bool bits_encoder = true;                // false: the byte-wise warp LZ4 matcher (HB_DONOR_ENCODER=lz4, and for chunks of < 6 records)
     int warps_per_cta = 8;
     size_t smem_site = 0;
     uint8_t *d_tmpl = nullptr, *d_stage = nullptr, *d_frames = nullptr;
@@ -532,7 +747,13 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     da.tmpl_len = f->d_tmpl_len; da.stage = f->d_stage; da.dslot = f->dslot; da.dlen = f->d_dlen;
     da.warp_smem = f->warp_smem;
     const int wpc = f->warps_per_cta;
-    donor_encode_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(da);
+    if (f->bits_encoder) {
+        DonorBitsArgs ba;
+        ba.d = da; ba.rb = f->rb; ba.bww = f->bww; ba.caps = f->caps;
+        donor_encode_bits_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(ba);
+    } else {
+        donor_encode_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(da);
+    }
     count_launch();
     CUF(cudaEventRecord(f->ev[2], f->stream));
     frame_offsets_kernel<<<f->n_samples, 256, 0, f->stream>>>(f->d_tmpl_len, f->d_dlen, (uint32_t)f->n_chunks, f->d_size,
@@ -622,7 +843,16 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     f->smem_site = 16 + ((n_site + 19) & ~15u) + f->tmpl_cap + (2u << 12);
     if (f->smem_site > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
     f->dslot = (16 + bound(n_gt) + FRAME_TAIL + 15) & ~15u;
-    f->warp_smem = (kHist + ((n_gt + 19) & ~15u) + f->dslot + (2u << 10) + 15) & ~15u;
+    const char *enc = getenv("HB_DONOR_ENCODER");
+    f->bits_encoder = cr >= 6 && !(enc && !strcmp(enc, "lz4"));
+    if (f->bits_encoder) {
+        f->rb = ((15 + cr + 15) & ~15u) + 16;
+        f->bww = ((cr + 30) / 32 + 4 + 3) & ~3u;
+        f->caps = ((cr + 15) / 16) / 4 + 2;
+        f->warp_smem = 2 * f->rb + 16 * f->bww + 64 * f->caps + f->dslot;
+    } else {
+        f->warp_smem = (kHist + ((n_gt + 19) & ~15u) + f->dslot + (2u << 10) + 15) & ~15u;
+    }
     f->warps_per_cta = 8;
     while (f->warps_per_cta > 1 && (size_t)f->warps_per_cta * f->warp_smem > 200 * 1024) f->warps_per_cta >>= 1;
     if ((size_t)f->warps_per_cta * f->warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
@@ -640,7 +870,8 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     ck(cudaMalloc(&f->d_sum, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
     ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_site));
-    ck(cudaFuncSetAttribute(donor_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
+    if (f->bits_encoder) ck(cudaFuncSetAttribute(donor_encode_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
+    else ck(cudaFuncSetAttribute(donor_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
     if (e != cudaSuccess) { hb_frames_free(f); return api_fail(HB_ERR_MEM, std::string("CUDA: ") + cudaGetErrorString(e)); }
     int rc = frames_run(f, p);
     if (rc != HB_OK) { hb_frames_free(f); return rc; }

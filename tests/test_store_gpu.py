@@ -103,6 +103,30 @@ def test_synthetic_shapes_chunks_roundtrip(capi):
         assert info.total_bytes < info.raw_bytes
 
 
+@pytest.mark.parametrize("mix,chunk_records", [(0, 1075), (0, 1465), (1, 2730), (1, 777), (0, 33)])
+def test_long_segments_and_layout(capi, mix, chunk_records):
+    """Chunk sizes of the bench shapes (1075 = 1.1M variants, 1465 = 3M) and the largest one: the bit-parallel
+    allele encoder then walks several mask words per lane.  Also pins the buffer layout: [sample][chunk],
+    16-byte aligned, fetch_all + layout agree with the per-sample fetch."""
+    spec = capi.synth_spec(7000, 96, seed=31 + mix, mix=mix)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    _check(capi, text, spec.n_samples, "chr22", chunk_records, [0, 1, 47, 95])
+    p = capi.Parse.from_host(synth.body_of(text), spec.n_samples, region="chr22")
+    fr = p.compress(chunk_records)
+    offs, sizes = fr.layout()
+    buf = fr.fetch_all()
+    assert offs.shape == (96, fr.info.n_chunks) and (offs % 16 == 0).all()
+    flat = offs.reshape(-1)
+    assert (np.diff(flat.astype(np.int64)) >= sizes.reshape(-1)[:-1]).all()          # [sample][chunk] order, no overlap
+    assert int(sizes.sum()) == fr.info.total_bytes and len(buf) == fr.info.padded_bytes
+    for s in (0, 95):
+        for k, f in enumerate(fr.sample(s)):
+            o = int(offs[s, k])
+            assert buf[o:o + int(sizes[s, k])].tobytes() == f
+    fr.rerun(p)                                                                       # deterministic: same bytes again
+    assert np.array_equal(fr.fetch_all(), buf)
+
+
 def test_tiny_and_empty(capi):
     S = ["a", "b"]
     one = (synth.header(S) + "chr22\t5\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1|1\n").encode()
