@@ -1,8 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- genotype calls/sec of the VCF -> tensor hot path on B200.
 
-A "step" = one pass of tokenize -> site extraction -> GT decode (kernels 1-3, output in the
-byte-shuffled planar layout) over one synthetic VCF body resident in HBM.  N=1 workload:
+A "step" = one pass of the whole device-resident path over one synthetic VCF body resident in HBM:
+record location (head walker / tokenizer) -> site extraction -> GT decode (kernels 1-3, output in the
+byte-shuffled planar layout) -> kernel 4 (site templates, allele-plane LZ4, size scan, frame assembly):
+decompressed text in, Blosc2 frames of every (donor, HDF5 chunk) out -- SURVEY.md 8(d)'s timing span.
+`--parse-only` times kernels 1-3 alone.  N=1 workload:
 BASELINE.json configs[1] (synthetic chr22-like, 1.1M biallelic variants x 2504 phased samples,
 ~11.1 GB of text).  N>1: every rank parses its own chromosome-sized shard of that shape (the
 path shards by chromosome / BGZF range with no collective on the data path); a 6-int64
@@ -160,6 +163,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--parse-only", action="store_true", help="step = kernels 1-3 only (no Blosc2 frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -198,8 +202,15 @@ def main():
     meta = torch.zeros(6, dtype=torch.int64, device=dev)
     gathered = [torch.zeros(6, dtype=torch.int64, device=dev) for _ in range(world)]
 
+    frames = [None]
+
     def step(p):
         p.rerun()
+        if not args.parse_only:
+            if frames[0] is None:
+                frames[0] = p.compress(0)           # first call allocates (warm-up)
+            else:
+                frames[0].rerun(p)
         if world > 1:            # the path's only exchange: per-shard index metadata
             i = p.info
             meta[0], meta[1], meta[2] = int(i.n_records), int(i.n_lines), int(i.text_bytes)
@@ -207,6 +218,8 @@ def main():
 
     # first parse allocates; it is warm-up step 1
     p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr22", device=local, stream=stream)
+    if not args.parse_only:
+        frames[0] = p.compress(0)
     for _ in range(args.warmup - 1):
         step(p)
     info = p.info
@@ -217,11 +230,16 @@ def main():
     clocks = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tok, sit, dec = [], [], []
+    k4 = {"site_templates": [], "allele_encode": [], "offsets": [], "assemble": []}
     ev0.record()
     for _ in range(args.steps):
         step(p)
         i = p.info
         tok.append(i.ms_tokenize); sit.append(i.ms_sites); dec.append(i.ms_decode)
+        if frames[0] is not None:
+            fi = frames[0].info
+            k4["site_templates"].append(fi.ms_site); k4["allele_encode"].append(fi.ms_gt)
+            k4["offsets"].append(fi.ms_offsets); k4["assemble"].append(fi.ms_assemble)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -284,17 +302,36 @@ def main():
         med = lambda a: float(sorted(a)[len(a) // 2])
         alg_tok = T
         alg_dec = 4.0 * Vk * S + 2.0 * Vk * S
-        alg_all = T + 2.0 * Vk * S + 33.0 * Vk
+        alg_parse = T + 2.0 * Vk * S + 33.0 * Vk
         step_s = ms / 1e3 / args.steps
-        dec_gbs = alg_dec / (med(dec) / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "decode_gt_kernel", "achieved": dec_gbs, "peak": peak, "unit": "GB/s",
-                "frac": dec_gbs / peak, "traffic": None, "peak_source": peak_src, "nominal_peak": NOMINAL_HBM_GBS,
-                "algorithmic_bytes_per_launch": alg_dec, "ms_per_launch": med(dec),
+        stages = {"locate_records": {"ms": med(tok), "gbs": alg_tok / (med(tok) / 1e3) / 1e9, "bytes": alg_tok,
+                                     "note": "head walker reads ~2% of the text; tokenizer reads all of it"},
+                  "sites": {"ms": med(sit)},
+                  "decode_gt": {"ms": med(dec), "gbs": alg_dec / (med(dec) / 1e3) / 1e9, "bytes": alg_dec}}
+        alg_all = alg_parse
+        store = None
+        if frames[0] is not None:
+            fi = frames[0].info
+            c_out = float(fi.total_bytes)
+            alg_store = 2.0 * Vk * S + 33.0 * Vk + c_out
+            alg_all = alg_parse + alg_store
+            stages["site_templates"] = {"ms": med(k4["site_templates"])}
+            stages["allele_encode"] = {"ms": med(k4["allele_encode"]), "bytes": 2.0 * Vk * S,
+                                       "gbs": 2.0 * Vk * S / (med(k4["allele_encode"]) / 1e3) / 1e9}
+            stages["offsets"] = {"ms": med(k4["offsets"])}
+            stages["assemble"] = {"ms": med(k4["assemble"]), "bytes": c_out, "gbs": c_out / (med(k4["assemble"]) / 1e3) / 1e9}
+            store = {"c_out_bytes": int(c_out), "frames": int(fi.n_chunks) * S, "chunk_records": int(fi.chunk_records),
+                     "compression_ratio": float(fi.raw_bytes) / max(1.0, c_out), "raw_bytes_logical": int(fi.raw_bytes)}
+        # the dominant kernel = the stage with the largest measured time that has algorithmic bytes
+        dom = max((k for k in stages if "bytes" in stages[k]), key=lambda k: stages[k]["ms"])
+        roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src, "nominal_peak": NOMINAL_HBM_GBS,
+                "algorithmic_bytes_per_launch": stages[dom]["bytes"], "ms_per_launch": stages[dom]["ms"],
                 "path": {"algorithmic_bytes": alg_all, "gbs": alg_all / step_s / 1e9, "frac": alg_all / step_s / 1e9 / peak,
-                         "definition": "T + 2*V'*S + 33*V' per step (SURVEY.md 8d), whole step incl. host syncs"},
-                "stages": {"tokenize": {"ms": med(tok), "gbs": alg_tok / (med(tok) / 1e3) / 1e9, "bytes": alg_tok},
-                           "sites": {"ms": med(sit)},
-                           "decode_gt": {"ms": med(dec), "gbs": dec_gbs, "bytes": alg_dec}}}
+                         "definition": ("T + 2*(2*V'*S + 33*V') + C_out per step (SURVEY.md 8d 'fused total'), whole step incl. host syncs"
+                                        if frames[0] is not None else
+                                        "T + 2*V'*S + 33*V' per step (SURVEY.md 8d parse+decode), whole step incl. host syncs")},
+                "stages": stages, "store": store}
         cpu = None
         if not args.no_cpu:
             nv = args.cpu_sample_variants
@@ -309,9 +346,12 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
                 "variants_per_s": float(V) * world / step_s, "records_kept": Vk, "text_bytes_per_rank": T,
+                "step": "parse only (kernels 1-3)" if args.parse_only else "text -> Blosc2 frames (kernels 1-4)",
                 "tokenizer": int(info.tokenizer_used), "parity_spot_check": parity,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
+    if frames[0] is not None:
+        frames[0].close()
     p.close()
     if world > 1:
         dist.destroy_process_group()
