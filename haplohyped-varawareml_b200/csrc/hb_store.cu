@@ -33,7 +33,6 @@
 
 namespace hb {
 
-constexpr int kHist = 64;                 // bytes of history kept in front of the donor planes
 constexpr int FRAME_HDR = 97, CHUNK_HDR = 32, OFFS_CHUNK = 40, FRAME_TRAILER = 35;
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {     // unaligned 4-byte read (shared memory)
@@ -148,13 +147,15 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
 // Kernels:
 //   site_template_kernel   one CTA per chunk: site planes -> LZ4; writes the frame TEMPLATE (header with
 //                          the donor-dependent fields left zero + shared LZ4 head), 16-byte aligned.
-//   donor_encode_kernel    one warp per (sample, chunk): allele planes -> LZ4 tail of the same block;
-//                          writes [pad][sequences][offsets chunk][trailer] into a staging slot, shifted
-//                          so that it lines up with the template's end modulo 16.
-//   frame_offsets_kernel / row_base_kernel   frame sizes -> 16-byte aligned offsets, [sample][chunk] order.
-//   assemble_kernel        one warp per frame: 16-byte vector copy template + staged tail -> final
-//                          position, patching the four size fields in registers.  This is where the
-//                          bytes go: C_out is written exactly once, the templates stay in L2.
+//   donor_frames_kernel    one warp per (sample, chunk) frame, fused: allele planes -> LZ4 tail of the
+//                          block (bit-parallel matcher, below) -> template (from L2) + own tail (from
+//                          shared memory) written straight to the frame's slot with 16-byte vector
+//                          stores, the four size fields patched in registers.  C_out is written exactly
+//                          once and nothing else of size leaves the SM; warps never wait on each other.
+// Output: ONE buffer of slots in [sample][chunk] order.  The slot of (sample s, chunk c) starts at
+// s * row_stride + slot_off[c]; slot_off is the running sum of round16(template_len[c] + worst-case
+// allele tail), so every frame's address is known before it is encoded (no scan, no look-back) and the
+// layout is deterministic.  A frame fills the front of its slot; its true length is recorded.
 // ------------------------------------------------------------------------------------------
 constexpr int TMPL_HDR = FRAME_HDR + CHUNK_HDR + 8;        // 137 bytes of a frame precede its LZ4 block
 constexpr int FRAME_TAIL = OFFS_CHUNK + FRAME_TRAILER;     // 75 bytes follow it
@@ -299,76 +300,28 @@ __global__ void __launch_bounds__(256) site_template_kernel(const SiteArgs4 a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// one warp per (sample, chunk): allele planes -> LZ4 tail of the block -> staging slot
+// Allele-plane encoder, bit-parallel.  After the SNP filter the allele bytes are 0 / 1 (rarely -9), so
+// the two planes are packed to one bit per byte (B = bit 0, N = "any other bit set") and LZ4 matches
+// are found with word-wide logic instead of byte-wise hashing.  Two match sources:
+//   Z  a zero byte: matches the all-zero site plane two planes back      (offset 2*cr),  Z = ~B & ~N
+//   C  plane 1 only: equal to the same record's byte in plane 0           (offset cr),    C = ~(B1^B0) & ~(N1|N0)
+// A byte with N set never matches, so the stream is exact for ANY byte values; it just compresses
+// best on genotype data.  Runs of >= 5 Z positions become matches first, then runs of >= 4 C positions
+// in what is left; everything else is literal.  Lanes 0-15 own 16 segments of plane 0, lanes 16-31 the
+// same segments of plane 1 (a match never crosses a segment); trailing literals of a segment are
+// carried into the next lane's first sequence; warp scans give every lane its output offset, its first
+// global sequence index and literal index; each lane writes the headers of its own sequences, then all
+// literals of the frame are copied in one balanced pass (32 equal shares of the literal index space).
 // ------------------------------------------------------------------------------------------
-struct DonorArgs {
-    const int8_t *gt0, *gt1;
-    uint64_t gt_stride, n_records;
-    uint32_t cr, n_samples, s0;  // samples [s0, s0 + n_samples)
-    uint64_t n_chunks;
-    const uint32_t *tmpl_len;
-    uint8_t *stage;              // [n_samples * n_chunks][dslot]
-    uint32_t dslot;
-    uint32_t *dlen;              // [n_samples * n_chunks] LZ4 bytes of the allele planes
-    uint32_t warp_smem;          // bytes of shared memory per warp
-};
-
-__global__ void __launch_bounds__(256) donor_encode_kernel(const DonorArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (wid >= a.n_chunks * a.n_samples) return;
-    const uint32_t s = (uint32_t)(wid / a.n_chunks);
-    const uint64_t c = wid % a.n_chunks;
-    const uint32_t cr = a.cr, n = 2u * cr;
-    uint8_t *base = smem + (size_t)warp * a.warp_smem;
-    uint8_t *src = base + kHist;                                   // history sits right in front
-    uint8_t *outb = src + ((n + 19) & ~15u);
-    uint16_t *table = reinterpret_cast<uint16_t *>(outb + a.dslot);
-    // history (the zero tail of the site planes) + the two allele planes (zero-padded past n_records,
-    // like an HDF5 edge chunk)
-    for (int i = lane; i < kHist; i += 32) base[i] = 0;
-    const uint64_t r0 = c * cr;
-    const int8_t *g0 = a.gt0 + (uint64_t)(a.s0 + s) * a.gt_stride + r0, *g1 = a.gt1 + (uint64_t)(a.s0 + s) * a.gt_stride + r0;
-    for (uint32_t i = lane; i < cr; i += 32) {
-        const bool in = r0 + i < a.n_records;
-        src[i] = in ? (uint8_t)g0[i] : 0;
-        src[cr + i] = in ? (uint8_t)g1[i] : 0;
-    }
-    const uint32_t sh = a.tmpl_len[c] & 15u;                       // lines the slot up with the template's end
-    if (lane < 16) outb[lane] = 0;
-    __syncwarp();
-    uint8_t *seq = outb + sh;
-    int dlen;
-    if (cr < 6) {                                  // raw block, see site_template_kernel
-        for (uint32_t i = lane; i < n; i += 32) seq[i] = src[i];
-        dlen = (int)n;
-    } else {
-        dlen = warp_lz4(src, (int)n, min(kHist, 9 * (int)cr - 1), 0, true, seq, table, 10, nullptr);
-    }
-    for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
-    const uint32_t used = sh + (uint32_t)dlen + FRAME_TAIL;
-    for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
-    __syncwarp();
-    uint4 *dstp = reinterpret_cast<uint4 *>(a.stage + wid * (uint64_t)a.dslot);
-    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
-    for (uint32_t i = lane; i < (used + 15) / 16; i += 32) dstp[i] = srcp[i];
-    if (lane == 0) a.dlen[wid] = (uint32_t)dlen;
+__device__ __forceinline__ uint4 ldg_nc(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
 }
 
-// ------------------------------------------------------------------------------------------
-// Allele-plane encoder, bit-parallel (the default).  After the SNP filter the allele bytes are 0 / 1
-// (rarely -9), so the two planes are packed to one bit per byte (B = bit 0, N = "any other bit set")
-// and LZ4 matches are found with word-wide logic instead of byte-wise hashing:
-//   offset 1   (run of equal bytes)                 m1 = ~(B ^ B<<1) & ~(N | N<<1)
-//   offset cr  (same record, the other haplotype;   mc = ~(B1 ^ B0) & ~(N1 | N0)
-//               for plane 0 the zero plane 32 of the site part: mc = ~B0 & ~N0)
-// A byte with N set never matches, so the stream is exact for ANY byte values; it just compresses
-// best on genotype data.  Lanes 0-15 parse 16 segments of plane 0, lanes 16-31 the same segments of
-// plane 1, greedily and independently (a match never crosses a segment); trailing literals of a
-// segment are carried into the next lane's first sequence, an exclusive scan of the encoded sizes
-// gives every lane its output offset, and each lane writes its own sequences.
-// ------------------------------------------------------------------------------------------
+constexpr int kMinZ = 5, kMinC = 4;
+constexpr int kWpc = 4;                       // warps (= frames) per CTA
+
 __device__ __forceinline__ uint32_t pack_lsb4(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
 __device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {       // bit j = byte j has one of bits 1..7 set
     const uint32_t t = w & 0xFEFEFEFEu;
@@ -377,294 +330,280 @@ __device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {       // bit j = byte
 }
 __device__ __forceinline__ uint32_t low_mask(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)); }
 __device__ __forceinline__ int ctz32(uint32_t v) { return __clz(__brev(v)); }       // 32 for 0
-__device__ __forceinline__ int seq_bytes(int lit, int ml) {
-    return 3 + lit + (lit >= 15 ? 1 + (lit - 15) / 255 : 0) + (ml >= 19 ? 1 + (ml - 19) / 255 : 0);
+__device__ __forceinline__ int lit_ext(int lit) { return lit >= 15 ? 1 + (lit - 15) / 255 : 0; }
+
+// R = the positions of X that lie inside a run of at least MINRUN consecutive ones (multi-word, LSB first)
+template <int NW, int MINRUN>
+__device__ __forceinline__ void runs_cover(const uint32_t (&X)[NW], uint32_t (&R)[NW]) {
+    uint32_t S[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const uint32_t nxt = k + 1 < NW ? X[k + 1] : 0u;
+        uint32_t s = X[k];
+#pragma unroll
+        for (int d = 1; d < MINRUN; ++d) s &= __funnelshift_r(X[k], nxt, d);
+        S[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const uint32_t prv = k > 0 ? S[k - 1] : 0u;
+        uint32_t r = S[k];
+#pragma unroll
+        for (int d = 1; d < MINRUN; ++d) r |= __funnelshift_l(prv, S[k], d);
+        R[k] = r;
+    }
 }
 
-struct DonorBitsArgs {
-    DonorArgs d;
+struct FusedArgs {
+    const int8_t *gt0, *gt1;
+    uint64_t gt_stride, n_records;
+    uint32_t cr, n_samples, s0;          // samples [s0, s0 + n_samples)
+    uint64_t n_chunks;
+    const uint8_t *tmpl; uint32_t tmpl_cap; const uint32_t *tmpl_len;
+    uint8_t *frames;
+    const uint64_t *slot_off;            // [n_chunks + 1] offset of chunk c's slot inside a sample row; [n_chunks] = row stride
+    uint32_t *size;                      // [n_samples * n_chunks] true length of each frame
+    unsigned long long *totals;          // [0] sum of frame lengths
     uint32_t rb;        // bytes of one raw plane row in shared memory (multiple of 16)
     uint32_t bww;       // words of one packed bit array (word 0 is a leading zero word)
     uint32_t caps;      // sequence slots per lane
+    uint32_t dcap;      // literal-run descriptors per frame (non-empty runs only)
+    uint32_t outcap;    // bytes of the frame-tail buffer
+    uint32_t warp_smem;
 };
 
-__global__ void __launch_bounds__(256) donor_encode_bits_kernel(const DonorBitsArgs A) {
+template <int NW>
+__global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const DonorArgs &a = A.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (wid >= a.n_chunks * a.n_samples) return;
-    const uint32_t s = (uint32_t)(wid / a.n_chunks);
-    const uint64_t c = wid % a.n_chunks;
-    const int cr = (int)a.cr, n = 2 * cr;
-    uint8_t *base = smem + (size_t)warp * a.warp_smem;
+    const uint64_t n_frames = A.n_chunks * A.n_samples;
+    const uint64_t wid = (uint64_t)blockIdx.x * kWpc + warp;
+    if (wid >= n_frames) return;
+    const bool active = true;
+    const int cr = (int)A.cr, n = 2 * cr;
+    uint8_t *base = smem + (size_t)warp * A.warp_smem;
     uint8_t *raw0 = base, *raw1 = base + A.rb;
     uint32_t *bits = reinterpret_cast<uint32_t *>(base + 2 * A.rb);      // B0, N0, B1, N1
     const int BWW = (int)A.bww;
     uint16_t *seqs = reinterpret_cast<uint16_t *>(bits + 4 * BWW);       // [caps][32]
-    uint8_t *outb = reinterpret_cast<uint8_t *>(seqs + A.caps * 32);
+    uint32_t *d_sd = reinterpret_cast<uint32_t *>(seqs + A.caps * 32);   // literal runs: source position | destination << 16
+    uint16_t *d_cum = reinterpret_cast<uint16_t *>(d_sd + A.dcap);       //               literal index of the run's first byte
+    uint8_t *outb = reinterpret_cast<uint8_t *>(d_cum + A.dcap);
 
-    // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
-    const uint64_t r0 = c * (uint64_t)cr;
-    const int alpha = (int)(r0 & 15);
-    const int valid = (int)min((uint64_t)cr, a.n_records - r0);          // rows past n_records read as zero (HDF5 edge chunk)
-    const int nvec = (alpha + cr + 15) >> 4;
-    for (int i = lane; i < 4 * BWW; i += 32) bits[i] = 0;
-    if (lane < 16) outb[lane] = 0;
-    __syncwarp();
-    const uint64_t rowbase = (uint64_t)(a.s0 + s) * a.gt_stride + (r0 & ~15ull);
-    for (int v = lane; v < 2 * nvec; v += 32) {
-        const int p = v >= nvec, k = v - p * nvec;
-        const int lo = alpha - 16 * k, hi = alpha + valid - 16 * k;      // bytes [lo, hi) of this vector belong to the chunk
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (hi > 0) x = ldg_stream(reinterpret_cast<const uint4 *>((p ? a.gt1 : a.gt0) + rowbase + 16 * k));
-        reinterpret_cast<uint4 *>(p ? raw1 : raw0)[k] = x;
-        uint32_t b16 = pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
-        uint32_t n16 = 0;
-        if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
-            n16 = pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
-        const uint32_t m = low_mask(hi) & ~low_mask(lo) & 0xFFFFu;
-        reinterpret_cast<uint16_t *>(bits + (2 * p) * BWW + 1)[k] = (uint16_t)(b16 & m);
-        reinterpret_cast<uint16_t *>(bits + (2 * p + 1) * BWW + 1)[k] = (uint16_t)(n16 & m);
-    }
-    __syncwarp();
-    if (valid < cr && lane < 16) {               // the vector that straddles n_records: bytes past it must read 0
-        const int idx = alpha + valid + lane;
-        if (idx < ((alpha + valid + 15) & ~15)) { raw0[idx] = 0; raw1[idx] = 0; }
-    }
-    const uint32_t sh16 = a.tmpl_len[c] & 15u;   // lines the slot up with the template's end
-    uint8_t *seq = outb + sh16;
+    uint32_t tl = 0;
+    int dlen = 0, alpha = 0;
+    uint64_t c = 0;
+    // state of the parse that the emission needs
+    int m = 0, carry = 0, a0 = 0, p = 0, first_ml = 0;
+    (void)active;
+    unsigned long long kindmask = 0;
+    int out_base = 0, run_base = 0, lit_base = 0, total = 0, totrun = 0, totlit = 0, final_lit = 0;
+    uint32_t sidx = 0;
 
-    // ---- 2. per-lane greedy parse of one segment
-    const int p = lane >> 4, q = lane & 15;
-    const int seg = (cr + 15) >> 4;
-    const int a0 = q * seg;
-    const int seglen = max(0, min(seg, cr - a0));
-    const int NW = (seg + 31) >> 5;
-    const uint32_t *B = bits + (2 * p) * BWW + 1, *N = B + BWW;
-    const uint32_t *B0 = bits + 1, *N0 = bits + BWW + 1;
-    const int bi = alpha + a0, j0 = bi >> 5, shb = bi & 31;
-    const int mlimit = (p ? min(seglen, cr - 5 - a0) : seglen);      // positions < mlimit may lie inside a match
-    const int slimit = p ? cr - 11 - a0 : 0x7fffffff;                // positions < slimit may start one
-    uint32_t cb = 0, cn = 0;                                         // the byte in front of the segment
-    if (a0 > 0 && seglen > 0) { const int i = bi - 1; cb = (B[i >> 5] >> (i & 31)) & 1u; cn = (N[i >> 5] >> (i & 31)) & 1u; }
-    else if (p && seglen > 0) { const int i = alpha + cr - 1; cb = (B0[i >> 5] >> (i & 31)) & 1u; cn = (N0[i >> 5] >> (i & 31)) & 1u; }
-
-    int m = 0, prev_end = 0, first_lit = 0, first_ml = 0, size_rest = 0;
-    unsigned long long offmask = 0;
-    bool open = false;
-    int open_off = 0, open_start = 0, open_len = 0;
-    auto record = [&](int st, int ml, int off) {
-        seqs[m * 32 + lane] = (uint16_t)((st << 8) | ml);
-        offmask |= (unsigned long long)off << m;
-        const int lit = st - prev_end;
-        if (m == 0) { first_lit = lit; first_ml = ml; }
-        else size_rest += seq_bytes(lit, ml);
-        prev_end = st + ml;
-        ++m;
-    };
-    uint32_t m1c = 0, mcc = 0, m1n, mcn;
-    auto masks = [&](int k, uint32_t &m1, uint32_t &mc) {
-        if (k >= NW) { m1 = mc = 0; return; }
-        const uint32_t bw = __funnelshift_r(B[j0 + k], B[j0 + k + 1], shb);
-        const uint32_t nw = __funnelshift_r(N[j0 + k], N[j0 + k + 1], shb);
-        const uint32_t bprev = (bw << 1) | cb, nprev = (nw << 1) | cn;
-        cb = bw >> 31; cn = nw >> 31;
-        const uint32_t vm = low_mask(mlimit - 32 * k);
-        m1 = ~(bw ^ bprev) & ~(nw | nprev) & vm;
-        if (p) {
-            const uint32_t b0w = __funnelshift_r(B0[j0 + k], B0[j0 + k + 1], shb);
-            const uint32_t n0w = __funnelshift_r(N0[j0 + k], N0[j0 + k + 1], shb);
-            mc = ~(bw ^ b0w) & ~(nw | n0w) & vm;
-        } else mc = ~bw & ~nw & vm;
-    };
-    masks(0, m1c, mcc);
-    for (int k = 0; k < NW; ++k) {
-        masks(k + 1, m1n, mcn);
-        const uint32_t r1 = m1c & __funnelshift_r(m1c, m1n, 1) & __funnelshift_r(m1c, m1n, 2) & __funnelshift_r(m1c, m1n, 3);
-        const uint32_t rc = mcc & __funnelshift_r(mcc, mcn, 1) & __funnelshift_r(mcc, mcn, 2) & __funnelshift_r(mcc, mcn, 3);
-        const uint32_t r = (r1 | rc) & low_mask(slimit - 32 * k);
-        int pos = 0;
-        if (open) {
-            const int cont = ctz32(~(open_off ? mcc : m1c));
-            open_len += cont;
-            pos = cont;
-            if (cont < 32) { record(open_start, open_len, open_off); open = false; }
+    if (active) {
+        const uint32_t s = (uint32_t)(wid / A.n_chunks);
+        sidx = s;
+        c = wid % A.n_chunks;
+        tl = A.tmpl_len[c];
+        // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
+        const uint64_t r0 = c * (uint64_t)cr;
+        alpha = (int)(r0 & 15);
+        const int valid = (int)min((uint64_t)cr, A.n_records - r0);       // rows past n_records read as zero (HDF5 edge chunk)
+        const int nvec = (alpha + cr + 15) >> 4;
+        for (int i = lane; i < BWW; i += 32) reinterpret_cast<uint4 *>(bits)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const uint64_t rowbase = (uint64_t)(A.s0 + s) * A.gt_stride + (r0 & ~15ull);
+        for (int v = lane; v < 2 * nvec; v += 32) {
+            const int pl = v >= nvec, k = v - pl * nvec;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (alpha + valid - 16 * k > 0) x = ldg_stream(reinterpret_cast<const uint4 *>((pl ? A.gt1 : A.gt0) + rowbase + 16 * k));
+            reinterpret_cast<uint4 *>(pl ? raw1 : raw0)[k] = x;
+            const uint32_t b16 = pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
+            uint32_t n16 = 0;
+            if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
+                n16 = pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
+            reinterpret_cast<uint16_t *>(bits + (2 * pl) * BWW + 1)[k] = (uint16_t)b16;
+            reinterpret_cast<uint16_t *>(bits + (2 * pl + 1) * BWW + 1)[k] = (uint16_t)n16;
         }
-        while (pos < 32) {
-            const uint32_t x = r & (0xFFFFFFFFu << pos);
-            if (!x) break;
-            const int st = ctz32(x);
-            const int l1 = ctz32(~(m1c >> st)), lc = ctz32(~(mcc >> st));
-            // a run that reaches the end of this word is measured on into the next one, so that the
-            // offset chosen is the one whose run is really the longer (and >= 4, as r promises)
-            const int l1x = st + l1 == 32 ? l1 + ctz32(~m1n) : l1, lcx = st + lc == 32 ? lc + ctz32(~mcn) : lc;
-            const int off = lcx > l1x;
-            const int best = off ? lc : l1;
-            if (st + best >= 32) { open = true; open_off = off; open_start = 32 * k + st; open_len = 32 - st; break; }
-            record(32 * k + st, best, off);
-            pos = st + best;
+        __syncwarp();
+        if (valid < cr) {                    // the vector that straddles n_records: bytes / bits past it must read 0
+            const int e = alpha + valid;
+            if (lane < 16) { const int idx = e + lane; if (idx < ((e + 15) & ~15)) { raw0[idx] = 0; raw1[idx] = 0; } }
+            if (lane < 4) bits[lane * BWW + 1 + (e >> 5)] &= low_mask(e & 31);
+            __syncwarp();
         }
-        m1c = m1n; mcc = mcn;
-    }
-    if (open) record(open_start, open_len, open_off);
-    const int trail = seglen - prev_end;
+        const uint32_t sh16 = tl & 15u;      // the tail buffer lines up with the template's end modulo 16
+        uint8_t *seq = outb + sh16;
+        if (lane < 16) outb[lane] = 0;
+        __syncwarp();
 
-    // ---- 3. carry trailing literals forward, size scan
-    int val = trail, flag = m > 0;
+        if (cr < 6) {                        // raw block, see site_template_kernel
+            for (int i = lane; i < n; i += 32) seq[i] = i < cr ? raw0[alpha + i] : raw1[alpha + i - cr];
+            dlen = n;
+        } else {
+            // ---- 2. per-lane parse of one segment, position-parallel
+            p = lane >> 4;
+            const int q = lane & 15;
+            const int seg = (cr + 15) >> 4;
+            a0 = q * seg;
+            const int seglen = max(0, min(seg, cr - a0));
+            const int mlim = p ? min(seglen, cr - 11 - a0) : seglen;      // the last 11 bytes of the block stay literals
+            const uint32_t *B = bits + (2 * p) * BWW + 1, *N = B + BWW;
+            const uint32_t *B0 = bits + 1, *N0 = bits + BWW + 1;
+            const int bi = alpha + a0, j0 = bi >> 5, shb = bi & 31;
+            uint32_t Z[NW], C[NW], ZR[NW], CR[NW];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v2 = __shfl_up_sync(0xffffffffu, val, d), f2 = __shfl_up_sync(0xffffffffu, flag, d);
-        if (lane >= d && !flag) { val += v2; flag = f2; }
+            for (int k = 0; k < NW; ++k) {
+                const uint32_t bw = __funnelshift_r(B[j0 + k], B[j0 + k + 1], shb);
+                const uint32_t nw = __funnelshift_r(N[j0 + k], N[j0 + k + 1], shb);
+                const uint32_t vm = low_mask(mlim - 32 * k);
+                Z[k] = ~(bw | nw) & vm;
+                C[k] = 0;
+                if (p) {
+                    const uint32_t b0w = __funnelshift_r(B0[j0 + k], B0[j0 + k + 1], shb);
+                    const uint32_t n0w = __funnelshift_r(N0[j0 + k], N0[j0 + k + 1], shb);
+                    C[k] = ~((bw ^ b0w) | nw | n0w) & vm;
+                }
+            }
+            runs_cover<NW, kMinZ>(Z, ZR);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) C[k] &= ~ZR[k];
+            runs_cover<NW, kMinC>(C, CR);
+            int prev_end = 0, first_lit = 0, size_rest = 0, lit_rest = 0, ne_rest = 0;
+            {
+                bool open = false;
+                int ost = 0, okind = 0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    const uint32_t zp = k > 0 ? ZR[k - 1] : 0u, zn = k + 1 < NW ? ZR[k + 1] : 0u;
+                    const uint32_t cp = k > 0 ? CR[k - 1] : 0u, cn = k + 1 < NW ? CR[k + 1] : 0u;
+                    uint32_t st = (ZR[k] & ~__funnelshift_l(zp, ZR[k], 1)) | (CR[k] & ~__funnelshift_l(cp, CR[k], 1));
+                    uint32_t en = (ZR[k] & ~__funnelshift_r(ZR[k], zn, 1)) | (CR[k] & ~__funnelshift_r(CR[k], cn, 1));
+                    for (;;) {
+                        if (!open) {
+                            if (!st) break;
+                            const int ts = ctz32(st);
+                            st &= st - 1;
+                            ost = 32 * k + ts; okind = (CR[k] >> ts) & 1u; open = true;
+                        }
+                        if (!en) break;
+                        const int te = ctz32(en);
+                        en &= en - 1;
+                        const int ml = 32 * k + te - ost + 1, lit = ost - prev_end;
+                        seqs[m * 32 + lane] = (uint16_t)((ost << 8) | ml);
+                        kindmask |= (unsigned long long)okind << m;
+                        if (m == 0) { first_lit = lit; first_ml = ml; }
+                        else { size_rest += 3 + lit + (lit >= 15) + (ml >= 19); lit_rest += lit; ne_rest += lit > 0; }
+                        prev_end = ost + ml;
+                        ++m;
+                        open = false;
+                    }
+                }
+            }
+            const int trail = seglen - prev_end;
+
+            // ---- 3. carry trailing literals forward; scans: output offset, literal index, sequence index
+            int val = trail, flag = m > 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v2 = __shfl_up_sync(0xffffffffu, val, d), f2 = __shfl_up_sync(0xffffffffu, flag, d);
+                if (lane >= d && !flag) { val += v2; flag = f2; }
+            }
+            carry = __shfl_up_sync(0xffffffffu, val, 1);
+            if (lane == 0) carry = 0;
+            final_lit = __shfl_sync(0xffffffffu, val, 31);
+            const int lit0 = first_lit + carry;
+            const int mysize = m > 0 ? 3 + lit0 + lit_ext(lit0) + (first_ml >= 19) + size_rest : 0;
+            const int mylit = m > 0 ? lit0 + lit_rest : 0;
+            const int myrun = m > 0 ? (lit0 > 0) + ne_rest : 0;
+            uint32_t inc1 = (uint32_t)mysize | ((uint32_t)mylit << 16), inc2 = (uint32_t)myrun;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t1 = __shfl_up_sync(0xffffffffu, inc1, d), t2 = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (lane >= d) { inc1 += t1; inc2 += t2; }
+            }
+            const uint32_t tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+            total = (int)(tot1 & 0xFFFFu); totlit = (int)(tot1 >> 16);
+            totrun = (int)__shfl_sync(0xffffffffu, inc2, 31);
+            out_base = (int)(inc1 & 0xFFFFu) - mysize;
+            lit_base = (int)(inc1 >> 16) - mylit;
+            run_base = (int)inc2 - myrun;
+            dlen = total + 1 + lit_ext(final_lit) + final_lit;
+        }
     }
-    int carry = __shfl_up_sync(0xffffffffu, val, 1);
-    if (lane == 0) carry = 0;
-    const int final_lit = __shfl_sync(0xffffffffu, val, 31);
-    const int mysize = m > 0 ? seq_bytes(first_lit + carry, first_ml) + size_rest : 0;
-    int inc = mysize;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t flen = tl + (uint32_t)dlen + FRAME_TAIL;
+
+    // ---- 4. every lane writes the headers of its own sequences, then the literals are copied in 32 equal shares
+    if (active && cr >= 6) {
+        uint8_t *seq = outb + (tl & 15u);
+        {
+            int o = out_base, r = run_base, lc = lit_base;
+            int prev_abs = p * cr + a0 - carry;
+            for (int j = 0; j < m; ++j) {
+                const uint32_t e = seqs[j * 32 + lane];
+                const int st = p * cr + a0 + (int)(e >> 8), ml = (int)(e & 255u);
+                const int off = ((kindmask >> j) & 1ull) ? cr : 2 * cr;
+                const int lit = st - prev_abs;
+                seq[o++] = (uint8_t)((min(lit, 15) << 4) | min(ml - 4, 15));
+                if (lit >= 15) { int rem = lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
+                if (lit > 0) { d_cum[r] = (uint16_t)lc; d_sd[r] = (uint32_t)prev_abs | ((uint32_t)o << 16); ++r; }
+                lc += lit; o += lit;
+                seq[o++] = (uint8_t)off; seq[o++] = (uint8_t)(off >> 8);
+                if (ml >= 19) seq[o++] = (uint8_t)(ml - 19);
+                prev_abs = st + ml;
+            }
+        }
+        if (lane == 0) {                     // the last sequence of the block: literals only (>= 11 of them)
+            int o = total;
+            seq[o++] = (uint8_t)(min(final_lit, 15) << 4);
+            if (final_lit >= 15) { int rem = final_lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
+            d_cum[totrun] = (uint16_t)totlit; d_sd[totrun] = (uint32_t)(n - final_lit) | ((uint32_t)o << 16);
+            d_cum[totrun + 1] = (uint16_t)(totlit + final_lit);
+        }
+        __syncwarp();
+        {
+            const int totL = totlit + final_lit;
+            const int share = (totL + 31) >> 5;
+            const int g0 = lane * share;
+            int cnt = min(share, totL - g0);
+            int lo = 0, hi = totrun + 1;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)d_cum[mid] <= g0) lo = mid; else hi = mid; }
+            if (cnt > 0) {
+                int idx = lo, g = g0;
+                uint32_t sd = d_sd[idx];
+                int src = (int)(sd & 0xFFFFu) + g0 - (int)d_cum[idx], dst = (int)(sd >> 16) + g0 - (int)d_cum[idx];
+                int nextcum = d_cum[idx + 1];
+                for (; cnt > 0; --cnt) {
+                    seq[dst] = src < cr ? raw0[alpha + src] : raw1[alpha + src - cr];
+                    ++src; ++dst; ++g;
+                    if (g == nextcum) { ++idx; sd = d_sd[idx]; src = (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
+                }
+            }
+        }
+    }
+    if (active) {
+        uint8_t *seq = outb + (tl & 15u);
+        for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
+        const uint32_t used = (tl & 15u) + (uint32_t)dlen + FRAME_TAIL;
+        for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
+    }
     __syncwarp();
 
-    // ---- 4. every lane writes its own sequences
-    {
-        int o = inc - mysize;
-        int prev_abs = p * cr + a0 - carry;
-        for (int j = 0; j < m; ++j) {
-            const uint32_t e = seqs[j * 32 + lane];
-            const int st = p * cr + a0 + (int)(e >> 8), ml = (int)(e & 255u);
-            const int off = ((offmask >> j) & 1ull) ? cr : 1;
-            const int lit = st - prev_abs;
-            seq[o++] = (uint8_t)((min(lit, 15) << 4) | min(ml - 4, 15));
-            if (lit >= 15) { int rem = lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-            for (int i = 0; i < lit; ++i) { const int P = prev_abs + i; seq[o++] = P < cr ? raw0[alpha + P] : raw1[alpha + P - cr]; }
-            seq[o++] = (uint8_t)off; seq[o++] = (uint8_t)(off >> 8);
-            if (ml >= 19) { int rem = ml - 19; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-            prev_abs = st + ml;
-        }
-    }
-    // the last sequence of the block: literals only (at least the 5 bytes the format demands)
-    int o = total;
-    if (lane == 0) seq[o] = (uint8_t)(min(final_lit, 15) << 4);
-    ++o;
-    if (final_lit >= 15) {
-        int rem = final_lit - 15;
-        while (rem >= 255) { if (lane == 0) seq[o] = 255; ++o; rem -= 255; }
-        if (lane == 0) seq[o] = (uint8_t)rem;
-        ++o;
-    }
-    for (int i = lane; i < final_lit; i += 32) { const int P = n - final_lit + i; seq[o + i] = P < cr ? raw0[alpha + P] : raw1[alpha + P - cr]; }
-    const int dlen = o + final_lit;
-
-    // ---- 5. constant frame tail, pad, copy out
-    for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
-    const uint32_t used = sh16 + (uint32_t)dlen + FRAME_TAIL;
-    for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
-    __syncwarp();
-    uint4 *dstp = reinterpret_cast<uint4 *>(a.stage + wid * (uint64_t)a.dslot);
-    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
-    for (uint32_t i = lane; i < (used + 15) / 16; i += 32) dstp[i] = srcp[i];
-    if (lane == 0) a.dlen[wid] = (uint32_t)dlen;
-}
-
-// ------------------------------------------------------------------------------------------
-// frame sizes -> offsets.  Frames are laid out [sample][chunk], each starting on a 16-byte boundary.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-frame_offsets_kernel(const uint32_t *__restrict__ tmpl_len, const uint32_t *__restrict__ dlen, uint32_t n_chunks,
-                     uint32_t *__restrict__ size, uint32_t *__restrict__ rowoff, uint64_t *__restrict__ rowtot,
-                     unsigned long long *__restrict__ sum_sizes) {
-    __shared__ uint32_t wsum[8];
-    __shared__ uint64_t carry;
-    const uint32_t s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    unsigned long long mine = 0;
-    for (uint32_t base = 0; base < n_chunks; base += 256) {
-        const uint32_t c = base + threadIdx.x;
-        const uint64_t wid = (uint64_t)s * n_chunks + c;
-        uint32_t sz = 0;
-        if (c < n_chunks) { sz = FRAME_TAIL + tmpl_len[c] + dlen[wid]; size[wid] = sz; mine += sz; }
-        const uint32_t pad = (sz + 15u) & ~15u;
-        uint32_t inc = pad;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        uint32_t wbase = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < (int)warp) wbase += wsum[w]; total += wsum[w]; }
-        if (c < n_chunks) rowoff[wid] = (uint32_t)(carry + wbase + inc - pad);
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
-    if (lane == 0 && mine) atomicAdd(sum_sizes, mine);
-    if (threadIdx.x == 0) rowtot[s] = carry;
-}
-
-__global__ void __launch_bounds__(1024) row_base_kernel(const uint64_t *__restrict__ rowtot, uint32_t n, uint64_t *__restrict__ rowbase) {
-    __shared__ uint64_t wsum[32];
-    __shared__ uint64_t carry;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint64_t v = i < n ? rowtot[i] : 0;
-        uint64_t inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        uint64_t wbase = 0, total = 0;
-        for (int w = 0; w < 32; ++w) { if (w < (int)warp) wbase += wsum[w]; total += wsum[w]; }
-        if (i < n) rowbase[i] = carry + wbase + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) rowbase[n] = carry;
-}
-
-// ------------------------------------------------------------------------------------------
-// one warp per frame: template + staged tail -> final position
-// ------------------------------------------------------------------------------------------
-struct AsmArgs {
-    const uint8_t *tmpl; uint32_t tmpl_cap; const uint32_t *tmpl_len;
-    const uint8_t *stage; uint32_t dslot; const uint32_t *dlen;
-    const uint32_t *rowoff; const uint64_t *rowbase;
-    uint8_t *frames;
-    uint32_t n_chunks, n_samples;
-};
-
-__device__ __forceinline__ uint4 ldg_nc(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-__global__ void __launch_bounds__(256) assemble_kernel(const AsmArgs a) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (uint64_t)a.n_chunks * a.n_samples) return;
-    const uint32_t s = (uint32_t)(wid / a.n_chunks), c = (uint32_t)(wid % a.n_chunks);
-    const uint32_t tl = a.tmpl_len[c], dl = a.dlen[wid];
-    const uint32_t lz = tl - TMPL_HDR + dl, cb = CHUNK_HDR + 8 + lz, flen = tl + dl + FRAME_TAIL;
-    const uint32_t jb = tl >> 4, nvec = (flen + 15) >> 4;
-    const uint4 *T = reinterpret_cast<const uint4 *>(a.tmpl + (uint64_t)c * a.tmpl_cap);
-    const uint4 *G = reinterpret_cast<const uint4 *>(a.stage + wid * (uint64_t)a.dslot);
-    uint4 *D = reinterpret_cast<uint4 *>(a.frames + a.rowbase[s] + a.rowoff[wid]);
+    // ---- 5. template (L2) + own tail (shared memory) -> the frame's slot
+    const unsigned long long fbase = (unsigned long long)sidx * A.slot_off[A.n_chunks] + A.slot_off[c];
+    if (lane == 0) A.size[wid] = flen;
+    const uint32_t lz = tl - TMPL_HDR + (uint32_t)dlen, cb = CHUNK_HDR + 8 + lz;
+    const uint32_t jb = tl >> 4, nv = (flen + 15) >> 4;
+    const uint4 *T = reinterpret_cast<const uint4 *>(A.tmpl + c * A.tmpl_cap);
+    const uint4 *G = reinterpret_cast<const uint4 *>(outb);
+    uint4 *D = reinterpret_cast<uint4 *>(A.frames + fbase);
 #pragma unroll 4
-    for (uint32_t j = lane; j < nvec; j += 32) {
+    for (uint32_t j = lane; j < nv; j += 32) {
         uint4 v;
         if (j < jb) v = ldg_nc(T + j);
         else {
-            v = ldg_stream(G + (j - jb));
-            if (j == jb && (tl & 15u)) {           // the template's last bytes and the slot's pad are zero where the other has data
+            v = G[j - jb];
+            if (j == jb && (tl & 15u)) {           // the template's last bytes and the tail's pad are zero where the other has data
                 const uint4 t = ldg_nc(T + j);
                 v.x |= t.x; v.y |= t.y; v.z |= t.z; v.w |= t.w;
             }
@@ -678,6 +617,14 @@ __global__ void __launch_bounds__(256) assemble_kernel(const AsmArgs a) {
         }
         stg_stream(D + j, v);
     }
+}
+
+__global__ void __launch_bounds__(256) sum_sizes_kernel(const uint32_t *__restrict__ size, uint64_t n, unsigned long long *__restrict__ total) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += size[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
 }
 
 uint64_t guess_chunk_records(uint64_t n) {      // h5py/_hl/filters.py guess_chunk for shape (n,), 35-byte items
@@ -705,25 +652,35 @@ struct hb_frames {
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t n_records = 0, n_chunks = 0, cr = 0;
-    uint32_t n_samples = 0, tmpl_cap = 0, dslot = 0, warp_smem = 0;
-    uint32_t rb = 0, bww = 0, caps = 0;      // bit-parallel allele encoder geometry
-    bool bits_encoder = true;                // false: the byte-wise warp LZ4 matcher (HB_DONOR_ENCODER=lz4, and for chunks of < 6 records)
-    int warps_per_cta = 8;
+    uint32_t n_samples = 0, tmpl_cap = 0;
     size_t smem_site = 0;
-    uint8_t *d_tmpl = nullptr, *d_stage = nullptr, *d_frames = nullptr;
-    uint32_t *d_tmpl_len = nullptr, *d_dlen = nullptr, *d_size = nullptr, *d_rowoff = nullptr;
-    uint64_t *d_rowtot = nullptr, *d_rowbase = nullptr;
-    unsigned long long *d_sum = nullptr;
+    FusedArgs fa;                            // geometry of the fused kernel
+    int nw = 1;
+    uint64_t n_ctas = 0;
+    uint8_t *d_tmpl = nullptr, *d_frames = nullptr;
+    uint32_t *d_tmpl_len = nullptr, *d_size = nullptr;
+    uint64_t *d_slot_off = nullptr;
+    unsigned long long *d_totals = nullptr;
+    std::vector<uint64_t> h_slot_off;            // [n_chunks + 1]
     uint64_t frames_cap = 0;
     uint64_t total_bytes = 0, padded_bytes = 0;
+    std::vector<uint32_t> h_tmpl_len;
     // host copies of the layout, fetched on demand
     bool layout_valid = false;
-    std::vector<uint32_t> h_size, h_rowoff;      // [n_samples][n_chunks]
-    std::vector<uint64_t> h_rowbase;             // [n_samples + 1]
+    std::vector<uint32_t> h_size;                // [n_samples][n_chunks]
     std::vector<uint8_t> h_row;                  // scratch for hb_frames_fetch_sample
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float ms_site = 0, ms_gt = 0, ms_offsets = 0, ms_assemble = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float ms_site = 0, ms_frames = 0;
 };
+
+template <int NW>
+static void launch_donor_frames(const FusedArgs &fa, uint64_t n_ctas, cudaStream_t st) {
+    donor_frames_kernel<NW><<<(unsigned)n_ctas, kWpc * 32, (size_t)kWpc * fa.warp_smem, st>>>(fa);
+}
+template <int NW>
+static cudaError_t attr_donor_frames(size_t smem) {
+    return cudaFuncSetAttribute(donor_frames_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
 
 static int frames_run(hb_frames *f, hb_parse *p) {
     cudaError_t e;
@@ -736,59 +693,55 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     SiteArgs4 sa;
     sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
     sa.n_records = n; sa.cr = cr; sa.tmpl = f->d_tmpl; sa.tmpl_cap = f->tmpl_cap; sa.tmpl_len = f->d_tmpl_len;
-    CUF(cudaMemsetAsync(f->d_sum, 0, 8, f->stream));
+    CUF(cudaMemsetAsync(f->d_totals, 0, 8, f->stream));
     CUF(cudaEventRecord(f->ev[0], f->stream));
     site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, f->stream>>>(sa);
     count_launch();
     CUF(cudaEventRecord(f->ev[1], f->stream));
-    DonorArgs da;
-    da.gt0 = p->d_gt[0]; da.gt1 = p->d_gt[1]; da.gt_stride = p->gt_stride; da.n_records = n;
-    da.cr = cr; da.n_samples = f->n_samples; da.s0 = 0; da.n_chunks = f->n_chunks;
-    da.tmpl_len = f->d_tmpl_len; da.stage = f->d_stage; da.dslot = f->dslot; da.dlen = f->d_dlen;
-    da.warp_smem = f->warp_smem;
-    const int wpc = f->warps_per_cta;
-    if (f->bits_encoder) {
-        DonorBitsArgs ba;
-        ba.d = da; ba.rb = f->rb; ba.bww = f->bww; ba.caps = f->caps;
-        donor_encode_bits_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(ba);
-    } else {
-        donor_encode_kernel<<<(unsigned)((n_frames + wpc - 1) / wpc), wpc * 32, (size_t)wpc * f->warp_smem, f->stream>>>(da);
-    }
-    count_launch();
-    CUF(cudaEventRecord(f->ev[2], f->stream));
-    frame_offsets_kernel<<<f->n_samples, 256, 0, f->stream>>>(f->d_tmpl_len, f->d_dlen, (uint32_t)f->n_chunks, f->d_size,
-                                                              f->d_rowoff, f->d_rowtot, f->d_sum);
-    row_base_kernel<<<1, 1024, 0, f->stream>>>(f->d_rowtot, f->n_samples, f->d_rowbase);
-    count_launch(2);
-    CUF(cudaEventRecord(f->ev[3], f->stream));
-    uint64_t tot[2] = {0, 0};
-    CUF(cudaMemcpyAsync(&tot[0], f->d_rowbase + f->n_samples, 8, cudaMemcpyDeviceToHost, f->stream));
-    CUF(cudaMemcpyAsync(&tot[1], f->d_sum, 8, cudaMemcpyDeviceToHost, f->stream));
+    // the frame buffer is sized from the longest template: frame <= template + worst-case allele tail
+    CUF(cudaMemcpyAsync(f->h_tmpl_len.data(), f->d_tmpl_len, f->n_chunks * 4, cudaMemcpyDeviceToHost, f->stream));
     CUF(cudaStreamSynchronize(f->stream));
     CUF(cudaGetLastError());
-    f->padded_bytes = tot[0];
-    f->total_bytes = tot[1];
-    if (f->frames_cap < f->padded_bytes) {
+    // slots: frame <= template + worst-case allele tail, so every address is known before the encode
+    uint64_t need = 0;
+    {
+        const uint64_t tail = 2ull * cr + 2ull * cr / 255 + 24 + FRAME_TAIL;
+        uint64_t run = 0;
+        for (uint64_t c = 0; c < f->n_chunks; ++c) { f->h_slot_off[c] = run; run += (f->h_tmpl_len[c] + tail + 15) & ~15ull; }
+        f->h_slot_off[f->n_chunks] = run;
+        need = run * f->n_samples;
+    }
+    if (f->frames_cap < need) {
         if (f->d_frames) { cudaFree(f->d_frames); f->d_frames = nullptr; f->frames_cap = 0; }
-        const uint64_t cap = f->padded_bytes + f->padded_bytes / 64 + 4096;     // head-room for re-runs on new data
-        e = cudaMalloc(&f->d_frames, cap);
-        if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
-        f->frames_cap = cap;
+        e = cudaMalloc(&f->d_frames, need);
+        if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(need) + " bytes): " + cudaGetErrorString(e));
+        f->frames_cap = need;
     }
-    AsmArgs aa;
-    aa.tmpl = f->d_tmpl; aa.tmpl_cap = f->tmpl_cap; aa.tmpl_len = f->d_tmpl_len;
-    aa.stage = f->d_stage; aa.dslot = f->dslot; aa.dlen = f->d_dlen;
-    aa.rowoff = f->d_rowoff; aa.rowbase = f->d_rowbase; aa.frames = f->d_frames;
-    aa.n_chunks = (uint32_t)f->n_chunks; aa.n_samples = f->n_samples;
-    assemble_kernel<<<(unsigned)((n_frames + 7) / 8), 256, 0, f->stream>>>(aa);
-    count_launch();
-    CUF(cudaEventRecord(f->ev[4], f->stream));
+    CUF(cudaMemcpyAsync(f->d_slot_off, f->h_slot_off.data(), (f->n_chunks + 1) * 8, cudaMemcpyHostToDevice, f->stream));
+    FusedArgs fa = f->fa;
+    fa.gt0 = p->d_gt[0]; fa.gt1 = p->d_gt[1]; fa.gt_stride = p->gt_stride; fa.n_records = n;
+    fa.cr = cr; fa.n_samples = f->n_samples; fa.s0 = 0; fa.n_chunks = f->n_chunks;
+    fa.tmpl = f->d_tmpl; fa.tmpl_cap = f->tmpl_cap; fa.tmpl_len = f->d_tmpl_len;
+    fa.frames = f->d_frames; fa.slot_off = f->d_slot_off; fa.size = f->d_size; fa.totals = f->d_totals;
+    switch (f->nw) {
+        case 1: launch_donor_frames<1>(fa, f->n_ctas, f->stream); break;
+        case 2: launch_donor_frames<2>(fa, f->n_ctas, f->stream); break;
+        case 3: launch_donor_frames<3>(fa, f->n_ctas, f->stream); break;
+        case 4: launch_donor_frames<4>(fa, f->n_ctas, f->stream); break;
+        case 5: launch_donor_frames<5>(fa, f->n_ctas, f->stream); break;
+        default: launch_donor_frames<6>(fa, f->n_ctas, f->stream); break;
+    }
+    sum_sizes_kernel<<<296, 256, 0, f->stream>>>(f->d_size, n_frames, f->d_totals);
+    count_launch(2);
+    CUF(cudaEventRecord(f->ev[2], f->stream));
+    unsigned long long tot = 0;
+    CUF(cudaMemcpyAsync(&tot, f->d_totals, 8, cudaMemcpyDeviceToHost, f->stream));
     CUF(cudaStreamSynchronize(f->stream));
     CUF(cudaGetLastError());
+    f->padded_bytes = need;
+    f->total_bytes = tot;
     cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
-    cudaEventElapsedTime(&f->ms_gt, f->ev[1], f->ev[2]);
-    cudaEventElapsedTime(&f->ms_offsets, f->ev[2], f->ev[3]);
-    cudaEventElapsedTime(&f->ms_assemble, f->ev[3], f->ev[4]);
+    cudaEventElapsedTime(&f->ms_frames, f->ev[1], f->ev[2]);
 #undef CUF
     return HB_OK;
 }
@@ -796,12 +749,10 @@ static int frames_run(hb_frames *f, hb_parse *p) {
 static int frames_layout(hb_frames *f) {
     if (f->layout_valid) return HB_OK;
     const uint64_t n_frames = f->n_chunks * f->n_samples;
-    f->h_size.resize(n_frames); f->h_rowoff.resize(n_frames); f->h_rowbase.resize((size_t)f->n_samples + 1);
+    f->h_size.resize(n_frames);
     if (n_frames) {
         if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
         cudaError_t e = cudaMemcpyAsync(f->h_size.data(), f->d_size, n_frames * 4, cudaMemcpyDeviceToHost, f->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_rowoff.data(), f->d_rowoff, n_frames * 4, cudaMemcpyDeviceToHost, f->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_rowbase.data(), f->d_rowbase, ((size_t)f->n_samples + 1) * 8, cudaMemcpyDeviceToHost, f->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
         if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     }
@@ -816,9 +767,8 @@ uint64_t hb_guess_chunk_records(uint64_t n_records) { return guess_chunk_records
 void hb_frames_free(hb_frames *f) {
     if (!f) return;
     cudaSetDevice(f->device);
-    cudaFree(f->d_tmpl); cudaFree(f->d_stage); cudaFree(f->d_frames);
-    cudaFree(f->d_tmpl_len); cudaFree(f->d_dlen); cudaFree(f->d_size); cudaFree(f->d_rowoff);
-    cudaFree(f->d_rowtot); cudaFree(f->d_rowbase); cudaFree(f->d_sum);
+    cudaFree(f->d_tmpl); cudaFree(f->d_frames); cudaFree(f->d_tmpl_len); cudaFree(f->d_size);
+    cudaFree(f->d_slot_off); cudaFree(f->d_totals);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
     delete f;
 }
@@ -830,11 +780,12 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     const uint64_t n = p->h_st.n_records;
     if (!p->d_gt[0] && n) return api_fail(HB_ERR_NOGT, "parse was made without genotypes");
     hb_frames *f = new hb_frames();
+    memset(&f->fa, 0, sizeof f->fa);
     f->device = p->device; f->stream = p->stream;
     f->n_records = n; f->n_samples = p->n_samples;
     f->cr = chunk_records ? chunk_records : guess_chunk_records(n);
     f->n_chunks = n ? (n + f->cr - 1) / f->cr : 0;
-    if (!f->n_chunks || !f->n_samples) { f->n_chunks = n ? f->n_chunks : 0; *out = f; f->layout_valid = false; return HB_OK; }
+    if (!f->n_chunks || !f->n_samples) { f->n_chunks = n ? f->n_chunks : 0; *out = f; return HB_OK; }
     if (f->cr > 2730) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk_records too large (at most 2730: the site encoder indexes 24*chunk_records+1 positions with 16 bits)"); }
     const uint32_t cr = (uint32_t)f->cr;
     const uint32_t n_site = 33u * cr, n_gt = 2u * cr;
@@ -842,36 +793,38 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     f->tmpl_cap = (TMPL_HDR + bound(n_site) + 15) & ~15u;
     f->smem_site = 16 + ((n_site + 19) & ~15u) + f->tmpl_cap + (2u << 12);
     if (f->smem_site > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
-    f->dslot = (16 + bound(n_gt) + FRAME_TAIL + 15) & ~15u;
-    const char *enc = getenv("HB_DONOR_ENCODER");
-    f->bits_encoder = cr >= 6 && !(enc && !strcmp(enc, "lz4"));
-    if (f->bits_encoder) {
-        f->rb = ((15 + cr + 15) & ~15u) + 16;
-        f->bww = ((cr + 30) / 32 + 4 + 3) & ~3u;
-        f->caps = ((cr + 15) / 16) / 4 + 2;
-        f->warp_smem = 2 * f->rb + 16 * f->bww + 64 * f->caps + f->dslot;
-    } else {
-        f->warp_smem = (kHist + ((n_gt + 19) & ~15u) + f->dslot + (2u << 10) + 15) & ~15u;
-    }
-    f->warps_per_cta = 8;
-    while (f->warps_per_cta > 1 && (size_t)f->warps_per_cta * f->warp_smem > 200 * 1024) f->warps_per_cta >>= 1;
-    if ((size_t)f->warps_per_cta * f->warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
+    const uint32_t seg = (cr + 15) / 16;
+    f->nw = (int)((seg + 31) / 32);
+    FusedArgs &fa = f->fa;
+    fa.rb = ((15 + cr + 15) & ~15u) + 16;
+    fa.bww = ((cr + 30) / 32 + 4 + 3) & ~3u;
+    fa.caps = seg / 4 + 2;
+    fa.dcap = (cr / 6 + cr / 5 + 8 + 7) & ~7u;           // Z runs take >= 6 bytes each (5 + a break), C runs >= 5
+    fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
+    fa.warp_smem = 2 * fa.rb + 16 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
+    if ((size_t)kWpc * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
     const uint64_t n_frames = f->n_chunks * f->n_samples;
+    f->n_ctas = (n_frames + kWpc - 1) / kWpc;
+    f->h_tmpl_len.resize(f->n_chunks);
+    f->h_slot_off.resize(f->n_chunks + 1);
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     ck(cudaMalloc(&f->d_tmpl, f->n_chunks * (uint64_t)f->tmpl_cap));
     ck(cudaMalloc(&f->d_tmpl_len, f->n_chunks * 4));
-    ck(cudaMalloc(&f->d_stage, n_frames * (uint64_t)f->dslot));
-    ck(cudaMalloc(&f->d_dlen, n_frames * 4));
     ck(cudaMalloc(&f->d_size, n_frames * 4));
-    ck(cudaMalloc(&f->d_rowoff, n_frames * 4));
-    ck(cudaMalloc(&f->d_rowtot, (uint64_t)f->n_samples * 8));
-    ck(cudaMalloc(&f->d_rowbase, ((uint64_t)f->n_samples + 1) * 8));
-    ck(cudaMalloc(&f->d_sum, 8));
+    ck(cudaMalloc(&f->d_slot_off, (f->n_chunks + 1) * 8));
+    ck(cudaMalloc(&f->d_totals, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
     ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_site));
-    if (f->bits_encoder) ck(cudaFuncSetAttribute(donor_encode_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
-    else ck(cudaFuncSetAttribute(donor_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)f->warps_per_cta * f->warp_smem)));
+    const size_t smem_fused = (size_t)kWpc * fa.warp_smem;
+    switch (f->nw) {
+        case 1: ck(attr_donor_frames<1>(smem_fused)); break;
+        case 2: ck(attr_donor_frames<2>(smem_fused)); break;
+        case 3: ck(attr_donor_frames<3>(smem_fused)); break;
+        case 4: ck(attr_donor_frames<4>(smem_fused)); break;
+        case 5: ck(attr_donor_frames<5>(smem_fused)); break;
+        default: ck(attr_donor_frames<6>(smem_fused)); break;
+    }
     if (e != cudaSuccess) { hb_frames_free(f); return api_fail(HB_ERR_MEM, std::string("CUDA: ") + cudaGetErrorString(e)); }
     int rc = frames_run(f, p);
     if (rc != HB_OK) { hb_frames_free(f); return rc; }
@@ -893,10 +846,12 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
     info->n_records = f->n_records; info->n_chunks = f->n_chunks; info->chunk_records = f->cr;
     info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
     info->raw_bytes = 35ull * f->n_records * f->n_samples;
-    info->ms_site = f->ms_site; info->ms_gt = f->ms_gt;
+    info->ms_site = f->ms_site; info->ms_frames = f->ms_frames;
     info->padded_bytes = f->padded_bytes;
     info->d_frames = f->d_frames;
-    info->ms_offsets = f->ms_offsets; info->ms_assemble = f->ms_assemble;
+    uint64_t st = 0;
+    for (uint32_t t : f->h_tmpl_len) st += t - TMPL_HDR;
+    info->site_lz4_bytes = st;
     return HB_OK;
 }
 
@@ -904,12 +859,11 @@ int hb_frames_layout(hb_frames *f, uint64_t *offsets, uint32_t *sizes) {
     if (!f) return api_fail(HB_ERR_ARG, "null handle");
     int rc = frames_layout(f);
     if (rc != HB_OK) return rc;
-    const uint64_t nc = f->n_chunks;
-    for (uint32_t s = 0; s < f->n_samples; ++s)
-        for (uint64_t c = 0; c < nc; ++c) {
-            if (offsets) offsets[s * nc + c] = f->h_rowbase[s] + f->h_rowoff[s * nc + c];
-            if (sizes) sizes[s * nc + c] = f->h_size[s * nc + c];
-        }
+    const uint64_t n_frames = f->n_chunks * f->n_samples, nc = f->n_chunks;
+    if (offsets)
+        for (uint32_t s = 0; s < f->n_samples; ++s)
+            for (uint64_t c = 0; c < nc; ++c) offsets[s * nc + c] = s * f->h_slot_off[nc] + f->h_slot_off[c];
+    if (sizes && n_frames) memcpy(sizes, f->h_size.data(), n_frames * 4);
     return HB_OK;
 }
 
@@ -939,17 +893,18 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *b
     if (total) *total = tot;
     if (!buf || !nc) return HB_OK;
     if (cap < tot) return api_fail(HB_ERR_ARG, "buffer too small");
-    // one contiguous D2H of the sample's (16-byte padded) row, then the pads are squeezed out on the host
-    const uint64_t row = f->h_rowbase[s + 1] - f->h_rowbase[s];
+    // one contiguous D2H of the sample's row of slots, then the frames are packed together on the host
+    const uint64_t row0 = s * f->h_slot_off[nc];
+    const uint64_t row = f->h_slot_off[nc - 1] + f->h_size[s * nc + nc - 1];
     f->h_row.resize(row);
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
-    cudaError_t e = cudaMemcpyAsync(f->h_row.data(), f->d_frames + f->h_rowbase[s], row, cudaMemcpyDeviceToHost, f->stream);
+    cudaError_t e = cudaMemcpyAsync(f->h_row.data(), f->d_frames + row0, row, cudaMemcpyDeviceToHost, f->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("D2H of frames failed: ") + cudaGetErrorString(e));
     uint64_t o = 0;
     for (uint64_t c = 0; c < nc; ++c) {
         const uint32_t sz = f->h_size[s * nc + c];
-        memcpy(buf + o, f->h_row.data() + f->h_rowoff[s * nc + c], sz);
+        memcpy(buf + o, f->h_row.data() + f->h_slot_off[c], sz);
         o += sz;
     }
     return HB_OK;

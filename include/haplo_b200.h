@@ -136,10 +136,10 @@ typedef struct hb_frames_info {
     uint32_t n_samples;
     uint64_t total_bytes;           /* all frames of all samples (C_out) */
     uint64_t raw_bytes;             /* 35 * n_records * n_samples */
-    float ms_site, ms_gt;           /* kernel times: site templates, allele-plane encoder */
-    uint64_t padded_bytes;          /* size of the device frame buffer: frames start on 16-byte boundaries */
+    float ms_site, ms_frames;       /* kernel times: site templates; fused allele encode + frame assembly */
+    uint64_t padded_bytes;          /* bytes of the device frame buffer in use: frames start on 16-byte boundaries */
     const uint8_t *d_frames;        /* device: frames in [sample][chunk] order, see hb_frames_layout */
-    float ms_offsets, ms_assemble;  /* kernel times: size scan, frame assembly (the C_out write) */
+    uint64_t site_lz4_bytes;        /* LZ4 bytes of the site planes, summed over chunks (shared by every sample) */
 } hb_frames_info;
 
 /* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items (at most 2730).

@@ -21,9 +21,9 @@ for r in range(reps):
     i = fr.info
     pi = p.info
     alg = 2.0 * i.n_records * S + 33.0 * i.n_records + i.total_bytes
-    ms = i.ms_site + i.ms_gt + i.ms_offsets + i.ms_assemble
+    ms = i.ms_site + i.ms_frames
     print(json.dumps({"records": i.n_records, "chunks": i.n_chunks, "cr": i.chunk_records, "C_out": i.total_bytes,
                       "padded": i.padded_bytes, "ratio": i.raw_bytes / max(1, i.total_bytes),
-                      "ms_site": i.ms_site, "ms_gt": i.ms_gt, "ms_offsets": i.ms_offsets, "ms_assemble": i.ms_assemble,
-                      "ms_total": ms, "alg_GBs": alg / ms / 1e6, "assemble_GBs": i.total_bytes / max(1e-9, i.ms_assemble) / 1e6,
-                      "bytes_per_frame": i.total_bytes / max(1, i.n_chunks * S)}))
+                      "ms_site": i.ms_site, "ms_frames": i.ms_frames,
+                      "ms_total": ms, "alg_GBs": alg / ms / 1e6, "frames_alg_GBs": (2.0 * i.n_records * S + i.total_bytes) / max(1e-9, i.ms_frames) / 1e6,
+                      "bytes_per_frame": i.total_bytes / max(1, i.n_chunks * S), "site_lz4_per_chunk": i.site_lz4_bytes / max(1, i.n_chunks)}))
