@@ -16,6 +16,7 @@ Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]; rank
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -162,7 +163,8 @@ def main():
     ap.add_argument("--cpu-sample-variants", type=int, default=60000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--slab-bytes", type=int, default=256 << 20, help="slab size of the streamed e2e path")
     ap.add_argument("--parse-only", action="store_true", help="step = kernels 1-3 only (no Blosc2 frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -272,13 +274,17 @@ def main():
         host.copy_(text[:T])
         out0 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
         out1 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
-        sites = [np.empty(Vk, np.uint32), np.empty(Vk, np.uint32), np.empty(Vk, "S1"), np.empty(Vk, "S1")]
+        sites = [torch.empty(Vk, dtype=torch.int32).pin_memory(), torch.empty(Vk, dtype=torch.int32).pin_memory(),
+                 torch.empty(Vk, dtype=torch.uint8).pin_memory(), torch.empty(Vk, dtype=torch.uint8).pin_memory()]
+
+        nrec = C.c_uint64()
+        opts = capi.Parse._opts(S, "chr22", False, True, local, 0, None)
 
         def e2e_step():
-            q = capi.Parse.from_host(host.data_ptr(), S, region="chr22", device=local, stream=stream, nbytes=T)
-            capi.check(capi.lib().hb_parse_fetch_matrix(q._h, out0.data_ptr(), out1.data_ptr()))
-            capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.ctypes.data for a in sites]))
-            q.close()
+            capi.check(capi.lib().hb_parse_stream_host(host.data_ptr(), T, C.byref(opts), args.slab_bytes, out0.data_ptr(),
+                                                       out1.data_ptr(), Vk, sites[0].data_ptr(), sites[1].data_ptr(),
+                                                       sites[2].data_ptr(), sites[3].data_ptr(), None, None, C.byref(nrec), None))
+            assert nrec.value == Vk
 
         e2e_step()
         barrier()
@@ -293,7 +299,12 @@ def main():
         dt = float(tt.item())
         e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T,
                "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk, "steps": args.e2e_steps,
-               "api": "hb_parse_host_text + hb_parse_fetch_matrix + hb_parse_fetch_sites (pinned host buffers)"}
+               "api": "hb_parse_stream_host: pinned host text -> genotype matrix [S][V'] x2 + site columns in pinned host "
+                      "memory; slabs of %d MiB, H2D / kernels / D2H overlapped" % (args.slab_bytes >> 20)}
+        # the streamed result is the same matrix the device-resident step produced
+        if rank == 0:
+            g0, g1 = p.sample(S // 3)
+            e2e["matches_device_path"] = bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1))
         del host, out0, out1
 
     if rank == 0:

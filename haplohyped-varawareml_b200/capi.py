@@ -68,7 +68,7 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
-    "hb_parse_host_text", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_compress_records", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
@@ -94,6 +94,9 @@ def lib():
         L.hb_load_vcf_without_sample.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Records)]
         L.hb_records_free.argtypes = [C.POINTER(Records)]
         L.hb_parse_host_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
+        L.hb_parse_stream_host.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.c_uint64, C.c_void_p, C.c_void_p,
+                                           C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.hb_parse_device_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.hb_parse_samples.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -321,6 +324,25 @@ class Frames:
 
 
 # ------------------------------------------------------------------------------------------------
+def parse_stream_host(text, n_samples, capacity, region="", end_is_int=False, want_gt=True, device=0, tokenizer=0,
+                      slab_bytes=0):
+    """hb_parse_stream_host on a bytes / uint8 array: returns a dict of numpy arrays trimmed to n_records."""
+    keep = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    o = Parse._opts(n_samples, region, end_is_int, want_gt, device, tokenizer, None)
+    g0 = np.empty((n_samples, capacity), np.int8)
+    g1 = np.empty((n_samples, capacity), np.int8)
+    start, stop = np.empty(capacity, np.uint32), np.empty(capacity, np.uint32)
+    ref, alt = np.empty(capacity, "S1"), np.empty(capacity, "S1")
+    pl, bg = np.zeros(max(1, n_samples), np.uint32), np.zeros(max(1, n_samples), np.uint32)
+    n, ns = C.c_uint64(), C.c_uint32()
+    check(lib().hb_parse_stream_host(keep.ctypes.data, keep.size, C.byref(o), slab_bytes, g0.ctypes.data, g1.ctypes.data,
+                                     capacity, start.ctypes.data, stop.ctypes.data, ref.ctypes.data, alt.ctypes.data,
+                                     pl.ctypes.data, bg.ctypes.data, C.byref(n), C.byref(ns)))
+    k = int(n.value)
+    return {"n": k, "n_slabs": int(ns.value), "gt0": g0[:, :k], "gt1": g1[:, :k], "start": start[:k], "stop": stop[:k],
+            "ref": ref[:k], "alt": alt[:k], "ploidy_err": pl[:n_samples], "badgt_err": bg[:n_samples]}
+
+
 def load_vcf_columns(path: str, sample: str, chrom: str = ""):
     """hb_load_vcf / hb_load_vcf_without_sample through ctypes, columnar."""
     r = Records()

@@ -149,16 +149,19 @@ static void probe_head(const uint8_t *h, size_t n, uint32_t n_samples, bool &gt_
 static int index_by_tokenizer(hb_parse *p, const Launch &L) {
     const uint64_t tile = tokenize_tile_bytes();
     const uint64_t n_tiles = (p->nbytes + tile - 1) / tile;
-    if (!p->d_cta) {
-        // one contiguous range of tiles per persistent CTA, 2 CTAs per SM
+    {
+        // one contiguous range of tiles per persistent CTA, 2 CTAs per SM (re-planned per run: a handle may
+        // be re-run on text of another length, see hb_parse_stream_host)
         uint64_t want = std::min<uint64_t>((uint64_t)p->sm_count * 2, n_tiles);
         if (want > 1024) want = 1024;
         p->tiles_per_cta = (n_tiles + want - 1) / want;
         p->n_cta = (uint32_t)((n_tiles + p->tiles_per_cta - 1) / p->tiles_per_cta);
         uint64_t est = p->tiles_per_cta * tile / p->first_line_len;
-        p->stage_cap = (uint32_t)std::min<uint64_t>(est + est / 2 + 64, 0x7fffffffull);
-        TRY(dev_alloc(&p->d_cta, p->n_cta));
-        TRY(dev_alloc(&p->d_cbase, p->n_cta + 1));
+        p->stage_cap = std::max<uint32_t>(p->stage_cap, (uint32_t)std::min<uint64_t>(est + est / 2 + 64, 0x7fffffffull));
+        if (!p->d_cta) {
+            TRY(dev_alloc(&p->d_cta, 1024));
+            TRY(dev_alloc(&p->d_cbase, 1024 + 1));
+        }
     }
     std::vector<CtaTok> h_cta(p->n_cta);
     std::vector<uint64_t> h_base(p->n_cta + 1);
@@ -192,7 +195,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
     LineIndex li{p->d_nl_after, p->d_cbase, p->n_cta, p->stage_cap};
 
     if (p->row_cap < n_lines || !p->d_start || !p->d_sites_state) {
-        uint64_t cap = std::max(n_lines, p->row_cap);
+        uint64_t cap = p->d_start ? std::max(n_lines + n_lines / 8 + 1024, p->row_cap) : n_lines;
         TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
         TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
         TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
@@ -213,15 +216,18 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
 
 // ---- records located by walking heads (uniform GT-only text): hb_walk.cu
 static int index_by_walker(hb_parse *p, const Launch &L) {
-    if (!p->d_wstart) {
+    {
         uint32_t k = 16;
         if (const char *e = getenv("HB_WALK_LINES")) { int v = atoi(e); if (v > 0 && v < 65536) k = (uint32_t)v; }
         p->n_walkers = walk_plan(p->nbytes, p->first_line_len, k, &p->walk_range);
-        TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
-        TRY(dev_alloc(&p->d_wrow, p->n_walkers));
-        uint64_t *wc = nullptr;
-        TRY(dev_alloc(&wc, p->n_walkers));
-        p->d_wcount = wc;
+        if (!p->d_wstart || p->n_walkers > p->walk_cap) {
+            TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
+            TRY(dev_alloc(&p->d_wrow, p->n_walkers));
+            uint64_t *wc = (uint64_t *)p->d_wcount;
+            TRY(dev_alloc(&wc, p->n_walkers));
+            p->d_wcount = wc;
+            p->walk_cap = p->n_walkers;
+        }
     }
     CU(cudaEventRecord(p->ev[0], p->stream));
     launch_walk_count(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
@@ -233,7 +239,7 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
     const uint64_t n_lines = p->h_st.n_lines, n_rec = p->h_st.n_records;
     p->n_lines = n_lines;
     if (p->row_cap < n_rec || !p->d_start) {
-        uint64_t cap = std::max(n_rec, p->row_cap);
+        uint64_t cap = p->d_start ? std::max(n_rec + n_rec / 8 + 1024, p->row_cap) : n_rec;
         TRY(dev_alloc(&p->d_start, cap)); TRY(dev_alloc(&p->d_stop, cap));
         TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
         TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
@@ -241,7 +247,10 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
         if (p->d_sites_state) { cudaFree(p->d_sites_state); p->d_sites_state = nullptr; }
         p->row_cap = cap;
     }
-    if (p->verify_cap < n_lines || !p->d_verify) { TRY(dev_alloc(&p->d_verify, n_lines)); p->verify_cap = n_lines; }
+    if (p->verify_cap < n_lines || !p->d_verify) {
+        const uint64_t cap = p->d_verify ? n_lines + n_lines / 8 + 1024 : n_lines;
+        TRY(dev_alloc(&p->d_verify, cap)); p->verify_cap = cap;
+    }
     launch_walk_write(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
                       p->d_wstart, p->d_wcount, p->d_wrow, p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs,
                       p->d_chrom_len, p->d_chrom5, p->d_rowinfo, p->d_nu_rows, p->d_verify, p->verify_cap, p->d_st, L);
@@ -293,9 +302,12 @@ static int run_parse(hb_parse *p) {
             CU(cudaMemsetAsync(p->d_cp, 0xff, p->cp_rows * p->ncp * sizeof(uint64_t), p->stream));
             launch_index_columns(p->d_text, p->d_rowinfo, p->d_nu_rows, n_nu, p->d_cp, p->ncp, L);
         }
-        uint64_t stride = (n_rec + kTV - 1) / kTV * kTV;
-        uint64_t bytes = stride * p->n_samples;
-        if (p->gt_bytes < bytes || p->gt_stride != stride) {
+        // the planes are re-used (with their stride) whenever the rows fit: a handle that is re-run on slabs of
+        // slightly different length must not re-allocate -- cudaFree synchronises the whole device
+        if (!p->d_gt[0] || n_rec > p->gt_stride) {
+            const uint64_t want = p->d_gt[0] ? n_rec + n_rec / 8 + 1024 : n_rec;
+            const uint64_t stride = (want + kTV - 1) / kTV * kTV;
+            const uint64_t bytes = stride * p->n_samples;
             TRY(dev_alloc(&p->d_gt[0], bytes)); TRY(dev_alloc(&p->d_gt[1], bytes));
             p->gt_bytes = bytes; p->gt_stride = stride;
         }
@@ -392,6 +404,116 @@ int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts
     rc = run_parse(p);
     if (rc != HB_OK) { hb_parse_free(p); return rc; }
     *out = p;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming form of hb_parse_host_text + hb_parse_fetch_matrix + hb_parse_fetch_sites: the text is cut
+// into slabs at line boundaries and two device slots alternate, so that the H2D copy of slab k+1, the
+// kernels of slab k and the D2H copy of slab k-1 run at the same time (PCIe is full duplex: the 2 bytes
+// per call going back hide behind the 4 bytes per call coming in).  Device memory is O(slab), so the
+// text may be far larger than HBM.
+// ---------------------------------------------------------------------------------------------
+int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, uint64_t slab_bytes,
+                         int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start, uint32_t *stop, char *ref,
+                         char *alt, uint32_t *ploidy_err, uint32_t *badgt_err, uint64_t *n_records, uint32_t *n_slabs) {
+    if (!opts || !n_records || (nbytes && !text)) return fail(HB_ERR_ARG, "null argument");
+    *n_records = 0;
+    if (n_slabs) *n_slabs = 0;
+    if (ploidy_err) memset(ploidy_err, 0, 4ull * opts->n_samples);
+    if (badgt_err) memset(badgt_err, 0, 4ull * opts->n_samples);
+    if (nbytes == 0) return HB_OK;
+    if (text[nbytes - 1] != '\n') return fail(HB_ERR_ARG, "the text must end with a newline");
+    if (slab_bytes == 0) slab_bytes = 1ull << 30;
+    std::vector<std::pair<uint64_t, uint64_t>> slabs;
+    uint64_t cap = 0;
+    for (uint64_t off = 0; off < nbytes;) {
+        uint64_t end = std::min(nbytes, off + slab_bytes);
+        if (end < nbytes) {
+            const void *q = memrchr(text + off, '\n', end - off);
+            if (q) end = (uint64_t)((const uint8_t *)q - text) + 1;
+            else {                                   // one line longer than a slab: take the whole line
+                const void *f = memchr(text + end, '\n', nbytes - end);
+                end = f ? (uint64_t)((const uint8_t *)f - text) + 1 : nbytes;
+            }
+        }
+        slabs.emplace_back(off, end - off);
+        cap = std::max(cap, end - off);
+        off = end;
+    }
+    TRY(ensure_device(opts->device));
+    struct Slot { hb_parse *p = nullptr; cudaStream_t compute = nullptr, d2h = nullptr; cudaEvent_t fetched = nullptr; } slot[2];
+    int rc = HB_OK;
+    auto cleanup = [&]() {
+        for (auto &s : slot) {
+            if (s.compute) cudaStreamSynchronize(s.compute);
+            if (s.d2h) cudaStreamSynchronize(s.d2h);
+            if (s.p) hb_parse_free(s.p);
+            if (s.fetched) cudaEventDestroy(s.fetched);
+            if (s.compute) cudaStreamDestroy(s.compute);
+            if (s.d2h) cudaStreamDestroy(s.d2h);
+        }
+    };
+    const size_t n_slots = std::min<size_t>(2, slabs.size());
+    for (size_t i = 0; i < n_slots && rc == HB_OK; ++i) {
+        Slot &s = slot[i];
+        if (cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fetched, cudaEventDisableTiming) != cudaSuccess) { rc = fail(HB_ERR_CUDA, "cannot create streams"); break; }
+        hb_parse_opts o = *opts;
+        o.stream = s.compute;
+        rc = new_parse(&o, &s.p);
+        if (rc == HB_OK) rc = dev_alloc(&s.p->d_text_owned, cap + 256);
+        if (rc == HB_OK) s.p->d_text = s.p->d_text_owned;
+    }
+    if (rc != HB_OK) { cleanup(); return rc; }
+    auto h2d = [&](size_t k) -> cudaError_t {
+        Slot &s = slot[k & 1];
+        cudaError_t e = cudaStreamWaitEvent(s.compute, s.fetched, 0);       // the slot's previous results have left
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.p->d_text_owned, text + slabs[k].first, slabs[k].second, cudaMemcpyHostToDevice, s.compute);
+        if (e == cudaSuccess) e = cudaMemsetAsync(s.p->d_text_owned + slabs[k].second, 0, 256, s.compute);
+        return e;
+    };
+    cudaError_t e = h2d(0);
+    uint64_t R = 0;
+    std::vector<uint32_t> pl(opts->n_samples), bg(opts->n_samples);
+    for (size_t k = 0; k < slabs.size() && rc == HB_OK && e == cudaSuccess; ++k) {
+        if (k + 1 < slabs.size()) e = h2d(k + 1);
+        if (e != cudaSuccess) break;
+        Slot &s = slot[k & 1];
+        s.p->nbytes = slabs[k].second;
+        rc = run_parse(s.p);                         // returns with the slot's compute stream idle
+        if (rc != HB_OK) break;
+        const uint64_t n = s.p->h_st.n_records;
+        if (R + n > out_stride) { rc = fail(HB_ERR_ARG, "more records than the output arrays hold"); break; }
+        if (n) {
+            if (opts->want_gt && opts->n_samples && s.p->d_gt[0]) {
+                if (gt0) e = cudaMemcpy2DAsync(gt0 + R, out_stride, s.p->d_gt[0], s.p->gt_stride, n, opts->n_samples, cudaMemcpyDeviceToHost, s.d2h);
+                if (gt1 && e == cudaSuccess) e = cudaMemcpy2DAsync(gt1 + R, out_stride, s.p->d_gt[1], s.p->gt_stride, n, opts->n_samples, cudaMemcpyDeviceToHost, s.d2h);
+            }
+            if (start && e == cudaSuccess) e = cudaMemcpyAsync(start + R, s.p->d_start, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+            if (stop && e == cudaSuccess) e = cudaMemcpyAsync(stop + R, s.p->d_stop, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+            if (ref && e == cudaSuccess) e = cudaMemcpyAsync(ref + R, s.p->d_ref, n, cudaMemcpyDeviceToHost, s.d2h);
+            if (alt && e == cudaSuccess) e = cudaMemcpyAsync(alt + R, s.p->d_alt, n, cudaMemcpyDeviceToHost, s.d2h);
+        }
+        if ((ploidy_err || badgt_err) && opts->want_gt && opts->n_samples && e == cudaSuccess) {
+            e = cudaMemcpyAsync(pl.data(), s.p->d_ploidy, 4ull * opts->n_samples, cudaMemcpyDeviceToHost, s.d2h);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(bg.data(), s.p->d_badgt, 4ull * opts->n_samples, cudaMemcpyDeviceToHost, s.d2h);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.d2h);
+            for (uint32_t i = 0; i < opts->n_samples && e == cudaSuccess; ++i) {
+                if (ploidy_err) ploidy_err[i] += pl[i];
+                if (badgt_err) badgt_err[i] += bg[i];
+            }
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(s.fetched, s.d2h);
+        R += n;
+    }
+    for (auto &s : slot) if (s.d2h && e == cudaSuccess) e = cudaStreamSynchronize(s.d2h);
+    cleanup();
+    if (rc != HB_OK) return rc;
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    *n_records = R;
+    if (n_slabs) *n_slabs = (uint32_t)slabs.size();
     return HB_OK;
 }
 

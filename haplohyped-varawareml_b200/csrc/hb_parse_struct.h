@@ -21,7 +21,7 @@ struct hb_parse {
     int end_is_int = 0, want_gt = 1, tokenizer = 0;
     bool with_tabs = false;
     bool use_walker = false;            // records located by walking heads (hb_walk.cu) instead of tokenizing
-    uint32_t n_walkers = 0;
+    uint32_t n_walkers = 0, walk_cap = 0;
     uint64_t walk_range = 0;
     uint64_t *d_wstart = nullptr, *d_wrow = nullptr, *d_verify = nullptr;
     void *d_wcount = nullptr;

@@ -815,16 +815,14 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     ck(cudaMalloc(&f->d_slot_off, (f->n_chunks + 1) * 8));
     ck(cudaMalloc(&f->d_totals, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
-    ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_site));
-    const size_t smem_fused = (size_t)kWpc * fa.warp_smem;
-    switch (f->nw) {
-        case 1: ck(attr_donor_frames<1>(smem_fused)); break;
-        case 2: ck(attr_donor_frames<2>(smem_fused)); break;
-        case 3: ck(attr_donor_frames<3>(smem_fused)); break;
-        case 4: ck(attr_donor_frames<4>(smem_fused)); break;
-        case 5: ck(attr_donor_frames<5>(smem_fused)); break;
-        default: ck(attr_donor_frames<6>(smem_fused)); break;
-    }
+    // the opt-in shared-memory ceiling is a per-function, process-wide attribute: always raise it to the device
+    // maximum, so that concurrent callers (the converter parses two files at once) cannot shrink each other's limit
+    int smem_max = 0;
+    ck(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, f->device));
+    smem_max -= 1024;                            // room for the kernels' few static __shared__ words
+    ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    ck(attr_donor_frames<1>(smem_max)); ck(attr_donor_frames<2>(smem_max)); ck(attr_donor_frames<3>(smem_max));
+    ck(attr_donor_frames<4>(smem_max)); ck(attr_donor_frames<5>(smem_max)); ck(attr_donor_frames<6>(smem_max));
     if (e != cudaSuccess) { hb_frames_free(f); return api_fail(HB_ERR_MEM, std::string("CUDA: ") + cudaGetErrorString(e)); }
     int rc = frames_run(f, p);
     if (rc != HB_OK) { hb_frames_free(f); return rc; }

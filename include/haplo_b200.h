@@ -103,6 +103,17 @@ typedef struct hb_parse_info {
 int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
 /* text already in HBM.  d_text must be 16-byte aligned with >= 64 readable bytes of slack after nbytes. */
 int hb_parse_device_text(const uint8_t *d_text, uint64_t nbytes, const hb_parse_opts *opts, hb_parse **out);
+/* Streaming form: host text -> genotype matrix + site columns in HOST memory, in one call.  The text is cut into
+ * slabs of about slab_bytes (0 = 1 GiB) at line boundaries; H2D of the next slab, the kernels of the current one and
+ * D2H of the previous one overlap, and device memory is O(slab_bytes) whatever the size of the text.  Use pinned
+ * host buffers for the overlap to be real.  gt0/gt1: [n_samples][out_stride] (row = sample, as
+ * hb_parse_fetch_matrix with out_stride instead of n_records); out_stride = capacity in records of every output
+ * array (HB_ERR_ARG when exceeded; the number of lines is always enough).  Any output pointer may be NULL.
+ * ploidy_err / badgt_err: [n_samples], see hb_parse_fetch_sample_errors.  Replaces, for one (file, region), the
+ * n_samples calls of parse_vcf.cpp:30-71 that vcf_to_h5.py:150-152 makes. */
+int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, uint64_t slab_bytes,
+                         int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start, uint32_t *stop, char *ref,
+                         char *alt, uint32_t *ploidy_err, uint32_t *badgt_err, uint64_t *n_records, uint32_t *n_slabs);
 /* a whole .vcf / .vcf.gz (BGZF or plain gzip): header + body, all samples, no per-sample cache.
  * What the vcf_to_h5 converter drives (src/haplohyped/vcf_to_h5.py:98-101 without the per-donor re-scan). */
 int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int device, hb_parse **out);

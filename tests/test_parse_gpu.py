@@ -260,3 +260,39 @@ def test_walker_cannot_be_fooled_by_hidden_newlines(capi, monkeypatch):
             p, info = _check_matrix(capi, text, n, "chr22", tokenizer=3)
             assert info.walker_fallbacks == 1 and info.tokenizer_used == 1 and info.n_lines == 102
             assert info.n_records == 100
+
+
+@pytest.mark.parametrize("fmt,kinds,slab", [("GT", "phased", 3000), ("GT", "mixed", 20000), ("GT:GQ:DP", "mixed", 7000),
+                                            ("GT", "mixed", 1 << 30)])
+def test_stream_host_equals_oracle(capi, fmt, kinds, slab):
+    """hb_parse_stream_host: slabs cut at line boundaries, two device slots, H2D / kernels / D2H overlapped --
+    the concatenated result is the same matrix, whatever the slab size (here: many slabs, and one)."""
+    text, samples = synth.random_vcf(1500, 41, seed=77, fmt=fmt, kinds=kinds)
+    ora = oracle.parse_text(text, "*", "chr22")
+    body = synth.body_of(text)
+    r = capi.parse_stream_host(body, len(samples), capacity=1500, region="chr22", slab_bytes=slab)
+    assert r["n"] == ora["n"] and r["n_slabs"] == (1 if slab >= len(body) else r["n_slabs"]) and r["n_slabs"] >= 1
+    if slab < len(body):
+        assert r["n_slabs"] >= len(body) // slab
+    assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"])
+    assert np.array_equal(r["start"], ora["start"]) and np.array_equal(r["stop"], ora["stop"])
+    assert np.array_equal(r["ref"], ora["ref"]) and np.array_equal(r["alt"], ora["alt"])
+    assert r["ploidy_err"].sum() == 0 and r["badgt_err"].sum() == 0
+    with pytest.raises(capi.HaploError):                               # capacity is checked, not overrun
+        capi.parse_stream_host(body, len(samples), capacity=ora["n"] - 1, region="chr22", slab_bytes=slab)
+
+
+def test_stream_host_uniform_text_and_errors(capi):
+    spec = capi.synth_spec(4000, 300, seed=3, mix=1)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    ora = oracle.parse_text(text, "*", "chr22")
+    body = synth.body_of(text)
+    r = capi.parse_stream_host(body, 300, capacity=4000, region="chr22", slab_bytes=len(body) // 7)
+    assert r["n"] == ora["n"] and r["n_slabs"] >= 7
+    assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"]) and np.array_equal(r["start"], ora["start"])
+    # a haploid call of one sample in a late slab is reported for that sample only
+    S = ["a", "b", "c"]
+    lines = [f"chr22\t{100 + i}\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1|1\t0|0\n" for i in range(400)]
+    lines[333] = "chr22\t433\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1\t0|0\n"
+    r = capi.parse_stream_host("".join(lines).encode(), 3, capacity=400, region="", slab_bytes=2000)
+    assert r["n"] == 400 and list(r["ploidy_err"]) == [0, 1, 0] and r["n_slabs"] > 3
