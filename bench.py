@@ -185,6 +185,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off stdout: rank 0 prints ONE line
         dist.init_process_group("nccl", device_id=dev)
 
     V, S = args.variants, args.samples
@@ -297,8 +298,8 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T,
-               "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk, "steps": args.e2e_steps,
+        e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T * world,
+               "d2h_bytes_per_step": (2 * S * Vk + 10 * Vk) * world, "steps": args.e2e_steps,
                "api": "hb_parse_stream_host: pinned host text -> genotype matrix [S][V'] x2 + site columns in pinned host "
                       "memory; slabs of %d MiB, H2D / kernels / D2H overlapped" % (args.slab_bytes >> 20)}
         # the streamed result is the same matrix the device-resident step produced

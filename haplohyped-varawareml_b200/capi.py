@@ -71,6 +71,7 @@ EXPORTS = [
     "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
+    "hb_bgzf_inflate",
     "hb_compress_records", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_decode_frames",
@@ -109,6 +110,8 @@ def lib():
         L.hb_parse_chrom_runs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p,
                                           C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_parse_free.argtypes = [C.c_void_p]
+        L.hb_bgzf_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int,
+                                      C.POINTER(C.c_float)]
         if hasattr(L, "hb_compress_records"):
             L.hb_compress_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
             L.hb_frames_get_info.argtypes = [C.c_void_p, C.POINTER(FramesInfo)]
@@ -369,6 +372,18 @@ def load_vcf_columns(path: str, sample: str, chrom: str = ""):
         return d
     finally:
         lib().hb_records_free(C.byref(r))
+
+
+def bgzf_inflate(data: bytes, device: int = 0, with_ms: bool = False):
+    """BGZF bytes -> text, inflated on the GPU (hb_bgzf_inflate)."""
+    src = np.frombuffer(data, np.uint8)
+    n = C.c_uint64()
+    check(lib().hb_bgzf_inflate(src.ctypes.data, src.size, None, 0, C.byref(n), device, None))
+    out = np.empty(max(1, n.value), np.uint8)
+    ms = C.c_float()
+    check(lib().hb_bgzf_inflate(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(n), device, C.byref(ms)))
+    text = out[:n.value].tobytes()
+    return (text, float(ms.value)) if with_ms else text
 
 
 def decode_frames(frames, chunk_nbytes: int, planar: bool = False, device: int = 0) -> np.ndarray:

@@ -1,0 +1,382 @@
+// hb_inflate.cu -- BGZF -> text on the GPU: the step in front of the path.
+//
+// In the reference every byte of VCF text comes out of htslib's BGZF reader (tbx_itr_next / bcf_read inside
+// vcfpp.h:1455-1484): zlib inflate of <= 64 KiB gzip members, one core, once per (donor, chromosome) call.  BGZF
+// members are independent DEFLATE streams (RFC 1951 inside RFC 1952 framing with a 'BC' extra subfield that
+// carries the member size), so here the COMPRESSED file goes over PCIe (20-50x fewer bytes than the text) and
+// one warp inflates one member straight into the HBM text buffer the tokenizer / walker reads:
+//   * the warp builds the literal/length and distance decode tables of each DEFLATE block together
+//     (canonical code assignment with match.any ranks, table entries filled 32 at a time),
+//   * every lane then runs the same symbol loop on the same bit buffer (no divergence, no communication),
+//   * LZ77 copies are done by all 32 lanes (sources always precede the current output position, so the
+//     32-byte pieces of one match are independent), literals are stored by lane 0.
+// Stored and fixed-Huffman blocks are handled too.  CRC32 is not checked; ISIZE is.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/haplo_b200.h"
+#include "hb_common.cuh"
+#include "hb_internal.h"
+#include "hb_parse_struct.h"
+
+namespace hb {
+
+constexpr int kLitBits = 10, kDistBits = 8;       // primary table widths; longer codes take the canonical slow path
+constexpr int kInfWarps = 8;
+
+__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct HuffTab {            // one canonical Huffman code, in shared memory
+    uint16_t *tab;          // [1 << bits]: (symbol << 4) | length, 0 = longer than `bits` (or unused)
+    uint16_t *sorted;       // symbols ordered by (length, symbol)
+    uint16_t *count;        // [16] codes per length
+    int bits;
+};
+
+struct BitReader {          // identical in every lane of the warp
+    const uint8_t *src;
+    uint32_t ip, n;         // next byte, payload bytes
+    uint64_t bb;
+    int bc;
+    __device__ __forceinline__ void refill() {
+        if (bc <= 32) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(src + ip);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+            const uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8u);   // may read past n: the buffer has slack
+            bb |= (uint64_t)v << bc;
+            bc += 32;
+            ip += 4;
+        }
+    }
+    __device__ __forceinline__ uint32_t take(int k) {
+        const uint32_t v = (uint32_t)bb & ((1u << k) - 1u);
+        bb >>= k;
+        bc -= k;
+        return v;
+    }
+    // bytes of the payload really consumed (bits still in the buffer were fetched, not used)
+    __device__ __forceinline__ bool overrun() const { return (int64_t)ip * 8 - bc > (int64_t)n * 8; }
+};
+
+// canonical decode of one symbol whose code may be up to 15 bits (puff's loop); -1 on an invalid code
+__device__ int decode_slow(const HuffTab &h, BitReader &br) {
+    int code = 0, first = 0, index = 0;
+    uint32_t bits = (uint32_t)br.bb;
+    for (int len = 1; len <= 15; ++len) {
+        code |= bits & 1;
+        bits >>= 1;
+        const int count = h.count[len];
+        if (code - count < first) { br.take(len); return h.sorted[index + (code - first)]; }
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+__device__ __forceinline__ int decode_sym(const HuffTab &h, BitReader &br) {
+    const uint32_t e = h.tab[(uint32_t)br.bb & ((1u << h.bits) - 1u)];
+    const int len = e & 15;
+    if (len) { br.take(len); return (int)(e >> 4); }
+    return decode_slow(h, br);
+}
+
+// lens[0..nsym) in shared memory -> count / sorted / primary table.  Returns false for an over-subscribed code.
+__device__ bool build_table(HuffTab &h, const uint8_t *lens, int nsym, uint16_t *cursor /* [16] scratch */) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 16) h.count[lane] = 0;
+    __syncwarp();
+    for (int base = 0; base < nsym; base += 32) {
+        const int s = base + lane;
+        const int L = s < nsym ? lens[s] : 0;
+        const unsigned peers = __match_any_sync(0xffffffffu, L);
+        if (L && (peers & ((1u << lane) - 1u)) == 0) h.count[L] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    // offsets of each length in `sorted`; Kraft check (every lane, redundantly)
+    int left = 1, off = 0;
+    bool ok = true;
+    for (int len = 1; len <= 15; ++len) {
+        left <<= 1;
+        left -= h.count[len];
+        if (left < 0) ok = false;
+        if (lane == 0) cursor[len] = (uint16_t)off;
+        off += h.count[len];
+    }
+    __syncwarp();
+    for (int base = 0; base < nsym; base += 32) {
+        const int s = base + lane;
+        const int L = s < nsym ? lens[s] : 0;
+        const unsigned peers = __match_any_sync(0xffffffffu, L);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (L) h.sorted[cursor[L] + rank] = (uint16_t)s;
+        __syncwarp();
+        if (L && rank == 0) cursor[L] += (uint16_t)__popc(peers);
+        __syncwarp();
+    }
+    // primary table: entry idx holds the symbol whose code is a prefix of idx (bit 0 of idx = first bit read)
+    for (int idx = lane; idx < (1 << h.bits); idx += 32) {
+        int code = 0, first = 0, index = 0;
+        uint16_t e = 0;
+        for (int len = 1; len <= h.bits; ++len) {
+            code |= (idx >> (len - 1)) & 1;
+            const int count = h.count[len];
+            if (code - count < first) { e = (uint16_t)((h.sorted[index + (code - first)] << 4) | len); break; }
+            index += count;
+            first += count;
+            first <<= 1;
+            code <<= 1;
+        }
+        h.tab[idx] = e;
+    }
+    __syncwarp();
+    return ok;
+}
+
+struct InflateArgs {
+    const uint8_t *comp;         // the whole compressed file in HBM
+    const uint64_t *coff;        // [n] offset of each member's DEFLATE payload
+    const uint32_t *clen;        // [n] payload bytes
+    const uint64_t *ooff;        // [n] offset of the member's text in `out`
+    const uint32_t *olen;        // [n] ISIZE
+    uint8_t *out;
+    uint32_t n_blocks;
+    int *status;                 // [n] 0 = ok
+};
+
+constexpr int kInfSmemPerWarp = 2 * (1 << kLitBits) + 2 * (1 << kDistBits) + 2 * 288 + 2 * 32 + 2 * 16 * 3 + 2 * 16 + 320 + 2 * 128 + 2 * 19 + 2 * 16 + 26;
+
+__global__ void __launch_bounds__(kInfWarps * 32) inflate_bgzf_kernel(const InflateArgs a) {
+    __shared__ __align__(16) uint8_t smem[kInfWarps][(kInfSmemPerWarp + 15) & ~15];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t blk = blockIdx.x * kInfWarps + warp;
+    if (blk >= a.n_blocks) return;
+    uint8_t *sm = smem[warp];
+    HuffTab lit, dist, cl;
+    lit.tab = reinterpret_cast<uint16_t *>(sm); sm += 2 * (1 << kLitBits);
+    dist.tab = reinterpret_cast<uint16_t *>(sm); sm += 2 * (1 << kDistBits);
+    lit.sorted = reinterpret_cast<uint16_t *>(sm); sm += 2 * 288;
+    dist.sorted = reinterpret_cast<uint16_t *>(sm); sm += 2 * 32;
+    lit.count = reinterpret_cast<uint16_t *>(sm); sm += 2 * 16;
+    dist.count = reinterpret_cast<uint16_t *>(sm); sm += 2 * 16;
+    cl.count = reinterpret_cast<uint16_t *>(sm); sm += 2 * 16;
+    uint16_t *cursor = reinterpret_cast<uint16_t *>(sm); sm += 2 * 16;
+    cl.tab = reinterpret_cast<uint16_t *>(sm); sm += 2 * 128;
+    cl.sorted = reinterpret_cast<uint16_t *>(sm); sm += 2 * 19 + 2;
+    uint8_t *lens = sm;          // [320] code lengths: literal/length symbols then distance symbols
+    lit.bits = kLitBits; dist.bits = kDistBits; cl.bits = 7;
+
+    BitReader br;
+    br.src = a.comp + a.coff[blk];
+    br.n = a.clen[blk];
+    br.ip = 0; br.bb = 0; br.bc = 0;
+    uint8_t *out = a.out + a.ooff[blk];
+    const uint32_t olen = a.olen[blk];
+    uint32_t op = 0;
+    int err = 0;
+    for (int last = 0; !last && !err;) {
+        br.refill();
+        last = (int)br.take(1);
+        const int type = (int)br.take(2);
+        if (type == 0) {                                   // stored
+            br.take(br.bc & 7);                            // to the byte boundary
+            br.refill();
+            const uint32_t len = br.take(16), nlen = br.take(16);
+            if ((len ^ nlen) != 0xFFFFu) { err = 1; break; }
+            // bytes still in the bit buffer belong to the stored data
+            const uint32_t pos = br.ip - (uint32_t)(br.bc >> 3);
+            if (pos + len > br.n || op + len > olen) { err = 2; break; }
+            for (uint32_t i = lane; i < len; i += 32) out[op + i] = br.src[pos + i];
+            op += len;
+            br.ip = pos + len; br.bb = 0; br.bc = 0;
+            __syncwarp();
+            continue;
+        }
+        if (type == 3) { err = 3; break; }
+        int nlit, ndist;
+        if (type == 1) {                                   // fixed code
+            for (int s = lane; s < 288; s += 32) lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+            if (lane < 30) lens[288 + lane] = 5;
+            nlit = 288; ndist = 30;
+            __syncwarp();
+        } else {                                           // dynamic code
+            nlit = (int)br.take(5) + 257;
+            ndist = (int)br.take(5) + 1;
+            const int ncl = (int)br.take(4) + 4;
+            if (nlit > 286 || ndist > 30) { err = 4; break; }
+            if (lane < 19) lens[lane] = 0;
+            __syncwarp();
+            for (int i = 0; i < ncl; ++i) {
+                br.refill();
+                const uint32_t v = br.take(3);
+                if (lane == 0) lens[c_clorder[i]] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (!build_table(cl, lens, 19, cursor)) { err = 5; break; }
+            // the nlit + ndist code lengths, run-length coded (every lane decodes; lane 0 writes)
+            int i = 0, prev = 0;
+            while (i < nlit + ndist) {
+                br.refill();
+                const int sym = decode_sym(cl, br);
+                if (sym < 0) { err = 6; break; }
+                int rep = 1, val = sym;
+                if (sym == 16) { if (i == 0) { err = 7; break; } val = prev; rep = 3 + (int)br.take(2); }
+                else if (sym == 17) { val = 0; rep = 3 + (int)br.take(3); }
+                else if (sym == 18) { val = 0; rep = 11 + (int)br.take(7); }
+                if (i + rep > nlit + ndist) { err = 8; break; }
+                // lens is laid out [0,288) literal/length, [288,320) distance
+                for (int k = lane; k < rep; k += 32) { const int s = i + k; lens[s < nlit ? s : 288 + (s - nlit)] = (uint8_t)val; }
+                prev = val;
+                i += rep;
+            }
+            if (err) break;
+            __syncwarp();
+            if (lens[256] == 0) { err = 9; break; }
+        }
+        if (!build_table(lit, lens, nlit, cursor)) { err = 10; break; }
+        if (!build_table(dist, lens + 288, ndist, cursor)) { err = 11; break; }
+        // ---- symbols
+        for (;;) {
+            br.refill();
+            int sym = decode_sym(lit, br);
+            if (sym < 256) {
+                if (sym < 0) { err = 12; break; }
+                if (op >= olen) { err = 13; break; }
+                if (lane == 0) out[op] = (uint8_t)sym;
+                ++op;
+                continue;
+            }
+            if (sym == 256) break;
+            sym -= 257;
+            if (sym >= 29) { err = 14; break; }
+            const uint32_t len = c_lbase[sym] + br.take(c_lext[sym]);
+            br.refill();
+            const int ds = decode_sym(dist, br);
+            if (ds < 0 || ds >= 30) { err = 15; break; }
+            const uint32_t d = c_dbase[ds] + br.take(c_dext[ds]);
+            if (d > op || op + len > olen) { err = 16; break; }
+            __syncwarp();                                  // earlier stores of the warp are visible to the loads below
+            const uint8_t *from = out + op - d;
+            if (d >= len) { for (uint32_t i = lane; i < len; i += 32) out[op + i] = __ldcg(from + i); }
+            else { for (uint32_t i = lane; i < len; i += 32) out[op + i] = __ldcg(from + i % d); }
+            op += len;
+        }
+        if (br.overrun()) err = 17;
+        __syncwarp();
+    }
+    if (!err && op != olen) err = 18;
+    if (lane == 0) a.status[blk] = err;
+}
+
+// BGZF member table of a whole file (host): false when the bytes are not BGZF
+bool bgzf_index(const uint8_t *raw, uint64_t size, std::vector<uint64_t> &coff, std::vector<uint32_t> &clen,
+                std::vector<uint64_t> &ooff, std::vector<uint32_t> &olen, uint64_t &total) {
+    uint64_t p = 0;
+    total = 0;
+    while (p < size) {
+        if (p + 18 > size) return false;
+        const uint8_t *h = raw + p;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+        const uint32_t xlen = h[10] | (h[11] << 8);
+        uint32_t bsize = 0;
+        bool found = false;
+        uint64_t q = p + 12;
+        const uint64_t xe = p + 12 + xlen;
+        if (xe > size) return false;
+        while (q + 4 <= xe) {
+            const uint32_t slen = raw[q + 2] | (raw[q + 3] << 8);
+            if (raw[q] == 'B' && raw[q + 1] == 'C' && slen == 2) { bsize = (raw[q + 4] | (raw[q + 5] << 8)) + 1; found = true; }
+            q += 4 + slen;
+        }
+        if (!found || p + bsize > size || bsize < 12 + xlen + 8) return false;
+        if (h[3] & ~4) return false;                       // FNAME / FCOMMENT / FHCRC: not what bgzip writes
+        const uint8_t *tr = raw + p + bsize - 4;
+        const uint32_t isize = tr[0] | (tr[1] << 8) | (tr[2] << 16) | ((uint32_t)tr[3] << 24);
+        if (isize > 65536) return false;
+        if (isize) {                                       // the 28-byte EOF marker (and any empty member) carries no text
+            coff.push_back(p + 12 + xlen);
+            clen.push_back(bsize - 12 - xlen - 8);
+            ooff.push_back(total);
+            olen.push_back(isize);
+        }
+        total += isize;
+        p += bsize;
+    }
+    return true;
+}
+
+// raw (host, BGZF) -> d_out (device, `total` bytes).  d_out must hold total bytes.
+int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<uint64_t> &coff,
+                           const std::vector<uint32_t> &clen, const std::vector<uint64_t> &ooff,
+                           const std::vector<uint32_t> &olen, uint8_t *d_out, cudaStream_t stream, float *ms) {
+    const uint32_t n = (uint32_t)coff.size();
+    if (!n) return HB_OK;
+    uint8_t *d_comp = nullptr;
+    uint64_t *d_coff = nullptr, *d_ooff = nullptr;
+    uint32_t *d_clen = nullptr, *d_olen = nullptr;
+    int *d_status = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cudaMalloc(&d_comp, size + 64));
+    ck(cudaMalloc(&d_coff, n * 8ull)); ck(cudaMalloc(&d_ooff, n * 8ull));
+    ck(cudaMalloc(&d_clen, n * 4ull)); ck(cudaMalloc(&d_olen, n * 4ull));
+    ck(cudaMalloc(&d_status, n * 4ull));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<int> status(n, 0);
+    if (e == cudaSuccess) {
+        ck(cudaMemcpyAsync(d_comp, raw, size, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemsetAsync(d_comp + size, 0, 64, stream));
+        ck(cudaMemcpyAsync(d_coff, coff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_ooff, ooff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_clen, clen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_olen, olen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
+        InflateArgs a{d_comp, d_coff, d_clen, d_ooff, d_olen, d_out, n, d_status};
+        if (ms) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, stream); }
+        inflate_bgzf_kernel<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, stream>>>(a);
+        count_launch();
+        if (ms) cudaEventRecord(ev1, stream);
+        ck(cudaGetLastError());
+        ck(cudaMemcpyAsync(status.data(), d_status, n * 4ull, cudaMemcpyDeviceToHost, stream));
+        ck(cudaStreamSynchronize(stream));
+        if (ms && e == cudaSuccess) cudaEventElapsedTime(ms, ev0, ev1);
+    }
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    cudaFree(d_comp); cudaFree(d_coff); cudaFree(d_ooff); cudaFree(d_clen); cudaFree(d_olen); cudaFree(d_status);
+    if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    for (uint32_t i = 0; i < n; ++i)
+        if (status[i]) return api_fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")");
+    return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+// host BGZF bytes -> host text, inflated on the GPU (tests; the file path keeps the text in HBM)
+extern "C" int hb_bgzf_inflate(const uint8_t *bgzf, uint64_t nbytes, uint8_t *out, uint64_t cap, uint64_t *out_len,
+                               int device, float *kernel_ms) {
+    if (!bgzf || !out_len) return api_fail(HB_ERR_ARG, "null argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return api_fail(HB_ERR_CUDA, "no CUDA device: libhaplo_b200 has no CPU fallback");
+    if (cudaSetDevice(device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    std::vector<uint64_t> coff, ooff;
+    std::vector<uint32_t> clen, olen;
+    uint64_t total = 0;
+    if (!bgzf_index(bgzf, nbytes, coff, clen, ooff, olen, total)) return api_fail(HB_ERR_IO, "not a BGZF file");
+    *out_len = total;
+    if (!out) return HB_OK;
+    if (cap < total) return api_fail(HB_ERR_ARG, "buffer too small");
+    if (!total) return HB_OK;
+    uint8_t *d_out = nullptr;
+    if (cudaMalloc(&d_out, total) != cudaSuccess) return api_fail(HB_ERR_MEM, "cudaMalloc failed");
+    int rc = inflate_bgzf_to_device(bgzf, nbytes, coff, clen, ooff, olen, d_out, nullptr, kernel_ms);
+    if (rc == HB_OK && cudaMemcpy(out, d_out, total, cudaMemcpyDeviceToHost) != cudaSuccess) rc = api_fail(HB_ERR_CUDA, "D2H failed");
+    cudaFree(d_out);
+    return rc;
+}

@@ -134,6 +134,12 @@ int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint
                         char *names, uint64_t names_cap, uint64_t *names_len);
 void hb_parse_free(hb_parse *p);
 
+/* BGZF (htslib's block gzip: what `bgzip` writes and tabix / vcfpp.h:1381,1468 read) inflated on the GPU, one warp per
+ * <= 64 KiB member: host BGZF bytes -> host text.  out == NULL: only *out_len is set.  The file-level entry points
+ * (hb_load_vcf, hb_parse_file) use the same kernel but leave the text in HBM.  kernel_ms may be NULL. */
+int hb_bgzf_inflate(const uint8_t *bgzf, uint64_t nbytes, uint8_t *out, uint64_t cap, uint64_t *out_len, int device,
+                    float *kernel_ms);
+
 /* ------------------------------------------------------------------------------------------
  * C. Storage: Blosc2 byte-shuffle (typesize 35) + LZ4 block encoder + Blosc2 chunk / cframe
  *    framing, one frame per (sample, HDF5 chunk) -- what h5py + hdf5plugin produce for

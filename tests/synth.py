@@ -105,3 +105,21 @@ def body_of(text: bytes) -> bytes:
     i = text.index(b"#CHROM")
     j = text.index(b"\n", i)
     return text[j + 1:]
+
+
+def bgzf_compress(data: bytes, level: int = 6, block: int = 0xff00, strategy=None) -> bytes:
+    """What `bgzip` writes: <= 64 KiB gzip members with a 'BC' extra subfield + the 28-byte EOF member
+    (htslib bgzf.c).  Stock zlib does the DEFLATE, so this is an independent producer for the GPU inflater."""
+    import struct
+    import zlib
+    out = []
+    for i in range(0, len(data), block):
+        chunk = data[i:i + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY if strategy is None else strategy)
+        comp = c.compress(chunk) + c.flush()
+        assert len(comp) + 26 <= 65536
+        out.append(struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, len(comp) + 25))
+        out.append(comp)
+        out.append(struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    out.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return b"".join(out)

@@ -1,0 +1,90 @@
+"""GPU BGZF inflate (the step in front of the path) against stock zlib: the members are
+produced by Python's zlib (an independent, third-party DEFLATE encoder) in BGZF framing, inflated on the GPU
+and compared byte for byte with the input.  Dynamic, fixed and stored DEFLATE blocks, all levels."""
+import gzip
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(built):
+    from haplohyped_varawareml_b200 import capi as c
+    return c
+
+
+def _vcf_text(n=3000, s=60, fmt="GT", seed=1):
+    text, samples = synth.random_vcf(n, s, seed=seed, fmt=fmt, kinds="mixed")
+    return text, samples
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_vcf_text_roundtrip(capi, level):
+    text, _ = _vcf_text(fmt="GT:GQ:DP" if level == 6 else "GT")
+    assert len(text) > 200_000                                         # several members
+    assert capi.bgzf_inflate(synth.bgzf_compress(text, level)) == text
+
+
+def test_block_types_and_edges(capi):
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, 150_000, dtype=np.uint8).tobytes()    # incompressible -> stored blocks
+    assert capi.bgzf_inflate(synth.bgzf_compress(noise, 6)) == noise
+    assert capi.bgzf_inflate(synth.bgzf_compress(noise, 0)) == noise   # level 0: stored only
+    text, _ = _vcf_text(800, 20)
+    assert capi.bgzf_inflate(synth.bgzf_compress(text, 6, strategy=zlib.Z_FIXED)) == text          # fixed Huffman
+    assert capi.bgzf_inflate(synth.bgzf_compress(text, 6, strategy=zlib.Z_HUFFMAN_ONLY)) == text   # no matches at all
+    assert capi.bgzf_inflate(synth.bgzf_compress(text, 6, strategy=zlib.Z_RLE)) == text            # distance-1 matches only
+    runs = (b"A" * 70_000 + b"ab" * 40_000 + bytes(range(256)) * 300)                              # overlapping copies, long matches
+    assert capi.bgzf_inflate(synth.bgzf_compress(runs, 9)) == runs
+    skew = bytes(rng.choice(np.arange(256, dtype=np.uint8), 120_000, p=np.r_[0.6, 0.2, [0.2 / 254] * 254]))
+    assert capi.bgzf_inflate(synth.bgzf_compress(skew, 9)) == skew     # very uneven code lengths (> 10-bit codes)
+    assert capi.bgzf_inflate(synth.bgzf_compress(b"x", 6)) == b"x"
+    assert capi.bgzf_inflate(synth.bgzf_compress(b"", 6)) == b""       # EOF member only
+    small = synth.bgzf_compress(text, 6, block=777)                    # many tiny members
+    assert capi.bgzf_inflate(small) == text
+
+
+def test_corrupt_and_foreign_input_is_rejected(capi, golden_dir):
+    text, _ = _vcf_text(500, 10)
+    good = bytearray(synth.bgzf_compress(text, 6))
+    bad = bytearray(good)
+    bad[18 + 40] ^= 0x55                                               # inside the first DEFLATE payload
+    try:
+        out = capi.bgzf_inflate(bytes(bad))
+        assert out != text                                             # (a flipped bit may still be a valid stream)
+    except capi.HaploError:
+        pass
+    plain = open(os.path.join(golden_dir, "chr22.filtered.vcf.gz"), "rb").read()                    # plain gzip, not BGZF
+    with pytest.raises(capi.HaploError):
+        capi.bgzf_inflate(plain)
+
+
+def test_bgzf_file_through_the_reference_api(capi, tmp_path, built):
+    """A bgzipped VCF through parse_vcf.load_vcf / hb_parse_file: GPU inflate -> GPU parse, vs the oracle on the text."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "haplohyped-varawareml_b200"))
+    import parse_vcf
+    text, samples = _vcf_text(2500, 17, seed=9)
+    path = str(tmp_path / "chr22.filtered.vcf.gz")
+    open(path, "wb").write(synth.bgzf_compress(text, 6))
+    gz = str(tmp_path / "same.vcf.gz")
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+    for s in (samples[0], samples[9], samples[16]):
+        exp = oracle.parse_text(text, s, "chr22")
+        got = parse_vcf.load_vcf(path, s, "chr22")
+        assert len(got) == exp["n"]
+        assert [r[1] for r in got] == list(exp["start"]) and [r[5] for r in got] == list(exp["gt0"]) and [r[6] for r in got] == list(exp["gt1"])
+        assert got == parse_vcf.load_vcf(gz, s, "chr22")                # plain gzip (CPU zlib) gives the same tuples
+    p = capi.Parse.from_file(path, region="chr22")
+    assert p.sample_names() == samples
+    ora = oracle.parse_text(text, "*", "chr22")
+    g0, g1 = p.matrix()
+    assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
