@@ -33,7 +33,7 @@ class ParseInfo(C.Structure):
                 ("n_nonuniform", C.c_uint64), ("n_bad_gt", C.c_uint64), ("n_bad_cols", C.c_uint64),
                 ("n_nogt", C.c_uint64), ("tokenizer_used", C.c_int),
                 ("ms_tokenize", C.c_float), ("ms_sites", C.c_float), ("ms_decode", C.c_float),
-                ("walker_fallbacks", C.c_int)]
+                ("walker_fallbacks", C.c_int), ("ms_inflate", C.c_float), ("compressed_bytes", C.c_uint64)]
 
 
 class Records(C.Structure):
@@ -71,7 +71,7 @@ EXPORTS = [
     "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
-    "hb_bgzf_inflate",
+    "hb_bgzf_inflate", "hb_bgzf_compress_host",
     "hb_compress_records", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_decode_frames",
@@ -372,6 +372,18 @@ def load_vcf_columns(path: str, sample: str, chrom: str = ""):
         return d
     finally:
         lib().hb_records_free(C.byref(r))
+
+
+def bgzf_compress_host(text, level: int = 6) -> np.ndarray:
+    """text (bytes / uint8 array) -> BGZF bytes (uint8 array), stock zlib on all host threads (test / bench utility)."""
+    src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    L = lib()
+    L.hb_bgzf_compress_host.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    n = C.c_uint64()
+    check(L.hb_bgzf_compress_host(src.ctypes.data, src.size, level, None, 0, C.byref(n)))
+    out = np.empty(n.value, np.uint8)
+    check(L.hb_bgzf_compress_host(src.ctypes.data, src.size, level, out.ctypes.data, out.size, C.byref(n)))
+    return out[:n.value]
 
 
 def bgzf_inflate(data: bytes, device: int = 0, with_ms: bool = False):

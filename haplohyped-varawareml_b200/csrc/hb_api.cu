@@ -540,6 +540,7 @@ int hb_parse_get_info(const hb_parse *p, hb_parse_info *info) {
     info->tokenizer_used = p->index_used;
     info->walker_fallbacks = p->walker_fallbacks;
     info->ms_tokenize = p->ms_tok; info->ms_sites = p->ms_sites; info->ms_decode = p->ms_decode;
+    info->ms_inflate = p->ms_inflate; info->compressed_bytes = p->compressed_bytes;
     return HB_OK;
 }
 
@@ -608,6 +609,14 @@ int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint
 // =============================================================================================
 // File level: .vcf / .vcf.gz reader (BGZF blocks inflate in parallel) + per-(file, region) cache
 // =============================================================================================
+namespace hb {
+bool bgzf_index(const uint8_t *raw, uint64_t size, std::vector<uint64_t> &coff, std::vector<uint32_t> &clen,
+                std::vector<uint64_t> &ooff, std::vector<uint32_t> &olen, uint64_t &total);
+int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<uint64_t> &coff,
+                           const std::vector<uint32_t> &clen, const std::vector<uint64_t> &ooff,
+                           const std::vector<uint32_t> &olen, uint8_t *d_out, cudaStream_t stream, float *ms);
+}
+
 namespace {
 
 struct FileText {
@@ -728,18 +737,15 @@ int inflate_all(const std::vector<uint8_t> &raw, std::vector<uint8_t> &out) {
     return HB_OK;
 }
 
-int read_vcf(const char *path, FileText &ft) {
-    std::vector<uint8_t> raw;
-    TRY(read_all(path, raw));
-    TRY(inflate_all(raw, ft.data));
-    raw.clear(); raw.shrink_to_fit();
-    if (!ft.data.empty() && ft.data.back() != '\n') ft.data.push_back('\n');
-    // header
-    uint64_t p = 0, n = ft.data.size();
-    const uint8_t *d = ft.data.data();
-    bool have = false;
+// header lines of decompressed VCF text: sample names, INFO/END type, where the records start.
+// complete = the #CHROM line (with its newline, or the end of the text when `whole`) lies inside [d, d + n)
+bool parse_header(const uint8_t *d, uint64_t n, bool whole, FileText &ft) {
+    ft.samples.clear();
+    ft.end_is_int = 0;
+    uint64_t p = 0;
     while (p < n && d[p] == '#') {
         const uint8_t *e = (const uint8_t *)memchr(d + p, '\n', n - p);
+        if (!e && !whole) return false;                    // the line continues in text not inflated yet
         uint64_t le = e ? (uint64_t)(e - d) : n;
         if (p + 1 < n && d[p + 1] == '#') {
             std::string line((const char *)d + p, (const char *)d + le);
@@ -756,13 +762,96 @@ int read_vcf(const char *path, FileText &ft) {
                 if (!t) break;
                 q = te + 1;
             }
-            have = true;
+            ft.body = e ? le + 1 : n;
+            return true;
         }
         p = e ? le + 1 : n;
-        if (have) break;
     }
-    if (!have) return fail(HB_ERR_HEADER, "no #CHROM header line");
+    if (p >= n && !whole) return false;
     ft.body = p;
+    return false;                                          // text without a #CHROM line
+}
+
+int read_vcf(const std::vector<uint8_t> &raw, FileText &ft) {
+    TRY(inflate_all(raw, ft.data));
+    if (!ft.data.empty() && ft.data.back() != '\n') ft.data.push_back('\n');
+    if (!parse_header(ft.data.data(), ft.data.size(), true, ft)) return fail(HB_ERR_HEADER, "no #CHROM header line");
+    return HB_OK;
+}
+
+// One .vcf / .vcf.gz -> device-resident parse.  BGZF files (what bgzip writes, what the reference's tabix path
+// reads) travel over PCIe COMPRESSED and are inflated on the GPU (hb_inflate.cu) straight into the text buffer;
+// only the header members are also inflated on the host, to learn the sample names.  Plain gzip (one DEFLATE
+// stream: nothing to parallelise) and plain text go through zlib / as they are.  HB_CPU_INFLATE=1 forces zlib.
+int parse_file_common(const char *path, const char *region, bool want_gt, int device, hb_parse **out,
+                      std::vector<std::string> &samples) {
+    std::vector<uint8_t> raw;
+    TRY(read_all(path, raw));
+    std::vector<uint64_t> coff, ooff;
+    std::vector<uint32_t> clen, olen;
+    uint64_t total = 0;
+    const char *force = getenv("HB_CPU_INFLATE");
+    const bool gpu_inflate = !(force && *force == '1') && raw.size() >= 28 && raw[0] == 0x1f && raw[1] == 0x8b &&
+                             bgzf_index(raw.data(), raw.size(), coff, clen, ooff, olen, total) && total > 0;
+    hb_parse_opts o;
+    memset(&o, 0, sizeof o);
+    o.region = region;
+    o.want_gt = want_gt ? 1 : 0;
+    o.device = device;
+    if (!gpu_inflate) {
+        FileText ft;
+        TRY(read_vcf(raw, ft));
+        raw.clear(); raw.shrink_to_fit();
+        samples = ft.samples;
+        o.n_samples = (uint32_t)ft.samples.size();
+        o.end_is_int = ft.end_is_int;
+        return hb_parse_host_text(ft.data.data() + ft.body, ft.data.size() - ft.body, &o, out);
+    }
+    // ---- header: inflate leading members on the host until the #CHROM line is complete
+    FileText ft;
+    {
+        std::vector<uint8_t> head;
+        bool have = false;
+        for (size_t i = 0; i < coff.size() && !have; ++i) {
+            const size_t at = head.size();
+            head.resize(at + olen[i]);
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) return fail(HB_ERR_IO, "inflateInit2 failed");
+            zs.next_in = const_cast<Bytef *>(raw.data() + coff[i]);
+            zs.avail_in = clen[i];
+            zs.next_out = head.data() + at;
+            zs.avail_out = olen[i];
+            const int zr = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (zr != Z_STREAM_END || zs.avail_out != 0) return fail(HB_ERR_IO, "BGZF inflate failed (header)");
+            have = parse_header(head.data(), head.size(), i + 1 == coff.size(), ft);
+        }
+        if (!have) return fail(HB_ERR_HEADER, "no #CHROM header line");
+    }
+    samples = ft.samples;
+    o.n_samples = (uint32_t)ft.samples.size();
+    o.end_is_int = ft.end_is_int;
+    hb_parse *p = nullptr;
+    TRY(new_parse(&o, &p));
+    const uint64_t pad = (16 - ft.body % 16) % 16;         // the records must start on a 16-byte boundary
+    int rc = dev_alloc(&p->d_text_owned, pad + total + 1 + 256);
+    if (rc == HB_OK) rc = inflate_bgzf_to_device(raw.data(), raw.size(), coff, clen, ooff, olen, p->d_text_owned + pad, p->stream, &p->ms_inflate);
+    uint8_t last = 0;
+    cudaError_t e = cudaSuccess;
+    if (rc == HB_OK) e = cudaMemcpy(&last, p->d_text_owned + pad + total - 1, 1, cudaMemcpyDeviceToHost);
+    uint64_t end = pad + total;
+    if (rc == HB_OK && e == cudaSuccess && last != '\n') { e = cudaMemset(p->d_text_owned + end, '\n', 1); ++end; }
+    if (rc == HB_OK && e == cudaSuccess) e = cudaMemset(p->d_text_owned + end, 0, 256);
+    if (rc == HB_OK && e != cudaSuccess) rc = fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    if (rc == HB_OK) {
+        p->d_text = p->d_text_owned + pad + ft.body;
+        p->nbytes = end - pad - ft.body;
+        p->compressed_bytes = raw.size();
+        rc = run_parse(p);
+    }
+    if (rc != HB_OK) { hb_parse_free(p); return rc; }
+    *out = p;
     return HB_OK;
 }
 
@@ -794,18 +883,9 @@ int env_device() {
 }
 
 int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_gt) {
-    FileText ft;
-    TRY(read_vcf(path, ft));
-    ce.samples = ft.samples;
     ce.want_gt = want_gt;
-    hb_parse_opts o;
-    memset(&o, 0, sizeof o);
-    o.n_samples = (uint32_t)ft.samples.size();
-    o.region = region;
-    o.end_is_int = ft.end_is_int;
-    o.want_gt = want_gt ? 1 : 0;
-    o.device = env_device();
-    TRY(hb_parse_host_text(ft.data.data() + ft.body, ft.data.size() - ft.body, &o, &ce.parse));
+    TRY(parse_file_common(path, region, want_gt, env_device(), &ce.parse, ce.samples));
+    const uint32_t n_samples = (uint32_t)ce.samples.size();
     hb_parse *p = ce.parse;
     uint64_t n = p->h_st.n_records;
     ce.start.resize(n); ce.stop.resize(n); ce.ref.resize(n); ce.alt.resize(n); ce.chrom_off.resize(n);
@@ -818,7 +898,7 @@ int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_
         for (uint64_t r = b; r < e; ++r) ce.chrom_off[r] = off;
     }
     if (want_gt) {
-        ce.ploidy_err.resize(o.n_samples); ce.badgt_err.resize(o.n_samples);
+        ce.ploidy_err.resize(n_samples); ce.badgt_err.resize(n_samples);
         TRY(hb_parse_fetch_sample_errors(p, ce.ploidy_err.data(), ce.badgt_err.data()));
     }
     // the text is no longer needed once names are resolved: give the HBM back
@@ -937,17 +1017,62 @@ uint64_t hb_kernel_launches(void) { return g_launches.load(); }
 // ---------------------------------------------------------------------------------------------
 int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int device, hb_parse **out) {
     if (!in_vcf || !out) return fail(HB_ERR_ARG, "null argument");
-    FileText ft;
-    TRY(read_vcf(in_vcf, ft));
-    hb_parse_opts o;
-    memset(&o, 0, sizeof o);
-    o.n_samples = (uint32_t)ft.samples.size();
-    o.region = region;
-    o.end_is_int = ft.end_is_int;
-    o.want_gt = want_gt;
-    o.device = device;
-    TRY(hb_parse_host_text(ft.data.data() + ft.body, ft.data.size() - ft.body, &o, out));
-    (*out)->samples = ft.samples;
+    std::vector<std::string> samples;
+    TRY(parse_file_common(in_vcf, region, want_gt != 0, device, out, samples));
+    (*out)->samples = samples;
+    return HB_OK;
+}
+
+// Host utility (tests, bench): text -> BGZF with stock zlib on all host threads -- what `bgzip -@` does.
+// Not part of the product path (the path READS BGZF); it exists so that BGZF inputs of bench size can be made
+// here without htslib.  out == NULL: *len is set to a sufficient capacity.
+int hb_bgzf_compress_host(const uint8_t *text, uint64_t nbytes, int level, uint8_t *out, uint64_t cap, uint64_t *len) {
+    if (!len || (nbytes && !text)) return fail(HB_ERR_ARG, "null argument");
+    const uint64_t blk = 0xff00;
+    const uint64_t n_blocks = (nbytes + blk - 1) / blk;
+    const uint64_t worst = 18 + 8 + blk + blk / 1000 + 64;
+    if (!out) { *len = n_blocks * worst + 28; return HB_OK; }
+    if (cap < n_blocks * worst + 28) return fail(HB_ERR_ARG, "buffer too small");
+    std::vector<uint32_t> sizes(n_blocks);
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t i = next.fetch_add(1);
+            if (i >= n_blocks) break;
+            const uint8_t *src = text + i * blk;
+            const uint32_t n = (uint32_t)std::min<uint64_t>(blk, nbytes - i * blk);
+            uint8_t *dst = out + i * worst;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; break; }
+            zs.next_in = const_cast<Bytef *>(src); zs.avail_in = n;
+            zs.next_out = dst + 18; zs.avail_out = (uInt)(worst - 26);
+            const int zr = deflate(&zs, Z_FINISH);
+            const uint32_t clen = (uint32_t)zs.total_out;
+            deflateEnd(&zs);
+            if (zr != Z_STREAM_END || clen + 26 > 65536) { bad = 1; break; }
+            const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+            memcpy(dst, hdr, 16);
+            const uint32_t bs = clen + 25;
+            dst[16] = (uint8_t)bs; dst[17] = (uint8_t)(bs >> 8);
+            const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, n);
+            uint8_t *tr = dst + 18 + clen;
+            for (int k = 0; k < 4; ++k) { tr[k] = (uint8_t)(crc >> (8 * k)); tr[4 + k] = (uint8_t)(n >> (8 * k)); }
+            sizes[i] = clen + 26;
+        }
+    };
+    unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (bad) return fail(HB_ERR_IO, "deflate failed");
+    uint64_t o = 0;
+    for (uint64_t i = 0; i < n_blocks; ++i) { memmove(out + o, out + i * worst, sizes[i]); o += sizes[i]; }
+    const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    memcpy(out + o, eof, 28);
+    *len = o + 28;
     return HB_OK;
 }
 

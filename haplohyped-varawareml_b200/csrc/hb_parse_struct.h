@@ -55,7 +55,8 @@ struct hb_parse {
     uint64_t *d_run_rows = nullptr;
     static constexpr uint64_t kMaxRuns = 4096;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float ms_tok = 0, ms_sites = 0, ms_decode = 0;
+    float ms_tok = 0, ms_sites = 0, ms_decode = 0, ms_inflate = 0;
+    uint64_t compressed_bytes = 0;      // BGZF bytes shipped over PCIe when the file was inflated on the GPU
     // chrom runs (host)
     std::vector<uint64_t> run_rows;
     std::vector<std::string> run_names;

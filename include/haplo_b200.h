@@ -97,6 +97,8 @@ typedef struct hb_parse_info {
     int tokenizer_used;             /* 1 newline-only, 2 newline + tab checkpoints, 3 head walker */
     float ms_tokenize, ms_sites, ms_decode;   /* CUDA-event kernel times of the last parse */
     int walker_fallbacks;           /* times the head walker could not prove itself exact and the tokenizer re-ran */
+    float ms_inflate;               /* GPU BGZF inflate kernel time (file-level parses of BGZF input), else 0 */
+    uint64_t compressed_bytes;      /* BGZF bytes that crossed PCIe instead of the text, else 0 */
 } hb_parse_info;
 
 /* text on the HOST (pageable or pinned): H2D copy + kernels.  body must end with '\n'. */
@@ -139,6 +141,10 @@ void hb_parse_free(hb_parse *p);
  * (hb_load_vcf, hb_parse_file) use the same kernel but leave the text in HBM.  kernel_ms may be NULL. */
 int hb_bgzf_inflate(const uint8_t *bgzf, uint64_t nbytes, uint8_t *out, uint64_t cap, uint64_t *out_len, int device,
                     float *kernel_ms);
+
+/* Host utility for tests and the bench (NOT on the product path, which only reads BGZF): text -> BGZF with stock
+ * zlib on all host threads, as `bgzip -@` would.  out == NULL: *len = a sufficient capacity. */
+int hb_bgzf_compress_host(const uint8_t *text, uint64_t nbytes, int level, uint8_t *out, uint64_t cap, uint64_t *len);
 
 /* ------------------------------------------------------------------------------------------
  * C. Storage: Blosc2 byte-shuffle (typesize 35) + LZ4 block encoder + Blosc2 chunk / cframe
