@@ -330,13 +330,22 @@ def main():
             alg_df = 2.0 * Vk * S + c_out           # allele planes read once, every frame written once
             stages["donor_frames"] = {"ms": med(k4["donor_frames"]), "bytes": alg_df,
                                       "gbs": alg_df / (med(k4["donor_frames"]) / 1e3) / 1e9,
-                                      "note": "fused: allele-plane LZ4 + look-back offsets + frame assembly"}
+                                      "note": "fused: allele-plane LZ4 + frame assembly into closed-form slots"}
             store = {"c_out_bytes": int(c_out), "frames": int(fi.n_chunks) * S, "chunk_records": int(fi.chunk_records),
                      "compression_ratio": float(fi.raw_bytes) / max(1.0, c_out), "raw_bytes_logical": int(fi.raw_bytes)}
         # the dominant kernel = the stage with the largest measured time that has algorithmic bytes
         dom = max((k for k in stages if "bytes" in stages[k]), key=lambda k: stages[k]["ms"])
+        traffic, traffic_note = None, None
+        try:        # DRAM bytes per launch: the ratio ncu measured for this kernel (profiles/) times this launch's algorithmic bytes
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))[dom]
+            traffic = tr["ratio"] * stages[dom]["bytes"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum = %.3f x algorithmic bytes in the ncu --set full capture "
+                            "(200000 variants x 2504 samples, profiles/r01b_ncu_top_kernels.txt), scaled to this launch" % tr["ratio"])
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src, "nominal_peak": NOMINAL_HBM_GBS,
+                "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peak_src, "nominal_peak": NOMINAL_HBM_GBS,
                 "algorithmic_bytes_per_launch": stages[dom]["bytes"], "ms_per_launch": stages[dom]["ms"],
                 "path": {"algorithmic_bytes": alg_all, "gbs": alg_all / step_s / 1e9, "frac": alg_all / step_s / 1e9 / peak,
                          "definition": ("T + 2*(2*V'*S + 33*V') + C_out per step (SURVEY.md 8d 'fused total'), whole step incl. host syncs"
