@@ -223,6 +223,7 @@ def main():
     p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr22", device=local, stream=stream)
     if not args.parse_only:
         frames[0] = p.compress(0)
+        p.attach(frames[0])                         # site templates are made while the GT decoder runs
     for _ in range(args.warmup - 1):
         step(p)
     info = p.info
@@ -371,6 +372,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
     if frames[0] is not None:
+        p.attach(None)
         frames[0].close()
     p.close()
     if world > 1:

@@ -72,7 +72,7 @@ EXPORTS = [
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
-    "hb_compress_records", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
+    "hb_compress_records", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_decode_frames",
     "hb_encode_haplotypes",
@@ -116,6 +116,7 @@ def lib():
             L.hb_compress_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
             L.hb_frames_get_info.argtypes = [C.c_void_p, C.POINTER(FramesInfo)]
             L.hb_frames_rerun.argtypes = [C.c_void_p, C.c_void_p]
+            L.hb_parse_attach_frames.argtypes = [C.c_void_p, C.c_void_p]
             L.hb_frames_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.hb_frames_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
             L.hb_frames_fetch_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
@@ -254,6 +255,10 @@ class Parse:
             e = rows[k + 1] if k + 1 < len(rows) else n
             out.extend([names[k]] * (e - r))
         return out
+
+    def attach(self, frames: "Frames | None"):
+        """Overlap the frames' site-template kernel with the GT decoder on every rerun (hb_parse_attach_frames)."""
+        check(lib().hb_parse_attach_frames(self._h, frames._h if frames is not None else None))
 
     def compress(self, chunk_records: int = 0) -> "Frames":
         h = C.c_void_p()

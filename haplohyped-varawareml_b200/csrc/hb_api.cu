@@ -293,6 +293,7 @@ static int run_parse(hb_parse *p) {
     if (p->use_walker) TRY(index_by_walker(p, L));
     else TRY(index_by_tokenizer(p, L));
     const uint64_t n_rec = p->h_st.n_records;
+    if (p->attached_frames && n_rec) frames_early_site_pass(p->attached_frames, p);
 
     // ---- GT decode
     if (p->want_gt && n_rec && p->n_samples) {

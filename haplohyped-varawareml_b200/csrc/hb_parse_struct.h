@@ -61,5 +61,11 @@ struct hb_parse {
     std::vector<uint64_t> run_rows;
     std::vector<std::string> run_names;
     std::vector<std::string> samples;   // sample names when the parse was made from a file
+    void *attached_frames = nullptr;    // hb_frames whose site templates are made while the GT decoder runs (hb_store.cu)
 };
 
+
+namespace hb {
+// hb_store.cu: start the site-template kernel of the attached frames on their side stream (called by run_parse)
+void frames_early_site_pass(void *frames, hb_parse *p);
+}

@@ -41,21 +41,25 @@ __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {     // unaligned 4-
     return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8u);
 }
 
-// Warp-cooperative LZ4 block encoder over src[0..n) with `hist` readable bytes before src.
-//   anchor0 <= 0: literals still pending from the previous part of the block (src[anchor0..0)).
-//   final: obey the end-of-block rules (last 5 bytes literal, last match starts <= n-12) and flush
-//          the trailing literals; otherwise stop after the last match and report the pending
-//          literal count through *pending.
-// table: 1 << hashlog uint16 entries (position + 1; 0 = empty), cleared here.  n < 65535.
-// Returns the number of bytes written to dst.  All lanes return the same value.
-__device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool final, uint8_t *dst,
-                        uint16_t *table, int hashlog, int *pending) {
+// Warp-cooperative LZ4 encoder of one SEGMENT src[0..n) of a block whose earlier bytes (`hist` of them) sit right
+// in front of src.  32 positions are examined per step; each lane tests three candidates for its position -- `far`
+// bytes back (0 = none), the last position with the same 4-byte hash (own segment only), one byte back -- the first
+// lane with a hit wins and the match is extended with ballots.  Only complete sequences are emitted and no match
+// crosses the end of the segment.  The first sequence assumes that its literal run starts at src[0]: its header
+// (token + literal-length bytes) occupies dst[0..*first_hdr) and announces *first_lit literals, so that a caller
+// which carries literals in from the previous segment can re-write just that header.  *pending = trailing bytes of
+// the segment not covered by a sequence.  table: 1 << hashlog uint16 entries (position + 1), cleared here;
+// n < 65535.  Returns the bytes written to dst; all lanes return the same values.
+// The site planes pass far = 4*cr: the stop column is the start column + 1, so bytes 1..3 of `stop` (planes 10-12)
+// repeat bytes 1..3 of `start` (planes 6-8) almost everywhere.
+__device__ int warp_lz4_segment(const uint8_t *src, int n, int hist, uint8_t *dst, uint16_t *table, int hashlog,
+                                int far, int *first_lit, int *first_hdr, int *pending) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < (1 << hashlog); i += 32) table[i] = 0;
     __syncwarp();
-    int op = 0, anchor = anchor0, pos = 0;
-    const int mflimit = final ? n - 12 : n - 4;      // last position a match may start at
-    const int mend = final ? n - 5 : n;              // matches end at or before this
+    int op = 0, anchor = 0, pos = 0;
+    const int mflimit = n - 4;                       // last position a match may start at
+    *first_lit = 0; *first_hdr = 0;
     while (pos <= mflimit) {
         const int p = pos + lane;
         const bool valid = p <= mflimit;
@@ -65,8 +69,9 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
             v = rd32(src + p);
             h = (v * 2654435761u) >> (32 - hashlog);
             const int c = (int)table[h] - 1;
-            if (c >= 0 && c < p && rd32(src + c) == v) cand = c;   // c == p: left by a re-examined window
-            else if (p - 1 >= -hist && rd32(src + p - 1) == v) cand = p - 1;     // run of one byte
+            if (far && p + hist >= far && rd32(src + p - far) == v) cand = p - far;
+            else if (c >= 0 && c < p && rd32(src + c) == v) cand = c;   // c == p: left by a re-examined window
+            else if (p + hist >= 1 && rd32(src + p - 1) == v) cand = p - 1;      // run of one byte
         }
         __syncwarp();
         if (valid) table[h] = (uint16_t)(p + 1);
@@ -79,19 +84,15 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
         int ml = 4;
         for (;;) {
             const int i = ml + lane;
-            const bool same = (m + i < mend) && src[m + i] == src[c + i];
+            const bool same = (m + i < n) && src[m + i] == src[c + i];
             const unsigned bal = __ballot_sync(0xffffffffu, same);
             if (bal == 0xffffffffu) { ml += 32; continue; }
             ml += __ffs(~bal) - 1;
             break;
         }
-        if (m + ml > mend) ml = mend - m;             // (cannot happen: guarded above)
-        if (ml < 4) { pos = m + 1; continue; }        // match would cross the end-of-block limit
         const int litlen = m - anchor;
         int o = op;
-        if (lane == 0) {
-            dst[o] = (uint8_t)((min(litlen, 15) << 4) | min(ml - 4, 15));
-        }
+        if (lane == 0) dst[o] = (uint8_t)((min(litlen, 15) << 4) | min(ml - 4, 15));
         ++o;
         if (litlen >= 15) {
             int rem = litlen - 15;
@@ -99,6 +100,7 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
             if (lane == 0) dst[o] = (uint8_t)rem;
             ++o;
         }
+        if (op == 0) { *first_lit = litlen; *first_hdr = o; }
         for (int i = lane; i < litlen; i += 32) dst[o + i] = src[anchor + i];
         o += litlen;
         const int off = m - c;
@@ -113,23 +115,7 @@ __device__ int warp_lz4(const uint8_t *src, int n, int hist, int anchor0, bool f
         op = o;
         anchor = pos = m + ml;
     }
-    if (final) {
-        const int litlen = n - anchor;
-        int o = op;
-        if (lane == 0) dst[o] = (uint8_t)(min(litlen, 15) << 4);
-        ++o;
-        if (litlen >= 15) {
-            int rem = litlen - 15;
-            while (rem >= 255) { if (lane == 0) dst[o] = 255; ++o; rem -= 255; }
-            if (lane == 0) dst[o] = (uint8_t)rem;
-            ++o;
-        }
-        for (int i = lane; i < litlen; i += 32) dst[o + i] = src[anchor + i];
-        op = o + litlen;
-        if (pending) *pending = 0;
-    } else if (pending) {
-        *pending = n - anchor;
-    }
+    *pending = n - anchor;
     __syncwarp();
     return op;
 }
@@ -242,14 +228,36 @@ struct SiteArgs4 {
     uint32_t *tmpl_len;          // [n_chunks] = TMPL_HDR + LZ4 bytes of the site planes
 };
 
-__global__ void __launch_bounds__(256) site_template_kernel(const SiteArgs4 a) {
+constexpr int kSiteSegs = 8;                     // = warps of the CTA
+constexpr int kSiteHashLog = 10;
+__host__ __device__ inline uint32_t site_seg_cap(uint32_t len) { return (len + len / 255 + 24 + 15) & ~15u; }
+// Segment s of the encoded part [0, 24*cr+1) of the site planes covers [site_seg_begin(s), site_seg_begin(s+1)).
+// The cuts follow where the work is: the REF plane (13) and the ALT plane (23) are random A/C/G/T -- hundreds of
+// short matches each -- and get three warps each; everything else (constant, zero, or literal-only planes) is cheap.
+__host__ __device__ inline uint32_t site_seg_begin(int s, uint32_t cr) {
+    switch (s) {
+        case 0: return 0;
+        case 1: return 9 * cr;
+        case 2: return 13 * cr;
+        case 3: return 13 * cr + cr / 3;
+        case 4: return 13 * cr + 2 * cr / 3;
+        case 5: return 23 * cr;
+        case 6: return 23 * cr + cr / 3;
+        case 7: return 23 * cr + 2 * cr / 3;
+        default: return 24 * cr + 1;
+    }
+}
+
+__global__ void __launch_bounds__(kSiteSegs * 32) site_template_kernel(const SiteArgs4 a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_len;
+    __shared__ int s_len[kSiteSegs], s_pend[kSiteSegs], s_flit[kSiteSegs], s_fhdr[kSiteSegs];
+    __shared__ int s_dst[kSiteSegs], s_carry[kSiteSegs], s_final[2];
+    __shared__ uint8_t s_head[TMPL_HDR + 7];
     const uint32_t cr = a.cr;
     const uint32_t n = 33u * cr;
-    uint8_t *planes = smem + 16;                            // 16 bytes of (unused) history in front
-    uint8_t *outb = planes + ((n + 19) & ~15u);             // the template: header, then LZ4 bytes
-    uint16_t *table = reinterpret_cast<uint16_t *>(outb + a.tmpl_cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *planes = smem + 16;                            // 16 zero bytes of history in front
+    uint8_t *outs = planes + ((n + 19) & ~15u);             // per-segment output regions
     const uint64_t c = blockIdx.x;
     const uint64_t r0 = c * cr;
     for (uint32_t i = threadIdx.x; i < cr; i += blockDim.x) {
@@ -271,32 +279,71 @@ __global__ void __launch_bounds__(256) site_template_kernel(const SiteArgs4 a) {
         for (int k = 0; k < 9; ++k) { planes[(14 + k) * cr + i] = 0; planes[(24 + k) * cr + i] = 0; }
     }
     if (threadIdx.x < 16) smem[threadIdx.x] = 0;
-    for (uint32_t i = threadIdx.x; i < a.tmpl_cap / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(outb)[i] = 0;
+    if (threadIdx.x == 0) write_frame_head(s_head, 35u * cr);
     __syncthreads();
-    if (threadIdx.x == 0) write_frame_head(outb, 35u * cr);
+    uint8_t *g = a.tmpl + c * a.tmpl_cap;
     // Chunks of fewer than 6 records cannot honour LZ4's end-of-block rules (last match >= 12 bytes
     // before the end) once the 2*cr allele bytes follow: such blocks are stored raw (csize == size).
-    const bool raw = cr < 6;
-    uint8_t *lz = outb + TMPL_HDR;
-    if (raw) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) lz[i] = planes[i];
-        if (threadIdx.x == 0) s_len = n;
-    } else if (threadIdx.x < 32) {
-        // Planes 24..32 (ALT bytes 1..9) are all zero: the head is encoded up to the first of those
-        // zeros, then ONE offset-1 match covers the other 9*cr-1 -- so the site part always ends on a
-        // sequence boundary and every donor continues the block with nothing pending and zeros behind it.
-        const int n1 = 24 * (int)cr + 1;
-        int pending = 0;
-        int len = warp_lz4(planes, n1, 0, 0, false, lz, table, 12, &pending);
-        len = warp_emit_seq(lz, len, planes + n1 - pending, pending, 1, (int)n - n1);
-        if (threadIdx.x == 0) s_len = (uint32_t)len;
+    if (cr < 6) {
+        for (uint32_t i = threadIdx.x; i < TMPL_HDR; i += blockDim.x) g[i] = s_head[i];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) g[TMPL_HDR + i] = planes[i];
+        const uint32_t tl = TMPL_HDR + n;
+        for (uint32_t i = tl + threadIdx.x; i < ((tl + 15) & ~15u); i += blockDim.x) g[i] = 0;
+        if (threadIdx.x == 0) a.tmpl_len[c] = tl;
+        return;
+    }
+    // Planes 24..32 (ALT bytes 1..9) are all zero: the head is encoded up to the first of those zeros, then ONE
+    // offset-1 match covers the other 9*cr-1 -- so the site part always ends on a sequence boundary and every donor
+    // continues the block with nothing pending and zeros behind it.  The head is cut into kSiteSegs segments, one
+    // per warp, encoded independently (own hash table; the fixed-distance candidates reach back across segments).
+    const int n1 = 24 * (int)cr + 1;
+    const int sb = (int)site_seg_begin(warp, cr), se = (int)site_seg_begin(warp + 1, cr);
+    uint32_t out_off = 0;
+    for (int w = 0; w < warp; ++w) out_off += site_seg_cap(site_seg_begin(w + 1, cr) - site_seg_begin(w, cr));
+    uint8_t *my_out = outs + out_off;
+    uint16_t *table = reinterpret_cast<uint16_t *>(outs + ((site_seg_cap((uint32_t)n1) + kSiteSegs * 48 + 15) & ~15u)) + ((size_t)warp << kSiteHashLog);
+    {
+        int flit, fhdr, pend;
+        const int len = warp_lz4_segment(planes + sb, se - sb, sb, my_out, table, kSiteHashLog, 4 * (int)cr, &flit, &fhdr, &pend);
+        if (lane == 0) { s_len[warp] = len; s_pend[warp] = pend; s_flit[warp] = flit; s_fhdr[warp] = fhdr; }
     }
     __syncthreads();
-    const uint32_t tl = TMPL_HDR + s_len;
+    if (threadIdx.x == 0) {                       // stitch: literals left over by a segment open the next one's first sequence
+        int carry = 0, off = 0;
+        for (int w = 0; w < kSiteSegs; ++w) {
+            s_dst[w] = off; s_carry[w] = carry;
+            if (s_len[w] == 0) { carry += s_pend[w]; continue; }
+            const int lit = s_flit[w] + carry;
+            off += 1 + (lit >= 15 ? 1 + (lit - 15) / 255 : 0) + carry + (s_len[w] - s_fhdr[w]);
+            carry = s_pend[w];
+        }
+        s_final[0] = off; s_final[1] = carry;
+    }
+    __syncthreads();
+    uint8_t *lz = g + TMPL_HDR;
+    if (s_len[warp] > 0) {
+        const int carry = s_carry[warp], lit = s_flit[warp] + carry;
+        int o = s_dst[warp];
+        if (lane == 0) lz[o] = (uint8_t)((min(lit, 15) << 4) | (my_out[0] & 15));
+        ++o;
+        if (lit >= 15) {
+            int rem = lit - 15;
+            while (rem >= 255) { if (lane == 0) lz[o] = 255; ++o; rem -= 255; }
+            if (lane == 0) lz[o] = (uint8_t)rem;
+            ++o;
+        }
+        for (int i = lane; i < carry; i += 32) lz[o + i] = planes[sb - carry + i];
+        o += carry;
+        const int rest = s_len[warp] - s_fhdr[warp];
+        for (int i = lane; i < rest; i += 32) lz[o + i] = my_out[s_fhdr[warp] + i];
+    }
+    int o = s_final[0];
+    if (warp == 0) o = warp_emit_seq(lz, o, planes + n1 - s_final[1], s_final[1], 1, (int)n - n1);
+    else o = o + 1 + (s_final[1] >= 15 ? 1 + (s_final[1] - 15) / 255 : 0) + s_final[1] + 2 + ((int)n - n1 >= 19 ? 1 + ((int)n - n1 - 19) / 255 : 0);
+    const uint32_t tl = TMPL_HDR + (uint32_t)o;
+    for (uint32_t i = threadIdx.x; i < TMPL_HDR; i += blockDim.x) g[i] = s_head[i];
+    for (uint32_t i = tl + threadIdx.x; i < ((tl + 15) & ~15u); i += blockDim.x) g[i] = 0;
     if (threadIdx.x == 0) a.tmpl_len[c] = tl;
-    uint4 *dstp = reinterpret_cast<uint4 *>(a.tmpl + c * a.tmpl_cap);
-    const uint4 *srcp = reinterpret_cast<const uint4 *>(outb);
-    for (uint32_t i = threadIdx.x; i < (tl + 15) / 16; i += blockDim.x) dstp[i] = srcp[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -671,6 +718,11 @@ struct hb_frames {
     std::vector<uint8_t> h_row;                  // scratch for hb_frames_fetch_sample
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float ms_site = 0, ms_frames = 0;
+    // the site templates only need the site columns, not the genotype planes: when the frames are attached to
+    // their parse (hb_parse_attach_frames) the template kernel runs on `side`, concurrently with the GT decoder
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_sites = nullptr, ev_tmpl = nullptr, ev_side0 = nullptr;
+    bool early_site = false;                     // the template pass of the current parse run is already in flight
 };
 
 template <int NW>
@@ -682,6 +734,38 @@ static cudaError_t attr_donor_frames(size_t smem) {
     return cudaFuncSetAttribute(donor_frames_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// templates of all chunks.  early: launched from inside run_parse on the side stream, right after the site columns
+// were written on the parse's stream; otherwise on the parse's stream itself.
+static int frames_site_pass(hb_frames *f, hb_parse *p, bool early) {
+    cudaError_t e;
+#define CUF(x) do { e = (x); if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e) + " at " #x); } while (0)
+    SiteArgs4 sa;
+    sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
+    sa.n_records = f->n_records; sa.cr = (uint32_t)f->cr; sa.tmpl = f->d_tmpl; sa.tmpl_cap = f->tmpl_cap; sa.tmpl_len = f->d_tmpl_len;
+    cudaStream_t st = early ? f->side : f->stream;
+    if (early) {
+        CUF(cudaEventRecord(f->ev_sites, p->stream));
+        CUF(cudaStreamWaitEvent(f->side, f->ev_sites, 0));
+    }
+    CUF(cudaEventRecord(early ? f->ev_side0 : f->ev[0], st));
+    site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, st>>>(sa);
+    count_launch();
+    CUF(cudaEventRecord(early ? f->ev_tmpl : f->ev[1], st));
+    f->early_site = early;
+#undef CUF
+    return HB_OK;
+}
+
+namespace hb {
+// called by run_parse (hb_api.cu) once the site columns of this run are on their way
+void frames_early_site_pass(void *frames, hb_parse *p) {
+    hb_frames *f = static_cast<hb_frames *>(frames);
+    if (!f || !f->n_chunks || !f->n_samples || !f->side) return;
+    if (p->h_st.n_records != f->n_records || p->device != f->device) return;     // shape changed: hb_frames_rerun will say so
+    frames_site_pass(f, p, true);
+}
+}  // namespace hb
+
 static int frames_run(hb_frames *f, hb_parse *p) {
     cudaError_t e;
 #define CUF(x) do { e = (x); if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e) + " at " #x); } while (0)
@@ -690,14 +774,16 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     const uint32_t cr = (uint32_t)f->cr;
     const uint64_t n_frames = f->n_chunks * f->n_samples;
     f->layout_valid = false;
-    SiteArgs4 sa;
-    sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
-    sa.n_records = n; sa.cr = cr; sa.tmpl = f->d_tmpl; sa.tmpl_cap = f->tmpl_cap; sa.tmpl_len = f->d_tmpl_len;
     CUF(cudaMemsetAsync(f->d_totals, 0, 8, f->stream));
-    CUF(cudaEventRecord(f->ev[0], f->stream));
-    site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, f->stream>>>(sa);
-    count_launch();
-    CUF(cudaEventRecord(f->ev[1], f->stream));
+    const bool was_early = f->early_site;
+    if (was_early) {
+        CUF(cudaStreamWaitEvent(f->stream, f->ev_tmpl, 0));       // the templates were made while the decoder ran
+        CUF(cudaEventRecord(f->ev[1], f->stream));
+    } else {
+        int rc = frames_site_pass(f, p, false);
+        if (rc != HB_OK) return rc;
+    }
+    f->early_site = false;
     // the frame buffer is sized from the longest template: frame <= template + worst-case allele tail
     CUF(cudaMemcpyAsync(f->h_tmpl_len.data(), f->d_tmpl_len, f->n_chunks * 4, cudaMemcpyDeviceToHost, f->stream));
     CUF(cudaStreamSynchronize(f->stream));
@@ -740,7 +826,8 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     CUF(cudaGetLastError());
     f->padded_bytes = need;
     f->total_bytes = tot;
-    cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
+    if (was_early) cudaEventElapsedTime(&f->ms_site, f->ev_side0, f->ev_tmpl);
+    else cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
     cudaEventElapsedTime(&f->ms_frames, f->ev[1], f->ev[2]);
 #undef CUF
     return HB_OK;
@@ -766,10 +853,15 @@ uint64_t hb_guess_chunk_records(uint64_t n_records) { return guess_chunk_records
 
 void hb_frames_free(hb_frames *f) {
     if (!f) return;
+    if (f->side) cudaStreamSynchronize(f->side);
     cudaSetDevice(f->device);
     cudaFree(f->d_tmpl); cudaFree(f->d_frames); cudaFree(f->d_tmpl_len); cudaFree(f->d_size);
     cudaFree(f->d_slot_off); cudaFree(f->d_totals);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
+    if (f->ev_sites) cudaEventDestroy(f->ev_sites);
+    if (f->ev_tmpl) cudaEventDestroy(f->ev_tmpl);
+    if (f->ev_side0) cudaEventDestroy(f->ev_side0);
+    if (f->side) cudaStreamDestroy(f->side);
     delete f;
 }
 
@@ -791,7 +883,8 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     const uint32_t n_site = 33u * cr, n_gt = 2u * cr;
     auto bound = [](uint32_t x) { return x + x / 255 + 64; };
     f->tmpl_cap = (TMPL_HDR + bound(n_site) + 15) & ~15u;
-    f->smem_site = 16 + ((n_site + 19) & ~15u) + f->tmpl_cap + (2u << 12);
+    f->smem_site = 16 + ((n_site + 19) & ~15u) + ((site_seg_cap(24 * cr + 1) + kSiteSegs * 48 + 15) & ~15u) +
+                   ((size_t)kSiteSegs << kSiteHashLog) * 2;
     if (f->smem_site > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
     const uint32_t seg = (cr + 15) / 16;
     f->nw = (int)((seg + 31) / 32);
@@ -815,6 +908,13 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     ck(cudaMalloc(&f->d_slot_off, (f->n_chunks + 1) * 8));
     ck(cudaMalloc(&f->d_totals, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
+    {   // highest priority: its few long CTAs must get SM slots while the decoder's many short ones stream through
+        int lo = 0, hi = 0;
+        ck(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ck(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, hi));
+    }
+    ck(cudaEventCreateWithFlags(&f->ev_sites, cudaEventDisableTiming));
+    ck(cudaEventCreate(&f->ev_tmpl)); ck(cudaEventCreate(&f->ev_side0));
     // the opt-in shared-memory ceiling is a per-function, process-wide attribute: always raise it to the device
     // maximum, so that concurrent callers (the converter parses two files at once) cannot shrink each other's limit
     int smem_max = 0;
@@ -827,6 +927,12 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     int rc = frames_run(f, p);
     if (rc != HB_OK) { hb_frames_free(f); return rc; }
     *out = f;
+    return HB_OK;
+}
+
+int hb_parse_attach_frames(hb_parse *p, hb_frames *f) {
+    if (!p) return api_fail(HB_ERR_ARG, "null handle");
+    p->attached_frames = f;
     return HB_OK;
 }
 

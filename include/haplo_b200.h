@@ -170,6 +170,11 @@ typedef struct hb_frames_info {
  * [sample][chunk] with every frame starting on a 16-byte boundary: a sample's dataset is one contiguous
  * byte range, and the whole buffer can be written to the HDF5 file with one write. */
 int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out);
+/* Attach frames to the parse they were made from (NULL detaches): from then on every hb_parse_rerun of p also
+ * starts the site-template kernel of f, on a side stream, as soon as the site columns exist -- it overlaps the GT
+ * decoder instead of following it.  hb_frames_rerun then only runs what needs the genotype planes.  The frames must
+ * outlive the attachment. */
+int hb_parse_attach_frames(hb_parse *p, hb_frames *f);
 /* run the kernels again on the (re-parsed) handle the frames were made from: no allocation unless C_out grew */
 int hb_frames_rerun(hb_frames *f, hb_parse *p);
 int hb_frames_get_info(const hb_frames *f, hb_frames_info *info);
