@@ -61,11 +61,13 @@ def _expected(items, seqs, records, L, spec):
     return h1, h2
 
 
-@pytest.mark.parametrize("L,B,spec", [(1000, 8, None), (1001, 5, None), (4096, 3, "ACGT"), (333, 6, ["T", "G", "C", "A", "N"])])
+@pytest.mark.parametrize("L,B,spec", [(1000, 8, None), (1001, 5, None), (4096, 3, "ACGT"), (333, 6, ["T", "G", "C", "A", "N"]),
+                                      (131072, 3, None)])             # BASELINE configs[4]: seq_length 1000 and 131072
 def test_dataset_matches_oracle(mods, tmp_path, L, B, spec):
     capi, hd, cu = mods
     rng = np.random.default_rng(7)
-    donors, seqs, records, bed = _make_world(tmp_path, rng)
+    donors, seqs, records, bed = (_make_world(tmp_path, rng) if L < 100_000 else
+                                  _make_world(tmp_path, rng, n_donors=2, chrom_len=260_000, n_rec=2500, L=L))
     ds = hd.RandomHaplotypeDataset(str(bed), None, None, str(tmp_path / "samples.txt"), encode_spec=spec, seed=42,
                                    batch_size=B, seq_length=L,
                                    genotype_store=hd.GenotypeStore.from_records(records),

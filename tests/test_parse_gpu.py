@@ -296,3 +296,28 @@ def test_stream_host_uniform_text_and_errors(capi):
     lines[333] = "chr22\t433\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1\t0|0\n"
     r = capi.parse_stream_host("".join(lines).encode(), 3, capacity=400, region="", slab_bytes=2000)
     assert r["n"] == 400 and list(r["ploidy_err"]) == [0, 1, 0] and r["n_slabs"] > 3
+
+
+def test_biobank_width_200k_samples(capi):
+    """BASELINE configs[3] at reduced depth: 200,000 sample columns (a record is ~800 KB of text), multiallelic /
+    indel sites dropped by the SNP filter, unphased and missing calls -- parse, then kernel 4 on a few samples."""
+    S = 200_000
+    spec = capi.synth_spec(48, S, seed=17, mix=1)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    ora = oracle.parse_text(text, "*", "chr22")
+    assert 0 < ora["n"] < 48
+    for tok in (0, 1):                                   # head walker (auto) and plain newline tokenizer
+        p = capi.Parse.from_host(synth.body_of(text), S, region="chr22", tokenizer=tok)
+        assert p.info.n_records == ora["n"]
+        g0, g1 = p.matrix()
+        assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
+        start, stop, ref, alt = p.sites()
+        assert np.array_equal(start, ora["start"]) and np.array_equal(alt, ora["alt"])
+    fr = p.compress(0)
+    assert fr.info.n_samples == S and fr.info.n_chunks == 1
+    cr = int(fr.info.chunk_records)
+    for s in (0, 99_999, S - 1):
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
+        raw = rec.tobytes() + b"\0" * (cr * 35 - rec.nbytes)
+        (f,) = fr.sample(s)
+        assert oracle.cframe_decode(f, cr * 35).tobytes() == raw
