@@ -448,9 +448,10 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     uint32_t sidx = 0;
 
     if (active) {
-        const uint32_t s = (uint32_t)(wid / A.n_chunks);
+        uint32_t s;
+        if (n_frames <= 0xFFFFFFFFull) { s = (uint32_t)wid / (uint32_t)A.n_chunks; c = (uint32_t)wid - s * (uint32_t)A.n_chunks; }
+        else { s = (uint32_t)(wid / A.n_chunks); c = wid % A.n_chunks; }
         sidx = s;
-        c = wid % A.n_chunks;
         tl = A.tmpl_len[c];
         // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
         const uint64_t r0 = c * (uint64_t)cr;
@@ -630,9 +631,8 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     }
     if (active) {
         uint8_t *seq = outb + (tl & 15u);
-        for (int i = lane; i < FRAME_TAIL; i += 32) seq[dlen + i] = kFrameTail[i];
-        const uint32_t used = (tl & 15u) + (uint32_t)dlen + FRAME_TAIL;
-        for (uint32_t i = used + lane; i < ((used + 15) & ~15u); i += 32) outb[i] = 0;
+        const int padded = (int)((((tl & 15u) + (uint32_t)dlen + FRAME_TAIL + 15u) & ~15u) - (tl & 15u)) - dlen;   // tail + zero pad
+        for (int i = lane; i < padded; i += 32) seq[dlen + i] = i < FRAME_TAIL ? kFrameTail[i] : (uint8_t)0;
     }
     __syncwarp();
 
