@@ -58,6 +58,16 @@ class _MiniFile:
         self._w.create_dataset_chunked(path, dtype, n, chunk, frames, filter_id=FILTER_BLOSC2,
                                        cd_values=_cd_values(dtype.itemsize, chunk * dtype.itemsize), filter_name="blosc2")
 
+    def write_frames_bulk(self, paths, dtype, n: int, chunk: int, buf: np.ndarray, offsets: np.ndarray, sizes: np.ndarray):
+        """Many datasets at once: `buf` (all their stored chunks, e.g. hb_frames_fetch_all) goes into the file with ONE
+        write; dataset i = chunks sizes[i, k] bytes at buf offset offsets[i, k].  No per-chunk Python work."""
+        dtype = np.dtype(dtype)
+        base = self._w.write_blob(buf)
+        cd = _cd_values(dtype.itemsize, chunk * dtype.itemsize)
+        for i, path in enumerate(paths):
+            self._w.create_dataset_chunked_at(path, dtype, n, chunk, np.uint64(base) + offsets[i].astype(np.uint64), sizes[i],
+                                              filter_id=FILTER_BLOSC2, cd_values=cd, filter_name="blosc2")
+
     def write_array(self, path: str, data: np.ndarray):
         self._w.create_dataset_contiguous(path, np.asarray(data))
 
@@ -108,6 +118,11 @@ class _H5pyFile:
                                    compression_opts=BLOSC2_OPTS)
         for k, payload in enumerate(frames):
             d.id.write_direct_chunk((k * chunk,), bytes(payload))
+
+    def write_frames_bulk(self, paths, dtype, n: int, chunk: int, buf: np.ndarray, offsets: np.ndarray, sizes: np.ndarray):
+        for i, path in enumerate(paths):
+            self.write_chunked(path, dtype, n, chunk,
+                               [buf[int(o):int(o) + int(z)].tobytes() for o, z in zip(offsets[i], sizes[i])])
 
     def write_array(self, path: str, data: np.ndarray):
         self._f.create_dataset(path, data=np.asarray(data))

@@ -174,6 +174,74 @@ class H5Writer:
             msgs.append((0x000B, struct.pack("<BB6x", 1, 1) + filt))
         self._link(path, self._object_header(msgs))
 
+    def write_blob(self, data, align: int = 16) -> int:
+        """Append raw bytes (anything with the buffer protocol) and return their address.  Used to put ALL stored
+        chunks of many datasets into the file with one write; the datasets are then declared with
+        create_dataset_chunked_at."""
+        pad = -self.pos % align
+        if pad:
+            self.f.write(b"\0" * pad)
+            self.pos += pad
+        addr = self.pos
+        mv = memoryview(data).cast("B")
+        self.f.write(mv)
+        self.pos += mv.nbytes
+        return addr
+
+    def create_dataset_chunked_at(self, path: str, dtype: np.dtype, n: int, chunk: int, addrs: np.ndarray,
+                                  sizes: np.ndarray, filter_id: Optional[int] = None, cd_values: Sequence[int] = (),
+                                  filter_name: str = ""):
+        """Chunked dataset whose stored chunks already sit in the file: chunk k = sizes[k] bytes at addrs[k]."""
+        dtype = np.dtype(dtype)
+        addrs = np.asarray(addrs, np.uint64)
+        sizes = np.asarray(sizes, np.uint32)
+        btree = self._chunk_btree_np(sizes, addrs, chunk) if len(addrs) else UNDEF
+        layout = struct.pack("<BBBQII", 3, 2, 2, btree, chunk, dtype.itemsize)
+        msgs = self._common_messages(dtype, n) + [(0x0008, layout)]
+        if filter_id is not None:
+            name = _pad8(filter_name.encode() + b"\0") if filter_name else b""
+            cd = b"".join(struct.pack("<I", v & 0xFFFFFFFF) for v in cd_values)
+            if len(cd_values) % 2:
+                cd += b"\0\0\0\0"
+            filt = struct.pack("<HHHH", filter_id, len(name), 1, len(cd_values)) + name + cd
+            msgs.append((0x000B, struct.pack("<BB6x", 1, 1) + filt))
+        self._link(path, self._object_header(msgs))
+
+    _KEY_DT = np.dtype([("size", "<u4"), ("mask", "<u4"), ("off", "<u8"), ("zero", "<u8"), ("child", "<u8")])
+
+    def _chunk_btree_np(self, sizes: np.ndarray, addrs: np.ndarray, chunk: int) -> int:
+        """_chunk_btree with the node bodies assembled by numpy (a node body is an array of key+child records)."""
+        cap = 2 * CHUNK_K
+        node_size = 24 + (cap + 1) * 24 + cap * 8
+        n = len(sizes)
+        rec = np.zeros(n, self._KEY_DT)
+        rec["size"], rec["off"], rec["child"] = sizes, np.arange(n, dtype=np.uint64) * np.uint64(chunk), addrs
+        last_key = struct.pack("<IIQQ", 0, 0, n * chunk, 0)
+        level = 0
+        while True:
+            m = len(rec)
+            ngroups = (m + cap - 1) // cap
+            base = self._write(b"", align=8)
+            node_addr = base + np.arange(ngroups, dtype=np.uint64) * np.uint64(node_size)
+            raw = rec.tobytes()
+            out = bytearray()
+            for gi in range(ngroups):
+                lo, hi = gi * cap, min(m, (gi + 1) * cap)
+                body = raw[lo * 32:hi * 32]
+                final = raw[hi * 32:hi * 32 + 24] if hi < m else last_key
+                left = int(node_addr[gi - 1]) if gi > 0 else UNDEF
+                right = int(node_addr[gi + 1]) if gi + 1 < ngroups else UNDEF
+                node = b"TREE" + struct.pack("<BBHQQ", 1, level, hi - lo, left, right) + body + final
+                out += node + b"\0" * (node_size - len(node))
+            self._write(bytes(out))
+            if ngroups == 1:
+                return int(node_addr[0])
+            nxt = np.zeros(ngroups, self._KEY_DT)
+            first = rec[::cap]
+            nxt["size"], nxt["mask"], nxt["off"], nxt["child"] = first["size"], first["mask"], first["off"], node_addr
+            rec = nxt
+            level += 1
+
     def _chunk_btree(self, entries, chunk: int, end_offset: int) -> int:
         """v1 B-tree, node type 1.  entries: (stored size, element offset, address), offset-sorted."""
         def key(size, off):

@@ -140,7 +140,25 @@ class VCFtoHDF5Converter:
             logger.warning(f"{vcf_file} does not exist; chromosome {chromosome} skipped")
             self.stats["skipped_files"] += 1
             return
+        cp = self._chrom_parse(vcf_file, chromosome)
+        good = [d for d in self.donor_ids if d in cp.index and not cp.badgt_err[cp.index[d]] and not cp.ploidy_err[cp.index[d]]]
+        bulk = cp.frames is not None and len(good) * 4 >= len(cp.samples) and hasattr(self._final(), "write_frames_bulk")
+        if bulk:
+            # the frames of ALL donors leave the GPU in one copy and enter the file with one write; each dataset's
+            # chunk index then points into that block (no per-chunk work on the host)
+            buf = cp.frames.fetch_all()
+            offs, sizes = cp.frames.layout()
+            rows = [cp.index[d] for d in good]
+            self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in good], RECORD_DTYPE,
+                                            cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])
+            self.stats["datasets"] += len(good)
+            self.stats["records"] += cp.n_records * len(good)
+            self.stats["stored_bytes"] += int(sizes[rows].sum())
+            del buf
+        done = set(good) if bulk else set()
         for donor_id in self.donor_ids:
+            if donor_id in done:
+                continue
             try:
                 self.genotype_vcf_to_hdf5(vcf_file, donor_id, chromosome)
             except capi.HaploError:

@@ -95,3 +95,30 @@ def test_duplicate_and_bad_paths(tmp_path, minih5):
     with pytest.raises(OSError):
         (tmp_path / "junk.h5").write_bytes(b"not hdf5" * 20)
         minih5.H5Reader(str(tmp_path / "junk.h5"))
+
+
+@pytest.mark.parametrize("n_chunks", [1, 5, 64, 65, 300, 5000])
+def test_bulk_blob_writer_equals_per_chunk_writer(tmp_path, minih5, n_chunks):
+    """write_blob + create_dataset_chunked_at (one write for all stored chunks, numpy-built chunk B-tree, gaps between
+    chunks allowed) must describe the same dataset as the per-chunk writer."""
+    rng = np.random.default_rng(n_chunks)
+    dt = np.dtype([("a", "S5"), ("b", "<u4")])
+    chunks = [rng.integers(0, 256, int(rng.integers(1, 50)), dtype=np.uint8).tobytes() for _ in range(n_chunks)]
+    cd = (2, 2, 9, 90, 5, 1, 2)
+    with minih5.H5Writer(str(tmp_path / "a.h5")) as w:
+        w.create_dataset_chunked("g/x/snp", dt, n_chunks * 10, 10, chunks, filter_id=32001, cd_values=cd, filter_name="blosc2")
+    offs, blob = [], bytearray()
+    for c in chunks:
+        blob += b"\xee" * int(rng.integers(0, 16))
+        offs.append(len(blob))
+        blob += c
+    with minih5.H5Writer(str(tmp_path / "b.h5")) as w:
+        base = w.write_blob(bytes(blob))
+        assert base % 16 == 0
+        w.create_dataset_chunked_at("g/x/snp", dt, n_chunks * 10, 10, base + np.array(offs, np.uint64),
+                                    np.array([len(c) for c in chunks], np.uint32), filter_id=32001, cd_values=cd, filter_name="blosc2")
+    ra, rb = minih5.H5Reader(str(tmp_path / "a.h5")), minih5.H5Reader(str(tmp_path / "b.h5"))
+    ia, ib = ra.dataset_info("g/x/snp"), rb.dataset_info("g/x/snp")
+    assert [c for _, c in ra.chunks(ia)] == chunks and rb.chunks(ib) == ra.chunks(ia)
+    assert ia.filters == ib.filters and ia.chunk == ib.chunk and ia.shape == ib.shape and ia.dtype == ib.dtype
+    ra.close(); rb.close()
