@@ -68,7 +68,7 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
-    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
@@ -100,6 +100,7 @@ def lib():
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.hb_parse_device_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.hb_parse_vcf_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.hb_parse_samples.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_parse_rerun.argtypes = [C.c_void_p]
         L.hb_parse_get_info.argtypes = [C.c_void_p, C.POINTER(ParseInfo)]
@@ -193,6 +194,20 @@ class Parse:
     def from_file(cls, path: str, region="", want_gt=True, device=0):
         h = C.c_void_p()
         check(lib().hb_parse_file(path.encode(), (region or "").encode(), int(want_gt), device, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_vcf_bytes(cls, data, region="", want_gt=True, device=0, nbytes=None):
+        """The bytes of a .vcf / .vcf.gz in host memory (bytes, uint8 array, or address + nbytes)."""
+        if isinstance(data, (bytes, bytearray)):
+            keep = np.frombuffer(data, np.uint8); addr, n = keep.ctypes.data, keep.size
+        elif isinstance(data, np.ndarray):
+            keep = data; addr, n = data.ctypes.data, data.size
+        else:
+            keep = None; addr, n = int(data), int(nbytes)
+        h = C.c_void_p()
+        check(lib().hb_parse_vcf_bytes(addr, n, (region or "").encode(), int(want_gt), device, C.byref(h)))
+        del keep
         return cls(h)
 
     def sample_names(self):

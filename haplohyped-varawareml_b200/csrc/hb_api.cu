@@ -784,10 +784,22 @@ int read_vcf(const std::vector<uint8_t> &raw, FileText &ft) {
 // reads) travel over PCIe COMPRESSED and are inflated on the GPU (hb_inflate.cu) straight into the text buffer;
 // only the header members are also inflated on the host, to learn the sample names.  Plain gzip (one DEFLATE
 // stream: nothing to parallelise) and plain text go through zlib / as they are.  HB_CPU_INFLATE=1 forces zlib.
+int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, uint64_t raw_n, const char *region, bool want_gt,
+                       int device, hb_parse **out, std::vector<std::string> &samples);
+
 int parse_file_common(const char *path, const char *region, bool want_gt, int device, hb_parse **out,
                       std::vector<std::string> &samples) {
     std::vector<uint8_t> raw;
     TRY(read_all(path, raw));
+    return parse_bytes_common(raw, raw.data(), raw.size(), region, want_gt, device, out, samples);
+}
+
+// raw_p[0..raw_n): the bytes of a .vcf / .vcf.gz; raw_owned: the vector that holds them when the caller read a file
+// (released early on the zlib path), empty when they belong to the caller
+int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, uint64_t raw_n, const char *region, bool want_gt,
+                       int device, hb_parse **out, std::vector<std::string> &samples) {
+    struct View { const uint8_t *p; uint64_t n; const uint8_t *data() const { return p; } uint64_t size() const { return n; }
+                  uint8_t operator[](uint64_t i) const { return p[i]; } } raw{raw_p, raw_n};
     std::vector<uint64_t> coff, ooff;
     std::vector<uint32_t> clen, olen;
     uint64_t total = 0;
@@ -801,8 +813,9 @@ int parse_file_common(const char *path, const char *region, bool want_gt, int de
     o.device = device;
     if (!gpu_inflate) {
         FileText ft;
-        TRY(read_vcf(raw, ft));
-        raw.clear(); raw.shrink_to_fit();
+        if (raw_owned.empty()) raw_owned.assign(raw_p, raw_p + raw_n);
+        TRY(read_vcf(raw_owned, ft));
+        raw_owned.clear(); raw_owned.shrink_to_fit();
         samples = ft.samples;
         o.n_samples = (uint32_t)ft.samples.size();
         o.end_is_int = ft.end_is_int;
@@ -1074,6 +1087,15 @@ int hb_bgzf_compress_host(const uint8_t *text, uint64_t nbytes, int level, uint8
     const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     memcpy(out + o, eof, 28);
     *len = o + 28;
+    return HB_OK;
+}
+
+int hb_parse_vcf_bytes(const uint8_t *data, uint64_t nbytes, const char *region, int want_gt, int device, hb_parse **out) {
+    if (!data || !out) return fail(HB_ERR_ARG, "null argument");
+    std::vector<std::string> samples;
+    std::vector<uint8_t> none;
+    TRY(parse_bytes_common(none, data, nbytes, region, want_gt != 0, device, out, samples));
+    (*out)->samples = samples;
     return HB_OK;
 }
 

@@ -119,6 +119,9 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
 /* a whole .vcf / .vcf.gz (BGZF or plain gzip): header + body, all samples, no per-sample cache.
  * What the vcf_to_h5 converter drives (src/haplohyped/vcf_to_h5.py:98-101 without the per-donor re-scan). */
 int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int device, hb_parse **out);
+/* the same for the bytes of a .vcf / .vcf.gz already in host memory (BGZF bytes cross PCIe compressed and are
+ * inflated on the GPU; pinned memory makes that copy asynchronous) */
+int hb_parse_vcf_bytes(const uint8_t *data, uint64_t nbytes, const char *region, int want_gt, int device, hb_parse **out);
 /* sample names of a file-level parse, NUL-separated */
 int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */
