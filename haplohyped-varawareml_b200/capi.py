@@ -68,7 +68,7 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
-    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
@@ -103,6 +103,7 @@ def lib():
         L.hb_parse_vcf_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.hb_parse_samples.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_parse_rerun.argtypes = [C.c_void_p]
+        L.hb_parse_rerun_bytes.argtypes = [C.c_void_p, C.c_uint64]
         L.hb_parse_get_info.argtypes = [C.c_void_p, C.POINTER(ParseInfo)]
         L.hb_parse_fetch_sites.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.hb_parse_fetch_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]

@@ -523,6 +523,13 @@ int hb_parse_rerun(hb_parse *p) {
     return run_parse(p);
 }
 
+int hb_parse_rerun_bytes(hb_parse *p, uint64_t nbytes) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    if (p->d_text_owned) return fail(HB_ERR_ARG, "hb_parse_rerun_bytes is for handles made by hb_parse_device_text");
+    p->nbytes = nbytes;
+    return run_parse(p);
+}
+
 int hb_parse_get_info(const hb_parse *p, hb_parse_info *info) {
     if (!p || !info) return fail(HB_ERR_ARG, "null argument");
     memset(info, 0, sizeof *info);

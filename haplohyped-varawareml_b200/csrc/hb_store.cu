@@ -699,6 +699,8 @@ struct hb_frames {
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t n_records = 0, n_chunks = 0, cr = 0;
+    uint64_t chunk_cap = 0;                  // chunks the per-chunk arrays were allocated for
+    bool cr_explicit = false;                // chunk_records was given by the caller (it does not follow n_records)
     uint32_t n_samples = 0, tmpl_cap = 0;
     size_t smem_site = 0;
     FusedArgs fa;                            // geometry of the fused kernel
@@ -876,6 +878,7 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     f->device = p->device; f->stream = p->stream;
     f->n_records = n; f->n_samples = p->n_samples;
     f->cr = chunk_records ? chunk_records : guess_chunk_records(n);
+    f->cr_explicit = chunk_records != 0;
     f->n_chunks = n ? (n + f->cr - 1) / f->cr : 0;
     if (!f->n_chunks || !f->n_samples) { f->n_chunks = n ? f->n_chunks : 0; *out = f; return HB_OK; }
     if (f->cr > 2730) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk_records too large (at most 2730: the site encoder indexes 24*chunk_records+1 positions with 16 bits)"); }
@@ -896,16 +899,17 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
     fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
     fa.warp_smem = 2 * fa.rb + 16 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
     if ((size_t)kWpc * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
-    const uint64_t n_frames = f->n_chunks * f->n_samples;
-    f->n_ctas = (n_frames + kWpc - 1) / kWpc;
+    f->chunk_cap = f->n_chunks + 4;          // a re-run on a slightly longer record set (streaming) still fits
+    const uint64_t n_frames = f->chunk_cap * f->n_samples;
+    f->n_ctas = (f->n_chunks * f->n_samples + kWpc - 1) / kWpc;
     f->h_tmpl_len.resize(f->n_chunks);
     f->h_slot_off.resize(f->n_chunks + 1);
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    ck(cudaMalloc(&f->d_tmpl, f->n_chunks * (uint64_t)f->tmpl_cap));
-    ck(cudaMalloc(&f->d_tmpl_len, f->n_chunks * 4));
+    ck(cudaMalloc(&f->d_tmpl, f->chunk_cap * (uint64_t)f->tmpl_cap));
+    ck(cudaMalloc(&f->d_tmpl_len, f->chunk_cap * 4));
     ck(cudaMalloc(&f->d_size, n_frames * 4));
-    ck(cudaMalloc(&f->d_slot_off, (f->n_chunks + 1) * 8));
+    ck(cudaMalloc(&f->d_slot_off, (f->chunk_cap + 1) * 8));
     ck(cudaMalloc(&f->d_totals, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
     {   // highest priority: its few long CTAs must get SM slots while the decoder's many short ones stream through
@@ -938,8 +942,20 @@ int hb_parse_attach_frames(hb_parse *p, hb_frames *f) {
 
 int hb_frames_rerun(hb_frames *f, hb_parse *p) {
     if (!f || !p) return api_fail(HB_ERR_ARG, "null argument");
-    if (p->h_st.n_records != f->n_records || p->n_samples != f->n_samples || p->device != f->device)
+    if (p->n_samples != f->n_samples || p->device != f->device)
         return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
+    if (p->h_st.n_records != f->n_records) {
+        // another record count is fine when the chunk size was fixed by the caller and the chunk arrays are large enough
+        const uint64_t nc = p->h_st.n_records ? (p->h_st.n_records + f->cr - 1) / f->cr : 0;
+        if (!f->cr_explicit || nc > f->chunk_cap || nc == 0)
+            return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
+        f->n_records = p->h_st.n_records;
+        f->n_chunks = nc;
+        f->n_ctas = (nc * f->n_samples + kWpc - 1) / kWpc;
+        f->h_tmpl_len.resize(nc);
+        f->h_slot_off.resize(nc + 1);
+        f->early_site = false;                   // an early template pass (if any) was made for the old shape
+    }
     if (!f->n_chunks || !f->n_samples) return HB_OK;
     return frames_run(f, p);
 }

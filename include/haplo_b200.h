@@ -126,6 +126,8 @@ int hb_parse_vcf_bytes(const uint8_t *data, uint64_t nbytes, const char *region,
 int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */
 int hb_parse_rerun(hb_parse *p);
+/* the same for a handle made by hb_parse_device_text whose buffer now holds nbytes of (other) text: slab streaming */
+int hb_parse_rerun_bytes(hb_parse *p, uint64_t nbytes);
 int hb_parse_get_info(const hb_parse *p, hb_parse_info *info);
 /* host copies.  Any pointer may be NULL.  chrom names: see hb_parse_chrom_runs. */
 int hb_parse_fetch_sites(hb_parse *p, uint32_t *start, uint32_t *stop, char *ref, char *alt);
@@ -178,7 +180,9 @@ int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out);
  * decoder instead of following it.  hb_frames_rerun then only runs what needs the genotype planes.  The frames must
  * outlive the attachment. */
 int hb_parse_attach_frames(hb_parse *p, hb_frames *f);
-/* run the kernels again on the (re-parsed) handle the frames were made from: no allocation unless C_out grew */
+/* run the kernels again on the (re-parsed) handle the frames were made from: no allocation unless C_out grew.  The
+ * record count may differ from the first run when chunk_records was given explicitly (slab streaming: a few chunks
+ * more than the first slab had are provided for). */
 int hb_frames_rerun(hb_frames *f, hb_parse *p);
 int hb_frames_get_info(const hb_frames *f, hb_frames_info *info);
 /* offsets (into the frame buffer) and true sizes of every frame, [n_samples][n_chunks]; either may be NULL */
