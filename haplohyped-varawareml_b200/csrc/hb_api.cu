@@ -270,12 +270,13 @@ static int run_parse(hb_parse *p) {
 
     // ---- how to locate the records, from the first one
     if (!p->probed) {
-        uint8_t head[65536];
-        size_t hn = (size_t)std::min<uint64_t>(sizeof head, p->nbytes);
-        CU(cudaMemcpyAsync(head, p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
+        // the whole first record: 4 bytes per sample when it is GT-only (800 KB at 200,000 samples) + its head
+        std::vector<uint8_t> head((size_t)std::min<uint64_t>(4ull * p->n_samples + 65536, p->nbytes));
+        const size_t hn = head.size();
+        CU(cudaMemcpyAsync(head.data(), p->d_text, hn, cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         bool gt_only, uniform; uint64_t l0;
-        probe_head(head, hn, p->n_samples, gt_only, uniform, l0);
+        probe_head(head.data(), hn, p->n_samples, gt_only, uniform, l0);
         p->with_tabs = p->tokenizer == 2 || ((p->tokenizer == 0 || p->tokenizer == 3) && !gt_only);
         if (!p->want_gt) p->with_tabs = false;
         // walking pays when a record is much longer than its head (and needs the decoder to validate the jumps)

@@ -196,7 +196,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + aa[k]);
                     const uint32_t x = __funnelshift_r(colp[0], colp[1], hh[k]) ^ 0x307C3009u;   // "\t0|0"
-                    bad |= x & 0xFEFFFEFFu;                   // anything but the two allele bits left?
+                    if (x & 0xFEFFFEFFu) bad |= 1u << (4 * q + k);   // anything but the two allele bits left? remember which call
                     // byte k of acc0 <- byte 1 of x, byte k of acc1 <- byte 3 of x
                     acc0[q] = __byte_perm(acc0[q], x, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
                     acc1[q] = __byte_perm(acc1[q], x, k == 0 ? 0x3217 : k == 1 ? 0x3270 : k == 2 ? 0x3710 : 0x7210);
@@ -205,18 +205,15 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         }
         *reinterpret_cast<uint4 *>(&sm.out[0][s][16 * rg]) = make_uint4(acc0[0], acc0[1], acc0[2], acc0[3]);
         *reinterpret_cast<uint4 *>(&sm.out[1][s][16 * rg]) = make_uint4(acc1[0], acc1[1], acc1[2], acc1[3]);
-        if (bad) {
-#pragma unroll 1
-            for (int i = 0; i < 16; ++i) {
-                const int r = 16 * rg + i;
-                const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + sm.addr[r]);
-                const uint32_t w = __funnelshift_r(colp[0], colp[1], sm.shft[r]);
-                if ((w ^ 0x307C3009u) & 0xFEFFFEFFu) {
-                    const uint32_t x = decode_group_slow(w, &sm.mode[r], st);
-                    sm.out[0][s][r] = (uint8_t)(x >> 8);
-                    sm.out[1][s][r] = (uint8_t)(x >> 24);
-                }
-            }
+        while (bad) {                                         // the thread's odd calls (a/b, '.', alleles >= 2), one by one
+            const int i = __ffs(bad) - 1;
+            bad &= bad - 1;
+            const int r = 16 * rg + i;
+            const uint32_t *colp = reinterpret_cast<const uint32_t *>(tbase + sm.addr[r]);
+            const uint32_t w = __funnelshift_r(colp[0], colp[1], sm.shft[r]);
+            const uint32_t x = decode_group_slow(w, &sm.mode[r], st);
+            sm.out[0][s][r] = (uint8_t)(x >> 8);
+            sm.out[1][s][r] = (uint8_t)(x >> 24);
         }
     }
     __syncthreads();

@@ -800,10 +800,14 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         need = run * f->n_samples;
     }
     if (f->frames_cap < need) {
+        const bool regrow = f->d_frames != nullptr;
         if (f->d_frames) { cudaFree(f->d_frames); f->d_frames = nullptr; f->frames_cap = 0; }
-        e = cudaMalloc(&f->d_frames, need);
-        if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(need) + " bytes): " + cudaGetErrorString(e));
-        f->frames_cap = need;
+        // head-room: a re-run on other data (slab streaming) has slightly different template lengths, and growing
+        // means cudaFree + cudaMalloc of many GB (~100 ms)
+        const uint64_t cap = regrow ? need + need / 16 + (64ull << 20) : need + need / 64 + (16ull << 20);
+        e = cudaMalloc(&f->d_frames, cap);
+        if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
+        f->frames_cap = cap;
     }
     CUF(cudaMemcpyAsync(f->d_slot_off, f->h_slot_off.data(), (f->n_chunks + 1) * 8, cudaMemcpyHostToDevice, f->stream));
     FusedArgs fa = f->fa;

@@ -52,6 +52,8 @@ for k in range(n_slabs):
     tot["text"] += T; tot["records"] += int(i.n_records); tot["c_out"] += int(fi.total_bytes)
     tot["ms_synth"] += ev[0].elapsed_time(ev[1]); tot["ms_parse"] += ev[1].elapsed_time(ev[2]); tot["ms_store"] += ev[2].elapsed_time(ev[3])
     tot["alg"] += T + 2.0 * (2.0 * i.n_records * S + 33.0 * i.n_records) + fi.total_bytes
+    if os.environ.get("C4_VERBOSE"):
+        print(k, "parse %.2f store %.2f (site %.2f frames %.2f) n_rec %d tok %d" % (ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]), fi.ms_site, fi.ms_frames, i.n_records, i.tokenizer_used), flush=True)
     if k == 0:      # parity spot check: the oracle regenerates the first records of this slab on the CPU
         nchk = 3
         head = capi.synth_header(sp) + capi.synth_host(sp, 0, nchk)
