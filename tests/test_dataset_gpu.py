@@ -138,3 +138,33 @@ def test_encode_sequence_contract(mods):
     assert cu.encode_sequence("AXGT")[1, 4] == 1
     with pytest.raises(TypeError):
         cu.encode_sequence([1, 2, 3, 4])
+
+
+def test_fasta_encoder_to_dataset(mods, tmp_path):
+    """fasta_encoder mirror end to end: FASTA -> reference_genome.h5 -> RandomHaplotypeDataset windows; and its
+    encode_sequence (GPU) against the oracle one-hot."""
+    capi, hd, cu = mods
+    from haplohyped_varawareml_b200 import fasta_encoder as fe
+    rng = np.random.default_rng(11)
+    donors, seqs, records, bed = _make_world(tmp_path, rng, n_donors=2, chrom_len=20_000, n_rec=200)
+    fa = tmp_path / "ref.fa"
+    with open(fa, "wb") as f:
+        for k, v in seqs.items():
+            b = v.tobytes()
+            f.write(b">" + k.encode() + b"\n" + b"\n".join(b[i:i + 70] for i in range(0, len(b), 70)) + b"\n")
+    fe.main(["--fasta", str(fa), "--outdir", str(tmp_path / "refout")])
+    ds = hd.RandomHaplotypeDataset(str(bed), None, str(tmp_path / "refout" / "reference_genome.h5"), str(tmp_path / "samples.txt"),
+                                   batch_size=4, seq_length=600, genotype_store=hd.GenotypeStore.from_records(records))
+    items = ds.draw()
+    h1, h2 = ds.encode_items(items)
+    e1, e2 = _expected(items, seqs, records, 600, oracle.parse_encode_dict(None))
+    assert np.array_equal(h1.cpu().numpy(), e1) and np.array_equal(h2.cpu().numpy(), e2)
+    ds.close()
+    rg = fe.ReferenceGenome()
+    s = "ACGTNacgtnRYxx"
+    spec = oracle.parse_encode_dict(None)
+    idx = np.array([spec.get(c.upper(), spec["N"]) for c in s], np.int8)
+    assert np.array_equal(rg.encode_sequence(s), oracle.onehot(idx, 5))
+    assert np.array_equal(rg.encode_sequence(np.frombuffer(s.encode(), "|S1")), oracle.onehot(idx, 5))
+    with pytest.raises(TypeError):
+        rg.encode_sequence([1, 2])

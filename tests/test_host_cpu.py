@@ -128,3 +128,29 @@ def test_metadata_allgather_world2_gloo():
     for rank, mine, g, offs in res:
         assert [x["n_records"] for x in g] == [100, 200] and offs == [0, 100]
         assert g[1]["text_bytes"] == 1001 and g[0]["last_pos"] == 9
+
+
+def test_fasta_encoder_writes_the_reference_file_the_dataset_reads(tmp_path):
+    """fasta_encoder mirror: FASTA (plain and gzip, wrapped lines, extra contigs) -> reference_genome.h5 with one
+    byte-per-base dataset per chr1..chr22 -- the file RandomHaplotypeDataset(hdf5_reference_file=...) opens."""
+    import gzip
+    from haplohyped_varawareml_b200 import fasta_encoder as fe
+    rng = np.random.default_rng(2)
+    seqs = {f"chr{c}": bytes(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=int(rng.integers(50, 400)))) for c in (1, 2, 22)}
+    seqs["chrUn_x"] = b"ACGT" * 5
+    text = b""
+    for k, v in seqs.items():
+        text += b">" + k.encode() + b" some description\n" + b"\n".join(v[i:i + 60] for i in range(0, len(v), 60)) + b"\n"
+    plain, gz = tmp_path / "ref.fa", tmp_path / "ref.fa.gz"
+    plain.write_bytes(text)
+    with gzip.open(gz, "wb") as f:
+        f.write(text)
+    for src in (plain, gz):
+        out = tmp_path / ("o_" + src.name)
+        fe.main(["--fasta", str(src), "--outdir", str(out), "--cores", "2"])
+        assert not (out / "tmp_chrom_files").exists()
+        got = fe.HDF5Handler.load_from_hdf5(str(out / "reference_genome.h5"))
+        assert sorted(got) == ["chr1", "chr2", "chr22"]                 # chr1..22 only, as the reference's chrom list
+        for k in got:
+            assert got[k].tobytes() == seqs[k]
+    assert fe.ReferenceGenome.parse_encode_list(None) == [b"A", b"C", b"G", b"T", b"N"]
