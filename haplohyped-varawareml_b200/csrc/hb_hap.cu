@@ -32,7 +32,7 @@ __device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t *a, uint64_t 
 
 template <int CC>   // CC > 0: compile-time class count; 0: runtime
 __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
-    __shared__ __align__(16) int8_t s_idx[2][HP_TILE];
+    __shared__ int8_t s_idx[2][HP_TILE];
     __shared__ int8_t s_lut[256];
     const int tid = threadIdx.x;
     const uint32_t b = blockIdx.y;
@@ -89,26 +89,7 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
     for (int h = 0; h < 2; ++h) {
         float *out = (h ? a.hap2 : a.hap1) + base_el;
         const int8_t *idx = s_idx[h];
-        if (CC > 0 && (base_el & 3) == 0 && (tn & 3) == 0) {
-            // compile-time class count: 4 positions = 4*CC floats = CC 16-byte vectors, every element a compare against
-            // a constant -- one 4-byte index load and CC vector stores per thread step
-            for (uint32_t q = tid; q < (tn >> 2); q += HP_THREADS) {
-                const uint32_t i4 = *reinterpret_cast<const uint32_t *>(idx + 4 * q);
-                const int ix[4] = {(int)(int8_t)(i4 & 0xff), (int)(int8_t)((i4 >> 8) & 0xff), (int)(int8_t)((i4 >> 16) & 0xff),
-                                   (int)(int8_t)(i4 >> 24)};
-                uint4 *dst = reinterpret_cast<uint4 *>(out + (uint64_t)q * 4 * CC);
-#pragma unroll
-                for (int v = 0; v < CC; ++v) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int e = 4 * v + j;                 // element of the 4*CC block: position e / CC, class e % CC
-                        w[j] = ix[e / CC] == e % CC ? 0x3f800000u : 0u;
-                    }
-                    stg_stream(dst + v, make_uint4(w[0], w[1], w[2], w[3]));
-                }
-            }
-        } else if ((base_el & 3) == 0) {
+        if ((base_el & 3) == 0) {
             const uint32_t n4 = n_el >> 2;
             for (uint32_t q = tid; q < n4; q += HP_THREADS) {
                 uint32_t e = 4 * q;
