@@ -272,81 +272,95 @@ def main():
 
     # ---- e2e: host (pinned) text -> C ABI -> genotype matrix back in host memory
     e2e = None
-    if not args.no_e2e:
-        host = torch.empty(T, dtype=torch.uint8).pin_memory()
-        host.copy_(text[:T])
-        out0 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
-        out1 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
-        sites = [torch.empty(Vk, dtype=torch.int32).pin_memory(), torch.empty(Vk, dtype=torch.int32).pin_memory(),
-                 torch.empty(Vk, dtype=torch.uint8).pin_memory(), torch.empty(Vk, dtype=torch.uint8).pin_memory()]
+    try:
+      if not args.no_e2e:
+          # every rank must get its pinned buffers, or none runs the e2e leg (a rank that dropped out alone would leave
+          # the others waiting at the barrier)
+          alloc_err = None
+          try:
+              host = torch.empty(T, dtype=torch.uint8).pin_memory()
+              host.copy_(text[:T])
+              out0 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
+              out1 = torch.empty((S, Vk), dtype=torch.int8).pin_memory()
+              sites = [torch.empty(Vk, dtype=torch.int32).pin_memory(), torch.empty(Vk, dtype=torch.int32).pin_memory(),
+                       torch.empty(Vk, dtype=torch.uint8).pin_memory(), torch.empty(Vk, dtype=torch.uint8).pin_memory()]
+          except Exception as ex:
+              alloc_err = "%s: %s" % (type(ex).__name__, ex)
+          okf = torch.tensor([0 if alloc_err else 1], dtype=torch.int32, device=dev)
+          if world > 1:
+              dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+          if int(okf.item()) == 0:
+              raise RuntimeError("pinned host buffers for the e2e leg could not be allocated on every rank (%s)" % (alloc_err or "another rank"))
 
-        nrec = C.c_uint64()
-        opts = capi.Parse._opts(S, "chr22", False, True, local, 0, None)
+          nrec = C.c_uint64()
+          opts = capi.Parse._opts(S, "chr22", False, True, local, 0, None)
 
-        def e2e_step():
-            capi.check(capi.lib().hb_parse_stream_host(host.data_ptr(), T, C.byref(opts), args.slab_bytes, out0.data_ptr(),
-                                                       out1.data_ptr(), Vk, sites[0].data_ptr(), sites[1].data_ptr(),
-                                                       sites[2].data_ptr(), sites[3].data_ptr(), None, None, C.byref(nrec), None))
-            assert nrec.value == Vk
+          def e2e_step():
+              capi.check(capi.lib().hb_parse_stream_host(host.data_ptr(), T, C.byref(opts), args.slab_bytes, out0.data_ptr(),
+                                                         out1.data_ptr(), Vk, sites[0].data_ptr(), sites[1].data_ptr(),
+                                                         sites[2].data_ptr(), sites[3].data_ptr(), None, None, C.byref(nrec), None))
+              assert nrec.value == Vk
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T * world,
-               "d2h_bytes_per_step": (2 * S * Vk + 10 * Vk) * world, "steps": args.e2e_steps,
-               "api": "hb_parse_stream_host: pinned host text -> genotype matrix [S][V'] x2 + site columns in pinned host "
-                      "memory; slabs of %d MiB, H2D / kernels / D2H overlapped" % (args.slab_bytes >> 20)}
-        # the streamed result is the same matrix the device-resident step produced
-        if rank == 0:
-            g0, g1 = p.sample(S // 3)
-            e2e["matches_device_path"] = bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1))
-        # ---- the same, starting from what is on disk: the BGZF bytes of the .vcf.gz in pinned host memory.  They cross
-        # PCIe compressed, are inflated and parsed on the GPU; the matrix + site columns come back to pinned host memory.
-        if not args.no_bgzf and rank == 0:
-            import numpy as _np
-            hdr = capi.synth_header(spec)
-            full = _np.empty(len(hdr) + T, _np.uint8)
-            full[:len(hdr)] = _np.frombuffer(hdr, _np.uint8)
-            full[len(hdr):] = host.numpy()
-            t0 = time.perf_counter()
-            bg = capi.bgzf_compress_host(full, 6)
-            t_comp = time.perf_counter() - t0
-            del full
-            bgp = torch.empty(bg.size, dtype=torch.uint8).pin_memory()
-            bgp.numpy()[:] = bg
-            del bg
+          e2e_step()
+          barrier()
+          t0 = time.perf_counter()
+          for _ in range(args.e2e_steps):
+              e2e_step()
+          barrier()
+          dt = time.perf_counter() - t0
+          tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+          if world > 1:
+              dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+          dt = float(tt.item())
+          e2e = {"value": calls_total / (dt / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": T * world,
+                 "d2h_bytes_per_step": (2 * S * Vk + 10 * Vk) * world, "steps": args.e2e_steps,
+                 "api": "hb_parse_stream_host: pinned host text -> genotype matrix [S][V'] x2 + site columns in pinned host "
+                        "memory; slabs of %d MiB, H2D / kernels / D2H overlapped" % (args.slab_bytes >> 20)}
+          # the streamed result is the same matrix the device-resident step produced
+          if rank == 0:
+              g0, g1 = p.sample(S // 3)
+              e2e["matches_device_path"] = bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1))
+          # ---- the same, starting from what is on disk: the BGZF bytes of the .vcf.gz in pinned host memory.  They cross
+          # PCIe compressed, are inflated and parsed on the GPU; the matrix + site columns come back to pinned host memory.
+          if not args.no_bgzf and rank == 0:
+              import numpy as _np
+              hdr = capi.synth_header(spec)
+              full = _np.empty(len(hdr) + T, _np.uint8)
+              full[:len(hdr)] = _np.frombuffer(hdr, _np.uint8)
+              full[len(hdr):] = host.numpy()
+              t0 = time.perf_counter()
+              bg = capi.bgzf_compress_host(full, 6)
+              t_comp = time.perf_counter() - t0
+              del full
+              bgp = torch.empty(bg.size, dtype=torch.uint8).pin_memory()
+              bgp.numpy()[:] = bg
+              del bg
 
-            def bgzf_step():
-                q = capi.Parse.from_vcf_bytes(bgp.data_ptr(), region="chr22", device=local, nbytes=bgp.numel())
-                capi.check(capi.lib().hb_parse_fetch_matrix(q._h, out0.data_ptr(), out1.data_ptr()))
-                capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.data_ptr() for a in sites]))
-                ms_inf = q.info.ms_inflate
-                q.close()
-                return ms_inf
+              def bgzf_step():
+                  q = capi.Parse.from_vcf_bytes(bgp.data_ptr(), region="chr22", device=local, nbytes=bgp.numel())
+                  capi.check(capi.lib().hb_parse_fetch_matrix(q._h, out0.data_ptr(), out1.data_ptr()))
+                  capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.data_ptr() for a in sites]))
+                  ms_inf = q.info.ms_inflate
+                  q.close()
+                  return ms_inf
 
-            bgzf_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            ms_inf = [bgzf_step() for _ in range(args.e2e_steps)]
-            torch.cuda.synchronize()
-            dtb = time.perf_counter() - t0
-            g0, g1 = p.sample(S // 3)
-            e2e["from_bgzf"] = {"value": float(V) * S / (dtb / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": int(bgp.numel()),
-                                "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk, "steps": args.e2e_steps,
-                                "inflate_kernel_ms": sorted(ms_inf)[len(ms_inf) // 2], "text_over_bgzf": T / float(bgp.numel()),
-                                "matches_device_path": bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1)),
-                                "api": "hb_parse_vcf_bytes (BGZF in pinned host memory -> GPU inflate -> GPU parse) + hb_parse_fetch_matrix "
-                                       "+ hb_parse_fetch_sites; rank 0 only", "bgzip_equivalent_host_s": t_comp}
-            del bgp
-        del host, out0, out1
+              bgzf_step()
+              torch.cuda.synchronize()
+              t0 = time.perf_counter()
+              ms_inf = [bgzf_step() for _ in range(args.e2e_steps)]
+              torch.cuda.synchronize()
+              dtb = time.perf_counter() - t0
+              g0, g1 = p.sample(S // 3)
+              e2e["from_bgzf"] = {"value": float(V) * S / (dtb / args.e2e_steps), "unit": "calls/s", "h2d_bytes_per_step": int(bgp.numel()),
+                                  "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk, "steps": args.e2e_steps,
+                                  "inflate_kernel_ms": sorted(ms_inf)[len(ms_inf) // 2], "text_over_bgzf": T / float(bgp.numel()),
+                                  "matches_device_path": bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1)),
+                                  "api": "hb_parse_vcf_bytes (BGZF in pinned host memory -> GPU inflate -> GPU parse) + hb_parse_fetch_matrix "
+                                         "+ hb_parse_fetch_sites; rank 0 only", "bgzip_equivalent_host_s": t_comp}
+              del bgp
+          del host, out0, out1
+    except Exception as ex:          # e.g. not enough pinnable host memory on a crowded box: the device-resident numbers stand
+        e2e = {"value": None, "unit": "calls/s", "error": "%s: %s" % (type(ex).__name__, ex)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

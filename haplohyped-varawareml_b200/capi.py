@@ -112,6 +112,7 @@ def lib():
         L.hb_parse_chrom_runs.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p,
                                           C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_parse_free.argtypes = [C.c_void_p]
+        L.hb_bgzf_compress_host.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.hb_bgzf_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int,
                                       C.POINTER(C.c_float)]
         if hasattr(L, "hb_compress_records"):
@@ -399,7 +400,6 @@ def bgzf_compress_host(text, level: int = 6) -> np.ndarray:
     """text (bytes / uint8 array) -> BGZF bytes (uint8 array), stock zlib on all host threads (test / bench utility)."""
     src = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
     L = lib()
-    L.hb_bgzf_compress_host.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     n = C.c_uint64()
     check(L.hb_bgzf_compress_host(src.ctypes.data, src.size, level, None, 0, C.byref(n)))
     out = np.empty(n.value, np.uint8)

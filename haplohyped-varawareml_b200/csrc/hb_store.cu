@@ -426,7 +426,6 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     const uint64_t n_frames = A.n_chunks * A.n_samples;
     const uint64_t wid = (uint64_t)blockIdx.x * kWpc + warp;
     if (wid >= n_frames) return;
-    const bool active = true;
     const int cr = (int)A.cr, n = 2 * cr;
     uint8_t *base = smem + (size_t)warp * A.warp_smem;
     uint8_t *raw0 = base, *raw1 = base + A.rb;
@@ -442,12 +441,11 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     uint64_t c = 0;
     // state of the parse that the emission needs
     int m = 0, carry = 0, a0 = 0, p = 0, first_ml = 0;
-    (void)active;
     unsigned long long kindmask = 0;
     int out_base = 0, run_base = 0, lit_base = 0, total = 0, totrun = 0, totlit = 0, final_lit = 0;
     uint32_t sidx = 0;
 
-    if (active) {
+    {
         uint32_t s;
         if (n_frames <= 0xFFFFFFFFull) { s = (uint32_t)wid / (uint32_t)A.n_chunks; c = (uint32_t)wid - s * (uint32_t)A.n_chunks; }
         else { s = (uint32_t)(wid / A.n_chunks); c = wid % A.n_chunks; }
@@ -582,7 +580,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     const uint32_t flen = tl + (uint32_t)dlen + FRAME_TAIL;
 
     // ---- 4. every lane writes the headers of its own sequences, then the literals are copied in 32 equal shares
-    if (active && cr >= 6) {
+    if (cr >= 6) {
         uint8_t *seq = outb + (tl & 15u);
         {
             int o = out_base, r = run_base, lc = lit_base;
@@ -629,7 +627,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             }
         }
     }
-    if (active) {
+    {
         uint8_t *seq = outb + (tl & 15u);
         const int padded = (int)((((tl & 15u) + (uint32_t)dlen + FRAME_TAIL + 15u) & ~15u) - (tl & 15u)) - dlen;   // tail + zero pad
         for (int i = lane; i < padded; i += 32) seq[dlen + i] = i < FRAME_TAIL ? kFrameTail[i] : (uint8_t)0;
