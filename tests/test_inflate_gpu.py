@@ -84,7 +84,15 @@ def test_bgzf_file_through_the_reference_api(capi, tmp_path, built):
         assert [r[1] for r in got] == list(exp["start"]) and [r[5] for r in got] == list(exp["gt0"]) and [r[6] for r in got] == list(exp["gt1"])
         assert got == parse_vcf.load_vcf(gz, s, "chr22")                # plain gzip (CPU zlib) gives the same tuples
     p = capi.Parse.from_file(path, region="chr22")
-    assert p.sample_names() == samples
+    assert p.sample_names() == samples and p.info.compressed_bytes == os.path.getsize(path) and p.info.ms_inflate > 0
+    pb = capi.Parse.from_vcf_bytes(open(path, "rb").read(), region="chr22")          # the same bytes from host memory
+    assert pb.sample_names() == samples and np.array_equal(pb.matrix()[0], p.matrix()[0])
+    os.environ["HB_CPU_INFLATE"] = "1"                                                # zlib on the host: same result
+    try:
+        pc = capi.Parse.from_file(path, region="chr22")
+        assert pc.info.compressed_bytes == 0 and np.array_equal(pc.matrix()[1], p.matrix()[1])
+    finally:
+        del os.environ["HB_CPU_INFLATE"]
     ora = oracle.parse_text(text, "*", "chr22")
     g0, g1 = p.matrix()
     assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])

@@ -134,3 +134,44 @@ def test_tiny_and_empty(capi):
     p = capi.Parse.from_host(synth.body_of(one), 2, region="chrNope")
     fr = p.compress(0)
     assert fr.info.n_chunks == 0 and fr.info.total_bytes == 0
+
+
+def test_slab_streaming_rerun_with_other_record_counts(capi):
+    """The streaming form used for inputs larger than HBM (tools/config4_stream.py): ONE device text buffer and ONE
+    frames handle are re-used for slabs whose kept-record counts differ (explicit chunk_records keeps the chunk
+    geometry); every slab's frames still decode to that slab's records."""
+    import torch
+    S, cr = 70, 64
+    specs = [capi.synth_spec(nv, S, seed=50 + k, mix=1, first_pos=10_000_000 + 100_000 * k) for k, nv in enumerate((900, 1000, 760, 1030))]
+    cap = max(int(capi.lib().hb_synth_body_bytes(sp)) for sp in specs)
+    text = torch.zeros(cap + 256, dtype=torch.uint8, device="cuda")
+    p = fr = None
+    seen = set()
+    for sp in specs:
+        T = int(capi.lib().hb_synth_body_bytes(sp))
+        capi.check(capi.lib().hb_synth_device(sp, text.data_ptr(), T, 0, None))
+        text[T:T + 256].zero_()
+        torch.cuda.synchronize()
+        if p is None:
+            p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr22")
+            fr = p.compress(cr)
+            p.attach(fr)
+        else:
+            capi.check(capi.lib().hb_parse_rerun_bytes(p._h, T))
+            fr.rerun(p)
+        ora = oracle.parse_text(capi.synth_header(sp) + capi.synth_host(sp), "*", "chr22")
+        assert p.info.n_records == ora["n"] == fr.info.n_records and fr.info.chunk_records == cr
+        seen.add(ora["n"])
+        for s in (0, S - 1):
+            exp = _expected_chunks(ora, s, cr)
+            frames = fr.sample(s)
+            assert len(frames) == len(exp) == fr.info.n_chunks
+            for f, e in zip(frames, exp):
+                assert oracle.cframe_decode(f, len(e)).tobytes() == e
+    assert len(seen) > 1                                   # the record count really changed between slabs
+    p.attach(None)
+    with pytest.raises(capi.HaploError):                   # without explicit chunk_records the geometry follows n_records
+        q = capi.Parse.from_host(synth.body_of(capi.synth_header(specs[0]) + capi.synth_host(specs[0])), S, region="chr22")
+        f2 = q.compress(0)
+        q2 = capi.Parse.from_host(synth.body_of(capi.synth_header(specs[2]) + capi.synth_host(specs[2])), S, region="chr22")
+        f2.rerun(q2)
