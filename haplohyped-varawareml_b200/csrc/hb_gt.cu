@@ -17,6 +17,8 @@
 //   * the tile is written out as 16-byte vectors, kTV contiguous bytes per (plane, sample).
 // Output layout = the Blosc2 byte-shuffled layout of the reference's 35-byte records
 // (planes 33 and 34 of every chunk), see DESIGN.md.
+#include <cstdlib>
+
 #include "hb_common.cuh"
 #include "hb_internal.h"
 
@@ -101,7 +103,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                  uint32_t n_samples, uint32_t n_stiles, const uint64_t *__restrict__ cp, uint32_t ncp,
                  int8_t *__restrict__ gt0, int8_t *__restrict__ gt1, uint64_t gt_stride,
                  uint32_t *__restrict__ ploidy_err, uint32_t *__restrict__ badgt_err,
-                 DevStatus *__restrict__ st) {
+                 DevStatus *__restrict__ st, uint32_t pf_dist) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     GtSmem &sm = *reinterpret_cast<GtSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,6 +124,8 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     __syncthreads();
 
     // ---- phase 0: locate each record's segment; stage uniform ones with TMA
+    uint64_t pf_addr = 0;
+    uint32_t pf_bytes = 0;
     if (tid < kTV) {
         int mode = 0;
         uint64_t b = 0;
@@ -145,6 +149,22 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                         len = (uint32_t)(ee - bb);
                         mode = (len == 4u * ns && g == 0) ? 1 : 2;
                     }
+                }
+            }
+        }
+        // The tile that will run in this CTA's slot once it retires (pf_dist tiles ahead = resident CTAs of the whole
+        // GPU): its text is pulled into L2 now (UBLKPF), so that CTA's TMA loads find it there instead of in DRAM.
+        const uint64_t tf = tile + pf_dist;
+        if (pf_dist && tf < gridDim.x) {
+            const uint32_t s0f = (uint32_t)(tf % n_stiles) * kTS;
+            const uint64_t rf = (tf / n_stiles) * kTV + tid;
+            if (rf < n_rows) {
+                const RowInfo rif = rowinfo[rf];
+                if ((rif.misc & kRowHasSamples) && (rif.misc & kRowUniform) && (rif.misc & 0xffu) != 255u) {
+                    const uint64_t bf = rif.samp_abs + 4ull * s0f;
+                    const uint32_t nsf = min((uint32_t)kTS, n_samples - s0f);
+                    pf_addr = bf & ~15ull;
+                    pf_bytes = (uint32_t)(((bf & 15ull) + 4u * nsf + 15ull) & ~15ull);
                 }
             }
         }
@@ -173,6 +193,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
             uint32_t bytes = (uint32_t)(((b & 15ull) + sm.seg_len[tid] + 15ull) & ~15ull);
             tma_load_1d(sm.text[tid], text + (b & ~15ull), bytes, &sm.bar);
         }
+        if (pf_bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(text + pf_addr), "r"(pf_bytes) : "memory");
         mbar_wait(&sm.bar, 0);
     }
 
@@ -304,9 +325,11 @@ void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t 
     uint32_t n_stiles = (n_samples + kTS - 1) / kTS;
     uint64_t n_rtiles = (n_rows + kTV - 1) / kTV;
     uint64_t tiles = n_rtiles * n_stiles;
+    uint32_t pf_dist = 4u * (uint32_t)L.sm_count;            // 4 CTAs per SM are resident (__launch_bounds__)
+    if (const char *e = getenv("HB_GT_PREFETCH")) pf_dist = (uint32_t)atoi(e);
     decode_gt_kernel<<<(unsigned)tiles, GT_THREADS, smem, L.stream>>>(d_text, d_rowinfo, n_rows, n_samples, n_stiles,
                                                                       d_cp, ncp, d_gt0, d_gt1, gt_stride,
-                                                                      d_ploidy_err, d_badgt_err, d_st);
+                                                                      d_ploidy_err, d_badgt_err, d_st, pf_dist);
     count_launch();
 }
 
