@@ -72,7 +72,7 @@ EXPORTS = [
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
-    "hb_compress_records", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
+    "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_decode_frames",
     "hb_encode_haplotypes",
@@ -119,6 +119,9 @@ def lib():
             L.hb_compress_records.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
             L.hb_frames_get_info.argtypes = [C.c_void_p, C.POINTER(FramesInfo)]
             L.hb_frames_rerun.argtypes = [C.c_void_p, C.c_void_p]
+            L.hb_compress_sample_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+            L.hb_frames_set_window.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+            L.hb_parse_release_text.argtypes = [C.c_void_p]
             L.hb_parse_attach_frames.argtypes = [C.c_void_p, C.c_void_p]
             L.hb_frames_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.hb_frames_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -277,10 +280,17 @@ class Parse:
         """Overlap the frames' site-template kernel with the GT decoder on every rerun (hb_parse_attach_frames)."""
         check(lib().hb_parse_attach_frames(self._h, frames._h if frames is not None else None))
 
-    def compress(self, chunk_records: int = 0) -> "Frames":
+    def compress(self, chunk_records: int = 0, s0: int = 0, ns: int | None = None) -> "Frames":
+        """Blosc2 frames of samples [s0, s0 + ns) (default: all)."""
         h = C.c_void_p()
-        check(lib().hb_compress_records(self._h, chunk_records, C.byref(h)))
+        if ns is None and s0 == 0:
+            check(lib().hb_compress_records(self._h, chunk_records, C.byref(h)))
+        else:
+            check(lib().hb_compress_sample_range(self._h, chunk_records, s0, self.info.n_samples - s0 if ns is None else ns, C.byref(h)))
         return Frames(h)
+
+    def release_text(self):
+        check(lib().hb_parse_release_text(self._h))
 
     def close(self):
         if self._h:
@@ -308,6 +318,10 @@ class Frames:
 
     def rerun(self, parse: "Parse"):
         check(lib().hb_frames_rerun(self._h, parse._h))
+
+    def set_window(self, s0: int, ns: int):
+        """Move the sample window (ns <= the window the frames were made for); then rerun(parse)."""
+        check(lib().hb_frames_set_window(self._h, s0, ns))
 
     def layout(self):
         """(offsets uint64 [n_samples, n_chunks] into the frame buffer, sizes uint32 [n_samples, n_chunks])"""

@@ -519,8 +519,22 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
     return HB_OK;
 }
 
+int hb_parse_release_text(hb_parse *p) {
+    if (!p) return fail(HB_ERR_ARG, "null handle");
+    if (p->d_text_owned) {
+        CU(cudaSetDevice(p->device));
+        cudaFree(p->d_text_owned);
+        p->d_text_owned = nullptr;
+        p->d_text = nullptr;
+        p->nbytes = 0;
+        p->text_released = true;
+    }
+    return HB_OK;
+}
+
 int hb_parse_rerun(hb_parse *p) {
     if (!p) return fail(HB_ERR_ARG, "null handle");
+    if (p->text_released) return fail(HB_ERR_ARG, "the text of this parse was released");
     return run_parse(p);
 }
 

@@ -15,6 +15,7 @@ struct hb_parse {
     int sm_count = 148;
     const uint8_t *d_text = nullptr;
     uint8_t *d_text_owned = nullptr;
+    bool text_released = false;         // hb_parse_release_text: the results stay, a re-run is no longer possible
     uint64_t nbytes = 0;
     uint32_t n_samples = 0;
     hb::RegionArg rg;

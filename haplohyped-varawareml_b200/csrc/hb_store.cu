@@ -699,7 +699,8 @@ struct hb_frames {
     uint64_t n_records = 0, n_chunks = 0, cr = 0;
     uint64_t chunk_cap = 0;                  // chunks the per-chunk arrays were allocated for
     bool cr_explicit = false;                // chunk_records was given by the caller (it does not follow n_records)
-    uint32_t n_samples = 0, tmpl_cap = 0;
+    uint32_t n_samples = 0, tmpl_cap = 0;    // n_samples: samples of the current window
+    uint32_t s0 = 0, win_cap = 0;            // window = samples [s0, s0 + n_samples) of the parse; win_cap = allocated for
     size_t smem_site = 0;
     FusedArgs fa;                            // geometry of the fused kernel
     int nw = 1;
@@ -810,7 +811,7 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     CUF(cudaMemcpyAsync(f->d_slot_off, f->h_slot_off.data(), (f->n_chunks + 1) * 8, cudaMemcpyHostToDevice, f->stream));
     FusedArgs fa = f->fa;
     fa.gt0 = p->d_gt[0]; fa.gt1 = p->d_gt[1]; fa.gt_stride = p->gt_stride; fa.n_records = n;
-    fa.cr = cr; fa.n_samples = f->n_samples; fa.s0 = 0; fa.n_chunks = f->n_chunks;
+    fa.cr = cr; fa.n_samples = f->n_samples; fa.s0 = f->s0; fa.n_chunks = f->n_chunks;
     fa.tmpl = f->d_tmpl; fa.tmpl_cap = f->tmpl_cap; fa.tmpl_len = f->d_tmpl_len;
     fa.frames = f->d_frames; fa.slot_off = f->d_slot_off; fa.size = f->d_size; fa.totals = f->d_totals;
     switch (f->nw) {
@@ -870,15 +871,21 @@ void hb_frames_free(hb_frames *f) {
 }
 
 int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out) {
+    if (!p) return api_fail(HB_ERR_ARG, "null argument");
+    return hb_compress_sample_range(p, chunk_records, 0, p->n_samples, out);
+}
+
+int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, uint32_t ns, hb_frames **out) {
     if (!p || !out) return api_fail(HB_ERR_ARG, "null argument");
     *out = nullptr;
+    if ((uint64_t)s0 + ns > p->n_samples) return api_fail(HB_ERR_ARG, "sample window outside the parse");
     if (cudaSetDevice(p->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
     const uint64_t n = p->h_st.n_records;
     if (!p->d_gt[0] && n) return api_fail(HB_ERR_NOGT, "parse was made without genotypes");
     hb_frames *f = new hb_frames();
     memset(&f->fa, 0, sizeof f->fa);
     f->device = p->device; f->stream = p->stream;
-    f->n_records = n; f->n_samples = p->n_samples;
+    f->n_records = n; f->n_samples = ns; f->s0 = s0; f->win_cap = ns;
     f->cr = chunk_records ? chunk_records : guess_chunk_records(n);
     f->cr_explicit = chunk_records != 0;
     f->n_chunks = n ? (n + f->cr - 1) / f->cr : 0;
@@ -944,7 +951,7 @@ int hb_parse_attach_frames(hb_parse *p, hb_frames *f) {
 
 int hb_frames_rerun(hb_frames *f, hb_parse *p) {
     if (!f || !p) return api_fail(HB_ERR_ARG, "null argument");
-    if (p->n_samples != f->n_samples || p->device != f->device)
+    if ((uint64_t)f->s0 + f->n_samples > p->n_samples || p->device != f->device)
         return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
     if (p->h_st.n_records != f->n_records) {
         // another record count is fine when the chunk size was fixed by the caller and the chunk arrays are large enough
@@ -960,6 +967,16 @@ int hb_frames_rerun(hb_frames *f, hb_parse *p) {
     }
     if (!f->n_chunks || !f->n_samples) return HB_OK;
     return frames_run(f, p);
+}
+
+int hb_frames_set_window(hb_frames *f, uint32_t s0, uint32_t ns) {
+    if (!f) return api_fail(HB_ERR_ARG, "null handle");
+    if (ns == 0 || ns > f->win_cap) return api_fail(HB_ERR_ARG, "window larger than the one the frames were made for");
+    f->s0 = s0;
+    f->n_samples = ns;
+    f->n_ctas = (f->n_chunks * (uint64_t)ns + kWpc - 1) / kWpc;
+    f->layout_valid = false;
+    return HB_OK;
 }
 
 int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {

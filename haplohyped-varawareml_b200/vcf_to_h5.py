@@ -43,17 +43,47 @@ def _configure_logging():
 
 
 class _ChromParse:
-    """One chromosome file: device-resident parse + Blosc2 frames of every donor's chunks."""
+    """One chromosome file: device-resident parse + Blosc2 frames of the donors' chunks.
 
-    def __init__(self, data_path: str, chromosome: int, device: int):
+    The frames of ALL donors of a big chromosome may not fit in HBM next to the genotype planes (1000G chr1: 64 GB of
+    text, 32 GB of planes, ~100 GB of frames), so the text is given back right after the parse and the frames are made
+    for a WINDOW of samples at a time; the window is as large as free HBM allows -- all samples for anything chr22-sized."""
+
+    def __init__(self, data_path: str, chromosome: int, device: int, window: Optional[int] = None):
         self.parse = capi.Parse.from_file(data_path, region=f"chr{chromosome}", want_gt=True, device=device)
         self.samples = self.parse.sample_names()
         self.index = {s: i for i, s in enumerate(self.samples)}
         info = self.parse.info
         self.n_records = int(info.n_records)
         self.ploidy_err, self.badgt_err = self.parse.sample_errors()
-        self.frames = self.parse.compress(0) if self.n_records else None
-        self.chunk_records = int(self.frames.info.chunk_records) if self.frames else 0
+        self.parse.release_text()
+        self.frames = None
+        self.win0 = self.win_n = 0
+        self.chunk_records = int(capi.lib().hb_guess_chunk_records(max(1, self.n_records))) if self.n_records else 0
+        n = len(self.samples)
+        if window is None and self.n_records and n:
+            import torch
+            free, _ = torch.cuda.mem_get_info(device)
+            est_row = int(0.25 * 35 * self.n_records) + (1 << 16)         # slots are ~0.2 x the raw record bytes per sample
+            window = max(1, min(n, int(0.8 * free / est_row)))
+        self.window = max(1, min(n, window or n)) if n else 0
+
+    def windows(self):
+        """(s0, ns) of every sample window."""
+        return [(s0, min(self.window, len(self.samples) - s0)) for s0 in range(0, len(self.samples), max(1, self.window))]
+
+    def frames_for(self, s0: int, ns: int):
+        """Frames handle positioned on samples [s0, s0 + ns): made on first use, re-run when the window moves."""
+        if not self.n_records:
+            return None
+        if self.frames is None:
+            self.frames = self.parse.compress(0, 0, self.window)           # window 0; also fixes the allocation
+            self.win0, self.win_n = 0, self.window
+        if (s0, ns) != (self.win0, self.win_n):
+            self.frames.set_window(s0, ns)
+            self.frames.rerun(self.parse)
+            self.win0, self.win_n = s0, ns
+        return self.frames
 
     def donor_frames(self, donor_id: str):
         if donor_id not in self.index:
@@ -63,7 +93,11 @@ class _ChromParse:
             raise RuntimeError("Error parsing VCF file: Couldn't read GT data: value not a number or '.'")
         if self.ploidy_err[s]:
             raise RuntimeError("Error parsing VCF file: ploidy != 2 (reference: assert(var.ploidy() == 2), parse_vcf.cpp:46)")
-        return self.frames.sample(s) if self.frames else []
+        if not self.n_records:
+            return []
+        s0 = s - s % self.window
+        fr = self.frames_for(s0, min(self.window, len(self.samples) - s0))
+        return fr.sample(s - s0)
 
     def close(self):
         if self.frames:
@@ -73,7 +107,8 @@ class _ChromParse:
 
 class VCFtoHDF5Converter:
     def __init__(self, cohort_name: str, vcf_dir: str, out_dir: str, sample_list_path: str, cores: int,
-                 cxx_threads: int, device: int = 0, chromosomes=None, backend: Optional[str] = None):
+                 cxx_threads: int, device: int = 0, chromosomes=None, backend: Optional[str] = None,
+                 sample_window: Optional[int] = None):
         self.cohort_name = cohort_name
         self.vcf_dir = vcf_dir
         self.out_dir = out_dir
@@ -82,6 +117,7 @@ class VCFtoHDF5Converter:
         self.cxx_threads = cxx_threads            # kept for interface parity; a no-op in the reference too
         self.device = device
         self.backend = backend
+        self.sample_window = sample_window        # None: as many samples per frames pass as free HBM allows
         self.donor_ids = self.read_sample_list(sample_list_path)
         self.chromosomes = range(1, 23) if chromosomes is None else chromosomes
         self.tmp_dir = os.path.join(out_dir, "tmp_files")
@@ -111,7 +147,7 @@ class VCFtoHDF5Converter:
     def _chrom_parse(self, data_path: str, chromosome: int) -> _ChromParse:
         cp = self._chrom.get(chromosome)
         if cp is None:
-            cp = _ChromParse(data_path, chromosome, self.device)
+            cp = _ChromParse(data_path, chromosome, self.device, self.sample_window)
             self._chrom[chromosome] = cp
         return cp
 
@@ -142,19 +178,24 @@ class VCFtoHDF5Converter:
             return
         cp = self._chrom_parse(vcf_file, chromosome)
         good = [d for d in self.donor_ids if d in cp.index and not cp.badgt_err[cp.index[d]] and not cp.ploidy_err[cp.index[d]]]
-        bulk = cp.frames is not None and len(good) * 4 >= len(cp.samples) and hasattr(self._final(), "write_frames_bulk")
+        bulk = cp.n_records > 0 and len(good) * 4 >= len(cp.samples) and hasattr(self._final(), "write_frames_bulk")
         if bulk:
-            # the frames of ALL donors leave the GPU in one copy and enter the file with one write; each dataset's
-            # chunk index then points into that block (no per-chunk work on the host)
-            buf = cp.frames.fetch_all()
-            offs, sizes = cp.frames.layout()
-            rows = [cp.index[d] for d in good]
-            self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in good], RECORD_DTYPE,
-                                            cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])
-            self.stats["datasets"] += len(good)
-            self.stats["records"] += cp.n_records * len(good)
-            self.stats["stored_bytes"] += int(sizes[rows].sum())
-            del buf
+            # window by window: the frames of all its donors leave the GPU in one copy and enter the file with one write;
+            # each dataset's chunk index then points into that block (no per-chunk work on the host)
+            for s0, ns in cp.windows():
+                mine = [d for d in good if s0 <= cp.index[d] < s0 + ns]
+                if not mine:
+                    continue
+                fr = cp.frames_for(s0, ns)
+                buf = fr.fetch_all()
+                offs, sizes = fr.layout()
+                rows = [cp.index[d] - s0 for d in mine]
+                self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in mine], RECORD_DTYPE,
+                                                cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])
+                self.stats["datasets"] += len(mine)
+                self.stats["records"] += cp.n_records * len(mine)
+                self.stats["stored_bytes"] += int(sizes[rows].sum())
+                del buf
         done = set(good) if bulk else set()
         for donor_id in self.donor_ids:
             if donor_id in done:
@@ -224,7 +265,7 @@ class VCFtoHDF5Converter:
     def _safe_parse(self, chromosome: int):
         vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
         try:
-            return _ChromParse(vcf_file, chromosome, self.device)
+            return _ChromParse(vcf_file, chromosome, self.device, self.sample_window)
         except capi.HaploError as e:
             logger.error(f"An error occurred while processing VCF file: Error parsing VCF file: {e}")
             self.stats["skipped_files"] += 1

@@ -128,6 +128,9 @@ int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64
 int hb_parse_rerun(hb_parse *p);
 /* the same for a handle made by hb_parse_device_text whose buffer now holds nbytes of (other) text: slab streaming */
 int hb_parse_rerun_bytes(hb_parse *p, uint64_t nbytes);
+/* give the text buffer of a host-text / file parse back (a 64 GB chromosome needs the HBM for its frames); every result
+ * stays valid, only hb_parse_rerun is no longer possible */
+int hb_parse_release_text(hb_parse *p);
 int hb_parse_get_info(const hb_parse *p, hb_parse_info *info);
 /* host copies.  Any pointer may be NULL.  chrom names: see hb_parse_chrom_runs. */
 int hb_parse_fetch_sites(hb_parse *p, uint32_t *start, uint32_t *stop, char *ref, char *alt);
@@ -175,6 +178,11 @@ typedef struct hb_frames_info {
  * [sample][chunk] with every frame starting on a 16-byte boundary: a sample's dataset is one contiguous
  * byte range, and the whole buffer can be written to the HDF5 file with one write. */
 int hb_compress_records(hb_parse *p, uint64_t chunk_records, hb_frames **out);
+/* the same for samples [s0, s0 + ns) only: when all frames of a big chromosome do not fit in HBM next to the genotype
+ * planes, the converter walks a window over the samples -- hb_frames_set_window(f, s0', ns' <= ns) + hb_frames_rerun.
+ * Sample indices of hb_frames_layout / hb_frames_fetch_sample are relative to the window. */
+int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, uint32_t ns, hb_frames **out);
+int hb_frames_set_window(hb_frames *f, uint32_t s0, uint32_t ns);
 /* Attach frames to the parse they were made from (NULL detaches): from then on every hb_parse_rerun of p also
  * starts the site-template kernel of f, on a side stream, as soon as the site columns exist -- it overlaps the GT
  * decoder instead of following it.  hb_frames_rerun then only runs what needs the genotype planes.  The frames must

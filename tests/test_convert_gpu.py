@@ -146,3 +146,46 @@ def test_dataset_from_files(mods, tmp_path):
         assert np.array_equal(h1[b].cpu().numpy(), oracle.onehot(a, 5))
         assert np.array_equal(h2[b].cpu().numpy(), oracle.onehot(bb, 5))
     ds.close()
+
+
+def test_sample_windows_give_the_same_file_contents(mods, tmp_path):
+    """Big chromosomes are converted a window of samples at a time (frames of all donors would not fit in HBM next to
+    the genotype planes): any window size must store the same records; frames API: window-relative sample indices."""
+    capi, container, h5_reader, hd, v2h = mods
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    text, samples = synth.random_vcf(2100, 23, seed=8, fmt="GT", kinds="mixed", chrom="chr3", site_mix=True)
+    with open(vdir / "chr3.filtered.vcf.gz", "wb") as f:
+        f.write(synth.bgzf_compress(text, 6))
+    (tmp_path / "donors.txt").write_text("\n".join(samples))
+    got = {}
+    for w in (None, 5, 1):
+        out = tmp_path / f"o{w}"
+        conv = v2h.VCFtoHDF5Converter("c", str(vdir), str(out), str(tmp_path / "donors.txt"), 2, 4, chromosomes=[3], sample_window=w)
+        conv.run()
+        assert conv.stats["datasets"] == 23
+        rd = h5_reader.VCFH5Reader(str(out / "c.h5"))
+        got[w] = {d: rd.fetch_genotypes(d, 3).tobytes() for d in samples}
+        rd.close()
+    ora = oracle.parse_text(text, "*", "chr3")
+    for k, d in enumerate(samples):
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][k], ora["gt1"][k])
+        assert got[None][d] == rec.tobytes() and got[5][d] == got[None][d] and got[1][d] == got[None][d]
+    # the window API directly: frames of samples [7, 12) equal the same samples of an all-sample pass
+    p = capi.Parse.from_host(synth.body_of(text), 23, region="chr3")
+    allf = p.compress(0)
+    win = p.compress(0, 7, 5)
+    assert win.info.n_samples == 5
+    for k in range(5):
+        assert win.sample(k) == allf.sample(7 + k)
+    win.set_window(18, 5)
+    win.rerun(p)
+    assert win.sample(4) == allf.sample(22)
+    with pytest.raises(capi.HaploError):
+        win.set_window(0, 6)
+    p.release_text()
+    with pytest.raises(capi.HaploError):
+        p.rerun()
+    win.set_window(2, 3)
+    win.rerun(p)                                             # frames only need the planes, not the text
+    assert win.sample(0) == allf.sample(2)
