@@ -416,6 +416,7 @@ struct FusedArgs {
     uint32_t caps;      // sequence slots per lane
     uint32_t dcap;      // literal-run descriptors per frame (non-empty runs only)
     uint32_t outcap;    // bytes of the frame-tail buffer
+    uint32_t pf_dist;   // frames between a warp and the one that will follow it in its SM slot (0 = no L2 prefetch)
     uint32_t warp_smem;
 };
 
@@ -451,6 +452,15 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
         else { s = (uint32_t)(wid / A.n_chunks); c = wid % A.n_chunks; }
         sidx = s;
         tl = A.tmpl_len[c];
+        // the frame whose warp will take this warp's place when it retires: pull its two allele-plane slices into L2
+        if (A.pf_dist && lane < 2 && wid + A.pf_dist < n_frames) {
+            const uint64_t wf = wid + A.pf_dist;
+            const uint64_t sf = wf / A.n_chunks, cf = wf - sf * A.n_chunks;
+            const uint64_t rf = cf * (uint64_t)cr;
+            const uint64_t off = (uint64_t)(A.s0 + sf) * A.gt_stride + (rf & ~15ull);
+            const uint32_t bytes = (uint32_t)((((rf & 15ull) + min((uint64_t)cr, A.n_records - rf) + 15ull) & ~15ull));
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((lane ? A.gt1 : A.gt0) + off), "r"(bytes) : "memory");
+        }
         // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
         const uint64_t r0 = c * (uint64_t)cr;
         alpha = (int)(r0 & 15);
@@ -814,6 +824,15 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     fa.cr = cr; fa.n_samples = f->n_samples; fa.s0 = f->s0; fa.n_chunks = f->n_chunks;
     fa.tmpl = f->d_tmpl; fa.tmpl_cap = f->tmpl_cap; fa.tmpl_len = f->d_tmpl_len;
     fa.frames = f->d_frames; fa.slot_off = f->d_slot_off; fa.size = f->d_size; fa.totals = f->d_totals;
+    {
+        int sms = 148, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
+        // resident warps of this kernel on the whole GPU (shared memory decides): the distance to prefetch at
+        const size_t smem_cta = (size_t)kWpc * fa.warp_smem + 1024;
+        per_sm = (int)std::min<size_t>(32 / 1, (227 * 1024) / smem_cta);
+        fa.pf_dist = (uint32_t)(sms * per_sm * kWpc);
+        if (const char *e = getenv("HB_DF_PREFETCH")) fa.pf_dist = (uint32_t)atoi(e);
+    }
     switch (f->nw) {
         case 1: launch_donor_frames<1>(fa, f->n_ctas, f->stream); break;
         case 2: launch_donor_frames<2>(fa, f->n_ctas, f->stream); break;

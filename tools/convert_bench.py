@@ -9,6 +9,7 @@ from haplohyped_varawareml_b200 import capi, h5_reader, vcf_to_h5
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 2504
 root = sys.argv[3] if len(sys.argv) > 3 else tempfile.mkdtemp()
+window = int(sys.argv[4]) if len(sys.argv) > 4 else None          # samples per frames pass (None: as many as HBM allows)
 vdir = os.path.join(root, "vcf"); os.makedirs(vdir, exist_ok=True)
 spec = capi.synth_spec(V, S, seed=42)
 text = np.frombuffer(capi.synth_header(spec) + capi.synth_host(spec), np.uint8)
@@ -19,11 +20,11 @@ open(os.path.join(root, "samples.txt"), "w").write("\n".join(names))
 capi.Parse.from_host(b"chr22\t5\t.\tA\tC\t.\t.\t.\tGT\t0|1\n", 1).close()      # CUDA context + module load outside the timing
 t0 = time.time()
 conv = vcf_to_h5.VCFtoHDF5Converter("cohort", vdir, os.path.join(root, "out"), os.path.join(root, "samples.txt"), os.cpu_count(), 4,
-                                    chromosomes=[22])
+                                    chromosomes=[22], sample_window=window)
 conv.run()
 t1 = time.time()
 out = os.path.join(root, "out", "cohort.h5")
-res = {"variants": V, "samples": S, "text_bytes": int(text.size), "bgzf_bytes": int(bg.size), "h5_bytes": os.path.getsize(out),
+res = {"variants": V, "samples": S, "sample_window": window, "text_bytes": int(text.size), "bgzf_bytes": int(bg.size), "h5_bytes": os.path.getsize(out),
        "convert_s": t1 - t0, "records_per_s": conv.stats["records"] / (t1 - t0), "variants_per_s": V / (t1 - t0),
        "datasets": conv.stats["datasets"], "stored_bytes": conv.stats["stored_bytes"],
        "ratio": 35.0 * conv.stats["records"] / max(1, conv.stats["stored_bytes"]),
