@@ -13,6 +13,10 @@
 // composed in shared memory (window gather through a 256-entry LUT, then the item's records in
 // range -- found by binary search in the sorted start column -- scattered on top), and the
 // float32 one-hot rows are streamed out as 16-byte vectors.  HBM-write bound: 2*B*L*C*4 bytes.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "../../include/haplo_b200.h"
 #include "hb_common.cuh"
 #include "hb_internal.h"
@@ -30,8 +34,21 @@ __device__ __forceinline__ uint64_t lower_bound_u32(const uint32_t *a, uint64_t 
     return lo;
 }
 
+// Record range of every tile, found once per tile boundary by one thread each (a binary search is ~16 dependent
+// loads: done inside hap_kernel it was most of a CTA's lifetime).  rng[b * (ntiles + 1) + t] = first record of item b
+// at or after window position min(t * HP_TILE, len).
+__global__ void __launch_bounds__(256) hap_ranges_kernel(const hb_hap_batch a, uint32_t ntiles, uint64_t *__restrict__ rng) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint64_t)a.B * (ntiles + 1)) return;
+    const uint32_t b = (uint32_t)(i / (ntiles + 1)), t = (uint32_t)(i % (ntiles + 1));
+    const uint64_t nrec = a.item_nrec[b];
+    const uint64_t g = (uint64_t)a.item_win_start[b] + min((uint64_t)t * HP_TILE, (uint64_t)a.item_len[b]);
+    const uint32_t *start = reinterpret_cast<const uint32_t *>(a.item_start[b]);
+    rng[i] = (nrec == 0 || g > 0xffffffffull) ? nrec : lower_bound_u32(start, 0, nrec, (uint32_t)g);
+}
+
 template <int CC>   // CC > 0: compile-time class count; 0: runtime
-__global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
+__global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a, const uint64_t *__restrict__ rng, uint32_t ntiles) {
     __shared__ int8_t s_idx[2][HP_TILE];
     __shared__ int8_t s_lut[256];
     const int tid = threadIdx.x;
@@ -67,9 +84,7 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
             const int8_t *p1 = reinterpret_cast<const int8_t *>(a.item_p1[b]);
             const int8_t *p2 = reinterpret_cast<const int8_t *>(a.item_p2[b]);
             // genomic range [ws + tile0, ws + wend)
-            const uint64_t g0 = (uint64_t)ws + tile0, g1 = (uint64_t)ws + wend;
-            const uint64_t rb = g0 > 0xffffffffull ? nrec : lower_bound_u32(start, 0, nrec, (uint32_t)g0);
-            const uint64_t re = g1 > 0xffffffffull ? nrec : lower_bound_u32(start, rb, nrec, (uint32_t)g1);
+            const uint64_t rb = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x], re = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x + 1];
             for (uint64_t r = rb + tid; r < re; r += HP_THREADS) {
                 const uint32_t st = start[r];
                 if (r + 1 < nrec && start[r + 1] == st) continue;   // a later record at the same position wins
@@ -122,13 +137,38 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a) {
 
 using namespace hb;
 
+namespace {
+// scratch for the tile ranges: one buffer per (device, stream), grown on demand and kept (at most ~1 MB each).  Work on
+// one stream is ordered, so a launch never overwrites ranges that an earlier launch on the same stream still reads;
+// cudaMallocAsync would do too but costs ~200 us per call, ten times the kernel at small batches.
+struct RangeScratch { uint64_t *p = nullptr; uint64_t n = 0; };
+std::mutex g_rng_mu;
+std::map<std::pair<int, cudaStream_t>, RangeScratch> g_rng;
+}
+
 extern "C" int hb_encode_haplotypes(const hb_hap_batch *batch) {
     if (!batch || !batch->B || !batch->L || !batch->C) return HB_OK;
-    dim3 grid((batch->L + HP_TILE - 1) / HP_TILE, batch->B);
+    const uint32_t ntiles = (batch->L + HP_TILE - 1) / HP_TILE;
+    dim3 grid(ntiles, batch->B);
     cudaStream_t st = (cudaStream_t)batch->stream;
-    if (batch->C == 5) hap_kernel<5><<<grid, HP_THREADS, 0, st>>>(*batch);
-    else if (batch->C == 4) hap_kernel<4><<<grid, HP_THREADS, 0, st>>>(*batch);
-    else hap_kernel<0><<<grid, HP_THREADS, 0, st>>>(*batch);
-    count_launch();
+    const uint64_t n_rng = (uint64_t)batch->B * (ntiles + 1);
+    uint64_t *rng = nullptr;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(g_rng_mu);
+        RangeScratch &sc = g_rng[{dev, st}];
+        if (sc.n < n_rng) {
+            if (sc.p) { cudaStreamSynchronize(st); cudaFree(sc.p); sc.p = nullptr; sc.n = 0; }
+            if (cudaMalloc(&sc.p, (n_rng + n_rng / 4 + 64) * 8) != cudaSuccess) return HB_ERR_MEM;
+            sc.n = n_rng + n_rng / 4 + 64;
+        }
+        rng = sc.p;
+    }
+    hap_ranges_kernel<<<(unsigned)((n_rng + 255) / 256), 256, 0, st>>>(*batch, ntiles, rng);
+    if (batch->C == 5) hap_kernel<5><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
+    else if (batch->C == 4) hap_kernel<4><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
+    else hap_kernel<0><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
+    count_launch(2);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
