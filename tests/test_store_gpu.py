@@ -175,3 +175,34 @@ def test_slab_streaming_rerun_with_other_record_counts(capi):
         f2 = q.compress(0)
         q2 = capi.Parse.from_host(synth.body_of(capi.synth_header(specs[2]) + capi.synth_host(specs[2])), S, region="chr22")
         f2.rerun(q2)
+
+
+def _pattern_vcf(n_variants, columns):
+    """VCF whose sample k has the GT sequence columns[k](i) for record i (all records biallelic SNPs)."""
+    S = synth.sample_names(len(columns))
+    out = [synth.header(S)]
+    for i in range(n_variants):
+        out.append("\t".join(["chr22", str(1000 + 3 * i), ".", "ACGT"[i % 4], "CGTA"[i % 4], ".", "PASS", ".", "GT"] +
+                             [f(i) for f in columns]) + "\n")
+    return "".join(out).encode(), S
+
+
+def test_allele_plane_encoder_on_degenerate_and_hostile_planes(capi):
+    """The bit-parallel allele encoder is exact for ANY plane bytes: all zero / all one / all missing planes (one long
+    match, or no match at all), period-2 and period-5 patterns, zero runs of every length 1..40 around single ones,
+    runs ending exactly at segment and plane ends, multi-digit alleles (bytes with other bits set, incl. negative int8),
+    hom/het structure between the two planes."""
+    import random
+    rng = random.Random(4)
+    cols = [
+        lambda i: "0|0", lambda i: "1|1", lambda i: "./.", lambda i: "0|1", lambda i: "1|0",
+        lambda i: "%d|%d" % (i & 1, (i >> 1) & 1), lambda i: "%d|%d" % (i % 5 == 0, i % 5 == 3),
+        lambda i: "%d|0" % (1 if any(i == k * (k + 3) // 2 for k in range(60)) else 0),      # zero runs of growing length
+        lambda i: "0|%d" % (i % 67 == 66), lambda i: "%d|%d" % (i % 68 == 0, i % 68 == 67),  # run ends at segment ends (cr 1075 -> 68)
+        lambda i: "10|200", lambda i: "%s|%s" % (rng.choice(["0", "1", "12", "127", "255", "."]), rng.choice(["0", "1", "7", "128"])),
+        lambda i: "1|1" if (i // 97) & 1 else "0|0", lambda i: ".|1" if i % 11 == 0 else "0|0",
+        lambda i: "%d|%d" % (rng.random() < 0.02, rng.random() < 0.02), lambda i: "%d|%d" % (rng.random() < 0.5, rng.random() < 0.5),
+    ]
+    text, samples = _pattern_vcf(2300, cols)
+    for cr in (1075, 0, 64, 6, 2300):
+        _check(capi, text, len(samples), "chr22", cr, list(range(len(samples))))
