@@ -252,6 +252,17 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 uint4 v = *reinterpret_cast<const uint4 *>(text + o);
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             }
+            // the 512 bytes (+ 16 of look-ahead) also go to this record's row of the staging buffer, which the general
+            // path does not use otherwise: the common field shape "X|Y" + terminator is then decoded from shared memory
+            // with one unaligned 4-byte read instead of a byte-wise parse over global memory
+            uint8_t *row = sm.text[r];
+            *reinterpret_cast<uint4 *>(row + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (lane == 0) {
+                uint4 x = make_uint4(0, 0, 0, 0);
+                if (base + 512 < e + 4) x = *reinterpret_cast<const uint4 *>(text + base + 512);
+                *reinterpret_cast<uint4 *>(row + 512) = x;
+            }
+            __syncwarp();
             uint32_t m[4], cnt = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -278,8 +289,18 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                     const int bit = __ffs(mm) - 1;
                     mm &= mm - 1;
                     if (k < ns) {
-                        int a0, a1;
-                        const int pl = decode_field(text, o + 4ull * q + (bit >> 3) + 1, g, a0, a1);
+                        int a0, a1, pl;
+                        const int rel = 16 * lane + 4 * q + (bit >> 3) + 1;          // first byte of the field, in `row`
+                        const uint32_t *fw = reinterpret_cast<const uint32_t *>(row + (rel & ~3));
+                        const uint32_t x = __funnelshift_r(fw[0], fw[1], (rel & 3) * 8);
+                        const uint32_t X = x & 0xffu, sep = (x >> 8) & 0xffu, Y = (x >> 16) & 0xffu, T = x >> 24;
+                        const uint32_t dx = X - '0', dy = Y - '0';
+                        if (g == 0 && (sep == '|' || sep == '/') && (T == ':' || T == '\t' || T == '\n' || T == '\r') &&
+                            (dx <= 9u || X == '.') && (dy <= 9u || Y == '.')) {
+                            a0 = X == '.' ? -9 : (int)dx;
+                            a1 = Y == '.' ? -9 : (int)dy;
+                            pl = 2;
+                        } else pl = decode_field(text, o + 4ull * q + (bit >> 3) + 1, g, a0, a1);
                         if (pl < 0) { atomicAdd(&st->n_bad_gt, 1ull); atomicAdd(&badgt_err[s0 + k], 1u); a0 = 0; a1 = 0; }
                         else if (pl != 2) atomicAdd(&ploidy_err[s0 + k], 1u);
                         sm.out[0][k][r] = (uint8_t)a0;
@@ -289,6 +310,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 }
             }
             seen += __shfl_sync(0xffffffffu, inc, 31);
+            __syncwarp();                                     // the row is overwritten by the next 512 bytes
         }
         if (seen != ns) {
             if (lane == 0) atomicAdd(&st->n_bad_cols, 1ull);
