@@ -127,6 +127,16 @@ def test_long_segments_and_layout(capi, mix, chunk_records):
     assert np.array_equal(fr.fetch_all(), buf)
 
 
+def test_deep_site_matcher_is_smaller_and_exact(capi, monkeypatch):
+    """HB_SITE_MATCHER=deep: 4-way hash buckets in the site encoder -- same decoded bytes, smaller frames."""
+    spec = capi.synth_spec(6000, 40, seed=9)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    info_fast, total_fast = _check(capi, text, 40, "chr22", 1075, [0, 39])
+    monkeypatch.setenv("HB_SITE_MATCHER", "deep")
+    info_deep, total_deep = _check(capi, text, 40, "chr22", 1075, [0, 39])
+    assert total_deep < total_fast and info_deep.site_lz4_bytes < info_fast.site_lz4_bytes
+
+
 def test_tiny_and_empty(capi):
     S = ["a", "b"]
     one = (synth.header(S) + "chr22\t5\t.\tA\tC\t.\t.\t.\tGT\t0|1\t1|1\n").encode()
