@@ -24,10 +24,13 @@ HD uint64_t mix64(uint64_t x) {
 }
 HD uint64_t site_hash(uint64_t seed, uint64_t i) { return mix64(seed ^ mix64(i)); }
 HD uint64_t call_hash(uint64_t sh, uint32_t s) { return mix64(sh ^ mix64(0x5851F42D4C957F2Dull * (s + 1))); }
-HD uint32_t af_threshold(uint64_t sh) {       // ~ u^4: most sites rare, a few common (1000G-like skew)
+// ALT-allele frequency of a site ~ u^4 (u uniform): most sites rare, a few common -- mean 0.2, harsher than 1000G.
+// Bits 8-15 of spec.mix ask for more squarings (1: u^8, mean 0.11, about Beta(0.2, 2); 2: u^16, mean 0.06).
+HD uint32_t af_threshold(uint64_t sh, uint32_t mix) {
     uint64_t u = sh >> 32;
     u = (u * u) >> 32;
     u = (u * u) >> 32;
+    for (uint32_t k = (mix >> 8) & 0xffu; k; --k) u = (u * u) >> 32;
     return (uint32_t)u;
 }
 HD int ndigits(uint64_t v) {
@@ -49,7 +52,7 @@ HD SiteDesc site_desc(const hb_synth_spec &sp, uint64_t i, uint64_t sh) {
     int r = (int)(sh & 3), a = (r + 1 + (int)((sh >> 2) % 3)) & 3;
     d.ref[0] = B[r]; d.ref_len = 1;
     d.alt[0] = B[a]; d.alt_len = 1;
-    if (sp.mix == 1) {
+    if ((sp.mix & 0xffu) == 1) {
         uint32_t sk = (uint32_t)((sh >> 8) % 100);
         if (sk >= 90 && sk < 95) {                 // multiallelic: dropped by the SNP filter
             int a2 = (a + 1) & 3;
@@ -97,7 +100,7 @@ HD uint32_t call_word(const hb_synth_spec &sp, uint64_t sh, uint32_t thr, uint32
     uint32_t a = ((uint32_t)ch < thr) ? '1' : '0';
     uint32_t b = ((uint32_t)(ch >> 32) < thr) ? '1' : '0';
     uint32_t sep = '|';
-    if (sp.mix == 1) {
+    if ((sp.mix & 0xffu) == 1) {
         uint64_t k = mix64(ch);
         uint32_t ck = (uint32_t)(k % 100);
         if (ck == 0) sep = '/';
@@ -128,7 +131,7 @@ synth_kernel(const hb_synth_spec sp, int chrom_len, const uint64_t *__restrict__
         uint64_t sh = site_hash(sp.seed, i);
         SiteDesc d = site_desc(sp, i, sh);
         s_hl = write_head(sp, chrom_len, i, d, s_head);
-        s_thr = af_threshold(sh);
+        s_thr = af_threshold(sh, sp.mix);
         s_sh = sh;
     }
     __syncthreads();
@@ -220,7 +223,7 @@ int hb_synth_host(const hb_synth_spec *s, uint64_t first_variant, uint64_t n, ui
         SiteDesc d = site_desc(*s, i, sh);
         char *o = (char *)buf + off[k];
         uint32_t hl = write_head(*s, cl, i, d, o);
-        uint32_t thr = af_threshold(sh);
+        uint32_t thr = af_threshold(sh, s->mix);
         for (uint32_t sm = 0; sm < s->n_samples; ++sm) {
             uint32_t w = call_word(*s, sh, thr, sm);
             memcpy(o + hl + 4ull * sm, &w, 4);

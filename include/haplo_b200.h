@@ -244,8 +244,9 @@ typedef struct hb_synth_spec {
     uint32_t n_samples;
     uint64_t seed;
     uint32_t first_pos, pos_step;   /* POS_i = first_pos + i*pos_step + hash(i) % pos_step */
-    uint32_t mix;                   /* 0: config 2/3 (biallelic SNP, a|b); 1: config 4 (multiallelic,
-                                       indel, a/b, missing) */
+    uint32_t mix;                   /* bits 0-7: 0 config 2/3 (biallelic SNP, a|b); 1 config 4 (multiallelic,
+                                       indel, a/b, missing); bits 8-15: ALT-frequency skew, 0 = u^4 (mean 0.2, the
+                                       bench workload), 1 = u^8 (mean 0.11, about Beta(0.2, 2)), 2 = u^16 (mean 0.06) */
     char chrom[16];
 } hb_synth_spec;
 

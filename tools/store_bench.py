@@ -7,7 +7,7 @@ from haplohyped_varawareml_b200 import capi
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 1_100_000
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 2504
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-mix = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+mix = int(sys.argv[4]) if len(sys.argv) > 4 else 0            # bits 8-15: ALT-frequency skew (see hb_synth_spec)
 spec = capi.synth_spec(V, S, seed=42, mix=mix)
 T = int(capi.lib().hb_synth_body_bytes(spec))
 text = torch.empty(T + 256, dtype=torch.uint8, device="cuda")
@@ -26,4 +26,4 @@ for r in range(reps):
                       "padded": i.padded_bytes, "ratio": i.raw_bytes / max(1, i.total_bytes),
                       "ms_site": i.ms_site, "ms_frames": i.ms_frames,
                       "ms_total": ms, "alg_GBs": alg / ms / 1e6, "frames_alg_GBs": (2.0 * i.n_records * S + i.total_bytes) / max(1e-9, i.ms_frames) / 1e6,
-                      "bytes_per_frame": i.total_bytes / max(1, i.n_chunks * S), "site_lz4_per_chunk": i.site_lz4_bytes / max(1, i.n_chunks)}))
+                      "bytes_per_frame": i.total_bytes / max(1, i.n_chunks * S), "mix": mix, "site_lz4_per_chunk": i.site_lz4_bytes / max(1, i.n_chunks)}))
