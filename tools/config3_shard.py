@@ -1,0 +1,71 @@
+"""BASELINE configs[2]: a synthetic whole genome -- 3,000,000 variants x 2,504 samples in 22 chromosome files, variant counts
+proportional to GRCh38 chromosome lengths -- sharded BY CHROMOSOME over the ranks (LPT bin packing, shard.plan_shards), each
+rank pushing its chromosomes through the whole device path (locate -> sites -> GT decode -> Blosc2 frames); the only exchange
+is the all_gather of per-shard index metadata.  Strong scaling: the genome is fixed, N grows.
+    python tools/config3_shard.py                         (1 GPU)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/config3_shard.py
+"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from haplohyped_varawareml_b200 import capi, shard
+
+GRCH38_MB = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09, 133.28, 114.36, 107.04,
+             101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82]
+V_TOTAL = int(os.environ.get("C3_VARIANTS", 3_000_000))
+S = int(os.environ.get("C3_SAMPLES", 2504))
+REPS = int(os.environ.get("C3_REPS", 3))
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=dev)
+tot = sum(GRCH38_MB)
+nv = [int(round(V_TOTAL * m / tot)) for m in GRCH38_MB]
+nv[0] += V_TOTAL - sum(nv)
+plan = shard.plan_shards(nv, world)
+mine = plan[rank]
+specs = [capi.synth_spec(nv[c], S, seed=42 + c, chrom="chr%d" % (c + 1)) for c in mine]
+sizes = [int(capi.lib().hb_synth_body_bytes(sp)) for sp in specs]
+cap = max(sizes) if sizes else 0
+text = torch.empty(cap + 256, dtype=torch.uint8, device=dev)
+stream = torch.cuda.current_stream().cuda_stream
+
+def one_pass():
+    meta = {"n_records": 0, "n_lines": 0, "text_bytes": 0, "out_bytes": 0}
+    for sp, T, c in zip(specs, sizes, mine):
+        capi.check(capi.lib().hb_synth_device(sp, text.data_ptr(), T, local, None))
+        text[T:T + 256].zero_()
+        p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr%d" % (c + 1), device=local, stream=stream)
+        fr = p.compress(0)
+        i, fi = p.info, fr.info
+        meta["n_records"] += int(i.n_records); meta["n_lines"] += int(i.n_lines); meta["text_bytes"] += T; meta["out_bytes"] += int(fi.total_bytes)
+        fr.close(); p.close()
+    return shard.gather_metadata(meta, device=dev)
+
+one_pass()                                   # warm-up (allocator, module load)
+times = []
+for _ in range(REPS):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gathered = one_pass()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    times.append(float(dt.item()))
+if rank == 0:
+    t = sorted(times)[len(times) // 2]
+    recs = sum(g["n_records"] for g in gathered)
+    print(json.dumps({"config": "3M variants x 2504 samples, 22 chromosomes, sharded by chromosome (LPT)", "n_gpus": world,
+                      "variants": V_TOTAL, "samples": S, "records": recs, "text_bytes": sum(g["text_bytes"] for g in gathered),
+                      "c_out_bytes": sum(g["out_bytes"] for g in gathered), "seconds_max_over_ranks": t,
+                      "calls_per_s": V_TOTAL * S / t, "largest_bin_share": max(sum(nv[c] for c in b) for b in plan) / V_TOTAL,
+                      "includes": "on-device text generation, allocation and release of every chromosome's buffers (wall clock, max over ranks)"}))
+if world > 1:
+    dist.destroy_process_group()
