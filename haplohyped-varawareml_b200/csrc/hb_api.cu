@@ -1040,8 +1040,11 @@ void hb_records_free(hb_records *r) {
 }
 
 void hb_cache_clear(void) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_cache.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cache.clear();
+    }
+    hb::frames_buffer_cache_clear();
 }
 
 const char *hb_last_error(void) { return g_err.c_str(); }

@@ -69,4 +69,5 @@ struct hb_parse {
 namespace hb {
 // hb_store.cu: start the site-template kernel of the attached frames on their side stream (called by run_parse)
 void frames_early_site_pass(void *frames, hb_parse *p);
+void frames_buffer_cache_clear();       // hb_store.cu: release the kept frame buffers
 }

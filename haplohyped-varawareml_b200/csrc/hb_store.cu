@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -770,6 +771,22 @@ static cudaError_t attr_donor_frames(size_t smem) {
     return cudaFuncSetAttribute(donor_frames_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+// The frame buffer is many GB and cudaMalloc / cudaFree of that size cost ~100 ms (and cudaFree synchronises the device):
+// a released buffer is kept, one per device, for the next frames handle of the process (a converter walks 22 chromosomes).
+// hb_cache_clear() gives it back.
+namespace {
+struct BufCache { uint8_t *p = nullptr; uint64_t cap = 0; };
+std::mutex g_fb_mu;
+BufCache g_fb[64];
+}
+namespace hb {
+void frames_buffer_cache_clear() {
+    std::lock_guard<std::mutex> lk(g_fb_mu);
+    for (int d = 0; d < 64; ++d)
+        if (g_fb[d].p) { cudaSetDevice(d); cudaFree(g_fb[d].p); g_fb[d] = BufCache(); }
+}
+}
+
 // templates of all chunks.  early: launched from inside run_parse on the side stream, right after the site columns
 // were written on the parse's stream; otherwise on the parse's stream itself.
 static int frames_site_pass(hb_frames *f, hb_parse *p, bool early) {
@@ -837,9 +854,17 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         f->h_slot_off[f->n_chunks] = run;
         need = run * f->n_samples;
     }
+    bool regrow = false;
     if (f->frames_cap < need) {
-        const bool regrow = f->d_frames != nullptr;
+        regrow = f->d_frames != nullptr;
         if (f->d_frames) { cudaFree(f->d_frames); f->d_frames = nullptr; f->frames_cap = 0; }
+        if (f->device >= 0 && f->device < 64) {            // a buffer left behind by an earlier handle?
+            std::lock_guard<std::mutex> lk(g_fb_mu);
+            BufCache &c = g_fb[f->device];
+            if (c.p && c.cap >= need) { f->d_frames = c.p; f->frames_cap = c.cap; c = BufCache(); }
+        }
+    }
+    if (f->frames_cap < need) {
         // head-room: a re-run on other data (slab streaming) has slightly different template lengths, and growing
         // means cudaFree + cudaMalloc of many GB (~100 ms)
         const uint64_t cap = regrow ? need + need / 16 + (64ull << 20) : need + need / 64 + (16ull << 20);
@@ -908,6 +933,11 @@ void hb_frames_free(hb_frames *f) {
     if (!f) return;
     if (f->side) cudaStreamSynchronize(f->side);
     cudaSetDevice(f->device);
+    if (f->d_frames && f->device >= 0 && f->device < 64) {     // keep the big buffer for the next handle (see g_fb)
+        std::lock_guard<std::mutex> lk(g_fb_mu);
+        BufCache &c = g_fb[f->device];
+        if (c.cap < f->frames_cap) { std::swap(c.p, f->d_frames); std::swap(c.cap, f->frames_cap); }
+    }
     cudaFree(f->d_tmpl); cudaFree(f->d_frames); cudaFree(f->d_tmpl_len); cudaFree(f->d_size);
     cudaFree(f->d_slot_off); cudaFree(f->d_totals);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
