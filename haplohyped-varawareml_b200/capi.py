@@ -49,7 +49,7 @@ class FramesInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_chunks", C.c_uint64), ("chunk_records", C.c_uint64),
                 ("n_samples", C.c_uint32), ("total_bytes", C.c_uint64), ("raw_bytes", C.c_uint64),
                 ("ms_site", C.c_float), ("ms_frames", C.c_float), ("padded_bytes", C.c_uint64), ("d_frames", C.c_void_p),
-                ("site_lz4_bytes", C.c_uint64)]
+                ("site_lz4_bytes", C.c_uint64), ("ms_pack", C.c_float)]
 
 
 class HapBatch(C.Structure):

@@ -171,7 +171,7 @@ __device__ int warp_lz4_segment(const uint8_t *src, int n, int hist, uint8_t *ds
 constexpr int TMPL_HDR = FRAME_HDR + CHUNK_HDR + 8;        // 137 bytes of a frame precede its LZ4 block
 constexpr int FRAME_TAIL = OFFS_CHUNK + FRAME_TRAILER;     // 75 bytes follow it
 
-__device__ const uint8_t kFrameTail[FRAME_TAIL] = {
+__device__ __align__(16) const uint8_t kFrameTail[FRAME_TAIL + 1] = {      // + 1: read as 19 words by the lane encoder
     // offsets chunk: Blosc2 chunk header (version 5, LZ4 format 1, flags memcpyed|shuffle|bitshuffle(=extended),
     // typesize 8, nbytes 8, blocksize 8, cbytes 40, filters[5] = shuffle) + one int64 0
     5, 1, 0x17, 8, 8, 0, 0, 0, 8, 0, 0, 0, OFFS_CHUNK, 0, 0, 0,
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             const int seg = (cr + 15) >> 4;
             a0 = q * seg;
             const int seglen = max(0, min(seg, cr - a0));
-            const int mlim = p ? min(seglen, cr - 11 - a0) : seglen;      // the last 11 bytes of the block stay literals
+            const int mlim = min(seglen, n - 11 - (p * cr + a0));         // the last 11 bytes of the block stay literals
             const uint32_t *B = bits + (2 * p) * BWW + 1, *N = B + BWW;
             const uint32_t *B0 = bits + 1, *N0 = bits + BWW + 1;
             const int bi = alpha + a0, j0 = bi >> 5, shb = bi & 31;
@@ -700,6 +700,318 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 4b, lane-per-frame split (experimental, HB_DONOR_SPLIT=lane; NOT the default).  The warp-per-frame
+// kernel above spends ~2500-3000 warp instructions on a frame that has ~150 LZ4 sequences: scans, ballots and
+// divergent per-lane loops keep most lanes idle.  Here a LANE owns a frame and runs a plain sequential encoder, a
+// warp owns the 32 frames (one chunk) x (32 consecutive samples):
+//   pack_alleles_kernel       allele planes gt[plane][sample][row] -> bit arrays B (byte & 1) and N (any other
+//                             bit) laid out [array][row / 32][sample]: the 32 lanes of a warp read the same
+//                             row word of 32 neighbouring samples with one 128-byte request.
+//   donor_frames_lane_kernel  phase 1, lock-step over the chunk's words: Z / C run covers with a 2-word
+//                             look-ahead pipeline in registers, matches appended to a per-lane list in
+//                             shared memory; phase 2 (when a list is nearly full, and at the end): every lane
+//                             emits its sequences -- token, literals rebuilt from the bits, offset -- through
+//                             an 8-byte register accumulator straight into its frame's slot; phase 3: the
+//                             chunk's template is read ONCE per warp and stored to the 32 slots with the four
+//                             size fields patched.
+// Same parse rules as above (zero runs >= 5 -> offset 2*cr, plane-1 == plane-0 runs >= 4 -> offset cr, last
+// 11 bytes literal) without the 32 segment breaks: streams are 0.6 % smaller (5.877x vs 5.84x overall).
+// Measured (1.1M x 2504, profiles/r01e_lane_split.txt): pack 1.60 ms + encode 11.9 ms = 13.5 ms against 9.19 ms
+// for the warp-per-frame kernel.  Phases 1 and 3 are cheap (~400 and ~100 warp instructions per frame) but phase 2
+// costs ~1650: the 32 lanes walk 32 different sequence lists in lock step, so every step pays for the longest
+// literal run among them (mean 5.7 literals per sequence, maximum over 32 lanes ~25).  The total, 2370 per frame,
+// is no better than the 2460 of the warp-per-frame kernel.
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+    const int8_t *gt0, *gt1;
+    uint64_t gt_stride, n_records;
+    uint32_t s0, n_samples;
+    uint32_t sp;                 // samples per row word of the bit arrays (window rounded up to 32)
+    uint32_t rw;                 // row words per array
+    uint32_t *bits;              // [4][rw][sp]: B0, N0, B1, N1
+};
+
+__device__ __forceinline__ uint32_t pack_lsb16(const uint4 &x) {
+    return pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
+}
+__device__ __forceinline__ uint32_t pack_nz16(const uint4 &x) {
+    if (!((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)) return 0u;
+    return pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
+}
+
+constexpr int kPackWords = 4;    // row words (128 rows) per thread
+
+__global__ void __launch_bounds__(256) pack_alleles_kernel(const PackArgs A) {
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * 32 + lane;
+    const uint32_t j0 = (blockIdx.y * 8 + wy) * kPackWords;
+    if (j0 >= A.rw) return;
+    const bool live = s < A.n_samples;
+    const uint64_t row = (uint64_t)(A.s0 + (live ? s : 0)) * A.gt_stride;
+    const size_t plane = (size_t)A.rw * A.sp;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+        const int8_t *g = (pl ? A.gt1 : A.gt0) + row;
+        uint4 x[2 * kPackWords];
+#pragma unroll
+        for (int i = 0; i < 2 * kPackWords; ++i) {
+            const uint64_t r = (uint64_t)j0 * 32 + 16 * i;
+            x[i] = make_uint4(0, 0, 0, 0);
+            if (live && r < A.n_records) x[i] = ldg_stream(reinterpret_cast<const uint4 *>(g + r));
+        }
+#pragma unroll
+        for (int w = 0; w < kPackWords; ++w) {
+            if (j0 + w < A.rw) {
+                const uint64_t r = (uint64_t)(j0 + w) * 32;
+                const uint32_t vm = r >= A.n_records ? 0u : low_mask((int)min((uint64_t)32, A.n_records - r));
+                const uint32_t b = pack_lsb16(x[2 * w]) | (pack_lsb16(x[2 * w + 1]) << 16);
+                const uint32_t nn = pack_nz16(x[2 * w]) | (pack_nz16(x[2 * w + 1]) << 16);
+                uint32_t *o = A.bits + (size_t)(2 * pl) * plane + (size_t)(j0 + w) * A.sp + s;
+                o[0] = b & vm;
+                o[plane] = nn & vm;
+            }
+        }
+    }
+}
+
+struct LaneArgs {
+    const uint32_t *bits;
+    uint32_t sp, rw;
+    const int8_t *gt0, *gt1;             // raw bytes: only read for alleles other than 0 / 1
+    uint64_t gt_stride, n_records;
+    uint32_t cr, n_samples, s0, groups;  // groups: 32-sample groups of the window
+    uint64_t n_chunks;
+    const uint8_t *tmpl;
+    uint32_t tmpl_cap;
+    const uint32_t *tmpl_len;
+    uint8_t *frames;
+    const uint64_t *slot_off;
+    uint32_t *size;
+};
+
+constexpr int kLaneWpc = 4;              // warps per CTA
+constexpr int kEntCap = 48;              // matches a lane collects before the warp emits
+
+// the 8-byte accumulator a lane writes its frame through
+struct LaneOut {
+    uint64_t lo;
+    int fill;
+    uint64_t *p;
+    __device__ __forceinline__ void put(uint32_t v, int k) {       // k in 1..4 bytes of v (the others are zero)
+        lo |= (uint64_t)v << (8 * fill);
+        fill += k;
+        if (fill >= 8) {
+            *p++ = lo;
+            fill -= 8;
+            lo = (uint64_t)v >> (8 * (k - fill));
+        }
+    }
+    __device__ __forceinline__ void put_len(int rem) {             // LZ4 length extension bytes
+        while (rem >= 255) { put(255u, 1); rem -= 255; }
+        put((uint32_t)rem, 1);
+    }
+};
+
+template <int R>
+__device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t nxt) {      // bit i: x has R ones from i on
+    uint32_t s = x;
+#pragma unroll
+    for (int d = 1; d < R; ++d) s &= __funnelshift_r(x, nxt, d);
+    return s;
+}
+template <int R>
+__device__ __forceinline__ uint32_t run_cover(uint32_t sprev, uint32_t s) {     // positions inside such runs
+    uint32_t r = s;
+#pragma unroll
+    for (int d = 1; d < R; ++d) r |= __funnelshift_l(sprev, s, d);
+    return r;
+}
+
+__global__ void __launch_bounds__(kLaneWpc * 32) donor_frames_lane_kernel(const LaneArgs A) {
+    __shared__ uint32_t s_ent[kLaneWpc][kEntCap * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wid = (uint64_t)blockIdx.x * kLaneWpc + warp;
+    if (wid >= A.n_chunks * A.groups) return;
+    const uint32_t c = (uint32_t)(wid / A.groups), g = (uint32_t)(wid - (uint64_t)c * A.groups);
+    const uint32_t s = g * 32 + lane;
+    const bool live = s < A.n_samples;
+    const int cr = (int)A.cr, n = 2 * cr;
+    const uint32_t tl = A.tmpl_len[c];
+    const uint64_t row_stride = A.slot_off[A.n_chunks], so = A.slot_off[c];
+    uint8_t *frame = A.frames + (uint64_t)(live ? s : 0) * row_stride + so;
+    const uint64_t r0 = (uint64_t)c * cr;
+    const uint32_t j0 = (uint32_t)(r0 >> 5);
+    const int sh = (int)(r0 & 31);
+    const size_t plane = (size_t)A.rw * A.sp;
+    const uint32_t *col = A.bits + (size_t)j0 * A.sp + s;      // this lane's column, first row word of the chunk
+    uint32_t *ent = s_ent[warp] + lane;
+
+    LaneOut o;
+    o.p = reinterpret_cast<uint64_t *>(frame + (tl & ~7u));
+    o.fill = (int)(tl & 7u);
+    o.lo = 0;
+    if (o.fill) o.lo = *reinterpret_cast<const uint64_t *>(A.tmpl + (size_t)c * A.tmpl_cap + (tl & ~7u)) & ((1ull << (8 * o.fill)) - 1ull);
+    uint64_t *const p_first = o.p;
+    int lit_start = 0, cnt = 0;
+
+    // literals [a, b) of the block, rebuilt from the bit arrays (raw bytes only where N is set)
+    auto put_literals = [&](int a, int b) {
+        int x = a;
+        while (x < b) {
+            const int pl = x >= cr, i = x - pl * cr;
+            const int rb = sh + i, bo = rb & 31;
+            int take = min(b - x, 32 - bo);
+            if (!pl) take = min(take, cr - x);
+            const uint32_t *w = col + (size_t)(2 * pl) * plane + (size_t)(rb >> 5) * A.sp;
+            const uint32_t m = low_mask(take);
+            const uint32_t bw = (__ldg(w) >> bo) & m, nw = (__ldg(w + plane) >> bo) & m;
+            for (int q = 0; q < take; q += 4) {
+                const int k4 = min(4, take - q);
+                uint32_t v = (((bw >> q) & 15u) * 0x00204081u) & 0x01010101u;
+                const uint32_t nq = (nw >> q) & 15u;
+                if (nq) {
+                    const int8_t *raw = (pl ? A.gt1 : A.gt0) + (uint64_t)(A.s0 + s) * A.gt_stride + r0 + i + q;
+                    for (int t = 0; t < k4; ++t)
+                        if ((nq >> t) & 1u) v = (v & ~(0xFFu << (8 * t))) | ((uint32_t)(uint8_t)raw[t] << (8 * t));
+                }
+                o.put(v, k4);
+            }
+            x += take;
+        }
+    };
+    auto emit = [&](uint32_t e) {
+        const int ost = (int)(e & 0x1FFFu), ml = (int)((e >> 13) & 0xFFFu);
+        const int off = (e >> 31) ? cr : 2 * cr;
+        const int lit = ost - lit_start;
+        o.put((uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15)), 1);
+        if (lit >= 15) o.put_len(lit - 15);
+        put_literals(lit_start, ost);
+        if (ml < 19) o.put((uint32_t)off, 2);
+        else if (ml < 19 + 255) o.put((uint32_t)off | ((uint32_t)(ml - 19) << 16), 3);
+        else { o.put((uint32_t)off | 0xFF0000u, 3); o.put_len(ml - 19 - 255); }
+        lit_start = ost + ml;
+    };
+    auto drain = [&]() {
+        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+        for (int i = 0; i < maxc; ++i)
+            if (i < cnt) emit(ent[i * 32]);
+        cnt = 0;
+    };
+
+    // ---- 1. matches of both planes, word by word
+    for (int p = 0; p < 2; ++p) {
+        const int lim = live ? max(0, min(cr, n - 11 - p * cr)) : 0;           // the last 11 bytes of the block stay literals
+        const int W = (__reduce_max_sync(0xffffffffu, lim) + 31) >> 5;
+        const uint32_t *cb = col + (size_t)(2 * p) * plane;
+        // row words: cur = word j0 + t, nxt = word j0 + t + 1 (loaded one step ahead of their use)
+        uint32_t rb_ = __ldg(cb), rn_ = __ldg(cb + plane), r0b = 0, r0n = 0;
+        uint32_t xb_ = __ldg(cb + A.sp), xn_ = __ldg(cb + A.sp + plane), x0b = 0, x0n = 0;
+        if (p) { r0b = __ldg(col); r0n = __ldg(col + plane); x0b = __ldg(col + A.sp); x0n = __ldg(col + A.sp + plane); }
+        uint32_t zA = 0, cxA = 0, zsA = 0, zrA = 0, ccA = 0, csA = 0, pz = 0, pc = 0;
+        bool open = false;
+        int ost = 0;
+        uint32_t okind = 0;
+        for (int t = 0; t <= W + 2; ++t) {
+            // chunk-relative word t of this plane (zero past lim)
+            const uint32_t *nx = cb + (size_t)(t + 2) * A.sp;
+            const uint32_t ldb = __ldg(nx), ldn = __ldg(nx + plane);
+            uint32_t ld0b = 0, ld0n = 0;
+            if (p) { const uint32_t *n0 = col + (size_t)(t + 2) * A.sp; ld0b = __ldg(n0); ld0n = __ldg(n0 + plane); }
+            const uint32_t vm = low_mask(lim - 32 * t);
+            const uint32_t bw = __funnelshift_r(rb_, xb_, sh), nw = __funnelshift_r(rn_, xn_, sh);
+            const uint32_t zN = ~(bw | nw) & vm;
+            uint32_t cxN = 0;
+            if (p) {
+                const uint32_t b0w = __funnelshift_r(r0b, x0b, sh), n0w = __funnelshift_r(r0n, x0n, sh);
+                cxN = ~((bw ^ b0w) | nw | n0w) & vm;
+            }
+            rb_ = xb_; rn_ = xn_; r0b = x0b; r0n = x0n;
+            xb_ = ldb; xn_ = ldn; x0b = ld0b; x0n = ld0n;
+            const uint32_t zsB = run_starts<kMinZ>(zA, zN);           // word t-1
+            const uint32_t zrB = run_cover<kMinZ>(zsA, zsB);          // word t-1
+            const uint32_t ccB = cxA & ~zrB;                          // word t-1
+            const uint32_t csB = run_starts<kMinC>(ccA, ccB);         // word t-2
+            const uint32_t crW = run_cover<kMinC>(csA, csB);          // word t-2
+            if (t >= 2) {
+                if (__any_sync(0xffffffffu, cnt > kEntCap - 9)) drain();
+                const int k = t - 2;
+                const uint32_t mz = zrA, mc = crW;
+                const uint32_t mz1 = (mz << 1) | pz, mc1 = (mc << 1) | pc;
+                uint32_t st = (mz & ~mz1) | (mc & ~mc1);
+                uint32_t enx = (mz1 & ~mz) | (mc1 & ~mc);
+                pz = mz >> 31; pc = mc >> 31;
+                const int base = p * cr + 32 * k;
+                for (;;) {
+                    if (open) {
+                        if (!enx) break;
+                        const int te = ctz32(enx);
+                        enx &= enx - 1;
+                        ent[cnt * 32] = (uint32_t)ost | ((uint32_t)(base + te - ost) << 13) | (okind << 31);
+                        ++cnt;
+                        open = false;
+                    }
+                    if (!st) break;
+                    const int ts = ctz32(st);
+                    st &= st - 1;
+                    ost = base + ts; okind = (mc >> ts) & 1u; open = true;
+                }
+            }
+            zA = zN; cxA = cxN; zsA = zsB; zrA = zrB; ccA = ccB; csA = csB;
+        }
+    }
+    drain();
+
+    // ---- 2. the last sequence (literals only), the frame's tail, zero pad to 16 bytes
+    uint32_t flen = 0;
+    int dlen = 0;
+    if (live) {
+        const int L = n - lit_start;
+        o.put((uint32_t)(min(L, 15) << 4), 1);
+        if (L >= 15) o.put_len(L - 15);
+        put_literals(lit_start, n);
+        dlen = (int)(o.p - p_first) * 8 + o.fill - (int)(tl & 7u);
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(kFrameTail);
+#pragma unroll 1
+        for (int i = 0; i < FRAME_TAIL / 4; ++i) o.put(tw[i], 4);
+        o.put(tw[FRAME_TAIL / 4] & 0xFFFFFFu, FRAME_TAIL & 3);
+        if (o.fill) *o.p++ = o.lo;
+        if ((o.p - reinterpret_cast<uint64_t *>(frame)) & 1) *o.p++ = 0ull;
+        flen = tl + (uint32_t)dlen + FRAME_TAIL;
+        A.size[(uint64_t)s * A.n_chunks + c] = flen;
+    }
+
+    // ---- 3. the template, once per warp, into the 32 slots; the four donor-dependent size fields patched
+    const int nact = (int)min(32u, A.n_samples - g * 32);
+    const uint32_t ncopy = tl & ~7u, nv = ncopy >> 4;
+    const uint4 *T = reinterpret_cast<const uint4 *>(A.tmpl + (size_t)c * A.tmpl_cap);
+    uint8_t *slot0 = A.frames + (uint64_t)(g * 32) * row_stride + so;
+    {
+        // vectors 0..31 (the patched ones are 1, 2, 6, 7, 8)
+        const uint32_t j = (uint32_t)lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (j < nv) v = ldg_nc(T + j);
+        for (int f = 0; f < nact; ++f) {
+            const uint32_t fl = __shfl_sync(0xffffffffu, flen, f);
+            const uint32_t lz = fl - FRAME_TAIL - TMPL_HDR, cbz = CHUNK_HDR + 8 + lz;
+            uint4 x = v;
+            if (j == 1) x.y |= __byte_perm(fl, 0, 0x0123);                                   // frame_len, BE64 @16
+            else if (j == 2) { x.z |= (cbz >> 24) << 24; x.w |= __byte_perm(cbz, 0, 0x0123) >> 8; }   // cbytes, BE64 @39
+            else if (j == 6) x.w |= cbz << 8;                                                // chunk cbytes, LE32 @109
+            else if (j == 7) x.x |= cbz >> 24;
+            else if (j == 8) { x.y |= lz << 8; x.z |= lz >> 24; }                            // stream csize, LE32 @133
+            if (j < nv) stg_stream(reinterpret_cast<uint4 *>(slot0 + (uint64_t)f * row_stride) + j, x);
+        }
+    }
+    for (uint32_t j = 32 + lane; j < nv; j += 32) {
+        const uint4 v = ldg_nc(T + j);
+        uint8_t *d = slot0 + (size_t)j * 16;
+#pragma unroll 4
+        for (int f = 0; f < nact; ++f) { stg_stream(reinterpret_cast<uint4 *>(d), v); d += row_stride; }
+    }
+    if ((ncopy & 8u) && live) *reinterpret_cast<uint64_t *>(frame + (size_t)nv * 16) = *reinterpret_cast<const uint64_t *>(A.tmpl + (size_t)c * A.tmpl_cap + (size_t)nv * 16);
+}
+
 __global__ void __launch_bounds__(256) sum_sizes_kernel(const uint32_t *__restrict__ size, uint64_t n, unsigned long long *__restrict__ total) {
     unsigned long long acc = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += size[i];
@@ -760,6 +1072,12 @@ struct hb_frames {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_sites = nullptr, ev_tmpl = nullptr, ev_side0 = nullptr;
     bool early_site = false;                     // the template pass of the current parse run is already in flight
+    // lane-per-frame encoder: bit arrays of the window's allele planes
+    uint32_t *d_bits = nullptr;
+    uint64_t bits_cap = 0;                       // bytes
+    cudaEvent_t ev_pack = nullptr;
+    float ms_pack = 0;
+    bool lane_split = false;                     // the last run used the lane-per-frame kernels
 };
 
 template <int NW>
@@ -887,6 +1205,37 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         fa.pf_dist = (uint32_t)(sms * per_sm * kWpc);
         if (const char *e = getenv("HB_DF_PREFETCH")) fa.pf_dist = (uint32_t)atoi(e);
     }
+    // HB_DONOR_SPLIT=lane asks for the lane-per-frame kernels (measured slower, see their header); they need chunks
+    // that are not tiny: the four size fields must lie inside the template copy
+    bool lane_split = false;
+    if (const char *e = getenv("HB_DONOR_SPLIT")) lane_split = !strcmp(e, "lane") && cr >= 16;
+    for (uint64_t c = 0; c < f->n_chunks && lane_split; ++c) lane_split = f->h_tmpl_len[c] >= 152;
+    f->lane_split = lane_split;
+    if (lane_split) {
+        const uint32_t sp_cap = (f->win_cap + 31) & ~31u, sp = (f->n_samples + 31) & ~31u;
+        const uint64_t rw_cap = (f->chunk_cap * (uint64_t)cr + 31) / 32 + 8, rw = (f->n_chunks * (uint64_t)cr + 31) / 32 + 8;
+        const uint64_t need_bits = 16ull * rw_cap * sp_cap;
+        if (f->bits_cap < need_bits) {
+            if (f->d_bits) { cudaFree(f->d_bits); f->d_bits = nullptr; f->bits_cap = 0; }
+            e = cudaMalloc(&f->d_bits, need_bits);
+            if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the allele bit arrays (") + std::to_string(need_bits) + " bytes): " + cudaGetErrorString(e));
+            f->bits_cap = need_bits;
+        }
+        PackArgs pa;
+        pa.gt0 = fa.gt0; pa.gt1 = fa.gt1; pa.gt_stride = fa.gt_stride; pa.n_records = n;
+        pa.s0 = f->s0; pa.n_samples = f->n_samples; pa.sp = sp; pa.rw = (uint32_t)rw; pa.bits = f->d_bits;
+        pack_alleles_kernel<<<dim3(sp / 32, (unsigned)((rw + 8 * kPackWords - 1) / (8 * kPackWords))), 256, 0, f->stream>>>(pa);
+        CUF(cudaEventRecord(f->ev_pack, f->stream));
+        LaneArgs la;
+        la.bits = f->d_bits; la.sp = sp; la.rw = (uint32_t)rw;
+        la.gt0 = fa.gt0; la.gt1 = fa.gt1; la.gt_stride = fa.gt_stride; la.n_records = n;
+        la.cr = cr; la.n_samples = f->n_samples; la.s0 = f->s0; la.groups = sp / 32; la.n_chunks = f->n_chunks;
+        la.tmpl = f->d_tmpl; la.tmpl_cap = f->tmpl_cap; la.tmpl_len = f->d_tmpl_len;
+        la.frames = f->d_frames; la.slot_off = f->d_slot_off; la.size = f->d_size;
+        const uint64_t n_warps = f->n_chunks * la.groups;
+        donor_frames_lane_kernel<<<(unsigned)((n_warps + kLaneWpc - 1) / kLaneWpc), kLaneWpc * 32, 0, f->stream>>>(la);
+        count_launch(1);
+    } else
     switch (f->nw) {
         case 1: launch_donor_frames<1>(fa, f->n_ctas, f->stream); break;
         case 2: launch_donor_frames<2>(fa, f->n_ctas, f->stream); break;
@@ -907,6 +1256,8 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     if (was_early) cudaEventElapsedTime(&f->ms_site, f->ev_side0, f->ev_tmpl);
     else cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
     cudaEventElapsedTime(&f->ms_frames, f->ev[1], f->ev[2]);
+    f->ms_pack = 0;
+    if (lane_split) cudaEventElapsedTime(&f->ms_pack, f->ev[1], f->ev_pack);
 #undef CUF
     return HB_OK;
 }
@@ -939,7 +1290,8 @@ void hb_frames_free(hb_frames *f) {
         if (c.cap < f->frames_cap) { std::swap(c.p, f->d_frames); std::swap(c.cap, f->frames_cap); }
     }
     cudaFree(f->d_tmpl); cudaFree(f->d_frames); cudaFree(f->d_tmpl_len); cudaFree(f->d_size);
-    cudaFree(f->d_slot_off); cudaFree(f->d_totals);
+    cudaFree(f->d_slot_off); cudaFree(f->d_totals); cudaFree(f->d_bits);
+    if (f->ev_pack) cudaEventDestroy(f->ev_pack);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
     if (f->ev_sites) cudaEventDestroy(f->ev_sites);
     if (f->ev_tmpl) cudaEventDestroy(f->ev_tmpl);
@@ -1005,7 +1357,7 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
         ck(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, hi));
     }
     ck(cudaEventCreateWithFlags(&f->ev_sites, cudaEventDisableTiming));
-    ck(cudaEventCreate(&f->ev_tmpl)); ck(cudaEventCreate(&f->ev_side0));
+    ck(cudaEventCreate(&f->ev_tmpl)); ck(cudaEventCreate(&f->ev_side0)); ck(cudaEventCreate(&f->ev_pack));
     // the opt-in shared-memory ceiling is a per-function, process-wide attribute: always raise it to the device
     // maximum, so that concurrent callers (the converter parses two files at once) cannot shrink each other's limit
     int smem_max = 0;
@@ -1063,7 +1415,7 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
     info->n_records = f->n_records; info->n_chunks = f->n_chunks; info->chunk_records = f->cr;
     info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
     info->raw_bytes = 35ull * f->n_records * f->n_samples;
-    info->ms_site = f->ms_site; info->ms_frames = f->ms_frames;
+    info->ms_site = f->ms_site; info->ms_frames = f->ms_frames; info->ms_pack = f->ms_pack;
     info->padded_bytes = f->padded_bytes;
     info->d_frames = f->d_frames;
     uint64_t st = 0;

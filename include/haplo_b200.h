@@ -171,6 +171,7 @@ typedef struct hb_frames_info {
     uint64_t padded_bytes;          /* bytes of the device frame buffer in use: frames start on 16-byte boundaries */
     const uint8_t *d_frames;        /* device: frames in [sample][chunk] order, see hb_frames_layout */
     uint64_t site_lz4_bytes;        /* LZ4 bytes of the site planes, summed over chunks (shared by every sample) */
+    float ms_pack;                  /* part of ms_frames: allele planes -> bit arrays (lane-per-frame encoder); 0 otherwise */
 } hb_frames_info;
 
 /* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items (at most 2730).

@@ -216,3 +216,22 @@ def test_allele_plane_encoder_on_degenerate_and_hostile_planes(capi):
     text, samples = _pattern_vcf(2300, cols)
     for cr in (1075, 0, 64, 6, 2300):
         _check(capi, text, len(samples), "chr22", cr, list(range(len(samples))))
+
+
+@pytest.mark.parametrize("chunk_records", [0, 100, 1075])
+def test_lane_per_frame_split_is_exact_too(capi, monkeypatch, chunk_records):
+    """HB_DONOR_SPLIT=lane: allele planes -> bit arrays -> one lane per frame (hb_store.cu, experimental kernels).
+    Same parity bar; its streams are never longer than the warp-per-frame kernel's."""
+    text, samples = synth.random_vcf(2600, 37, seed=5, kinds="mixed", multidigit=True)
+    _, base = _check(capi, text, len(samples), "chr22", chunk_records, range(len(samples)))
+    monkeypatch.setenv("HB_DONOR_SPLIT", "lane")
+    info, total = _check(capi, text, len(samples), "chr22", chunk_records, range(len(samples)))
+    assert info.ms_pack > 0, "the lane-per-frame kernels did not run"
+    assert total <= base
+    # degenerate planes: all zero, all one, all missing, plane 1 == plane 0, alternating
+    cols = [lambda i: "0|0", lambda i: "1|1", lambda i: ".|.", lambda i: "0|1", lambda i: "2|2",
+            lambda i: "%d|%d" % (i & 1, (i >> 1) & 1), lambda i: "%d|0" % (i % 331 == 0), lambda i: "12|%d" % (i % 7 == 0)]
+    text2, _ = _pattern_vcf(3000, cols)
+    for cr in (1075, 64, 2300):
+        info, _ = _check(capi, text2, len(cols), "chr22", cr, range(len(cols)))
+        assert info.ms_pack > 0
