@@ -437,12 +437,12 @@ struct FusedArgs {
     const uint64_t *slot_off;            // [n_chunks + 1] offset of chunk c's slot inside a sample row; [n_chunks] = row stride
     uint32_t *size;                      // [n_samples * n_chunks] true length of each frame
     unsigned long long *totals;          // [0] sum of frame lengths
-    uint32_t rb;        // bytes of one raw plane row in shared memory (multiple of 16)
     uint32_t bww;       // words of one packed bit array (word 0 is a leading zero word)
     uint32_t caps;      // sequence slots per lane
     uint32_t dcap;      // literal-run descriptors per frame (non-empty runs only)
     uint32_t outcap;    // bytes of the frame-tail buffer
     uint32_t pf_dist;   // frames between a warp and the one that will follow it in its SM slot (0 = no L2 prefetch)
+    uint32_t pf_dq, pf_dr;   // pf_dist = pf_dq * n_chunks + pf_dr
     uint32_t warp_smem;
 };
 
@@ -455,10 +455,9 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     if (wid >= n_frames) return;
     const int cr = (int)A.cr, n = 2 * cr;
     uint8_t *base = smem + (size_t)warp * A.warp_smem;
-    uint8_t *raw0 = base, *raw1 = base + A.rb;
-    uint32_t *bits = reinterpret_cast<uint32_t *>(base + 2 * A.rb);      // B0, N0, B1, N1
+    uint32_t *bits = reinterpret_cast<uint32_t *>(base);                 // B string, N string (BWW words each)
     const int BWW = (int)A.bww;
-    uint16_t *seqs = reinterpret_cast<uint16_t *>(bits + 4 * BWW);       // [caps][32]
+    uint16_t *seqs = reinterpret_cast<uint16_t *>(bits + 2 * BWW);       // [caps][32]
     uint32_t *d_sd = reinterpret_cast<uint32_t *>(seqs + A.caps * 32);   // literal runs: source position | destination << 16
     uint16_t *d_cum = reinterpret_cast<uint16_t *>(d_sd + A.dcap);       //               literal index of the run's first byte
     uint8_t *outb = reinterpret_cast<uint8_t *>(d_cum + A.dcap);
@@ -471,6 +470,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     unsigned long long kindmask = 0;
     int out_base = 0, run_base = 0, lit_base = 0, total = 0, totrun = 0, totlit = 0, final_lit = 0;
     uint32_t sidx = 0;
+    bool any_n = false;                  // some allele of the frame is neither 0 nor 1
 
     {
         uint32_t s;
@@ -479,48 +479,63 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
         sidx = s;
         tl = A.tmpl_len[c];
         // the frame whose warp will take this warp's place when it retires: pull its two allele-plane slices into L2
-        if (A.pf_dist && lane < 2 && wid + A.pf_dist < n_frames) {
-            const uint64_t wf = wid + A.pf_dist;
-            const uint64_t sf = wf / A.n_chunks, cf = wf - sf * A.n_chunks;
+        if (A.pf_dist && lane < 2) {
+            uint64_t cf = c + A.pf_dr, sf = (uint64_t)s + A.pf_dq;           // frame wid + pf_dist, without a division
+            if (cf >= A.n_chunks) { cf -= A.n_chunks; ++sf; }
+            if (sf < A.n_samples) {
             const uint64_t rf = cf * (uint64_t)cr;
             const uint64_t off = (uint64_t)(A.s0 + sf) * A.gt_stride + (rf & ~15ull);
             const uint32_t bytes = (uint32_t)((((rf & 15ull) + min((uint64_t)cr, A.n_records - rf) + 15ull) & ~15ull));
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((lane ? A.gt1 : A.gt0) + off), "r"(bytes) : "memory");
+            }
         }
-        // ---- 1. planes -> shared memory (raw bytes for the literals) + packed bits
+        // ---- 1. planes -> packed bits in shared memory (the literals are rebuilt from the bits: keeping the raw bytes
+        //         too would cost 2 * cr bytes of shared memory per warp, i.e. a quarter of the resident warps)
         const uint64_t r0 = c * (uint64_t)cr;
         alpha = (int)(r0 & 15);
         const int valid = (int)min((uint64_t)cr, A.n_records - r0);       // rows past n_records read as zero (HDF5 edge chunk)
         const int nvec = (alpha + cr + 15) >> 4;
-        for (int i = lane; i < BWW; i += 32) reinterpret_cast<uint4 *>(bits)[i] = make_uint4(0, 0, 0, 0);
+        // B and N are ONE bit string each over both planes: block position x (0 .. 2 * cr) is bit alpha + x, so the
+        // parse and the literal copy walk from plane 0 into plane 1 without a seam
+        uint32_t *Bw = bits + 1, *Nw = Bw + BWW;
+        for (int i = lane; i < BWW / 2; i += 32) reinterpret_cast<uint4 *>(bits)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         const uint64_t rowbase = (uint64_t)(A.s0 + s) * A.gt_stride + (r0 & ~15ull);
+        uint32_t nacc = 0;
         for (int v = lane; v < 2 * nvec; v += 32) {
             const int pl = v >= nvec, k = v - pl * nvec;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (alpha + valid - 16 * k > 0) x = ldg_stream(reinterpret_cast<const uint4 *>((pl ? A.gt1 : A.gt0) + rowbase + 16 * k));
-            reinterpret_cast<uint4 *>(pl ? raw1 : raw0)[k] = x;
-            const uint32_t b16 = pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
+            // rows of this vector that belong to the chunk: [lo_i, hi_i); rows before r0 or past n_records read as zero
+            const int lo_i = max(0, alpha - 16 * k), hi_i = alpha + valid - 16 * k;
+            if (hi_i <= 0) continue;
+            const uint4 x = ldg_stream(reinterpret_cast<const uint4 *>((pl ? A.gt1 : A.gt0) + rowbase + 16 * k));
+            const uint32_t vm16 = low_mask(hi_i) & ~low_mask(lo_i) & 0xFFFFu;
+            const uint32_t b16 = (pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12)) & vm16;
             uint32_t n16 = 0;
             if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
-                n16 = pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
-            reinterpret_cast<uint16_t *>(bits + (2 * pl) * BWW + 1)[k] = (uint16_t)b16;
-            reinterpret_cast<uint16_t *>(bits + (2 * pl + 1) * BWW + 1)[k] = (uint16_t)n16;
+                n16 = (pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12)) & vm16;
+            nacc |= n16;
+            const int bit = pl * cr + 16 * k, w = bit >> 5, sh = bit & 31;      // row i of the vector is bit 16 * k + i (+ cr)
+            if (b16) {
+                atomicOr(Bw + w, b16 << sh);
+                if (sh > 16) atomicOr(Bw + w + 1, b16 >> (32 - sh));
+            }
+            if (n16) {
+                atomicOr(Nw + w, n16 << sh);
+                if (sh > 16) atomicOr(Nw + w + 1, n16 >> (32 - sh));
+            }
         }
         __syncwarp();
-        if (valid < cr) {                    // the vector that straddles n_records: bytes / bits past it must read 0
-            const int e = alpha + valid;
-            if (lane < 16) { const int idx = e + lane; if (idx < ((e + 15) & ~15)) { raw0[idx] = 0; raw1[idx] = 0; } }
-            if (lane < 4) bits[lane * BWW + 1 + (e >> 5)] &= low_mask(e & 31);
-            __syncwarp();
-        }
+        any_n = __any_sync(0xffffffffu, nacc != 0);
         const uint32_t sh16 = tl & 15u;      // the tail buffer lines up with the template's end modulo 16
         uint8_t *seq = outb + sh16;
         if (lane < 16) outb[lane] = 0;
         __syncwarp();
 
         if (cr < 6) {                        // raw block, see site_template_kernel
-            for (int i = lane; i < n; i += 32) seq[i] = i < cr ? raw0[alpha + i] : raw1[alpha + i - cr];
+            for (int i = lane; i < n; i += 32) {
+                const int x = i < cr ? i : i - cr;
+                seq[i] = x < valid ? (uint8_t)(i < cr ? A.gt0 : A.gt1)[(uint64_t)(A.s0 + s) * A.gt_stride + r0 + x] : (uint8_t)0;
+            }
             dlen = n;
         } else {
             // ---- 2. per-lane parse of one segment, position-parallel
@@ -530,20 +545,19 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             a0 = q * seg;
             const int seglen = max(0, min(seg, cr - a0));
             const int mlim = min(seglen, n - 11 - (p * cr + a0));         // the last 11 bytes of the block stay literals
-            const uint32_t *B = bits + (2 * p) * BWW + 1, *N = B + BWW;
-            const uint32_t *B0 = bits + 1, *N0 = bits + BWW + 1;
-            const int bi = alpha + a0, j0 = bi >> 5, shb = bi & 31;
+            const int bi = alpha + p * cr + a0, j0 = bi >> 5, shb = bi & 31;
+            const int bi0 = alpha + a0, j00 = bi0 >> 5, shb0 = bi0 & 31;     // the same rows in plane 0
             uint32_t Z[NW], C[NW], ZR[NW], CR[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
-                const uint32_t bw = __funnelshift_r(B[j0 + k], B[j0 + k + 1], shb);
-                const uint32_t nw = __funnelshift_r(N[j0 + k], N[j0 + k + 1], shb);
+                const uint32_t bw = __funnelshift_r(Bw[j0 + k], Bw[j0 + k + 1], shb);
+                const uint32_t nw = __funnelshift_r(Nw[j0 + k], Nw[j0 + k + 1], shb);
                 const uint32_t vm = low_mask(mlim - 32 * k);
                 Z[k] = ~(bw | nw) & vm;
                 C[k] = 0;
                 if (p) {
-                    const uint32_t b0w = __funnelshift_r(B0[j0 + k], B0[j0 + k + 1], shb);
-                    const uint32_t n0w = __funnelshift_r(N0[j0 + k], N0[j0 + k + 1], shb);
+                    const uint32_t b0w = __funnelshift_r(Bw[j00 + k], Bw[j00 + k + 1], shb0);
+                    const uint32_t n0w = __funnelshift_r(Nw[j00 + k], Nw[j00 + k + 1], shb0);
                     C[k] = ~((bw ^ b0w) | nw | n0w) & vm;
                 }
             }
@@ -552,6 +566,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             for (int k = 0; k < NW; ++k) C[k] &= ~ZR[k];
             runs_cover<NW, kMinC>(C, CR);
             int prev_end = 0, first_lit = 0, size_rest = 0, lit_rest = 0, ne_rest = 0;
+            int n15 = 0, n19 = 0, nnz = 0;
             {
                 bool open = false;
                 int ost = 0, okind = 0;
@@ -575,12 +590,20 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                         seqs[m * 32 + lane] = (uint16_t)((ost << 8) | ml);
                         kindmask |= (unsigned long long)okind << m;
                         if (m == 0) { first_lit = lit; first_ml = ml; }
-                        else { size_rest += 3 + lit + (lit >= 15) + (ml >= 19); lit_rest += lit; ne_rest += lit > 0; }
+                        n15 += lit >= 15; n19 += ml >= 19; nnz += lit > 0;
                         prev_end = ost + ml;
                         ++m;
                         open = false;
                     }
                 }
+            }
+            if (m > 0) {                     // sizes of the sequences after the first, from totals
+                int matched = 0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) matched += __popc(ZR[k] | CR[k]);
+                lit_rest = prev_end - matched - first_lit;
+                size_rest = 3 * (m - 1) + lit_rest + (n15 - (first_lit >= 15)) + (n19 - (first_ml >= 19));
+                ne_rest = nnz - (first_lit > 0);
             }
             const int trail = seglen - prev_end;
 
@@ -645,6 +668,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
         __syncwarp();
         {
             const int totL = totlit + final_lit;
+            const uint64_t grow = (uint64_t)(A.s0 + sidx) * A.gt_stride + c * (uint64_t)cr;
             const int share = (totL + 31) >> 5;
             const int g0 = lane * share;
             int cnt = min(share, totL - g0);
@@ -655,10 +679,26 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 uint32_t sd = d_sd[idx];
                 int src = (int)(sd & 0xFFFFu) + g0 - (int)d_cum[idx], dst = (int)(sd >> 16) + g0 - (int)d_cum[idx];
                 int nextcum = d_cum[idx + 1];
-                for (; cnt > 0; --cnt) {
-                    seq[dst] = src < cr ? raw0[alpha + src] : raw1[alpha + src - cr];
-                    ++src; ++dst; ++g;
-                    if (g == nextcum) { ++idx; sd = d_sd[idx]; src = (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
+                // literal bytes come back from the bits: block position x is bit alpha + x of the B / N strings
+                const uint32_t *Bw = bits + 1, *Nw = Bw + BWW;
+                int G = alpha + src;
+                if (!any_n) {                                 // every allele of the frame is 0 or 1: the bit is the byte
+                    for (; cnt > 0; --cnt) {
+                        seq[dst] = (uint8_t)(__funnelshift_r(Bw[G >> 5], 0u, G) & 1u);
+                        ++dst; ++g; ++G;
+                        if (g == nextcum) { ++idx; sd = d_sd[idx]; G = alpha + (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
+                    }
+                } else {
+                    for (; cnt > 0; --cnt) {
+                        uint32_t v = __funnelshift_r(Bw[G >> 5], 0u, G) & 1u;
+                        if (__funnelshift_r(Nw[G >> 5], 0u, G) & 1u) {        // an allele other than 0 / 1: the byte itself
+                            const int x = G - alpha;
+                            v = (uint8_t)(x < cr ? A.gt0 : A.gt1)[grow + (x < cr ? x : x - cr)];
+                        }
+                        seq[dst] = (uint8_t)v;
+                        ++dst; ++g; ++G;
+                        if (g == nextcum) { ++idx; sd = d_sd[idx]; G = alpha + (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
+                    }
                 }
             }
         }
@@ -1204,6 +1244,7 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         per_sm = (int)std::min<size_t>(32 / 1, (227 * 1024) / smem_cta);
         fa.pf_dist = (uint32_t)(sms * per_sm * kWpc);
         if (const char *e = getenv("HB_DF_PREFETCH")) fa.pf_dist = (uint32_t)atoi(e);
+        fa.pf_dq = (uint32_t)(fa.pf_dist / f->n_chunks); fa.pf_dr = (uint32_t)(fa.pf_dist % f->n_chunks);
     }
     // HB_DONOR_SPLIT=lane asks for the lane-per-frame kernels (measured slower, see their header); they need chunks
     // that are not tiny: the four size fields must lie inside the template copy
@@ -1331,12 +1372,12 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     const uint32_t seg = (cr + 15) / 16;
     f->nw = (int)((seg + 31) / 32);
     FusedArgs &fa = f->fa;
-    fa.rb = ((15 + cr + 15) & ~15u) + 16;
-    fa.bww = ((cr + 30) / 32 + 4 + 3) & ~3u;
+    fa.bww = ((2 * cr + 15) / 32 + 12) & ~3u;        // words of the B (and of the N) bit string: 1 pad + both planes + look-ahead
     fa.caps = seg / 4 + 2;
     fa.dcap = (cr / 6 + cr / 5 + 8 + 7) & ~7u;           // Z runs take >= 6 bytes each (5 + a break), C runs >= 5
     fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
-    fa.warp_smem = 2 * fa.rb + 16 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
+    fa.warp_smem = 8 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
+    if (const char *e = getenv("HB_DF_PAD")) fa.warp_smem += (uint32_t)atoi(e) & ~15u;       // experiment: occupancy sensitivity
     if ((size_t)kWpc * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
     f->chunk_cap = f->n_chunks + 4;          // a re-run on a slightly longer record set (streaming) still fits
     const uint64_t n_frames = f->chunk_cap * f->n_samples;

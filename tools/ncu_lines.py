@@ -45,7 +45,7 @@ for key in agg:
         except Exception: src[key[0]] = []
 print("total instr", tot, "per unit", tot / div)
 for key, (v, smp) in sorted(agg.items(), key=lambda kv: (kv[0] or ("", 0))):
-    if v < tot * 0.003: continue
+    if v < tot * float(__import__("os").environ.get("NCU_LINES_MIN", "0.003")): continue
     text = ""
     if key and src.get(key[0]) and key[1] - 1 < len(src[key[0]]): text = src[key[0]][key[1] - 1].strip()[:110]
     print(f"{v / div:9.1f} {100.0 * v / tot:5.1f}% smp {smp:6d}  {key[0] if key else '?'}:{key[1] if key else 0:<5d} {text}")
