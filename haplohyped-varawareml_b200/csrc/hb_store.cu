@@ -25,6 +25,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/haplo_b200.h"
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     uint64_t c = 0;
     // state of the parse that the emission needs
     int m = 0, carry = 0, a0 = 0, p = 0, first_ml = 0;
-    unsigned long long kindmask = 0;
+    typename std::conditional<(NW <= 4), uint32_t, unsigned long long>::type kindmask = 0;    // <= 8 sequences per word of the segment
     int out_base = 0, run_base = 0, lit_base = 0, total = 0, totrun = 0, totlit = 0, final_lit = 0;
     uint32_t sidx = 0;
     bool any_n = false;                  // some allele of the frame is neither 0 nor 1
@@ -508,7 +509,8 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             const int lo_i = max(0, alpha - 16 * k), hi_i = alpha + valid - 16 * k;
             if (hi_i <= 0) continue;
             const uint4 x = ldg_stream(reinterpret_cast<const uint4 *>((pl ? A.gt1 : A.gt0) + rowbase + 16 * k));
-            const uint32_t vm16 = low_mask(hi_i) & ~low_mask(lo_i) & 0xFFFFu;
+            uint32_t vm16 = 0xFFFFu;                                           // only the chunk's first / last vector is partial
+            if (lo_i > 0 || hi_i < 16) vm16 = low_mask(hi_i) & ~low_mask(lo_i) & 0xFFFFu;
             const uint32_t b16 = (pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12)) & vm16;
             uint32_t n16 = 0;
             if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                         en &= en - 1;
                         const int ml = 32 * k + te - ost + 1, lit = ost - prev_end;
                         seqs[m * 32 + lane] = (uint16_t)((ost << 8) | ml);
-                        kindmask |= (unsigned long long)okind << m;
+                        kindmask |= (decltype(kindmask))okind << m;
                         if (m == 0) { first_lit = lit; first_ml = ml; }
                         n15 += lit >= 15; n19 += ml >= 19; nnz += lit > 0;
                         prev_end = ost + ml;
@@ -647,11 +649,12 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             for (int j = 0; j < m; ++j) {
                 const uint32_t e = seqs[j * 32 + lane];
                 const int st = p * cr + a0 + (int)(e >> 8), ml = (int)(e & 255u);
-                const int off = ((kindmask >> j) & 1ull) ? cr : 2 * cr;
+                const int off = ((kindmask >> j) & 1u) ? cr : 2 * cr;
                 const int lit = st - prev_abs;
                 seq[o++] = (uint8_t)((min(lit, 15) << 4) | min(ml - 4, 15));
                 if (lit >= 15) { int rem = lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-                if (lit > 0) { d_cum[r] = (uint16_t)lc; d_sd[r] = (uint32_t)prev_abs | ((uint32_t)o << 16); ++r; }
+                // literal run: literal index g of the frame sits at bit g + dG of the B / N strings and goes to byte g + dD
+                if (lit > 0) { d_cum[r] = (uint16_t)lc; d_sd[r] = (uint32_t)(alpha + prev_abs - lc) | ((uint32_t)(o - lc) << 16); ++r; }
                 lc += lit; o += lit;
                 seq[o++] = (uint8_t)off; seq[o++] = (uint8_t)(off >> 8);
                 if (ml >= 19) seq[o++] = (uint8_t)(ml - 19);
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             int o = total;
             seq[o++] = (uint8_t)(min(final_lit, 15) << 4);
             if (final_lit >= 15) { int rem = final_lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-            d_cum[totrun] = (uint16_t)totlit; d_sd[totrun] = (uint32_t)(n - final_lit) | ((uint32_t)o << 16);
+            d_cum[totrun] = (uint16_t)totlit; d_sd[totrun] = (uint32_t)(alpha + n - final_lit - totlit) | ((uint32_t)(o - totlit) << 16);
             d_cum[totrun + 1] = (uint16_t)(totlit + final_lit);
         }
         __syncwarp();
@@ -675,30 +678,33 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             int lo = 0, hi = totrun + 1;
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)d_cum[mid] <= g0) lo = mid; else hi = mid; }
             if (cnt > 0) {
-                int idx = lo, g = g0;
-                uint32_t sd = d_sd[idx];
-                int src = (int)(sd & 0xFFFFu) + g0 - (int)d_cum[idx], dst = (int)(sd >> 16) + g0 - (int)d_cum[idx];
-                int nextcum = d_cum[idx + 1];
-                // literal bytes come back from the bits: block position x is bit alpha + x of the B / N strings
+                // literal bytes come back from the bits (block position x is bit alpha + x of the B / N strings)
                 const uint32_t *Bw = bits + 1, *Nw = Bw + BWW;
-                int G = alpha + src;
+                const uint32_t *psd = d_sd + lo;
+                const uint16_t *pcum = d_cum + lo + 1;
+                uint32_t sd = *psd;
+                int nextcum = *pcum, dG = (int)(sd & 0xFFFFu), dD = (int)(sd >> 16);
+                int g = g0;
+                const int gend = g0 + cnt;
                 if (!any_n) {                                 // every allele of the frame is 0 or 1: the bit is the byte
-                    for (; cnt > 0; --cnt) {
-                        seq[dst] = (uint8_t)(__funnelshift_r(Bw[G >> 5], 0u, G) & 1u);
-                        ++dst; ++g; ++G;
-                        if (g == nextcum) { ++idx; sd = d_sd[idx]; G = alpha + (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
-                    }
+                    do {
+                        const int G = g + dG;
+                        seq[g + dD] = (uint8_t)(__funnelshift_r(Bw[G >> 5], 0u, G) & 1u);
+                        ++g;
+                        if (g == nextcum) { sd = *++psd; nextcum = *++pcum; dG = (int)(sd & 0xFFFFu); dD = (int)(sd >> 16); }
+                    } while (g < gend);
                 } else {
-                    for (; cnt > 0; --cnt) {
+                    do {
+                        const int G = g + dG;
                         uint32_t v = __funnelshift_r(Bw[G >> 5], 0u, G) & 1u;
                         if (__funnelshift_r(Nw[G >> 5], 0u, G) & 1u) {        // an allele other than 0 / 1: the byte itself
                             const int x = G - alpha;
                             v = (uint8_t)(x < cr ? A.gt0 : A.gt1)[grow + (x < cr ? x : x - cr)];
                         }
-                        seq[dst] = (uint8_t)v;
-                        ++dst; ++g; ++G;
-                        if (g == nextcum) { ++idx; sd = d_sd[idx]; G = alpha + (int)(sd & 0xFFFFu); dst = (int)(sd >> 16); nextcum = d_cum[idx + 1]; }
-                    }
+                        seq[g + dD] = (uint8_t)v;
+                        ++g;
+                        if (g == nextcum) { sd = *++psd; nextcum = *++pcum; dG = (int)(sd & 0xFFFFu); dD = (int)(sd >> 16); }
+                    } while (g < gend);
                 }
             }
         }
