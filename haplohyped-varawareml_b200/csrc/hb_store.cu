@@ -1378,7 +1378,7 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     const uint32_t seg = (cr + 15) / 16;
     f->nw = (int)((seg + 31) / 32);
     FusedArgs &fa = f->fa;
-    fa.bww = ((2 * cr + 15) / 32 + 12) & ~3u;        // words of the B (and of the N) bit string: 1 pad + both planes + look-ahead
+    fa.bww = ((2 * cr + 15) / 32 + 14) & ~3u;        // words of the B (and of the N) bit string: 1 pad + both planes + look-ahead
     fa.caps = seg / 4 + 2;
     fa.dcap = (cr / 6 + cr / 5 + 8 + 7) & ~7u;           // Z runs take >= 6 bytes each (5 + a break), C runs >= 5
     fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
