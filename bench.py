@@ -185,8 +185,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # rank 0 prints ONE line on stdout: whatever libraries print there meanwhile (NCCL's version banner, when NCCL_DEBUG
+    # is set in the environment) goes to stderr -- file descriptor 1 is pointed at stderr until the JSON line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off stdout: rank 0 prints ONE line
         dist.init_process_group("nccl", device_id=dev)
 
     V, S = args.variants, args.samples
@@ -423,6 +427,8 @@ def main():
                 "step": "parse only (kernels 1-3)" if args.parse_only else "text -> Blosc2 frames (kernels 1-4)",
                 "tokenizer": int(info.tokenizer_used), "parity_spot_check": parity,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if frames[0] is not None:
         p.attach(None)
