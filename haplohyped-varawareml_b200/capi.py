@@ -68,7 +68,7 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
-    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_stream_bgzf_host", "hb_bgzf_vcf_info", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
@@ -98,6 +98,10 @@ def lib():
         L.hb_parse_stream_host.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.hb_bgzf_vcf_info.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.hb_parse_stream_bgzf_host.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
+                                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.hb_parse_device_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.hb_parse_vcf_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -380,6 +384,36 @@ def parse_stream_host(text, n_samples, capacity, region="", end_is_int=False, wa
     k = int(n.value)
     return {"n": k, "n_slabs": int(ns.value), "gt0": g0[:, :k], "gt1": g1[:, :k], "start": start[:k], "stop": stop[:k],
             "ref": ref[:k], "alt": alt[:k], "ploidy_err": pl[:n_samples], "badgt_err": bg[:n_samples]}
+
+
+def bgzf_vcf_info(data):
+    """(n_samples, decompressed bytes, offset of the first record) of the BGZF bytes of a .vcf.gz"""
+    keep = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data
+    ns, tb, bo = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    check(lib().hb_bgzf_vcf_info(keep.ctypes.data, keep.size, C.byref(ns), C.byref(tb), C.byref(bo)))
+    return int(ns.value), int(tb.value), int(bo.value)
+
+
+def parse_stream_bgzf_host(data, capacity, region="", want_gt=True, device=0, slab_bytes=0, out=None):
+    """hb_parse_stream_bgzf_host on the BGZF bytes of a .vcf.gz (bytes / uint8 array, ideally pinned): a dict of numpy
+    arrays trimmed to n_records.  out: pre-allocated (gt0, gt1, start, stop, ref, alt) to write into (e.g. pinned)."""
+    keep = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data
+    n_samples, _, _ = bgzf_vcf_info(keep)
+    if out is None:
+        g0 = np.empty((n_samples, capacity), np.int8)
+        g1 = np.empty((n_samples, capacity), np.int8)
+        start, stop = np.empty(capacity, np.uint32), np.empty(capacity, np.uint32)
+        ref, alt = np.empty(capacity, "S1"), np.empty(capacity, "S1")
+    else:
+        g0, g1, start, stop, ref, alt = out
+    pl, bg = np.zeros(max(1, n_samples), np.uint32), np.zeros(max(1, n_samples), np.uint32)
+    n, ns = C.c_uint64(), C.c_uint32()
+    check(lib().hb_parse_stream_bgzf_host(keep.ctypes.data, keep.size, (region or "").encode(), int(want_gt), device, slab_bytes,
+                                          g0.ctypes.data, g1.ctypes.data, capacity, start.ctypes.data, stop.ctypes.data,
+                                          ref.ctypes.data, alt.ctypes.data, pl.ctypes.data, bg.ctypes.data, C.byref(n), C.byref(ns)))
+    k = int(n.value)
+    return {"n": k, "n_samples": n_samples, "n_slabs": int(ns.value), "gt0": g0[:, :k], "gt1": g1[:, :k], "start": start[:k],
+            "stop": stop[:k], "ref": ref[:k], "alt": alt[:k], "ploidy_err": pl[:n_samples], "badgt_err": bg[:n_samples]}
 
 
 def load_vcf_columns(path: str, sample: str, chrom: str = ""):

@@ -816,6 +816,30 @@ int parse_file_common(const char *path, const char *region, bool want_gt, int de
     return parse_bytes_common(raw, raw.data(), raw.size(), region, want_gt, device, out, samples);
 }
 
+// the VCF header of a BGZF file: leading members are inflated on the host (zlib) until the #CHROM line is complete
+static int bgzf_header(const uint8_t *raw, const std::vector<uint64_t> &coff, const std::vector<uint32_t> &clen,
+                       const std::vector<uint32_t> &olen, FileText &ft) {
+    std::vector<uint8_t> head;
+    bool have = false;
+    for (size_t i = 0; i < coff.size() && !have; ++i) {
+        const size_t at = head.size();
+        head.resize(at + olen[i]);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) return fail(HB_ERR_IO, "inflateInit2 failed");
+        zs.next_in = const_cast<Bytef *>(raw + coff[i]);
+        zs.avail_in = clen[i];
+        zs.next_out = head.data() + at;
+        zs.avail_out = olen[i];
+        const int zr = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (zr != Z_STREAM_END || zs.avail_out != 0) return fail(HB_ERR_IO, "BGZF inflate failed (header)");
+        have = parse_header(head.data(), head.size(), i + 1 == coff.size(), ft);
+    }
+    if (!have) return fail(HB_ERR_HEADER, "no #CHROM header line");
+    return HB_OK;
+}
+
 // raw_p[0..raw_n): the bytes of a .vcf / .vcf.gz; raw_owned: the vector that holds them when the caller read a file
 // (released early on the zlib path), empty when they belong to the caller
 int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, uint64_t raw_n, const char *region, bool want_gt,
@@ -845,26 +869,7 @@ int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, ui
     }
     // ---- header: inflate leading members on the host until the #CHROM line is complete
     FileText ft;
-    {
-        std::vector<uint8_t> head;
-        bool have = false;
-        for (size_t i = 0; i < coff.size() && !have; ++i) {
-            const size_t at = head.size();
-            head.resize(at + olen[i]);
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) return fail(HB_ERR_IO, "inflateInit2 failed");
-            zs.next_in = const_cast<Bytef *>(raw.data() + coff[i]);
-            zs.avail_in = clen[i];
-            zs.next_out = head.data() + at;
-            zs.avail_out = olen[i];
-            const int zr = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (zr != Z_STREAM_END || zs.avail_out != 0) return fail(HB_ERR_IO, "BGZF inflate failed (header)");
-            have = parse_header(head.data(), head.size(), i + 1 == coff.size(), ft);
-        }
-        if (!have) return fail(HB_ERR_HEADER, "no #CHROM header line");
-    }
+    TRY(bgzf_header(raw.data(), coff, clen, olen, ft));
     samples = ft.samples;
     o.n_samples = (uint32_t)ft.samples.size();
     o.end_is_int = ft.end_is_int;
@@ -1059,6 +1064,196 @@ int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int devic
     std::vector<std::string> samples;
     TRY(parse_file_common(in_vcf, region, want_gt != 0, device, out, samples));
     (*out)->samples = samples;
+    return HB_OK;
+}
+
+// header of the BGZF bytes of a .vcf.gz: sample count, decompressed size, offset of the first record in it
+int hb_bgzf_vcf_info(const uint8_t *bgzf, uint64_t nbytes, uint32_t *n_samples, uint64_t *text_bytes, uint64_t *body_offset) {
+    if (!bgzf) return fail(HB_ERR_ARG, "null argument");
+    std::vector<uint64_t> coff, ooff;
+    std::vector<uint32_t> clen, olen;
+    uint64_t total = 0;
+    if (!bgzf_index(bgzf, nbytes, coff, clen, ooff, olen, total)) return fail(HB_ERR_IO, "not a BGZF file");
+    FileText ft;
+    TRY(bgzf_header(bgzf, coff, clen, olen, ft));
+    if (n_samples) *n_samples = (uint32_t)ft.samples.size();
+    if (text_bytes) *text_bytes = total;
+    if (body_offset) *body_offset = ft.body;
+    return HB_OK;
+}
+
+// BGZF bytes in host memory -> results in host memory, streamed: slabs of whole BGZF members cross PCIe compressed,
+// are inflated on the GPU behind the unfinished last line of the slab before, parsed up to their own last newline and
+// fetched -- H2D + inflate of slab k + 1 and the D2H of slab k - 1 run while slab k is parsed.
+int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
+                              uint64_t slab_bytes, int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start,
+                              uint32_t *stop, char *ref, char *alt, uint32_t *ploidy_err, uint32_t *badgt_err,
+                              uint64_t *n_records, uint32_t *n_slabs) {
+    if (!bgzf || !n_records) return fail(HB_ERR_ARG, "null argument");
+    *n_records = 0;
+    if (n_slabs) *n_slabs = 0;
+    std::vector<uint64_t> coff, ooff;
+    std::vector<uint32_t> clen, olen;
+    uint64_t total = 0;
+    if (!bgzf_index(bgzf, nbytes, coff, clen, ooff, olen, total)) return fail(HB_ERR_IO, "not a BGZF file");
+    FileText ft;
+    TRY(bgzf_header(bgzf, coff, clen, olen, ft));
+    hb_parse_opts opts;
+    memset(&opts, 0, sizeof opts);
+    opts.region = region;
+    opts.want_gt = want_gt ? 1 : 0;
+    opts.device = device;
+    opts.n_samples = (uint32_t)ft.samples.size();
+    opts.end_is_int = ft.end_is_int;
+    if (ploidy_err) memset(ploidy_err, 0, 4ull * opts.n_samples);
+    if (badgt_err) memset(badgt_err, 0, 4ull * opts.n_samples);
+    if (total <= ft.body) return HB_OK;
+    if (slab_bytes == 0) slab_bytes = 256ull << 20;
+    // slabs of whole members, about slab_bytes of text each
+    struct Slab { size_t m0, m1; uint64_t text; uint64_t comp0, comp; };
+    std::vector<Slab> slabs;
+    uint64_t text_cap = 0, comp_cap = 0;
+    size_t n_cap = 0;
+    for (size_t m = 0; m < coff.size();) {
+        Slab sl{m, m, 0, coff[m], 0};
+        while (sl.m1 < coff.size() && (sl.text == 0 || sl.text + olen[sl.m1] <= slab_bytes)) { sl.text += olen[sl.m1]; ++sl.m1; }
+        sl.comp = coff[sl.m1 - 1] + clen[sl.m1 - 1] - sl.comp0;
+        if (sl.text) slabs.push_back(sl);
+        text_cap = std::max(text_cap, sl.text); comp_cap = std::max(comp_cap, sl.comp); n_cap = std::max(n_cap, sl.m1 - sl.m0);
+        m = sl.m1;
+    }
+    if (slabs.empty()) return HB_OK;
+    if (ft.body >= slabs[0].text) return fail(HB_ERR_ARG, "the VCF header is longer than a slab: raise slab_bytes");
+    const uint64_t carry_cap = std::min<uint64_t>((text_cap + 15) & ~15ull, 256ull << 20);   // longest unfinished line carried over
+    TRY(ensure_device(device));
+    struct Slot {
+        hb_parse *p = nullptr;
+        cudaStream_t compute = nullptr, d2h = nullptr;
+        cudaEvent_t fetched = nullptr;
+        InflateScratch sc;
+        uint8_t *buf = nullptr;                       // [carry_cap + 16 | slab text | '\n' + 256]
+        std::vector<uint64_t> hc, ho;
+        std::vector<int> status;
+        unsigned long long last_nl = 0;
+        uint64_t x = 0, end = 0, begin = 0;           // slab text at buf + x .. buf + end; the parse starts at buf + begin
+    } slot[2];
+    int rc = HB_OK;
+    auto cleanup = [&]() {
+        for (auto &s : slot) {
+            if (s.compute) cudaStreamSynchronize(s.compute);
+            if (s.d2h) cudaStreamSynchronize(s.d2h);
+            if (s.p) { s.p->d_text = nullptr; hb_parse_free(s.p); }
+            cudaFree(s.buf);
+            inflate_scratch_free(s.sc);
+            if (s.fetched) cudaEventDestroy(s.fetched);
+            if (s.compute) cudaStreamDestroy(s.compute);
+            if (s.d2h) cudaStreamDestroy(s.d2h);
+        }
+    };
+    const size_t n_slots = std::min<size_t>(2, slabs.size());
+    for (size_t i = 0; i < n_slots && rc == HB_OK; ++i) {
+        Slot &s = slot[i];
+        if (cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fetched, cudaEventDisableTiming) != cudaSuccess) { rc = fail(HB_ERR_CUDA, "cannot create streams"); break; }
+        hb_parse_opts o = opts;
+        o.stream = s.compute;
+        rc = new_parse(&o, &s.p);
+        if (rc == HB_OK) rc = dev_alloc(&s.buf, carry_cap + 32 + text_cap + 1 + 256);
+        if (rc == HB_OK) rc = inflate_scratch_alloc(s.sc, comp_cap, (uint32_t)n_cap);
+        s.hc.resize(n_cap); s.ho.resize(n_cap); s.status.resize(n_cap);
+    }
+    if (rc != HB_OK) { cleanup(); return rc; }
+    cudaError_t e = cudaSuccess;
+    // H2D + inflate of slab k behind a carry of carry_len bytes, then the search for its last newline
+    auto enqueue = [&](size_t k, uint64_t carry_len) -> int {
+        Slot &s = slot[k & 1];
+        const Slab &sl = slabs[k];
+        const uint64_t skip = k == 0 ? ft.body : 0;            // slab 0 starts with the header
+        s.x = carry_cap + (k == 0 ? (16 - ft.body % 16) % 16 : carry_len % 16);    // the parse starts on a 16-byte boundary
+        s.begin = s.x + skip - carry_len;
+        s.end = s.x + sl.text;
+        const uint32_t n = (uint32_t)(sl.m1 - sl.m0);
+        for (uint32_t i = 0; i < n; ++i) { s.hc[i] = coff[sl.m0 + i] - sl.comp0; s.ho[i] = s.x + (ooff[sl.m0 + i] - ooff[sl.m0]); }
+        if (cudaStreamWaitEvent(s.compute, s.fetched, 0) != cudaSuccess) return fail(HB_ERR_CUDA, "cudaStreamWaitEvent failed");
+        int r = inflate_bgzf_enqueue(s.sc, bgzf + sl.comp0, sl.comp, s.hc.data(), clen.data() + sl.m0, s.ho.data(), olen.data() + sl.m0, n, s.buf, s.compute);
+        if (r != HB_OK) return r;
+        if (k + 1 == slabs.size()) {                           // a file that does not end with a newline
+            cudaError_t ee = cudaMemsetAsync(s.buf + s.end, '\n', 1, s.compute);
+            if (ee != cudaSuccess) return fail(HB_ERR_CUDA, "cudaMemsetAsync failed");
+        }
+        launch_last_newline(s.buf, s.x + skip, s.end, s.sc.d_last_nl, s.compute);
+        cudaError_t ee = cudaMemcpyAsync(&s.last_nl, s.sc.d_last_nl, 8, cudaMemcpyDeviceToHost, s.compute);
+        if (ee == cudaSuccess) ee = cudaMemcpyAsync(s.status.data(), s.sc.d_status, 4ull * n, cudaMemcpyDeviceToHost, s.compute);
+        if (ee != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(ee));
+        return HB_OK;
+    };
+    rc = enqueue(0, 0);
+    uint64_t R = 0;
+    std::vector<uint32_t> pl(opts.n_samples), bg(opts.n_samples);
+    for (size_t k = 0; k < slabs.size() && rc == HB_OK && e == cudaSuccess; ++k) {
+        Slot &s = slot[k & 1];
+        e = cudaStreamSynchronize(s.compute);                  // slab k is inflated, its last newline is known
+        if (e != cudaSuccess) break;
+        for (size_t i = 0; i < slabs[k].m1 - slabs[k].m0; ++i)
+            if (s.status[i]) { rc = fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(slabs[k].m0 + i) + ", code " + std::to_string(s.status[i]) + ")"); break; }
+        if (rc != HB_OK) break;
+        const bool last = k + 1 == slabs.size();
+        uint64_t parse_end;                                     // one past the last newline of the slab's text
+        if (s.last_nl == ~0ull) {
+            if (!last) { rc = fail(HB_ERR_ARG, "a line is longer than a slab: raise slab_bytes"); break; }
+            parse_end = s.begin;
+        } else parse_end = s.last_nl + 1;
+        if (last && parse_end < s.end) parse_end = s.end + 1;   // no newline at the end of the file: the one appended ends the last line
+        const uint64_t carry_len = last ? 0 : s.end - parse_end;
+        if (carry_len > carry_cap) { rc = fail(HB_ERR_ARG, "a line is longer than the carry buffer: raise slab_bytes"); break; }
+        if (!last) {
+            Slot &nx = slot[(k + 1) & 1];
+            // the unfinished line goes in front of the next slab's text (that buffer's last parse has returned)
+            const uint64_t nx_x = carry_cap + carry_len % 16;
+            if (carry_len) e = cudaMemcpyAsync(nx.buf + nx_x - carry_len, s.buf + parse_end, carry_len, cudaMemcpyDeviceToDevice, s.compute);
+            if (e != cudaSuccess) break;
+        }
+        e = cudaMemsetAsync(s.buf + parse_end, 0, 256, s.compute);
+        if (e != cudaSuccess) break;
+        if (!last) { rc = enqueue(k + 1, carry_len); if (rc != HB_OK) break; }
+        uint64_t n = 0;
+        if (parse_end > s.begin) {
+            s.p->d_text = s.buf + s.begin;
+            s.p->nbytes = parse_end - s.begin;
+            rc = run_parse(s.p);                                // returns with the slot's compute stream idle
+            if (rc != HB_OK) break;
+            n = s.p->h_st.n_records;
+        }
+        if (R + n > out_stride && (gt0 || gt1 || start || stop || ref || alt)) { rc = fail(HB_ERR_ARG, "more records than the output arrays hold"); break; }
+        if (n) {
+            if (opts.want_gt && opts.n_samples && s.p->d_gt[0]) {
+                if (gt0) e = cudaMemcpy2DAsync(gt0 + R, out_stride, s.p->d_gt[0], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+                if (gt1 && e == cudaSuccess) e = cudaMemcpy2DAsync(gt1 + R, out_stride, s.p->d_gt[1], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+            }
+            if (start && e == cudaSuccess) e = cudaMemcpyAsync(start + R, s.p->d_start, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+            if (stop && e == cudaSuccess) e = cudaMemcpyAsync(stop + R, s.p->d_stop, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+            if (ref && e == cudaSuccess) e = cudaMemcpyAsync(ref + R, s.p->d_ref, n, cudaMemcpyDeviceToHost, s.d2h);
+            if (alt && e == cudaSuccess) e = cudaMemcpyAsync(alt + R, s.p->d_alt, n, cudaMemcpyDeviceToHost, s.d2h);
+            if ((ploidy_err || badgt_err) && opts.want_gt && opts.n_samples && e == cudaSuccess) {
+                e = cudaMemcpyAsync(pl.data(), s.p->d_ploidy, 4ull * opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(bg.data(), s.p->d_badgt, 4ull * opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s.d2h);
+                for (uint32_t i = 0; i < opts.n_samples && e == cudaSuccess; ++i) {
+                    if (ploidy_err) ploidy_err[i] += pl[i];
+                    if (badgt_err) badgt_err[i] += bg[i];
+                }
+            }
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(s.fetched, s.d2h);
+        R += n;
+    }
+    for (auto &s : slot) if (s.d2h && e == cudaSuccess && rc == HB_OK) e = cudaStreamSynchronize(s.d2h);
+    cleanup();
+    if (rc != HB_OK) return rc;
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    *n_records = R;
+    if (n_slabs) *n_slabs = (uint32_t)slabs.size();
     return HB_OK;
 }
 

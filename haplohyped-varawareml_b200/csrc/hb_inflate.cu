@@ -354,6 +354,68 @@ int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<
     return HB_OK;
 }
 
+// ---- slab streaming: pre-allocated tables, enqueue only (no allocation, no synchronisation)
+int inflate_scratch_alloc(InflateScratch &sc, uint64_t comp_cap, uint32_t n_cap) {
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    sc.comp_cap = comp_cap; sc.n_cap = n_cap;
+    ck(cudaMalloc(&sc.d_comp, comp_cap + 64));
+    ck(cudaMalloc(&sc.d_coff, n_cap * 8ull)); ck(cudaMalloc(&sc.d_ooff, n_cap * 8ull));
+    ck(cudaMalloc(&sc.d_clen, n_cap * 4ull)); ck(cudaMalloc(&sc.d_olen, n_cap * 4ull));
+    ck(cudaMalloc(&sc.d_status, n_cap * 4ull));
+    ck(cudaMalloc(&sc.d_last_nl, 8));
+    if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc (inflate tables): ") + cudaGetErrorString(e));
+    return HB_OK;
+}
+void inflate_scratch_free(InflateScratch &sc) {
+    cudaFree(sc.d_comp); cudaFree(sc.d_coff); cudaFree(sc.d_ooff); cudaFree(sc.d_clen); cudaFree(sc.d_olen);
+    cudaFree(sc.d_status); cudaFree(sc.d_last_nl);
+    sc = InflateScratch();
+}
+// comp[0 .. comp_bytes): the compressed bytes of n consecutive members; coff relative to comp, ooff relative to d_out
+int inflate_bgzf_enqueue(InflateScratch &sc, const uint8_t *comp, uint64_t comp_bytes, const uint64_t *coff, const uint32_t *clen,
+                         const uint64_t *ooff, const uint32_t *olen, uint32_t n, uint8_t *d_out, cudaStream_t stream) {
+    if (!n) return HB_OK;
+    if (comp_bytes > sc.comp_cap || n > sc.n_cap) return api_fail(HB_ERR_ARG, "inflate scratch too small");
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ck(cudaMemcpyAsync(sc.d_comp, comp, comp_bytes, cudaMemcpyHostToDevice, stream));
+    ck(cudaMemsetAsync(sc.d_comp + comp_bytes, 0, 64, stream));
+    ck(cudaMemcpyAsync(sc.d_coff, coff, n * 8ull, cudaMemcpyHostToDevice, stream));
+    ck(cudaMemcpyAsync(sc.d_ooff, ooff, n * 8ull, cudaMemcpyHostToDevice, stream));
+    ck(cudaMemcpyAsync(sc.d_clen, clen, n * 4ull, cudaMemcpyHostToDevice, stream));
+    ck(cudaMemcpyAsync(sc.d_olen, olen, n * 4ull, cudaMemcpyHostToDevice, stream));
+    InflateArgs a{sc.d_comp, sc.d_coff, sc.d_clen, sc.d_ooff, sc.d_olen, d_out, n, sc.d_status};
+    inflate_bgzf_kernel<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, stream>>>(a);
+    count_launch();
+    ck(cudaGetLastError());
+    if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    return HB_OK;
+}
+
+// position of the last '\n' in buf[begin, end), or ~0: one CTA walks back from the end in 16 KiB steps
+__global__ void __launch_bounds__(1024) last_newline_kernel(const uint8_t *__restrict__ buf, uint64_t begin, uint64_t end,
+                                                            unsigned long long *__restrict__ res) {
+    __shared__ unsigned long long best;
+    if (threadIdx.x == 0) best = 0;
+    __syncthreads();
+    for (uint64_t hi = end; hi > begin;) {
+        const uint64_t lo = hi - begin > 16384 ? hi - 16384 : begin;
+        unsigned long long mine = 0;                        // position + 1
+        for (uint64_t q = lo + 16ull * threadIdx.x; q < hi && q < lo + 16ull * threadIdx.x + 16; ++q)
+            if (buf[q] == '\n') mine = q + 1;
+        if (mine) atomicMax(&best, mine);
+        __syncthreads();
+        if (best) break;
+        hi = lo;
+    }
+    if (threadIdx.x == 0) *res = best ? best - 1 : ~0ull;
+}
+void launch_last_newline(const uint8_t *d_buf, uint64_t begin, uint64_t end, unsigned long long *d_res, cudaStream_t stream) {
+    last_newline_kernel<<<1, 1024, 0, stream>>>(d_buf, begin, end, d_res);
+    count_launch();
+}
+
 }  // namespace hb
 
 using namespace hb;

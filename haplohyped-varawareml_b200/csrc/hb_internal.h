@@ -94,4 +94,20 @@ void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t 
 
 void count_launch(uint64_t n = 1);
 
+// BGZF slab streaming (hb_inflate.cu): device tables of one slot, enqueue-only inflate, last newline of a text range
+struct InflateScratch {
+    uint8_t *d_comp = nullptr;
+    uint64_t comp_cap = 0;
+    uint64_t *d_coff = nullptr, *d_ooff = nullptr;
+    uint32_t *d_clen = nullptr, *d_olen = nullptr;
+    int *d_status = nullptr;
+    unsigned long long *d_last_nl = nullptr;
+    uint32_t n_cap = 0;
+};
+int inflate_scratch_alloc(InflateScratch &sc, uint64_t comp_cap, uint32_t n_cap);
+void inflate_scratch_free(InflateScratch &sc);
+int inflate_bgzf_enqueue(InflateScratch &sc, const uint8_t *comp, uint64_t comp_bytes, const uint64_t *coff, const uint32_t *clen,
+                         const uint64_t *ooff, const uint32_t *olen, uint32_t n, uint8_t *d_out, cudaStream_t stream);
+void launch_last_newline(const uint8_t *d_buf, uint64_t begin, uint64_t end, unsigned long long *d_res, cudaStream_t stream);
+
 }  // namespace hb

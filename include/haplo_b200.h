@@ -122,6 +122,16 @@ int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int devic
 /* the same for the bytes of a .vcf / .vcf.gz already in host memory (BGZF bytes cross PCIe compressed and are
  * inflated on the GPU; pinned memory makes that copy asynchronous) */
 int hb_parse_vcf_bytes(const uint8_t *data, uint64_t nbytes, const char *region, int want_gt, int device, hb_parse **out);
+/* BGZF bytes of a .vcf.gz in (pinned) host memory -> the same results as hb_parse_stream_host, streamed: slabs of whole
+ * BGZF members (about slab_bytes of text each, 0 = 256 MiB) cross PCIe compressed, are inflated on the GPU behind the
+ * unfinished last line of the slab before, parsed and fetched; H2D + inflate of slab k + 1 and the D2H of slab k - 1
+ * overlap the parse of slab k.  This is the reference's whole read path (tbx_itr_next + vcf_parse1 + getGenotypes,
+ * vcfpp.h:1468-1472, :546-588) for all samples at once.  hb_bgzf_vcf_info gives what is needed to size the outputs. */
+int hb_bgzf_vcf_info(const uint8_t *bgzf, uint64_t nbytes, uint32_t *n_samples, uint64_t *text_bytes, uint64_t *body_offset);
+int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
+                              uint64_t slab_bytes, int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start,
+                              uint32_t *stop, char *ref, char *alt, uint32_t *ploidy_err, uint32_t *badgt_err,
+                              uint64_t *n_records, uint32_t *n_slabs);
 /* sample names of a file-level parse, NUL-separated */
 int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */

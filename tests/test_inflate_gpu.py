@@ -96,3 +96,45 @@ def test_bgzf_file_through_the_reference_api(capi, tmp_path, built):
     ora = oracle.parse_text(text, "*", "chr22")
     g0, g1 = p.matrix()
     assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
+
+
+@pytest.mark.parametrize("fmt,kinds,slab,block", [("GT", "phased", 5000, 0xff00), ("GT", "mixed", 30000, 4000),
+                                                  ("GT:GQ:DP", "mixed", 9000, 1500), ("GT", "mixed", 1 << 30, 0xff00)])
+def test_stream_bgzf_host_equals_oracle(capi, fmt, kinds, slab, block):
+    """hb_parse_stream_bgzf_host: BGZF members cross PCIe compressed in slabs, are inflated on the GPU behind the
+    unfinished line of the slab before, parsed and fetched -- the same matrix as the oracle, whatever the slab and
+    member sizes (lines straddle members and slabs)."""
+    text, samples = synth.random_vcf(1500, 41, seed=78, fmt=fmt, kinds=kinds)
+    ora = oracle.parse_text(text, "*", "chr22")
+    gz = synth.bgzf_compress(text, block=block)
+    ns, tb, body = capi.bgzf_vcf_info(gz)
+    assert ns == len(samples) and tb == len(text) and body == len(text) - len(synth.body_of(text))
+    r = capi.parse_stream_bgzf_host(gz, capacity=1500, region="chr22", slab_bytes=slab)
+    assert r["n"] == ora["n"] and r["n_slabs"] >= 1
+    if slab < len(text):
+        assert r["n_slabs"] > 1
+    assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"])
+    assert np.array_equal(r["start"], ora["start"]) and np.array_equal(r["stop"], ora["stop"])
+    assert np.array_equal(r["ref"], ora["ref"]) and np.array_equal(r["alt"], ora["alt"])
+    assert r["ploidy_err"].sum() == 0 and r["badgt_err"].sum() == 0
+    with pytest.raises(capi.HaploError):                               # capacity is checked, not overrun
+        capi.parse_stream_bgzf_host(gz, capacity=ora["n"] - 1, region="chr22", slab_bytes=slab)
+
+
+def test_stream_bgzf_host_edges(capi):
+    # no newline at the end of the file; a slab smaller than one line is an error, not a wrong result
+    text, samples = synth.random_vcf(300, 200, seed=9, fmt="GT", kinds="phased", site_mix=False)
+    ora = oracle.parse_text(text, "*", "chr22")
+    gz = synth.bgzf_compress(text[:-1], block=3000)
+    r = capi.parse_stream_bgzf_host(gz, capacity=300, region="chr22", slab_bytes=20000)
+    assert r["n"] == ora["n"] == 300 and r["n_slabs"] > 5
+    assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"]) and np.array_equal(r["start"], ora["start"])
+    with pytest.raises(capi.HaploError):
+        capi.parse_stream_bgzf_host(synth.bgzf_compress(text, block=300), capacity=300, region="chr22", slab_bytes=500)
+    # uniform GT-only text (walker path) in many slabs
+    spec = capi.synth_spec(4000, 300, seed=3, mix=1)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    ora = oracle.parse_text(text, "*", "chr22")
+    r = capi.parse_stream_bgzf_host(synth.bgzf_compress(text), capacity=4000, region="chr22", slab_bytes=len(text) // 7)
+    assert r["n"] == ora["n"] and r["n_slabs"] >= 7
+    assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"]) and np.array_equal(r["start"], ora["start"])
