@@ -361,6 +361,26 @@ def main():
                                   "matches_device_path": bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1)),
                                   "api": "hb_parse_vcf_bytes (BGZF in pinned host memory -> GPU inflate -> GPU parse) + hb_parse_fetch_matrix "
                                          "+ hb_parse_fetch_sites; rank 0 only", "bgzip_equivalent_host_s": t_comp}
+              # streamed: slabs of BGZF members, H2D + inflate / parse / D2H overlapped (hb_parse_stream_bgzf_host)
+              def bgzf_stream_step():
+                  capi.check(capi.lib().hb_parse_stream_bgzf_host(bgp.data_ptr(), bgp.numel(), b"chr22", 1, local, args.slab_bytes,
+                                                                  out0.data_ptr(), out1.data_ptr(), Vk, sites[0].data_ptr(),
+                                                                  sites[1].data_ptr(), sites[2].data_ptr(), sites[3].data_ptr(),
+                                                                  None, None, C.byref(nrec), None))
+                  assert nrec.value == Vk
+
+              out0.zero_(); out1.zero_()
+              bgzf_stream_step()
+              ok_stream = bool(np.array_equal(out0[S // 3].numpy(), g0) and np.array_equal(out1[S // 3].numpy(), g1))
+              t0 = time.perf_counter()
+              for _ in range(args.e2e_steps):
+                  bgzf_stream_step()
+              dts = time.perf_counter() - t0
+              e2e["from_bgzf_streamed"] = {"value": float(V) * S / (dts / args.e2e_steps), "unit": "calls/s",
+                                           "h2d_bytes_per_step": int(bgp.numel()), "d2h_bytes_per_step": 2 * S * Vk + 10 * Vk,
+                                           "steps": args.e2e_steps, "matches_device_path": ok_stream,
+                                           "api": "hb_parse_stream_bgzf_host: BGZF in pinned host memory -> slabs of %d MiB of text: "
+                                                  "H2D compressed + GPU inflate / GPU parse / D2H overlapped; rank 0 only" % (args.slab_bytes >> 20)}
               del bgp
           del host, out0, out1
     except Exception as ex:          # e.g. not enough pinnable host memory on a crowded box: the device-resident numbers stand
