@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bgzf", action="store_true", help="skip the e2e variant that starts from BGZF bytes")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--slab-bytes", type=int, default=256 << 20, help="slab size of the streamed e2e path")
+    ap.add_argument("--slab-bytes", type=int, default=1 << 30, help="slab size of the streamed e2e path")
     ap.add_argument("--parse-only", action="store_true", help="step = kernels 1-3 only (no Blosc2 frames)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

@@ -9,6 +9,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
@@ -51,10 +52,16 @@ static int ensure_device(int device) {
                                      std::string(e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) + ")");
     if (device < 0 || device >= n) return fail(HB_ERR_ARG, "bad device ordinal");
     CU(cudaSetDevice(device));
-    cudaDeviceProp p;
-    CU(cudaGetDeviceProperties(&p, device));
-    if (p.major != 10) return fail(HB_ERR_CUDA, "libhaplo_b200 is built for sm_100a only; device is sm_" +
-                                                    std::to_string(p.major) + std::to_string(p.minor));
+    // cudaGetDeviceProperties takes tens of milliseconds when the GPU is busy: two attributes, looked up once per device
+    static std::atomic<int> cc_major[64];
+    int major = device < 64 ? cc_major[device].load() : 0, minor = 0;
+    if (!major) {
+        CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        CU(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        if (major != 10) return fail(HB_ERR_CUDA, "libhaplo_b200 is built for sm_100a only; device is sm_" +
+                                                      std::to_string(major) + std::to_string(minor));
+        if (device < 64) cc_major[device].store(major);
+    }
     return HB_OK;
 }
 
@@ -106,6 +113,7 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->h_st_pin) cudaFreeHost(p->h_st_pin);
     delete p;
 }
 
@@ -118,6 +126,24 @@ static int dev_alloc(T **p, uint64_t n) {
     return HB_OK;
 }
 #define TRY(expr) do { int rc_ = (expr); if (rc_ != HB_OK) return rc_; } while (0)
+
+// device status -> host, through PINNED memory: a D2H copy into pageable memory is staged by the driver and was seen to
+// wait behind the 256 MiB H2D copy of the next slab that streams on another stream (hb_parse_stream_host)
+static int fetch_status(hb_parse *p) {
+    if (!p->h_st_pin && cudaMallocHost((void **)&p->h_st_pin, sizeof(DevStatus)) != cudaSuccess) {
+        cudaGetLastError();
+        p->h_st_pin = nullptr;                             // no pinned memory left: the pageable copy still works
+        cudaError_t e = cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+        return HB_OK;
+    }
+    cudaError_t e = cudaMemcpyAsync(p->h_st_pin, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    p->h_st = *p->h_st_pin;
+    return HB_OK;
+}
 
 // look at the first record of the body: FORMAT == "GT" -> newline-only tokenizer is enough;
 // and exactly 4 bytes per sample after the 9th tab -> the walker (hb_walk.cu) applies
@@ -207,8 +233,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
                  p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_chrom5, p->d_rowinfo,
                  p->d_nu_rows, p->d_sites_state, p->d_st, L);
     CU(cudaEventRecord(p->ev[2], p->stream));
-    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    TRY(fetch_status(p));
     CU(cudaGetLastError());
     p->index_used = p->with_tabs ? 2 : 1;
     return HB_OK;
@@ -233,8 +258,7 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
     launch_walk_count(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
                       p->d_wstart, p->d_wcount, p->d_wrow, p->d_st, L);
     CU(cudaEventRecord(p->ev[1], p->stream));
-    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    TRY(fetch_status(p));
     CU(cudaGetLastError());
     const uint64_t n_lines = p->h_st.n_lines, n_rec = p->h_st.n_records;
     p->n_lines = n_lines;
@@ -325,8 +349,7 @@ static int run_parse(hb_parse *p) {
     }
     CU(cudaEventRecord(p->ev[3], p->stream));
     launch_chrom_runs(p->d_text, p->d_chrom_abs, p->d_chrom_len, n_rec, p->d_run_rows, hb_parse::kMaxRuns, p->d_st, L);
-    CU(cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream));
-    CU(cudaStreamSynchronize(p->stream));
+    TRY(fetch_status(p));
     CU(cudaGetLastError());
     cudaEventElapsedTime(&p->ms_tok, p->ev[0], p->ev[1]);
     cudaEventElapsedTime(&p->ms_sites, p->ev[1], p->ev[2]);
@@ -416,6 +439,86 @@ int hb_parse_host_text(const uint8_t *text, uint64_t nbytes, const hb_parse_opts
 // per call going back hide behind the 4 bytes per call coming in).  Device memory is O(slab), so the
 // text may be far larger than HBM.
 // ---------------------------------------------------------------------------------------------
+// ---- the two device slots of the streaming entry points.  Making and freeing them costs little on a good day and
+// hundreds of milliseconds on a bad one (cudaMalloc / cudaFree of the slab buffers: 150 ms setup, 340-520 ms cleanup were
+// measured inside otherwise 225 ms calls), so a finished call leaves them in a per-process cache for the next call with the
+// same options; hb_cache_clear() frees them.
+namespace {
+struct StreamSlot {
+    hb_parse *p = nullptr;
+    cudaStream_t compute = nullptr, d2h = nullptr;
+    cudaEvent_t fetched = nullptr;
+    // BGZF streaming only
+    hb::InflateScratch sc;
+    uint8_t *buf = nullptr;                       // [carry_cap + 32 | slab text | '\n' + 256]
+    unsigned long long *h_pin = nullptr;          // pinned: [last newline | inflate status of every member]
+    std::vector<uint64_t> hc, ho;
+    uint64_t x = 0, end = 0, begin = 0;           // slab text at buf + x .. buf + end; the parse starts at buf + begin
+};
+struct StreamSlots {
+    StreamSlot slot[2];
+    size_t n_slots = 0;
+    int device = -1, want_gt = 0, end_is_int = 0, tokenizer = 0;
+    uint32_t n_samples = 0;
+    std::string region;
+    uint64_t text_cap = 0, comp_cap = 0, carry_cap = 0;
+    uint32_t n_cap = 0;
+    void destroy() {
+        if (device >= 0) cudaSetDevice(device);
+        for (auto &s : slot) {
+            if (s.compute) cudaStreamSynchronize(s.compute);
+            if (s.d2h) cudaStreamSynchronize(s.d2h);
+            if (s.p) { if (s.buf) s.p->d_text = nullptr; hb_parse_free(s.p); }
+            cudaFree(s.buf);
+            if (s.h_pin) cudaFreeHost(s.h_pin);
+            hb::inflate_scratch_free(s.sc);
+            if (s.fetched) cudaEventDestroy(s.fetched);
+            if (s.compute) cudaStreamDestroy(s.compute);
+            if (s.d2h) cudaStreamDestroy(s.d2h);
+            s = StreamSlot();
+        }
+        n_slots = 0;
+    }
+    bool same_options(const hb_parse_opts &o) const {
+        return device == o.device && n_samples == o.n_samples && want_gt == (o.want_gt ? 1 : 0) && end_is_int == (o.end_is_int ? 1 : 0) &&
+               tokenizer == o.tokenizer && region == (o.region ? o.region : "");
+    }
+};
+struct SlotCache { std::mutex mu; StreamSlots *kept = nullptr; bool in_use = false; };
+SlotCache g_text_slots, g_bgzf_slots;
+
+// the cached slots when they were made with these options and are free, else fresh (empty) ones
+StreamSlots *acquire_slots(SlotCache &c, const hb_parse_opts &o, size_t n_slots) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.kept && !c.in_use) {
+        if (c.kept->same_options(o) && c.kept->n_slots >= n_slots) { c.in_use = true; return c.kept; }
+        c.kept->destroy();
+        delete c.kept;
+        c.kept = nullptr;
+    }
+    StreamSlots *ss = new StreamSlots();
+    ss->device = o.device; ss->n_samples = o.n_samples; ss->want_gt = o.want_gt ? 1 : 0; ss->end_is_int = o.end_is_int ? 1 : 0;
+    ss->tokenizer = o.tokenizer; ss->region = o.region ? o.region : "";
+    return ss;
+}
+void release_slots(SlotCache &c, StreamSlots *ss, bool keep) {
+    if (keep) for (auto &s : ss->slot) { if (s.compute) cudaStreamSynchronize(s.compute); if (s.d2h) cudaStreamSynchronize(s.d2h); }
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (ss == c.kept) {
+        c.in_use = false;
+        if (!keep) { ss->destroy(); delete ss; c.kept = nullptr; }
+        return;
+    }
+    if (keep && !c.kept) { c.kept = ss; return; }
+    ss->destroy();
+    delete ss;
+}
+void clear_slot_cache(SlotCache &c) {
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.kept && !c.in_use) { c.kept->destroy(); delete c.kept; c.kept = nullptr; }
+}
+}  // namespace
+
 int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_opts *opts, uint64_t slab_bytes,
                          int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start, uint32_t *stop, char *ref,
                          char *alt, uint32_t *ploidy_err, uint32_t *badgt_err, uint64_t *n_records, uint32_t *n_slabs) {
@@ -444,20 +547,17 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
         off = end;
     }
     TRY(ensure_device(opts->device));
-    struct Slot { hb_parse *p = nullptr; cudaStream_t compute = nullptr, d2h = nullptr; cudaEvent_t fetched = nullptr; } slot[2];
+    const bool trace = getenv("HB_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_setup = 0, t_loop = 0, t_tail = 0, t_parse = 0, t_maxparse = 0;
+    typedef StreamSlot Slot;
     int rc = HB_OK;
-    auto cleanup = [&]() {
-        for (auto &s : slot) {
-            if (s.compute) cudaStreamSynchronize(s.compute);
-            if (s.d2h) cudaStreamSynchronize(s.d2h);
-            if (s.p) hb_parse_free(s.p);
-            if (s.fetched) cudaEventDestroy(s.fetched);
-            if (s.compute) cudaStreamDestroy(s.compute);
-            if (s.d2h) cudaStreamDestroy(s.d2h);
-        }
-    };
     const size_t n_slots = std::min<size_t>(2, slabs.size());
-    for (size_t i = 0; i < n_slots && rc == HB_OK; ++i) {
+    StreamSlots *ss = acquire_slots(g_text_slots, *opts, n_slots);
+    Slot *slot = ss->slot;
+    auto cleanup = [&]() { release_slots(g_text_slots, ss, rc == HB_OK); };
+    for (size_t i = ss->n_slots; i < n_slots && rc == HB_OK; ++i) {      // slots the cache did not have
         Slot &s = slot[i];
         if (cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking) != cudaSuccess ||
@@ -465,17 +565,25 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
         hb_parse_opts o = *opts;
         o.stream = s.compute;
         rc = new_parse(&o, &s.p);
-        if (rc == HB_OK) rc = dev_alloc(&s.p->d_text_owned, cap + 256);
-        if (rc == HB_OK) s.p->d_text = s.p->d_text_owned;
+        if (rc == HB_OK) ss->n_slots = i + 1;
     }
+    for (size_t i = 0; i < ss->n_slots && rc == HB_OK; ++i) {
+        Slot &s = slot[i];
+        s.p->probed = false;                         // this call's text may have another shape than the last one's
+        if (ss->text_cap < cap || !s.p->d_text_owned) {
+            rc = dev_alloc(&s.p->d_text_owned, std::max(cap + cap / 16, ss->text_cap) + 256);
+            if (rc == HB_OK) s.p->d_text = s.p->d_text_owned;
+        }
+    }
+    if (rc == HB_OK && ss->text_cap < cap) ss->text_cap = cap + cap / 16;
     if (rc != HB_OK) { cleanup(); return rc; }
     auto h2d = [&](size_t k) -> cudaError_t {
         Slot &s = slot[k & 1];
-        cudaError_t e = cudaStreamWaitEvent(s.compute, s.fetched, 0);       // the slot's previous results have left
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s.p->d_text_owned, text + slabs[k].first, slabs[k].second, cudaMemcpyHostToDevice, s.compute);
+        cudaError_t e = cudaMemcpyAsync(s.p->d_text_owned, text + slabs[k].first, slabs[k].second, cudaMemcpyHostToDevice, s.compute);
         if (e == cudaSuccess) e = cudaMemsetAsync(s.p->d_text_owned + slabs[k].second, 0, 256, s.compute);
         return e;
     };
+    t_setup = now() - t_begin;
     cudaError_t e = h2d(0);
     uint64_t R = 0;
     std::vector<uint32_t> pl(opts->n_samples), bg(opts->n_samples);
@@ -484,7 +592,11 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
         if (e != cudaSuccess) break;
         Slot &s = slot[k & 1];
         s.p->nbytes = slabs[k].second;
+        e = cudaStreamWaitEvent(s.compute, s.fetched, 0);       // the slot's previous results have left (the H2D copy did not need that)
+        if (e != cudaSuccess) break;
+        const double tp = now();
         rc = run_parse(s.p);                         // returns with the slot's compute stream idle
+        { const double d = now() - tp; t_parse += d; t_maxparse = std::max(t_maxparse, d); }
         if (rc != HB_OK) break;
         const uint64_t n = s.p->h_st.n_records;
         if (R + n > out_stride) { rc = fail(HB_ERR_ARG, "more records than the output arrays hold"); break; }
@@ -510,8 +622,14 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
         if (e == cudaSuccess) e = cudaEventRecord(s.fetched, s.d2h);
         R += n;
     }
-    for (auto &s : slot) if (s.d2h && e == cudaSuccess) e = cudaStreamSynchronize(s.d2h);
+    t_loop = now() - t_begin - t_setup;
+    for (size_t i = 0; i < ss->n_slots; ++i) if (slot[i].d2h && e == cudaSuccess) e = cudaStreamSynchronize(slot[i].d2h);
+    t_tail = now() - t_begin - t_setup - t_loop;
+    if (e != cudaSuccess && rc == HB_OK) rc = fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     cleanup();
+    if (trace)
+        fprintf(stderr, "[hb_parse_stream_host] %zu slabs: setup %.1f ms, loop %.1f ms (run_parse %.1f, longest %.1f), D2H tail %.1f ms, cleanup %.1f ms\n",
+                slabs.size(), t_setup, t_loop, t_parse, t_maxparse, t_tail, now() - t_begin - t_setup - t_loop - t_tail);
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     *n_records = R;
@@ -1050,6 +1168,8 @@ void hb_cache_clear(void) {
         g_cache.clear();
     }
     hb::frames_buffer_cache_clear();
+    clear_slot_cache(g_text_slots);
+    clear_slot_cache(g_bgzf_slots);
 }
 
 const char *hb_last_error(void) { return g_err.c_str(); }
@@ -1092,12 +1212,17 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
     if (!bgzf || !n_records) return fail(HB_ERR_ARG, "null argument");
     *n_records = 0;
     if (n_slabs) *n_slabs = 0;
+    const bool trace = getenv("HB_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_index = 0, t_setup = 0, t_wait = 0, t_parse = 0, t_enq = 0;
     std::vector<uint64_t> coff, ooff;
     std::vector<uint32_t> clen, olen;
     uint64_t total = 0;
     if (!bgzf_index(bgzf, nbytes, coff, clen, ooff, olen, total)) return fail(HB_ERR_IO, "not a BGZF file");
     FileText ft;
     TRY(bgzf_header(bgzf, coff, clen, olen, ft));
+    t_index = now() - t_begin;
     hb_parse_opts opts;
     memset(&opts, 0, sizeof opts);
     opts.region = region;
@@ -1108,7 +1233,7 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
     if (ploidy_err) memset(ploidy_err, 0, 4ull * opts.n_samples);
     if (badgt_err) memset(badgt_err, 0, 4ull * opts.n_samples);
     if (total <= ft.body) return HB_OK;
-    if (slab_bytes == 0) slab_bytes = 256ull << 20;
+    if (slab_bytes == 0) slab_bytes = 1ull << 30;
     // slabs of whole members, about slab_bytes of text each
     struct Slab { size_t m0, m1; uint64_t text; uint64_t comp0, comp; };
     std::vector<Slab> slabs;
@@ -1126,56 +1251,55 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
     if (ft.body >= slabs[0].text) return fail(HB_ERR_ARG, "the VCF header is longer than a slab: raise slab_bytes");
     const uint64_t carry_cap = std::min<uint64_t>((text_cap + 15) & ~15ull, 256ull << 20);   // longest unfinished line carried over
     TRY(ensure_device(device));
-    struct Slot {
-        hb_parse *p = nullptr;
-        cudaStream_t compute = nullptr, d2h = nullptr;
-        cudaEvent_t fetched = nullptr;
-        InflateScratch sc;
-        uint8_t *buf = nullptr;                       // [carry_cap + 16 | slab text | '\n' + 256]
-        std::vector<uint64_t> hc, ho;
-        std::vector<int> status;
-        unsigned long long last_nl = 0;
-        uint64_t x = 0, end = 0, begin = 0;           // slab text at buf + x .. buf + end; the parse starts at buf + begin
-    } slot[2];
+    typedef StreamSlot Slot;
     int rc = HB_OK;
-    auto cleanup = [&]() {
-        for (auto &s : slot) {
-            if (s.compute) cudaStreamSynchronize(s.compute);
-            if (s.d2h) cudaStreamSynchronize(s.d2h);
-            if (s.p) { s.p->d_text = nullptr; hb_parse_free(s.p); }
-            cudaFree(s.buf);
-            inflate_scratch_free(s.sc);
-            if (s.fetched) cudaEventDestroy(s.fetched);
-            if (s.compute) cudaStreamDestroy(s.compute);
-            if (s.d2h) cudaStreamDestroy(s.d2h);
-        }
-    };
     const size_t n_slots = std::min<size_t>(2, slabs.size());
+    StreamSlots *ss = acquire_slots(g_bgzf_slots, opts, n_slots);
+    Slot *slot = ss->slot;
+    auto cleanup = [&]() { release_slots(g_bgzf_slots, ss, rc == HB_OK); };
+    // buffers grow together when any capacity is short (the carry offset is part of the layout)
+    const bool grow = ss->text_cap < text_cap || ss->comp_cap < comp_cap || ss->n_cap < n_cap || ss->carry_cap < carry_cap;
+    if (grow) {
+        ss->text_cap = std::max(ss->text_cap, text_cap + text_cap / 16);
+        ss->comp_cap = std::max(ss->comp_cap, comp_cap + comp_cap / 8);
+        ss->n_cap = std::max<uint32_t>(ss->n_cap, (uint32_t)(n_cap + n_cap / 8 + 16));
+        ss->carry_cap = std::max(ss->carry_cap, carry_cap);
+    }
     for (size_t i = 0; i < n_slots && rc == HB_OK; ++i) {
         Slot &s = slot[i];
-        if (cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.fetched, cudaEventDisableTiming) != cudaSuccess) { rc = fail(HB_ERR_CUDA, "cannot create streams"); break; }
-        hb_parse_opts o = opts;
-        o.stream = s.compute;
-        rc = new_parse(&o, &s.p);
-        if (rc == HB_OK) rc = dev_alloc(&s.buf, carry_cap + 32 + text_cap + 1 + 256);
-        if (rc == HB_OK) rc = inflate_scratch_alloc(s.sc, comp_cap, (uint32_t)n_cap);
-        s.hc.resize(n_cap); s.ho.resize(n_cap); s.status.resize(n_cap);
+        if (!s.p) {
+            if (cudaStreamCreateWithFlags(&s.compute, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&s.d2h, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.fetched, cudaEventDisableTiming) != cudaSuccess) { rc = fail(HB_ERR_CUDA, "cannot create streams"); break; }
+            hb_parse_opts o = opts;
+            o.stream = s.compute;
+            rc = new_parse(&o, &s.p);
+            if (rc == HB_OK) ss->n_slots = std::max(ss->n_slots, i + 1);
+        }
+        if (rc != HB_OK) break;
+        s.p->probed = false;
+        if (grow || !s.buf) {
+            if (s.h_pin) { cudaFreeHost(s.h_pin); s.h_pin = nullptr; }
+            inflate_scratch_free(s.sc);
+            rc = dev_alloc(&s.buf, ss->carry_cap + 32 + ss->text_cap + 1 + 256);
+            if (rc == HB_OK) rc = inflate_scratch_alloc(s.sc, ss->comp_cap, ss->n_cap);
+            s.hc.resize(ss->n_cap); s.ho.resize(ss->n_cap);
+            if (rc == HB_OK && cudaMallocHost((void **)&s.h_pin, 8 + 4ull * ss->n_cap) != cudaSuccess) rc = fail(HB_ERR_MEM, "cudaMallocHost failed");
+        }
     }
     if (rc != HB_OK) { cleanup(); return rc; }
+    const uint64_t carry_base = ss->carry_cap;                 // offset of a slab's text when nothing is carried
     cudaError_t e = cudaSuccess;
     // H2D + inflate of slab k behind a carry of carry_len bytes, then the search for its last newline
     auto enqueue = [&](size_t k, uint64_t carry_len) -> int {
         Slot &s = slot[k & 1];
         const Slab &sl = slabs[k];
         const uint64_t skip = k == 0 ? ft.body : 0;            // slab 0 starts with the header
-        s.x = carry_cap + (k == 0 ? (16 - ft.body % 16) % 16 : carry_len % 16);    // the parse starts on a 16-byte boundary
+        s.x = carry_base + (k == 0 ? (16 - ft.body % 16) % 16 : carry_len % 16);   // the parse starts on a 16-byte boundary
         s.begin = s.x + skip - carry_len;
         s.end = s.x + sl.text;
         const uint32_t n = (uint32_t)(sl.m1 - sl.m0);
         for (uint32_t i = 0; i < n; ++i) { s.hc[i] = coff[sl.m0 + i] - sl.comp0; s.ho[i] = s.x + (ooff[sl.m0 + i] - ooff[sl.m0]); }
-        if (cudaStreamWaitEvent(s.compute, s.fetched, 0) != cudaSuccess) return fail(HB_ERR_CUDA, "cudaStreamWaitEvent failed");
         int r = inflate_bgzf_enqueue(s.sc, bgzf + sl.comp0, sl.comp, s.hc.data(), clen.data() + sl.m0, s.ho.data(), olen.data() + sl.m0, n, s.buf, s.compute);
         if (r != HB_OK) return r;
         if (k + 1 == slabs.size()) {                           // a file that does not end with a newline
@@ -1183,45 +1307,54 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
             if (ee != cudaSuccess) return fail(HB_ERR_CUDA, "cudaMemsetAsync failed");
         }
         launch_last_newline(s.buf, s.x + skip, s.end, s.sc.d_last_nl, s.compute);
-        cudaError_t ee = cudaMemcpyAsync(&s.last_nl, s.sc.d_last_nl, 8, cudaMemcpyDeviceToHost, s.compute);
-        if (ee == cudaSuccess) ee = cudaMemcpyAsync(s.status.data(), s.sc.d_status, 4ull * n, cudaMemcpyDeviceToHost, s.compute);
+        cudaError_t ee = cudaMemcpyAsync(s.h_pin, s.sc.d_last_nl, 8, cudaMemcpyDeviceToHost, s.compute);
+        if (ee == cudaSuccess) ee = cudaMemcpyAsync(s.h_pin + 1, s.sc.d_status, 4ull * n, cudaMemcpyDeviceToHost, s.compute);
         if (ee != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(ee));
         return HB_OK;
     };
+    t_setup = now() - t_begin - t_index;
     rc = enqueue(0, 0);
     uint64_t R = 0;
     std::vector<uint32_t> pl(opts.n_samples), bg(opts.n_samples);
     for (size_t k = 0; k < slabs.size() && rc == HB_OK && e == cudaSuccess; ++k) {
         Slot &s = slot[k & 1];
+        { const double t0 = now();
         e = cudaStreamSynchronize(s.compute);                  // slab k is inflated, its last newline is known
+        t_wait += now() - t0; }
         if (e != cudaSuccess) break;
+        const unsigned long long last_nl = s.h_pin[0];
+        const int *status = reinterpret_cast<const int *>(s.h_pin + 1);
         for (size_t i = 0; i < slabs[k].m1 - slabs[k].m0; ++i)
-            if (s.status[i]) { rc = fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(slabs[k].m0 + i) + ", code " + std::to_string(s.status[i]) + ")"); break; }
+            if (status[i]) { rc = fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(slabs[k].m0 + i) + ", code " + std::to_string(status[i]) + ")"); break; }
         if (rc != HB_OK) break;
         const bool last = k + 1 == slabs.size();
         uint64_t parse_end;                                     // one past the last newline of the slab's text
-        if (s.last_nl == ~0ull) {
+        if (last_nl == ~0ull) {
             if (!last) { rc = fail(HB_ERR_ARG, "a line is longer than a slab: raise slab_bytes"); break; }
             parse_end = s.begin;
-        } else parse_end = s.last_nl + 1;
+        } else parse_end = last_nl + 1;
         if (last && parse_end < s.end) parse_end = s.end + 1;   // no newline at the end of the file: the one appended ends the last line
         const uint64_t carry_len = last ? 0 : s.end - parse_end;
-        if (carry_len > carry_cap) { rc = fail(HB_ERR_ARG, "a line is longer than the carry buffer: raise slab_bytes"); break; }
+        if (carry_len > carry_base) { rc = fail(HB_ERR_ARG, "a line is longer than the carry buffer: raise slab_bytes"); break; }
         if (!last) {
             Slot &nx = slot[(k + 1) & 1];
             // the unfinished line goes in front of the next slab's text (that buffer's last parse has returned)
-            const uint64_t nx_x = carry_cap + carry_len % 16;
+            const uint64_t nx_x = carry_base + carry_len % 16;
             if (carry_len) e = cudaMemcpyAsync(nx.buf + nx_x - carry_len, s.buf + parse_end, carry_len, cudaMemcpyDeviceToDevice, s.compute);
             if (e != cudaSuccess) break;
         }
         e = cudaMemsetAsync(s.buf + parse_end, 0, 256, s.compute);
         if (e != cudaSuccess) break;
-        if (!last) { rc = enqueue(k + 1, carry_len); if (rc != HB_OK) break; }
+        if (!last) { const double t0 = now(); rc = enqueue(k + 1, carry_len); t_enq += now() - t0; if (rc != HB_OK) break; }
         uint64_t n = 0;
         if (parse_end > s.begin) {
+            e = cudaStreamWaitEvent(s.compute, s.fetched, 0);   // the slot's previous results have left (the inflate did not need that)
+            if (e != cudaSuccess) break;
             s.p->d_text = s.buf + s.begin;
             s.p->nbytes = parse_end - s.begin;
+            const double t0 = now();
             rc = run_parse(s.p);                                // returns with the slot's compute stream idle
+            t_parse += now() - t0;
             if (rc != HB_OK) break;
             n = s.p->h_st.n_records;
         }
@@ -1248,8 +1381,14 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
         if (e == cudaSuccess) e = cudaEventRecord(s.fetched, s.d2h);
         R += n;
     }
-    for (auto &s : slot) if (s.d2h && e == cudaSuccess && rc == HB_OK) e = cudaStreamSynchronize(s.d2h);
+    for (size_t i = 0; i < ss->n_slots; ++i) if (slot[i].d2h && e == cudaSuccess && rc == HB_OK) e = cudaStreamSynchronize(slot[i].d2h);
+    if (e != cudaSuccess && rc == HB_OK) rc = fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    const double t_loop_end = now();
     cleanup();
+    if (trace)
+        fprintf(stderr, "[hb_parse_stream_bgzf_host] %zu slabs: index+header %.1f ms, setup %.1f ms, waits for inflate %.1f ms, enqueue %.1f ms, "
+                        "run_parse %.1f ms, loop+tail %.1f ms, release %.1f ms\n", slabs.size(), t_index, t_setup, t_wait, t_enq, t_parse,
+                t_loop_end - t_begin - t_index - t_setup, now() - t_loop_end);
     if (rc != HB_OK) return rc;
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     *n_records = R;

@@ -42,6 +42,7 @@ struct hb_parse {
     uint64_t *d_cp = nullptr; uint64_t cp_rows = 0;
     hb::DevStatus *d_st = nullptr;
     hb::DevStatus h_st;
+    hb::DevStatus *h_st_pin = nullptr;       // pinned landing buffer of h_st
     uint32_t *d_start = nullptr, *d_stop = nullptr;
     uint8_t *d_ref = nullptr, *d_alt = nullptr, *d_chrom_len = nullptr;
     uint64_t *d_chrom_abs = nullptr;

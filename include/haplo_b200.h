@@ -123,7 +123,7 @@ int hb_parse_file(const char *in_vcf, const char *region, int want_gt, int devic
  * inflated on the GPU; pinned memory makes that copy asynchronous) */
 int hb_parse_vcf_bytes(const uint8_t *data, uint64_t nbytes, const char *region, int want_gt, int device, hb_parse **out);
 /* BGZF bytes of a .vcf.gz in (pinned) host memory -> the same results as hb_parse_stream_host, streamed: slabs of whole
- * BGZF members (about slab_bytes of text each, 0 = 256 MiB) cross PCIe compressed, are inflated on the GPU behind the
+ * BGZF members (about slab_bytes of text each, 0 = 1 GiB) cross PCIe compressed, are inflated on the GPU behind the
  * unfinished last line of the slab before, parsed and fetched; H2D + inflate of slab k + 1 and the D2H of slab k - 1
  * overlap the parse of slab k.  This is the reference's whole read path (tbx_itr_next + vcf_parse1 + getGenotypes,
  * vcfpp.h:1468-1472, :546-588) for all samples at once.  hb_bgzf_vcf_info gives what is needed to size the outputs. */
