@@ -394,7 +394,7 @@ __device__ __forceinline__ uint4 ldg_nc(const uint4 *p) {
 }
 
 constexpr int kMinZ = 5, kMinC = 4;
-constexpr int kWpc = 4;                       // warps (= frames) per CTA
+constexpr int kWpcMax = 12;                   // warps (= frames) per CTA: 4, 8 or 12, whichever fits most warps on an SM
 
 __device__ __forceinline__ uint32_t pack_lsb4(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
 __device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {       // bit j = byte j has one of bits 1..7 set
@@ -444,15 +444,16 @@ struct FusedArgs {
     uint32_t outcap;    // bytes of the frame-tail buffer
     uint32_t pf_dist;   // frames between a warp and the one that will follow it in its SM slot (0 = no L2 prefetch)
     uint32_t pf_dq, pf_dr;   // pf_dist = pf_dq * n_chunks + pf_dr
+    uint32_t wpc;       // warps per CTA
     uint32_t warp_smem;
 };
 
 template <int NW>
-__global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs A) {
+__global__ void __launch_bounds__(kWpcMax * 32) donor_frames_kernel(const FusedArgs A) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t n_frames = A.n_chunks * A.n_samples;
-    const uint64_t wid = (uint64_t)blockIdx.x * kWpc + warp;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (wid >= n_frames) return;
     const int cr = (int)A.cr, n = 2 * cr;
     uint8_t *base = smem + (size_t)warp * A.warp_smem;
@@ -1128,7 +1129,7 @@ struct hb_frames {
 
 template <int NW>
 static void launch_donor_frames(const FusedArgs &fa, uint64_t n_ctas, cudaStream_t st) {
-    donor_frames_kernel<NW><<<(unsigned)n_ctas, kWpc * 32, (size_t)kWpc * fa.warp_smem, st>>>(fa);
+    donor_frames_kernel<NW><<<(unsigned)n_ctas, fa.wpc * 32, (size_t)fa.wpc * fa.warp_smem, st>>>(fa);
 }
 template <int NW>
 static cudaError_t attr_donor_frames(size_t smem) {
@@ -1246,9 +1247,9 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         int sms = 148, per_sm = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
         // resident warps of this kernel on the whole GPU (shared memory decides): the distance to prefetch at
-        const size_t smem_cta = (size_t)kWpc * fa.warp_smem + 1024;
-        per_sm = (int)std::min<size_t>(32 / 1, (227 * 1024) / smem_cta);
-        fa.pf_dist = (uint32_t)(sms * per_sm * kWpc);
+        const size_t smem_cta = (size_t)fa.wpc * fa.warp_smem + 1024;
+        per_sm = (int)std::min<size_t>(32, (227 * 1024) / smem_cta);
+        fa.pf_dist = (uint32_t)(sms * std::min<uint32_t>(40, per_sm * fa.wpc));
         if (const char *e = getenv("HB_DF_PREFETCH")) fa.pf_dist = (uint32_t)atoi(e);
         fa.pf_dq = (uint32_t)(fa.pf_dist / f->n_chunks); fa.pf_dr = (uint32_t)(fa.pf_dist % f->n_chunks);
     }
@@ -1379,15 +1380,26 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     f->nw = (int)((seg + 31) / 32);
     FusedArgs &fa = f->fa;
     fa.bww = ((2 * cr + 15) / 32 + 14) & ~3u;        // words of the B (and of the N) bit string: 1 pad + both planes + look-ahead
-    fa.caps = seg / 4 + 2;
-    fa.dcap = (cr / 6 + cr / 5 + 8 + 7) & ~7u;           // Z runs take >= 6 bytes each (5 + a break), C runs >= 5
+    // most sequences in a segment: Z (>= 5) and C (>= 4) runs alternating without a gap, 2 per 9 positions
+    fa.caps = 2 * (seg / 9) + (seg % 9 >= 4 ? 1 : 0) + 1;
+    fa.dcap = (cr / 6 + cr / 5 + 2 + 7) & ~7u;           // a literal run + Z run take >= 6 positions (plane 0), + C run >= 5 (plane 1); + the last run
     fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
     fa.warp_smem = 8 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
     if (const char *e = getenv("HB_DF_PAD")) fa.warp_smem += (uint32_t)atoi(e) & ~15u;       // experiment: occupancy sensitivity
-    if ((size_t)kWpc * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
+    if ((size_t)4 * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
+    {   // warps per CTA: every CTA costs 1 KB of reserved shared memory on top of its warps' buffers
+        uint32_t best = 4, best_warps = 0;
+        for (uint32_t w : {4u, 8u, 12u}) {
+            const size_t cta = (size_t)w * fa.warp_smem + 1024;
+            const uint32_t warps = (uint32_t)std::min<size_t>(40, std::min<size_t>(32, (227 * 1024) / cta) * w);   // 49 registers per thread: 40 warps
+            if (warps > best_warps) { best = w; best_warps = warps; }
+        }
+        if (const char *e = getenv("HB_DF_WPC")) { const int v = atoi(e); if (v >= 1 && v <= kWpcMax && (size_t)v * fa.warp_smem + 1024 <= 227 * 1024) best = (uint32_t)v; }
+        fa.wpc = best;
+    }
     f->chunk_cap = f->n_chunks + 4;          // a re-run on a slightly longer record set (streaming) still fits
     const uint64_t n_frames = f->chunk_cap * f->n_samples;
-    f->n_ctas = (f->n_chunks * f->n_samples + kWpc - 1) / kWpc;
+    f->n_ctas = (f->n_chunks * f->n_samples + fa.wpc - 1) / fa.wpc;
     f->h_tmpl_len.resize(f->n_chunks);
     f->h_slot_off.resize(f->n_chunks + 1);
     cudaError_t e = cudaSuccess;
@@ -1437,7 +1449,7 @@ int hb_frames_rerun(hb_frames *f, hb_parse *p) {
             return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
         f->n_records = p->h_st.n_records;
         f->n_chunks = nc;
-        f->n_ctas = (nc * f->n_samples + kWpc - 1) / kWpc;
+        f->n_ctas = (nc * f->n_samples + f->fa.wpc - 1) / f->fa.wpc;
         f->h_tmpl_len.resize(nc);
         f->h_slot_off.resize(nc + 1);
         f->early_site = false;                   // an early template pass (if any) was made for the old shape
@@ -1451,7 +1463,7 @@ int hb_frames_set_window(hb_frames *f, uint32_t s0, uint32_t ns) {
     if (ns == 0 || ns > f->win_cap) return api_fail(HB_ERR_ARG, "window larger than the one the frames were made for");
     f->s0 = s0;
     f->n_samples = ns;
-    f->n_ctas = (f->n_chunks * (uint64_t)ns + kWpc - 1) / kWpc;
+    f->n_ctas = (f->n_chunks * (uint64_t)ns + f->fa.wpc - 1) / f->fa.wpc;
     f->layout_valid = false;
     return HB_OK;
 }

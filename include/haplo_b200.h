@@ -62,7 +62,8 @@ typedef struct hb_records {
 int hb_load_vcf(const char *in_vcf, const char *sample, const char *chrom, hb_records *out);
 int hb_load_vcf_without_sample(const char *in_vcf, const char *chrom, hb_records *out);
 void hb_records_free(hb_records *r);
-void hb_cache_clear(void);      /* drop the per-(file, region) device-resident parse cache and the kept frame buffer */
+void hb_cache_clear(void);      /* drop the per-(file, region) device-resident parse cache, the kept frame buffer and the
+                                 * device slots the streaming entry points keep between calls */
 
 /* ------------------------------------------------------------------------------------------
  * B. Text-level entry points: the kernels behind A, on a caller-supplied buffer of decompressed
