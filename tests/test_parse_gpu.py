@@ -321,3 +321,48 @@ def test_biobank_width_200k_samples(capi):
         raw = rec.tobytes() + b"\0" * (cr * 35 - rec.nbytes)
         (f,) = fr.sample(s)
         assert oracle.cframe_decode(f, cr * 35).tobytes() == raw
+
+
+def test_stream_slots_are_reused_and_safe_across_options_and_threads(capi):
+    """The streaming entry points keep their device slots between calls (hb_api.cu, StreamSlots cache): same options ->
+    reused; other options / other text shapes -> rebuilt; a concurrent call gets its own slots; hb_cache_clear frees them."""
+    import threading
+    t1, s1 = synth.random_vcf(900, 33, seed=5, fmt="GT", kinds="mixed")
+    t2, s2 = synth.random_vcf(700, 57, seed=6, fmt="GT:GQ:DP", kinds="mixed")
+    spec = capi.synth_spec(3000, 300, seed=8, mix=1)
+    t3 = capi.synth_header(spec) + capi.synth_host(spec)
+    cases = [(t1, len(s1)), (t2, len(s2)), (t3, 300), (t1, len(s1)), (t1, len(s1))]
+    oras = {id(t): oracle.parse_text(t, "*", "chr22") for t, _ in cases}
+
+    def check(text, ns, slab):
+        ora = oras[id(text)]
+        r = capi.parse_stream_host(synth.body_of(text), ns, capacity=ora["n"], region="chr22", slab_bytes=slab)
+        assert r["n"] == ora["n"]
+        assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"]) and np.array_equal(r["start"], ora["start"])
+
+    for text, ns in cases:                       # same handle options twice in a row, then others, then back
+        check(text, ns, 9000)
+        check(text, ns, 50000)                   # larger slabs than the cached buffers were made for
+    capi.lib().hb_cache_clear()
+    errs = []
+
+    def worker(text, ns):
+        try:
+            for _ in range(3):
+                check(text, ns, 7000)
+        except Exception as ex:                  # noqa: BLE001
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker, args=c) for c in cases[:3] + cases[:1]]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    # the BGZF form, alternating inputs
+    for text, ns in cases[:3] + cases[:1]:
+        ora = oras[id(text)]
+        for slab in (8000, 1 << 30):
+            r = capi.parse_stream_bgzf_host(synth.bgzf_compress(text, block=2500), capacity=ora["n"], region="chr22", slab_bytes=slab)
+            assert r["n"] == ora["n"] and np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["stop"], ora["stop"])
+    capi.lib().hb_cache_clear()
