@@ -101,7 +101,85 @@ using namespace hb;
 // =============================================================================================
 #include "hb_parse_struct.h"
 
-static void free_dev(void *p) { if (p) cudaFree(p); }
+// ---- big device buffers are pooled.  cudaMalloc / cudaFree of GB-sized buffers take anything from 10 to 500 ms on these
+// hosts (measured inside the streaming entry points); a converter that walks 22 chromosome files, or a caller that makes a
+// parse handle per file, would pay that for the text buffer and both allele planes every time.  Buffers >= 64 MiB that are
+// freed go to an idle list (at most 8 per process) and are handed out again to requests they fit with at most 50 % slack;
+// when a cudaMalloc fails the list is emptied and the call retried; hb_cache_clear() empties it too.
+namespace {
+struct DevPool {
+    static constexpr uint64_t kMin = 64ull << 20;
+    static constexpr size_t kMaxIdle = 8;
+    struct Item { void *p; uint64_t bytes; int device; };
+    std::mutex mu;
+    std::map<void *, Item> live;                 // big allocations handed out
+    std::vector<Item> idle;
+} g_pool;
+}
+namespace hb {
+void dev_pool_flush() {
+    std::vector<DevPool::Item> items;
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        items.swap(g_pool.idle);
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &it : items) { cudaSetDevice(it.device); cudaFree(it.p); }
+    cudaSetDevice(cur);
+}
+cudaError_t dev_pool_alloc(void **out, uint64_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    int device = 0;
+    cudaGetDevice(&device);
+    if (bytes >= DevPool::kMin) {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < g_pool.idle.size(); ++i) {
+            const auto &it = g_pool.idle[i];
+            if (it.device == device && it.bytes >= bytes && it.bytes <= bytes + bytes / 2 &&
+                (best == (size_t)-1 || it.bytes < g_pool.idle[best].bytes)) best = i;
+        }
+        if (best != (size_t)-1) {
+            DevPool::Item it = g_pool.idle[best];
+            g_pool.idle.erase(g_pool.idle.begin() + (long)best);
+            g_pool.live[it.p] = it;
+            *out = it.p;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {                      // memory held by idle buffers may be what is missing
+        cudaGetLastError();
+        dev_pool_flush();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess && bytes >= DevPool::kMin) {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        g_pool.live[*out] = DevPool::Item{*out, bytes, device};
+    }
+    return e;
+}
+void dev_pool_free(void *p) {
+    if (!p) return;
+    DevPool::Item it{nullptr, 0, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        auto f = g_pool.live.find(p);
+        if (f != g_pool.live.end()) { it = f->second; g_pool.live.erase(f); }
+    }
+    if (!it.p) { cudaFree(p); return; }
+    cudaDeviceSynchronize();                     // what cudaFree would have done: nothing in flight still uses the buffer
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        if (g_pool.idle.size() < DevPool::kMaxIdle) { g_pool.idle.push_back(it); return; }
+    }
+    cudaFree(p);
+}
+}  // namespace hb
+
+static void free_dev(void *p) { hb::dev_pool_free(p); }
 
 void hb_parse_free(hb_parse *p) {
     if (!p) return;
@@ -119,9 +197,9 @@ void hb_parse_free(hb_parse *p) {
 
 template <typename T>
 static int dev_alloc(T **p, uint64_t n) {
-    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (*p) { free_dev(*p); *p = nullptr; }
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    cudaError_t e = hb::dev_pool_alloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) return fail(HB_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     return HB_OK;
 }
@@ -268,7 +346,7 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
         TRY(dev_alloc(&p->d_ref, cap)); TRY(dev_alloc(&p->d_alt, cap));
         TRY(dev_alloc(&p->d_chrom_abs, cap)); TRY(dev_alloc(&p->d_chrom_len, cap)); TRY(dev_alloc(&p->d_chrom5, cap));
         TRY(dev_alloc(&p->d_rowinfo, cap)); TRY(dev_alloc(&p->d_nu_rows, cap));
-        if (p->d_sites_state) { cudaFree(p->d_sites_state); p->d_sites_state = nullptr; }
+        if (p->d_sites_state) { free_dev(p->d_sites_state); p->d_sites_state = nullptr; }
         p->row_cap = cap;
     }
     if (p->verify_cap < n_lines || !p->d_verify) {
@@ -469,7 +547,7 @@ struct StreamSlots {
             if (s.compute) cudaStreamSynchronize(s.compute);
             if (s.d2h) cudaStreamSynchronize(s.d2h);
             if (s.p) { if (s.buf) s.p->d_text = nullptr; hb_parse_free(s.p); }
-            cudaFree(s.buf);
+            free_dev(s.buf);
             if (s.h_pin) cudaFreeHost(s.h_pin);
             hb::inflate_scratch_free(s.sc);
             if (s.fetched) cudaEventDestroy(s.fetched);
@@ -641,6 +719,10 @@ int hb_parse_release_text(hb_parse *p) {
     if (!p) return fail(HB_ERR_ARG, "null handle");
     if (p->d_text_owned) {
         CU(cudaSetDevice(p->device));
+        {   // the caller wants the HBM back: not into the idle pool
+            std::lock_guard<std::mutex> lk(g_pool.mu);
+            g_pool.live.erase(p->d_text_owned);
+        }
         cudaFree(p->d_text_owned);
         p->d_text_owned = nullptr;
         p->d_text = nullptr;
@@ -1061,7 +1143,7 @@ int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_
         TRY(hb_parse_fetch_sample_errors(p, ce.ploidy_err.data(), ce.badgt_err.data()));
     }
     // the text is no longer needed once names are resolved: give the HBM back
-    if (p->d_text_owned) { cudaFree(p->d_text_owned); p->d_text_owned = nullptr; p->d_text = nullptr; }
+    if (p->d_text_owned) { free_dev(p->d_text_owned); p->d_text_owned = nullptr; p->d_text = nullptr; }
     return HB_OK;
 }
 
@@ -1170,6 +1252,7 @@ void hb_cache_clear(void) {
     hb::frames_buffer_cache_clear();
     clear_slot_cache(g_text_slots);
     clear_slot_cache(g_bgzf_slots);
+    hb::dev_pool_flush();
 }
 
 const char *hb_last_error(void) { return g_err.c_str(); }

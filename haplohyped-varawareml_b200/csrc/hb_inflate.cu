@@ -322,7 +322,7 @@ int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<
     int *d_status = nullptr;
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    ck(cudaMalloc(&d_comp, size + 64));
+    ck(dev_pool_alloc((void **)&d_comp, size + 64));
     ck(cudaMalloc(&d_coff, n * 8ull)); ck(cudaMalloc(&d_ooff, n * 8ull));
     ck(cudaMalloc(&d_clen, n * 4ull)); ck(cudaMalloc(&d_olen, n * 4ull));
     ck(cudaMalloc(&d_status, n * 4ull));
@@ -347,7 +347,7 @@ int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<
     }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    cudaFree(d_comp); cudaFree(d_coff); cudaFree(d_ooff); cudaFree(d_clen); cudaFree(d_olen); cudaFree(d_status);
+    dev_pool_free(d_comp); cudaFree(d_coff); cudaFree(d_ooff); cudaFree(d_clen); cudaFree(d_olen); cudaFree(d_status);
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     for (uint32_t i = 0; i < n; ++i)
         if (status[i]) return api_fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")");

@@ -94,6 +94,11 @@ void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t 
 
 void count_launch(uint64_t n = 1);
 
+// pooled big device buffers (hb_api.cu): cudaMalloc / cudaFree of GB-sized buffers are slow and erratic on these hosts
+cudaError_t dev_pool_alloc(void **out, uint64_t bytes);
+void dev_pool_free(void *p);
+void dev_pool_flush();
+
 // BGZF slab streaming (hb_inflate.cu): device tables of one slot, enqueue-only inflate, last newline of a text range
 struct InflateScratch {
     uint8_t *d_comp = nullptr;

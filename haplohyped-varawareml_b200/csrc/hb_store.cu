@@ -1234,6 +1234,7 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         // means cudaFree + cudaMalloc of many GB (~100 ms)
         const uint64_t cap = regrow ? need + need / 16 + (64ull << 20) : need + need / 64 + (16ull << 20);
         e = cudaMalloc(&f->d_frames, cap);
+        if (e != cudaSuccess) { cudaGetLastError(); dev_pool_flush(); e = cudaMalloc(&f->d_frames, cap); }     // idle pooled buffers may hold what is missing
         if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the frame buffer (") + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
         f->frames_cap = cap;
     }
