@@ -103,13 +103,13 @@ using namespace hb;
 
 // ---- big device buffers are pooled.  cudaMalloc / cudaFree of GB-sized buffers take anything from 10 to 500 ms on these
 // hosts (measured inside the streaming entry points); a converter that walks 22 chromosome files, or a caller that makes a
-// parse handle per file, would pay that for the text buffer and both allele planes every time.  Buffers >= 64 MiB that are
-// freed go to an idle list (at most 8 per process) and are handed out again to requests they fit with at most 50 % slack;
+// parse handle per file, would pay that for the text buffer, both allele planes and every column every time.  Buffers >= 1 MiB
+// that are freed go to an idle list (at most 48 per process) and are handed out again to requests they fit with at most 50 % slack;
 // when a cudaMalloc fails the list is emptied and the call retried; hb_cache_clear() empties it too.
 namespace {
 struct DevPool {
-    static constexpr uint64_t kMin = 64ull << 20;
-    static constexpr size_t kMaxIdle = 8;
+    static constexpr uint64_t kMin = 1ull << 20;
+    static constexpr size_t kMaxIdle = 48;
     struct Item { void *p; uint64_t bytes; int device; };
     std::mutex mu;
     std::map<void *, Item> live;                 // big allocations handed out
@@ -181,8 +181,11 @@ void dev_pool_free(void *p) {
 
 static void free_dev(void *p) { hb::dev_pool_free(p); }
 
+namespace { void pin_slot_release(hb::DevStatus *s); }
+
 void hb_parse_free(hb_parse *p) {
     if (!p) return;
+    const double t_free0 = getenv("HB_TRACE") ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
     cudaSetDevice(p->device);
     free_dev(p->d_text_owned); free_dev(p->d_nl_after); free_dev(p->d_cta); free_dev(p->d_cbase); free_dev(p->d_cp);
     free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
@@ -191,7 +194,8 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->h_st_pin) cudaFreeHost(p->h_st_pin);
+    pin_slot_release(p->h_st_pin);
+    if (t_free0 > 0) fprintf(stderr, "[hb_parse_free] %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_free0);
     delete p;
 }
 
@@ -207,10 +211,38 @@ static int dev_alloc(T **p, uint64_t n) {
 
 // device status -> host, through PINNED memory: a D2H copy into pageable memory is staged by the driver and was seen to
 // wait behind the 256 MiB H2D copy of the next slab that streams on another stream (hb_parse_stream_host)
+// pinned landing slots for the status words: cudaMallocHost / cudaFreeHost per handle cost up to 170 ms each on these hosts,
+// so one pinned block is made per process and its slots are handed out and taken back
+namespace {
+struct PinSlots {
+    static constexpr int kSlots = 256;
+    std::mutex mu;
+    DevStatus *base = nullptr;
+    bool tried = false;
+    std::vector<int> free_list;
+} g_pin;
+DevStatus *pin_slot_acquire() {
+    std::lock_guard<std::mutex> lk(g_pin.mu);
+    if (!g_pin.tried) {
+        g_pin.tried = true;
+        if (cudaMallocHost((void **)&g_pin.base, sizeof(DevStatus) * PinSlots::kSlots) != cudaSuccess) { cudaGetLastError(); g_pin.base = nullptr; }
+        else for (int i = PinSlots::kSlots - 1; i >= 0; --i) g_pin.free_list.push_back(i);
+    }
+    if (!g_pin.base || g_pin.free_list.empty()) return nullptr;
+    const int i = g_pin.free_list.back();
+    g_pin.free_list.pop_back();
+    return g_pin.base + i;
+}
+void pin_slot_release(DevStatus *s) {
+    if (!s) return;
+    std::lock_guard<std::mutex> lk(g_pin.mu);
+    g_pin.free_list.push_back((int)(s - g_pin.base));
+}
+}  // namespace
+
 static int fetch_status(hb_parse *p) {
-    if (!p->h_st_pin && cudaMallocHost((void **)&p->h_st_pin, sizeof(DevStatus)) != cudaSuccess) {
-        cudaGetLastError();
-        p->h_st_pin = nullptr;                             // no pinned memory left: the pageable copy still works
+    if (!p->h_st_pin && !(p->h_st_pin = pin_slot_acquire())) {
+        // no pinned slot left: the pageable copy still works
         cudaError_t e = cudaMemcpyAsync(&p->h_st, p->d_st, sizeof(DevStatus), cudaMemcpyDeviceToHost, p->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
         if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
@@ -1074,9 +1106,13 @@ int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, ui
     o.n_samples = (uint32_t)ft.samples.size();
     o.end_is_int = ft.end_is_int;
     hb_parse *p = nullptr;
+    const bool trace = getenv("HB_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     TRY(new_parse(&o, &p));
     const uint64_t pad = (16 - ft.body % 16) % 16;         // the records must start on a 16-byte boundary
     int rc = dev_alloc(&p->d_text_owned, pad + total + 1 + 256);
+    const double t1 = now();
     if (rc == HB_OK) rc = inflate_bgzf_to_device(raw.data(), raw.size(), coff, clen, ooff, olen, p->d_text_owned + pad, p->stream, &p->ms_inflate);
     uint8_t last = 0;
     cudaError_t e = cudaSuccess;
@@ -1089,7 +1125,9 @@ int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, ui
         p->d_text = p->d_text_owned + pad + ft.body;
         p->nbytes = end - pad - ft.body;
         p->compressed_bytes = raw.size();
+        const double t2 = now();
         rc = run_parse(p);
+        if (trace) fprintf(stderr, "[parse_bytes_common] text buffer %.1f ms, H2D + inflate %.1f ms, parse %.1f ms\n", t1 - t0, t2 - t1, now() - t2);
     }
     if (rc != HB_OK) { hb_parse_free(p); return rc; }
     *out = p;
@@ -1367,7 +1405,8 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
             rc = dev_alloc(&s.buf, ss->carry_cap + 32 + ss->text_cap + 1 + 256);
             if (rc == HB_OK) rc = inflate_scratch_alloc(s.sc, ss->comp_cap, ss->n_cap);
             s.hc.resize(ss->n_cap); s.ho.resize(ss->n_cap);
-            if (rc == HB_OK && cudaMallocHost((void **)&s.h_pin, 8 + 4ull * ss->n_cap) != cudaSuccess) rc = fail(HB_ERR_MEM, "cudaMallocHost failed");
+            // pinned: [last newline 8 | status 4n | coff 8n | ooff 8n | clen 4n | olen 4n] -- copies from / to pageable memory stall here
+            if (rc == HB_OK && cudaMallocHost((void **)&s.h_pin, 8 + 28ull * ss->n_cap + 8) != cudaSuccess) rc = fail(HB_ERR_MEM, "cudaMallocHost failed");
         }
     }
     if (rc != HB_OK) { cleanup(); return rc; }
@@ -1382,8 +1421,14 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
         s.begin = s.x + skip - carry_len;
         s.end = s.x + sl.text;
         const uint32_t n = (uint32_t)(sl.m1 - sl.m0);
-        for (uint32_t i = 0; i < n; ++i) { s.hc[i] = coff[sl.m0 + i] - sl.comp0; s.ho[i] = s.x + (ooff[sl.m0 + i] - ooff[sl.m0]); }
-        int r = inflate_bgzf_enqueue(s.sc, bgzf + sl.comp0, sl.comp, s.hc.data(), clen.data() + sl.m0, s.ho.data(), olen.data() + sl.m0, n, s.buf, s.compute);
+        const uint64_t nc = ss->n_cap + (ss->n_cap & 1);        // keeps the 8-byte tables aligned behind the status words
+        uint64_t *pc = reinterpret_cast<uint64_t *>(s.h_pin + 1 + nc / 2), *po = pc + ss->n_cap;
+        uint32_t *pcl = reinterpret_cast<uint32_t *>(po + ss->n_cap), *pol = pcl + ss->n_cap;
+        for (uint32_t i = 0; i < n; ++i) {
+            pc[i] = coff[sl.m0 + i] - sl.comp0; po[i] = s.x + (ooff[sl.m0 + i] - ooff[sl.m0]);
+            pcl[i] = clen[sl.m0 + i]; pol[i] = olen[sl.m0 + i];
+        }
+        int r = inflate_bgzf_enqueue(s.sc, bgzf + sl.comp0, sl.comp, pc, pcl, po, pol, n, s.buf, s.compute);
         if (r != HB_OK) return r;
         if (k + 1 == slabs.size()) {                           // a file that does not end with a newline
             cudaError_t ee = cudaMemsetAsync(s.buf + s.end, '\n', 1, s.compute);

@@ -12,6 +12,7 @@
 //     32-byte pieces of one match are independent), literals are stored by lane 0.
 // Stored and fixed-Huffman blocks are handled too.  CRC32 is not checked; ISIZE is.
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -310,6 +311,14 @@ bool bgzf_index(const uint8_t *raw, uint64_t size, std::vector<uint64_t> &coff, 
     return true;
 }
 
+// pinned staging for the member tables and the status words of inflate_bgzf_to_device: copies from / to pageable memory
+// were seen to stall for 100-1400 ms on these hosts; one pinned block per process, grown on demand, used under its lock
+namespace {
+std::mutex g_stage_mu;
+uint8_t *g_stage = nullptr;
+size_t g_stage_cap = 0;
+}
+
 // raw (host, BGZF) -> d_out (device, `total` bytes).  d_out must hold total bytes.
 int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<uint64_t> &coff,
                            const std::vector<uint32_t> &clen, const std::vector<uint64_t> &ooff,
@@ -323,31 +332,47 @@ int inflate_bgzf_to_device(const uint8_t *raw, uint64_t size, const std::vector<
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     ck(dev_pool_alloc((void **)&d_comp, size + 64));
-    ck(cudaMalloc(&d_coff, n * 8ull)); ck(cudaMalloc(&d_ooff, n * 8ull));
-    ck(cudaMalloc(&d_clen, n * 4ull)); ck(cudaMalloc(&d_olen, n * 4ull));
-    ck(cudaMalloc(&d_status, n * 4ull));
+    ck(dev_pool_alloc((void **)&d_coff, n * 8ull)); ck(dev_pool_alloc((void **)&d_ooff, n * 8ull));
+    ck(dev_pool_alloc((void **)&d_clen, n * 4ull)); ck(dev_pool_alloc((void **)&d_olen, n * 4ull));
+    ck(dev_pool_alloc((void **)&d_status, n * 4ull));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<int> status(n, 0);
+    std::lock_guard<std::mutex> stage_lock(g_stage_mu);
+    const size_t stage_need = 28ull * n;                 // coff, ooff (8 B), clen, olen, status (4 B)
+    if (e == cudaSuccess && g_stage_cap < stage_need) {
+        if (g_stage) cudaFreeHost(g_stage);
+        g_stage = nullptr; g_stage_cap = 0;
+        if (cudaMallocHost((void **)&g_stage, stage_need + stage_need / 4) == cudaSuccess) g_stage_cap = stage_need + stage_need / 4;
+        else cudaGetLastError();
+    }
+    const bool staged = g_stage_cap >= stage_need;
+    uint8_t *h_coff = g_stage, *h_ooff = g_stage + 8ull * n, *h_clen = g_stage + 16ull * n, *h_olen = g_stage + 20ull * n,
+            *h_status = g_stage + 24ull * n;
+    if (staged) {
+        memcpy(h_coff, coff.data(), 8ull * n); memcpy(h_ooff, ooff.data(), 8ull * n);
+        memcpy(h_clen, clen.data(), 4ull * n); memcpy(h_olen, olen.data(), 4ull * n);
+    }
     if (e == cudaSuccess) {
         ck(cudaMemcpyAsync(d_comp, raw, size, cudaMemcpyHostToDevice, stream));
         ck(cudaMemsetAsync(d_comp + size, 0, 64, stream));
-        ck(cudaMemcpyAsync(d_coff, coff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
-        ck(cudaMemcpyAsync(d_ooff, ooff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
-        ck(cudaMemcpyAsync(d_clen, clen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
-        ck(cudaMemcpyAsync(d_olen, olen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_coff, staged ? (const void *)h_coff : (const void *)coff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_ooff, staged ? (const void *)h_ooff : (const void *)ooff.data(), n * 8ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_clen, staged ? (const void *)h_clen : (const void *)clen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
+        ck(cudaMemcpyAsync(d_olen, staged ? (const void *)h_olen : (const void *)olen.data(), n * 4ull, cudaMemcpyHostToDevice, stream));
         InflateArgs a{d_comp, d_coff, d_clen, d_ooff, d_olen, d_out, n, d_status};
         if (ms) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, stream); }
         inflate_bgzf_kernel<<<(n + kInfWarps - 1) / kInfWarps, kInfWarps * 32, 0, stream>>>(a);
         count_launch();
         if (ms) cudaEventRecord(ev1, stream);
         ck(cudaGetLastError());
-        ck(cudaMemcpyAsync(status.data(), d_status, n * 4ull, cudaMemcpyDeviceToHost, stream));
+        ck(cudaMemcpyAsync(staged ? (void *)h_status : (void *)status.data(), d_status, n * 4ull, cudaMemcpyDeviceToHost, stream));
         ck(cudaStreamSynchronize(stream));
+        if (staged && e == cudaSuccess) memcpy(status.data(), h_status, 4ull * n);
         if (ms && e == cudaSuccess) cudaEventElapsedTime(ms, ev0, ev1);
     }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    dev_pool_free(d_comp); cudaFree(d_coff); cudaFree(d_ooff); cudaFree(d_clen); cudaFree(d_olen); cudaFree(d_status);
+    dev_pool_free(d_comp); dev_pool_free(d_coff); dev_pool_free(d_ooff); dev_pool_free(d_clen); dev_pool_free(d_olen); dev_pool_free(d_status);
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     for (uint32_t i = 0; i < n; ++i)
         if (status[i]) return api_fail(HB_ERR_IO, "BGZF inflate failed (member " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")");

@@ -1265,8 +1265,8 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         const uint64_t rw_cap = (f->chunk_cap * (uint64_t)cr + 31) / 32 + 8, rw = (f->n_chunks * (uint64_t)cr + 31) / 32 + 8;
         const uint64_t need_bits = 16ull * rw_cap * sp_cap;
         if (f->bits_cap < need_bits) {
-            if (f->d_bits) { cudaFree(f->d_bits); f->d_bits = nullptr; f->bits_cap = 0; }
-            e = cudaMalloc(&f->d_bits, need_bits);
+            if (f->d_bits) { dev_pool_free(f->d_bits); f->d_bits = nullptr; f->bits_cap = 0; }
+            e = dev_pool_alloc((void **)&f->d_bits, need_bits);
             if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the allele bit arrays (") + std::to_string(need_bits) + " bytes): " + cudaGetErrorString(e));
             f->bits_cap = need_bits;
         }
@@ -1338,8 +1338,8 @@ void hb_frames_free(hb_frames *f) {
         BufCache &c = g_fb[f->device];
         if (c.cap < f->frames_cap) { std::swap(c.p, f->d_frames); std::swap(c.cap, f->frames_cap); }
     }
-    cudaFree(f->d_tmpl); cudaFree(f->d_frames); cudaFree(f->d_tmpl_len); cudaFree(f->d_size);
-    cudaFree(f->d_slot_off); cudaFree(f->d_totals); cudaFree(f->d_bits);
+    dev_pool_free(f->d_tmpl); cudaFree(f->d_frames); dev_pool_free(f->d_tmpl_len); dev_pool_free(f->d_size);
+    dev_pool_free(f->d_slot_off); dev_pool_free(f->d_totals); dev_pool_free(f->d_bits);
     if (f->ev_pack) cudaEventDestroy(f->ev_pack);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
     if (f->ev_sites) cudaEventDestroy(f->ev_sites);
@@ -1405,11 +1405,11 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     f->h_slot_off.resize(f->n_chunks + 1);
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    ck(cudaMalloc(&f->d_tmpl, f->chunk_cap * (uint64_t)f->tmpl_cap));
-    ck(cudaMalloc(&f->d_tmpl_len, f->chunk_cap * 4));
-    ck(cudaMalloc(&f->d_size, n_frames * 4));
-    ck(cudaMalloc(&f->d_slot_off, (f->chunk_cap + 1) * 8));
-    ck(cudaMalloc(&f->d_totals, 8));
+    ck(dev_pool_alloc((void **)&f->d_tmpl, f->chunk_cap * (uint64_t)f->tmpl_cap));       // pooled (hb_api.cu): cudaMalloc / cudaFree are slow here
+    ck(dev_pool_alloc((void **)&f->d_tmpl_len, f->chunk_cap * 4));
+    ck(dev_pool_alloc((void **)&f->d_size, n_frames * 4));
+    ck(dev_pool_alloc((void **)&f->d_slot_off, (f->chunk_cap + 1) * 8));
+    ck(dev_pool_alloc((void **)&f->d_totals, 8));
     for (auto &x : f->ev) ck(cudaEventCreate(&x));
     {   // highest priority: its few long CTAs must get SM slots while the decoder's many short ones stream through
         int lo = 0, hi = 0;
