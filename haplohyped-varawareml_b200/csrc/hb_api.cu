@@ -216,8 +216,10 @@ static int dev_alloc(T **p, uint64_t n) {
 namespace {
 struct PinSlots {
     static constexpr int kSlots = 256;
+    static constexpr size_t kStride = 16896;     // DevStatus (256 B reserved) + 1024 CtaTok + 1025 prefix sums of the tokenizer path
+    static constexpr size_t kCtaOff = 256, kBaseOff = 256 + 8192;
     std::mutex mu;
-    DevStatus *base = nullptr;
+    uint8_t *base = nullptr;
     bool tried = false;
     std::vector<int> free_list;
 } g_pin;
@@ -225,18 +227,19 @@ DevStatus *pin_slot_acquire() {
     std::lock_guard<std::mutex> lk(g_pin.mu);
     if (!g_pin.tried) {
         g_pin.tried = true;
-        if (cudaMallocHost((void **)&g_pin.base, sizeof(DevStatus) * PinSlots::kSlots) != cudaSuccess) { cudaGetLastError(); g_pin.base = nullptr; }
+        static_assert(sizeof(DevStatus) <= PinSlots::kCtaOff, "status words fit their reserve");
+        if (cudaMallocHost((void **)&g_pin.base, PinSlots::kStride * PinSlots::kSlots) != cudaSuccess) { cudaGetLastError(); g_pin.base = nullptr; }
         else for (int i = PinSlots::kSlots - 1; i >= 0; --i) g_pin.free_list.push_back(i);
     }
     if (!g_pin.base || g_pin.free_list.empty()) return nullptr;
     const int i = g_pin.free_list.back();
     g_pin.free_list.pop_back();
-    return g_pin.base + i;
+    return reinterpret_cast<DevStatus *>(g_pin.base + (size_t)i * PinSlots::kStride);
 }
 void pin_slot_release(DevStatus *s) {
     if (!s) return;
     std::lock_guard<std::mutex> lk(g_pin.mu);
-    g_pin.free_list.push_back((int)(s - g_pin.base));
+    g_pin.free_list.push_back((int)((reinterpret_cast<uint8_t *>(s) - g_pin.base) / PinSlots::kStride));
 }
 }  // namespace
 
@@ -299,8 +302,20 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
             TRY(dev_alloc(&p->d_cbase, 1024 + 1));
         }
     }
-    std::vector<CtaTok> h_cta(p->n_cta);
-    std::vector<uint64_t> h_base(p->n_cta + 1);
+    // per-CTA counts come back, and their prefix sums go out, through the handle's pinned block when it has one
+    // (copies from / to pageable memory stall behind the big DMA transfers of a streaming caller)
+    std::vector<CtaTok> v_cta;
+    std::vector<uint64_t> v_base;
+    if (!p->h_st_pin) p->h_st_pin = pin_slot_acquire();
+    CtaTok *h_cta;
+    uint64_t *h_base;
+    if (p->h_st_pin && p->n_cta <= 1024) {
+        h_cta = reinterpret_cast<CtaTok *>(reinterpret_cast<uint8_t *>(p->h_st_pin) + PinSlots::kCtaOff);
+        h_base = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(p->h_st_pin) + PinSlots::kBaseOff);
+    } else {
+        v_cta.resize(p->n_cta); v_base.resize(p->n_cta + 1);
+        h_cta = v_cta.data(); h_base = v_base.data();
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         uint64_t need = (uint64_t)p->n_cta * p->stage_cap;
         if (p->nl_after_cap < need) { TRY(dev_alloc(&p->d_nl_after, need)); p->nl_after_cap = need; }
@@ -312,7 +327,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
         launch_tokenize(p->with_tabs, p->d_text, p->nbytes, p->n_cta, p->tiles_per_cta, p->d_nl_after, p->stage_cap,
                         p->d_cp, p->ncp, p->d_cta, L);
         CU(cudaEventRecord(p->ev[1], p->stream));
-        CU(cudaMemcpyAsync(h_cta.data(), p->d_cta, p->n_cta * sizeof(CtaTok), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaMemcpyAsync(h_cta, p->d_cta, p->n_cta * sizeof(CtaTok), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         CU(cudaGetLastError());
         uint32_t mx = 0;
@@ -325,7 +340,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
         if (attempt == 1) return fail(HB_ERR_MEM, "line index overflow");
         p->stage_cap = mx + 2;                 // exact counts are known even when the index overflowed
     }
-    CU(cudaMemcpyAsync(p->d_cbase, h_base.data(), (p->n_cta + 1) * 8ull, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_cbase, h_base, (p->n_cta + 1) * 8ull, cudaMemcpyHostToDevice, p->stream));
     const uint64_t n_lines = h_base[p->n_cta];
     p->n_lines = n_lines;
     LineIndex li{p->d_nl_after, p->d_cbase, p->n_cta, p->stage_cap};
