@@ -99,6 +99,10 @@ cudaError_t dev_pool_alloc(void **out, uint64_t bytes);
 void dev_pool_free(void *p);
 void dev_pool_flush();
 
+// device -> host memory of any kind, synchronous: pinned destinations directly, pageable ones through pinned staging
+cudaError_t d2h_copy(void *dst, const void *src, uint64_t bytes, cudaStream_t stream);
+cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height, cudaStream_t stream);
+
 // BGZF slab streaming (hb_inflate.cu): device tables of one slot, enqueue-only inflate, last newline of a text range
 struct InflateScratch {
     uint8_t *d_comp = nullptr;

@@ -1317,8 +1317,7 @@ static int frames_layout(hb_frames *f) {
     f->h_size.resize(n_frames);
     if (n_frames) {
         if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
-        cudaError_t e = cudaMemcpyAsync(f->h_size.data(), f->d_size, n_frames * 4, cudaMemcpyDeviceToHost, f->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+        cudaError_t e = d2h_copy(f->h_size.data(), f->d_size, n_frames * 4, f->stream);      // pageable destination: staged (hb_api.cu)
         if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     }
     f->layout_valid = true;
@@ -1501,8 +1500,7 @@ int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap) {
     if (cap < f->padded_bytes) return api_fail(HB_ERR_ARG, "buffer too small");
     if (!f->padded_bytes) return HB_OK;
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
-    cudaError_t e = cudaMemcpyAsync(buf, f->d_frames, f->padded_bytes, cudaMemcpyDeviceToHost, f->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    cudaError_t e = d2h_copy(buf, f->d_frames, f->padded_bytes, f->stream);      // pinned: one copy; pageable: staged
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     return HB_OK;
 }
@@ -1527,8 +1525,7 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *b
     const uint64_t row = f->h_slot_off[nc - 1] + f->h_size[s * nc + nc - 1];
     f->h_row.resize(row);
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
-    cudaError_t e = cudaMemcpyAsync(f->h_row.data(), f->d_frames + row0, row, cudaMemcpyDeviceToHost, f->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+    cudaError_t e = d2h_copy(f->h_row.data(), f->d_frames + row0, row, f->stream);
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("D2H of frames failed: ") + cudaGetErrorString(e));
     uint64_t o = 0;
     for (uint64_t c = 0; c < nc; ++c) {
