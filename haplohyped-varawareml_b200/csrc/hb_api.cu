@@ -186,7 +186,7 @@ static void free_dev(void *p) { hb::dev_pool_free(p); }
 // path ran at 3.7 GB/s on these hosts and stalled at random.  Both return when the data is in place.
 namespace {
 struct D2HStage {
-    static constexpr size_t kCap = 32ull << 20;
+    size_t cap = 32ull << 20;                    // HB_D2H_STAGE_KB overrides (the tests use a small one to walk every piece shape)
     std::mutex mu;
     uint8_t *buf[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -200,8 +200,9 @@ bool is_pinned(const void *p) {
 bool d2h_stage_ready() {                        // g_d2h.mu held
     if (!g_d2h.tried) {
         g_d2h.tried = true;
-        g_d2h.ok = cudaMallocHost((void **)&g_d2h.buf[0], D2HStage::kCap) == cudaSuccess &&
-                   cudaMallocHost((void **)&g_d2h.buf[1], D2HStage::kCap) == cudaSuccess &&
+        if (const char *e = getenv("HB_D2H_STAGE_KB")) { const long v = atol(e); if (v >= 4 && v <= (1 << 22)) g_d2h.cap = (size_t)v << 10; }
+        g_d2h.ok = cudaMallocHost((void **)&g_d2h.buf[0], g_d2h.cap) == cudaSuccess &&
+                   cudaMallocHost((void **)&g_d2h.buf[1], g_d2h.cap) == cudaSuccess &&
                    cudaEventCreateWithFlags(&g_d2h.ev[0], cudaEventDisableTiming) == cudaSuccess &&
                    cudaEventCreateWithFlags(&g_d2h.ev[1], cudaEventDisableTiming) == cudaSuccess;
         if (!g_d2h.ok) cudaGetLastError();
@@ -238,8 +239,8 @@ cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t sp
     uint64_t row = 0, col = 0;
     while (row < height) {
         Piece pc;
-        if (width <= D2HStage::kCap) { pc = Piece{row, 0, std::min<uint64_t>(height - row, D2HStage::kCap / width), width}; }
-        else { pc = Piece{row, col, 1, std::min<uint64_t>(width - col, D2HStage::kCap)}; }
+        if (width <= g_d2h.cap) { pc = Piece{row, 0, std::min<uint64_t>(height - row, g_d2h.cap / width), width}; }
+        else { pc = Piece{row, col, 1, std::min<uint64_t>(width - col, g_d2h.cap)}; }
         const int b = k & 1;
         const uint8_t *sp = (const uint8_t *)src + pc.row * spitch + pc.col;
         if (pc.bytes == width && pc.rows > 1) e = cudaMemcpy2DAsync(g_d2h.buf[b], width, sp, spitch, width, pc.rows, cudaMemcpyDeviceToHost, stream);

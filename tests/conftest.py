@@ -10,6 +10,10 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# D2H copies into pageable memory are staged through pinned buffers (hb_api.cu, d2h_copy_2d); with a small staging size
+# the tests walk every piece shape -- several rows per piece, one row per piece, parts of one row
+os.environ.setdefault("HB_D2H_STAGE_KB", "24")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
