@@ -415,10 +415,10 @@ def main():
         dom = max((k for k in stages if "bytes" in stages[k]), key=lambda k: stages[k]["ms"])
         traffic, traffic_note = None, None
         try:        # DRAM bytes per launch: the ratio ncu measured for this kernel (profiles/) times this launch's algorithmic bytes
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))[dom]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_traffic.json")))[dom]
             traffic = tr["ratio"] * stages[dom]["bytes"]
             traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum = %.3f x algorithmic bytes in the ncu --set full capture "
-                            "(200000 variants x 2504 samples, profiles/r01d_ncu_top_kernels.txt), scaled to this launch" % tr["ratio"])
+                            "(200000 variants x 2504 samples, profiles/r01e_traffic.json), scaled to this launch" % tr["ratio"])
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
