@@ -189,7 +189,7 @@ struct D2HStage {
     size_t cap = 32ull << 20;                    // HB_D2H_STAGE_KB overrides (the tests use a small one to walk every piece shape)
     std::mutex mu;
     uint8_t *buf[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[64][2] = {};                  // per device: an event is recorded on streams of its own device only
     bool tried = false, ok = false;
 } g_d2h;
 bool is_pinned(const void *p) {
@@ -202,12 +202,19 @@ bool d2h_stage_ready() {                        // g_d2h.mu held
         g_d2h.tried = true;
         if (const char *e = getenv("HB_D2H_STAGE_KB")) { const long v = atol(e); if (v >= 4 && v <= (1 << 22)) g_d2h.cap = (size_t)v << 10; }
         g_d2h.ok = cudaMallocHost((void **)&g_d2h.buf[0], g_d2h.cap) == cudaSuccess &&
-                   cudaMallocHost((void **)&g_d2h.buf[1], g_d2h.cap) == cudaSuccess &&
-                   cudaEventCreateWithFlags(&g_d2h.ev[0], cudaEventDisableTiming) == cudaSuccess &&
-                   cudaEventCreateWithFlags(&g_d2h.ev[1], cudaEventDisableTiming) == cudaSuccess;
+                   cudaMallocHost((void **)&g_d2h.buf[1], g_d2h.cap) == cudaSuccess;
         if (!g_d2h.ok) cudaGetLastError();
     }
     return g_d2h.ok;
+}
+cudaEvent_t *d2h_events() {                     // g_d2h.mu held; the two events of the current device, or nullptr
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+    if (!g_d2h.ev[dev][0]) {
+        if (cudaEventCreateWithFlags(&g_d2h.ev[dev][0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g_d2h.ev[dev][1], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    return g_d2h.ev[dev];
 }
 }  // namespace
 namespace hb {
@@ -221,7 +228,8 @@ cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t sp
         return e == cudaSuccess ? cudaStreamSynchronize(stream) : e;
     }
     std::lock_guard<std::mutex> lk(g_d2h.mu);
-    if (!d2h_stage_ready()) {                   // no pinned memory to be had: the plain path
+    cudaEvent_t *ev = d2h_stage_ready() ? d2h_events() : nullptr;
+    if (!ev) {                                  // no pinned memory to be had: the plain path
         e = height == 1 ? cudaMemcpyAsync(dst, src, width, cudaMemcpyDeviceToHost, stream)
                         : cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToHost, stream);
         return e == cudaSuccess ? cudaStreamSynchronize(stream) : e;
@@ -245,10 +253,10 @@ cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t sp
         const uint8_t *sp = (const uint8_t *)src + pc.row * spitch + pc.col;
         if (pc.bytes == width && pc.rows > 1) e = cudaMemcpy2DAsync(g_d2h.buf[b], width, sp, spitch, width, pc.rows, cudaMemcpyDeviceToHost, stream);
         else e = cudaMemcpyAsync(g_d2h.buf[b], sp, pc.bytes, cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaEventRecord(g_d2h.ev[b], stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], stream);
         if (e != cudaSuccess) return e;
         if (k > 0) {                            // the piece before is complete: put it in place while this one is in flight
-            e = cudaEventSynchronize(g_d2h.ev[b ^ 1]);
+            e = cudaEventSynchronize(ev[b ^ 1]);
             if (e != cudaSuccess) return e;
             land(prev, b ^ 1);
         }
@@ -257,7 +265,7 @@ cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t sp
         if (pc.bytes == width) { row += pc.rows; col = 0; }
         else { col += pc.bytes; if (col >= width) { col = 0; ++row; } }
     }
-    e = cudaEventSynchronize(g_d2h.ev[(k - 1) & 1]);
+    e = cudaEventSynchronize(ev[(k - 1) & 1]);
     if (e != cudaSuccess) return e;
     land(prev, (k - 1) & 1);
     return cudaSuccess;
