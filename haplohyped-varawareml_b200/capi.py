@@ -49,7 +49,7 @@ class FramesInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_chunks", C.c_uint64), ("chunk_records", C.c_uint64),
                 ("n_samples", C.c_uint32), ("total_bytes", C.c_uint64), ("raw_bytes", C.c_uint64),
                 ("ms_site", C.c_float), ("ms_frames", C.c_float), ("padded_bytes", C.c_uint64), ("d_frames", C.c_void_p),
-                ("site_lz4_bytes", C.c_uint64), ("ms_pack", C.c_float)]
+                ("site_lz4_bytes", C.c_uint64)]
 
 
 class HapBatch(C.Structure):
@@ -74,7 +74,7 @@ EXPORTS = [
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
     "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
     "hb_frames_fetch_sample", "hb_frames_free",
-    "hb_guess_chunk_records", "hb_decode_frames",
+    "hb_guess_chunk_records", "hb_set_site_matcher", "hb_decode_frames",
     "hb_encode_haplotypes",
     "hb_synth_body_bytes", "hb_synth_header", "hb_synth_device", "hb_synth_host",
 ]
@@ -134,6 +134,8 @@ def lib():
             L.hb_frames_free.argtypes = [C.c_void_p]
             L.hb_guess_chunk_records.argtypes = [C.c_uint64]
             L.hb_guess_chunk_records.restype = C.c_uint64
+            L.hb_set_site_matcher.argtypes = [C.c_int]
+            L.hb_set_site_matcher.restype = None
             L.hb_decode_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
         L.hb_encode_haplotypes.argtypes = [C.POINTER(HapBatch)]
         L.hb_synth_body_bytes.argtypes = [C.POINTER(SynthSpec)]
@@ -285,7 +287,7 @@ class Parse:
         check(lib().hb_parse_attach_frames(self._h, frames._h if frames is not None else None))
 
     def compress(self, chunk_records: int = 0, s0: int = 0, ns: int | None = None) -> "Frames":
-        """Blosc2 frames of samples [s0, s0 + ns) (default: all)."""
+        """Blosc frames of samples [s0, s0 + ns) (default: all)."""
         h = C.c_void_p()
         if ns is None and s0 == 0:
             check(lib().hb_compress_records(self._h, chunk_records, C.byref(h)))
@@ -309,7 +311,7 @@ class Parse:
 
 
 class Frames:
-    """Blosc2 cframes (one per sample per HDF5 chunk), device resident (section C)."""
+    """Stored HDF5 chunks = bare Blosc chunks (one per sample per HDF5 chunk), device resident (section C)."""
 
     def __init__(self, handle):
         self._h = handle
@@ -468,7 +470,7 @@ def bgzf_inflate(data: bytes, device: int = 0, with_ms: bool = False):
 
 
 def decode_frames(frames, chunk_nbytes: int, planar: bool = False, device: int = 0) -> np.ndarray:
-    """Stored HDF5 chunks (Blosc2 cframes) -> uint8 [n_frames, chunk_nbytes], decoded on the GPU."""
+    """Stored HDF5 chunks (bare Blosc chunks, filter 32001) -> uint8 [n_frames, chunk_nbytes], decoded on the GPU."""
     n = len(frames)
     out = np.empty((n, chunk_nbytes), np.uint8)
     if n == 0:

@@ -4,13 +4,13 @@
 
 Two backends behind one small interface (`open_h5`):
 
-  * h5py + hdf5plugin when both import: GPU-compressed Blosc2 frames enter the file through HDF5's
+  * h5py + hdf5plugin when both import: GPU-compressed Blosc chunks enter the file through HDF5's
     direct-chunk-write call (`dset.id.write_direct_chunk`), which stores pre-filtered bytes without
     running the filter; reads pull the stored chunks with `read_direct_chunk`.  (Neither package is
     in this image, so this branch has not been run here -- see DESIGN.md.)
   * otherwise `minih5`, this repo's own writer/reader of the same HDF5 structures.
 
-Either way the chunk payloads are Blosc2 cframes, produced by kernel 4 (`hb_compress_records`) on the
+Either way the chunk payloads are bare Blosc1 chunks (what hdf5-blosc, filter 32001, stores), produced by kernel 4 (`hb_compress_records`) on the
 way in and decoded by `hb_decode_frames` on the way out: no CPU codec is involved in the product path.
 """
 from __future__ import annotations
@@ -19,14 +19,14 @@ import numpy as np
 
 from . import minih5
 
-FILTER_BLOSC2 = 32001
+FILTER_BLOSC = 32001
 # what the reference passes (vcf_to_h5.py:135); the filter's set_local overwrites slots 0-3 with
-# (filter revision, Blosc2 format version, typesize, chunk bytes) before they reach the file
-BLOSC2_OPTS = (2, 2, 0, 0, 5, 1, 2)
+# (filter revision, Blosc format version, typesize, chunk bytes) before they reach the file
+BLOSC_OPTS = (2, 2, 0, 0, 5, 1, 2)
 
 
 def _cd_values(itemsize: int, chunk_nbytes: int):
-    return (BLOSC2_OPTS[0], BLOSC2_OPTS[1], itemsize, chunk_nbytes) + BLOSC2_OPTS[4:]
+    return (BLOSC_OPTS[0], BLOSC_OPTS[1], itemsize, chunk_nbytes) + BLOSC_OPTS[4:]
 
 
 def have_h5py() -> bool:
@@ -55,8 +55,8 @@ class _MiniFile:
     # ---- write
     def write_chunked(self, path: str, dtype, n: int, chunk: int, frames):
         dtype = np.dtype(dtype)
-        self._w.create_dataset_chunked(path, dtype, n, chunk, frames, filter_id=FILTER_BLOSC2,
-                                       cd_values=_cd_values(dtype.itemsize, chunk * dtype.itemsize), filter_name="blosc2")
+        self._w.create_dataset_chunked(path, dtype, n, chunk, frames, filter_id=FILTER_BLOSC,
+                                       cd_values=_cd_values(dtype.itemsize, chunk * dtype.itemsize), filter_name="blosc")
 
     def write_frames_bulk(self, paths, dtype, n: int, chunk: int, buf: np.ndarray, offsets: np.ndarray, sizes: np.ndarray):
         """Many datasets at once: `buf` (all their stored chunks, e.g. hb_frames_fetch_all) goes into the file with ONE
@@ -66,7 +66,7 @@ class _MiniFile:
         cd = _cd_values(dtype.itemsize, chunk * dtype.itemsize)
         for i, path in enumerate(paths):
             self._w.create_dataset_chunked_at(path, dtype, n, chunk, np.uint64(base) + offsets[i].astype(np.uint64), sizes[i],
-                                              filter_id=FILTER_BLOSC2, cd_values=cd, filter_name="blosc2")
+                                              filter_id=FILTER_BLOSC, cd_values=cd, filter_name="blosc")
 
     def write_array(self, path: str, data: np.ndarray):
         self._w.create_dataset_contiguous(path, np.asarray(data))
@@ -87,7 +87,7 @@ class _MiniFile:
         if not info.filters:
             raw = b"".join(b for _, b in stored)
             return np.frombuffer(raw, info.dtype)[:n].copy()
-        if [f for f, _ in info.filters] != [FILTER_BLOSC2]:
+        if [f for f, _ in info.filters] != [FILTER_BLOSC]:
             raise OSError(f"{path}: unsupported filter pipeline {info.filters}")
         return _decode([b for _, b in stored], info.dtype, n, info.chunk)
 
@@ -114,8 +114,8 @@ class _H5pyFile:
 
     def write_chunked(self, path: str, dtype, n: int, chunk: int, frames):
         dtype = np.dtype(dtype)
-        d = self._f.create_dataset(path, shape=(n,), dtype=dtype, chunks=(chunk,), compression=FILTER_BLOSC2,
-                                   compression_opts=BLOSC2_OPTS)
+        d = self._f.create_dataset(path, shape=(n,), dtype=dtype, chunks=(chunk,), compression=FILTER_BLOSC,
+                                   compression_opts=BLOSC_OPTS)
         for k, payload in enumerate(frames):
             d.id.write_direct_chunk((k * chunk,), bytes(payload))
 

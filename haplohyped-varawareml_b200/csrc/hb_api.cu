@@ -284,7 +284,7 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_text_owned); free_dev(p->d_nl_after); free_dev(p->d_cta); free_dev(p->d_cbase); free_dev(p->d_cp);
     free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
     free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_chrom5); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
-    free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_ploidy);
+    free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_bits); free_dev(p->d_ploidy);
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
@@ -551,10 +551,14 @@ static int run_parse(hb_parse *p) {
         // slightly different length must not re-allocate -- cudaFree synchronises the whole device
         if (!p->d_gt[0] || n_rec > p->gt_stride) {
             const uint64_t want = p->d_gt[0] ? n_rec + n_rec / 8 + 1024 : n_rec;
-            const uint64_t stride = (want + kTV - 1) / kTV * kTV;
+            const uint64_t stride = (want + 127) / 128 * 128;         // whole 128-row groups of the bit planes
             const uint64_t bytes = stride * p->n_samples;
             TRY(dev_alloc(&p->d_gt[0], bytes)); TRY(dev_alloc(&p->d_gt[1], bytes));
             p->gt_bytes = bytes; p->gt_stride = stride;
+            p->bits_stride = stride / 128 * kBitGroupWords;
+            TRY(dev_alloc(&p->d_bits, p->bits_stride * p->n_samples));
+            // rows between the last decode tile and the end of its group are never written: they read as "no allele"
+            CU(cudaMemsetAsync(p->d_bits, 0, p->bits_stride * p->n_samples * 4, p->stream));
         }
         if (p->index_used == 3 && p->h_st.n_nu_count) {
             // walker: the count pass told the host how many kept records are not plain "\tX|Y" columns
@@ -564,7 +568,7 @@ static int run_parse(hb_parse *p) {
             launch_index_columns(p->d_text, p->d_rowinfo, p->d_nu_rows, n_nu, p->d_cp, p->ncp, L);
         }
         launch_decode_gt(p->d_text, p->d_rowinfo, n_rec, p->n_samples, p->d_cp, p->ncp, p->d_gt[0], p->d_gt[1],
-                         p->gt_stride, p->d_ploidy, p->d_badgt, p->d_st, L);
+                         p->gt_stride, p->d_bits, p->bits_stride, p->d_ploidy, p->d_badgt, p->d_st, L);
     }
     CU(cudaEventRecord(p->ev[3], p->stream));
     launch_chrom_runs(p->d_text, p->d_chrom_abs, p->d_chrom_len, n_rec, p->d_run_rows, hb_parse::kMaxRuns, p->d_st, L);

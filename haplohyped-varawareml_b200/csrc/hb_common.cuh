@@ -99,4 +99,14 @@ __device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------- allele bytes -> bits
+// bit j of the result = bit 0 of byte j of w
+__device__ __forceinline__ uint32_t pack_lsb4(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
+// bit j of the result = byte j of w has one of bits 1..7 set (the byte is neither 0 nor 1)
+__device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {
+    const uint32_t t = w & 0xFEFEFEFEu;
+    const uint32_t nz = ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u) >> 7;
+    return (nz * 0x01020408u) >> 24;
+}
+
 }  // namespace hb

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(GT_THREADS, 4)
 decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ rowinfo, uint64_t n_rows,
                  uint32_t n_samples, uint32_t n_stiles, const uint64_t *__restrict__ cp, uint32_t ncp,
                  int8_t *__restrict__ gt0, int8_t *__restrict__ gt1, uint64_t gt_stride,
+                 uint32_t *__restrict__ bits, uint64_t bits_stride,
                  uint32_t *__restrict__ ploidy_err, uint32_t *__restrict__ badgt_err,
                  DevStatus *__restrict__ st, uint32_t pf_dist) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -319,38 +320,55 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     }
     __syncthreads();
 
-    // ---- phase 3: kTV contiguous bytes per (plane, sample), 16-byte vector stores
+    // ---- phase 3: kTV contiguous bytes per (plane, sample), 16-byte vector stores; and the same alleles as bit planes
+    //      (B = bit 0 of the byte, N = "neither 0 nor 1") for the frame encoder: the 4 lanes that hold the 4 pieces of one
+    //      (plane, sample) combine their 16-bit masks with shuffles and one of them stores 2 words of each array
     {
         constexpr int PIECES = kTV / 16;
+        static_assert(PIECES == 4 && (2 * kTS * PIECES) % GT_THREADS == 0, "the 4 pieces of a row sit in 4 neighbouring lanes");
         for (int item = tid; item < 2 * kTS * PIECES; item += GT_THREADS) {
             const int piece = item % PIECES;
             const int ps = item / PIECES;       // plane * kTS + s
             const int s = ps % kTS, p = ps / kTS;
-            if ((uint32_t)s >= ns) continue;
-            const uint4 v = *reinterpret_cast<const uint4 *>(&sm.out[p][s][16 * piece]);
-            int8_t *dst = (p ? gt1 : gt0) + (uint64_t)(s0 + s) * gt_stride + r0 + 16ull * piece;
-            stg_stream(reinterpret_cast<uint4 *>(dst), v);
+            const bool live = (uint32_t)s < ns;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (live) {
+                v = *reinterpret_cast<const uint4 *>(&sm.out[p][s][16 * piece]);
+                int8_t *dst = (p ? gt1 : gt0) + (uint64_t)(s0 + s) * gt_stride + r0 + 16ull * piece;
+                stg_stream(reinterpret_cast<uint4 *>(dst), v);
+            }
+            if (bits) {
+                uint32_t t = pack_lsb4(v.x) | (pack_lsb4(v.y) << 4) | (pack_lsb4(v.z) << 8) | (pack_lsb4(v.w) << 12);
+                if ((v.x | v.y | v.z | v.w) & 0xFEFEFEFEu)
+                    t |= (pack_nz4(v.x) | (pack_nz4(v.y) << 4) | (pack_nz4(v.z) << 8) | (pack_nz4(v.w) << 12)) << 16;
+                const uint32_t u = __shfl_down_sync(0xffffffffu, t, 1);
+                const uint32_t bw = (t & 0xffffu) | (u << 16), nw = (t >> 16) | (u & 0xffff0000u);   // valid in even lanes
+                const uint32_t bw1 = __shfl_down_sync(0xffffffffu, bw, 2), nw1 = __shfl_down_sync(0xffffffffu, nw, 2);
+                if (live && piece == 0) {
+                    uint32_t *row = bits + (uint64_t)(s0 + s) * bits_stride + (r0 >> 7) * kBitGroupWords + ((r0 >> 5) & 3u);
+                    *reinterpret_cast<uint2 *>(row + 4 * p) = make_uint2(bw, bw1);
+                    *reinterpret_cast<uint2 *>(row + 4 * (2 + p)) = make_uint2(nw, nw1);
+                }
+            }
         }
     }
 }
 
 void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t n_rows, uint32_t n_samples,
                       const uint64_t *d_cp, uint32_t ncp, int8_t *d_gt0, int8_t *d_gt1, uint64_t gt_stride,
-                      uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st, const Launch &L) {
+                      uint32_t *d_bits, uint64_t bits_stride, uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st,
+                      const Launch &L) {
     if (!n_rows || !n_samples) return;
-    static bool attr_set = false;
     size_t smem = sizeof(GtSmem);
-    if (!attr_set) {
-        cudaFuncSetAttribute(decode_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    // > 48 KB of dynamic shared memory is opt-in per function AND per device: set on every launch (a microsecond), so a
+    // process that moves to another device is served too
+    cudaFuncSetAttribute(decode_gt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     uint32_t n_stiles = (n_samples + kTS - 1) / kTS;
     uint64_t n_rtiles = (n_rows + kTV - 1) / kTV;
     uint64_t tiles = n_rtiles * n_stiles;
-    uint32_t pf_dist = 4u * (uint32_t)L.sm_count;            // 4 CTAs per SM are resident (__launch_bounds__)
-    if (const char *e = getenv("HB_GT_PREFETCH")) pf_dist = (uint32_t)atoi(e);
+    const uint32_t pf_dist = 4u * (uint32_t)L.sm_count;      // 4 CTAs per SM are resident (__launch_bounds__)
     decode_gt_kernel<<<(unsigned)tiles, GT_THREADS, smem, L.stream>>>(d_text, d_rowinfo, n_rows, n_samples, n_stiles,
-                                                                      d_cp, ncp, d_gt0, d_gt1, gt_stride,
+                                                                      d_cp, ncp, d_gt0, d_gt1, gt_stride, d_bits, bits_stride,
                                                                       d_ploidy_err, d_badgt_err, d_st, pf_dist);
     count_launch();
 }

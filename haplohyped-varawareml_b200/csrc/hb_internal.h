@@ -11,6 +11,12 @@ constexpr int kTS = 128;          // samples per decode tile (== kCP)
 constexpr int kTV = 64;           // records (rows) per decode tile
 constexpr uint64_t kNoCp = ~0ull; // "no checkpoint written"
 
+// Allele bit planes, written by the GT decoder next to the byte planes and read by the frame encoder (hb_store.cu):
+// per sample kBitGroupWords-word groups of 128 rows, [sample][group][array][4 words], array 0/1 = bit 0 of the phase1 /
+// phase2 byte ("B"), array 2/3 = "the byte is neither 0 nor 1" ("N").  Row r of a sample: group r >> 7, word (r >> 5) & 3,
+// bit r & 31.  A frame's rows are one contiguous byte range of every sample: one TMA bulk copy.
+constexpr int kBitGroupWords = 16;
+
 // Per kept record, produced by the site kernel, consumed by the GT decoder.
 struct RowInfo {
     uint64_t samp_abs;   // offset of the TAB that precedes sample 0
@@ -90,7 +96,8 @@ void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const
                        const Launch &L);
 void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t n_rows, uint32_t n_samples,
                       const uint64_t *d_cp, uint32_t ncp, int8_t *d_gt0, int8_t *d_gt1, uint64_t gt_stride,
-                      uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st, const Launch &L);
+                      uint32_t *d_bits, uint64_t bits_stride, uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st,
+                      const Launch &L);
 
 void count_launch(uint64_t n = 1);
 

@@ -53,6 +53,8 @@ struct hb_parse {
     uint64_t row_cap = 0;
     int8_t *d_gt[2] = {nullptr, nullptr};
     uint64_t gt_stride = 0, gt_bytes = 0;
+    uint32_t *d_bits = nullptr;         // the same alleles as bit planes (hb_common.cuh, kBitGroupWords): what kernel 4b reads
+    uint64_t bits_stride = 0;           // words per sample = gt_stride / 128 * kBitGroupWords
     uint32_t *d_ploidy = nullptr, *d_badgt = nullptr;
     uint64_t *d_run_rows = nullptr;
     static constexpr uint64_t kMaxRuns = 4096;

@@ -1,25 +1,21 @@
-// hb_store.cu -- kernel 4: Blosc2 byte-shuffle + LZ4 block encoder + Blosc2 chunk / cframe framing.
+// hb_store.cu -- kernel 4: Blosc byte-shuffle + LZ4 block encoder + Blosc chunk framing, and the read side.
 //
 // Replaces what h5py + hdf5plugin do for every HDF5 chunk of
 //   create_dataset('snp_data', data=<35-byte records>, compression=32001,
 //                  compression_opts=(2,2,0,0,5,1,2), chunks=True)        (vcf_to_h5.py:119-135)
-// i.e. c-blosc2's shuffle(typesize 35) + LZ4-family codec, wrapped by the hdf5-blosc2 filter as a
-// contiguous frame holding one Blosc2 chunk.  The reference asks for LZ4HC (compcode 2); LZ4 and
-// LZ4HC share one block format and one Blosc codec-format id, so a stock decoder cannot tell.
+// Filter 32001 is hdf5-blosc, i.e. c-blosc 1.x: shuffle(typesize 35) + an LZ4-family codec, one bare Blosc1 chunk
+// per HDF5 chunk (the opts are [filter rev 2, Blosc format 2, typesize, chunk bytes, clevel 5, shuffle 1, compcode 2 =
+// LZ4HC]).  LZ4 and LZ4HC share one block format and one Blosc codec-format id, so a stock decoder cannot tell
+// which encoder wrote a stream.
 //
 // The byte-shuffled image of one (sample, chunk) is 35 planes of `cr` bytes.  Planes 0..32 hold
 // site bytes and are IDENTICAL for every sample; only planes 33/34 (the two allele planes, which
-// the GT decoder already wrote in exactly this planar layout) differ.  So:
-//   site_prefix_kernel   one CTA per chunk: builds the 33 site planes in shared memory straight
-//                        from the SoA columns (the 35-byte AoS records are never materialised) and
-//                        LZ4-encodes them once, as the head of a no-split LZ4 block;
-//   donor_frames_kernel  one warp per (chunk, sample): LZ4-encodes the 2*cr allele bytes as the
-//                        continuation of that block (history = tail of the site planes), then
-//                        writes cframe header + chunk header + shared prefix + own sequences +
-//                        offsets chunk + trailer.
-// The encoder is a warp-cooperative greedy matcher: 32 candidate positions per step are hashed in
-// parallel, the first hit is extended with ballots, literals are copied 32 bytes per step.
+// the GT decoder already wrote in exactly this planar layout) differ.  So the 33 site planes are encoded once per
+// chunk (site_template_kernel) and every donor continues that LZ4 block with its own 2 * cr allele bytes
+// (donor_frames_kernel).  The site encoder is a warp-cooperative greedy matcher: 32 candidate positions per step are
+// hashed in parallel, the first hit is extended with ballots, literals are copied 32 bytes per step.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -35,7 +31,6 @@
 
 namespace hb {
 
-constexpr int FRAME_HDR = 97, CHUNK_HDR = 32, OFFS_CHUNK = 40, FRAME_TRAILER = 35;
 
 __device__ __forceinline__ uint32_t rd32(const uint8_t *p) {     // unaligned 4-byte read (shared memory)
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -147,77 +142,45 @@ __device__ int warp_lz4_segment(const uint8_t *src, int n, int hist, uint8_t *ds
 }
 
 // ------------------------------------------------------------------------------------------
-// Frame anatomy.  One HDF5 chunk of one donor = one Blosc2 contiguous frame holding one chunk:
-//   [0,97)     cframe header        frame_len @16 (BE64) and cbytes @39 (BE64) depend on the donor
-//   [97,129)   Blosc2 chunk header  cbytes @109 (LE32) depends on the donor
-//   [129,133)  bstarts[0] = 36
-//   [133,137)  csize of the single (no-split) stream, LE32: depends on the donor
-//   [137,137+plen)   LZ4 sequences of the 33 site planes    -- identical for every donor
-//   [.., +dlen)      LZ4 sequences of the 2 allele planes   -- the donor's own
-//   [.., +40)        offsets chunk (one int64 0, memcpyed)  -- constant
-//   [.., +35)        cframe trailer                          -- constant
+// Chunk anatomy.  HDF5 filter 32001 is hdf5-blosc (c-blosc 1.x): one HDF5 chunk of one donor is stored as ONE
+// bare Blosc1 chunk (blosc_compress output), little-endian:
+//   [0,16)   header: version 2 (BLOSC_VERSION_FORMAT), versionlz 1 (LZ4 format), flags 0x31 (byte-shuffle |
+//            don't-split | LZ4 codec format << 5), typesize 35, nbytes, blocksize (= nbytes: one block),
+//            cbytes @12 (whole chunk incl. this header)                          -- cbytes depends on the donor
+//   [16,20)  bstarts[0] = 20
+//   [20,24)  csize of the block's single (no-split) stream, LE32                 -- depends on the donor
+//   [24,24+plen)   LZ4 sequences of the 33 site planes    -- identical for every donor
+//   [.., +dlen)    LZ4 sequences of the 2 allele planes   -- the donor's own
+// typesize 35 > 16, so c-blosc itself never splits such a block either; the decoder (blosc_d) reads
+// "int32 csize + stream" per block, csize == blocksize meaning "stored raw".
 // Kernels:
-//   site_template_kernel   one CTA per chunk: site planes -> LZ4; writes the frame TEMPLATE (header with
-//                          the donor-dependent fields left zero + shared LZ4 head), 16-byte aligned.
-//   donor_frames_kernel    one warp per (sample, chunk) frame, fused: allele planes -> LZ4 tail of the
-//                          block (bit-parallel matcher, below) -> template (from L2) + own tail (from
-//                          shared memory) written straight to the frame's slot with 16-byte vector
-//                          stores, the four size fields patched in registers.  C_out is written exactly
-//                          once and nothing else of size leaves the SM; warps never wait on each other.
+//   site_template_kernel   one CTA per chunk: site planes -> LZ4; writes the chunk TEMPLATE (header with the two
+//                          donor-dependent fields left zero + shared LZ4 head), 16-byte aligned.
+//   donor_frames_kernel    one CTA per (chunk, group of samples), one warp per frame at a time.  The chunk's
+//                          template is pulled into shared memory ONCE per CTA (TMA bulk copy); every frame's allele
+//                          bits arrive by TMA one frame ahead; the warp encodes the allele planes as the LZ4 tail of
+//                          the block (bit-parallel matcher, below) into shared memory; the frame then leaves as two
+//                          TMA bulk stores (template body from the shared copy, own tail) + two 16-byte header
+//                          vectors with the size fields filled in.  C_out is written exactly once.
 // Output: ONE buffer of slots in [sample][chunk] order.  The slot of (sample s, chunk c) starts at
 // s * row_stride + slot_off[c]; slot_off is the running sum of round16(template_len[c] + worst-case
 // allele tail), so every frame's address is known before it is encoded (no scan, no look-back) and the
 // layout is deterministic.  A frame fills the front of its slot; its true length is recorded.
 // ------------------------------------------------------------------------------------------
-constexpr int TMPL_HDR = FRAME_HDR + CHUNK_HDR + 8;        // 137 bytes of a frame precede its LZ4 block
-constexpr int FRAME_TAIL = OFFS_CHUNK + FRAME_TRAILER;     // 75 bytes follow it
+constexpr int BLOSC_HDR = 16;
+constexpr int TMPL_HDR = BLOSC_HDR + 8;        // 24 bytes of a chunk precede its LZ4 block
 
-__device__ __align__(16) const uint8_t kFrameTail[FRAME_TAIL + 1] = {      // + 1: read as 19 words by the lane encoder
-    // offsets chunk: Blosc2 chunk header (version 5, LZ4 format 1, flags memcpyed|shuffle|bitshuffle(=extended),
-    // typesize 8, nbytes 8, blocksize 8, cbytes 40, filters[5] = shuffle) + one int64 0
-    5, 1, 0x17, 8, 8, 0, 0, 0, 8, 0, 0, 0, OFFS_CHUNK, 0, 0, 0,
-    0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    0, 0, 0, 0, 0, 0, 0, 0,
-    // trailer: [version 1, vlmetalayers {index, map16 0, array16 0}, uint32 trailer_len, fixext16 fingerprint]
-    0x94, 0x01, 0x93, 0xcd, 0, 5, 0xde, 0, 0, 0xdc, 0, 0, 0xce, 0, 0, 0, FRAME_TRAILER, 0xd8, 0,
-    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-
-__device__ __forceinline__ void put_be(uint8_t *p, uint64_t v, int nb) {
-    for (int i = 0; i < nb; ++i) p[i] = (uint8_t)(v >> (8 * (nb - 1 - i)));
-}
 __device__ __forceinline__ void put_le32(uint8_t *p, uint32_t v) {
     p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 
-// the 137 header bytes of a frame for chunks of `nbytes` uncompressed bytes; donor-dependent fields are zero
+// the 24 header bytes of a chunk of `nbytes` uncompressed bytes; the donor-dependent fields are zero
 __device__ void write_frame_head(uint8_t *h, uint32_t nbytes) {
     for (int i = 0; i < TMPL_HDR; ++i) h[i] = 0;
-    // ---- cframe header (c-blosc2 README_CFRAME_FORMAT; msgpack, big-endian)
-    h[0] = 0x9e; h[1] = 0xa8;
-    const char magic[8] = {'b', '2', 'f', 'r', 'a', 'm', 'e', 0};
-    for (int i = 0; i < 8; ++i) h[2 + i] = (uint8_t)magic[i];
-    h[10] = 0xd2; put_be(h + 11, FRAME_HDR, 4);
-    h[15] = 0xcf;                                            // frame_len: patched
-    h[24] = 0xa4; h[25] = 0x12; h[26] = 0x00; h[27] = 0x51; h[28] = 0x03;   // v2 | 64-bit offs, contiguous, LZ4 | clevel 5, split mode
-    h[29] = 0xd3; put_be(h + 30, nbytes, 8);
-    h[38] = 0xd3;                                            // cbytes: patched
-    h[47] = 0xd2; put_be(h + 48, 35, 4);
-    h[52] = 0xd2; put_be(h + 53, nbytes, 4);
-    h[57] = 0xd2; put_be(h + 58, nbytes, 4);
-    h[62] = 0xd1; put_be(h + 63, 1, 2);
-    h[65] = 0xd1; put_be(h + 66, 1, 2);
-    h[68] = 0xc2;
-    h[69] = 0xd8; h[70] = 6;
-    h[76] = 1;                                               // filters[5] = BLOSC_SHUFFLE
-    h[87] = 0x93; h[88] = 0xcd; put_be(h + 89, 5, 2);
-    h[91] = 0xde; h[94] = 0xdc;
-    // ---- Blosc2 chunk header (extended, 32 bytes, little-endian)
-    uint8_t *k = h + FRAME_HDR;
-    k[0] = 5; k[1] = 1; k[2] = 0x35; k[3] = 35;              // format 5, LZ4 format 1, shuffle|bitshuffle(=extended)|dont-split|LZ4
-    put_le32(k + 4, nbytes); put_le32(k + 8, nbytes);        // cbytes @12: patched
-    k[21] = 1;                                               // filters[5] = BLOSC_SHUFFLE
-    put_le32(k + 32, CHUNK_HDR + 4);                         // bstarts[0]
-}                                                            // csize @36: patched
+    h[0] = 2; h[1] = 1; h[2] = 0x31; h[3] = 35;
+    put_le32(h + 4, nbytes); put_le32(h + 8, nbytes);        // cbytes @12: patched
+    put_le32(h + 16, BLOSC_HDR + 4);                         // bstarts[0]
+}                                                            // csize @20: patched
 
 // one LZ4 sequence, written by the whole warp; returns the new output offset
 __device__ int warp_emit_seq(uint8_t *dst, int o, const uint8_t *lit, int litlen, int off, int ml) {
@@ -374,37 +337,30 @@ __global__ void __launch_bounds__(kSiteSegs * 32) site_template_kernel(const Sit
 }
 
 // ------------------------------------------------------------------------------------------
-// Allele-plane encoder, bit-parallel.  After the SNP filter the allele bytes are 0 / 1 (rarely -9), so
-// the two planes are packed to one bit per byte (B = bit 0, N = "any other bit set") and LZ4 matches
-// are found with word-wide logic instead of byte-wise hashing.  Two match sources:
+// Allele-plane encoder, bit-parallel.  After the SNP filter the allele bytes are 0 / 1 (rarely -9), and the GT
+// decoder leaves them as bit planes too (B = bit 0 of the byte, N = "neither 0 nor 1"; hb_internal.h), so LZ4
+// matches are found with word-wide logic instead of byte-wise hashing.  Two match sources:
 //   Z  a zero byte: matches the all-zero site plane two planes back      (offset 2*cr),  Z = ~B & ~N
 //   C  plane 1 only: equal to the same record's byte in plane 0           (offset cr),    C = ~(B1^B0) & ~(N1|N0)
 // A byte with N set never matches, so the stream is exact for ANY byte values; it just compresses
 // best on genotype data.  Runs of >= 5 Z positions become matches first, then runs of >= 4 C positions
 // in what is left; everything else is literal.  Lanes 0-15 own 16 segments of plane 0, lanes 16-31 the
 // same segments of plane 1 (a match never crosses a segment); trailing literals of a segment are
-// carried into the next lane's first sequence; warp scans give every lane its output offset, its first
-// global sequence index and literal index; each lane writes the headers of its own sequences, then all
-// literals of the frame are copied in one balanced pass (32 equal shares of the literal index space).
+// carried into the next lane's first sequence.  The size of every lane's output follows from popcounts
+// (3 bytes per match + literals + one extension byte per literal run >= 15 / match >= 19, counted with
+// shifted-OR windows), one warp scan turns the sizes into output offsets, and every lane then walks its
+// matches ONCE, emitting token, literals (bits -> bytes, four per step) and offset through a 4-byte
+// register accumulator into the frame's tail buffer in shared memory.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 ldg_nc(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
 constexpr int kMinZ = 5, kMinC = 4;
-constexpr int kWpcMax = 12;                   // warps (= frames) per CTA: 4, 8 or 12, whichever fits most warps on an SM
+constexpr int kWpc = 8;                       // warps per CTA
+constexpr int kFramesPerWarp = 8;             // frames (samples of one chunk) a warp encodes one after the other
 
-__device__ __forceinline__ uint32_t pack_lsb4(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
-__device__ __forceinline__ uint32_t pack_nz4(uint32_t w) {       // bit j = byte j has one of bits 1..7 set
-    const uint32_t t = w & 0xFEFEFEFEu;
-    const uint32_t nz = ((((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u) >> 7;
-    return (nz * 0x01020408u) >> 24;
-}
 __device__ __forceinline__ uint32_t low_mask(int n) { return n <= 0 ? 0u : (n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u)); }
 __device__ __forceinline__ int ctz32(uint32_t v) { return __clz(__brev(v)); }       // 32 for 0
 __device__ __forceinline__ int lit_ext(int lit) { return lit >= 15 ? 1 + (lit - 15) / 255 : 0; }
+// bits 0..3 of b -> bytes 0..3 (0 / 1)
+__device__ __forceinline__ uint32_t spread4(uint32_t b) { return ((b & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 // R = the positions of X that lie inside a run of at least MINRUN consecutive ones (multi-word, LSB first)
 template <int NW, int MINRUN>
@@ -427,190 +383,209 @@ __device__ __forceinline__ void runs_cover(const uint32_t (&X)[NW], uint32_t (&R
         R[k] = r;
     }
 }
+// Y = X | (X >> d): bit i of Y = X(i) | X(i + d) (multi-word, LSB first, 0 < d < 32)
+template <int NW>
+__device__ __forceinline__ void or_shr(const uint32_t (&X)[NW], int d, uint32_t (&Y)[NW]) {
+    uint32_t T[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) T[k] = X[k] | __funnelshift_r(X[k], k + 1 < NW ? X[k + 1] : 0u, d);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) Y[k] = T[k];
+}
+template <int NW>
+__device__ __forceinline__ uint32_t shr_word(const uint32_t (&X)[NW], int k, int d) {
+    return __funnelshift_r(X[k], k + 1 < NW ? X[k + 1] : 0u, d);
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_or32(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 struct FusedArgs {
-    const int8_t *gt0, *gt1;
+    const int8_t *gt0, *gt1;             // byte planes: read only where an allele is neither 0 nor 1 (and for raw blocks)
     uint64_t gt_stride, n_records;
+    const uint32_t *bits;                // allele bit planes (hb_internal.h)
+    uint64_t bits_stride;                // words per sample
     uint32_t cr, n_samples, s0;          // samples [s0, s0 + n_samples)
     uint64_t n_chunks;
     const uint8_t *tmpl; uint32_t tmpl_cap; const uint32_t *tmpl_len;
     uint8_t *frames;
     const uint64_t *slot_off;            // [n_chunks + 1] offset of chunk c's slot inside a sample row; [n_chunks] = row stride
     uint32_t *size;                      // [n_samples * n_chunks] true length of each frame
-    unsigned long long *totals;          // [0] sum of frame lengths
-    uint32_t bww;       // words of one packed bit array (word 0 is a leading zero word)
-    uint32_t caps;      // sequence slots per lane
-    uint32_t dcap;      // literal-run descriptors per frame (non-empty runs only)
-    uint32_t outcap;    // bytes of the frame-tail buffer
-    uint32_t pf_dist;   // frames between a warp and the one that will follow it in its SM slot (0 = no L2 prefetch)
-    uint32_t pf_dq, pf_dr;   // pf_dist = pf_dq * n_chunks + pf_dr
-    uint32_t wpc;       // warps per CTA
-    uint32_t warp_smem;
+    uint32_t strw;       // words of one seamless bit string (B, N)
+    uint32_t stg_bytes;  // bytes of a warp's staging area for the bit-plane slices of one frame
+    uint32_t outcap;     // bytes of a warp's tail buffer
+    uint32_t tmpl_smem;  // bytes reserved for the chunk's template
+    uint32_t warp_smem;  // bytes per warp
+    uint32_t groups, gs; // sample groups per chunk (= CTAs per chunk), samples per group
 };
 
 template <int NW>
-__global__ void __launch_bounds__(kWpcMax * 32) donor_frames_kernel(const FusedArgs A) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs A) {
+    extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t n_frames = A.n_chunks * A.n_samples;
-    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (wid >= n_frames) return;
+    const uint32_t c = blockIdx.x / A.groups, grp = blockIdx.x - c * A.groups;
     const int cr = (int)A.cr, n = 2 * cr;
-    uint8_t *base = smem + (size_t)warp * A.warp_smem;
-    uint32_t *bits = reinterpret_cast<uint32_t *>(base);                 // B string, N string (BWW words each)
-    const int BWW = (int)A.bww;
-    uint16_t *seqs = reinterpret_cast<uint16_t *>(bits + 2 * BWW);       // [caps][32]
-    uint32_t *d_sd = reinterpret_cast<uint32_t *>(seqs + A.caps * 32);   // literal runs: source position | destination << 16
-    uint16_t *d_cum = reinterpret_cast<uint16_t *>(d_sd + A.dcap);       //               literal index of the run's first byte
-    uint8_t *outb = reinterpret_cast<uint8_t *>(d_cum + A.dcap);
+    uint64_t *tbar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *tmpl_s = smem + 16;
+    uint8_t *wbase = smem + 16 + A.tmpl_smem + (size_t)warp * A.warp_smem;
+    uint64_t *wbar = reinterpret_cast<uint64_t *>(wbase);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + 16);
+    uint32_t *strB = reinterpret_cast<uint32_t *>(wbase + 16 + A.stg_bytes);
+    uint32_t *strN = strB + A.strw;
+    uint8_t *outb = reinterpret_cast<uint8_t *>(strN + A.strw);
 
-    uint32_t tl = 0;
-    int dlen = 0, alpha = 0;
-    uint64_t c = 0;
-    // state of the parse that the emission needs
-    int m = 0, carry = 0, a0 = 0, p = 0, first_ml = 0;
-    typename std::conditional<(NW <= 4), uint32_t, unsigned long long>::type kindmask = 0;    // <= 8 sequences per word of the segment
-    int out_base = 0, run_base = 0, lit_base = 0, total = 0, totrun = 0, totlit = 0, final_lit = 0;
-    uint32_t sidx = 0;
-    bool any_n = false;                  // some allele of the frame is neither 0 nor 1
+    const uint32_t tl = A.tmpl_len[c];
+    const uint32_t tl16 = tl & ~15u, sh16 = tl & 15u;
+    if (threadIdx.x == 0) mbar_init(tbar, 1);
+    if (lane == 0) mbar_init(wbar, 1);
+    mbar_fence_init();
+    __syncthreads();
+    if (threadIdx.x == 0) {            // the chunk's template: once per CTA, by TMA
+        const uint32_t bytes = (tl + 15u) & ~15u;
+        mbar_expect_tx(tbar, bytes);
+        tma_load_1d(tmpl_s, A.tmpl + (size_t)c * A.tmpl_cap, bytes, tbar);
+    }
+    const uint32_t s_end = min(A.n_samples, (grp + 1) * A.gs);
+    uint32_t s = grp * A.gs + warp;
+    if (s >= s_end) return;
 
-    {
-        uint32_t s;
-        if (n_frames <= 0xFFFFFFFFull) { s = (uint32_t)wid / (uint32_t)A.n_chunks; c = (uint32_t)wid - s * (uint32_t)A.n_chunks; }
-        else { s = (uint32_t)(wid / A.n_chunks); c = wid % A.n_chunks; }
-        sidx = s;
-        tl = A.tmpl_len[c];
-        // the frame whose warp will take this warp's place when it retires: pull its two allele-plane slices into L2
-        if (A.pf_dist && lane < 2) {
-            uint64_t cf = c + A.pf_dr, sf = (uint64_t)s + A.pf_dq;           // frame wid + pf_dist, without a division
-            if (cf >= A.n_chunks) { cf -= A.n_chunks; ++sf; }
-            if (sf < A.n_samples) {
-            const uint64_t rf = cf * (uint64_t)cr;
-            const uint64_t off = (uint64_t)(A.s0 + sf) * A.gt_stride + (rf & ~15ull);
-            const uint32_t bytes = (uint32_t)((((rf & 15ull) + min((uint64_t)cr, A.n_records - rf) + 15ull) & ~15ull));
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((lane ? A.gt1 : A.gt0) + off), "r"(bytes) : "memory");
-            }
-        }
-        // ---- 1. planes -> packed bits in shared memory (the literals are rebuilt from the bits: keeping the raw bytes
-        //         too would cost 2 * cr bytes of shared memory per warp, i.e. a quarter of the resident warps)
-        const uint64_t r0 = c * (uint64_t)cr;
-        alpha = (int)(r0 & 15);
-        const int valid = (int)min((uint64_t)cr, A.n_records - r0);       // rows past n_records read as zero (HDF5 edge chunk)
-        const int nvec = (alpha + cr + 15) >> 4;
-        // B and N are ONE bit string each over both planes: block position x (0 .. 2 * cr) is bit alpha + x, so the
-        // parse and the literal copy walk from plane 0 into plane 1 without a seam
-        uint32_t *Bw = bits + 1, *Nw = Bw + BWW;
-        for (int i = lane; i < BWW / 2; i += 32) reinterpret_cast<uint4 *>(bits)[i] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
-        const uint64_t rowbase = (uint64_t)(A.s0 + s) * A.gt_stride + (r0 & ~15ull);
-        uint32_t nacc = 0;
-        for (int v = lane; v < 2 * nvec; v += 32) {
-            const int pl = v >= nvec, k = v - pl * nvec;
-            // rows of this vector that belong to the chunk: [lo_i, hi_i); rows before r0 or past n_records read as zero
-            const int lo_i = max(0, alpha - 16 * k), hi_i = alpha + valid - 16 * k;
-            if (hi_i <= 0) continue;
-            const uint4 x = ldg_stream(reinterpret_cast<const uint4 *>((pl ? A.gt1 : A.gt0) + rowbase + 16 * k));
-            uint32_t vm16 = 0xFFFFu;                                           // only the chunk's first / last vector is partial
-            if (lo_i > 0 || hi_i < 16) vm16 = low_mask(hi_i) & ~low_mask(lo_i) & 0xFFFFu;
-            const uint32_t b16 = (pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12)) & vm16;
-            uint32_t n16 = 0;
-            if ((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)
-                n16 = (pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12)) & vm16;
-            nacc |= n16;
-            const int bit = pl * cr + 16 * k, w = bit >> 5, sh = bit & 31;      // row i of the vector is bit 16 * k + i (+ cr)
-            if (b16) {
-                atomicOr(Bw + w, b16 << sh);
-                if (sh > 16) atomicOr(Bw + w + 1, b16 >> (32 - sh));
-            }
-            if (n16) {
-                atomicOr(Nw + w, n16 << sh);
-                if (sh > 16) atomicOr(Nw + w + 1, n16 >> (32 - sh));
-            }
-        }
-        __syncwarp();
-        any_n = __any_sync(0xffffffffu, nacc != 0);
-        const uint32_t sh16 = tl & 15u;      // the tail buffer lines up with the template's end modulo 16
-        uint8_t *seq = outb + sh16;
-        if (lane < 16) outb[lane] = 0;
-        __syncwarp();
+    const uint64_t r0 = (uint64_t)c * (uint64_t)cr;
+    const int valid = (int)min((uint64_t)cr, A.n_records - r0);       // rows past n_records read as zero (HDF5 edge chunk)
+    const int alpha = (int)(r0 & 127);                                 // block position x is bit alpha + x of the strings
+    const bool raw = cr < 6;                                           // see site_template_kernel
+    // the 128-row groups of the bit planes that hold rows [r0, r0 + valid)
+    const uint32_t g0 = (uint32_t)(r0 >> 7);
+    const uint32_t ngrp = (uint32_t)((r0 + (uint64_t)valid - 1) >> 7) - g0 + 1;
+    const uint32_t stg = ngrp * (kBitGroupWords * 4);
+    const int nwst = 4 * (int)ngrp;                                    // staged words per array
+    if (!raw && lane == 0) {
+        mbar_expect_tx(wbar, stg);
+        tma_load_1d(stage, A.bits + (uint64_t)(A.s0 + s) * A.bits_stride + (uint64_t)g0 * kBitGroupWords, stg, wbar);
+    }
+    uint32_t phase = 0;
+    bool tmpl_ready = false;
+    const unsigned long long row_stride = A.slot_off[A.n_chunks], slot = A.slot_off[c];
+    const int strw = (int)A.strw;
+    const int sh = cr & 31, wsh = cr >> 5;       // plane 1 sits cr bits above plane 0 in the strings
 
-        if (cr < 6) {                        // raw block, see site_template_kernel
-            for (int i = lane; i < n; i += 32) {
-                const int x = i < cr ? i : i - cr;
-                seq[i] = x < valid ? (uint8_t)(i < cr ? A.gt0 : A.gt1)[(uint64_t)(A.s0 + s) * A.gt_stride + r0 + x] : (uint8_t)0;
+    for (; s < s_end; s += kWpc) {
+        int dlen = 0;
+        // state of the parse that the emission needs
+        uint32_t S[NW], E[NW], K[NW];
+        int m = 0, carry = 0, out_base = 0, total = 0, final_lit = 0;
+        bool any_n = false;
+        const int p = lane >> 4, q = lane & 15;
+        const int seg = (cr + 15) >> 4;
+        const int a0 = q * seg;
+        const uint64_t grow = (uint64_t)(A.s0 + s) * A.gt_stride + r0;         // the frame's first row in the byte planes
+
+        if (!raw) {
+            // ---- 1. this frame's slices of the bit planes (staged by TMA) -> ONE bit string each for B and N over
+            //         both planes: block position x (0 .. 2 * cr) is bit alpha + x, so the parse and the literal
+            //         emission walk from plane 0 into plane 1 without a seam
+            mbar_wait(wbar, phase);
+            phase ^= 1;
+            uint32_t nacc = 0;
+            for (int w = lane; w < nwst; w += 32) {     // rows outside [r0, r0 + valid) belong to other chunks (or to nobody)
+                const uint32_t mk = low_mask(alpha + valid - 32 * w) & ~low_mask(alpha - 32 * w);
+                uint32_t *gq = stage + (w >> 2) * kBitGroupWords + (w & 3);
+                if (mk != 0xFFFFFFFFu) { gq[0] &= mk; gq[4] &= mk; gq[8] &= mk; gq[12] &= mk; }
+                nacc |= gq[8] | gq[12];
             }
-            dlen = n;
-        } else {
+            any_n = __any_sync(0xffffffffu, nacc != 0);
+            __syncwarp();
+            for (int k = lane; k < strw; k += 32) {
+                const int j = k - wsh;
+                uint32_t b = 0, b1lo = 0, b1hi = 0;
+                if (k < nwst) b = stage[(k >> 2) * kBitGroupWords + (k & 3)];
+                if (j >= 1 && j <= nwst) b1lo = stage[((j - 1) >> 2) * kBitGroupWords + 4 + ((j - 1) & 3)];
+                if (j >= 0 && j < nwst) b1hi = stage[(j >> 2) * kBitGroupWords + 4 + (j & 3)];
+                strB[k] = b | __funnelshift_l(b1lo, b1hi, sh);
+                if (any_n) {
+                    uint32_t x = 0, x1lo = 0, x1hi = 0;
+                    if (k < nwst) x = stage[(k >> 2) * kBitGroupWords + 8 + (k & 3)];
+                    if (j >= 1 && j <= nwst) x1lo = stage[((j - 1) >> 2) * kBitGroupWords + 12 + ((j - 1) & 3)];
+                    if (j >= 0 && j < nwst) x1hi = stage[(j >> 2) * kBitGroupWords + 12 + (j & 3)];
+                    strN[k] = x | __funnelshift_l(x1lo, x1hi, sh);
+                }
+            }
+            fence_proxy_async();                        // the staging area was masked in place: order that before the copy engine's writes
+            __syncwarp();
+            if (lane == 0 && s + kWpc < s_end) {        // the next frame's slices: one TMA bulk copy, a whole frame ahead
+                mbar_expect_tx(wbar, stg);
+                tma_load_1d(stage, A.bits + (uint64_t)(A.s0 + s + kWpc) * A.bits_stride + (uint64_t)g0 * kBitGroupWords, stg, wbar);
+            }
+
             // ---- 2. per-lane parse of one segment, position-parallel
-            p = lane >> 4;
-            const int q = lane & 15;
-            const int seg = (cr + 15) >> 4;
-            a0 = q * seg;
             const int seglen = max(0, min(seg, cr - a0));
             const int mlim = min(seglen, n - 11 - (p * cr + a0));         // the last 11 bytes of the block stay literals
             const int bi = alpha + p * cr + a0, j0 = bi >> 5, shb = bi & 31;
             const int bi0 = alpha + a0, j00 = bi0 >> 5, shb0 = bi0 & 31;     // the same rows in plane 0
-            uint32_t Z[NW], C[NW], ZR[NW], CR[NW];
+            uint32_t Z[NW], C[NW], ZR[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
-                const uint32_t bw = __funnelshift_r(Bw[j0 + k], Bw[j0 + k + 1], shb);
-                const uint32_t nw = __funnelshift_r(Nw[j0 + k], Nw[j0 + k + 1], shb);
+                const uint32_t bw = __funnelshift_r(strB[j0 + k], strB[j0 + k + 1], shb);
+                const uint32_t nw = any_n ? __funnelshift_r(strN[j0 + k], strN[j0 + k + 1], shb) : 0u;
                 const uint32_t vm = low_mask(mlim - 32 * k);
                 Z[k] = ~(bw | nw) & vm;
                 C[k] = 0;
                 if (p) {
-                    const uint32_t b0w = __funnelshift_r(Bw[j00 + k], Bw[j00 + k + 1], shb0);
-                    const uint32_t n0w = __funnelshift_r(Nw[j00 + k], Nw[j00 + k + 1], shb0);
+                    const uint32_t b0w = __funnelshift_r(strB[j00 + k], strB[j00 + k + 1], shb0);
+                    const uint32_t n0w = any_n ? __funnelshift_r(strN[j00 + k], strN[j00 + k + 1], shb0) : 0u;
                     C[k] = ~((bw ^ b0w) | nw | n0w) & vm;
                 }
             }
             runs_cover<NW, kMinZ>(Z, ZR);
 #pragma unroll
             for (int k = 0; k < NW; ++k) C[k] &= ~ZR[k];
-            runs_cover<NW, kMinC>(C, CR);
-            int prev_end = 0, first_lit = 0, size_rest = 0, lit_rest = 0, ne_rest = 0;
-            int n15 = 0, n19 = 0, nnz = 0;
-            {
-                bool open = false;
-                int ost = 0, okind = 0;
+            runs_cover<NW, kMinC>(C, K);          // K = the C-run cover: a match that starts on a K bit copies from plane 0
+            int matched = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                const uint32_t zp = k > 0 ? ZR[k - 1] : 0u, zn = k + 1 < NW ? ZR[k + 1] : 0u;
+                const uint32_t cp = k > 0 ? K[k - 1] : 0u, cn = k + 1 < NW ? K[k + 1] : 0u;
+                S[k] = (ZR[k] & ~__funnelshift_l(zp, ZR[k], 1)) | (K[k] & ~__funnelshift_l(cp, K[k], 1));
+                E[k] = (ZR[k] & ~__funnelshift_r(ZR[k], zn, 1)) | (K[k] & ~__funnelshift_r(K[k], cn, 1));
+                m += __popc(S[k]);
+                matched += __popc(ZR[k] | K[k]);
+            }
+            // size of the lane's output from popcounts: 3 bytes per match + its literals + one extension byte per
+            // literal run >= 15 (runs inside a segment are < 270) and per match >= 19 (a match is < 274 long)
+            int prev_end = 0, first_lit = 0, n_ext = 0;
+            if (m > 0) {
+                bool f = false;
+#pragma unroll
+                for (int k = NW - 1; k >= 0; --k)
+                    if (!f && E[k]) { prev_end = 32 * k + 32 - __clz(E[k]); f = true; }
+                f = false;
+#pragma unroll
+                for (int k = 0; k < NW; ++k)
+                    if (!f && S[k]) { first_lit = 32 * k + ctz32(S[k]); f = true; }
+                // a match [st, en] is >= 19 long iff no end bit lies in [st, st + 17]
+                uint32_t e1[NW], w[NW];
+                or_shr<NW>(E, 1, e1);
+                or_shr<NW>(e1, 2, w);
+                or_shr<NW>(w, 4, w);
+                or_shr<NW>(w, 8, w);
+#pragma unroll
+                for (int k = 0; k < NW; ++k) n_ext += __popc(S[k] & ~(w[k] | shr_word<NW>(e1, k, 16)));
+                // the literal run after end bit e (not the last one: that run is carried) is >= 15 long iff no start
+                // bit lies in [e + 1, e + 15]
+                uint32_t s1[NW], s2[NW], s3[NW];
+                or_shr<NW>(S, 1, s1);
+                or_shr<NW>(s1, 2, s2);
+                or_shr<NW>(s2, 4, s3);
 #pragma unroll
                 for (int k = 0; k < NW; ++k) {
-                    const uint32_t zp = k > 0 ? ZR[k - 1] : 0u, zn = k + 1 < NW ? ZR[k + 1] : 0u;
-                    const uint32_t cp = k > 0 ? CR[k - 1] : 0u, cn = k + 1 < NW ? CR[k + 1] : 0u;
-                    uint32_t st = (ZR[k] & ~__funnelshift_l(zp, ZR[k], 1)) | (CR[k] & ~__funnelshift_l(cp, CR[k], 1));
-                    uint32_t en = (ZR[k] & ~__funnelshift_r(ZR[k], zn, 1)) | (CR[k] & ~__funnelshift_r(CR[k], cn, 1));
-                    for (;;) {
-                        if (!open) {
-                            if (!st) break;
-                            const int ts = ctz32(st);
-                            st &= st - 1;
-                            ost = 32 * k + ts; okind = (CR[k] >> ts) & 1u; open = true;
-                        }
-                        if (!en) break;
-                        const int te = ctz32(en);
-                        en &= en - 1;
-                        const int ml = 32 * k + te - ost + 1, lit = ost - prev_end;
-                        seqs[m * 32 + lane] = (uint16_t)((ost << 8) | ml);
-                        kindmask |= (decltype(kindmask))okind << m;
-                        if (m == 0) { first_lit = lit; first_ml = ml; }
-                        n15 += lit >= 15; n19 += ml >= 19; nnz += lit > 0;
-                        prev_end = ost + ml;
-                        ++m;
-                        open = false;
-                    }
+                    uint32_t ek = E[k];
+                    if (32 * k <= prev_end - 1 && prev_end - 1 < 32 * k + 32) ek &= ~(1u << ((prev_end - 1) & 31));
+                    const uint32_t near = shr_word<NW>(s3, k, 1) | shr_word<NW>(s2, k, 9) | shr_word<NW>(s1, k, 13) | shr_word<NW>(S, k, 15);
+                    n_ext += __popc(ek & ~near);
                 }
-            }
-            if (m > 0) {                     // sizes of the sequences after the first, from totals
-                int matched = 0;
-#pragma unroll
-                for (int k = 0; k < NW; ++k) matched += __popc(ZR[k] | CR[k]);
-                lit_rest = prev_end - matched - first_lit;
-                size_rest = 3 * (m - 1) + lit_rest + (n15 - (first_lit >= 15)) + (n19 - (first_ml >= 19));
-                ne_rest = nnz - (first_lit > 0);
             }
             const int trail = seglen - prev_end;
 
-            // ---- 3. carry trailing literals forward; scans: output offset, literal index, sequence index
+            // ---- 3. carry trailing literals forward; scan: output offsets
             int val = trail, flag = m > 0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -620,443 +595,148 @@ __global__ void __launch_bounds__(kWpcMax * 32) donor_frames_kernel(const FusedA
             carry = __shfl_up_sync(0xffffffffu, val, 1);
             if (lane == 0) carry = 0;
             final_lit = __shfl_sync(0xffffffffu, val, 31);
-            const int lit0 = first_lit + carry;
-            const int mysize = m > 0 ? 3 + lit0 + lit_ext(lit0) + (first_ml >= 19) + size_rest : 0;
-            const int mylit = m > 0 ? lit0 + lit_rest : 0;
-            const int myrun = m > 0 ? (lit0 > 0) + ne_rest : 0;
-            uint32_t inc1 = (uint32_t)mysize | ((uint32_t)mylit << 16), inc2 = (uint32_t)myrun;
+            const int mysize = m > 0 ? 3 * m + (prev_end - matched) + carry + lit_ext(first_lit + carry) + n_ext : 0;
+            int inc = mysize;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t1 = __shfl_up_sync(0xffffffffu, inc1, d), t2 = __shfl_up_sync(0xffffffffu, inc2, d);
-                if (lane >= d) { inc1 += t1; inc2 += t2; }
+                const int t1 = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t1;
             }
-            const uint32_t tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-            total = (int)(tot1 & 0xFFFFu); totlit = (int)(tot1 >> 16);
-            totrun = (int)__shfl_sync(0xffffffffu, inc2, 31);
-            out_base = (int)(inc1 & 0xFFFFu) - mysize;
-            lit_base = (int)(inc1 >> 16) - mylit;
-            run_base = (int)inc2 - myrun;
+            total = __shfl_sync(0xffffffffu, inc, 31);
+            out_base = inc - mysize;
             dlen = total + 1 + lit_ext(final_lit) + final_lit;
-        }
-    }
-    const uint32_t flen = tl + (uint32_t)dlen + FRAME_TAIL;
+        } else dlen = n;
 
-    // ---- 4. every lane writes the headers of its own sequences, then the literals are copied in 32 equal shares
-    if (cr >= 6) {
-        uint8_t *seq = outb + (tl & 15u);
-        {
-            int o = out_base, r = run_base, lc = lit_base;
-            int prev_abs = p * cr + a0 - carry;
-            for (int j = 0; j < m; ++j) {
-                const uint32_t e = seqs[j * 32 + lane];
-                const int st = p * cr + a0 + (int)(e >> 8), ml = (int)(e & 255u);
-                const int off = ((kindmask >> j) & 1u) ? cr : 2 * cr;
-                const int lit = st - prev_abs;
-                seq[o++] = (uint8_t)((min(lit, 15) << 4) | min(ml - 4, 15));
-                if (lit >= 15) { int rem = lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-                // literal run: literal index g of the frame sits at bit g + dG of the B / N strings and goes to byte g + dD
-                if (lit > 0) { d_cum[r] = (uint16_t)lc; d_sd[r] = (uint32_t)(alpha + prev_abs - lc) | ((uint32_t)(o - lc) << 16); ++r; }
-                lc += lit; o += lit;
-                seq[o++] = (uint8_t)off; seq[o++] = (uint8_t)(off >> 8);
-                if (ml >= 19) seq[o++] = (uint8_t)(ml - 19);
-                prev_abs = st + ml;
-            }
-        }
-        if (lane == 0) {                     // the last sequence of the block: literals only (>= 11 of them)
-            int o = total;
-            seq[o++] = (uint8_t)(min(final_lit, 15) << 4);
-            if (final_lit >= 15) { int rem = final_lit - 15; while (rem >= 255) { seq[o++] = 255; rem -= 255; } seq[o++] = (uint8_t)rem; }
-            d_cum[totrun] = (uint16_t)totlit; d_sd[totrun] = (uint32_t)(alpha + n - final_lit - totlit) | ((uint32_t)(o - totlit) << 16);
-            d_cum[totrun + 1] = (uint16_t)(totlit + final_lit);
-        }
+        // ---- 4. the tail buffer: zeroed (neighbouring lanes OR their shared boundary words together), lined up with
+        //         the template's end modulo 16 so that the frame leaves as 16-byte aligned bulk copies
+        if (lane == 0) tma_store_wait_read();           // the previous frame's bulk store has read the buffer
         __syncwarp();
         {
-            const int totL = totlit + final_lit;
-            const uint64_t grow = (uint64_t)(A.s0 + sidx) * A.gt_stride + c * (uint64_t)cr;
-            const int share = (totL + 31) >> 5;
-            const int g0 = lane * share;
-            int cnt = min(share, totL - g0);
-            int lo = 0, hi = totrun + 1;
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)d_cum[mid] <= g0) lo = mid; else hi = mid; }
-            if (cnt > 0) {
-                // literal bytes come back from the bits (block position x is bit alpha + x of the B / N strings)
-                const uint32_t *Bw = bits + 1, *Nw = Bw + BWW;
-                const uint32_t *psd = d_sd + lo;
-                const uint16_t *pcum = d_cum + lo + 1;
-                uint32_t sd = *psd;
-                int nextcum = *pcum, dG = (int)(sd & 0xFFFFu), dD = (int)(sd >> 16);
-                int g = g0;
-                const int gend = g0 + cnt;
-                if (!any_n) {                                 // every allele of the frame is 0 or 1: the bit is the byte
-                    do {
-                        const int G = g + dG;
-                        seq[g + dD] = (uint8_t)(__funnelshift_r(Bw[G >> 5], 0u, G) & 1u);
-                        ++g;
-                        if (g == nextcum) { sd = *++psd; nextcum = *++pcum; dG = (int)(sd & 0xFFFFu); dD = (int)(sd >> 16); }
-                    } while (g < gend);
-                } else {
-                    do {
-                        const int G = g + dG;
-                        uint32_t v = __funnelshift_r(Bw[G >> 5], 0u, G) & 1u;
-                        if (__funnelshift_r(Nw[G >> 5], 0u, G) & 1u) {        // an allele other than 0 / 1: the byte itself
-                            const int x = G - alpha;
-                            v = (uint8_t)(x < cr ? A.gt0 : A.gt1)[grow + (x < cr ? x : x - cr)];
-                        }
-                        seq[g + dD] = (uint8_t)v;
-                        ++g;
-                        if (g == nextcum) { sd = *++psd; nextcum = *++pcum; dG = (int)(sd & 0xFFFFu); dD = (int)(sd >> 16); }
-                    } while (g < gend);
+            const int nz = (int)((sh16 + (uint32_t)dlen + 15u) >> 4);
+            for (int i = lane; i < nz; i += 32) reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
+        }
+        if (!tmpl_ready) { mbar_wait(tbar, 0); tmpl_ready = true; }
+        __syncwarp();
+        if ((uint32_t)lane < sh16) outb[lane] = tmpl_s[tl16 + lane];      // the template's last, partial 16 bytes
+        __syncwarp();
+        uint8_t *seq = outb + sh16;
+
+        if (raw) {
+            for (int i = lane; i < n; i += 32) {
+                const int x = i < cr ? i : i - cr;
+                seq[i] = x < valid ? (uint8_t)(i < cr ? A.gt0 : A.gt1)[grow + x] : (uint8_t)0;
+            }
+        } else {
+            // ---- 5. every lane walks its matches once: token, literals (rebuilt from the bits), offset
+            uint32_t waddr = smem_u32(seq) + (uint32_t)out_base;
+            uint32_t fill = waddr & 3u, lo = 0;
+            waddr &= ~3u;
+            bool first = true;               // the lane's first word may be shared with the lanes before it
+            auto put = [&](uint32_t v, uint32_t nb) {       // append the low nb (<= 4) bytes of v; the bytes above must be zero
+                lo |= v << (8u * fill);
+                const uint32_t hi = __funnelshift_l(v, 0u, 8u * fill);
+                fill += nb;
+                if (fill >= 4u) {
+                    if (first) sts_or32(waddr, lo); else sts32(waddr, lo);
+                    first = false;
+                    waddr += 4; lo = hi; fill -= 4u;
                 }
-            }
-        }
-    }
-    {
-        uint8_t *seq = outb + (tl & 15u);
-        const int padded = (int)((((tl & 15u) + (uint32_t)dlen + FRAME_TAIL + 15u) & ~15u) - (tl & 15u)) - dlen;   // tail + zero pad
-        for (int i = lane; i < padded; i += 32) seq[dlen + i] = i < FRAME_TAIL ? kFrameTail[i] : (uint8_t)0;
-    }
-    __syncwarp();
-
-    // ---- 5. template (L2) + own tail (shared memory) -> the frame's slot
-    const unsigned long long fbase = (unsigned long long)sidx * A.slot_off[A.n_chunks] + A.slot_off[c];
-    if (lane == 0) A.size[wid] = flen;
-    const uint32_t lz = tl - TMPL_HDR + (uint32_t)dlen, cb = CHUNK_HDR + 8 + lz;
-    const uint32_t jb = tl >> 4, nv = (flen + 15) >> 4;
-    const uint4 *T = reinterpret_cast<const uint4 *>(A.tmpl + c * A.tmpl_cap);
-    const uint4 *G = reinterpret_cast<const uint4 *>(outb);
-    uint4 *D = reinterpret_cast<uint4 *>(A.frames + fbase);
-#pragma unroll 4
-    for (uint32_t j = lane; j < nv; j += 32) {
-        uint4 v;
-        if (j < jb) v = ldg_nc(T + j);
-        else {
-            v = G[j - jb];
-            if (j == jb && (tl & 15u)) {           // the template's last bytes and the tail's pad are zero where the other has data
-                const uint4 t = ldg_nc(T + j);
-                v.x |= t.x; v.y |= t.y; v.z |= t.z; v.w |= t.w;
-            }
-        }
-        if (j <= 8) {                              // the four donor-dependent size fields (all zero in the template)
-            if (j == 1) v.y |= __byte_perm(flen, 0, 0x0123);                               // frame_len, BE64 @16
-            else if (j == 2) { v.z |= (cb >> 24) << 24; v.w |= __byte_perm(cb, 0, 0x0123) >> 8; }   // cbytes, BE64 @39
-            else if (j == 6) v.w |= cb << 8;                                               // chunk cbytes, LE32 @109
-            else if (j == 7) v.x |= cb >> 24;
-            else if (j == 8) { v.y |= lz << 8; v.z |= lz >> 24; }                          // stream csize, LE32 @133
-        }
-        stg_stream(D + j, v);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Kernel 4b, lane-per-frame split (experimental, HB_DONOR_SPLIT=lane; NOT the default).  The warp-per-frame
-// kernel above spends ~2500-3000 warp instructions on a frame that has ~150 LZ4 sequences: scans, ballots and
-// divergent per-lane loops keep most lanes idle.  Here a LANE owns a frame and runs a plain sequential encoder, a
-// warp owns the 32 frames (one chunk) x (32 consecutive samples):
-//   pack_alleles_kernel       allele planes gt[plane][sample][row] -> bit arrays B (byte & 1) and N (any other
-//                             bit) laid out [array][row / 32][sample]: the 32 lanes of a warp read the same
-//                             row word of 32 neighbouring samples with one 128-byte request.
-//   donor_frames_lane_kernel  phase 1, lock-step over the chunk's words: Z / C run covers with a 2-word
-//                             look-ahead pipeline in registers, matches appended to a per-lane list in
-//                             shared memory; phase 2 (when a list is nearly full, and at the end): every lane
-//                             emits its sequences -- token, literals rebuilt from the bits, offset -- through
-//                             an 8-byte register accumulator straight into its frame's slot; phase 3: the
-//                             chunk's template is read ONCE per warp and stored to the 32 slots with the four
-//                             size fields patched.
-// Same parse rules as above (zero runs >= 5 -> offset 2*cr, plane-1 == plane-0 runs >= 4 -> offset cr, last
-// 11 bytes literal) without the 32 segment breaks: streams are 0.6 % smaller (5.877x vs 5.84x overall).
-// Measured (1.1M x 2504, profiles/r01e_lane_split.txt): pack 1.60 ms + encode 11.9 ms = 13.5 ms against 9.19 ms
-// for the warp-per-frame kernel.  Phases 1 and 3 are cheap (~400 and ~100 warp instructions per frame) but phase 2
-// costs ~1650: the 32 lanes walk 32 different sequence lists in lock step, so every step pays for the longest
-// literal run among them (mean 5.7 literals per sequence, maximum over 32 lanes ~25).  The total, 2370 per frame,
-// is no better than the 2460 of the warp-per-frame kernel.
-// ------------------------------------------------------------------------------------------
-struct PackArgs {
-    const int8_t *gt0, *gt1;
-    uint64_t gt_stride, n_records;
-    uint32_t s0, n_samples;
-    uint32_t sp;                 // samples per row word of the bit arrays (window rounded up to 32)
-    uint32_t rw;                 // row words per array
-    uint32_t *bits;              // [4][rw][sp]: B0, N0, B1, N1
-};
-
-__device__ __forceinline__ uint32_t pack_lsb16(const uint4 &x) {
-    return pack_lsb4(x.x) | (pack_lsb4(x.y) << 4) | (pack_lsb4(x.z) << 8) | (pack_lsb4(x.w) << 12);
-}
-__device__ __forceinline__ uint32_t pack_nz16(const uint4 &x) {
-    if (!((x.x | x.y | x.z | x.w) & 0xFEFEFEFEu)) return 0u;
-    return pack_nz4(x.x) | (pack_nz4(x.y) << 4) | (pack_nz4(x.z) << 8) | (pack_nz4(x.w) << 12);
-}
-
-constexpr int kPackWords = 4;    // row words (128 rows) per thread
-
-__global__ void __launch_bounds__(256) pack_alleles_kernel(const PackArgs A) {
-    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-    const uint32_t s = blockIdx.x * 32 + lane;
-    const uint32_t j0 = (blockIdx.y * 8 + wy) * kPackWords;
-    if (j0 >= A.rw) return;
-    const bool live = s < A.n_samples;
-    const uint64_t row = (uint64_t)(A.s0 + (live ? s : 0)) * A.gt_stride;
-    const size_t plane = (size_t)A.rw * A.sp;
-#pragma unroll
-    for (int pl = 0; pl < 2; ++pl) {
-        const int8_t *g = (pl ? A.gt1 : A.gt0) + row;
-        uint4 x[2 * kPackWords];
-#pragma unroll
-        for (int i = 0; i < 2 * kPackWords; ++i) {
-            const uint64_t r = (uint64_t)j0 * 32 + 16 * i;
-            x[i] = make_uint4(0, 0, 0, 0);
-            if (live && r < A.n_records) x[i] = ldg_stream(reinterpret_cast<const uint4 *>(g + r));
-        }
-#pragma unroll
-        for (int w = 0; w < kPackWords; ++w) {
-            if (j0 + w < A.rw) {
-                const uint64_t r = (uint64_t)(j0 + w) * 32;
-                const uint32_t vm = r >= A.n_records ? 0u : low_mask((int)min((uint64_t)32, A.n_records - r));
-                const uint32_t b = pack_lsb16(x[2 * w]) | (pack_lsb16(x[2 * w + 1]) << 16);
-                const uint32_t nn = pack_nz16(x[2 * w]) | (pack_nz16(x[2 * w + 1]) << 16);
-                uint32_t *o = A.bits + (size_t)(2 * pl) * plane + (size_t)(j0 + w) * A.sp + s;
-                o[0] = b & vm;
-                o[plane] = nn & vm;
-            }
-        }
-    }
-}
-
-struct LaneArgs {
-    const uint32_t *bits;
-    uint32_t sp, rw;
-    const int8_t *gt0, *gt1;             // raw bytes: only read for alleles other than 0 / 1
-    uint64_t gt_stride, n_records;
-    uint32_t cr, n_samples, s0, groups;  // groups: 32-sample groups of the window
-    uint64_t n_chunks;
-    const uint8_t *tmpl;
-    uint32_t tmpl_cap;
-    const uint32_t *tmpl_len;
-    uint8_t *frames;
-    const uint64_t *slot_off;
-    uint32_t *size;
-};
-
-constexpr int kLaneWpc = 4;              // warps per CTA
-constexpr int kEntCap = 48;              // matches a lane collects before the warp emits
-
-// the 8-byte accumulator a lane writes its frame through
-struct LaneOut {
-    uint64_t lo;
-    int fill;
-    uint64_t *p;
-    __device__ __forceinline__ void put(uint32_t v, int k) {       // k in 1..4 bytes of v (the others are zero)
-        lo |= (uint64_t)v << (8 * fill);
-        fill += k;
-        if (fill >= 8) {
-            *p++ = lo;
-            fill -= 8;
-            lo = (uint64_t)v >> (8 * (k - fill));
-        }
-    }
-    __device__ __forceinline__ void put_len(int rem) {             // LZ4 length extension bytes
-        while (rem >= 255) { put(255u, 1); rem -= 255; }
-        put((uint32_t)rem, 1);
-    }
-};
-
-template <int R>
-__device__ __forceinline__ uint32_t run_starts(uint32_t x, uint32_t nxt) {      // bit i: x has R ones from i on
-    uint32_t s = x;
-#pragma unroll
-    for (int d = 1; d < R; ++d) s &= __funnelshift_r(x, nxt, d);
-    return s;
-}
-template <int R>
-__device__ __forceinline__ uint32_t run_cover(uint32_t sprev, uint32_t s) {     // positions inside such runs
-    uint32_t r = s;
-#pragma unroll
-    for (int d = 1; d < R; ++d) r |= __funnelshift_l(sprev, s, d);
-    return r;
-}
-
-__global__ void __launch_bounds__(kLaneWpc * 32) donor_frames_lane_kernel(const LaneArgs A) {
-    __shared__ uint32_t s_ent[kLaneWpc][kEntCap * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t wid = (uint64_t)blockIdx.x * kLaneWpc + warp;
-    if (wid >= A.n_chunks * A.groups) return;
-    const uint32_t c = (uint32_t)(wid / A.groups), g = (uint32_t)(wid - (uint64_t)c * A.groups);
-    const uint32_t s = g * 32 + lane;
-    const bool live = s < A.n_samples;
-    const int cr = (int)A.cr, n = 2 * cr;
-    const uint32_t tl = A.tmpl_len[c];
-    const uint64_t row_stride = A.slot_off[A.n_chunks], so = A.slot_off[c];
-    uint8_t *frame = A.frames + (uint64_t)(live ? s : 0) * row_stride + so;
-    const uint64_t r0 = (uint64_t)c * cr;
-    const uint32_t j0 = (uint32_t)(r0 >> 5);
-    const int sh = (int)(r0 & 31);
-    const size_t plane = (size_t)A.rw * A.sp;
-    const uint32_t *col = A.bits + (size_t)j0 * A.sp + s;      // this lane's column, first row word of the chunk
-    uint32_t *ent = s_ent[warp] + lane;
-
-    LaneOut o;
-    o.p = reinterpret_cast<uint64_t *>(frame + (tl & ~7u));
-    o.fill = (int)(tl & 7u);
-    o.lo = 0;
-    if (o.fill) o.lo = *reinterpret_cast<const uint64_t *>(A.tmpl + (size_t)c * A.tmpl_cap + (tl & ~7u)) & ((1ull << (8 * o.fill)) - 1ull);
-    uint64_t *const p_first = o.p;
-    int lit_start = 0, cnt = 0;
-
-    // literals [a, b) of the block, rebuilt from the bit arrays (raw bytes only where N is set)
-    auto put_literals = [&](int a, int b) {
-        int x = a;
-        while (x < b) {
-            const int pl = x >= cr, i = x - pl * cr;
-            const int rb = sh + i, bo = rb & 31;
-            int take = min(b - x, 32 - bo);
-            if (!pl) take = min(take, cr - x);
-            const uint32_t *w = col + (size_t)(2 * pl) * plane + (size_t)(rb >> 5) * A.sp;
-            const uint32_t m = low_mask(take);
-            const uint32_t bw = (__ldg(w) >> bo) & m, nw = (__ldg(w + plane) >> bo) & m;
-            for (int q = 0; q < take; q += 4) {
-                const int k4 = min(4, take - q);
-                uint32_t v = (((bw >> q) & 15u) * 0x00204081u) & 0x01010101u;
-                const uint32_t nq = (nw >> q) & 15u;
-                if (nq) {
-                    const int8_t *raw = (pl ? A.gt1 : A.gt0) + (uint64_t)(A.s0 + s) * A.gt_stride + r0 + i + q;
-                    for (int t = 0; t < k4; ++t)
-                        if ((nq >> t) & 1u) v = (v & ~(0xFFu << (8 * t))) | ((uint32_t)(uint8_t)raw[t] << (8 * t));
-                }
-                o.put(v, k4);
-            }
-            x += take;
-        }
-    };
-    auto emit = [&](uint32_t e) {
-        const int ost = (int)(e & 0x1FFFu), ml = (int)((e >> 13) & 0xFFFu);
-        const int off = (e >> 31) ? cr : 2 * cr;
-        const int lit = ost - lit_start;
-        o.put((uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15)), 1);
-        if (lit >= 15) o.put_len(lit - 15);
-        put_literals(lit_start, ost);
-        if (ml < 19) o.put((uint32_t)off, 2);
-        else if (ml < 19 + 255) o.put((uint32_t)off | ((uint32_t)(ml - 19) << 16), 3);
-        else { o.put((uint32_t)off | 0xFF0000u, 3); o.put_len(ml - 19 - 255); }
-        lit_start = ost + ml;
-    };
-    auto drain = [&]() {
-        const int maxc = __reduce_max_sync(0xffffffffu, cnt);
-        for (int i = 0; i < maxc; ++i)
-            if (i < cnt) emit(ent[i * 32]);
-        cnt = 0;
-    };
-
-    // ---- 1. matches of both planes, word by word
-    for (int p = 0; p < 2; ++p) {
-        const int lim = live ? max(0, min(cr, n - 11 - p * cr)) : 0;           // the last 11 bytes of the block stay literals
-        const int W = (__reduce_max_sync(0xffffffffu, lim) + 31) >> 5;
-        const uint32_t *cb = col + (size_t)(2 * p) * plane;
-        // row words: cur = word j0 + t, nxt = word j0 + t + 1 (loaded one step ahead of their use)
-        uint32_t rb_ = __ldg(cb), rn_ = __ldg(cb + plane), r0b = 0, r0n = 0;
-        uint32_t xb_ = __ldg(cb + A.sp), xn_ = __ldg(cb + A.sp + plane), x0b = 0, x0n = 0;
-        if (p) { r0b = __ldg(col); r0n = __ldg(col + plane); x0b = __ldg(col + A.sp); x0n = __ldg(col + A.sp + plane); }
-        uint32_t zA = 0, cxA = 0, zsA = 0, zrA = 0, ccA = 0, csA = 0, pz = 0, pc = 0;
-        bool open = false;
-        int ost = 0;
-        uint32_t okind = 0;
-        for (int t = 0; t <= W + 2; ++t) {
-            // chunk-relative word t of this plane (zero past lim)
-            const uint32_t *nx = cb + (size_t)(t + 2) * A.sp;
-            const uint32_t ldb = __ldg(nx), ldn = __ldg(nx + plane);
-            uint32_t ld0b = 0, ld0n = 0;
-            if (p) { const uint32_t *n0 = col + (size_t)(t + 2) * A.sp; ld0b = __ldg(n0); ld0n = __ldg(n0 + plane); }
-            const uint32_t vm = low_mask(lim - 32 * t);
-            const uint32_t bw = __funnelshift_r(rb_, xb_, sh), nw = __funnelshift_r(rn_, xn_, sh);
-            const uint32_t zN = ~(bw | nw) & vm;
-            uint32_t cxN = 0;
-            if (p) {
-                const uint32_t b0w = __funnelshift_r(r0b, x0b, sh), n0w = __funnelshift_r(r0n, x0n, sh);
-                cxN = ~((bw ^ b0w) | nw | n0w) & vm;
-            }
-            rb_ = xb_; rn_ = xn_; r0b = x0b; r0n = x0n;
-            xb_ = ldb; xn_ = ldn; x0b = ld0b; x0n = ld0n;
-            const uint32_t zsB = run_starts<kMinZ>(zA, zN);           // word t-1
-            const uint32_t zrB = run_cover<kMinZ>(zsA, zsB);          // word t-1
-            const uint32_t ccB = cxA & ~zrB;                          // word t-1
-            const uint32_t csB = run_starts<kMinC>(ccA, ccB);         // word t-2
-            const uint32_t crW = run_cover<kMinC>(csA, csB);          // word t-2
-            if (t >= 2) {
-                if (__any_sync(0xffffffffu, cnt > kEntCap - 9)) drain();
-                const int k = t - 2;
-                const uint32_t mz = zrA, mc = crW;
-                const uint32_t mz1 = (mz << 1) | pz, mc1 = (mc << 1) | pc;
-                uint32_t st = (mz & ~mz1) | (mc & ~mc1);
-                uint32_t enx = (mz1 & ~mz) | (mc1 & ~mc);
-                pz = mz >> 31; pc = mc >> 31;
-                const int base = p * cr + 32 * k;
-                for (;;) {
-                    if (open) {
-                        if (!enx) break;
-                        const int te = ctz32(enx);
-                        enx &= enx - 1;
-                        ent[cnt * 32] = (uint32_t)ost | ((uint32_t)(base + te - ost) << 13) | (okind << 31);
-                        ++cnt;
-                        open = false;
+            };
+            // up to 4 literal bytes of block positions x .. x + nb - 1
+            auto lit4 = [&](int x, int nb) -> uint32_t {
+                const int G = alpha + x;
+                uint32_t v = spread4(__funnelshift_r(strB[G >> 5], strB[(G >> 5) + 1], G)) & low_mask(8 * nb);
+                if (any_n) {
+                    uint32_t nb4 = __funnelshift_r(strN[G >> 5], strN[(G >> 5) + 1], G) & low_mask(nb);
+                    while (nb4) {                            // an allele other than 0 / 1: the byte itself
+                        const int i = ctz32(nb4);
+                        nb4 &= nb4 - 1;
+                        const int xx = x + i;
+                        const uint32_t byte = (uint8_t)(xx < cr ? A.gt0 : A.gt1)[grow + (xx < cr ? xx : xx - cr)];
+                        v = (v & ~(0xFFu << (8 * i))) | (byte << (8 * i));
                     }
-                    if (!st) break;
-                    const int ts = ctz32(st);
-                    st &= st - 1;
-                    ost = base + ts; okind = (mc >> ts) & 1u; open = true;
                 }
+                return v;
+            };
+            auto lit_run = [&](int x, int cnt) {            // literals x .. x + cnt - 1, four per step
+                for (int k = 0; k < cnt; k += 4) { const int nb = min(4, cnt - k); put(lit4(x + k, nb), (uint32_t)nb); }
+            };
+            const int seg_abs = p * cr + a0;
+            int pos = seg_abs - carry, base = 0;
+            for (int jx = 0; jx < m; ++jx) {
+                while (S[0] == 0) {
+#pragma unroll
+                    for (int k = 0; k + 1 < NW; ++k) { S[k] = S[k + 1]; E[k] = E[k + 1]; K[k] = K[k + 1]; }
+                    S[NW - 1] = 0; E[NW - 1] = 0; K[NW - 1] = 0;
+                    base += 32;
+                }
+                const int ts = ctz32(S[0]);
+                S[0] &= S[0] - 1;
+                const int off = ((K[0] >> ts) & 1u) ? cr : 2 * cr;
+                int te = 0;
+                {
+                    bool f = false;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k)
+                        if (!f && E[k]) { te = 32 * k + ctz32(E[k]); E[k] &= E[k] - 1; f = true; }
+                }
+                const int st = seg_abs + base + ts, ml = te - ts + 1;
+                const int lit = st - pos;
+                const uint32_t tok = (uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15));
+                if (lit < 15) {
+                    const int n1 = min(lit, 3);
+                    put(tok | (lit4(pos, n1) << 8), (uint32_t)(1 + n1));
+                    if (lit > 3) lit_run(pos + 3, lit - 3);
+                } else {
+                    put(tok, 1);
+                    int rem = lit - 15;
+                    while (rem >= 255) { put(255u, 1); rem -= 255; }
+                    put((uint32_t)rem, 1);
+                    lit_run(pos, lit);
+                }
+                put((uint32_t)off | (ml >= 19 ? (uint32_t)(ml - 19) << 16 : 0u), ml >= 19 ? 3u : 2u);
+                pos = st + ml;
             }
-            zA = zN; cxA = cxN; zsA = zsB; zrA = zrB; ccA = ccB; csA = csB;
+            if (lane == 31) {                // the last sequence of the block: literals only (>= 11 of them)
+                put((uint32_t)(min(final_lit, 15) << 4), 1);
+                if (final_lit >= 15) {
+                    int rem = final_lit - 15;
+                    while (rem >= 255) { put(255u, 1); rem -= 255; }
+                    put((uint32_t)rem, 1);
+                }
+                lit_run(n - final_lit, final_lit);
+            }
+            if (fill) sts_or32(waddr, lo);
         }
-    }
-    drain();
+        fence_proxy_async();                 // the tail buffer is read by the bulk-copy engine next
+        __syncwarp();
 
-    // ---- 2. the last sequence (literals only), the frame's tail, zero pad to 16 bytes
-    uint32_t flen = 0;
-    int dlen = 0;
-    if (live) {
-        const int L = n - lit_start;
-        o.put((uint32_t)(min(L, 15) << 4), 1);
-        if (L >= 15) o.put_len(L - 15);
-        put_literals(lit_start, n);
-        dlen = (int)(o.p - p_first) * 8 + o.fill - (int)(tl & 7u);
-        const uint32_t *tw = reinterpret_cast<const uint32_t *>(kFrameTail);
-#pragma unroll 1
-        for (int i = 0; i < FRAME_TAIL / 4; ++i) o.put(tw[i], 4);
-        o.put(tw[FRAME_TAIL / 4] & 0xFFFFFFu, FRAME_TAIL & 3);
-        if (o.fill) *o.p++ = o.lo;
-        if ((o.p - reinterpret_cast<uint64_t *>(frame)) & 1) *o.p++ = 0ull;
-        flen = tl + (uint32_t)dlen + FRAME_TAIL;
-        A.size[(uint64_t)s * A.n_chunks + c] = flen;
-    }
-
-    // ---- 3. the template, once per warp, into the 32 slots; the four donor-dependent size fields patched
-    const int nact = (int)min(32u, A.n_samples - g * 32);
-    const uint32_t ncopy = tl & ~7u, nv = ncopy >> 4;
-    const uint4 *T = reinterpret_cast<const uint4 *>(A.tmpl + (size_t)c * A.tmpl_cap);
-    uint8_t *slot0 = A.frames + (uint64_t)(g * 32) * row_stride + so;
-    {
-        // vectors 0..31 (the patched ones are 1, 2, 6, 7, 8)
-        const uint32_t j = (uint32_t)lane;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < nv) v = ldg_nc(T + j);
-        for (int f = 0; f < nact; ++f) {
-            const uint32_t fl = __shfl_sync(0xffffffffu, flen, f);
-            const uint32_t lz = fl - FRAME_TAIL - TMPL_HDR, cbz = CHUNK_HDR + 8 + lz;
-            uint4 x = v;
-            if (j == 1) x.y |= __byte_perm(fl, 0, 0x0123);                                   // frame_len, BE64 @16
-            else if (j == 2) { x.z |= (cbz >> 24) << 24; x.w |= __byte_perm(cbz, 0, 0x0123) >> 8; }   // cbytes, BE64 @39
-            else if (j == 6) x.w |= cbz << 8;                                                // chunk cbytes, LE32 @109
-            else if (j == 7) x.x |= cbz >> 24;
-            else if (j == 8) { x.y |= lz << 8; x.z |= lz >> 24; }                            // stream csize, LE32 @133
-            if (j < nv) stg_stream(reinterpret_cast<uint4 *>(slot0 + (uint64_t)f * row_stride) + j, x);
+        // ---- 6. the frame leaves: 2 header vectors (size fields filled in) + template body + own tail by TMA bulk stores
+        const uint32_t flen = tl + (uint32_t)dlen;               // = cbytes of the Blosc chunk header
+        const uint32_t lz = flen - TMPL_HDR;                     // = csize of the block's stream
+        uint8_t *dst = A.frames + (unsigned long long)(s) * row_stride + slot;
+        if (tl16 >= 32) {
+            if (lane < 2) {
+                uint4 v = reinterpret_cast<const uint4 *>(tmpl_s)[lane];
+                if (lane == 0) v.w = flen; else v.y = lz;
+                stg_stream(reinterpret_cast<uint4 *>(dst) + lane, v);
+            }
+            if (lane == 0) {
+                if (tl16 > 32) tma_store_1d(dst + 32, tmpl_s + 32, tl16 - 32);
+                tma_store_1d(dst + tl16, outb, (sh16 + (uint32_t)dlen + 15u) & ~15u);
+                tma_store_commit();
+            }
+        } else {                             // a template shorter than its two header vectors (tiny chunks): byte by byte
+            for (uint32_t i = lane; i < flen; i += 32) {
+                uint32_t b = i < tl ? tmpl_s[i] : seq[i - tl];
+                if (i >= 12 && i < 16) b = (flen >> (8 * (i - 12))) & 0xFFu;
+                if (i >= 20 && i < 24) b = (lz >> (8 * (i - 20))) & 0xFFu;
+                dst[i] = (uint8_t)b;
+            }
         }
+        if (lane == 0) A.size[(uint64_t)s * A.n_chunks + c] = flen;
     }
-    for (uint32_t j = 32 + lane; j < nv; j += 32) {
-        const uint4 v = ldg_nc(T + j);
-        uint8_t *d = slot0 + (size_t)j * 16;
-#pragma unroll 4
-        for (int f = 0; f < nact; ++f) { stg_stream(reinterpret_cast<uint4 *>(d), v); d += row_stride; }
-    }
-    if ((ncopy & 8u) && live) *reinterpret_cast<uint64_t *>(frame + (size_t)nv * 16) = *reinterpret_cast<const uint64_t *>(A.tmpl + (size_t)c * A.tmpl_cap + (size_t)nv * 16);
+    if (lane == 0) tma_store_wait_read();    // shared memory must outlive the bulk stores that read it
 }
 
 __global__ void __launch_bounds__(256) sum_sizes_kernel(const uint32_t *__restrict__ size, uint64_t n, unsigned long long *__restrict__ total) {
@@ -1099,7 +779,6 @@ struct hb_frames {
     size_t smem_site = 0;
     FusedArgs fa;                            // geometry of the fused kernel
     int nw = 1;
-    uint64_t n_ctas = 0;
     uint8_t *d_tmpl = nullptr, *d_frames = nullptr;
     uint32_t *d_tmpl_len = nullptr, *d_size = nullptr;
     uint64_t *d_slot_off = nullptr;
@@ -1119,21 +798,23 @@ struct hb_frames {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_sites = nullptr, ev_tmpl = nullptr, ev_side0 = nullptr;
     bool early_site = false;                     // the template pass of the current parse run is already in flight
-    // lane-per-frame encoder: bit arrays of the window's allele planes
-    uint32_t *d_bits = nullptr;
-    uint64_t bits_cap = 0;                       // bytes
-    cudaEvent_t ev_pack = nullptr;
-    float ms_pack = 0;
-    bool lane_split = false;                     // the last run used the lane-per-frame kernels
 };
+
+// More than 48 KB of dynamic shared memory is opt-in per function AND per device.  The ceiling is always raised to the
+// device maximum (never to the size of one launch), so that concurrent callers cannot shrink each other's limit, and on
+// every launch (a microsecond), so that a process that moves to another device is served too.
+static void raise_smem_limit(const void *func) {
+    int dev = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max - 1024);
+}
 
 template <int NW>
 static void launch_donor_frames(const FusedArgs &fa, uint64_t n_ctas, cudaStream_t st) {
-    donor_frames_kernel<NW><<<(unsigned)n_ctas, fa.wpc * 32, (size_t)fa.wpc * fa.warp_smem, st>>>(fa);
-}
-template <int NW>
-static cudaError_t attr_donor_frames(size_t smem) {
-    return cudaFuncSetAttribute(donor_frames_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = 16 + (size_t)fa.tmpl_smem + (size_t)kWpc * fa.warp_smem;
+    raise_smem_limit(reinterpret_cast<const void *>(donor_frames_kernel<NW>));
+    donor_frames_kernel<NW><<<(unsigned)n_ctas, kWpc * 32, smem, st>>>(fa);
 }
 
 // The frame buffer is many GB and cudaMalloc / cudaFree of that size cost ~100 ms (and cudaFree synchronises the device):
@@ -1152,6 +833,9 @@ void frames_buffer_cache_clear() {
 }
 }
 
+static std::atomic<int> g_site_deep{0};
+extern "C" void hb_set_site_matcher(int deep) { g_site_deep.store(deep ? 1 : 0); }
+
 // templates of all chunks.  early: launched from inside run_parse on the side stream, right after the site columns
 // were written on the parse's stream; otherwise on the parse's stream itself.
 static int frames_site_pass(hb_frames *f, hb_parse *p, bool early) {
@@ -1160,16 +844,14 @@ static int frames_site_pass(hb_frames *f, hb_parse *p, bool early) {
     SiteArgs4 sa;
     sa.chrom5 = p->d_chrom5; sa.start = p->d_start; sa.stop = p->d_stop; sa.ref = p->d_ref; sa.alt = p->d_alt;
     sa.n_records = f->n_records; sa.cr = (uint32_t)f->cr; sa.tmpl = f->d_tmpl; sa.tmpl_cap = f->tmpl_cap; sa.tmpl_len = f->d_tmpl_len;
-    {
-        const char *e = getenv("HB_SITE_MATCHER");
-        sa.deep = e && !strcmp(e, "deep");
-    }
+    sa.deep = g_site_deep.load() ? 1 : 0;
     cudaStream_t st = early ? f->side : f->stream;
     if (early) {
         CUF(cudaEventRecord(f->ev_sites, p->stream));
         CUF(cudaStreamWaitEvent(f->side, f->ev_sites, 0));
     }
     CUF(cudaEventRecord(early ? f->ev_side0 : f->ev[0], st));
+    raise_smem_limit(reinterpret_cast<const void *>(site_template_kernel));
     site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, st>>>(sa);
     count_launch();
     CUF(cudaEventRecord(early ? f->ev_tmpl : f->ev[1], st));
@@ -1213,7 +895,7 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     // slots: frame <= template + worst-case allele tail, so every address is known before the encode
     uint64_t need = 0;
     {
-        const uint64_t tail = 2ull * cr + 2ull * cr / 255 + 24 + FRAME_TAIL;
+        const uint64_t tail = 2ull * cr + 2ull * cr / 255 + 24;
         uint64_t run = 0;
         for (uint64_t c = 0; c < f->n_chunks; ++c) { f->h_slot_off[c] = run; run += (f->h_tmpl_len[c] + tail + 15) & ~15ull; }
         f->h_slot_off[f->n_chunks] = run;
@@ -1243,55 +925,25 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     fa.gt0 = p->d_gt[0]; fa.gt1 = p->d_gt[1]; fa.gt_stride = p->gt_stride; fa.n_records = n;
     fa.cr = cr; fa.n_samples = f->n_samples; fa.s0 = f->s0; fa.n_chunks = f->n_chunks;
     fa.tmpl = f->d_tmpl; fa.tmpl_cap = f->tmpl_cap; fa.tmpl_len = f->d_tmpl_len;
-    fa.frames = f->d_frames; fa.slot_off = f->d_slot_off; fa.size = f->d_size; fa.totals = f->d_totals;
+    fa.frames = f->d_frames; fa.slot_off = f->d_slot_off; fa.size = f->d_size;
+    fa.bits = p->d_bits; fa.bits_stride = p->bits_stride;
     {
-        int sms = 148, per_sm = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, f->device);
-        // resident warps of this kernel on the whole GPU (shared memory decides): the distance to prefetch at
-        const size_t smem_cta = (size_t)fa.wpc * fa.warp_smem + 1024;
-        per_sm = (int)std::min<size_t>(32, (227 * 1024) / smem_cta);
-        fa.pf_dist = (uint32_t)(sms * std::min<uint32_t>(40, per_sm * fa.wpc));
-        if (const char *e = getenv("HB_DF_PREFETCH")) fa.pf_dist = (uint32_t)atoi(e);
-        fa.pf_dq = (uint32_t)(fa.pf_dist / f->n_chunks); fa.pf_dr = (uint32_t)(fa.pf_dist % f->n_chunks);
+        uint32_t mx = 0;
+        for (uint64_t c = 0; c < f->n_chunks; ++c) mx = std::max(mx, f->h_tmpl_len[c]);
+        fa.tmpl_smem = (mx + 15u) & ~15u;
+        fa.gs = kWpc * kFramesPerWarp;
+        fa.groups = (f->n_samples + fa.gs - 1) / fa.gs;
+        if (16 + (size_t)fa.tmpl_smem + (size_t)kWpc * fa.warp_smem > 227 * 1024)
+            return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder (template + tail buffers exceed shared memory)");
     }
-    // HB_DONOR_SPLIT=lane asks for the lane-per-frame kernels (measured slower, see their header); they need chunks
-    // that are not tiny: the four size fields must lie inside the template copy
-    bool lane_split = false;
-    if (const char *e = getenv("HB_DONOR_SPLIT")) lane_split = !strcmp(e, "lane") && cr >= 16;
-    for (uint64_t c = 0; c < f->n_chunks && lane_split; ++c) lane_split = f->h_tmpl_len[c] >= 152;
-    f->lane_split = lane_split;
-    if (lane_split) {
-        const uint32_t sp_cap = (f->win_cap + 31) & ~31u, sp = (f->n_samples + 31) & ~31u;
-        const uint64_t rw_cap = (f->chunk_cap * (uint64_t)cr + 31) / 32 + 8, rw = (f->n_chunks * (uint64_t)cr + 31) / 32 + 8;
-        const uint64_t need_bits = 16ull * rw_cap * sp_cap;
-        if (f->bits_cap < need_bits) {
-            if (f->d_bits) { dev_pool_free(f->d_bits); f->d_bits = nullptr; f->bits_cap = 0; }
-            e = dev_pool_alloc((void **)&f->d_bits, need_bits);
-            if (e != cudaSuccess) return api_fail(HB_ERR_MEM, std::string("cudaMalloc of the allele bit arrays (") + std::to_string(need_bits) + " bytes): " + cudaGetErrorString(e));
-            f->bits_cap = need_bits;
-        }
-        PackArgs pa;
-        pa.gt0 = fa.gt0; pa.gt1 = fa.gt1; pa.gt_stride = fa.gt_stride; pa.n_records = n;
-        pa.s0 = f->s0; pa.n_samples = f->n_samples; pa.sp = sp; pa.rw = (uint32_t)rw; pa.bits = f->d_bits;
-        pack_alleles_kernel<<<dim3(sp / 32, (unsigned)((rw + 8 * kPackWords - 1) / (8 * kPackWords))), 256, 0, f->stream>>>(pa);
-        CUF(cudaEventRecord(f->ev_pack, f->stream));
-        LaneArgs la;
-        la.bits = f->d_bits; la.sp = sp; la.rw = (uint32_t)rw;
-        la.gt0 = fa.gt0; la.gt1 = fa.gt1; la.gt_stride = fa.gt_stride; la.n_records = n;
-        la.cr = cr; la.n_samples = f->n_samples; la.s0 = f->s0; la.groups = sp / 32; la.n_chunks = f->n_chunks;
-        la.tmpl = f->d_tmpl; la.tmpl_cap = f->tmpl_cap; la.tmpl_len = f->d_tmpl_len;
-        la.frames = f->d_frames; la.slot_off = f->d_slot_off; la.size = f->d_size;
-        const uint64_t n_warps = f->n_chunks * la.groups;
-        donor_frames_lane_kernel<<<(unsigned)((n_warps + kLaneWpc - 1) / kLaneWpc), kLaneWpc * 32, 0, f->stream>>>(la);
-        count_launch(1);
-    } else
+    const uint64_t n_ctas = f->n_chunks * fa.groups;
     switch (f->nw) {
-        case 1: launch_donor_frames<1>(fa, f->n_ctas, f->stream); break;
-        case 2: launch_donor_frames<2>(fa, f->n_ctas, f->stream); break;
-        case 3: launch_donor_frames<3>(fa, f->n_ctas, f->stream); break;
-        case 4: launch_donor_frames<4>(fa, f->n_ctas, f->stream); break;
-        case 5: launch_donor_frames<5>(fa, f->n_ctas, f->stream); break;
-        default: launch_donor_frames<6>(fa, f->n_ctas, f->stream); break;
+        case 1: launch_donor_frames<1>(fa, n_ctas, f->stream); break;
+        case 2: launch_donor_frames<2>(fa, n_ctas, f->stream); break;
+        case 3: launch_donor_frames<3>(fa, n_ctas, f->stream); break;
+        case 4: launch_donor_frames<4>(fa, n_ctas, f->stream); break;
+        case 5: launch_donor_frames<5>(fa, n_ctas, f->stream); break;
+        default: launch_donor_frames<6>(fa, n_ctas, f->stream); break;
     }
     sum_sizes_kernel<<<296, 256, 0, f->stream>>>(f->d_size, n_frames, f->d_totals);
     count_launch(2);
@@ -1305,8 +957,6 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     if (was_early) cudaEventElapsedTime(&f->ms_site, f->ev_side0, f->ev_tmpl);
     else cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
     cudaEventElapsedTime(&f->ms_frames, f->ev[1], f->ev[2]);
-    f->ms_pack = 0;
-    if (lane_split) cudaEventElapsedTime(&f->ms_pack, f->ev[1], f->ev_pack);
 #undef CUF
     return HB_OK;
 }
@@ -1338,8 +988,7 @@ void hb_frames_free(hb_frames *f) {
         if (c.cap < f->frames_cap) { std::swap(c.p, f->d_frames); std::swap(c.cap, f->frames_cap); }
     }
     dev_pool_free(f->d_tmpl); cudaFree(f->d_frames); dev_pool_free(f->d_tmpl_len); dev_pool_free(f->d_size);
-    dev_pool_free(f->d_slot_off); dev_pool_free(f->d_totals); dev_pool_free(f->d_bits);
-    if (f->ev_pack) cudaEventDestroy(f->ev_pack);
+    dev_pool_free(f->d_slot_off); dev_pool_free(f->d_totals);
     for (auto &x : f->ev) if (x) cudaEventDestroy(x);
     if (f->ev_sites) cudaEventDestroy(f->ev_sites);
     if (f->ev_tmpl) cudaEventDestroy(f->ev_tmpl);
@@ -1379,27 +1028,12 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     const uint32_t seg = (cr + 15) / 16;
     f->nw = (int)((seg + 31) / 32);
     FusedArgs &fa = f->fa;
-    fa.bww = ((2 * cr + 15) / 32 + 14) & ~3u;        // words of the B (and of the N) bit string: 1 pad + both planes + look-ahead
-    // most sequences in a segment: Z (>= 5) and C (>= 4) runs alternating without a gap, 2 per 9 positions
-    fa.caps = 2 * (seg / 9) + (seg % 9 >= 4 ? 1 : 0) + 1;
-    fa.dcap = (cr / 6 + cr / 5 + 2 + 7) & ~7u;           // a literal run + Z run take >= 6 positions (plane 0), + C run >= 5 (plane 1); + the last run
-    fa.outcap = (16 + n_gt + n_gt / 255 + 24 + FRAME_TAIL + 15) & ~15u;
-    fa.warp_smem = 8 * fa.bww + 64 * fa.caps + 6 * fa.dcap + fa.outcap;   // dcap is a multiple of 8: 16-byte alignment holds
-    if (const char *e = getenv("HB_DF_PAD")) fa.warp_smem += (uint32_t)atoi(e) & ~15u;       // experiment: occupancy sensitivity
-    if ((size_t)4 * fa.warp_smem > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the allele encoder"); }
-    {   // warps per CTA: every CTA costs 1 KB of reserved shared memory on top of its warps' buffers
-        uint32_t best = 4, best_warps = 0;
-        for (uint32_t w : {4u, 8u, 12u}) {
-            const size_t cta = (size_t)w * fa.warp_smem + 1024;
-            const uint32_t warps = (uint32_t)std::min<size_t>(40, std::min<size_t>(32, (227 * 1024) / cta) * w);   // 49 registers per thread: 40 warps
-            if (warps > best_warps) { best = w; best_warps = warps; }
-        }
-        if (const char *e = getenv("HB_DF_WPC")) { const int v = atoi(e); if (v >= 1 && v <= kWpcMax && (size_t)v * fa.warp_smem + 1024 <= 227 * 1024) best = (uint32_t)v; }
-        fa.wpc = best;
-    }
+    fa.strw = (((127 + 2 * cr) >> 5) + (uint32_t)f->nw + 3 + 3) & ~3u;   // both planes from bit alpha <= 127 on, + look-ahead words
+    fa.stg_bytes = (((127 + cr - 1) >> 7) + 1) * (kBitGroupWords * 4);   // 128-row groups a chunk's rows can touch
+    fa.outcap = (16 + n_gt + n_gt / 255 + 24 + 15) & ~15u;
+    fa.warp_smem = 16 + fa.stg_bytes + 8 * fa.strw + fa.outcap;
     f->chunk_cap = f->n_chunks + 4;          // a re-run on a slightly longer record set (streaming) still fits
     const uint64_t n_frames = f->chunk_cap * f->n_samples;
-    f->n_ctas = (f->n_chunks * f->n_samples + fa.wpc - 1) / fa.wpc;
     f->h_tmpl_len.resize(f->n_chunks);
     f->h_slot_off.resize(f->n_chunks + 1);
     cudaError_t e = cudaSuccess;
@@ -1416,15 +1050,7 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
         ck(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, hi));
     }
     ck(cudaEventCreateWithFlags(&f->ev_sites, cudaEventDisableTiming));
-    ck(cudaEventCreate(&f->ev_tmpl)); ck(cudaEventCreate(&f->ev_side0)); ck(cudaEventCreate(&f->ev_pack));
-    // the opt-in shared-memory ceiling is a per-function, process-wide attribute: always raise it to the device
-    // maximum, so that concurrent callers (the converter parses two files at once) cannot shrink each other's limit
-    int smem_max = 0;
-    ck(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, f->device));
-    smem_max -= 1024;                            // room for the kernels' few static __shared__ words
-    ck(cudaFuncSetAttribute(site_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    ck(attr_donor_frames<1>(smem_max)); ck(attr_donor_frames<2>(smem_max)); ck(attr_donor_frames<3>(smem_max));
-    ck(attr_donor_frames<4>(smem_max)); ck(attr_donor_frames<5>(smem_max)); ck(attr_donor_frames<6>(smem_max));
+    ck(cudaEventCreate(&f->ev_tmpl)); ck(cudaEventCreate(&f->ev_side0));
     if (e != cudaSuccess) { hb_frames_free(f); return api_fail(HB_ERR_MEM, std::string("CUDA: ") + cudaGetErrorString(e)); }
     int rc = frames_run(f, p);
     if (rc != HB_OK) { hb_frames_free(f); return rc; }
@@ -1449,7 +1075,6 @@ int hb_frames_rerun(hb_frames *f, hb_parse *p) {
             return api_fail(HB_ERR_ARG, "hb_frames_rerun: the parse no longer has the shape these frames were made for");
         f->n_records = p->h_st.n_records;
         f->n_chunks = nc;
-        f->n_ctas = (nc * f->n_samples + f->fa.wpc - 1) / f->fa.wpc;
         f->h_tmpl_len.resize(nc);
         f->h_slot_off.resize(nc + 1);
         f->early_site = false;                   // an early template pass (if any) was made for the old shape
@@ -1463,7 +1088,6 @@ int hb_frames_set_window(hb_frames *f, uint32_t s0, uint32_t ns) {
     if (ns == 0 || ns > f->win_cap) return api_fail(HB_ERR_ARG, "window larger than the one the frames were made for");
     f->s0 = s0;
     f->n_samples = ns;
-    f->n_ctas = (f->n_chunks * (uint64_t)ns + f->fa.wpc - 1) / f->fa.wpc;
     f->layout_valid = false;
     return HB_OK;
 }
@@ -1474,7 +1098,7 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
     info->n_records = f->n_records; info->n_chunks = f->n_chunks; info->chunk_records = f->cr;
     info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
     info->raw_bytes = 35ull * f->n_records * f->n_samples;
-    info->ms_site = f->ms_site; info->ms_frames = f->ms_frames; info->ms_pack = f->ms_pack;
+    info->ms_site = f->ms_site; info->ms_frames = f->ms_frames;
     info->padded_bytes = f->padded_bytes;
     info->d_frames = f->d_frames;
     uint64_t st = 0;
@@ -1539,21 +1163,18 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *b
 }  // extern "C"
 
 // =============================================================================================
-// Read side: Blosc2 cframe -> chunk -> LZ4 -> un-shuffle, one warp per HDF5 chunk.
-// Replaces, for VCFH5Reader.fetch_genotypes (src/utils/h5_reader.py:37-41), what h5py + the Blosc2
-// filter do when a `snp_data` dataset is read.  Accepts what stock c-blosc2 writes for this path
-// too (several blocks per chunk, LZ4/LZ4HC streams, raw streams, zero-run streams, memcpyed chunks);
-// anything else sets the frame's status to non-zero.
+// Read side: Blosc chunk -> LZ4 -> un-shuffle, one warp per HDF5 chunk.
+// Replaces, for VCFH5Reader.fetch_genotypes (src/utils/h5_reader.py:37-41), what h5py + the hdf5-blosc filter
+// (32001, blosc_decompress of c-blosc 1.x) do when a `snp_data` dataset is read.  Accepts what stock c-blosc writes
+// for this path too -- several blocks per chunk, LZ4 / LZ4HC streams, split and unsplit blocks, raw streams,
+// memcpyed chunks -- and the extended (32-byte) header of a c-blosc2 chunk with byte-shuffle as its only filter;
+// anything else, and every field that would make the kernel read or write outside the frame / its output, sets the
+// frame's status to non-zero (a stored file is untrusted input).
 // =============================================================================================
 namespace hb {
 
 __device__ __forceinline__ uint32_t ld_le32(const uint8_t *p) {
     return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
-}
-__device__ __forceinline__ uint64_t ld_be(const uint8_t *p, int nb) {
-    uint64_t v = 0;
-    for (int i = 0; i < nb; ++i) v = (v << 8) | p[i];
-    return v;
 }
 
 // LZ4 block decode by one warp: sequences are walked in lock-step, bytes are copied 32 per step.
@@ -1566,8 +1187,8 @@ __device__ bool warp_lz4_decode(const uint8_t *src, uint32_t n, uint8_t *dst, ui
         if (ip >= n) return false;
         const uint32_t tok = src[ip++];
         uint32_t ll = tok >> 4;
-        if (ll == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ll += b; } while (b == 255); }
-        if (ip + ll > n || op + ll > cap) return false;
+        if (ll == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ll += b; } while (b == 255 && ll <= cap); }
+        if (ll > n - ip || ll > cap - op) return false;
         for (uint32_t i = lane; i < ll; i += 32) dst[op + i] = src[ip + i];
         ip += ll; op += ll;
         if (ip == n) break;
@@ -1576,9 +1197,9 @@ __device__ bool warp_lz4_decode(const uint8_t *src, uint32_t n, uint8_t *dst, ui
         ip += 2;
         if (off == 0 || off > op) return false;
         uint32_t ml = tok & 15;
-        if (ml == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ml += b; } while (b == 255); }
+        if (ml == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ml += b; } while (b == 255 && ml <= cap); }
         ml += 4;
-        if (op + ml > cap) return false;
+        if (ml > cap - op) return false;
         __syncwarp();
         // periodic copy: dst[op+i] = dst[op-off + i % off] only reads bytes written before this match
         for (uint32_t i = lane; i < ml; i += 32) {
@@ -1592,78 +1213,84 @@ __device__ bool warp_lz4_decode(const uint8_t *src, uint32_t n, uint8_t *dst, ui
     return op == cap;
 }
 
+constexpr uint32_t kBloscMaxSplits = 16, kBloscMinBuffer = 128;      // c-blosc: MAX_SPLITS, MIN_BUFFERSIZE
+
+// frame i = frames[off[i], off[i] + len[i]) (len == nullptr: the frames are contiguous, off has n_frames + 1 entries)
+// -> out + i * chunk_nbytes; tmp: n_frames * chunk_nbytes bytes of scratch (the shuffled image)
 __global__ void __launch_bounds__(256)
-decode_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restrict__ offsets, uint64_t n_frames,
-                     uint32_t chunk_nbytes, uint8_t *__restrict__ tmp, uint8_t *__restrict__ out, int planar,
-                     int *__restrict__ status) {
+decode_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restrict__ off, const uint32_t *__restrict__ len,
+                     uint64_t n_frames, uint32_t chunk_nbytes, uint8_t *__restrict__ tmp, uint8_t *__restrict__ out,
+                     int planar, int *__restrict__ status) {
     const int lane = threadIdx.x & 31;
     const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= n_frames) return;
-    const uint8_t *f = frames + offsets[wid];
-    const uint64_t flen = offsets[wid + 1] - offsets[wid];
+    const uint8_t *c = frames + off[wid];
+    const uint64_t flen = len ? (uint64_t)len[wid] : off[wid + 1] - off[wid];
     uint8_t *t = tmp + wid * (uint64_t)chunk_nbytes;
     uint8_t *o = out + wid * (uint64_t)chunk_nbytes;
     int err = 0;
-    // ---- cframe header
-    if (flen < 87 + 35 || f[1] != 0xa8 || f[2] != 'b' || f[3] != '2' || f[4] != 'f' || f[10] != 0xd2) err = 1;
-    uint64_t hlen = 0, nbytes = 0, cbytes = 0;
+    uint32_t typesize = 1, cn = 0, bs = 0, ccb = 0, hdr = 16, flags = 0;
+    bool ext = false, shuffle = false;
+    if (flen < 16) err = 1;
     if (!err) {
-        hlen = ld_be(f + 11, 4); nbytes = ld_be(f + 30, 8); cbytes = ld_be(f + 39, 8);
-        if (hlen < 87 || hlen + cbytes > flen || nbytes != chunk_nbytes) err = 2;
+        flags = c[2]; typesize = c[3];
+        cn = ld_le32(c + 4); bs = ld_le32(c + 8); ccb = ld_le32(c + 12);
+        ext = (flags & 1) && (flags & 4);                    // c-blosc2: both shuffle bits = extended header
+        hdr = ext ? 32 : 16;
+        shuffle = !ext && (flags & 1);
+        if (c[0] < 2 || c[0] > 5 || (!ext && (c[0] != 2 || (flags & 0x08)))) err = 2;      // format version / reserved bit
+        else if (cn != chunk_nbytes || ccb > flen || ccb < hdr || bs == 0 || bs > cn || typesize == 0) err = 4;
     }
-    uint32_t typesize = 1;
-    if (!err) {
-        const uint8_t *c = f + hlen;                         // the (single) Blosc2 chunk
-        const uint32_t flags = c[2];
-        typesize = c[3];
-        const uint32_t cn = ld_le32(c + 4), bs = ld_le32(c + 8), ccb = ld_le32(c + 12);
-        const bool ext = (flags & 1) && (flags & 4);
-        const uint32_t hdr = ext ? 32 : 16;
-        bool shuffle = !ext && (flags & 1);
-        if (ext) for (int i = 0; i < 6; ++i) { if (c[16 + i] == 1) shuffle = true; else if (c[16 + i] != 0) err = 3; }
-        if (cn != chunk_nbytes || ccb > cbytes || bs == 0 || typesize == 0) err = 4;
-        if (!err && (flags & 2)) {                           // memcpyed
-            for (uint32_t i = lane; i < cn; i += 32) t[i] = c[hdr + i];
-            shuffle = false;
-        } else if (!err) {
-            if ((flags >> 5) != 1) err = 5;                  // LZ4 / LZ4HC codec format
-            if (ext && ((c[31] >> 4) & 7)) err = 6;          // special chunks
-            const bool dont_split = flags & 0x10;
-            const uint32_t nblocks = (cn + bs - 1) / bs;
-            for (uint32_t b = 0; b < nblocks && !err; ++b) {
-                const uint32_t bsize = (b == nblocks - 1 && cn % bs) ? cn % bs : bs;
-                const bool leftover = (b == nblocks - 1) && (cn % bs);
-                const uint32_t nstreams = (!dont_split && !leftover) ? typesize : 1;
-                const uint32_t ne = bsize / nstreams;
-                uint32_t ip = ld_le32(c + hdr + 4 * b);
-                for (uint32_t s = 0; s < nstreams && !err; ++s) {
-                    if (ip + 4 > ccb) { err = 7; break; }
-                    const int32_t cs = (int32_t)ld_le32(c + ip);
-                    ip += 4;
-                    uint8_t *d = t + (uint64_t)b * bs + (uint64_t)s * ne;
-                    if (cs == 0) { for (uint32_t i = lane; i < ne; i += 32) d[i] = 0; }
-                    else if (cs < 0 || ip + (uint32_t)cs > ccb) err = 8;
-                    else if ((uint32_t)cs == ne) { for (uint32_t i = lane; i < ne; i += 32) d[i] = c[ip + i]; ip += cs; }
-                    else { if (!warp_lz4_decode(c + ip, (uint32_t)cs, d, ne)) err = 9; ip += cs; }
-                    __syncwarp();
-                }
+    if (!err && ext) {
+        for (int i = 0; i < 6; ++i) { if (c[16 + i] == 1) shuffle = true; else if (c[16 + i] != 0) err = 3; }
+        if ((c[31] >> 4) & 7) err = 6;                       // special chunks (runs of zeros / NaNs / uninit)
+    }
+    if (!err && (flags & 2)) {                               // memcpyed
+        if ((uint64_t)hdr + cn > ccb) err = 7;
+        else for (uint32_t i = lane; i < cn; i += 32) t[i] = c[hdr + i];
+        shuffle = false;
+    } else if (!err) {
+        if ((flags >> 5) != 1 || (!ext && c[1] != 1)) err = 5;       // LZ4 / LZ4HC codec format, its format version
+        const bool dont_split = flags & 0x10;
+        const uint32_t nblocks = (cn + bs - 1) / bs;
+        const uint64_t data0 = (uint64_t)hdr + 4ull * nblocks;        // first byte after bstarts
+        if (!err && data0 > ccb) err = 7;
+        for (uint32_t b = 0; b < nblocks && !err; ++b) {
+            const bool leftover = (b == nblocks - 1) && (cn % bs);
+            const uint32_t bsize = leftover ? cn % bs : bs;
+            const bool split = !dont_split && !leftover &&
+                               (ext || (typesize <= kBloscMaxSplits && bs / typesize >= kBloscMinBuffer));
+            const uint32_t nstreams = split ? typesize : 1;
+            const uint32_t ne = bsize / nstreams;
+            uint64_t ip = ld_le32(c + hdr + 4 * b);
+            if (ip < data0 || ip > ccb) { err = 7; break; }
+            for (uint32_t s = 0; s < nstreams && !err; ++s) {
+                if (ip + 4 > ccb) { err = 7; break; }
+                const int32_t cs = (int32_t)ld_le32(c + ip);
+                ip += 4;
+                uint8_t *d = t + (uint64_t)b * bs + (uint64_t)s * ne;
+                if (cs == 0 && ext) { for (uint32_t i = lane; i < ne; i += 32) d[i] = 0; }        // c-blosc2: run of zeros
+                else if (cs <= 0 || ip + (uint32_t)cs > ccb) err = 8;
+                else if ((uint32_t)cs == ne) { for (uint32_t i = lane; i < ne; i += 32) d[i] = c[ip + i]; ip += cs; }
+                else { if (!warp_lz4_decode(c + ip, (uint32_t)cs, d, ne)) err = 9; ip += cs; }
+                __syncwarp();
             }
-            // Blosc shuffles per block; this path only un-shuffles the single-block layout planar -> AoS
-            if (!err && shuffle && nblocks != 1 && !planar) {
-                // several blocks: un-shuffle each block on its own
-                for (uint32_t b = 0; b < nblocks; ++b) {
-                    const uint32_t bsize = (b == nblocks - 1 && cn % bs) ? cn % bs : bs;
-                    const uint32_t ne = bsize / typesize;
-                    const uint8_t *sb = t + (uint64_t)b * bs;
-                    uint8_t *ob = o + (uint64_t)b * bs;
-                    for (uint32_t i = lane; i < ne * typesize; i += 32) ob[i] = __ldcg(sb + (i % typesize) * ne + i / typesize);
-                    for (uint32_t i = ne * typesize + lane; i < bsize; i += 32) ob[i] = __ldcg(sb + i);
-                }
-                if (lane == 0) status[wid] = 0;
-                return;
-            }
-            if (!err && !shuffle) planar = 1;                // nothing to undo
         }
+        if (!err && shuffle && nblocks != 1 && !planar) {
+            // Blosc shuffles per block: un-shuffle each block on its own
+            for (uint32_t b = 0; b < nblocks; ++b) {
+                const uint32_t bsize = (b == nblocks - 1 && cn % bs) ? cn % bs : bs;
+                const uint32_t ne = bsize / typesize;
+                const uint8_t *sb = t + (uint64_t)b * bs;
+                uint8_t *ob = o + (uint64_t)b * bs;
+                for (uint32_t i = lane; i < ne * typesize; i += 32) ob[i] = __ldcg(sb + (i % typesize) * ne + i / typesize);
+                for (uint32_t i = ne * typesize + lane; i < bsize; i += 32) ob[i] = __ldcg(sb + i);
+            }
+            if (lane == 0) status[wid] = 0;
+            return;
+        }
+        if (!err && planar && shuffle && nblocks != 1) err = 10;     // the planar view exists for single-block chunks only
+        if (!err && !shuffle) planar = 1;                            // nothing to undo
     }
     __syncwarp();
     if (!err) {
@@ -1683,6 +1310,8 @@ extern "C" int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, 
                                 uint64_t chunk_nbytes, uint8_t *out, int planar, int device) {
     if (!n_frames) return HB_OK;
     if (!frames || !offsets || !out || chunk_nbytes == 0 || chunk_nbytes > 0x7fffffffull) return api_fail(HB_ERR_ARG, "bad argument");
+    for (uint64_t i = 0; i < n_frames; ++i)
+        if (offsets[i + 1] < offsets[i]) return api_fail(HB_ERR_ARG, "frame offsets must not decrease");
     int nd = 0;
     if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return api_fail(HB_ERR_CUDA, "no CUDA device: libhaplo_b200 has no CPU fallback");
     if (cudaSetDevice(device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
@@ -1702,7 +1331,7 @@ extern "C" int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, 
     if (e == cudaSuccess) {
         ck(cudaMemcpy(d_frames, frames, total, cudaMemcpyHostToDevice));
         ck(cudaMemcpy(d_off, offsets, (n_frames + 1) * 8, cudaMemcpyHostToDevice));
-        decode_frames_kernel<<<(unsigned)((n_frames + 7) / 8), 256>>>(d_frames, d_off, n_frames, (uint32_t)chunk_nbytes,
+        decode_frames_kernel<<<(unsigned)((n_frames + 7) / 8), 256>>>(d_frames, d_off, nullptr, n_frames, (uint32_t)chunk_nbytes,
                                                                      d_tmp, d_out, planar, d_status);
         count_launch();
         ck(cudaGetLastError());
@@ -1712,6 +1341,6 @@ extern "C" int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, 
     cudaFree(d_frames); cudaFree(d_off); cudaFree(d_tmp); cudaFree(d_out); cudaFree(d_status);
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     for (uint64_t i = 0; i < n_frames; ++i)
-        if (status[i]) { rc = api_fail(HB_ERR_IO, "corrupt or unsupported Blosc2 frame (chunk " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")"); break; }
+        if (status[i]) { rc = api_fail(HB_ERR_IO, "corrupt or unsupported Blosc chunk (chunk " + std::to_string(i) + ", code " + std::to_string(status[i]) + ")"); break; }
     return rc;
 }

@@ -349,14 +349,12 @@ head_fragment_kernel(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t
 void launch_tokenize(bool with_tabs, const uint8_t *d_text, uint64_t nbytes, uint32_t n_cta, uint64_t tiles_per_cta,
                      uint64_t *d_nl_after, uint32_t stage_cap, uint64_t *d_cp, uint32_t ncp, CtaTok *d_cta,
                      const Launch &L) {
-    static bool attr_set = false;
     size_t smem = sizeof(TkSmem);
-    if (!attr_set) {
-        cudaFuncSetAttribute(tokenize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(tokenize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     if (!n_cta) return;
+    // > 48 KB of dynamic shared memory is opt-in per function AND per device: set on every launch (a microsecond), so a
+    // process that moves to another device is served too
+    if (with_tabs) cudaFuncSetAttribute(tokenize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(tokenize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (with_tabs)
         tokenize_kernel<true><<<n_cta, TK_THREADS, smem, L.stream>>>(d_text, nbytes, tiles_per_cta, d_nl_after,
                                                                      stage_cap, d_cp, ncp, d_cta);

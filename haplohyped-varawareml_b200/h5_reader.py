@@ -6,7 +6,7 @@ absent.  Repair R4: the dataset is read under the name the writer
 (the reference reader asks for `genotype`, which the writer never creates).
 
 Container access goes through `container.open_h5`: h5py + hdf5plugin when they are importable,
-otherwise this repo's minimal HDF5 reader; chunks are Blosc2 cframes either way.
+otherwise this repo's minimal HDF5 reader; chunks are bare Blosc chunks (filter 32001) either way.
 """
 from __future__ import annotations
 

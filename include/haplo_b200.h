@@ -166,10 +166,13 @@ int hb_bgzf_inflate(const uint8_t *bgzf, uint64_t nbytes, uint8_t *out, uint64_t
 int hb_bgzf_compress_host(const uint8_t *text, uint64_t nbytes, int level, uint8_t *out, uint64_t cap, uint64_t *len);
 
 /* ------------------------------------------------------------------------------------------
- * C. Storage: Blosc2 byte-shuffle (typesize 35) + LZ4 block encoder + Blosc2 chunk / cframe
- *    framing, one frame per (sample, HDF5 chunk) -- what h5py + hdf5plugin produce for
+ * C. Storage: Blosc byte-shuffle (typesize 35) + LZ4 block encoder + Blosc chunk framing, one
+ *    frame (= one stored HDF5 chunk) per (sample, HDF5 chunk) -- what h5py + hdf5plugin produce for
  *    create_dataset('snp_data', compression=32001, compression_opts=(2,2,0,0,5,1,2), chunks=True)
- *    (src/haplohyped/vcf_to_h5.py:119-135).  Frames stay in HBM until fetched.
+ *    (src/haplohyped/vcf_to_h5.py:119-135).  Filter 32001 is hdf5-blosc, i.e. c-blosc 1.x: a stored
+ *    chunk is the bare output of blosc_compress (16-byte header, bstarts, one LZ4 stream per block;
+ *    the reference's docs call it "Blosc2", whose own filter id is 32026 -- c-blosc2 reads this
+ *    format as well).  Frames stay in HBM until fetched.
  * ------------------------------------------------------------------------------------------ */
 typedef struct hb_frames hb_frames;
 
@@ -182,7 +185,6 @@ typedef struct hb_frames_info {
     uint64_t padded_bytes;          /* bytes of the device frame buffer in use: frames start on 16-byte boundaries */
     const uint8_t *d_frames;        /* device: frames in [sample][chunk] order, see hb_frames_layout */
     uint64_t site_lz4_bytes;        /* LZ4 bytes of the site planes, summed over chunks (shared by every sample) */
-    float ms_pack;                  /* part of ms_frames: allele planes -> bit arrays (lane-per-frame encoder); 0 otherwise */
 } hb_frames_info;
 
 /* chunk_records = 0 -> h5py's auto-chunk heuristic for a 1-D dataset of 35-byte items (at most 2730).
@@ -214,10 +216,14 @@ int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes,
                            uint64_t *total);
 void hb_frames_free(hb_frames *f);
 uint64_t hb_guess_chunk_records(uint64_t n_records);   /* h5py guess_chunk restated for 35-byte items */
+/* Site-plane matcher of the encoder, process-wide: 0 (default) = one hash candidate per position, 1 = 4-way hash
+ * buckets (about 5 % smaller frames, the template kernel takes twice as long).  Same decoded bytes either way. */
+void hb_set_site_matcher(int deep);
 /* Read side (VCFH5Reader.fetch_genotypes, src/utils/h5_reader.py:37-41): n_frames stored HDF5 chunks
- * (Blosc2 cframes; frame i = frames[offsets[i] .. offsets[i+1])) -> out[i * chunk_nbytes ...], decoded on the
- * GPU (cframe -> chunk -> LZ4 -> un-shuffle).  planar != 0 keeps the byte-shuffled plane layout.
- * Host pointers. */
+ * (bare Blosc chunks as filter 32001 stores them; frame i = frames[offsets[i] .. offsets[i+1])) ->
+ * out[i * chunk_nbytes ...], decoded on the GPU (chunk -> LZ4 -> un-shuffle).  Reads what this library writes
+ * and what stock c-blosc writes for the path (several blocks, LZ4 / LZ4HC, split streams, memcpyed chunks).
+ * planar != 0 keeps the byte-shuffled plane layout (single-block chunks).  Host pointers. */
 int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, uint64_t n_frames, uint64_t chunk_nbytes,
                      uint8_t *out, int planar, int device);
 

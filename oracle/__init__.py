@@ -8,7 +8,7 @@ PARITY STATUS: "parity unpinned" for the parser (the reference parser needs htsl
 see ``vcf_oracle.c``).  Pinned against the fixture-derived known answers in ``tests/golden``.
 
 Python side:
-  * ctypes binding of ``liboracle.so`` (parser / shuffle / LZ4 / Blosc2 restatement in C);
+  * ctypes binding of ``liboracle.so`` (parser / shuffle / LZ4 / Blosc chunk restatement in C);
   * numpy restatement of the dataset leg (``haplotype_dataset.py:11-16,54-110`` and
     ``common_utils.py:62-103``) with the repairs R1-R4 listed in SURVEY.md section 8(a).
 """
@@ -53,9 +53,11 @@ def lib():
         L.orc_free.argtypes = [C.POINTER(_Result)]
         L.orc_shuffle.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
         L.orc_unshuffle.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
-        for f in (L.orc_lz4_decode, L.orc_blosc2_chunk_decode, L.orc_cframe_decode):
+        for f in (L.orc_lz4_decode, L.orc_blosc_chunk_decode):
             f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
             f.restype = C.c_int64
+        L.orc_blosc1_chunk_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]
+        L.orc_blosc1_chunk_encode.restype = C.c_int64
         L.orc_pack_records.argtypes = [C.POINTER(_Result), C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
@@ -183,12 +185,21 @@ def lz4_decode(buf, cap: int) -> np.ndarray:
     return _decode(lib().orc_lz4_decode, buf, cap)
 
 
-def blosc2_chunk_decode(buf, cap: int) -> np.ndarray:
-    return _decode(lib().orc_blosc2_chunk_decode, buf, cap)
+def blosc_chunk_decode(buf, cap: int) -> np.ndarray:
+    """One stored HDF5 chunk of filter 32001 (a bare Blosc1 chunk) -> its `cap` uncompressed bytes."""
+    return _decode(lib().orc_blosc_chunk_decode, buf, cap)
 
 
-def cframe_decode(buf, cap: int) -> np.ndarray:
-    return _decode(lib().orc_cframe_decode, buf, cap)
+def blosc1_chunk_encode(data, typesize: int, blocksize: int = 0, split: bool = False) -> bytes:
+    """Scalar Blosc1 chunk writer (byte-shuffle + greedy LZ4): chunks for the decoders that the GPU encoder did not write."""
+    a = np.ascontiguousarray(np.frombuffer(bytes(data), np.uint8))
+    nblocks = 1 if not blocksize else (a.size + blocksize - 1) // blocksize + 1
+    cap = 16 + 4 * nblocks + a.size + 4 * (nblocks * (typesize if split else 1)) + 64
+    out = np.empty(cap, np.uint8)
+    n = lib().orc_blosc1_chunk_encode(a.ctypes.data, a.size, typesize, blocksize, int(split), out.ctypes.data, cap)
+    if n < 0:
+        raise ValueError("oracle: chunk encode failed")
+    return out[:n].tobytes()
 
 
 # --------------------------------------------------------------------------------------------

@@ -26,8 +26,8 @@
  *                           header-declared Integer INFO/END > pos overrides it)
  *   int8 narrowing          cpp/parse_vcf.cpp:51-52
  *   ploidy == 2 assert      cpp/parse_vcf.cpp:46  (reported as an error instead of SIGABRT)
- *   shuffle / blosc2 / lz4  c-blosc2 (via hdf5plugin filter 32001, vcf_to_h5.py:134-135):
- *                           published chunk + cframe formats, LZ4 block format
+ *   shuffle / blosc / lz4   c-blosc 1.x (hdf5plugin filter 32001 = hdf5-blosc, vcf_to_h5.py:134-135):
+ *                           published Blosc1 chunk format, LZ4 block format
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -367,8 +367,8 @@ int orc_load_vcf(const char *path, const char *sample, const char *region, orc_r
 }
 
 /* ------------------------------------------------------------------------------------------
- * Storage side: 35-byte records (vcf_to_h5.py:119-127), Blosc2 byte-shuffle, LZ4 block decode,
- * Blosc2 chunk + contiguous-frame (cframe) decode.
+ * Storage side: 35-byte records (vcf_to_h5.py:119-127), Blosc byte-shuffle, LZ4 block decode,
+ * Blosc chunk decode (+ a scalar chunk encoder, so that the decoders see chunks the GPU encoder did not write).
  * ------------------------------------------------------------------------------------------ */
 
 /* Pack records exactly as np.array([...], dtype=[S5,u4,u4,S10,S10,i1,i1]) would: NUL pad,
@@ -389,7 +389,7 @@ void orc_pack_records(const orc_result *r, const int8_t *gt0, const int8_t *gt1,
     }
 }
 
-/* c-blosc2 shuffle_generic: plane j = byte j of every element; trailing n % typesize bytes copied */
+/* c-blosc shuffle_generic: plane j = byte j of every element; trailing n % typesize bytes copied */
 void orc_shuffle(uint32_t typesize, uint64_t n, const uint8_t *src, uint8_t *dst) {
     uint64_t ne = n / typesize, rem = n % typesize;
     for (uint64_t j = 0; j < typesize; ++j)
@@ -430,23 +430,30 @@ int64_t orc_lz4_decode(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t ca
 }
 
 static uint32_t rd32le(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
-static uint64_t rdbe(const uint8_t *p, int n) { uint64_t v = 0; for (int i = 0; i < n; ++i) v = (v << 8) | p[i]; return v; }
 
 /*
- * Blosc2 chunk decoder (extended 32-byte header).  Handles: memcpyed chunks, LZ4/LZ4HC codec
- * format (1), split and non-split blocks, raw-stored streams (csize == stream size), zero-run
- * streams (csize == 0), byte-shuffle in filters[5] (or Blosc1-style flag bit0).
+ * Blosc chunk decoder: what blosc_decompress of c-blosc 1.x (the library behind HDF5 filter 32001, hdf5-blosc)
+ * does with one stored HDF5 chunk.  Published format (c-blosc README_HEADER.rst / blosc.c blosc_d):
+ *   [0] version (BLOSC_VERSION_FORMAT = 2)   [1] versionlz (LZ4 family: 1)
+ *   [2] flags: 0x01 byte-shuffle, 0x02 memcpyed, 0x04 bit-shuffle, 0x08 reserved, 0x10 don't split, codec format << 5
+ *   [3] typesize   [4,8) nbytes   [8,12) blocksize   [12,16) cbytes (all LE32), then bstarts[nblocks] (LE32, from the
+ *   start of the chunk), then per block: per stream an LE32 csize + csize bytes; csize == stream size means stored raw.
+ *   A block is split into `typesize` streams iff !dont_split && typesize <= 16 && blocksize / typesize >= 128 && it is
+ *   not the leftover block.  Shuffle is per block.
+ * Also accepts the extended 32-byte header of a c-blosc2 chunk (both shuffle bits set; filters in [16,22)) with
+ * byte-shuffle as the only filter: memcpyed chunks, zero-run streams (csize == 0).
  * Returns nbytes or -1.
  */
-int64_t orc_blosc2_chunk_decode(const uint8_t *c, uint64_t clen, uint8_t *dst, uint64_t cap) {
+int64_t orc_blosc_chunk_decode(const uint8_t *c, uint64_t clen, uint8_t *dst, uint64_t cap) {
     if (clen < 16) return -1;
-    uint8_t version = c[0], flags = c[2], typesize = c[3];
+    uint8_t version = c[0], versionlz = c[1], flags = c[2], typesize = c[3];
     uint32_t nbytes = rd32le(c + 4), blocksize = rd32le(c + 8), cbytes = rd32le(c + 12);
-    (void)version;
     if (cbytes > clen || nbytes > cap) return -1;
     int extended = (flags & 0x01) && (flags & 0x04);
     uint32_t hdr = extended ? 32 : 16;
-    if (clen < hdr) return -1;
+    if (cbytes < hdr) return -1;
+    if (!extended && (version != 2 || (flags & 0x08))) return -1;   /* blosc.c: "version from future", reserved bit */
+    if (extended && (version < 2 || version > 5)) return -1;
     int doshuffle = extended ? 0 : (flags & 0x01);
     if (extended) for (int i = 0; i < 6; ++i) {
         if (c[16 + i] == 1) doshuffle = 1;
@@ -454,33 +461,36 @@ int64_t orc_blosc2_chunk_decode(const uint8_t *c, uint64_t clen, uint8_t *dst, u
     }
     if (nbytes == 0) return 0;
     if (flags & 0x02) {                           /* memcpyed */
-        if (hdr + nbytes > clen) return -1;
+        if ((uint64_t)hdr + nbytes > cbytes) return -1;
         memcpy(dst, c + hdr, nbytes);
         return nbytes;
     }
     if (extended && (c[31] >> 4) & 7) return -1;  /* special chunks not emitted on this path */
     uint32_t codec = flags >> 5;
     if (codec != 1) return -1;                    /* LZ4 / LZ4HC share format id 1 */
-    if (blocksize == 0 || typesize == 0) return -1;
+    if (!extended && versionlz != 1) return -1;   /* BLOSC_LZ4_VERSION_FORMAT */
+    if (blocksize == 0 || blocksize > nbytes || typesize == 0) return -1;
     int dont_split = (flags & 0x10) != 0;
     uint32_t nblocks = (nbytes + blocksize - 1) / blocksize;
-    if (hdr + 4ull * nblocks > clen) return -1;
-    uint8_t *tmp = malloc(blocksize ? blocksize : 1);
+    uint64_t data0 = hdr + 4ull * nblocks;
+    if (data0 > cbytes) return -1;
+    uint8_t *tmp = malloc(blocksize);
     for (uint32_t b = 0; b < nblocks; ++b) {
-        uint32_t bsize = (b == nblocks - 1 && nbytes % blocksize) ? nbytes % blocksize : blocksize;
         int leftover = (b == nblocks - 1) && (nbytes % blocksize);
+        uint32_t bsize = leftover ? nbytes % blocksize : blocksize;
         uint32_t bstart = rd32le(c + hdr + 4 * b);
-        uint32_t nstreams = (!dont_split && !leftover) ? typesize : 1;
+        int split = !dont_split && !leftover && (extended || (typesize <= 16 && blocksize / typesize >= 128));
+        uint32_t nstreams = split ? typesize : 1;
         uint32_t neblock = bsize / nstreams;
         uint64_t ip = bstart; uint8_t *o = doshuffle ? tmp : dst + (uint64_t)b * blocksize;
+        if (ip < data0 || ip > cbytes) { free(tmp); return -1; }
         for (uint32_t s = 0; s < nstreams; ++s) {
-            if (ip + 4 > clen) { free(tmp); return -1; }
+            if (ip + 4 > cbytes) { free(tmp); return -1; }
             int32_t cs = (int32_t)rd32le(c + ip); ip += 4;
-            if (cs == 0) memset(o + (uint64_t)s * neblock, 0, neblock);
-            else if (cs < 0) { free(tmp); return -1; }
-            else if ((uint32_t)cs == neblock) { if (ip + cs > clen) { free(tmp); return -1; } memcpy(o + (uint64_t)s * neblock, c + ip, neblock); ip += cs; }
+            if (cs == 0 && extended) memset(o + (uint64_t)s * neblock, 0, neblock);
+            else if (cs <= 0 || ip + (uint64_t)cs > cbytes) { free(tmp); return -1; }
+            else if ((uint32_t)cs == neblock) { memcpy(o + (uint64_t)s * neblock, c + ip, neblock); ip += cs; }
             else {
-                if (ip + cs > clen) { free(tmp); return -1; }
                 int64_t got = orc_lz4_decode(c + ip, (uint64_t)cs, o + (uint64_t)s * neblock, neblock);
                 if (got != (int64_t)neblock) { free(tmp); return -1; }
                 ip += cs;
@@ -493,46 +503,72 @@ int64_t orc_blosc2_chunk_decode(const uint8_t *c, uint64_t clen, uint8_t *dst, u
 }
 
 /*
- * Blosc2 contiguous frame ("cframe") decode, as emitted per HDF5 chunk by hdf5-blosc2's filter
- * (one Blosc2 chunk per frame on this path, but any nchunks of equal chunksize is accepted).
- * Validates every msgpack marker the stock reader checks.  Returns nbytes or -1.
+ * Blosc1 chunk ENCODER, scalar: what blosc_compress(clevel, doshuffle = 1, typesize, ...) of c-blosc 1.x emits with
+ * the LZ4 codec when the whole buffer is one block (blocksize = nbytes, no split: typesize > 16 or forced), using a
+ * plain greedy single-entry-hash LZ4 matcher.  Its LZ4 stream is NOT byte-identical to stock LZ4/LZ4HC (those are
+ * encoder choices, not format); it exists so that the CPU tests have chunks written by something other than the GPU
+ * encoder to feed the decoders with, incl. several blocks per chunk and split streams.
+ * blocksize: 0 = one block.  split != 0: split blocks into typesize streams where c-blosc's rule allows it.
+ * Returns cbytes or -1 (dst too small).
  */
-int64_t orc_cframe_decode(const uint8_t *f, uint64_t flen, uint8_t *dst, uint64_t cap) {
-    if (flen < 87 + 35) return -1;
-    if ((f[0] & 0xf0) != 0x90 || f[1] != 0xa8 || memcmp(f + 2, "b2frame\0", 8) != 0) return -1;
-    if (f[10] != 0xd2 || f[15] != 0xcf || f[24] != 0xa4 || f[29] != 0xd3 || f[38] != 0xd3) return -1;
-    if (f[47] != 0xd2 || f[52] != 0xd2 || f[57] != 0xd2 || f[62] != 0xd1 || f[65] != 0xd1) return -1;
-    if ((f[68] != 0xc2 && f[68] != 0xc3) || f[69] != 0xd8) return -1;
-    uint64_t header_len = rdbe(f + 11, 4), frame_len = rdbe(f + 16, 8);
-    uint64_t nbytes = rdbe(f + 30, 8), cbytes = rdbe(f + 39, 8);
-    uint64_t chunksize = rdbe(f + 58, 4);
-    if (frame_len != flen || header_len < 87 || header_len > flen) return -1;
-    if ((f[25] & 0x0f) != 2 || !(f[25] & 0x10) || f[26] != 0) return -1;   /* frame format 2, 64-bit offsets, contiguous */
-    if (f[87] != 0x93 || f[88] != 0xcd || f[91] != 0xde) return -1;
-    if (nbytes > cap) return -1;
-    /* trailer */
-    if (f[flen - 23] != 0xce) return -1;
-    uint64_t trailer_len = rdbe(f + flen - 22, 4);
-    if (trailer_len < 35 || header_len + cbytes + trailer_len > flen) return -1;
-    if ((f[flen - trailer_len] & 0xf0) != 0x90 || f[flen - 18] != 0xd8) return -1;
-    if (nbytes == 0) return 0;
-    if (chunksize == 0) return -1;
-    uint64_t nchunks = (nbytes + chunksize - 1) / chunksize;
-    /* offsets chunk sits right after the data chunks */
-    const uint8_t *oc = f + header_len + cbytes;
-    uint64_t oc_len = flen - trailer_len - header_len - cbytes;
-    int64_t *offs = malloc(nchunks * 8);
-    if (orc_blosc2_chunk_decode(oc, oc_len, (uint8_t *)offs, nchunks * 8) != (int64_t)(nchunks * 8)) { free(offs); return -1; }
-    uint64_t done = 0;
-    for (uint64_t k = 0; k < nchunks; ++k) {
-        if (offs[k] < 0 || (uint64_t)offs[k] + 16 > cbytes) { free(offs); return -1; }
-        const uint8_t *ch = f + header_len + offs[k];
-        uint32_t ccb = rd32le(ch + 12);
-        if ((uint64_t)offs[k] + ccb > cbytes) { free(offs); return -1; }
-        int64_t got = orc_blosc2_chunk_decode(ch, ccb, dst + done, cap - done);
-        if (got < 0) { free(offs); return -1; }
-        done += (uint64_t)got;
+static int64_t lz4_greedy(const uint8_t *src, uint32_t n, uint8_t *dst, uint64_t cap) {
+    uint32_t table[4096]; memset(table, 0xff, sizeof table);
+    uint64_t op = 0; uint32_t anchor = 0, ip = 0;
+#define PUT(b) do { if (op >= cap) return -1; dst[op++] = (uint8_t)(b); } while (0)
+    if (n >= 13) {
+        const uint32_t mflimit = n - 12;                       /* last match must start >= 12 bytes before the end */
+        while (ip < mflimit) {
+            uint32_t v; memcpy(&v, src + ip, 4);
+            uint32_t h = (v * 2654435761u) >> 20;
+            uint32_t cand = table[h]; table[h] = ip;
+            uint32_t cv = 0; if (cand != 0xffffffffu) memcpy(&cv, src + cand, 4);
+            if (cand == 0xffffffffu || ip - cand > 65535 || cv != v) { ++ip; continue; }
+            uint32_t ml = 4; const uint32_t lim = n - 5;       /* last 5 bytes are literals */
+            while (ip + ml < lim && src[ip + ml] == src[cand + ml]) ++ml;
+            uint32_t lit = ip - anchor, m = ml - 4;
+            PUT(((lit < 15 ? lit : 15) << 4) | (m < 15 ? m : 15));
+            if (lit >= 15) { uint32_t r = lit - 15; while (r >= 255) { PUT(255); r -= 255; } PUT(r); }
+            for (uint32_t k = 0; k < lit; ++k) PUT(src[anchor + k]);
+            PUT((ip - cand) & 255); PUT((ip - cand) >> 8);
+            if (m >= 15) { uint32_t r = m - 15; while (r >= 255) { PUT(255); r -= 255; } PUT(r); }
+            ip += ml; anchor = ip;
+        }
     }
-    free(offs);
-    return done == nbytes ? (int64_t)nbytes : -1;
+    uint32_t lit = n - anchor;
+    PUT((lit < 15 ? lit : 15) << 4);
+    if (lit >= 15) { uint32_t r = lit - 15; while (r >= 255) { PUT(255); r -= 255; } PUT(r); }
+    for (uint32_t k = 0; k < lit; ++k) PUT(src[anchor + k]);
+#undef PUT
+    return (int64_t)op;
+}
+
+int64_t orc_blosc1_chunk_encode(const uint8_t *src, uint32_t nbytes, uint32_t typesize, uint32_t blocksize, int split,
+                                uint8_t *dst, uint64_t cap) {
+    if (typesize == 0 || typesize > 255 || nbytes == 0) return -1;
+    if (blocksize == 0 || blocksize > nbytes) blocksize = nbytes;
+    if (blocksize > typesize) blocksize = blocksize / typesize * typesize;
+    uint32_t nblocks = (nbytes + blocksize - 1) / blocksize;
+    uint64_t op = 16 + 4ull * nblocks;
+    if (cap < op) return -1;
+    int can_split = split && typesize <= 16 && blocksize / typesize >= 128;
+    dst[0] = 2; dst[1] = 1; dst[2] = (uint8_t)(0x01 | (can_split ? 0 : 0x10) | (1 << 5)); dst[3] = (uint8_t)typesize;
+    uint8_t *tmp = malloc(blocksize);
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        int leftover = (b == nblocks - 1) && (nbytes % blocksize);
+        uint32_t bsize = leftover ? nbytes % blocksize : blocksize;
+        orc_shuffle(typesize, bsize, src + (uint64_t)b * blocksize, tmp);
+        uint32_t bstart = (uint32_t)op; memcpy(dst + 16 + 4 * b, &bstart, 4);
+        uint32_t nstreams = (can_split && !leftover) ? typesize : 1, ne = bsize / nstreams;
+        for (uint32_t s = 0; s < nstreams; ++s) {
+            if (op + 4 + ne > cap) { free(tmp); return -1; }
+            int64_t cs = lz4_greedy(tmp + (uint64_t)s * ne, ne, dst + op + 4, ne - 1);
+            if (cs <= 0) { cs = ne; memcpy(dst + op + 4, tmp + (uint64_t)s * ne, ne); }     /* incompressible: stored raw */
+            int32_t c32 = (int32_t)cs; memcpy(dst + op, &c32, 4);
+            op += 4 + (uint64_t)cs;
+        }
+    }
+    free(tmp);
+    uint32_t cb = (uint32_t)op;
+    memcpy(dst + 4, &nbytes, 4); memcpy(dst + 8, &blocksize, 4); memcpy(dst + 12, &cb, 4);
+    return (int64_t)op;
 }

@@ -45,7 +45,7 @@ def test_group_tree_roundtrip(tmp_path, minih5, n_donors, n_chroms):
                 chunks = [rng.integers(0, 256, int(rng.integers(1, 400)), dtype=np.uint8).tobytes() for _ in range(k)]
                 path = f"donor_{d:04d}-x/chr_{c}/snp_data"
                 w.create_dataset_chunked(path, REC, n, chunk, chunks, filter_id=32001,
-                                         cd_values=(2, 2, 35, chunk * 35, 5, 1, 2), filter_name="blosc2")
+                                         cd_values=(2, 2, 35, chunk * 35, 5, 1, 2), filter_name="blosc")
                 payloads[path] = (n, chunks)
     r = minih5.H5Reader(p)
     assert r.keys("/") == sorted({q.split("/")[0] for q in payloads})
@@ -106,7 +106,7 @@ def test_bulk_blob_writer_equals_per_chunk_writer(tmp_path, minih5, n_chunks):
     chunks = [rng.integers(0, 256, int(rng.integers(1, 50)), dtype=np.uint8).tobytes() for _ in range(n_chunks)]
     cd = (2, 2, 9, 90, 5, 1, 2)
     with minih5.H5Writer(str(tmp_path / "a.h5")) as w:
-        w.create_dataset_chunked("g/x/snp", dt, n_chunks * 10, 10, chunks, filter_id=32001, cd_values=cd, filter_name="blosc2")
+        w.create_dataset_chunked("g/x/snp", dt, n_chunks * 10, 10, chunks, filter_id=32001, cd_values=cd, filter_name="blosc")
     offs, blob = [], bytearray()
     for c in chunks:
         blob += b"\xee" * int(rng.integers(0, 16))
@@ -116,7 +116,7 @@ def test_bulk_blob_writer_equals_per_chunk_writer(tmp_path, minih5, n_chunks):
         base = w.write_blob(bytes(blob))
         assert base % 16 == 0
         w.create_dataset_chunked_at("g/x/snp", dt, n_chunks * 10, 10, base + np.array(offs, np.uint64),
-                                    np.array([len(c) for c in chunks], np.uint32), filter_id=32001, cd_values=cd, filter_name="blosc2")
+                                    np.array([len(c) for c in chunks], np.uint32), filter_id=32001, cd_values=cd, filter_name="blosc")
     ra, rb = minih5.H5Reader(str(tmp_path / "a.h5")), minih5.H5Reader(str(tmp_path / "b.h5"))
     ia, ib = ra.dataset_info("g/x/snp"), rb.dataset_info("g/x/snp")
     assert [c for _, c in ra.chunks(ia)] == chunks and rb.chunks(ib) == ra.chunks(ia)

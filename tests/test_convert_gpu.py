@@ -44,12 +44,33 @@ def test_decode_frames_matches_oracle(mods):
         planar = capi.decode_frames(frames, cr * 35, planar=True)
         for k in range(len(frames)):
             assert planar[k].tobytes() == oracle.shuffle(raw[k * cr * 35:(k + 1) * cr * 35], 35).tobytes()
-            assert oracle.cframe_decode(frames[k], cr * 35).tobytes() == got[k].tobytes()
+            assert oracle.blosc_chunk_decode(frames[k], cr * 35).tobytes() == got[k].tobytes()
     # corrupt frames are rejected, not decoded into garbage
-    bad = bytearray(fr.sample(0)[0])
-    bad[3] ^= 0xff
-    with pytest.raises(capi.HaploError):
-        capi.decode_frames([bytes(bad)], cr * 35)
+    good = fr.sample(0)[0]
+    import struct
+    def mutated(at, value):
+        b = bytearray(good); b[at:at + len(value)] = value; return bytes(b)
+    hostile = [
+        mutated(0, b"\x09"),                                  # format version from the future
+        mutated(2, bytes([good[2] | 0x08])),                  # reserved flag bit
+        mutated(2, bytes([(good[2] & 0x1f) | (2 << 5)])),     # another codec
+        mutated(4, struct.pack("<I", cr * 35 + 35)),          # nbytes != the dataset's chunk size
+        mutated(8, struct.pack("<I", 0)),                     # blocksize 0
+        mutated(8, struct.pack("<I", 1)),                     # blocksize 1: 37 K bstarts would lie outside the chunk
+        mutated(12, struct.pack("<I", len(good) + 1000)),     # cbytes beyond the stored bytes
+        mutated(16, struct.pack("<I", 0xfffffff0)),           # bstarts[0] far outside
+        mutated(16, struct.pack("<I", 4)),                    # bstarts[0] inside the header
+        mutated(20, struct.pack("<i", -5)),                   # negative stream size
+        mutated(20, struct.pack("<I", len(good))),            # stream runs past the end of the chunk
+        good[:len(good) // 2],                                # truncated
+        mutated(24, b"\xff" * 8),                             # LZ4: literal run longer than the block
+        mutated(len(good) - 40, b"\x00" * 8),                 # LZ4: damaged tail (offset 0 / wrong length)
+        good[:12],                                            # shorter than a header
+    ]
+    for k, bad in enumerate(hostile):
+        with pytest.raises(capi.HaploError):
+            capi.decode_frames([bad], cr * 35)
+    assert capi.decode_frames([good], cr * 35).tobytes() == oracle.blosc_chunk_decode(good, cr * 35).tobytes()   # the device is still healthy
     assert capi.decode_frames([], cr * 35).shape == (0, cr * 35)
 
 

@@ -320,7 +320,7 @@ def test_biobank_width_200k_samples(capi):
         rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
         raw = rec.tobytes() + b"\0" * (cr * 35 - rec.nbytes)
         (f,) = fr.sample(s)
-        assert oracle.cframe_decode(f, cr * 35).tobytes() == raw
+        assert oracle.blosc_chunk_decode(f, cr * 35).tobytes() == raw
 
 
 def test_stream_slots_are_reused_and_safe_across_options_and_threads(capi):

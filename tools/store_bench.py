@@ -24,6 +24,6 @@ for r in range(reps):
     ms = i.ms_site + i.ms_frames
     print(json.dumps({"records": i.n_records, "chunks": i.n_chunks, "cr": i.chunk_records, "C_out": i.total_bytes,
                       "padded": i.padded_bytes, "ratio": i.raw_bytes / max(1, i.total_bytes),
-                      "ms_site": i.ms_site, "ms_frames": i.ms_frames, "ms_pack": i.ms_pack,
+                      "ms_site": i.ms_site, "ms_frames": i.ms_frames, 
                       "ms_total": ms, "alg_GBs": alg / ms / 1e6, "frames_alg_GBs": (2.0 * i.n_records * S + i.total_bytes) / max(1e-9, i.ms_frames) / 1e6,
                       "bytes_per_frame": i.total_bytes / max(1, i.n_chunks * S), "mix": mix, "site_lz4_per_chunk": i.site_lz4_bytes / max(1, i.n_chunks)}))

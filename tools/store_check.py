@@ -1,5 +1,5 @@
 """Round-trip check of kernel 4 at a bench-like shape: every frame of a few samples is decoded by the
-oracle (cframe -> chunk -> LZ4 -> unshuffle) and compared with the oracle's records.
+oracle (chunk -> LZ4 -> unshuffle) and compared with the oracle's records.
 python tools/store_check.py [variants] [samples] [mix]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,7 +28,7 @@ for cr0 in crs:
         for k, f in enumerate(frames):
             tot += len(f)
             try:
-                got = oracle.cframe_decode(f, cr * 35).tobytes()
+                got = oracle.blosc_chunk_decode(f, cr * 35).tobytes()
             except ValueError:
                 got = None
             if got != raw[k * cr * 35:(k + 1) * cr * 35]:
