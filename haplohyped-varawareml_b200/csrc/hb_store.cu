@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     for (; s < s_end; s += kWpc) {
         int dlen = 0;
         // state of the parse that the emission needs
-        uint32_t S[NW], E[NW], K[NW];
+        uint32_t Rp[NW], K[NW];            // match cover without the last position of each run; C-run cover (match type)
         int m = 0, carry = 0, out_base = 0, total = 0, final_lit = 0;
         bool any_n = false;
         const int p = lane >> 4, q = lane & 15;
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             const int mlim = min(seglen, n - 11 - (p * cr + a0));         // the last 11 bytes of the block stay literals
             const int bi = alpha + p * cr + a0, j0 = bi >> 5, shb = bi & 31;
             const int bi0 = alpha + a0, j00 = bi0 >> 5, shb0 = bi0 & 31;     // the same rows in plane 0
-            uint32_t Z[NW], C[NW], ZR[NW];
+            uint32_t Z[NW], C[NW], ZR[NW], S[NW], E[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
                 const uint32_t bw = __funnelshift_r(strB[j0 + k], strB[j0 + k + 1], shb);
@@ -584,6 +584,10 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 }
             }
             const int trail = seglen - prev_end;
+            // runs of Rp are separated by at least one zero even where a Z run touches a C run, so "lowest run" arithmetic
+            // enumerates the matches in step 5
+#pragma unroll
+            for (int k = 0; k < NW; ++k) Rp[k] = (ZR[k] | K[k]) & ~E[k];
 
             // ---- 3. carry trailing literals forward; scan: output offsets
             int val = trail, flag = m > 0;
@@ -627,86 +631,120 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 seq[i] = x < valid ? (uint8_t)(i < cr ? A.gt0 : A.gt1)[grow + x] : (uint8_t)0;
             }
         } else {
-            // ---- 5. every lane walks its matches once: token, literals (rebuilt from the bits), offset
+            // ---- 5. emission.  Every lane walks its own byte stream -- per sequence: token [+ length bytes], literals
+            //         (rebuilt from the bits), offset [+ length byte] -- in passes of at most 8 bytes, all lanes in step: a
+            //         flat state machine, so a lane with a long literal run does not hold up the others' next sequence.
+            //         The bytes of a pass are gathered in a 64-bit value and appended to the lane's region of the tail
+            //         buffer through a word accumulator; a lane's first and last word may be shared with its neighbours:
+            //         those two are OR-ed into the zeroed buffer at the end, everything between is stored plainly.
             uint32_t waddr = smem_u32(seq) + (uint32_t)out_base;
-            uint32_t fill = waddr & 3u, lo = 0;
+            uint32_t fill = waddr & 3u, lo = 0, fw = 0;
             waddr &= ~3u;
-            bool first = true;               // the lane's first word may be shared with the lanes before it
-            auto put = [&](uint32_t v, uint32_t nb) {       // append the low nb (<= 4) bytes of v; the bytes above must be zero
-                lo |= v << (8u * fill);
-                const uint32_t hi = __funnelshift_l(v, 0u, 8u * fill);
-                fill += nb;
-                if (fill >= 4u) {
-                    if (first) sts_or32(waddr, lo); else sts32(waddr, lo);
-                    first = false;
-                    waddr += 4; lo = hi; fill -= 4u;
-                }
+            const uint32_t faddr = waddr;
+            bool first = true;               // the first word is still being filled: nothing stored yet
+            auto put = [&](uint64_t v, uint32_t nb) {       // append the low nb (<= 8) bytes of v; the bytes above must be zero
+                const uint32_t sh = 8u * fill, vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+                const uint32_t c0 = lo | (vlo << sh);
+                const uint32_t c1 = __funnelshift_l(vlo, vhi, sh), c2 = __funnelshift_l(vhi, 0u, sh);
+                const uint32_t tot = fill + nb, nw = tot >> 2;
+                if (nw >= 1u && !first) sts32(waddr, c0);
+                if (nw >= 2u) sts32(waddr + 4u, c1);
+                fw = (nw >= 1u && first) ? c0 : fw;
+                first = first && nw == 0u;
+                lo = nw == 0u ? c0 : (nw == 1u ? c1 : c2);
+                waddr += 4u * nw;
+                fill = tot & 3u;
             };
-            // up to 4 literal bytes of block positions x .. x + nb - 1
-            auto lit4 = [&](int x, int nb) -> uint32_t {
+            // up to 8 literal bytes of block positions x .. x + nb - 1
+            auto lit8 = [&](int x, int nb) -> uint64_t {
                 const int G = alpha + x;
-                uint32_t v = spread4(__funnelshift_r(strB[G >> 5], strB[(G >> 5) + 1], G)) & low_mask(8 * nb);
+                const uint32_t bits = __funnelshift_r(strB[G >> 5], strB[(G >> 5) + 1], G) & ((1u << nb) - 1u);
+                uint64_t v = (uint64_t)spread4(bits) | ((uint64_t)spread4(bits >> 4) << 32);
                 if (any_n) {
-                    uint32_t nb4 = __funnelshift_r(strN[G >> 5], strN[(G >> 5) + 1], G) & low_mask(nb);
-                    while (nb4) {                            // an allele other than 0 / 1: the byte itself
-                        const int i = ctz32(nb4);
-                        nb4 &= nb4 - 1;
+                    uint32_t nb8 = __funnelshift_r(strN[G >> 5], strN[(G >> 5) + 1], G) & ((1u << nb) - 1u);
+                    while (nb8) {                            // an allele other than 0 / 1: the byte itself
+                        const int i = ctz32(nb8);
+                        nb8 &= nb8 - 1;
                         const int xx = x + i;
-                        const uint32_t byte = (uint8_t)(xx < cr ? A.gt0 : A.gt1)[grow + (xx < cr ? xx : xx - cr)];
-                        v = (v & ~(0xFFu << (8 * i))) | (byte << (8 * i));
+                        const uint64_t byte = (uint8_t)(xx < cr ? A.gt0 : A.gt1)[grow + (xx < cr ? xx : xx - cr)];
+                        v = (v & ~(0xFFull << (8 * i))) | (byte << (8 * i));
                     }
                 }
                 return v;
             };
-            auto lit_run = [&](int x, int cnt) {            // literals x .. x + cnt - 1, four per step
-                for (int k = 0; k < cnt; k += 4) { const int nb = min(4, cnt - k); put(lit4(x + k, nb), (uint32_t)nb); }
-            };
             const int seg_abs = p * cr + a0;
-            int pos = seg_abs - carry, base = 0;
-            for (int jx = 0; jx < m; ++jx) {
-                while (S[0] == 0) {
+            int pos = seg_abs - carry;                       // next block position that has not been emitted
+            int left = m + (lane == 31 ? 1 : 0);             // sequences still to start; lane 31 closes the block with literals only
+            int litrem = 0, cur_ml = 0;
+            uint32_t cur_off = 0;
+            bool pend = false;                               // the current sequence's offset has not been emitted yet
+            while (left > 0 || litrem > 0 || pend) {
+                uint64_t v = 0;
+                uint32_t nb = 0;
+                if (litrem == 0 && !pend) {                  // the next sequence starts
+                    int lit;
+                    uint32_t tok;
+                    if (left > (lane == 31 ? 1 : 0)) {
+                        // lowest run of Rp: low = its first bit, t = Rp + low carries through it
+                        uint32_t low[NW], run[NW];
+                        bool found = false;
+                        int ts = 0;
+                        bool is_k = false;
 #pragma unroll
-                    for (int k = 0; k + 1 < NW; ++k) { S[k] = S[k + 1]; E[k] = E[k + 1]; K[k] = K[k + 1]; }
-                    S[NW - 1] = 0; E[NW - 1] = 0; K[NW - 1] = 0;
-                    base += 32;
-                }
-                const int ts = ctz32(S[0]);
-                S[0] &= S[0] - 1;
-                const int off = ((K[0] >> ts) & 1u) ? cr : 2 * cr;
-                int te = 0;
-                {
-                    bool f = false;
+                        for (int k = 0; k < NW; ++k) {
+                            const uint32_t l = found ? 0u : (Rp[k] & (0u - Rp[k]));
+                            if (!found && l) { ts = 32 * k + ctz32(l); is_k = (K[k] & l) != 0u; }
+                            found = found || l != 0u;
+                            low[k] = l;
+                        }
+                        uint64_t cy = 0;
+                        int ml = 1;
 #pragma unroll
-                    for (int k = 0; k < NW; ++k)
-                        if (!f && E[k]) { te = 32 * k + ctz32(E[k]); E[k] &= E[k] - 1; f = true; }
+                        for (int k = 0; k < NW; ++k) {
+                            cy += (uint64_t)Rp[k] + low[k];
+                            const uint32_t t = (uint32_t)cy;
+                            cy >>= 32;
+                            run[k] = Rp[k] & ~t;
+                            Rp[k] &= t;
+                            ml += __popc(run[k]);
+                        }
+                        const int st = seg_abs + ts;
+                        lit = st - pos;
+                        cur_ml = ml;
+                        cur_off = is_k ? (uint32_t)cr : 2u * (uint32_t)cr;
+                        pend = true;
+                        tok = (uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15));
+                    } else {                                 // the last sequence of the block: literals only (>= 11 of them)
+                        lit = final_lit;
+                        pos = n - final_lit;                 // (an empty last segment starts past the end of the block)
+                        tok = (uint32_t)(min(lit, 15) << 4);
+                    }
+                    --left;
+                    v = tok; nb = 1;
+                    if (lit >= 15) {
+                        int rem = lit - 15;
+                        while (rem >= 255) { put(v, nb); v = 255u; nb = 1; rem -= 255; }
+                        v |= (uint64_t)(uint32_t)rem << (8u * nb);
+                        ++nb;
+                    }
+                    litrem = lit;
                 }
-                const int st = seg_abs + base + ts, ml = te - ts + 1;
-                const int lit = st - pos;
-                const uint32_t tok = (uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15));
-                if (lit < 15) {
-                    const int n1 = min(lit, 3);
-                    put(tok | (lit4(pos, n1) << 8), (uint32_t)(1 + n1));
-                    if (lit > 3) lit_run(pos + 3, lit - 3);
-                } else {
-                    put(tok, 1);
-                    int rem = lit - 15;
-                    while (rem >= 255) { put(255u, 1); rem -= 255; }
-                    put((uint32_t)rem, 1);
-                    lit_run(pos, lit);
+                const int take = min(litrem, 8 - (int)nb);
+                if (take > 0) {
+                    v |= lit8(pos, take) << (8u * nb);
+                    nb += (uint32_t)take; pos += take; litrem -= take;
                 }
-                put((uint32_t)off | (ml >= 19 ? (uint32_t)(ml - 19) << 16 : 0u), ml >= 19 ? 3u : 2u);
-                pos = st + ml;
+                if (pend && litrem == 0) {
+                    const uint32_t ob = cur_ml >= 19 ? 3u : 2u;
+                    if (nb + ob <= 8u) {
+                        v |= (uint64_t)(cur_off | (cur_ml >= 19 ? (uint32_t)(cur_ml - 19) << 16 : 0u)) << (8u * nb);
+                        nb += ob; pend = false; pos += cur_ml;
+                    }
+                }
+                put(v, nb);
             }
-            if (lane == 31) {                // the last sequence of the block: literals only (>= 11 of them)
-                put((uint32_t)(min(final_lit, 15) << 4), 1);
-                if (final_lit >= 15) {
-                    int rem = final_lit - 15;
-                    while (rem >= 255) { put(255u, 1); rem -= 255; }
-                    put((uint32_t)rem, 1);
-                }
-                lit_run(n - final_lit, final_lit);
-            }
-            if (fill) sts_or32(waddr, lo);
+            sts_or32(faddr, first ? lo : fw);
+            if (!first && fill) sts_or32(waddr, lo);
         }
         fence_proxy_async();                 // the tail buffer is read by the bulk-copy engine next
         __syncwarp();
