@@ -398,6 +398,7 @@ __device__ __forceinline__ uint32_t shr_word(const uint32_t (&X)[NW], int k, int
 }
 
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void sts_or32(uint32_t addr, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 struct FusedArgs {
@@ -635,33 +636,36 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             //         (rebuilt from the bits), offset [+ length byte] -- in passes of at most 8 bytes, all lanes in step: a
             //         flat state machine, so a lane with a long literal run does not hold up the others' next sequence.
             //         The bytes of a pass are gathered in a 64-bit value and appended to the lane's region of the tail
-            //         buffer through a word accumulator; a lane's first and last word may be shared with its neighbours:
-            //         those two are OR-ed into the zeroed buffer at the end, everything between is stored plainly.
+            //         buffer through a 64-bit accumulator; a lane's first and last 8-byte word may be shared with its
+            //         neighbours: those two are OR-ed into the zeroed buffer at the end, everything between is stored plainly.
             uint32_t waddr = smem_u32(seq) + (uint32_t)out_base;
-            uint32_t fill = waddr & 3u, lo = 0, fw = 0;
-            waddr &= ~3u;
+            uint32_t fill = waddr & 7u;                      // bytes of the accumulator in use
+            waddr &= ~7u;
             const uint32_t faddr = waddr;
-            bool first = true;               // the first word is still being filled: nothing stored yet
-            auto put = [&](uint64_t v, uint32_t nb) {       // append the low nb (<= 8) bytes of v; the bytes above must be zero
-                const uint32_t sh = 8u * fill, vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
-                const uint32_t c0 = lo | (vlo << sh);
-                const uint32_t c1 = __funnelshift_l(vlo, vhi, sh), c2 = __funnelshift_l(vhi, 0u, sh);
-                const uint32_t tot = fill + nb, nw = tot >> 2;
-                if (nw >= 1u && !first) sts32(waddr, c0);
-                if (nw >= 2u) sts32(waddr + 4u, c1);
-                fw = (nw >= 1u && first) ? c0 : fw;
-                first = first && nw == 0u;
-                lo = nw == 0u ? c0 : (nw == 1u ? c1 : c2);
-                waddr += 4u * nw;
-                fill = tot & 3u;
+            uint64_t acc = 0, fw = 0;
+            uint32_t first = 1;                              // the first word is still being filled: nothing stored yet
+            auto put = [&](uint64_t v, uint32_t nb) {        // append the low nb (<= 8) bytes of v; the bytes above must be zero
+                const uint32_t sh = 8u * fill;
+                acc |= v << sh;
+                const uint64_t spill = (v >> 1) >> (63u - sh);            // = v >> (64 - sh), 0 for sh == 0
+                fill += nb;
+                const bool full = fill >= 8u;
+                if (full && !first) sts64(waddr, acc);
+                fw = (full && first) ? acc : fw;
+                first = full ? 0u : first;
+                waddr += full ? 8u : 0u;
+                acc = full ? spill : acc;
+                fill -= full ? 8u : 0u;
             };
             // up to 8 literal bytes of block positions x .. x + nb - 1
             auto lit8 = [&](int x, int nb) -> uint64_t {
                 const int G = alpha + x;
-                const uint32_t bits = __funnelshift_r(strB[G >> 5], strB[(G >> 5) + 1], G) & ((1u << nb) - 1u);
+                const uint32_t keep = (1u << nb) - 1u;
+                const uint32_t bits = __funnelshift_r(strB[G >> 5], strB[(G >> 5) + 1], G) & keep;
                 uint64_t v = (uint64_t)spread4(bits) | ((uint64_t)spread4(bits >> 4) << 32);
                 if (any_n) {
-                    uint32_t nb8 = __funnelshift_r(strN[G >> 5], strN[(G >> 5) + 1], G) & ((1u << nb) - 1u);
+                    uint32_t nb8 = __funnelshift_r(strN[G >> 5], strN[(G >> 5) + 1], G) & keep;
+#pragma unroll 1
                     while (nb8) {                            // an allele other than 0 / 1: the byte itself
                         const int i = ctz32(nb8);
                         nb8 &= nb8 - 1;
@@ -674,55 +678,56 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             };
             const int seg_abs = p * cr + a0;
             int pos = seg_abs - carry;                       // next block position that has not been emitted
-            int left = m + (lane == 31 ? 1 : 0);             // sequences still to start; lane 31 closes the block with literals only
+            int base = seg_abs;                              // block position of bit 0 of Rp[0]
+            int left = m;                                    // matches still to start
+            uint32_t fin = lane == 31 ? 1u : 0u;             // lane 31 closes the block with a literals-only sequence
             int litrem = 0, cur_ml = 0;
-            uint32_t cur_off = 0;
-            bool pend = false;                               // the current sequence's offset has not been emitted yet
-            while (left > 0 || litrem > 0 || pend) {
+            uint32_t cur_off = 0, pend = 0;                  // pend: the current sequence's offset has not been emitted yet
+            while ((left | litrem | (int)pend | (int)fin) != 0) {
                 uint64_t v = 0;
                 uint32_t nb = 0;
-                if (litrem == 0 && !pend) {                  // the next sequence starts
+                if ((litrem | (int)pend) == 0) {             // the next sequence starts
                     int lit;
                     uint32_t tok;
-                    if (left > (lane == 31 ? 1 : 0)) {
-                        // lowest run of Rp: low = its first bit, t = Rp + low carries through it
-                        uint32_t low[NW], run[NW];
-                        bool found = false;
-                        int ts = 0;
-                        bool is_k = false;
+                    if (left > 0) {
+                        // matches are taken in order: whole words that are used up move out (at most NW - 1 times)
 #pragma unroll
-                        for (int k = 0; k < NW; ++k) {
-                            const uint32_t l = found ? 0u : (Rp[k] & (0u - Rp[k]));
-                            if (!found && l) { ts = 32 * k + ctz32(l); is_k = (K[k] & l) != 0u; }
-                            found = found || l != 0u;
-                            low[k] = l;
+                        for (int r = 0; r + 1 < NW; ++r) {
+                            const bool z = Rp[0] == 0u;
+#pragma unroll
+                            for (int k = 0; k + 1 < NW; ++k) { Rp[k] = z ? Rp[k + 1] : Rp[k]; K[k] = z ? K[k + 1] : K[k]; }
+                            Rp[NW - 1] = z ? 0u : Rp[NW - 1];
+                            base += z ? 32 : 0;
                         }
-                        uint64_t cy = 0;
+                        // lowest run of Rp: low = its first bit, Rp + low carries through the run (and on into the next words)
+                        const uint32_t low = Rp[0] & (0u - Rp[0]);
+                        const int ts = __popc(low - 1u);
+                        const bool is_k = (K[0] & low) != 0u;
+                        uint32_t cyv = low;
                         int ml = 1;
 #pragma unroll
                         for (int k = 0; k < NW; ++k) {
-                            cy += (uint64_t)Rp[k] + low[k];
-                            const uint32_t t = (uint32_t)cy;
-                            cy >>= 32;
-                            run[k] = Rp[k] & ~t;
+                            const uint32_t t = Rp[k] + cyv;
+                            cyv = t < cyv ? 1u : 0u;
+                            ml += __popc(Rp[k] & ~t);
                             Rp[k] &= t;
-                            ml += __popc(run[k]);
                         }
-                        const int st = seg_abs + ts;
-                        lit = st - pos;
+                        lit = base + ts - pos;
                         cur_ml = ml;
                         cur_off = is_k ? (uint32_t)cr : 2u * (uint32_t)cr;
-                        pend = true;
+                        pend = 1;
+                        --left;
                         tok = (uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15));
                     } else {                                 // the last sequence of the block: literals only (>= 11 of them)
                         lit = final_lit;
                         pos = n - final_lit;                 // (an empty last segment starts past the end of the block)
+                        fin = 0;
                         tok = (uint32_t)(min(lit, 15) << 4);
                     }
-                    --left;
                     v = tok; nb = 1;
                     if (lit >= 15) {
                         int rem = lit - 15;
+#pragma unroll 1
                         while (rem >= 255) { put(v, nb); v = 255u; nb = 1; rem -= 255; }
                         v |= (uint64_t)(uint32_t)rem << (8u * nb);
                         ++nb;
@@ -734,17 +739,24 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                     v |= lit8(pos, take) << (8u * nb);
                     nb += (uint32_t)take; pos += take; litrem -= take;
                 }
-                if (pend && litrem == 0) {
+                if (pend != 0 && litrem == 0) {
                     const uint32_t ob = cur_ml >= 19 ? 3u : 2u;
                     if (nb + ob <= 8u) {
                         v |= (uint64_t)(cur_off | (cur_ml >= 19 ? (uint32_t)(cur_ml - 19) << 16 : 0u)) << (8u * nb);
-                        nb += ob; pend = false; pos += cur_ml;
+                        nb += ob; pend = 0; pos += cur_ml;
                     }
                 }
                 put(v, nb);
             }
-            sts_or32(faddr, first ? lo : fw);
-            if (!first && fill) sts_or32(waddr, lo);
+            {
+                const uint64_t fv = first ? acc : fw;
+                if ((uint32_t)fv) sts_or32(faddr, (uint32_t)fv);
+                if ((uint32_t)(fv >> 32)) sts_or32(faddr + 4u, (uint32_t)(fv >> 32));
+                if (!first) {
+                    if ((uint32_t)acc) sts_or32(waddr, (uint32_t)acc);
+                    if ((uint32_t)(acc >> 32)) sts_or32(waddr + 4u, (uint32_t)(acc >> 32));
+                }
+            }
         }
         fence_proxy_async();                 // the tail buffer is read by the bulk-copy engine next
         __syncwarp();
