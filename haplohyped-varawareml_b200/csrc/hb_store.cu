@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(kSiteSegs * 32) site_template_kernel(const Sit
 // register accumulator into the frame's tail buffer in shared memory.
 // ------------------------------------------------------------------------------------------
 constexpr int kMinZ = 5, kMinC = 4;
+constexpr uint32_t kSlack = 128;
 constexpr int kWpc = 8;                       // warps per CTA
 constexpr int kFramesPerWarp = 8;             // frames (samples of one chunk) a warp encodes one after the other
 
@@ -418,6 +419,9 @@ struct FusedArgs {
     uint32_t tmpl_smem;  // bytes reserved for the chunk's template
     uint32_t warp_smem;  // bytes per warp
     uint32_t groups, gs; // sample groups per chunk (= CTAs per chunk), samples per group
+    uint32_t seg;        // block positions per lane.  Normally ceil(2 * cr / 32); when one mask word less per lane leaves at
+                         // most kSlack positions of the block without an owner, those become part of the block's closing
+                         // literals instead (cr 1075: 64 instead of 68 per lane, 102 of 2150 positions; +0.5 % frame size)
 };
 
 template <int NW>
@@ -431,14 +435,15 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
     uint8_t *wbase = smem + 16 + A.tmpl_smem + (size_t)warp * A.warp_smem;
     uint64_t *wbar = reinterpret_cast<uint64_t *>(wbase);
     uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + 16);
-    uint32_t *strB = reinterpret_cast<uint32_t *>(wbase + 16 + A.stg_bytes);
-    uint32_t *strN = strB + A.strw;
+    uint32_t *strB = reinterpret_cast<uint32_t *>(wbase + 16 + A.stg_bytes) + 4;      // 4 zero words in front of each string:
+    uint32_t *strN = strB + A.strw + 4;                                                //   word -1 may be read (step 2)
     uint8_t *outb = reinterpret_cast<uint8_t *>(strN + A.strw);
 
     const uint32_t tl = A.tmpl_len[c];
     const uint32_t tl16 = tl & ~15u, sh16 = tl & 15u;
     if (threadIdx.x == 0) mbar_init(tbar, 1);
     if (lane == 0) mbar_init(wbar, 1);
+    if (lane < 4) { strB[lane - 4] = 0; strN[lane - 4] = 0; }
     mbar_fence_init();
     __syncthreads();
     if (threadIdx.x == 0) {            // the chunk's template: once per CTA, by TMA
@@ -475,9 +480,8 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
         uint32_t Rp[NW], K[NW];            // match cover without the last position of each run; C-run cover (match type)
         int m = 0, carry = 0, out_base = 0, total = 0, final_lit = 0;
         bool any_n = false;
-        const int p = lane >> 4, q = lane & 15;
-        const int seg = (cr + 15) >> 4;
-        const int a0 = q * seg;
+        const int seg = (int)A.seg;                  // block positions per lane: lane i owns [i * seg, (i + 1) * seg)
+        const int x0 = lane * seg;
         const uint64_t grow = (uint64_t)(A.s0 + s) * A.gt_stride + r0;         // the frame's first row in the byte planes
 
         if (!raw) {
@@ -518,10 +522,10 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             }
 
             // ---- 2. per-lane parse of one segment, position-parallel
-            const int seglen = max(0, min(seg, cr - a0));
-            const int mlim = min(seglen, n - 11 - (p * cr + a0));         // the last 11 bytes of the block stay literals
-            const int bi = alpha + p * cr + a0, j0 = bi >> 5, shb = bi & 31;
-            const int bi0 = alpha + a0, j00 = bi0 >> 5, shb0 = bi0 & 31;     // the same rows in plane 0
+            const int seglen = max(0, min(seg, n - x0));
+            const int mlim = min(seglen, n - 11 - x0);                    // the last 11 bytes of the block stay literals
+            const int bi = alpha + x0, j0 = bi >> 5, shb = bi & 31;
+            const int ci = bi - cr, jc = ci >> 5, shc = ci & 31;          // the same rows in plane 0 (positions >= cr only)
             uint32_t Z[NW], C[NW], ZR[NW], S[NW], E[NW];
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
@@ -530,10 +534,11 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 const uint32_t vm = low_mask(mlim - 32 * k);
                 Z[k] = ~(bw | nw) & vm;
                 C[k] = 0;
-                if (p) {
-                    const uint32_t b0w = __funnelshift_r(strB[j00 + k], strB[j00 + k + 1], shb0);
-                    const uint32_t n0w = any_n ? __funnelshift_r(strN[j00 + k], strN[j00 + k + 1], shb0) : 0u;
-                    C[k] = ~((bw ^ b0w) | nw | n0w) & vm;
+                const uint32_t cm = vm & ~low_mask(cr - x0 - 32 * k);     // the word's positions in plane 1
+                if (cm) {                                                 // (then jc + k >= -1: the zero words in front)
+                    const uint32_t b0w = __funnelshift_r(strB[jc + k], strB[jc + k + 1], shc);
+                    const uint32_t n0w = any_n ? __funnelshift_r(strN[jc + k], strN[jc + k + 1], shc) : 0u;
+                    C[k] = ~((bw ^ b0w) | nw | n0w) & cm;
                 }
             }
             runs_cover<NW, kMinZ>(Z, ZR);
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
             }
             carry = __shfl_up_sync(0xffffffffu, val, 1);
             if (lane == 0) carry = 0;
-            final_lit = __shfl_sync(0xffffffffu, val, 31);
+            final_lit = __shfl_sync(0xffffffffu, val, 31) + max(0, n - 32 * seg);    // + the positions no lane owns (FusedArgs::seg)
             const int mysize = m > 0 ? 3 * m + (prev_end - matched) + carry + lit_ext(first_lit + carry) + n_ext : 0;
             int inc = mysize;
 #pragma unroll
@@ -676,11 +681,11 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 }
                 return v;
             };
-            const int seg_abs = p * cr + a0;
+            const int seg_abs = x0;
             int pos = seg_abs - carry;                       // next block position that has not been emitted
             int base = seg_abs;                              // block position of bit 0 of Rp[0]
             int left = m;                                    // matches still to start
-            uint32_t fin = lane == 31 ? 1u : 0u;             // lane 31 closes the block with a literals-only sequence
+            uint32_t fin = lane == 31 ? 1u : 0u;             // lane 31 closes the block with the token of a literals-only sequence
             int litrem = 0, cur_ml = 0;
             uint32_t cur_off = 0, pend = 0;                  // pend: the current sequence's offset has not been emitted yet
             while ((left | litrem | (int)pend | (int)fin) != 0) {
@@ -703,12 +708,13 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                         const uint32_t low = Rp[0] & (0u - Rp[0]);
                         const int ts = __popc(low - 1u);
                         const bool is_k = (K[0] & low) != 0u;
-                        uint32_t cyv = low;
+                        uint64_t cy = low;
                         int ml = 1;
 #pragma unroll
                         for (int k = 0; k < NW; ++k) {
-                            const uint32_t t = Rp[k] + cyv;
-                            cyv = t < cyv ? 1u : 0u;
+                            cy += Rp[k];
+                            const uint32_t t = (uint32_t)cy;
+                            cy >>= 32;
                             ml += __popc(Rp[k] & ~t);
                             Rp[k] &= t;
                         }
@@ -718,10 +724,9 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                         pend = 1;
                         --left;
                         tok = (uint32_t)((min(lit, 15) << 4) | min(ml - 4, 15));
-                    } else {                                 // the last sequence of the block: literals only (>= 11 of them)
-                        lit = final_lit;
-                        pos = n - final_lit;                 // (an empty last segment starts past the end of the block)
-                        fin = 0;
+                    } else {                                 // the last sequence of the block: literals only (>= 11 of them);
+                        lit = final_lit;                     // lane 31 writes its token and length bytes, the literals
+                        fin = 0;                             // themselves are written by the whole warp below
                         tok = (uint32_t)(min(lit, 15) << 4);
                     }
                     v = tok; nb = 1;
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                         v |= (uint64_t)(uint32_t)rem << (8u * nb);
                         ++nb;
                     }
-                    litrem = lit;
+                    litrem = pend ? lit : 0;
                 }
                 const int take = min(litrem, 8 - (int)nb);
                 if (take > 0) {
@@ -755,6 +760,19 @@ __global__ void __launch_bounds__(kWpc * 32) donor_frames_kernel(const FusedArgs
                 if (!first) {
                     if ((uint32_t)acc) sts_or32(waddr, (uint32_t)acc);
                     if ((uint32_t)(acc >> 32)) sts_or32(waddr + 4u, (uint32_t)(acc >> 32));
+                }
+            }
+            __syncwarp();
+            // the block's closing literals (>= 11, and all the positions no lane owns): one byte per lane and step
+            {
+                uint8_t *fdst = seq + (dlen - final_lit);
+                const int fx = n - final_lit;
+                for (int i = lane; i < final_lit; i += 32) {
+                    const int x = fx + i, G = alpha + x;
+                    uint32_t byte = (strB[G >> 5] >> (G & 31)) & 1u;
+                    if (any_n && ((strN[G >> 5] >> (G & 31)) & 1u))
+                        byte = (uint8_t)(x < cr ? A.gt0 : A.gt1)[grow + (x < cr ? x : x - cr)];
+                    fdst[i] = (uint8_t)byte;
                 }
             }
         }
@@ -1075,13 +1093,15 @@ int hb_compress_sample_range(hb_parse *p, uint64_t chunk_records, uint32_t s0, u
     f->smem_site = 16 + ((n_site + 19) & ~15u) + ((site_seg_cap(24 * cr + 1) + kSiteSegs * 48 + 15) & ~15u) +
                    ((size_t)kSiteSegs << kSiteHashLog) * 2;
     if (f->smem_site > 220 * 1024) { hb_frames_free(f); return api_fail(HB_ERR_ARG, "chunk too large for the site encoder (33*chunk_records must fit shared memory)"); }
-    const uint32_t seg = (cr + 15) / 16;
+    uint32_t seg = (n_gt + 31) / 32;
     f->nw = (int)((seg + 31) / 32);
+    if (f->nw > 1 && 1024u * (uint32_t)(f->nw - 1) + kSlack >= n_gt) { f->nw -= 1; seg = 32u * (uint32_t)f->nw; }
     FusedArgs &fa = f->fa;
+    fa.seg = seg;
     fa.strw = (((127 + 2 * cr) >> 5) + (uint32_t)f->nw + 3 + 3) & ~3u;   // both planes from bit alpha <= 127 on, + look-ahead words
     fa.stg_bytes = (((127 + cr - 1) >> 7) + 1) * (kBitGroupWords * 4);   // 128-row groups a chunk's rows can touch
     fa.outcap = (16 + n_gt + n_gt / 255 + 24 + 15) & ~15u;
-    fa.warp_smem = 16 + fa.stg_bytes + 8 * fa.strw + fa.outcap;
+    fa.warp_smem = 16 + fa.stg_bytes + 2 * (16 + 4 * fa.strw) + fa.outcap;
     f->chunk_cap = f->n_chunks + 4;          // a re-run on a slightly longer record set (streaming) still fits
     const uint64_t n_frames = f->chunk_cap * f->n_samples;
     f->h_tmpl_len.resize(f->n_chunks);
