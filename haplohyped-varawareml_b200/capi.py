@@ -72,7 +72,7 @@ EXPORTS = [
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
-    "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all",
+    "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all", "hb_frames_fetch_packed",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_set_site_matcher", "hb_decode_frames",
     "hb_encode_haplotypes",
@@ -129,6 +129,7 @@ def lib():
             L.hb_parse_attach_frames.argtypes = [C.c_void_p, C.c_void_p]
             L.hb_frames_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.hb_frames_fetch_all.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+            L.hb_frames_fetch_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
             L.hb_frames_fetch_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
                                                  C.POINTER(C.c_uint64)]
             L.hb_frames_free.argtypes = [C.c_void_p]
@@ -342,6 +343,21 @@ class Frames:
         buf = np.empty(max(1, self.info.padded_bytes), np.uint8)
         check(lib().hb_frames_fetch_all(self._h, buf.ctypes.data, buf.size))
         return buf[:self.info.padded_bytes]
+
+    def fetch_packed(self, out=None):
+        """All frames back to back (16-byte aligned), [sample][chunk] order: (buf uint8, offsets uint64 [n_samples, n_chunks]
+        into buf, sizes uint32 [n_samples, n_chunks]).  out: a pre-allocated uint8 array / (address, capacity) to fill (e.g.
+        pinned memory), else a new numpy array."""
+        i = self.info
+        offs = np.zeros((i.n_samples, i.n_chunks), np.uint64)
+        sizes = np.zeros((i.n_samples, i.n_chunks), np.uint32)
+        tot = C.c_uint64()
+        check(lib().hb_frames_fetch_packed(self._h, None, 0, offs.ctypes.data, sizes.ctypes.data, C.byref(tot)))
+        if out is None:
+            out = np.empty(max(1, tot.value), np.uint8)
+        addr, cap = (out.ctypes.data, out.size) if isinstance(out, np.ndarray) else (int(out[0]), int(out[1]))
+        check(lib().hb_frames_fetch_packed(self._h, addr, cap, None, None, C.byref(tot)))
+        return (out[:tot.value] if isinstance(out, np.ndarray) else tot.value), offs, sizes
 
     def sample(self, s: int):
         i = self.info

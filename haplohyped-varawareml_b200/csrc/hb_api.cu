@@ -218,6 +218,7 @@ cudaEvent_t *d2h_events() {                     // g_d2h.mu held; the two events
 }
 }  // namespace
 namespace hb {
+bool host_is_pinned(const void *p) { return is_pinned(p); }
 // height rows of width bytes, spitch apart on the device, dpitch apart on the host
 cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height, cudaStream_t stream) {
     if (!width || !height) return cudaSuccess;

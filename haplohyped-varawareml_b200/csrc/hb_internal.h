@@ -107,6 +107,7 @@ void dev_pool_free(void *p);
 void dev_pool_flush();
 
 // device -> host memory of any kind, synchronous: pinned destinations directly, pageable ones through pinned staging
+bool host_is_pinned(const void *p);
 cudaError_t d2h_copy(void *dst, const void *src, uint64_t bytes, cudaStream_t stream);
 cudaError_t d2h_copy_2d(void *dst, uint64_t dpitch, const void *src, uint64_t spitch, uint64_t width, uint64_t height, cudaStream_t stream);
 

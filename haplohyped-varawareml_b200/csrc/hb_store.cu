@@ -815,6 +815,24 @@ __global__ void __launch_bounds__(256) sum_sizes_kernel(const uint32_t *__restri
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(total, acc);
 }
 
+// Frames out of their slots, packed back to back (16-byte aligned) into one piece of the packed image: one warp per
+// frame, 16-byte vectors.  slot of frame i = (i / n_chunks) * row_stride + slot_off[i % n_chunks]; packed_off = where the
+// frame starts in the packed image, piece_base = where this piece starts.
+__global__ void __launch_bounds__(256)
+pack_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restrict__ slot_off, uint64_t n_chunks,
+                   const uint32_t *__restrict__ size, const uint64_t *__restrict__ packed_off, uint64_t first, uint64_t count,
+                   uint64_t piece_base, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const uint64_t i = first + w;
+    const uint64_t s = i / n_chunks, c = i - s * n_chunks;
+    const uint4 *src = reinterpret_cast<const uint4 *>(frames + s * slot_off[n_chunks] + slot_off[c]);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (packed_off[i] - piece_base));
+    const uint32_t nv = (size[i] + 15u) >> 4;              // the slot is zero behind the frame up to the next 16-byte boundary
+    for (uint32_t k = lane; k < nv; k += 32) stg_stream(dst + k, ldg_stream(src + k));
+}
+
 uint64_t guess_chunk_records(uint64_t n) {      // h5py/_hl/filters.py guess_chunk for shape (n,), 35-byte items
     const double CHUNK_BASE = 16 * 1024, CHUNK_MIN = 8 * 1024, CHUNK_MAX = 1024 * 1024;
     if (n == 0) return 1;
@@ -1196,6 +1214,76 @@ int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap) {
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
     cudaError_t e = d2h_copy(buf, f->d_frames, f->padded_bytes, f->stream);      // pinned: one copy; pageable: staged
     if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    return HB_OK;
+}
+
+// All frames packed back to back (each starts on a 16-byte boundary of the image), [sample][chunk] order: what a
+// converter writes into the HDF5 file with one write.  The frames leave their slots through a gather kernel, a piece of
+// at most kPackPiece bytes at a time, and the D2H copy of piece k runs while piece k + 1 is gathered (two device
+// buffers); against hb_frames_fetch_all this moves total_bytes instead of padded_bytes over PCIe.  offsets [n_samples]
+// [n_chunks] = where each frame starts in buf; sizes as in hb_frames_layout; either may be NULL.  buf == NULL: only
+// *total (bytes needed) is set.
+int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *offsets, uint32_t *sizes, uint64_t *total) {
+    if (!f) return api_fail(HB_ERR_ARG, "null handle");
+    int rc = frames_layout(f);
+    if (rc != HB_OK) return rc;
+    const uint64_t nc = f->n_chunks, n_frames = nc * f->n_samples;
+    std::vector<uint64_t> poff(n_frames + 1);
+    uint64_t run = 0;
+    for (uint64_t i = 0; i < n_frames; ++i) { poff[i] = run; run += ((uint64_t)f->h_size[i] + 15) & ~15ull; }
+    poff[n_frames] = run;
+    if (total) *total = run;
+    if (offsets && n_frames) memcpy(offsets, poff.data(), n_frames * 8);
+    if (sizes && n_frames) memcpy(sizes, f->h_size.data(), n_frames * 4);
+    if (!buf || !n_frames) return HB_OK;
+    if (cap < run) return api_fail(HB_ERR_ARG, "buffer too small");
+    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    constexpr uint64_t kPackPiece = 256ull << 20;
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    uint64_t *d_poff = nullptr;
+    uint8_t *d_piece[2] = {nullptr, nullptr};
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_g[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr};
+    const uint64_t piece_cap = std::min<uint64_t>(run, kPackPiece + (1ull << 20));
+    ck(dev_pool_alloc((void **)&d_poff, (n_frames + 1) * 8));
+    ck(dev_pool_alloc((void **)&d_piece[0], piece_cap));
+    ck(dev_pool_alloc((void **)&d_piece[1], piece_cap));
+    ck(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) { ck(cudaEventCreateWithFlags(&ev_g[k], cudaEventDisableTiming)); ck(cudaEventCreateWithFlags(&ev_c[k], cudaEventDisableTiming)); }
+    if (e == cudaSuccess) ck(cudaMemcpyAsync(d_poff, poff.data(), (n_frames + 1) * 8, cudaMemcpyHostToDevice, f->stream));
+    const bool pinned = host_is_pinned(buf);
+    uint64_t first = 0;
+    int k = 0;
+    while (e == cudaSuccess && first < n_frames) {
+        // frames [first, last) = the next piece: at most kPackPiece bytes (one frame is far smaller than that)
+        const uint64_t base = poff[first];
+        uint64_t last = std::upper_bound(poff.begin() + first, poff.begin() + n_frames + 1, base + kPackPiece) - poff.begin() - 1;
+        if (last <= first) last = first + 1;
+        const uint64_t bytes = poff[last] - base;
+        const int b = k & 1;
+        if (k >= 2) ck(cudaStreamWaitEvent(f->stream, ev_c[b], 0));            // the copy that read this buffer last is done
+        pack_frames_kernel<<<(unsigned)((last - first + 7) / 8), 256, 0, f->stream>>>(f->d_frames, f->d_slot_off, nc, f->d_size, d_poff,
+                                                                                    first, last - first, base, d_piece[b]);
+        count_launch();
+        ck(cudaGetLastError());
+        ck(cudaEventRecord(ev_g[b], f->stream));
+        if (pinned) {
+            ck(cudaStreamWaitEvent(copy, ev_g[b], 0));
+            ck(cudaMemcpyAsync(buf + base, d_piece[b], bytes, cudaMemcpyDeviceToHost, copy));
+            ck(cudaEventRecord(ev_c[b], copy));
+        } else {                                                                // pageable destination: staged copy, piece by piece
+            ck(d2h_copy(buf + base, d_piece[b], bytes, f->stream));
+        }
+        first = last;
+        ++k;
+    }
+    if (copy) { cudaError_t e2 = cudaStreamSynchronize(copy); if (e == cudaSuccess) e = e2; }
+    { cudaError_t e2 = cudaStreamSynchronize(f->stream); if (e == cudaSuccess) e = e2; }
+    for (int q = 0; q < 2; ++q) { if (ev_g[q]) cudaEventDestroy(ev_g[q]); if (ev_c[q]) cudaEventDestroy(ev_c[q]); }
+    if (copy) cudaStreamDestroy(copy);
+    dev_pool_free(d_poff); dev_pool_free(d_piece[0]); dev_pool_free(d_piece[1]);
+    if (e != cudaSuccess) { cudaGetLastError(); return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); }
     return HB_OK;
 }
 

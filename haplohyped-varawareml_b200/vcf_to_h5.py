@@ -187,8 +187,7 @@ class VCFtoHDF5Converter:
                 if not mine:
                     continue
                 fr = cp.frames_for(s0, ns)
-                buf = fr.fetch_all()
-                offs, sizes = fr.layout()
+                buf, offs, sizes = fr.fetch_packed()            # gathered on the device: no slot padding crosses PCIe or reaches the file
                 rows = [cp.index[d] - s0 for d in mine]
                 self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in mine], RECORD_DTYPE,
                                                 cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])

@@ -211,6 +211,12 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info);
 int hb_frames_layout(hb_frames *f, uint64_t *offsets, uint32_t *sizes);
 /* the whole frame buffer (padded_bytes) in one D2H copy */
 int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap);
+/* All frames packed back to back, [sample][chunk] order, each starting on a 16-byte boundary of buf -- what a converter
+ * writes into the HDF5 file with one write (replaces the per-dataset writes of vcf_to_h5.py:131-135).  The frames are
+ * gathered out of their slots on the device in pieces and the D2H copy of one piece overlaps the gather of the next:
+ * total_bytes (+ < 16 per frame) cross PCIe instead of padded_bytes.  offsets / sizes [n_samples][n_chunks] may be
+ * NULL; buf == NULL only reports *total, the bytes buf must hold.  buf should be pinned memory. */
+int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *offsets, uint32_t *sizes, uint64_t *total);
 /* sizes[n_chunks] of one sample's frames; then the frames themselves, concatenated without padding */
 int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes, uint8_t *buf, uint64_t cap,
                            uint64_t *total);

@@ -126,6 +126,19 @@ def test_long_segments_and_layout(capi, mix, chunk_records):
         for k, f in enumerate(fr.sample(s)):
             o = int(offs[s, k])
             assert buf[o:o + int(sizes[s, k])].tobytes() == f
+    # packed image: the same frames back to back (16-byte aligned), pageable and pinned destinations, pieces of any size
+    import torch
+    pk, poffs, psizes = fr.fetch_packed()
+    assert np.array_equal(psizes, sizes) and (poffs % 16 == 0).all() and len(pk) == int(((sizes.astype(np.int64) + 15) // 16 * 16).sum())
+    assert np.array_equal(poffs.reshape(-1)[1:], np.cumsum((sizes.reshape(-1).astype(np.uint64) + 15) // 16 * 16)[:-1])
+    pin = torch.empty(len(pk) + 64, dtype=torch.uint8).pin_memory()
+    pin.fill_(0xEE)
+    tot, _, _ = fr.fetch_packed(out=(pin.data_ptr(), pin.numel()))
+    assert tot == len(pk) and np.array_equal(pin.numpy()[:tot], pk) and (pin.numpy()[tot:] == 0xEE).all()
+    for s in (0, 47, 95):
+        for k, f in enumerate(fr.sample(s)):
+            o = int(poffs[s, k])
+            assert pk[o:o + int(psizes[s, k])].tobytes() == f
     fr.rerun(p)                                                                       # deterministic: same bytes again
     assert np.array_equal(fr.fetch_all(), buf)
 
