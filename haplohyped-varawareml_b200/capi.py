@@ -15,6 +15,9 @@ LIB_PATH = os.path.join(_HERE, "libhaplo_b200.so")
 _lib = None
 
 
+HB_ERR_IO, HB_ERR_HEADER, HB_ERR_SAMPLE, HB_ERR_PLOIDY, HB_ERR_GT, HB_ERR_FORMAT, HB_ERR_NOGT, HB_ERR_MEM, HB_ERR_CUDA, HB_ERR_ARG = range(1, 11)
+
+
 class HaploError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(msg)
@@ -67,7 +70,7 @@ class SynthSpec(C.Structure):
 
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
-    "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear",
+    "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear", "hb_cache_set_limit",
     "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_stream_bgzf_host", "hb_bgzf_vcf_info", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
@@ -94,6 +97,8 @@ def lib():
         L.hb_load_vcf.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Records)]
         L.hb_load_vcf_without_sample.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(Records)]
         L.hb_records_free.argtypes = [C.POINTER(Records)]
+        L.hb_cache_set_limit.argtypes = [C.c_uint64]
+        L.hb_cache_set_limit.restype = None
         L.hb_parse_host_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_stream_host.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -19,6 +19,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/stat.h>
 #include <thread>
 #include <vector>
 
@@ -462,8 +463,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
 // ---- records located by walking heads (uniform GT-only text): hb_walk.cu
 static int index_by_walker(hb_parse *p, const Launch &L) {
     {
-        uint32_t k = 16;
-        if (const char *e = getenv("HB_WALK_LINES")) { int v = atoi(e); if (v > 0 && v < 65536) k = (uint32_t)v; }
+        const uint32_t k = 16;
         p->n_walkers = walk_plan(p->nbytes, p->first_line_len, k, &p->walk_range);
         if (!p->d_wstart || p->n_walkers > p->walk_cap) {
             TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
@@ -1154,7 +1154,7 @@ int read_vcf(const std::vector<uint8_t> &raw, FileText &ft) {
 // One .vcf / .vcf.gz -> device-resident parse.  BGZF files (what bgzip writes, what the reference's tabix path
 // reads) travel over PCIe COMPRESSED and are inflated on the GPU (hb_inflate.cu) straight into the text buffer;
 // only the header members are also inflated on the host, to learn the sample names.  Plain gzip (one DEFLATE
-// stream: nothing to parallelise) and plain text go through zlib / as they are.  HB_CPU_INFLATE=1 forces zlib.
+// stream: nothing to parallelise) and plain text go through zlib / as they are.
 int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, uint64_t raw_n, const char *region, bool want_gt,
                        int device, hb_parse **out, std::vector<std::string> &samples);
 
@@ -1198,8 +1198,7 @@ int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, ui
     std::vector<uint64_t> coff, ooff;
     std::vector<uint32_t> clen, olen;
     uint64_t total = 0;
-    const char *force = getenv("HB_CPU_INFLATE");
-    const bool gpu_inflate = !(force && *force == '1') && raw.size() >= 28 && raw[0] == 0x1f && raw[1] == 0x8b &&
+    const bool gpu_inflate = raw.size() >= 28 && raw[0] == 0x1f && raw[1] == 0x8b &&
                              bgzf_index(raw.data(), raw.size(), coff, clen, ooff, olen, total) && total > 0;
     hb_parse_opts o;
     memset(&o, 0, sizeof o);
@@ -1264,11 +1263,49 @@ struct CacheEntry {
     std::string chrom_pool;
     std::vector<uint32_t> ploidy_err, badgt_err;
     bool want_gt = true;
+    uint64_t hbm_bytes = 0;            // device memory the entry pins (genotype planes + bit planes)
+    uint64_t last_use = 0;             // LRU tick (g_cache_mu)
     ~CacheEntry() { if (parse) hb_parse_free(parse); }
 };
 
+// The per-sample reference API (one load_vcf call per donor and chromosome, vcf_to_h5.py:150-152) is served from
+// device-resident parses kept here.  Key = path + file identity (size, mtime, inode: a file rewritten in place is a
+// different key) + region.  Entries are dropped least-recently-used first once they pin more than g_cache_limit bytes
+// of HBM (default 40 % of the device), and all idle ones go when a parse runs out of device memory.  An entry that is
+// still referenced by records handed out lives on until they are freed.
 std::mutex g_cache_mu;
 std::map<std::string, std::shared_ptr<CacheEntry>> g_cache;
+uint64_t g_cache_tick = 0, g_cache_limit = 0;
+
+std::string file_identity(const char *path) {
+    struct stat st;
+    if (stat(path, &st) != 0) return "?";
+    return std::to_string((unsigned long long)st.st_size) + ":" + std::to_string((long long)st.st_mtim.tv_sec) + "." +
+           std::to_string((long)st.st_mtim.tv_nsec) + ":" + std::to_string((unsigned long long)st.st_ino);
+}
+
+uint64_t cache_limit_bytes() {           // g_cache_mu held
+    if (g_cache_limit) return g_cache_limit;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 64ull << 30; }
+    return (uint64_t)(0.4 * (double)tot);
+}
+
+// drop finished entries, least recently used first, until the rest pins at most `limit` bytes; `keep` stays
+void cache_evict(uint64_t limit, const CacheEntry *keep) {      // g_cache_mu held
+    for (;;) {
+        uint64_t sum = 0;
+        auto victim = g_cache.end();
+        for (auto it = g_cache.begin(); it != g_cache.end(); ++it) {
+            CacheEntry *ce = it->second.get();
+            sum += ce->hbm_bytes;
+            if (ce == keep || !ce->done) continue;                  // (done is set under ce->mu before the entry is used again)
+            if (victim == g_cache.end() || ce->last_use < victim->second->last_use) victim = it;
+        }
+        if (sum <= limit || victim == g_cache.end()) return;
+        g_cache.erase(victim);
+    }
+}
 
 int env_device() {
     const char *e = getenv("HB_DEVICE");
@@ -1299,31 +1336,53 @@ int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_
     }
     // the text is no longer needed once names are resolved: give the HBM back
     if (p->d_text_owned) { free_dev(p->d_text_owned); p->d_text_owned = nullptr; p->d_text = nullptr; }
+    ce.hbm_bytes = want_gt ? 2 * p->gt_bytes + 4 * p->bits_stride * p->n_samples : 0;
     return HB_OK;
 }
 
 std::shared_ptr<CacheEntry> get_entry(const char *path, const char *region, bool want_gt, int &rc) {
-    std::string key = std::string(path) + "\x01" + (region ? region : "") + (want_gt ? "\x01g" : "\x01s");
+    const std::string base = std::string(path) + "\x01" + file_identity(path) + "\x01" + (region ? region : "");
+    const std::string key = base + (want_gt ? "\x01g" : "\x01s");
     std::shared_ptr<CacheEntry> ce;
     bool builder = false;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_cache.find(key);
         if (it == g_cache.end() && !want_gt) {   // a genotype parse also answers site queries
-            auto it2 = g_cache.find(std::string(path) + "\x01" + (region ? region : "") + "\x01g");
+            auto it2 = g_cache.find(base + "\x01g");
             if (it2 != g_cache.end()) it = it2;
         }
-        if (it == g_cache.end()) { ce = std::make_shared<CacheEntry>(); g_cache[key] = ce; builder = true; }
-        else ce = it->second;
+        if (it == g_cache.end()) {
+            ce = std::make_shared<CacheEntry>(); g_cache[key] = ce; builder = true;
+            // an older parse of the same path (the file was rewritten since) can never be asked for again
+            const std::string any_id = std::string(path) + "\x01", this_id = any_id + file_identity(path) + "\x01";
+            for (auto jt = g_cache.begin(); jt != g_cache.end();) {
+                const bool same_path = jt->first.compare(0, any_id.size(), any_id) == 0;
+                const bool same_file = jt->first.compare(0, this_id.size(), this_id) == 0;
+                if (same_path && !same_file && jt->second->done) jt = g_cache.erase(jt);
+                else ++jt;
+            }
+        } else ce = it->second;
+        ce->last_use = ++g_cache_tick;
     }
     if (builder) {
         int r = build_entry(*ce, path, region, want_gt);
+        if (r == HB_ERR_MEM || r == HB_ERR_CUDA) {          // out of device memory? drop every idle entry and try once more
+            { std::lock_guard<std::mutex> lk(g_cache_mu); cache_evict(0, ce.get()); }
+            hb::dev_pool_flush();
+            cudaGetLastError();
+            if (ce->parse) { hb_parse_free(ce->parse); ce->parse = nullptr; }
+            ce->samples.clear(); ce->chrom_pool.clear();
+            r = build_entry(*ce, path, region, want_gt);
+        }
         {
             std::lock_guard<std::mutex> lk(ce->mu);
             ce->rc = r; ce->err = g_err; ce->done = true;
         }
         ce->cv.notify_all();
-        if (r != HB_OK) { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache.erase(key); }
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (r != HB_OK) g_cache.erase(key);
+        else cache_evict(cache_limit_bytes(), ce.get());
     } else {
         std::unique_lock<std::mutex> lk(ce->mu);
         ce->cv.wait(lk, [&] { return ce->done; });
@@ -1357,7 +1416,7 @@ void fill_records(hb_records *out, RecOwner *ow) {
 int hb_load_vcf(const char *in_vcf, const char *sample, const char *chrom, hb_records *out) {
     if (!in_vcf || !sample || !out) return fail(HB_ERR_ARG, "null argument");
     memset(out, 0, sizeof *out);
-    if (!*sample) return hb_load_vcf_without_sample(in_vcf, chrom, out);
+    if (!*sample) return fail(HB_ERR_SAMPLE, "load_vcf needs a sample name (hb_load_vcf_without_sample answers site queries)");
     int rc;
     auto ce = get_entry(in_vcf, chrom, true, rc);
     if (rc != HB_OK) return rc;
@@ -1397,6 +1456,12 @@ void hb_records_free(hb_records *r) {
     if (!r || !r->owner_) return;
     delete static_cast<RecOwner *>(r->owner_);
     memset(r, 0, sizeof *r);
+}
+
+void hb_cache_set_limit(uint64_t hbm_bytes) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_limit = hbm_bytes;
+    if (hbm_bytes) cache_evict(hbm_bytes, nullptr);
 }
 
 void hb_cache_clear(void) {

@@ -87,8 +87,8 @@ __device__ __noinline__ int decode_field(const uint8_t *__restrict__ t, uint64_t
 // A '\n' inside a group means the span was not one record's samples (possible only when the records
 // were located by the walker, hb_walk.cu): the whole index is void and the caller falls back.
 __device__ __noinline__ uint32_t decode_group_slow(uint32_t w, int *mode, DevStatus *st) {
+    if (has_byte(w, kNl4)) st->index_invalid = 1u;           // (before the early return: another lane may have demoted the record already)
     if (*mode != 1) return 0;
-    if (has_byte(w, kNl4)) st->index_invalid = 1u;
     const uint32_t sep = (w >> 16) & 0xffu, x = (w >> 8) & 0xffu, y = w >> 24;
     bool ok = (w & 0xffu) == '\t' && (sep == '|' || sep == '/');
     uint32_t a0 = x - '0', a1 = y - '0';

@@ -34,6 +34,10 @@ void raise_parse_error() {
 }
 
 void load(Records &rec, const std::string &in_vcf, const std::string &sample, const std::string &chrom, bool gt) {
+    if (gt && sample.empty()) {        // the reference subsets to zero samples and then indexes gt[0] (parse_vcf.cpp:50-52): reported
+        std::cerr << "Error parsing VCF file: load_vcf needs a sample name" << std::endl;
+        throw std::runtime_error("Error parsing VCF file: load_vcf needs a sample name (use load_vcf_without_sample for sites only)");
+    }
     int rc;
     {
         py::gil_scoped_release nogil;

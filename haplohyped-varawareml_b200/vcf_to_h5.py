@@ -237,9 +237,13 @@ class VCFtoHDF5Converter:
             for c in self.chromosomes:
                 if c not in present:
                     logger.warning(f"chr{c}.filtered.vcf.gz does not exist in {self.vcf_dir}; skipped")
-            with ThreadPoolExecutor(max_workers=max(1, min(int(self.cores or 1), 2))) as executor:
-                parses = executor.map(lambda c: (c, self._safe_parse(c)), present)
-                for c, cp in parses:
+            # one chromosome ahead, no more: the parse of the next file (file read + H2D + GPU inflate + kernels) overlaps
+            # the frames / D2H / file write of the current one, and at most two chromosomes' genotype planes are in HBM
+            with ThreadPoolExecutor(max_workers=1) as executor:
+                nxt = executor.submit(self._safe_parse, present[0]) if present else None
+                for k, c in enumerate(present):
+                    cp = nxt.result()
+                    nxt = executor.submit(self._safe_parse, present[k + 1]) if k + 1 < len(present) else None
                     if cp is None:
                         continue
                     self._chrom[c] = cp
@@ -267,7 +271,9 @@ class VCFtoHDF5Converter:
             return _ChromParse(vcf_file, chromosome, self.device, self.sample_window)
         except capi.HaploError as e:
             logger.error(f"An error occurred while processing VCF file: Error parsing VCF file: {e}")
-            self.stats["skipped_files"] += 1
+            if e.code in (capi.HB_ERR_MEM, capi.HB_ERR_CUDA):
+                raise                                   # out of device memory / a device fault: not this file's problem
+            self.stats["skipped_files"] += 1            # an unreadable or malformed file: the others still convert
             return None
 
 

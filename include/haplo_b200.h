@@ -62,6 +62,9 @@ typedef struct hb_records {
 int hb_load_vcf(const char *in_vcf, const char *sample, const char *chrom, hb_records *out);
 int hb_load_vcf_without_sample(const char *in_vcf, const char *chrom, hb_records *out);
 void hb_records_free(hb_records *r);
+/* Device memory the cache behind hb_load_vcf may pin (genotype planes of the parsed files): entries go least recently
+ * used first.  0 = the default, 40 % of the device.  A file whose size / mtime / inode changed is parsed again. */
+void hb_cache_set_limit(uint64_t hbm_bytes);
 void hb_cache_clear(void);      /* drop the per-(file, region) device-resident parse cache, the kept frame buffer and the
                                  * device slots the streaming entry points keep between calls */
 

@@ -366,3 +366,61 @@ def test_stream_slots_are_reused_and_safe_across_options_and_threads(capi):
             r = capi.parse_stream_bgzf_host(synth.bgzf_compress(text, block=2500), capacity=ora["n"], region="chr22", slab_bytes=slab)
             assert r["n"] == ora["n"] and np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["stop"], ora["stop"])
     capi.lib().hb_cache_clear()
+
+
+def test_load_vcf_cache_follows_the_file_and_is_bounded(capi, parse_vcf, tmp_path):
+    """The per-(file, region) cache behind load_vcf: a file rewritten at the same path is parsed again (size / mtime / inode
+    are part of the key), hb_cache_set_limit bounds the HBM it pins (least recently used entries go), and an empty sample
+    name is an error, not a crash."""
+    import os, time
+    S = synth.sample_names(4)
+    def write(path, alt, n):
+        body = "".join("chr22\t%d\t.\tA\t%s\t.\t.\t.\tGT\t0|1\t1|1\t0|0\t1|0\n" % (100 + 7 * i, alt) for i in range(n))
+        with open(path, "w") as f:
+            f.write(synth.header(S) + body)
+    a = str(tmp_path / "a.vcf")
+    write(a, "C", 50)
+    first = parse_vcf.load_vcf(a, S[0], "chr22")
+    assert len(first) == 50 and first[0][4] == "C"
+    time.sleep(0.01)
+    write(a, "G", 70)                                   # same path, new content
+    again = parse_vcf.load_vcf(a, S[1], "chr22")
+    assert len(again) == 70 and again[0][4] == "G" and again[0][5:] == (1, 1)
+    # a limit of one byte: every finished entry but the newest is dropped; results stay correct
+    capi.lib().hb_cache_set_limit(1)
+    try:
+        paths = []
+        for k in range(4):
+            pth = str(tmp_path / ("b%d.vcf" % k))
+            write(pth, "ACGT"[k], 30 + k)
+            paths.append(pth)
+        for rnd in range(2):
+            for k, pth in enumerate(paths):
+                got = parse_vcf.load_vcf(pth, S[3], "chr22")
+                assert len(got) == 30 + k and got[0][4] == "ACGT"[k] and got[0][5:] == (1, 0)
+    finally:
+        capi.lib().hb_cache_set_limit(0)
+        capi.lib().hb_cache_clear()
+    with pytest.raises(RuntimeError, match="Error parsing VCF file"):
+        parse_vcf.load_vcf(a, "", "chr22")
+    assert len(parse_vcf.load_vcf_without_sample(a, "chr22")) == 70
+
+
+def test_two_devices_in_one_process(capi):
+    """Kernels with > 48 KB of dynamic shared memory opt in per function AND per device: a process that parses on device 0
+    and then on device 1 (vcf_to_h5 --devices, a notebook that switches GPUs) must be served on both."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    text, samples = synth.random_vcf(700, 150, seed=3, fmt="GT", kinds="mixed")
+    ora = oracle.parse_text(text, "*", "chr22")
+    for dev in (0, 1, 0):
+        p = capi.Parse.from_host(synth.body_of(text), len(samples), region="chr22", device=dev)
+        g0, g1 = p.matrix()
+        assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
+        fr = p.compress(64)
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][7], ora["gt1"][7])
+        raw = rec.tobytes() + b"\0" * (int(fr.info.n_chunks) * 64 * 35 - rec.nbytes)
+        for k, f in enumerate(fr.sample(7)):
+            assert oracle.blosc_chunk_decode(f, 64 * 35).tobytes() == raw[k * 64 * 35:(k + 1) * 64 * 35]
+        fr.close(); p.close()
