@@ -203,6 +203,72 @@ def blosc1_chunk_encode(data, typesize: int, blocksize: int = 0, split: bool = F
 
 
 # --------------------------------------------------------------------------------------------
+# What the reference's writer stores: blosc_compress of c-blosc 1.x (hdf5-blosc, filter 32001) with
+# the opts of vcf_to_h5.py:135 -- clevel 5, shuffle 1, compcode 2 = LZ4HC -- restated around the STOCK
+# LZ4HC codec of the system liblz4 (the one third-party piece of that writer that is in the image).
+# [third-party, not in /root/reference: c-blosc 1.21.x blosc.c compute_blocksize / split_block /
+#  blosc_c / lz4hc_wrap_compress, published source; hdf5plugin >= 4 bundles it, requirements.txt]
+# --------------------------------------------------------------------------------------------
+def stock_lz4():
+    """ctypes handle of the system liblz4 (LZ4_compress_HC, LZ4_compress_default, LZ4_decompress_safe) or None."""
+    import ctypes.util
+    for name in ("liblz4.so.1", ctypes.util.find_library("lz4")):
+        if not name:
+            continue
+        try:
+            L = C.CDLL(name)
+            L.LZ4_compress_HC.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+            L.LZ4_compress_default.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+            L.LZ4_decompress_safe.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+            return L
+        except (OSError, AttributeError):
+            continue
+    return None
+
+
+def cblosc1_blocksize(nbytes: int, typesize: int, clevel: int = 5, hcr: bool = True) -> int:
+    """blosc.c compute_blocksize for a codec that never splits this typesize (35 > MAX_SPLITS = 16)."""
+    L1 = 32 * 1024
+    if nbytes < typesize:
+        return 1
+    bs = nbytes
+    if nbytes >= L1:
+        bs = L1 * (2 if hcr else 1)
+        bs = {0: bs // 4, 1: bs // 2, 2: bs, 3: bs * 2, 4: bs * 4, 5: bs * 4, 6: bs * 8, 7: bs * 8, 8: bs * 8,
+              9: bs * 8 * (2 if hcr else 1)}[clevel]
+    bs = min(bs, nbytes)
+    if bs > typesize:
+        bs = bs // typesize * typesize
+    return bs
+
+
+def reference_like_chunk(data, typesize: int = 35, clevel: int = 5, hc: bool = True) -> bytes:
+    """The stored HDF5 chunk the reference's writer produces for `data` (one HDF5 chunk of 35-byte records): Blosc1
+    header, bstarts, per block byte-shuffle + one stock LZ4HC(clevel) stream (stored raw where LZ4 does not gain)."""
+    L = stock_lz4()
+    if L is None:
+        raise RuntimeError("no system liblz4")
+    data = bytes(data)
+    n = len(data)
+    bs = cblosc1_blocksize(n, typesize, clevel, hc)
+    nblocks = (n + bs - 1) // bs
+    body, bstarts = b"", []
+    pos = 16 + 4 * nblocks
+    for b in range(nblocks):
+        blk = data[b * bs:(b + 1) * bs]
+        sh = shuffle(blk, typesize).tobytes()
+        out = C.create_string_buffer(len(sh) + 64)
+        # blosc_c: maxout = neblock (+ the codec's slack for LZ4); a stream that does not gain is stored raw
+        cs = (L.LZ4_compress_HC(sh, out, len(sh), len(sh) - 1, clevel) if hc else L.LZ4_compress_default(sh, out, len(sh), len(sh) - 1))
+        payload = out.raw[:cs] if cs > 0 else sh
+        bstarts.append(pos)
+        body += np.int32(len(payload)).tobytes() + payload
+        pos += 4 + len(payload)
+    hdr = bytes([2, 1, 0x01 | 0x10 | (1 << 5), typesize]) + np.array([n, bs, pos], "<u4").tobytes()
+    return hdr + np.array(bstarts, "<u4").tobytes() + body
+
+
+# --------------------------------------------------------------------------------------------
 # h5py auto-chunk heuristic (h5py/_hl/filters.py guess_chunk), restated: vcf_to_h5.py:134-135
 # passes chunks=True.  [third-party, not in /root/reference: h5py >= 3.0, requirements.txt]
 # --------------------------------------------------------------------------------------------

@@ -210,3 +210,59 @@ def test_sample_windows_give_the_same_file_contents(mods, tmp_path):
     win.set_window(2, 3)
     win.rerun(p)                                             # frames only need the planes, not the text
     assert win.sample(0) == allf.sample(2)
+
+
+def test_gpu_decoder_reads_what_the_reference_writer_stores(mods):
+    """Read side against the reference's WRITE side: chunks framed as c-blosc 1.x frames them (hdf5-blosc, clevel 5, shuffle,
+    LZ4HC) around stock liblz4 LZ4HC streams -- one block, several blocks, a leftover block, incompressible data stored raw,
+    tiny chunks -- decode on the GPU to the records."""
+    capi = mods[0]
+    if oracle.stock_lz4() is None:
+        pytest.skip("no system liblz4")
+    rng = np.random.default_rng(11)
+    def records(n):
+        rec = np.zeros(n, dtype=oracle.RECORD_DTYPE)
+        rec["chrom"] = b"chr1"
+        rec["start"] = np.sort(rng.integers(1, 200_000_000, n)); rec["stop"] = rec["start"] + 1
+        rec["ref"] = rng.choice([b"A", b"C", b"G", b"T"], n); rec["alt"] = rng.choice([b"A", b"C", b"G", b"T"], n)
+        rec["phase1"] = rng.random(n) < 0.2; rec["phase2"] = rng.random(n) < 0.2
+        return rec
+    for n in (1075, 8 * 1075 + 13, 5, 30000):
+        datas = [records(n).tobytes() for _ in range(3)] + [rng.integers(0, 256, 35 * n).astype(np.uint8).tobytes()]
+        chunks = [oracle.reference_like_chunk(d) for d in datas]
+        got = capi.decode_frames(chunks, 35 * n)
+        for k, d in enumerate(datas):
+            assert got[k].tobytes() == d
+        if oracle.cblosc1_blocksize(35 * n, 35) == 35 * n:              # single block: the planar view exists too
+            planar = capi.decode_frames(chunks, 35 * n, planar=True)
+            assert planar[0].tobytes() == oracle.shuffle(datas[0], 35).tobytes()
+
+
+def test_full_shape_parity_60000_x_2504(mods):
+    """The bench shape at a size the oracle finishes in seconds: 60,000 variants x 2,504 samples, chunk_records 1075 --
+    the WHOLE genotype matrix and site columns, and every stored chunk of 8 donors, against the oracle."""
+    capi = mods[0]
+    spec = capi.synth_spec(60000, 2504, seed=77, mix=1 << 8)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    ora = oracle.parse_text(text, "*", "chr22")
+    p = capi.Parse.from_host(synth.body_of(text), 2504, region="chr22")
+    assert p.info.n_records == ora["n"] == 60000
+    g0, g1 = p.matrix()
+    assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
+    start, stop, ref, alt = p.sites()
+    assert np.array_equal(start, ora["start"]) and np.array_equal(stop, ora["stop"])
+    assert np.array_equal(ref, ora["ref"]) and np.array_equal(alt, ora["alt"])
+    fr = p.compress(1075)
+    assert fr.info.n_chunks == 56
+    pk, offs, sizes = fr.fetch_packed()
+    for s in (0, 1, 313, 1251, 1252, 2000, 2502, 2503):
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
+        raw = rec.tobytes() + b"\0" * (56 * 1075 * 35 - rec.nbytes)
+        for c in range(56):
+            f = pk[int(offs[s, c]):int(offs[s, c]) + int(sizes[s, c])].tobytes()
+            assert oracle.blosc_chunk_decode(f, 1075 * 35).tobytes() == raw[c * 1075 * 35:(c + 1) * 1075 * 35], (s, c)
+    # and the GPU read side gives the same records back from its own frames
+    s = 1251
+    frames = [pk[int(offs[s, c]):int(offs[s, c]) + int(sizes[s, c])].tobytes() for c in range(56)]
+    rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
+    assert capi.decode_frames(frames, 1075 * 35).reshape(-1)[:rec.nbytes].tobytes() == rec.tobytes()

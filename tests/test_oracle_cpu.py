@@ -150,3 +150,35 @@ def test_dataset_oracle_semantics():
     assert oh.shape == (21, 5) and oh.sum() == 21          # tests/test_utils.py:42-43 intent
     assert oracle.calculate_midpoint_region(10_000_000, 10_001_000, 1000) == (10_000_000, 10_001_000)
     assert oracle.calculate_midpoint_region(100, 300, 1001) == (0, 700)     # clamped at 0, 2*(L//2)
+
+
+def test_blosc1_chunk_codec_against_stock_liblz4():
+    """Filter 32001 stores bare Blosc1 chunks.  The oracle's chunk decoder reads chunks framed the way c-blosc 1.x frames
+    them around STOCK LZ4HC streams (one block below 256 KB, several above), and the oracle's own greedy LZ4 encoder
+    writes streams stock liblz4 accepts."""
+    import ctypes
+    L = oracle.stock_lz4()
+    if L is None:
+        pytest.skip("no system liblz4")
+    rng = np.random.default_rng(3)
+    rec = np.zeros(1075, dtype=oracle.RECORD_DTYPE)
+    rec["chrom"] = b"chr22"
+    rec["start"] = np.sort(rng.integers(10_000_000, 50_000_000, 1075)); rec["stop"] = rec["start"] + 1
+    rec["ref"] = rng.choice([b"A", b"C", b"G", b"T"], 1075); rec["alt"] = rng.choice([b"A", b"C", b"G", b"T"], 1075)
+    rec["phase1"] = rng.random(1075) < 0.1; rec["phase2"] = rng.random(1075) < 0.1
+    for data in (rec.tobytes(), np.tile(rec, 8).tobytes(), rec[:3].tobytes(), rng.integers(0, 256, 35 * 400).astype(np.uint8).tobytes()):
+        for hc in (True, False):
+            c = oracle.reference_like_chunk(data, 35, 5, hc)
+            assert c[:4] == bytes([2, 1, 0x31, 35]) and int.from_bytes(c[12:16], "little") == len(c)
+            assert int.from_bytes(c[8:12], "little") == oracle.cblosc1_blocksize(len(data), 35, 5, hc)
+            assert oracle.blosc_chunk_decode(c, len(data)).tobytes() == data
+        own = oracle.blosc1_chunk_encode(data, 35)
+        assert oracle.blosc_chunk_decode(own, len(data)).tobytes() == data
+        csize = int.from_bytes(own[20:24], "little")
+        if csize != len(data):                                       # an LZ4 stream (not stored raw): stock liblz4 reads it
+            out = ctypes.create_string_buffer(len(data))
+            assert L.LZ4_decompress_safe(own[24:24 + csize], out, csize, len(data)) == len(data)
+            assert out.raw == oracle.shuffle(data, 35).tobytes()
+    assert oracle.cblosc1_blocksize(37625, 35) == 37625 and oracle.cblosc1_blocksize(35 * 30000, 35) == 262115
+    with pytest.raises(ValueError):
+        oracle.blosc_chunk_decode(b"\x09" + oracle.reference_like_chunk(rec.tobytes())[1:], rec.nbytes)
