@@ -592,8 +592,7 @@ def main():
 
           def convert_step():
               q = capi.Parse.from_vcf_bytes(bgp.data_ptr(), region="chr22", device=local, nbytes=nb)
-              q.release_text()
-              fr = q.compress(0)
+                        fr = q.compress(0)
               tot, offs, sizes = fr.fetch_packed(out=(pin.data_ptr(), cap))
               capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.data_ptr() for a in sites]))
               last.update(tot=int(tot), offs=offs, sizes=sizes, n=int(q.info.n_records), ms_inflate=float(q.info.ms_inflate),

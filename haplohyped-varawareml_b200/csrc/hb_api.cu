@@ -104,13 +104,15 @@ using namespace hb;
 
 // ---- big device buffers are pooled.  cudaMalloc / cudaFree of GB-sized buffers take anything from 10 to 500 ms on these
 // hosts (measured inside the streaming entry points); a converter that walks 22 chromosome files, or a caller that makes a
-// parse handle per file, would pay that for the text buffer, both allele planes and every column every time.  Buffers >= 1 MiB
-// that are freed go to an idle list (at most 48 per process) and are handed out again to requests they fit with at most 50 % slack;
-// when a cudaMalloc fails the list is emptied and the call retried; hb_cache_clear() empties it too.
+// parse handle per file, would pay that for the text buffer, both allele planes and every column every time -- and the SMALL
+// ones are no cheaper: r02's trace of the conversion step showed calls stalling 0.2-1.1 s in phases whose only driver work
+// was a handful of cudaMalloc / cudaFree of KB-sized tables.  Every buffer that is freed goes to an idle list (at most 512 per
+// process; sizes are rounded up to 512 bytes) and is handed out again to requests it fits with at most 50 % (or 64 KB) of
+// slack; when a cudaMalloc fails the list is emptied and the call retried; hb_cache_clear() empties it too.
 namespace {
 struct DevPool {
-    static constexpr uint64_t kMin = 1ull << 20;
-    static constexpr size_t kMaxIdle = 48;
+    static constexpr uint64_t kMin = 1;
+    static constexpr size_t kMaxIdle = 512;
     struct Item { void *p; uint64_t bytes; int device; };
     std::mutex mu;
     std::map<void *, Item> live;                 // big allocations handed out
@@ -132,6 +134,7 @@ void dev_pool_flush() {
 cudaError_t dev_pool_alloc(void **out, uint64_t bytes) {
     *out = nullptr;
     if (bytes == 0) bytes = 1;
+    bytes = (bytes + 511) & ~511ull;
     int device = 0;
     cudaGetDevice(&device);
     if (bytes >= DevPool::kMin) {
@@ -139,7 +142,7 @@ cudaError_t dev_pool_alloc(void **out, uint64_t bytes) {
         size_t best = (size_t)-1;
         for (size_t i = 0; i < g_pool.idle.size(); ++i) {
             const auto &it = g_pool.idle[i];
-            if (it.device == device && it.bytes >= bytes && it.bytes <= bytes + bytes / 2 &&
+            if (it.device == device && it.bytes >= bytes && it.bytes <= bytes + std::max<uint64_t>(bytes / 2, 65536) &&
                 (best == (size_t)-1 || it.bytes < g_pool.idle[best].bytes)) best = i;
         }
         if (best != (size_t)-1) {
