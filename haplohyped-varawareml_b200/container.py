@@ -91,6 +91,14 @@ class _MiniFile:
             raise OSError(f"{path}: unsupported filter pipeline {info.filters}")
         return _decode([b for _, b in stored], info.dtype, n, info.chunk)
 
+    def stored_chunks(self, path: str):
+        """The dataset as it is stored: (n_records, chunk_records, dtype, [stored chunk bytes in order]) -- no decoding.
+        None for a dataset that is not a 1-D chunked array behind filter 32001 alone."""
+        info = self._r.dataset_info(path)
+        if info.layout == "contiguous" or [f for f, _ in info.filters] != [FILTER_BLOSC]:
+            return None
+        return int(info.shape[0]), int(info.chunk), info.dtype, [b for _, b in self._r.chunks(info)]
+
     def close(self):
         if self._w is not None:
             self._w.close()
@@ -140,6 +148,14 @@ class _H5pyFile:
         chunk, n = d.chunks[0], d.shape[0]
         frames = [d.id.read_direct_chunk((off,))[1] for off in range(0, n, chunk)]
         return _decode(frames, d.dtype, n, chunk)
+
+    def stored_chunks(self, path: str):
+        d = self._f[path]
+        pl = d.id.get_create_plist()
+        if d.chunks is None or d.ndim != 1 or pl.get_nfilters() != 1 or pl.get_filter(0)[0] != FILTER_BLOSC:
+            return None
+        chunk, n = d.chunks[0], d.shape[0]
+        return int(n), int(chunk), d.dtype, [d.id.read_direct_chunk((off,))[1] for off in range(0, n, chunk)]
 
     def close(self):
         self._f.close()

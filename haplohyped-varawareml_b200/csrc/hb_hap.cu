@@ -51,6 +51,7 @@ template <int CC>   // CC > 0: compile-time class count; 0: runtime
 __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a, const uint64_t *__restrict__ rng, uint32_t ntiles) {
     __shared__ int8_t s_idx[2][HP_TILE];
     __shared__ int8_t s_lut[256];
+    __shared__ uint64_t s_rng[2];
     const int tid = threadIdx.x;
     const uint32_t b = blockIdx.y;
     const uint32_t tile0 = blockIdx.x * HP_TILE;
@@ -77,14 +78,24 @@ __global__ void __launch_bounds__(HP_THREADS) hap_kernel(const hb_hap_batch a, c
     {
         const uint64_t nrec = a.item_nrec[b];
         const uint32_t wend = min(len, tile0 + tn);              // exclusive, window-relative
-        if (nrec && tile0 < wend) {
+        if (nrec && tile0 < wend) {              // (uniform over the CTA: the barrier below is reached by all or none)
             const uint32_t *start = reinterpret_cast<const uint32_t *>(a.item_start[b]);
             const uint8_t *ref = reinterpret_cast<const uint8_t *>(a.item_ref[b]);
             const uint8_t *alt = reinterpret_cast<const uint8_t *>(a.item_alt[b]);
             const int8_t *p1 = reinterpret_cast<const int8_t *>(a.item_p1[b]);
             const int8_t *p2 = reinterpret_cast<const int8_t *>(a.item_p2[b]);
-            // genomic range [ws + tile0, ws + wend)
-            const uint64_t rb = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x], re = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x + 1];
+            // genomic range [ws + tile0, ws + wend): from the pre-kernel's table, or -- short windows, one launch -- searched
+            // here by two threads while the others wait (the table only pays when many tiles share the searches)
+            uint64_t rb, re;
+            if (rng) { rb = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x]; re = rng[(uint64_t)b * (ntiles + 1) + blockIdx.x + 1]; }
+            else {
+                if (tid < 2) {
+                    const uint64_t g = (uint64_t)ws + (tid ? wend : tile0);
+                    s_rng[tid] = g > 0xffffffffull ? nrec : lower_bound_u32(start, 0, nrec, (uint32_t)g);
+                }
+                __syncthreads();
+                rb = s_rng[0]; re = s_rng[1];
+            }
             for (uint64_t r = rb + tid; r < re; r += HP_THREADS) {
                 const uint32_t st = start[r];
                 if (r + 1 < nrec && start[r + 1] == st) continue;   // a later record at the same position wins
@@ -153,22 +164,23 @@ extern "C" int hb_encode_haplotypes(const hb_hap_batch *batch) {
     cudaStream_t st = (cudaStream_t)batch->stream;
     const uint64_t n_rng = (uint64_t)batch->B * (ntiles + 1);
     uint64_t *rng = nullptr;
-    {
+    const bool fused = ntiles <= 2;              // short windows (the reference's default seq_length 1000): ONE launch
+    if (!fused) {
         int dev = 0;
         cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lk(g_rng_mu);
         RangeScratch &sc = g_rng[{dev, st}];
         if (sc.n < n_rng) {
-            if (sc.p) { cudaStreamSynchronize(st); cudaFree(sc.p); sc.p = nullptr; sc.n = 0; }
-            if (cudaMalloc(&sc.p, (n_rng + n_rng / 4 + 64) * 8) != cudaSuccess) return HB_ERR_MEM;
+            if (sc.p) { cudaStreamSynchronize(st); dev_pool_free(sc.p); sc.p = nullptr; sc.n = 0; }
+            if (dev_pool_alloc((void **)&sc.p, (n_rng + n_rng / 4 + 64) * 8) != cudaSuccess) return HB_ERR_MEM;
             sc.n = n_rng + n_rng / 4 + 64;
         }
         rng = sc.p;
     }
-    hap_ranges_kernel<<<(unsigned)((n_rng + 255) / 256), 256, 0, st>>>(*batch, ntiles, rng);
+    if (!fused) hap_ranges_kernel<<<(unsigned)((n_rng + 255) / 256), 256, 0, st>>>(*batch, ntiles, rng);
     if (batch->C == 5) hap_kernel<5><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
     else if (batch->C == 4) hap_kernel<4><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
     else hap_kernel<0><<<grid, HP_THREADS, 0, st>>>(*batch, rng, ntiles);
-    count_launch(2);
+    count_launch(fused ? 1 : 2);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }

@@ -1462,7 +1462,142 @@ decode_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restr
     if (lane == 0) status[wid] = err;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Read side, device in / device out: stored chunks that are RESIDENT in HBM -> record COLUMNS, only
+// for the chunks a batch of windows touches.  One warp per chunk; the LZ4 block is decoded into SHARED memory (a chunk
+// of the reference's layout is 8-100 KB), then the five columns the dataset reads leave as coalesced stores.
+// chunk i = frames[off[i], off[i] + len[i]); its records go to rows [row[i], row[i] + cr) of the output columns.
+// ---------------------------------------------------------------------------------------------
+struct DecodeColsArgs {
+    const uint8_t *frames; const uint64_t *off; const uint32_t *len; const uint64_t *row;
+    uint64_t n; uint32_t cr;
+    uint32_t *start, *stop; uint8_t *ref, *alt; int8_t *p1, *p2;
+    int *status;
+    uint32_t warp_smem;
+};
+
+// LZ4 block decode by one warp into shared memory.  Returns true iff exactly cap bytes came out.
+__device__ bool warp_lz4_decode_smem(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst, uint32_t cap) {
+    const int lane = threadIdx.x & 31;
+    uint32_t ip = 0, op = 0;
+    if (n == 0) return false;
+    for (;;) {
+        if (ip >= n) return false;
+        const uint32_t tok = src[ip++];
+        uint32_t ll = tok >> 4;
+        if (ll == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ll += b; } while (b == 255 && ll <= cap); }
+        if (ll > n - ip || ll > cap - op) return false;
+        for (uint32_t i = lane; i < ll; i += 32) dst[op + i] = src[ip + i];
+        ip += ll; op += ll;
+        if (ip == n) break;
+        if (ip + 2 > n) return false;
+        const uint32_t off = src[ip] | ((uint32_t)src[ip + 1] << 8);
+        ip += 2;
+        if (off == 0 || off > op) return false;
+        uint32_t ml = tok & 15;
+        if (ml == 15) { uint32_t b; do { if (ip >= n) return false; b = src[ip++]; ml += b; } while (b == 255 && ml <= cap); }
+        ml += 4;
+        if (ml > cap - op) return false;
+        __syncwarp();
+        if (off >= ml) {                                // source and destination do not overlap
+            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = dst[op - off + i];
+        } else {                                        // periodic: dst[op + i] = dst[op - off + i % off]; every source precedes op
+            for (uint32_t i = lane; i < ml; i += 32) dst[op + i] = dst[op - off + i % off];
+        }
+        op += ml;
+        __syncwarp();
+    }
+    __syncwarp();
+    return op == cap;
+}
+
+__global__ void __launch_bounds__(128) decode_columns_kernel(const DecodeColsArgs a) {
+    extern __shared__ __align__(16) uint8_t dsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (wid >= a.n) return;
+    uint8_t *t = dsm + (size_t)warp * a.warp_smem;
+    const uint8_t *c = a.frames + a.off[wid];
+    const uint32_t flen = a.len[wid];
+    const uint32_t nbytes = 35u * a.cr;
+    int err = 0;
+    uint32_t flags = 0, bs = 0, ccb = 0, hdr = 16;
+    bool ext = false, shuffle = false;
+    if (flen < 16) err = 1;
+    if (!err) {
+        flags = c[2];
+        const uint32_t cn = ld_le32(c + 4);
+        bs = ld_le32(c + 8); ccb = ld_le32(c + 12);
+        ext = (flags & 1) && (flags & 4);
+        hdr = ext ? 32 : 16;
+        shuffle = !ext && (flags & 1);
+        if (c[0] < 2 || c[0] > 5 || (!ext && (c[0] != 2 || (flags & 0x08)))) err = 2;
+        else if (c[3] != 35 || cn != nbytes || ccb > flen || ccb < hdr) err = 4;
+        else if (!(flags & 2) && bs != cn) err = 11;                 // several blocks per chunk: the host-pointer decoder reads those
+    }
+    if (!err && ext) {
+        for (int i = 0; i < 6; ++i) { if (c[16 + i] == 1) shuffle = true; else if (c[16 + i] != 0) err = 3; }
+        if ((c[31] >> 4) & 7) err = 6;
+    }
+    if (!err && (flags & 2)) {                                       // memcpyed
+        if ((uint64_t)hdr + nbytes > ccb) err = 7;
+        else for (uint32_t i = lane; i < nbytes; i += 32) t[i] = c[hdr + i];
+        shuffle = false;
+    } else if (!err) {
+        if ((flags >> 5) != 1 || (!ext && c[1] != 1)) err = 5;
+        const uint64_t data0 = (uint64_t)hdr + 4;
+        uint64_t ip = 0;
+        if (!err && data0 + 4 > ccb) err = 7;
+        if (!err) { ip = ld_le32(c + hdr); if (ip < data0 || ip + 4 > ccb) err = 7; }
+        if (!err) {
+            const int32_t cs = (int32_t)ld_le32(c + ip);
+            ip += 4;
+            if (cs == 0 && ext) { for (uint32_t i = lane; i < nbytes; i += 32) t[i] = 0; }
+            else if (cs <= 0 || ip + (uint32_t)cs > ccb) err = 8;
+            else if ((uint32_t)cs == nbytes) { for (uint32_t i = lane; i < nbytes; i += 32) t[i] = c[ip + i]; }
+            else if (!warp_lz4_decode_smem(c + ip, (uint32_t)cs, t, nbytes)) err = 9;
+        }
+    }
+    __syncwarp();
+    if (!err) {
+        const uint32_t cr = a.cr;
+        const uint64_t row0 = a.row[wid];
+        // byte f of record r: plane-major when the chunk was byte-shuffled, record-major otherwise
+        for (uint32_t r = lane; r < cr; r += 32) {
+            auto B = [&](uint32_t f) -> uint32_t { return shuffle ? t[f * cr + r] : t[r * 35u + f]; };
+            if (a.start) a.start[row0 + r] = B(5) | (B(6) << 8) | (B(7) << 16) | (B(8) << 24);
+            if (a.stop) a.stop[row0 + r] = B(9) | (B(10) << 8) | (B(11) << 16) | (B(12) << 24);
+            if (a.ref) a.ref[row0 + r] = (uint8_t)B(13);
+            if (a.alt) a.alt[row0 + r] = (uint8_t)B(23);
+            if (a.p1) a.p1[row0 + r] = (int8_t)B(33);
+            if (a.p2) a.p2[row0 + r] = (int8_t)B(34);
+        }
+    }
+    if (lane == 0) a.status[wid] = err;
+}
+
 }  // namespace hb
+
+extern "C" int hb_decode_columns_device(const uint8_t *d_frames, const uint64_t *d_off, const uint32_t *d_len, const uint64_t *d_row,
+                                        uint64_t n_chunks, uint32_t chunk_records, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref,
+                                        uint8_t *d_alt, int8_t *d_p1, int8_t *d_p2, int *d_status, void *stream) {
+    if (!n_chunks) return HB_OK;
+    if (!d_off || !d_len || !d_row || !d_status || !chunk_records) return api_fail(HB_ERR_ARG, "bad argument");
+    const uint64_t nbytes = 35ull * chunk_records;
+    const uint32_t warp_smem = (uint32_t)((nbytes + 15) & ~15ull);
+    int dev = 0, smem_max = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return api_fail(HB_ERR_CUDA, "no CUDA device: libhaplo_b200 has no CPU fallback");
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    smem_max -= 1024;
+    if (nbytes > (uint64_t)smem_max) return api_fail(HB_ERR_ARG, "chunk too large for the device-side decoder (use hb_decode_frames)");
+    const int warps = (int)std::max<uint64_t>(1, std::min<uint64_t>(4, (uint64_t)smem_max / warp_smem));
+    DecodeColsArgs a{d_frames, d_off, d_len, d_row, n_chunks, chunk_records, d_start, d_stop, d_ref, d_alt, d_p1, d_p2, d_status, warp_smem};
+    cudaFuncSetAttribute(decode_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    decode_columns_kernel<<<(unsigned)((n_chunks + warps - 1) / warps), warps * 32, (size_t)warps * warp_smem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return api_fail(HB_ERR_CUDA, "decode_columns_kernel launch failed");
+    return HB_OK;
+}
 
 extern "C" int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, uint64_t n_frames,
                                 uint64_t chunk_nbytes, uint8_t *out, int planar, int device) {

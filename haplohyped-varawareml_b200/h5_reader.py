@@ -28,5 +28,13 @@ class VCFH5Reader:
             return self.hdf5_file.read_dataset(group_path + "/snp_data")
         raise KeyError(f"No data found for {group_path}")
 
+    def stored_chunks(self, donor_id, chromosome):
+        """The stored (compressed) chunks of donor_{id}/chr_{n}/snp_data, undecoded: (n_records, chunk_records, dtype,
+        [bytes]) or None when the dataset is not stored that way.  What the dataset's device-resident store keeps."""
+        group_path = f"donor_{donor_id}/chr_{chromosome}"
+        if group_path in self.hdf5_file:
+            return self.hdf5_file.stored_chunks(group_path + "/snp_data")
+        raise KeyError(f"No data found for {group_path}")
+
     def close(self):
         self.hdf5_file.close()

@@ -82,6 +82,14 @@ class ReferenceGenome:
             self._h5.close()
 
 
+class _Stored:
+    """One dataset as the file stores it, resident in HBM: blob (uint8 tensor) + per-chunk offsets / sizes (host)."""
+    __slots__ = ("blob", "offs", "sizes", "n", "cr")
+
+    def __init__(self, blob, offs, sizes, n, cr):
+        self.blob, self.offs, self.sizes, self.n, self.cr = blob, offs, sizes, n, cr
+
+
 class GenotypeStore:
     """(donor, chromosome) -> device columns (start u32 sorted, ref u8, alt u8, phase1 i8, phase2 i8).
 
@@ -94,6 +102,9 @@ class GenotypeStore:
         self._cols = {}
         self._reader = None
         self._parses = {}
+        self._stored = {}          # (donor, chrom) -> _Stored | None
+        self._first = {}           # (chrom, n_records, chunk_records) -> first start of every chunk
+        self.last_status = []
 
     @classmethod
     def from_reader(cls, reader, device="cuda:0"):
@@ -121,6 +132,122 @@ class GenotypeStore:
         return (t(rec["start"].astype(np.uint32).view(np.int32)), t(ref), t(alt),
                 t(rec["phase1"].astype(np.int8)), t(rec["phase2"].astype(np.int8)), len(rec))
 
+    # ---- compressed-resident datasets: the stored chunks of a (donor, chromosome) dataset stay in HBM as
+    # they are in the file; a batch decodes, on the device, only the chunks its windows touch.  The reference reads and
+    # decodes the whole dataset for every item (h5_reader.py:37-41, haplotype_dataset.py:71): O(chromosome) per item.
+    def _compressed(self, donor, chrom: int):
+        """-> _Stored of the dataset, uploading its stored chunks on first use; None when the file does not store it as
+        single-block Blosc chunks (then `columns` decodes it whole, once)."""
+        key = (donor, chrom)
+        if key in self._stored:
+            return self._stored[key]
+        st = None
+        got = self._reader.stored_chunks(donor, chrom) if (self._reader is not None and hasattr(self._reader, "stored_chunks")) else None
+        if got is not None:
+            n, cr, dtype, chunks = got
+            if dtype.itemsize == 35 and n > 0 and 35 * cr <= 200 * 1024:
+                sizes = np.array([len(c) for c in chunks], np.uint32)
+                offs = np.zeros(len(chunks), np.uint64)
+                offs[1:] = np.cumsum((sizes[:-1].astype(np.uint64) + 15) // 16 * 16)
+                blob = np.zeros(int(offs[-1]) + int(sizes[-1]) + 64, np.uint8)
+                for o, c in zip(offs, chunks):
+                    blob[int(o):int(o) + len(c)] = np.frombuffer(c, np.uint8)
+                st = _Stored(torch.from_numpy(blob).to(self.device), offs, sizes, n, cr)
+        self._stored[key] = st
+        return st
+
+    def _chunk_first(self, chrom: int, st):
+        """First `start` of every chunk of the chromosome (host, sorted): built once per (chromosome, geometry) by decoding
+        the start column of the first dataset seen -- every donor of a cohort file has the same sites (one VCF per
+        chromosome, vcf_to_h5.py:182-207), so it serves all of them."""
+        key = (chrom, st.n, st.cr)
+        if key not in self._first:
+            nck = len(st.sizes)
+            start = torch.empty(nck * st.cr, dtype=torch.int32, device=self.device)
+            status = self._decode(st, np.arange(nck), np.arange(nck, dtype=np.uint64) * st.cr, start=start)
+            if bool(status.any().item()):         # e.g. several Blosc blocks per chunk: this file is read whole instead
+                self._first[key] = None
+            else:
+                self._first[key] = start[::st.cr].cpu().numpy().view(np.uint32).astype(np.int64)
+        return self._first[key]
+
+    def _decode(self, st, chunk_ids, rows, start=None, ref=None, alt=None, p1=None, p2=None, frames=None, offs=None, lens=None):
+        """hb_decode_columns_device on chunks `chunk_ids` of one stored dataset (or on pre-built device lists)."""
+        dev = self.device
+        n = len(chunk_ids)
+        if offs is None:
+            base = st.blob.data_ptr()
+            offs = torch.from_numpy((st.offs[chunk_ids]).astype(np.int64)).to(dev)
+            lens = torch.from_numpy(st.sizes[chunk_ids].view(np.int32)).to(dev)
+            frames = base
+        rows_t = torch.from_numpy(np.asarray(rows, np.uint64).view(np.int64)).to(dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        capi.check(capi.lib().hb_decode_columns_device(frames, offs.data_ptr(), lens.data_ptr(), rows_t.data_ptr(), n, st.cr,
+                                                       ptr(start), None, ptr(ref), ptr(alt), ptr(p1), ptr(p2), status.data_ptr(),
+                                                       torch.cuda.current_stream(dev).cuda_stream))
+        return status
+
+    def window_columns(self, items):
+        """items: [(donor, chrom, new_start, new_end)] -> per item (addr_start, addr_ref, addr_alt, addr_p1, addr_p2, n_records)
+        covering at least every record with new_start <= start < new_end, decoded on the device from the resident
+        stored chunks in ONE launch for the whole batch; `keep` (second result) must outlive the kernel that reads them.
+        Items whose dataset is not kept compressed fall back to `columns`."""
+        dev = self.device
+        self.check_last()
+        plan, out = [], [None] * len(items)
+        for b, (donor, chrom, ws, we) in enumerate(items):
+            st = None if chrom in self._parses or (donor, chrom) in self._cols else self._compressed(donor, chrom)
+            if st is None:
+                out[b] = self.columns(donor, chrom)
+                continue
+            first = self._chunk_first(chrom, st)
+            if first is None:
+                self._stored[(donor, chrom)] = None
+                out[b] = self.columns(donor, chrom)
+                continue
+            c0 = max(0, int(np.searchsorted(first, ws, "left")) - 1)
+            c1 = max(c0, int(np.searchsorted(first, we, "left")) - 1)
+            plan.append((b, st, c0, c1))
+        keep = None
+        if plan:
+            by_cr = {}
+            for b, st, c0, c1 in plan:
+                by_cr.setdefault(st.cr, []).append((b, st, c0, c1))
+            keep = []
+            for cr, group in by_cr.items():
+                tot = sum(c1 - c0 + 1 for _, _, c0, c1 in group)
+                addr = np.empty(tot, np.uint64); lens = np.empty(tot, np.uint32); rows = np.empty(tot, np.uint64)
+                k = 0
+                spans = []
+                for b, st, c0, c1 in group:
+                    m = c1 - c0 + 1
+                    addr[k:k + m] = np.uint64(st.blob.data_ptr()) + st.offs[c0:c1 + 1]
+                    lens[k:k + m] = st.sizes[c0:c1 + 1]
+                    rows[k:k + m] = (np.arange(m, dtype=np.uint64) + np.uint64(k)) * np.uint64(cr)
+                    spans.append((b, k, m, min(st.n - c0 * cr, m * cr)))
+                    k += m
+                start = torch.empty(tot * cr, dtype=torch.int32, device=dev)
+                ref = torch.empty(tot * cr, dtype=torch.uint8, device=dev); alt = torch.empty_like(ref)
+                p1 = torch.empty(tot * cr, dtype=torch.int8, device=dev); p2 = torch.empty_like(p1)
+                # chunk addresses are absolute: frames base 0, offsets = device addresses
+                offs_t = torch.from_numpy(addr.view(np.int64)).to(dev)
+                lens_t = torch.from_numpy(lens.view(np.int32)).to(dev)
+                status = self._decode(group[0][1], range(tot), rows, start, ref, alt, p1, p2, frames=0, offs=offs_t, lens=lens_t)
+                keep.append((start, ref, alt, p1, p2, offs_t, lens_t, status))
+                for b, k0, m, nrec in spans:
+                    o = k0 * cr
+                    out[b] = (start.data_ptr() + 4 * o, ref.data_ptr() + o, alt.data_ptr() + o, p1.data_ptr() + o, p2.data_ptr() + o, int(nrec))
+            self.last_status = [t[-1] for t in keep]
+        return out, keep
+
+    def check_last(self):
+        """Raise if a chunk of the previous batch did not decode (checked one batch late: no sync on the hot path)."""
+        bad = [t for t in self.last_status if bool(t.any().item())]
+        self.last_status = []
+        if bad:
+            raise OSError("corrupt or unsupported stored chunk in the genotype file (device decode status %d)" % int(bad[0].max().item()))
+
     def columns(self, donor, chrom: int):
         """-> (addr_start, addr_ref, addr_alt, addr_p1, addr_p2, n_records) device addresses."""
         if chrom in self._parses:
@@ -144,6 +271,8 @@ class GenotypeStore:
             self._reader.close()
         self._cols.clear()
         self._parses.clear()
+        self._stored.clear()
+        self._first.clear()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,8 +378,11 @@ class RandomHaplotypeDataset(Dataset):
     def encode_items(self, items):
         L = 2 * (self.seq_length // 2)
         B = len(items)
-        seq_addr, lens, ws, cols = [], [], [], []
+        seq_addr, lens, ws = [], [], []
         keep = []
+        # record columns of every item: decoded on the device from the resident stored chunks, window-limited
+        cols, keep_cols = self.genotypes.window_columns([(d, c, a, e) for c, d, a, e in items])
+        keep.append(keep_cols)
         for chrom, donor_id, new_start, new_end in items:
             seq = self.reference_genome.device_sequence(f"chr{chrom}")
             keep.append(seq)
@@ -259,7 +391,6 @@ class RandomHaplotypeDataset(Dataset):
             seq_addr.append(seq.data_ptr() + min(new_start, n))
             lens.append(min(ln, L))
             ws.append(new_start)
-            cols.append(self.genotypes.columns(donor_id, chrom))
         return _launch(B, L, len(self.encode_spec), seq_addr, lens, ws, cols, self.lut, self.device)
 
     def __getitem__(self, idx):

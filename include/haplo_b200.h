@@ -235,6 +235,17 @@ void hb_set_site_matcher(int deep);
  * planar != 0 keeps the byte-shuffled plane layout (single-block chunks).  Host pointers. */
 int hb_decode_frames(const uint8_t *frames, const uint64_t *offsets, uint64_t n_frames, uint64_t chunk_nbytes,
                      uint8_t *out, int planar, int device);
+/* The same read, DEVICE in and DEVICE out, for the dataset (haplotype_dataset.py:71 reads a whole (donor, chromosome)
+ * dataset per item; here only the chunks a window touches are decoded, and nothing crosses PCIe): n_chunks stored
+ * `snp_data` chunks resident in device memory -- chunk i = d_frames[d_off[i] .. d_off[i] + d_len[i]); with d_frames == NULL
+ * d_off[i] is the chunk's device address itself, so one call serves chunks of many datasets -- are decoded into
+ * record COLUMNS: the chunk_records records of chunk i go to rows [d_row[i], d_row[i] + chunk_records) of d_start /
+ * d_stop (uint32), d_ref / d_alt (first byte of the S10 field), d_p1 / d_p2 (int8); any column may be NULL.
+ * d_status[i] = 0 or a non-zero code (corrupt or unsupported chunk; 11 = several Blosc blocks per chunk, which
+ * hb_decode_frames reads).  Asynchronous on `stream` (the current device's); all pointers are device pointers. */
+int hb_decode_columns_device(const uint8_t *d_frames, const uint64_t *d_off, const uint32_t *d_len, const uint64_t *d_row,
+                             uint64_t n_chunks, uint32_t chunk_records, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref,
+                             uint8_t *d_alt, int8_t *d_p1, int8_t *d_p2, int *d_status, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * D. Dataset: batched on-the-fly haplotype construction, replacing

@@ -168,3 +168,60 @@ def test_fasta_encoder_to_dataset(mods, tmp_path):
     assert np.array_equal(rg.encode_sequence(np.frombuffer(s.encode(), "|S1")), oracle.onehot(idx, 5))
     with pytest.raises(TypeError):
         rg.encode_sequence([1, 2])
+
+
+def test_dataset_reads_windows_from_compressed_resident_file(mods, tmp_path):
+    """Row f4: the dataset on a cohort .h5 -- stored chunks stay compressed in HBM, a batch decodes ON THE DEVICE only the
+    chunks its windows touch (chunk choice by binary search on the per-chunk first positions), no record crosses PCIe.
+    Same tensors as the oracle built from the full record arrays."""
+    capi, hd, cu = mods
+    from haplohyped_varawareml_b200 import container, h5_reader
+    text, samples = synth.random_vcf(5000, 6, seed=14, fmt="GT", kinds="mixed", site_mix=False)
+    ora = oracle.parse_text(text, "*", "chr22")
+    p = capi.Parse.from_host(synth.body_of(text), len(samples), region="chr22")
+    cr = 64
+    fr = p.compress(cr)
+    n = int(p.info.n_records)
+    path = str(tmp_path / "cohort.h5")
+    records = {}
+    with container.open_h5(path, "w", backend="minih5") as f:
+        for s, name in enumerate(samples):
+            frames = fr.sample(s)
+            rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
+            for c in range(1, 23):
+                f.write_chunked(f"donor_{name}/chr_{c}/snp_data", oracle.RECORD_DTYPE, n, cr, frames)
+                records[(name, c)] = rec
+    lo, hi = int(ora["start"].min()), int(ora["start"].max())
+    rng = np.random.default_rng(2)
+    seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=hi + 30000)
+    seqs = {f"chr{c}": seq for c in range(1, 23)}
+    (tmp_path / "samples.txt").write_text("\n".join(samples))
+    bed = tmp_path / "r.bed"
+    bed.write_text("".join(f"chr22\t{s}\t{s + 1000}\n" for s in list(rng.integers(lo, hi, 14)) + [lo - 400, hi - 100]))
+    for L, B in ((1000, 32), (20000, 8)):
+        ds = hd.RandomHaplotypeDataset(str(bed), path, None, str(tmp_path / "samples.txt"), batch_size=B, seq_length=L,
+                                       reference_genome=hd.ReferenceGenome(sequences=seqs))
+        store = ds.genotypes
+        for it in range(2):
+            items = ds.draw()
+            hap1, hap2 = ds.encode_items(items)
+            e1, e2 = _expected(items, seqs, records, L, oracle.parse_encode_dict(None))
+            assert np.array_equal(hap1.cpu().numpy(), e1) and np.array_equal(hap2.cpu().numpy(), e2)
+        store.check_last()
+        assert store._stored and all(v is not None for v in store._stored.values())     # kept compressed, never read whole
+        assert not store._cols
+        # window-limited: an item's columns cover a few chunks, not the chromosome
+        cols, keep = store.window_columns([(samples[0], 22, lo + 5000, lo + 5000 + L)])
+        span = (ora["start"] >= lo + 5000) & (ora["start"] < lo + 5000 + L)
+        assert cols[0][5] <= (int(span.sum()) // cr + 3) * cr and cols[0][5] < n
+        ds.close()
+    # a damaged stored chunk is reported, not decoded into garbage
+    st = hd.GenotypeStore.from_reader(h5_reader.VCFH5Reader(path))
+    sd = st._compressed(samples[1], 7)
+    st._chunk_first(7, sd)
+    sd.blob[int(sd.offs[3]) + 30:int(sd.offs[3]) + 60] = 0xFF
+    first = st._first[(7, sd.n, sd.cr)]
+    st.window_columns([(samples[1], 7, int(first[3]), int(first[3]) + 10)])
+    with pytest.raises(OSError):
+        st.check_last()
+    st.close()
