@@ -287,6 +287,67 @@ def leg_dataset(capi, torch, dev, peak):
     return out
 
 
+def leg_dataset_store(capi, torch, dev, local, peak, V=400_000, S=64):
+    """Row f4 end to end: a cohort's stored chunks resident in HBM (converter output, compressed) -> per batch the device decodes
+    only the chunks its windows touch (hb_decode_columns_device) -> kernel 5.  Times one whole batch, host work included."""
+    import numpy as np
+    from haplohyped_varawareml_b200 import haplotype_dataset as hd
+    spec = capi.synth_spec(V, S, seed=7, chrom="chr22", mix=AF_SKEW_HEADLINE)
+    T = int(capi.lib().hb_synth_body_bytes(spec))
+    text = torch.empty(T + 256, dtype=torch.uint8, device=dev)
+    text[T:].zero_()
+    capi.check(capi.lib().hb_synth_device(spec, text.data_ptr(), T, local, None))
+    torch.cuda.synchronize()
+    p = capi.Parse.from_device(text.data_ptr(), T, S, region="chr22", device=local)
+    fr = p.compress(0)
+    names = capi.synth_sample_names(spec)
+    store = hd.GenotypeStore(dev)
+    for c in range(1, 23):
+        store.add_frames(c, fr, names)
+    start = p.sites()[0]
+    lo, hi = int(start.min()), int(start.max())
+    rng = np.random.default_rng(3)
+    seq = torch.from_numpy(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=hi + 200_000)).to(dev)
+    rg = hd.ReferenceGenome(sequences={}, device=dev)
+    for c in range(1, 23):
+        rg._dev[f"chr{c}"] = seq
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "s.txt"), "w") as f:
+        f.write("\n".join(names))
+    with open(os.path.join(tmp, "r.bed"), "w") as f:
+        f.write("".join("chr22\t%d\t%d\n" % (a, a + 1000) for a in rng.integers(lo, hi, 4096)))
+    out = []
+    for B, L in ((32, 1000), (1024, 1000), (32, 131072), (1024, 131072)):
+        ds = hd.RandomHaplotypeDataset(os.path.join(tmp, "r.bed"), None, None, os.path.join(tmp, "s.txt"), batch_size=B, seq_length=L,
+                                       device=dev, genotype_store=store, reference_genome=rg)
+        for _ in range(2):
+            h = ds[0]
+        torch.cuda.synchronize()
+        del h
+        t, nchunks = [], 0
+        for _ in range(3 if B * L > 1e8 else 10):
+            t0 = time.perf_counter()
+            h1, h2 = ds[0]
+            torch.cuda.synchronize()
+            t.append(1e3 * (time.perf_counter() - t0))
+            del h1, h2
+        items = ds.draw()
+        cols, keep = store.window_columns([(d, c, a, e) for c, d, a, e in items])
+        nchunks = sum(k[5].numel() for k in keep) if keep else 0
+        torch.cuda.synchronize()
+        ms = sorted(t)[len(t) // 2]
+        alg = B * L + 2.0 * B * L * 5 * 4
+        out.append({"B": B, "L": L, "ms_per_batch": ms, "item_us": 1e3 * ms / B, "chunks_decoded_per_batch": int(nchunks),
+                    "chunks_per_dataset": int(fr.info.n_chunks), "gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak})
+    crec = int(fr.info.chunk_records)
+    store.close()
+    fr.close(); p.close()
+    return {"what": "RandomHaplotypeDataset.__getitem__ on a compressed-resident cohort (%d variants x %d donors, chunk %d records): draw + chunk "
+                    "selection (host) + hb_decode_columns_device + hb_encode_haplotypes, wall clock per batch; the reference decodes the whole "
+                    "(donor, chromosome) dataset per item" % (V, S, crec), "rows": out}
+
+
 def leg_config3(args, capi, torch, dist, dev, local, rank, world, shard):
     """configs[2]: the whole genome, sharded by chromosome (LPT), strong scaling; kernels only (text resident, handles
     allocated and warmed outside the timed region)."""
@@ -592,7 +653,7 @@ def main():
 
           def convert_step():
               q = capi.Parse.from_vcf_bytes(bgp.data_ptr(), region="chr22", device=local, nbytes=nb)
-                        fr = q.compress(0)
+              fr = q.compress(0)
               tot, offs, sizes = fr.fetch_packed(out=(pin.data_ptr(), cap))
               capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.data_ptr() for a in sites]))
               last.update(tot=int(tot), offs=offs, sizes=sizes, n=int(q.info.n_records), ms_inflate=float(q.info.ms_inflate),
@@ -711,7 +772,8 @@ def main():
     if not args.no_extra and not args.parse_only:
         for name, fn in (("config3", lambda: leg_config3(args, capi, torch, dist, dev, local, rank, world, shard)),
                          ("general_text", lambda: leg_general_text(capi, torch, dev, local, peak, S=S) if rank == 0 else None),
-                         ("dataset", lambda: leg_dataset(capi, torch, dev, peak) if rank == 0 else None)):
+                         ("dataset", lambda: leg_dataset(capi, torch, dev, peak) if rank == 0 else None),
+                         ("dataset_store", lambda: leg_dataset_store(capi, torch, dev, local, peak) if rank == 0 else None)):
             try:
                 extra[name] = fn()
             except Exception as ex:

@@ -82,6 +82,16 @@ class ReferenceGenome:
             self._h5.close()
 
 
+class _DevAddr:
+    """A device address that is kept alive by something else (quacks like a tensor for data_ptr())."""
+
+    def __init__(self, addr, owner):
+        self._addr, self._owner = int(addr), owner
+
+    def data_ptr(self):
+        return self._addr
+
+
 class _Stored:
     """One dataset as the file stores it, resident in HBM: blob (uint8 tensor) + per-chunk offsets / sizes (host)."""
     __slots__ = ("blob", "offs", "sizes", "n", "cr")
@@ -123,6 +133,14 @@ class GenotypeStore:
     def add_parse(self, chrom: int, parse, sample_names):
         """Zero-copy: columns of a capi.Parse (kept alive by this store)."""
         self._parses[chrom] = (parse, {n: i for i, n in enumerate(sample_names)})
+
+    def add_frames(self, chrom: int, frames, sample_names):
+        """Zero-copy: the stored chunks of every sample of a capi.Frames handle (kept alive by this store) serve as the
+        compressed-resident datasets of `chrom` -- converter output used straight from HBM."""
+        i = frames.info
+        offs, sizes = frames.layout()
+        for s, name in enumerate(sample_names):
+            self._stored[(name, chrom)] = _Stored(_DevAddr(i.d_frames, frames), offs[s].copy(), sizes[s].copy(), int(i.n_records), int(i.chunk_records))
 
     def _upload(self, rec):
         dev = self.device
