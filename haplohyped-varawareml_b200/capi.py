@@ -71,7 +71,7 @@ class SynthSpec(C.Structure):
 EXPORTS = [
     "hb_last_error", "hb_version", "hb_kernel_launches",
     "hb_load_vcf", "hb_load_vcf_without_sample", "hb_records_free", "hb_cache_clear", "hb_cache_set_limit",
-    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_stream_bgzf_host", "hb_bgzf_vcf_info", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
+    "hb_parse_host_text", "hb_parse_stream_host", "hb_parse_stream_bgzf_host", "hb_parse_stream_bgzf_resident", "hb_parse_set_text_limit", "hb_bgzf_vcf_info", "hb_parse_device_text", "hb_parse_file", "hb_parse_vcf_bytes", "hb_parse_samples", "hb_parse_rerun", "hb_parse_rerun_bytes", "hb_parse_get_info",
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
@@ -99,6 +99,8 @@ def lib():
         L.hb_records_free.argtypes = [C.POINTER(Records)]
         L.hb_cache_set_limit.argtypes = [C.c_uint64]
         L.hb_cache_set_limit.restype = None
+        L.hb_parse_set_text_limit.argtypes = [C.c_uint64]
+        L.hb_parse_set_text_limit.restype = None
         L.hb_parse_host_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_stream_host.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -107,6 +109,8 @@ def lib():
         L.hb_parse_stream_bgzf_host.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
                                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.hb_parse_stream_bgzf_resident.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p),
+                                                    C.POINTER(C.c_uint32)]
         L.hb_parse_device_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]
         L.hb_parse_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.hb_parse_vcf_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -227,6 +231,21 @@ class Parse:
         check(lib().hb_parse_vcf_bytes(addr, n, (region or "").encode(), int(want_gt), device, C.byref(h)))
         del keep
         return cls(h)
+
+    @classmethod
+    def from_vcf_bytes_streamed(cls, data, region="", want_gt=True, device=0, slab_bytes=0, nbytes=None):
+        """BGZF bytes of a .vcf.gz -> the same resident parse as from_vcf_bytes, but the text passes through HBM slab by slab
+        (hb_parse_stream_bgzf_resident).  Returns (Parse, n_slabs)."""
+        if isinstance(data, (bytes, bytearray)):
+            keep = np.frombuffer(data, np.uint8); addr, n = keep.ctypes.data, keep.size
+        elif isinstance(data, np.ndarray):
+            keep = data; addr, n = data.ctypes.data, data.size
+        else:
+            keep = None; addr, n = int(data), int(nbytes)
+        h, ns = C.c_void_p(), C.c_uint32()
+        check(lib().hb_parse_stream_bgzf_resident(addr, n, (region or "").encode(), int(want_gt), device, slab_bytes, C.byref(h), C.byref(ns)))
+        del keep
+        return cls(h), int(ns.value)
 
     def sample_names(self):
         n, ln = C.c_uint32(), C.c_uint64()

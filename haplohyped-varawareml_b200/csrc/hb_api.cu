@@ -31,6 +31,7 @@ namespace hb {
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_text_limit{0};      // hb_parse_set_text_limit: 0 = from free device memory
 void count_launch(uint64_t n) { g_launches += n; }
 
 static int fail(int code, const std::string &msg) {
@@ -120,6 +121,14 @@ struct DevPool {
 } g_pool;
 }
 namespace hb {
+uint64_t dev_pool_idle_bytes() {                 // on the current device
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    uint64_t sum = 0;
+    for (const auto &it : g_pool.idle) if (it.device == cur) sum += it.bytes;
+    return sum;
+}
 void dev_pool_flush() {
     std::vector<DevPool::Item> items;
     {
@@ -1222,6 +1231,19 @@ int parse_bytes_common(std::vector<uint8_t> &raw_owned, const uint8_t *raw_p, ui
     FileText ft;
     TRY(bgzf_header(raw.data(), coff, clen, olen, ft));
     samples = ft.samples;
+    {   // a file whose text does not fit HBM next to its genotype planes passes through in slabs instead: same rows, same
+        // handle minus the text (hb_parse_stream_bgzf_resident)
+        TRY(ensure_device(device));
+        uint64_t limit = g_text_limit.load();
+        const uint64_t slab = limit ? std::max<uint64_t>(limit / 2, 1 << 16) : 0;      // two slabs of text are resident at a time
+        if (!limit) {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); fr = 0; }
+            // GT-only text is ~4 bytes per call, the planes + bit planes it leaves 2.125: text + 0.55 x text must fit
+            limit = (uint64_t)(0.9 * (double)(fr + hb::dev_pool_idle_bytes()) / 1.55);
+        }
+        if (total > limit) return hb_parse_stream_bgzf_resident(raw_p, raw_n, region, want_gt ? 1 : 0, device, slab, out, nullptr);
+    }
     o.n_samples = (uint32_t)ft.samples.size();
     o.end_is_int = ft.end_is_int;
     hb_parse *p = nullptr;
@@ -1467,6 +1489,8 @@ void hb_cache_set_limit(uint64_t hbm_bytes) {
     if (hbm_bytes) cache_evict(hbm_bytes, nullptr);
 }
 
+void hb_parse_set_text_limit(uint64_t text_bytes) { g_text_limit.store(text_bytes); }
+
 void hb_cache_clear(void) {
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1511,10 +1535,17 @@ int hb_bgzf_vcf_info(const uint8_t *bgzf, uint64_t nbytes, uint32_t *n_samples, 
 // BGZF bytes in host memory -> results in host memory, streamed: slabs of whole BGZF members cross PCIe compressed,
 // are inflated on the GPU behind the unfinished last line of the slab before, parsed up to their own last newline and
 // fetched -- H2D + inflate of slab k + 1 and the D2H of slab k - 1 run while slab k is parsed.
-int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
-                              uint64_t slab_bytes, int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start,
-                              uint32_t *stop, char *ref, char *alt, uint32_t *ploidy_err, uint32_t *badgt_err,
-                              uint64_t *n_records, uint32_t *n_slabs) {
+namespace {
+// where the rows of a parsed slab go: host arrays (hb_parse_stream_bgzf_host) or the growing planes of ONE resident parse
+// (hb_parse_stream_bgzf_resident).  deliver() enqueues copies on s.d2h (the slot's compute stream is idle by then).
+struct SlabSink {
+    virtual ~SlabSink() {}
+    virtual int begin(const hb_parse_opts &opts, const std::vector<std::string> &samples, uint64_t total_text) { (void)opts; (void)samples; (void)total_text; return HB_OK; }
+    virtual int deliver(StreamSlot &s, uint64_t R, uint64_t n, uint64_t slab_text, cudaError_t &e) = 0;
+};
+}
+static int stream_bgzf(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device, uint64_t slab_bytes,
+                       SlabSink &sink, uint32_t *ploidy_err, uint32_t *badgt_err, uint64_t *n_records, uint32_t *n_slabs) {
     if (!bgzf || !n_records) return fail(HB_ERR_ARG, "null argument");
     *n_records = 0;
     if (n_slabs) *n_slabs = 0;
@@ -1538,6 +1569,8 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
     opts.end_is_int = ft.end_is_int;
     if (ploidy_err) memset(ploidy_err, 0, 4ull * opts.n_samples);
     if (badgt_err) memset(badgt_err, 0, 4ull * opts.n_samples);
+    TRY(ensure_device(device));
+    TRY(sink.begin(opts, ft.samples, total));
     if (total <= ft.body) return HB_OK;
     if (slab_bytes == 0) slab_bytes = 1ull << 30;
     // slabs of whole members, about slab_bytes of text each
@@ -1671,16 +1704,9 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
             if (rc != HB_OK) break;
             n = s.p->h_st.n_records;
         }
-        if (R + n > out_stride && (gt0 || gt1 || start || stop || ref || alt)) { rc = fail(HB_ERR_ARG, "more records than the output arrays hold"); break; }
         if (n) {
-            if (opts.want_gt && opts.n_samples && s.p->d_gt[0]) {
-                if (gt0) e = cudaMemcpy2DAsync(gt0 + R, out_stride, s.p->d_gt[0], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
-                if (gt1 && e == cudaSuccess) e = cudaMemcpy2DAsync(gt1 + R, out_stride, s.p->d_gt[1], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
-            }
-            if (start && e == cudaSuccess) e = cudaMemcpyAsync(start + R, s.p->d_start, n * 4, cudaMemcpyDeviceToHost, s.d2h);
-            if (stop && e == cudaSuccess) e = cudaMemcpyAsync(stop + R, s.p->d_stop, n * 4, cudaMemcpyDeviceToHost, s.d2h);
-            if (ref && e == cudaSuccess) e = cudaMemcpyAsync(ref + R, s.p->d_ref, n, cudaMemcpyDeviceToHost, s.d2h);
-            if (alt && e == cudaSuccess) e = cudaMemcpyAsync(alt + R, s.p->d_alt, n, cudaMemcpyDeviceToHost, s.d2h);
+            rc = sink.deliver(s, R, n, s.p->nbytes, e);
+            if (rc != HB_OK) break;
             if ((ploidy_err || badgt_err) && opts.want_gt && opts.n_samples && e == cudaSuccess) {
                 e = cudaMemcpyAsync(pl.data(), s.p->d_ploidy, 4ull * opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(bg.data(), s.p->d_badgt, 4ull * opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
@@ -1706,6 +1732,162 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
     if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
     *n_records = R;
     if (n_slabs) *n_slabs = (uint32_t)slabs.size();
+    return HB_OK;
+}
+
+namespace {
+struct HostSink : SlabSink {
+    int8_t *gt0, *gt1; uint64_t out_stride; uint32_t *start, *stop; char *ref, *alt;
+    hb_parse_opts opts{};
+    int begin(const hb_parse_opts &o, const std::vector<std::string> &, uint64_t) override { opts = o; return HB_OK; }
+    int deliver(StreamSlot &s, uint64_t R, uint64_t n, uint64_t, cudaError_t &e) override {
+        if (R + n > out_stride && (gt0 || gt1 || start || stop || ref || alt)) return fail(HB_ERR_ARG, "more records than the output arrays hold");
+        if (opts.want_gt && opts.n_samples && s.p->d_gt[0]) {
+            if (gt0) e = cudaMemcpy2DAsync(gt0 + R, out_stride, s.p->d_gt[0], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+            if (gt1 && e == cudaSuccess) e = cudaMemcpy2DAsync(gt1 + R, out_stride, s.p->d_gt[1], s.p->gt_stride, n, opts.n_samples, cudaMemcpyDeviceToHost, s.d2h);
+        }
+        if (start && e == cudaSuccess) e = cudaMemcpyAsync(start + R, s.p->d_start, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+        if (stop && e == cudaSuccess) e = cudaMemcpyAsync(stop + R, s.p->d_stop, n * 4, cudaMemcpyDeviceToHost, s.d2h);
+        if (ref && e == cudaSuccess) e = cudaMemcpyAsync(ref + R, s.p->d_ref, n, cudaMemcpyDeviceToHost, s.d2h);
+        if (alt && e == cudaSuccess) e = cudaMemcpyAsync(alt + R, s.p->d_alt, n, cudaMemcpyDeviceToHost, s.d2h);
+        return HB_OK;
+    }
+};
+
+// The rows of every slab appended to ONE resident parse: genotype planes and site columns grow in HBM (2.5 bytes per call),
+// the text never holds more than two slabs.  The result is the handle a whole-file parse would have given (without its
+// text): same rows, so hb_compress_records cuts it into the same HDF5 chunks -- chunk boundaries do not see slab boundaries.
+struct ResidentSink : SlabSink {
+    hb_parse *big = nullptr;
+    uint64_t total_text = 0, text_seen = 0, cap = 0;
+    std::vector<uint32_t> ploidy, badgt;
+    ~ResidentSink() override { if (big) hb_parse_free(big); }
+    int begin(const hb_parse_opts &o, const std::vector<std::string> &samples, uint64_t total) override {
+        total_text = total;
+        hb_parse_opts oo = o;
+        oo.stream = nullptr;
+        TRY(new_parse(&oo, &big));
+        big->samples = samples;
+        big->text_released = true;             // there is no text to re-run on
+        return HB_OK;
+    }
+    int grow(uint64_t need, cudaStream_t st, uint64_t R) {          // capacity for `need` rows, the R rows present are kept
+        const uint32_t S = big->n_samples;
+        const uint64_t stride = (need + 127) / 128 * 128;
+        struct { uint32_t *start, *stop; uint8_t *ref, *alt; uint64_t *chrom5; int8_t *gt[2]; uint32_t *bits; uint64_t gt_stride; } old =
+            {big->d_start, big->d_stop, big->d_ref, big->d_alt, big->d_chrom5, {big->d_gt[0], big->d_gt[1]}, big->d_bits, big->gt_stride};
+        cudaDeviceSynchronize();                   // (rare) copies of the other slot into the old planes are done
+        big->d_start = big->d_stop = nullptr; big->d_ref = big->d_alt = nullptr; big->d_chrom5 = nullptr;
+        big->d_gt[0] = big->d_gt[1] = nullptr; big->d_bits = nullptr;
+        int rc = dev_alloc(&big->d_start, stride);
+        if (rc == HB_OK) rc = dev_alloc(&big->d_stop, stride);
+        if (rc == HB_OK) rc = dev_alloc(&big->d_ref, stride);
+        if (rc == HB_OK) rc = dev_alloc(&big->d_alt, stride);
+        if (rc == HB_OK) rc = dev_alloc(&big->d_chrom5, stride);
+        if (rc == HB_OK && big->want_gt && S) {
+            rc = dev_alloc(&big->d_gt[0], stride * S);
+            if (rc == HB_OK) rc = dev_alloc(&big->d_gt[1], stride * S);
+            if (rc == HB_OK) rc = dev_alloc(&big->d_bits, stride / 128 * kBitGroupWords * S);
+        }
+        cudaError_t e = cudaSuccess;
+        if (rc == HB_OK && R) {
+            e = cudaMemcpyAsync(big->d_start, old.start, R * 4, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_stop, old.stop, R * 4, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_ref, old.ref, R, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_alt, old.alt, R, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_chrom5, old.chrom5, R * 8, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess && old.gt[0]) e = cudaMemcpy2DAsync(big->d_gt[0], stride, old.gt[0], old.gt_stride, R, S, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess && old.gt[1]) e = cudaMemcpy2DAsync(big->d_gt[1], stride, old.gt[1], old.gt_stride, R, S, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        free_dev(old.start); free_dev(old.stop); free_dev(old.ref); free_dev(old.alt); free_dev(old.chrom5);
+        free_dev(old.gt[0]); free_dev(old.gt[1]); free_dev(old.bits);
+        if (rc != HB_OK) return rc;
+        if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+        big->gt_stride = stride; big->gt_bytes = stride * S; big->bits_stride = stride / 128 * kBitGroupWords; big->row_cap = stride;
+        cap = stride;
+        return HB_OK;
+    }
+    int deliver(StreamSlot &s, uint64_t R, uint64_t n, uint64_t slab_text, cudaError_t &e) override {
+        text_seen += slab_text;
+        if (R + n > cap) {
+            // rows per byte seen so far, extrapolated to the whole file (+ 3 %): the planes are allocated once for most files
+            const double per = (double)(R + n) / (double)std::max<uint64_t>(1, text_seen);
+            uint64_t need = (uint64_t)(per * (double)total_text * 1.03) + 4096;
+            need = std::max(need, R + n);
+            e = cudaStreamSynchronize(s.d2h);
+            if (e != cudaSuccess) return HB_OK;
+            TRY(grow(need, s.d2h, R));
+        }
+        const uint32_t S = big->n_samples;
+        if (big->want_gt && S && s.p->d_gt[0]) {
+            e = cudaMemcpy2DAsync(big->d_gt[0] + R, big->gt_stride, s.p->d_gt[0], s.p->gt_stride, n, S, cudaMemcpyDeviceToDevice, s.d2h);
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(big->d_gt[1] + R, big->gt_stride, s.p->d_gt[1], s.p->gt_stride, n, S, cudaMemcpyDeviceToDevice, s.d2h);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_start + R, s.p->d_start, n * 4, cudaMemcpyDeviceToDevice, s.d2h);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_stop + R, s.p->d_stop, n * 4, cudaMemcpyDeviceToDevice, s.d2h);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_ref + R, s.p->d_ref, n, cudaMemcpyDeviceToDevice, s.d2h);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_alt + R, s.p->d_alt, n, cudaMemcpyDeviceToDevice, s.d2h);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_chrom5 + R, s.p->d_chrom5, n * 8, cudaMemcpyDeviceToDevice, s.d2h);
+        // CHROM runs of the slab continue the file's
+        for (size_t i = 0; i < s.p->run_rows.size(); ++i) {
+            if (!big->run_names.empty() && big->run_names.back() == s.p->run_names[i]) continue;
+            big->run_rows.push_back(R + s.p->run_rows[i]);
+            big->run_names.push_back(s.p->run_names[i]);
+        }
+        big->n_lines += s.p->n_lines;
+        big->h_st.n_nonuniform += s.p->h_st.n_nonuniform; big->h_st.n_bad_gt += s.p->h_st.n_bad_gt;
+        big->h_st.n_nogt += s.p->h_st.n_nogt;
+        big->index_used = s.p->index_used;
+        big->walker_fallbacks += s.p->walker_fallbacks;
+        big->ms_tok += s.p->ms_tok; big->ms_sites += s.p->ms_sites; big->ms_decode += s.p->ms_decode;
+        return HB_OK;
+    }
+};
+}  // namespace
+
+int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
+                              uint64_t slab_bytes, int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start,
+                              uint32_t *stop, char *ref, char *alt, uint32_t *ploidy_err, uint32_t *badgt_err,
+                              uint64_t *n_records, uint32_t *n_slabs) {
+    HostSink sink;
+    sink.gt0 = gt0; sink.gt1 = gt1; sink.out_stride = out_stride; sink.start = start; sink.stop = stop; sink.ref = ref; sink.alt = alt;
+    return stream_bgzf(bgzf, nbytes, region, want_gt, device, slab_bytes, sink, ploidy_err, badgt_err, n_records, n_slabs);
+}
+
+int hb_parse_stream_bgzf_resident(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
+                                  uint64_t slab_bytes, hb_parse **out, uint32_t *n_slabs) {
+    if (!out) return fail(HB_ERR_ARG, "null argument");
+    *out = nullptr;
+    ResidentSink sink;
+    uint64_t n = 0;
+    uint32_t S = 0;
+    {   // per-sample error counts are summed on the host and put on the device at the end
+        uint64_t tb = 0, bo = 0;
+        TRY(hb_bgzf_vcf_info(bgzf, nbytes, &S, &tb, &bo));
+    }
+    sink.ploidy.assign(S ? S : 1, 0); sink.badgt.assign(S ? S : 1, 0);
+    TRY(stream_bgzf(bgzf, nbytes, region, want_gt, device, slab_bytes, sink, sink.ploidy.data(), sink.badgt.data(), &n, n_slabs));
+    hb_parse *p = sink.big;
+    if (!p) return fail(HB_ERR_IO, "empty input");
+    cudaError_t e = cudaSuccess;
+    if (want_gt && S) {
+        int rc = dev_alloc(&p->d_ploidy, S);
+        if (rc == HB_OK) rc = dev_alloc(&p->d_badgt, S);
+        if (rc != HB_OK) return rc;
+        e = cudaMemcpy(p->d_ploidy, sink.ploidy.data(), 4ull * S, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_badgt, sink.badgt.data(), 4ull * S, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && n && p->d_gt[0]) {                 // the allele bit planes kernel 4b reads, from the assembled byte planes
+            Launch L{p->stream, p->sm_count};
+            launch_bits_from_planes(p->d_gt[0], p->d_gt[1], p->gt_stride, n, S, p->d_bits, p->bits_stride, L);
+            e = cudaStreamSynchronize(p->stream);
+        }
+    }
+    if (e != cudaSuccess) return fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+    p->h_st.n_records = n;
+    p->compressed_bytes = nbytes;
+    sink.big = nullptr;
+    *out = p;
     return HB_OK;
 }
 

@@ -373,4 +373,38 @@ void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t 
     count_launch();
 }
 
+// The allele bit planes (hb_internal.h, kBitGroupWords) of byte planes that were not written by the decoder above:
+// the resident streamed parse assembles its planes from slabs with device copies.  One thread = 32 rows of one sample.
+__global__ void __launch_bounds__(256)
+bits_from_planes_kernel(const int8_t *__restrict__ gt0, const int8_t *__restrict__ gt1, uint64_t gt_stride, uint64_t n_rows,
+                        uint32_t n_samples, uint32_t *__restrict__ bits, uint64_t bits_stride) {
+    const uint64_t words = (n_rows + 31) / 32;                  // 32-row words per sample
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words * n_samples) return;
+    const uint64_t s = i / words, w = i - s * words;
+    uint32_t out[4] = {0, 0, 0, 0};                             // B0, B1, N0, N1
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const uint4 *src = reinterpret_cast<const uint4 *>((p ? gt1 : gt0) + s * gt_stride + 32 * w);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint4 v = ldg_stream(src + h);
+            const uint32_t b = pack_lsb4(v.x) | (pack_lsb4(v.y) << 4) | (pack_lsb4(v.z) << 8) | (pack_lsb4(v.w) << 12);
+            const uint32_t nz = pack_nz4(v.x) | (pack_nz4(v.y) << 4) | (pack_nz4(v.z) << 8) | (pack_nz4(v.w) << 12);
+            out[p] |= b << (16 * h);
+            out[2 + p] |= nz << (16 * h);
+        }
+    }
+    uint32_t *row = bits + s * bits_stride + (w >> 2) * kBitGroupWords + (w & 3);
+    row[0] = out[0]; row[4] = out[1]; row[8] = out[2]; row[12] = out[3];
+}
+
+void launch_bits_from_planes(const int8_t *d_gt0, const int8_t *d_gt1, uint64_t gt_stride, uint64_t n_rows, uint32_t n_samples,
+                             uint32_t *d_bits, uint64_t bits_stride, const Launch &L) {
+    if (!n_rows || !n_samples) return;
+    const uint64_t n = (n_rows + 31) / 32 * n_samples;
+    bits_from_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(d_gt0, d_gt1, gt_stride, n_rows, n_samples, d_bits, bits_stride);
+    count_launch();
+}
+
 }  // namespace hb

@@ -99,12 +99,16 @@ void launch_decode_gt(const uint8_t *d_text, const RowInfo *d_rowinfo, uint64_t 
                       uint32_t *d_bits, uint64_t bits_stride, uint32_t *d_ploidy_err, uint32_t *d_badgt_err, DevStatus *d_st,
                       const Launch &L);
 
+void launch_bits_from_planes(const int8_t *d_gt0, const int8_t *d_gt1, uint64_t gt_stride, uint64_t n_rows, uint32_t n_samples,
+                             uint32_t *d_bits, uint64_t bits_stride, const Launch &L);
+
 void count_launch(uint64_t n = 1);
 
 // pooled big device buffers (hb_api.cu): cudaMalloc / cudaFree of GB-sized buffers are slow and erratic on these hosts
 cudaError_t dev_pool_alloc(void **out, uint64_t bytes);
 void dev_pool_free(void *p);
 void dev_pool_flush();
+uint64_t dev_pool_idle_bytes();
 
 // device -> host memory of any kind, synchronous: pinned destinations directly, pageable ones through pinned staging
 bool host_is_pinned(const void *p);

@@ -136,6 +136,17 @@ int hb_parse_stream_bgzf_host(const uint8_t *bgzf, uint64_t nbytes, const char *
                               uint64_t slab_bytes, int8_t *gt0, int8_t *gt1, uint64_t out_stride, uint32_t *start,
                               uint32_t *stop, char *ref, char *alt, uint32_t *ploidy_err, uint32_t *badgt_err,
                               uint64_t *n_records, uint32_t *n_slabs);
+/* The same streamed read, but the rows of every slab are appended to ONE device-resident parse: genotype planes and site
+ * columns grow in HBM (2.5 bytes per call) while the text never holds more than two slabs.  *out is the handle a whole-
+ * file hb_parse_vcf_bytes would have given, minus its text (hb_parse_rerun is refused): the same rows, so
+ * hb_compress_records cuts them into the same HDF5 chunks -- `chunks=True` on the whole dataset (vcf_to_h5.py:135) --
+ * and chunk boundaries never see slab boundaries.  For files whose text does not fit HBM next to the planes. */
+int hb_parse_stream_bgzf_resident(const uint8_t *bgzf, uint64_t nbytes, const char *region, int want_gt, int device,
+                                  uint64_t slab_bytes, hb_parse **out, uint32_t *n_slabs);
+/* hb_parse_file / hb_parse_vcf_bytes / hb_load_vcf take that streamed route by themselves when the text of a BGZF file
+ * would not fit the device next to its planes (text > 0.9 x free / 1.55).  text_bytes != 0 sets the threshold explicitly
+ * (bound the HBM a parse may take; tests); 0 = automatic. */
+void hb_parse_set_text_limit(uint64_t text_bytes);
 /* sample names of a file-level parse, NUL-separated */
 int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */

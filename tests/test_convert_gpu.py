@@ -266,3 +266,44 @@ def test_full_shape_parity_60000_x_2504(mods):
     frames = [pk[int(offs[s, c]):int(offs[s, c]) + int(sizes[s, c])].tobytes() for c in range(56)]
     rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
     assert capi.decode_frames(frames, 1075 * 35).reshape(-1)[:rec.nbytes].tobytes() == rec.tobytes()
+
+
+def test_file_larger_than_the_text_budget_converts_to_the_same_file(mods, tmp_path):
+    """A .vcf.gz whose text does not fit HBM next to its planes takes the streamed-resident route inside hb_parse_file /
+    hb_load_vcf (hb_parse_set_text_limit forces it here): the .h5 the converter writes is byte-identical to the whole-file
+    one -- chunk geometry of the whole dataset (vcf_to_h5.py:135), no chunk boundary at a slab boundary -- and load_vcf
+    returns the same tuples."""
+    capi, container, h5_reader, hd, v2h = mods
+    import sys
+    sys.path.insert(0, os.path.dirname(capi.__file__))
+    import parse_vcf
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    text, samples = synth.random_vcf(5200, 19, seed=77, fmt="GT", kinds="mixed", chrom="chr9", site_mix=True)
+    path = vdir / "chr9.filtered.vcf.gz"
+    path.write_bytes(synth.bgzf_compress(text, 6))
+    (tmp_path / "donors.txt").write_text("\n".join(samples))
+    blobs, tuples = {}, {}
+    try:
+        for limit in (0, 64 << 10):
+            capi.lib().hb_parse_set_text_limit(limit)
+            capi.lib().hb_cache_clear()
+            out = tmp_path / f"o{limit}"
+            conv = v2h.VCFtoHDF5Converter("c", str(vdir), str(out), str(tmp_path / "donors.txt"), 2, 4, chromosomes=[9])
+            conv.run()
+            assert conv.stats["datasets"] == 19
+            blobs[limit] = (out / "c.h5").read_bytes()
+            tuples[limit] = parse_vcf.load_vcf(str(path), samples[3], "chr9")
+            h = capi.Parse.from_file(str(path), region="chr9")
+            if limit:
+                assert h.info.text_bytes == 0                   # the streamed route was taken: no text is resident
+                with pytest.raises(capi.HaploError):
+                    h.rerun()
+            else:
+                h.rerun()
+            h.close()
+    finally:
+        capi.lib().hb_parse_set_text_limit(0)
+        capi.lib().hb_cache_clear()
+    assert blobs[0] == blobs[64 << 10]
+    assert tuples[0] == tuples[64 << 10] == oracle.load_vcf(str(path), samples[3], "chr9")

@@ -134,3 +134,41 @@ def test_stream_bgzf_host_edges(capi):
     r = capi.parse_stream_bgzf_host(synth.bgzf_compress(text), capacity=4000, region="chr22", slab_bytes=len(text) // 7)
     assert r["n"] == ora["n"] and r["n_slabs"] >= 7
     assert np.array_equal(r["gt0"], ora["gt0"]) and np.array_equal(r["gt1"], ora["gt1"]) and np.array_equal(r["start"], ora["start"])
+
+
+def test_streamed_resident_parse_gives_the_whole_file_chunks(capi):
+    """Chunk continuity across slabs: a .vcf.gz streamed through HBM in >= 5 slabs (hb_parse_stream_bgzf_resident) gives the
+    same resident parse as the whole-file call -- same matrix, site columns, CHROM runs, per-sample errors -- and therefore
+    byte-identical stored chunks with the whole file's h5py chunk geometry (vcf_to_h5.py:135, chunks=True on the whole
+    dataset): no chunk boundary sees a slab boundary."""
+    text, samples = synth.random_vcf(9000, 41, seed=23, fmt="GT", kinds="mixed")
+    bg = capi.bgzf_compress_host(text, 6)
+    whole = capi.Parse.from_vcf_bytes(bg, region="chr22")
+    for slab in (len(text) // 7 + 1, 150_000):
+        streamed, n_slabs = capi.Parse.from_vcf_bytes_streamed(bg, region="chr22", slab_bytes=slab)
+        assert n_slabs >= 5
+        assert streamed.info.n_records == whole.info.n_records and streamed.info.n_lines == whole.info.n_lines
+        assert streamed.sample_names() == whole.sample_names() == samples
+        for a, b in zip(streamed.matrix(), whole.matrix()):
+            assert np.array_equal(a, b)
+        for a, b in zip(streamed.sites(), whole.sites()):
+            assert np.array_equal(a, b)
+        assert streamed.chrom_column() == whole.chrom_column()
+        for a, b in zip(streamed.sample_errors(), whole.sample_errors()):
+            assert np.array_equal(a, b)
+        for cr in (0, 100):
+            fw, fs = whole.compress(cr), streamed.compress(cr)
+            assert fs.info.chunk_records == fw.info.chunk_records and fs.info.n_chunks == fw.info.n_chunks
+            bw, ow, zw = fw.fetch_packed()
+            bs, os_, zs = fs.fetch_packed()
+            assert np.array_equal(zw, zs) and np.array_equal(ow, os_) and np.array_equal(bw, bs)      # byte-identical frames
+            fw.close(); fs.close()
+        with pytest.raises(capi.HaploError):
+            streamed.rerun()                                   # there is no text to parse again
+        streamed.close()
+    # no region filter, sites only
+    s2, _ = capi.Parse.from_vcf_bytes_streamed(bg, region="", want_gt=False, slab_bytes=200_000)
+    w2 = capi.Parse.from_vcf_bytes(bg, region="", want_gt=False)
+    assert s2.info.n_records == w2.info.n_records and s2.chrom_column() == w2.chrom_column()
+    for a, b in zip(s2.sites(), w2.sites()):
+        assert np.array_equal(a, b)
