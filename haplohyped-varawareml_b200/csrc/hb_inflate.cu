@@ -11,6 +11,14 @@
 //   * LZ77 copies are done by all 32 lanes (sources always precede the current output position, so the
 //     32-byte pieces of one match are independent), literals are stored by lane 0.
 // Stored and fixed-Huffman blocks are handled too.  CRC32 is not checked; ISIZE is.
+//
+// Round 2 tried to remove the 32-fold redundant decode (profiles/r02g_inflate_experiments.txt): a thread per member with
+// tables in shared memory and an aligned-word byte FIFO (bit-exact, 5 of 32 lanes active on average: copy paths diverge),
+// and lanes decoding 32 members with the warp copying their matches round by round (bit-exact, 8x fewer instructions, but
+// ~10 K cycles of latency per round on the critical path of the heaviest member: 16-20 ms per GB-sized slab against 4.5
+// here).  Both lose to this kernel at the slab sizes the streaming path uses, so it stays; what was kept from them:
+// one aligned word per refill, length / distance bases computed instead of looked up, runs copied without a per-byte
+// modulo, loads of a match issued before its stores, 48 resident warps per SM.
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,10 +34,6 @@ namespace hb {
 constexpr int kLitBits = 10, kDistBits = 8;       // primary table widths; longer codes take the canonical slow path
 constexpr int kInfWarps = 8;
 
-__constant__ uint16_t c_lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct HuffTab {            // one canonical Huffman code, in shared memory
@@ -40,16 +44,23 @@ struct HuffTab {            // one canonical Huffman code, in shared memory
 };
 
 struct BitReader {          // identical in every lane of the warp
-    const uint8_t *src;
-    uint32_t ip, n;         // next byte, payload bytes
+    const uint32_t *wp;     // next aligned word of the payload
+    uint32_t cur, sh;       // the word before it; bit offset of the stream inside a word
+    uint32_t ip, n;         // payload bytes fetched / available
     uint64_t bb;
     int bc;
+    __device__ __forceinline__ void seek(const uint8_t *src, uint32_t at) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src + at);
+        wp = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        sh = (uint32_t)(a & 3) * 8u;
+        cur = __ldg(wp++);
+        ip = at; bb = 0; bc = 0;
+    }
     __device__ __forceinline__ void refill() {
         if (bc <= 32) {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(src + ip);
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
-            const uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8u);   // may read past n: the buffer has slack
-            bb |= (uint64_t)v << bc;
+            const uint32_t nxt = __ldg(wp++);                 // may read past n: the buffer has slack
+            bb |= (uint64_t)__funnelshift_r(cur, nxt, sh) << bc;
+            cur = nxt;
             bc += 32;
             ip += 4;
         }
@@ -152,7 +163,7 @@ struct InflateArgs {
 
 constexpr int kInfSmemPerWarp = 2 * (1 << kLitBits) + 2 * (1 << kDistBits) + 2 * 288 + 2 * 32 + 2 * 16 * 3 + 2 * 16 + 320 + 2 * 128 + 2 * 19 + 2 * 16 + 26;
 
-__global__ void __launch_bounds__(kInfWarps * 32) inflate_bgzf_kernel(const InflateArgs a) {
+__global__ void __launch_bounds__(kInfWarps * 32, 6) inflate_bgzf_kernel(const InflateArgs a) {
     __shared__ __align__(16) uint8_t smem[kInfWarps][(kInfSmemPerWarp + 15) & ~15];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t blk = blockIdx.x * kInfWarps + warp;
@@ -173,9 +184,9 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_bgzf_kernel(const Infl
     lit.bits = kLitBits; dist.bits = kDistBits; cl.bits = 7;
 
     BitReader br;
-    br.src = a.comp + a.coff[blk];
+    const uint8_t *src = a.comp + a.coff[blk];
     br.n = a.clen[blk];
-    br.ip = 0; br.bb = 0; br.bc = 0;
+    br.seek(src, 0);
     uint8_t *out = a.out + a.ooff[blk];
     const uint32_t olen = a.olen[blk];
     uint32_t op = 0;
@@ -192,9 +203,9 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_bgzf_kernel(const Infl
             // bytes still in the bit buffer belong to the stored data
             const uint32_t pos = br.ip - (uint32_t)(br.bc >> 3);
             if (pos + len > br.n || op + len > olen) { err = 2; break; }
-            for (uint32_t i = lane; i < len; i += 32) out[op + i] = br.src[pos + i];
+            for (uint32_t i = lane; i < len; i += 32) out[op + i] = src[pos + i];
             op += len;
-            br.ip = pos + len; br.bb = 0; br.bc = 0;
+            br.seek(src, pos + len);
             __syncwarp();
             continue;
         }
@@ -255,16 +266,41 @@ __global__ void __launch_bounds__(kInfWarps * 32) inflate_bgzf_kernel(const Infl
             if (sym == 256) break;
             sym -= 257;
             if (sym >= 29) { err = 14; break; }
-            const uint32_t len = c_lbase[sym] + br.take(c_lext[sym]);
+            uint32_t len;                                  // RFC 1951 3.2.5, computed instead of looked up
+            if (sym < 8) len = 3 + sym;
+            else if (sym == 28) len = 258;
+            else { const int eb = (sym >> 2) - 1; len = 3 + ((4 + (sym & 3)) << eb) + br.take(eb); }
             br.refill();
             const int ds = decode_sym(dist, br);
             if (ds < 0 || ds >= 30) { err = 15; break; }
-            const uint32_t d = c_dbase[ds] + br.take(c_dext[ds]);
+            uint32_t d;
+            if (ds < 4) d = 1 + ds;
+            else { const int eb = (ds >> 1) - 1; d = 1 + ((2 + (ds & 1)) << eb) + br.take(eb); }
             if (d > op || op + len > olen) { err = 16; break; }
             __syncwarp();                                  // earlier stores of the warp are visible to the loads below
-            const uint8_t *from = out + op - d;
-            if (d >= len) { for (uint32_t i = lane; i < len; i += 32) out[op + i] = __ldcg(from + i); }
-            else { for (uint32_t i = lane; i < len; i += 32) out[op + i] = __ldcg(from + i % d); }
+            uint8_t *to = out + op;
+            const uint8_t *from = to - d;
+            if (d >= len) {                                // no overlap: independent 32-byte pieces, three loads in flight
+                for (uint32_t base = 0; base < len; base += 96) {
+                    uint8_t v[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const uint32_t i = base + 32 * k + lane; v[k] = i < len ? __ldcg(from + i) : (uint8_t)0; }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { const uint32_t i = base + 32 * k + lane; if (i < len) to[i] = v[k]; }
+                }
+            } else if (d < 32) {                           // a run of period d (the "0|0\t" of genotype text is d = 4, len = 258):
+                const uint32_t D = d * (32u / d);          // a lane's byte repeats every D = the largest multiple of d <= 32
+                if ((uint32_t)lane < D) {
+                    const uint8_t b = __ldcg(from + (uint32_t)lane % d);
+                    for (uint32_t i = lane; i < len; i += D) to[i] = b;
+                }
+            } else {                                       // 32 <= d < len: each 32 bytes read what the ones before stored
+                for (uint32_t r = 0; r < len; r += 32) {
+                    const uint32_t i = r + lane;
+                    if (i < len) to[i] = __ldcg(from + i);
+                    __syncwarp();
+                }
+            }
             op += len;
         }
         if (br.overrun()) err = 17;
