@@ -23,6 +23,7 @@ from __future__ import annotations
 import logging
 import os
 import shutil
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional
@@ -108,7 +109,7 @@ class _ChromParse:
 class VCFtoHDF5Converter:
     def __init__(self, cohort_name: str, vcf_dir: str, out_dir: str, sample_list_path: str, cores: int,
                  cxx_threads: int, device: int = 0, chromosomes=None, backend: Optional[str] = None,
-                 sample_window: Optional[int] = None):
+                 sample_window: Optional[int] = None, devices: Optional[List[int]] = None):
         self.cohort_name = cohort_name
         self.vcf_dir = vcf_dir
         self.out_dir = out_dir
@@ -116,6 +117,11 @@ class VCFtoHDF5Converter:
         self.cores = cores
         self.cxx_threads = cxx_threads            # kept for interface parity; a no-op in the reference too
         self.device = device
+        # several GPUs of one box: the chromosome files are bin-packed onto them by size (shard.plan_shards, the reference's
+        # fan-out is executor.map over donors, :191-192); every GPU parses and compresses its own files, the datasets go into
+        # the one output file under a lock -- no genotype byte ever moves between GPUs
+        self.devices = [int(d) for d in devices] if devices else [device]
+        self._wlock = threading.RLock()
         self.backend = backend
         self.sample_window = sample_window        # None: as many samples per frames pass as free HBM allows
         self.donor_ids = self.read_sample_list(sample_list_path)
@@ -139,16 +145,24 @@ class VCFtoHDF5Converter:
 
     # -- output file, opened lazily so that single-call use of genotype_vcf_to_hdf5 works too
     def _final(self):
-        if self._out is None:
-            os.makedirs(self.out_dir, exist_ok=True)
-            self._out = open_h5(os.path.join(self.out_dir, f"{self.cohort_name}.h5"), "w", backend=self.backend)
-        return self._out
+        with self._wlock:
+            if self._out is None:
+                os.makedirs(self.out_dir, exist_ok=True)
+                self._out = open_h5(os.path.join(self.out_dir, f"{self.cohort_name}.h5"), "w", backend=self.backend)
+            return self._out
 
-    def _chrom_parse(self, data_path: str, chromosome: int) -> _ChromParse:
-        cp = self._chrom.get(chromosome)
+    def _count(self, **kw):
+        with self._wlock:
+            for k, v in kw.items():
+                self.stats[k] += v
+
+    def _chrom_parse(self, data_path: str, chromosome: int, device: Optional[int] = None) -> _ChromParse:
+        with self._wlock:
+            cp = self._chrom.get(chromosome)
         if cp is None:
-            cp = _ChromParse(data_path, chromosome, self.device, self.sample_window)
-            self._chrom[chromosome] = cp
+            cp = _ChromParse(data_path, chromosome, self.device if device is None else device, self.sample_window)
+            with self._wlock:
+                self._chrom[chromosome] = cp
         return cp
 
     def genotype_vcf_to_hdf5(self, data_path: str, donor_id: str, chromosome: int) -> None:
@@ -159,24 +173,23 @@ class VCFtoHDF5Converter:
                 cp = self._chrom_parse(data_path, chromosome)
                 frames = cp.donor_frames(donor_id)
                 chunk = cp.chunk_records or int(capi.lib().hb_guess_chunk_records(max(1, cp.n_records)))
-                self._final().write_chunked(f"donor_{donor_id}/chr_{chromosome}/snp_data", RECORD_DTYPE, cp.n_records,
-                                            chunk, frames)
-                self.stats["datasets"] += 1
-                self.stats["records"] += cp.n_records
-                self.stats["stored_bytes"] += sum(len(f) for f in frames)
+                with self._wlock:
+                    self._final().write_chunked(f"donor_{donor_id}/chr_{chromosome}/snp_data", RECORD_DTYPE, cp.n_records,
+                                                chunk, frames)
+                self._count(datasets=1, records=cp.n_records, stored_bytes=sum(len(f) for f in frames))
                 logger.info(f"Finished processing VCF file for donor {donor_id} and chromosome {chromosome}")
         except Exception as e:
             logger.error(f"An error occurred while processing VCF file: {e}")
             raise
 
-    def process_chromosome(self, chromosome: int) -> None:
+    def process_chromosome(self, chromosome: int, device: Optional[int] = None) -> None:
         """All donors of one chromosome file: one GPU parse + one compression pass."""
         vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
         if not os.path.exists(vcf_file):
             logger.warning(f"{vcf_file} does not exist; chromosome {chromosome} skipped")
-            self.stats["skipped_files"] += 1
+            self._count(skipped_files=1)
             return
-        cp = self._chrom_parse(vcf_file, chromosome)
+        cp = self._chrom_parse(vcf_file, chromosome, device)
         good = [d for d in self.donor_ids if d in cp.index and not cp.badgt_err[cp.index[d]] and not cp.ploidy_err[cp.index[d]]]
         bulk = cp.n_records > 0 and len(good) * 4 >= len(cp.samples) and hasattr(self._final(), "write_frames_bulk")
         if bulk:
@@ -189,11 +202,10 @@ class VCFtoHDF5Converter:
                 fr = cp.frames_for(s0, ns)
                 buf, offs, sizes = fr.fetch_packed()            # gathered on the device: no slot padding crosses PCIe or reaches the file
                 rows = [cp.index[d] - s0 for d in mine]
-                self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in mine], RECORD_DTYPE,
-                                                cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])
-                self.stats["datasets"] += len(mine)
-                self.stats["records"] += cp.n_records * len(mine)
-                self.stats["stored_bytes"] += int(sizes[rows].sum())
+                with self._wlock:
+                    self._final().write_frames_bulk([f"donor_{d}/chr_{chromosome}/snp_data" for d in mine], RECORD_DTYPE,
+                                                    cp.n_records, cp.chunk_records, buf, offs[rows], sizes[rows])
+                self._count(datasets=len(mine), records=cp.n_records * len(mine), stored_bytes=int(sizes[rows].sum()))
                 del buf
         done = set(good) if bulk else set()
         for donor_id in self.donor_ids:
@@ -204,8 +216,9 @@ class VCFtoHDF5Converter:
             except capi.HaploError:
                 raise                                   # the file itself is unreadable / malformed
             except RuntimeError:
-                self.stats["skipped_donors"] += 1       # this donor only (unknown, haploid, bad GT)
-        cp = self._chrom.pop(chromosome, None)
+                self._count(skipped_donors=1)           # this donor only (unknown, haploid, bad GT)
+        with self._wlock:
+            cp = self._chrom.pop(chromosome, None)
         if cp is not None:
             cp.close()
 
@@ -237,17 +250,10 @@ class VCFtoHDF5Converter:
             for c in self.chromosomes:
                 if c not in present:
                     logger.warning(f"chr{c}.filtered.vcf.gz does not exist in {self.vcf_dir}; skipped")
-            # one chromosome ahead, no more: the parse of the next file (file read + H2D + GPU inflate + kernels) overlaps
-            # the frames / D2H / file write of the current one, and at most two chromosomes' genotype planes are in HBM
-            with ThreadPoolExecutor(max_workers=1) as executor:
-                nxt = executor.submit(self._safe_parse, present[0]) if present else None
-                for k, c in enumerate(present):
-                    cp = nxt.result()
-                    nxt = executor.submit(self._safe_parse, present[k + 1]) if k + 1 < len(present) else None
-                    if cp is None:
-                        continue
-                    self._chrom[c] = cp
-                    self.process_chromosome(c)
+            if len(self.devices) > 1 and len(present) > 1:
+                self._run_devices(present)
+            else:
+                self._run_files(present, self.devices[0])
             merge_start_time = time.time()
             self.merge_h5_files()
             end_time = time.time()
@@ -265,15 +271,57 @@ class VCFtoHDF5Converter:
                 self._out = None
             shutil.rmtree(self.tmp_dir, ignore_errors=True)
 
-    def _safe_parse(self, chromosome: int):
+    def _run_files(self, files: List[int], device: int) -> None:
+        """The chromosome files of one GPU, in order.  One chromosome ahead, no more: the parse of the next file (file read +
+        H2D + GPU inflate + kernels) overlaps the frames / D2H / file write of the current one, and at most two chromosomes'
+        genotype planes are in HBM."""
+        with ThreadPoolExecutor(max_workers=1) as executor:
+            nxt = executor.submit(self._safe_parse, files[0], device) if files else None
+            for k, c in enumerate(files):
+                cp = nxt.result()
+                nxt = executor.submit(self._safe_parse, files[k + 1], device) if k + 1 < len(files) else None
+                if cp is None:
+                    continue
+                with self._wlock:
+                    self._chrom[c] = cp
+                self.process_chromosome(c, device)
+
+    def plan_devices(self, files: List[int]) -> List[List[int]]:
+        """Which chromosome files each GPU converts: longest-processing-time bin packing by file size, largest first."""
+        from .shard import plan_shards
+        sizes = [os.path.getsize(os.path.join(self.vcf_dir, f"chr{c}.filtered.vcf.gz")) for c in files]
+        bins = plan_shards(sizes, len(self.devices))
+        return [sorted((files[i] for i in b), key=lambda c: -sizes[files.index(c)]) for b in bins]
+
+    def _run_devices(self, present: List[int]) -> None:
+        plan = self.plan_devices(present)
+        for d, b in zip(self.devices, plan):
+            logger.info(f"GPU {d}: chromosomes {b}")
+        errors: List[BaseException] = []
+
+        def work(device, files):
+            try:
+                self._run_files(files, device)
+            except BaseException as e:           # noqa: BLE001 -- re-raised in the caller's thread
+                errors.append(e)
+
+        threads = [threading.Thread(target=work, args=(d, b), name=f"gpu{d}") for d, b in zip(self.devices, plan) if b]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def _safe_parse(self, chromosome: int, device: Optional[int] = None):
         vcf_file = os.path.join(self.vcf_dir, f"chr{chromosome}.filtered.vcf.gz")
         try:
-            return _ChromParse(vcf_file, chromosome, self.device, self.sample_window)
+            return _ChromParse(vcf_file, chromosome, self.device if device is None else device, self.sample_window)
         except capi.HaploError as e:
             logger.error(f"An error occurred while processing VCF file: Error parsing VCF file: {e}")
             if e.code in (capi.HB_ERR_MEM, capi.HB_ERR_CUDA):
                 raise                                   # out of device memory / a device fault: not this file's problem
-            self.stats["skipped_files"] += 1            # an unreadable or malformed file: the others still convert
+            self._count(skipped_files=1)                # an unreadable or malformed file: the others still convert
             return None
 
 
@@ -288,10 +336,19 @@ def main(argv=None):
     @click.option("--cores", default=os.cpu_count(), type=int, help="Number of CPU cores to use")
     @click.option("--cxx_threads", default=4, type=int, help="Number of threads to use in the C++ code")
     @click.option("--device", default=0, type=int, help="CUDA device ordinal")
-    def _main(cohort_name, vcf, outdir, sample_list, cores, cxx_threads, device):
+    @click.option("--devices", default=None, type=str,
+                  help="CUDA device ordinals, comma-separated (e.g. 0,1,2,3,4,5,6,7) or 'all': chromosome files are spread over them")
+    def _main(cohort_name, vcf, outdir, sample_list, cores, cxx_threads, device, devices):
         _configure_logging()
+        devs = None
+        if devices:
+            if devices.strip().lower() == "all":
+                import torch
+                devs = list(range(torch.cuda.device_count()))
+            else:
+                devs = [int(x) for x in devices.split(",") if x.strip() != ""]
         VCFtoHDF5Converter(cohort_name=cohort_name, vcf_dir=vcf, out_dir=outdir, sample_list_path=sample_list,
-                           cores=cores, cxx_threads=cxx_threads, device=device).run()
+                           cores=cores, cxx_threads=cxx_threads, device=device, devices=devs).run()
 
     return _main(args=argv, standalone_mode=argv is None)
 

@@ -307,3 +307,30 @@ def test_file_larger_than_the_text_budget_converts_to_the_same_file(mods, tmp_pa
         capi.lib().hb_cache_clear()
     assert blobs[0] == blobs[64 << 10]
     assert tuples[0] == tuples[64 << 10] == oracle.load_vcf(str(path), samples[3], "chr9")
+
+
+def test_two_gpus_write_the_same_datasets(mods, tmp_path):
+    """vcf_to_h5 --devices 0,1: the chromosome files are converted on two GPUs at once (one host thread per GPU, one
+    output file); every dataset holds the same stored chunks as the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    capi, container, h5_reader, hd, v2h = mods
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    samples = None
+    for c, nv in {1: 2600, 4: 1900, 9: 1300, 17: 700, 22: 350}.items():
+        text, samples = synth.random_vcf(nv, 13, seed=40 + c, fmt="GT", kinds="mixed", chrom=f"chr{c}", site_mix=True)
+        (vdir / f"chr{c}.filtered.vcf.gz").write_bytes(synth.bgzf_compress(text, 6))
+    (tmp_path / "donors.txt").write_text("\n".join(samples))
+    got = {}
+    for name, devs in (("one", [0]), ("two", [0, 1])):
+        conv = v2h.VCFtoHDF5Converter("c", str(vdir), str(tmp_path / name), str(tmp_path / "donors.txt"), 2, 4, devices=devs)
+        conv.run()
+        assert conv.stats["datasets"] == 5 * 13 and conv.stats["skipped_files"] == 17
+        rd = h5_reader.VCFH5Reader(str(tmp_path / name / "c.h5"))
+        got[name] = {(d, c): rd.fetch_genotypes(d, c).tobytes() for d in samples for c in (1, 4, 9, 17, 22)}
+        rd.close()
+    assert got["one"] == got["two"]
+    plan = v2h.VCFtoHDF5Converter("c", str(vdir), str(tmp_path / "p"), str(tmp_path / "donors.txt"), 2, 4, devices=[0, 1]).plan_devices([1, 4, 9, 17, 22])
+    assert all(plan) and sorted(c for b in plan for c in b) == [1, 4, 9, 17, 22]

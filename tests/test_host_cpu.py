@@ -154,3 +154,24 @@ def test_fasta_encoder_writes_the_reference_file_the_dataset_reads(tmp_path):
         for k in got:
             assert got[k].tobytes() == seqs[k]
     assert fe.ReferenceGenome.parse_encode_list(None) == [b"A", b"C", b"G", b"T", b"N"]
+
+
+def test_converter_spreads_chromosome_files_over_devices(tmp_path, built):
+    """vcf_to_h5 --devices: chromosome files are bin-packed onto the GPUs by size, largest first on every GPU (no GPU
+    work here: only the plan)."""
+    from haplohyped_varawareml_b200 import vcf_to_h5 as v2h
+    vdir = tmp_path / "vcf"
+    vdir.mkdir()
+    sizes = {1: 900, 2: 870, 3: 700, 7: 560, 12: 470, 19: 200, 21: 150, 22: 170}
+    for c, n in sizes.items():
+        (vdir / f"chr{c}.filtered.vcf.gz").write_bytes(b"x" * n)
+    (tmp_path / "donors.txt").write_text("a\nb\n")
+    conv = v2h.VCFtoHDF5Converter("c", str(vdir), str(tmp_path / "o"), str(tmp_path / "donors.txt"), 2, 4, devices=[0, 1, 2])
+    plan = conv.plan_devices(sorted(sizes))
+    assert sorted(c for b in plan for c in b) == sorted(sizes) and len(plan) == 3
+    loads = [sum(sizes[c] for c in b) for b in plan]
+    assert max(loads) - min(loads) <= max(sizes.values()) / 2            # LPT: bins within half the largest file of each other
+    for b in plan:
+        assert [sizes[c] for c in b] == sorted((sizes[c] for c in b), reverse=True)
+    assert conv.devices == [0, 1, 2]
+    assert v2h.VCFtoHDF5Converter("c", str(vdir), str(tmp_path / "o"), str(tmp_path / "donors.txt"), 2, 4, device=3).devices == [3]
