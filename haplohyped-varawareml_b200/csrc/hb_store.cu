@@ -904,18 +904,22 @@ static void launch_donor_frames(const FusedArgs &fa, uint64_t n_ctas, cudaStream
 }
 
 // The frame buffer is many GB and cudaMalloc / cudaFree of that size cost ~100 ms (and cudaFree synchronises the device):
-// a released buffer is kept, one per device, for the next frames handle of the process (a converter walks 22 chromosomes).
-// hb_cache_clear() gives it back.
+// released buffers are kept, two per device, for the next frames handles of the process: a converter walks 22 chromosomes
+// and parses + compresses one file ahead of the one whose frames are leaving, so two handles are alive at a time (with one
+// kept buffer every file paid a cudaMalloc and a device-synchronising cudaFree of 18 GB: the stalls of r02j's trace).
+// hb_cache_clear() gives them back.
 namespace {
 struct BufCache { uint8_t *p = nullptr; uint64_t cap = 0; };
+constexpr int kKeptBuffers = 2;
 std::mutex g_fb_mu;
-BufCache g_fb[64];
+BufCache g_fb[64][kKeptBuffers];
 }
 namespace hb {
 void frames_buffer_cache_clear() {
     std::lock_guard<std::mutex> lk(g_fb_mu);
     for (int d = 0; d < 64; ++d)
-        if (g_fb[d].p) { cudaSetDevice(d); cudaFree(g_fb[d].p); g_fb[d] = BufCache(); }
+        for (auto &c : g_fb[d])
+            if (c.p) { cudaSetDevice(d); cudaFree(c.p); c = BufCache(); }
 }
 }
 
@@ -993,8 +997,10 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         if (f->d_frames) { cudaFree(f->d_frames); f->d_frames = nullptr; f->frames_cap = 0; }
         if (f->device >= 0 && f->device < 64) {            // a buffer left behind by an earlier handle?
             std::lock_guard<std::mutex> lk(g_fb_mu);
-            BufCache &c = g_fb[f->device];
-            if (c.p && c.cap >= need) { f->d_frames = c.p; f->frames_cap = c.cap; c = BufCache(); }
+            BufCache *best = nullptr;                       // the smallest kept buffer that is large enough
+            for (auto &c : g_fb[f->device])
+                if (c.p && c.cap >= need && (!best || c.cap < best->cap)) best = &c;
+            if (best) { f->d_frames = best->p; f->frames_cap = best->cap; *best = BufCache(); }
         }
     }
     if (f->frames_cap < need) {
@@ -1070,8 +1076,9 @@ void hb_frames_free(hb_frames *f) {
     cudaSetDevice(f->device);
     if (f->d_frames && f->device >= 0 && f->device < 64) {     // keep the big buffer for the next handle (see g_fb)
         std::lock_guard<std::mutex> lk(g_fb_mu);
-        BufCache &c = g_fb[f->device];
-        if (c.cap < f->frames_cap) { std::swap(c.p, f->d_frames); std::swap(c.cap, f->frames_cap); }
+        BufCache *small = &g_fb[f->device][0];              // replace the smallest kept buffer if this one is larger
+        for (auto &c : g_fb[f->device]) if (c.cap < small->cap) small = &c;
+        if (small->cap < f->frames_cap) { std::swap(small->p, f->d_frames); std::swap(small->cap, f->frames_cap); }
     }
     dev_pool_free(f->d_tmpl); cudaFree(f->d_frames); dev_pool_free(f->d_tmpl_len); dev_pool_free(f->d_size);
     dev_pool_free(f->d_slot_off); dev_pool_free(f->d_totals);
@@ -1238,7 +1245,7 @@ int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *o
     if (!buf || !n_frames) return HB_OK;
     if (cap < run) return api_fail(HB_ERR_ARG, "buffer too small");
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
-    constexpr uint64_t kPackPiece = 256ull << 20;
+    constexpr uint64_t kPackPiece = 64ull << 20;
     cudaError_t e = cudaSuccess;
     auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     uint64_t *d_poff = nullptr;
@@ -1250,8 +1257,20 @@ int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *o
     ck(dev_pool_alloc((void **)&d_piece[0], piece_cap));
     ck(dev_pool_alloc((void **)&d_piece[1], piece_cap));
     ck(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    // the gather kernels run on a stream of the highest priority: when another host thread is parsing the next file (the
+    // converter does: one chromosome ahead), its 36-ms inflate kernel owns every SM, and a gather that waits for a free SM
+    // leaves the D2H engine idle; with priority its CTAs take the first slots that retire
+    cudaStream_t packs = nullptr;
+    cudaEvent_t ev_ready = nullptr;
+    {
+        int lo = 0, hi = 0;
+        ck(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ck(cudaStreamCreateWithPriority(&packs, cudaStreamNonBlocking, hi));
+        ck(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    }
     for (int k = 0; k < 2; ++k) { ck(cudaEventCreateWithFlags(&ev_g[k], cudaEventDisableTiming)); ck(cudaEventCreateWithFlags(&ev_c[k], cudaEventDisableTiming)); }
     if (e == cudaSuccess) ck(cudaMemcpyAsync(d_poff, poff.data(), (n_frames + 1) * 8, cudaMemcpyHostToDevice, f->stream));
+    if (e == cudaSuccess) { ck(cudaEventRecord(ev_ready, f->stream)); ck(cudaStreamWaitEvent(packs, ev_ready, 0)); }   // the frames are complete
     const bool pinned = host_is_pinned(buf);
     uint64_t first = 0;
     int k = 0;
@@ -1262,25 +1281,31 @@ int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *o
         if (last <= first) last = first + 1;
         const uint64_t bytes = poff[last] - base;
         const int b = k & 1;
-        if (k >= 2) ck(cudaStreamWaitEvent(f->stream, ev_c[b], 0));            // the copy that read this buffer last is done
-        pack_frames_kernel<<<(unsigned)((last - first + 7) / 8), 256, 0, f->stream>>>(f->d_frames, f->d_slot_off, nc, f->d_size, d_poff,
-                                                                                    first, last - first, base, d_piece[b]);
+        // the copy that read this buffer last is done.  Waited for on the HOST, so that at most two pieces are queued on the
+        // D2H engine at any time: the engine serves copies in submission order, and with all 60 pieces queued up front the
+        // 4-byte status reads of a parse running in another host thread sat behind 270 ms of frames (HB_TRACE, r02j)
+        if (k >= 2) ck(cudaEventSynchronize(ev_c[b]));
+        pack_frames_kernel<<<(unsigned)((last - first + 7) / 8), 256, 0, packs>>>(f->d_frames, f->d_slot_off, nc, f->d_size, d_poff,
+                                                                                first, last - first, base, d_piece[b]);
         count_launch();
         ck(cudaGetLastError());
-        ck(cudaEventRecord(ev_g[b], f->stream));
+        ck(cudaEventRecord(ev_g[b], packs));
         if (pinned) {
             ck(cudaStreamWaitEvent(copy, ev_g[b], 0));
             ck(cudaMemcpyAsync(buf + base, d_piece[b], bytes, cudaMemcpyDeviceToHost, copy));
             ck(cudaEventRecord(ev_c[b], copy));
         } else {                                                                // pageable destination: staged copy, piece by piece
-            ck(d2h_copy(buf + base, d_piece[b], bytes, f->stream));
+            ck(d2h_copy(buf + base, d_piece[b], bytes, packs));
         }
         first = last;
         ++k;
     }
     if (copy) { cudaError_t e2 = cudaStreamSynchronize(copy); if (e == cudaSuccess) e = e2; }
+    if (packs) { cudaError_t e2 = cudaStreamSynchronize(packs); if (e == cudaSuccess) e = e2; }
     { cudaError_t e2 = cudaStreamSynchronize(f->stream); if (e == cudaSuccess) e = e2; }
     for (int q = 0; q < 2; ++q) { if (ev_g[q]) cudaEventDestroy(ev_g[q]); if (ev_c[q]) cudaEventDestroy(ev_c[q]); }
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (packs) cudaStreamDestroy(packs);
     if (copy) cudaStreamDestroy(copy);
     dev_pool_free(d_poff); dev_pool_free(d_piece[0]); dev_pool_free(d_piece[1]);
     if (e != cudaSuccess) { cudaGetLastError(); return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); }
