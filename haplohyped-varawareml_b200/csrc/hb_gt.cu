@@ -246,21 +246,24 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         const uint64_t b = sm.seg_begin[r], e = b + sm.seg_len[r];
         const int g = (int)sm.seg_g[r];
         uint32_t seen = 0;
+        // the next 512 bytes are requested before these are decoded: a warp otherwise alternates between waiting for DRAM
+        // and decoding, and 32 warps x 512 bytes in flight per SM bound the general path at ~0.7 TB/s (r01c, r02e)
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if ((b & ~15ull) + 16ull * lane < e) nxt = *reinterpret_cast<const uint4 *>(text + (b & ~15ull) + 16ull * lane);
         for (uint64_t base = b & ~15ull; base < e; base += 512) {
             const uint64_t o = base + 16ull * lane;
-            uint32_t w[4] = {0, 0, 0, 0};
-            if (o < e) {
-                uint4 v = *reinterpret_cast<const uint4 *>(text + o);
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            }
+            const uint4 v = nxt;
+            nxt = make_uint4(0, 0, 0, 0);
+            if (o + 512 < e) nxt = *reinterpret_cast<const uint4 *>(text + o + 512);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             // the 512 bytes (+ 16 of look-ahead) also go to this record's row of the staging buffer, which the general
             // path does not use otherwise: the common field shape "X|Y" + terminator is then decoded from shared memory
             // with one unaligned 4-byte read instead of a byte-wise parse over global memory
             uint8_t *row = sm.text[r];
             *reinterpret_cast<uint4 *>(row + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (lane == 0) {
-                uint4 x = make_uint4(0, 0, 0, 0);
-                if (base + 512 < e + 4) x = *reinterpret_cast<const uint4 *>(text + base + 512);
+            if (lane == 0) {                                  // 16 bytes of look-ahead: lane 0's next piece (zeros past the segment,
+                uint4 x = nxt;                                //  except its first 4 bytes, which a field that ends the segment reads)
+                if (!(base + 512 < e) && base + 512 < e + 4) x = *reinterpret_cast<const uint4 *>(text + base + 512);
                 *reinterpret_cast<uint4 *>(row + 512) = x;
             }
             __syncwarp();
