@@ -473,6 +473,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     affinity = numa_local_affinity(local)
+    # host threads of the library (frame assembly in hb_frames_fetch_packed): this rank's share of the CPUs it may run on
+    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, world)))
+    capi.lib().hb_set_host_threads(host_threads)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # rank 0 prints ONE line on stdout: whatever libraries print there meanwhile (NCCL's version banner, when NCCL_DEBUG
@@ -685,7 +688,7 @@ def main():
               tot, offs, sizes = fr.fetch_packed(out=(pin.data_ptr(), cap))
               capi.check(capi.lib().hb_parse_fetch_sites(q._h, *[a.data_ptr() for a in sites]))
               last.update(tot=int(tot), offs=offs, sizes=sizes, n=int(q.info.n_records), ms_inflate=float(q.info.ms_inflate),
-                          ms_frames=float(fr.info.ms_frames))
+                          ms_frames=float(fr.info.ms_frames), d2h=int(capi.lib().hb_frames_last_d2h_bytes(fr._h)))
               fr.close(); q.close()
 
           K = max(2, args.e2e_steps + 1)
@@ -708,13 +711,14 @@ def main():
           dt = float(tt.item())
           Vb = float(last["n"])                    # (every rank converts rank 0's file)
           e2e = {"value": Vb * S * world / (dt / K), "unit": "calls/s", "h2d_bytes_per_step": nb * world,
-                 "d2h_bytes_per_step": (last["tot"] + 4 * last["sizes"].size + 10 * last["n"]) * world, "steps": K,
+                 "d2h_bytes_per_step": (last["d2h"] + 10 * last["n"]) * world, "steps": K,
                  "ms_per_step": 1e3 * dt / K, "ranks": world, "host_affinity": affinity,
                  "api": "per file and rank: hb_parse_vcf_bytes (BGZF of the .vcf.gz in pinned host memory -> H2D compressed -> GPU "
-                        "inflate -> GPU parse) + hb_compress_records (kernel 4) + hb_frames_fetch_packed (device gather + D2H of the "
-                        "packed frame image and the chunk index) + hb_parse_fetch_sites = what vcf_to_h5 writes to the HDF5 file with "
-                        "one write; %d files back to back driven as the converter drives them (the next file is parsed by a second "
-                        "host thread while this file's frames cross PCIe), pipeline fill inside the timed region" % K,
+                        "inflate -> GPU parse) + hb_compress_records (kernel 4) + hb_frames_fetch_packed (the packed image of every "
+                        "donor's stored chunks in pinned host memory + the chunk index: the chunk templates cross PCIe once, per donor "
+                        "only 32 header bytes and the own tail, %d host threads put the frames together with streaming stores) + "
+                        "hb_parse_fetch_sites = what vcf_to_h5 writes to the HDF5 file with one write; %d files back to back driven as the converter drives them (the next file is parsed by a second "
+                        "host thread while this file's frames cross PCIe), pipeline fill inside the timed region" % (host_threads, K),
                  "one_call_at_a_time": {"value": Vb * S * world / (dt_serial / args.e2e_steps), "ms_per_step": 1e3 * dt_serial / args.e2e_steps,
                                         "steps": args.e2e_steps, "what": "the same calls strictly one after the other (no second thread)"},
                  "inflate_kernel_ms": last["ms_inflate"], "donor_frames_ms": last["ms_frames"], "text_over_bgzf": T / float(nb),

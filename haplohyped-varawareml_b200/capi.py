@@ -75,7 +75,7 @@ EXPORTS = [
     "hb_parse_fetch_sites", "hb_parse_fetch_sample", "hb_parse_fetch_matrix", "hb_parse_fetch_sample_errors",
     "hb_parse_chrom_runs", "hb_parse_free",
     "hb_bgzf_inflate", "hb_bgzf_compress_host",
-    "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all", "hb_frames_fetch_packed",
+    "hb_compress_records", "hb_compress_sample_range", "hb_frames_set_window", "hb_parse_release_text", "hb_parse_attach_frames", "hb_frames_rerun", "hb_frames_get_info", "hb_frames_layout", "hb_frames_fetch_all", "hb_frames_fetch_packed", "hb_set_fetch_mode", "hb_set_host_threads", "hb_frames_last_d2h_bytes",
     "hb_frames_fetch_sample", "hb_frames_free",
     "hb_guess_chunk_records", "hb_set_site_matcher", "hb_decode_frames", "hb_decode_columns_device",
     "hb_encode_haplotypes",
@@ -99,6 +99,12 @@ def lib():
         L.hb_records_free.argtypes = [C.POINTER(Records)]
         L.hb_cache_set_limit.argtypes = [C.c_uint64]
         L.hb_cache_set_limit.restype = None
+        L.hb_set_fetch_mode.argtypes = [C.c_int]
+        L.hb_set_fetch_mode.restype = None
+        L.hb_set_host_threads.argtypes = [C.c_int]
+        L.hb_set_host_threads.restype = None
+        L.hb_frames_last_d2h_bytes.argtypes = [C.c_void_p]
+        L.hb_frames_last_d2h_bytes.restype = C.c_uint64
         L.hb_parse_set_text_limit.argtypes = [C.c_uint64]
         L.hb_parse_set_text_limit.restype = None
         L.hb_parse_host_text.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(ParseOpts), C.POINTER(C.c_void_p)]

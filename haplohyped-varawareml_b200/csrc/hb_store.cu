@@ -14,13 +14,19 @@
 // chunk (site_template_kernel) and every donor continues that LZ4 block with its own 2 * cr allele bytes
 // (donor_frames_kernel).  The site encoder is a warp-cooperative greedy matcher: 32 candidate positions per step are
 // hashed in parallel, the first hit is extended with ballots, literals are copied 32 bytes per step.
+#include <emmintrin.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <condition_variable>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -833,6 +839,28 @@ pack_frames_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restric
     for (uint32_t k = lane; k < nv; k += 32) stg_stream(dst + k, ldg_stream(src + k));
 }
 
+// The donor-specific bytes of frames [first, first + count): a stored chunk is the chunk's template with its first 32
+// bytes patched (size fields) and its own tail behind it, so only the 32 header bytes and the tail -- from the last 16-byte
+// boundary of the template on -- have to leave the GPU per donor; the template goes once per chunk.  Tails are packed
+// back to back (16-byte units, tail_off), the headers follow them.  One warp per frame.
+__global__ void __launch_bounds__(256)
+pack_tails_kernel(const uint8_t *__restrict__ frames, const uint64_t *__restrict__ slot_off, uint64_t n_chunks,
+                  const uint32_t *__restrict__ size, const uint32_t *__restrict__ tmpl_len, const uint64_t *__restrict__ tail_off,
+                  uint64_t first, uint64_t count, uint64_t piece_base, uint8_t *__restrict__ out_tails, uint4 *__restrict__ out_hdr) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const uint64_t i = first + w;
+    const uint64_t s = i / n_chunks, c = i - s * n_chunks;
+    const uint8_t *slot = frames + s * slot_off[n_chunks] + slot_off[c];
+    const uint32_t tl16 = tmpl_len[c] & ~15u, sz = size[i];
+    const uint32_t nv = sz > tl16 ? (sz - tl16 + 15u) >> 4 : 0u;       // the slot is zero behind the frame up to the next 16-byte boundary
+    const uint4 *src = reinterpret_cast<const uint4 *>(slot + tl16);
+    uint4 *dst = reinterpret_cast<uint4 *>(out_tails + (tail_off[i] - piece_base));
+    for (uint32_t k = lane; k < nv; k += 32) stg_stream(dst + k, ldg_stream(src + k));
+    if (lane < 2) out_hdr[2 * w + lane] = ldg_stream(reinterpret_cast<const uint4 *>(slot) + lane);
+}
+
 uint64_t guess_chunk_records(uint64_t n) {      // h5py/_hl/filters.py guess_chunk for shape (n,), 35-byte items
     const double CHUNK_BASE = 16 * 1024, CHUNK_MIN = 8 * 1024, CHUNK_MAX = 1024 * 1024;
     if (n == 0) return 1;
@@ -884,6 +912,7 @@ struct hb_frames {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_sites = nullptr, ev_tmpl = nullptr, ev_side0 = nullptr;
     bool early_site = false;                     // the template pass of the current parse run is already in flight
+    uint64_t last_d2h_bytes = 0;                 // bytes the last hb_frames_fetch_packed moved device -> host
 };
 
 // More than 48 KB of dynamic shared memory is opt-in per function AND per device.  The ceiling is always raised to the
@@ -1224,26 +1253,11 @@ int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap) {
     return HB_OK;
 }
 
-// All frames packed back to back (each starts on a 16-byte boundary of the image), [sample][chunk] order: what a
-// converter writes into the HDF5 file with one write.  The frames leave their slots through a gather kernel, a piece of
-// at most kPackPiece bytes at a time, and the D2H copy of piece k runs while piece k + 1 is gathered (two device
-// buffers); against hb_frames_fetch_all this moves total_bytes instead of padded_bytes over PCIe.  offsets [n_samples]
-// [n_chunks] = where each frame starts in buf; sizes as in hb_frames_layout; either may be NULL.  buf == NULL: only
-// *total (bytes needed) is set.
-int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *offsets, uint32_t *sizes, uint64_t *total) {
-    if (!f) return api_fail(HB_ERR_ARG, "null handle");
-    int rc = frames_layout(f);
-    if (rc != HB_OK) return rc;
+// ---- hb_frames_fetch_packed, way 1: every frame gathered whole on the device (C_out bytes cross PCIe)
+static int fetch_packed_gather(hb_frames *f, uint8_t *buf, const std::vector<uint64_t> &poff) {
     const uint64_t nc = f->n_chunks, n_frames = nc * f->n_samples;
-    std::vector<uint64_t> poff(n_frames + 1);
-    uint64_t run = 0;
-    for (uint64_t i = 0; i < n_frames; ++i) { poff[i] = run; run += ((uint64_t)f->h_size[i] + 15) & ~15ull; }
-    poff[n_frames] = run;
-    if (total) *total = run;
-    if (offsets && n_frames) memcpy(offsets, poff.data(), n_frames * 8);
-    if (sizes && n_frames) memcpy(sizes, f->h_size.data(), n_frames * 4);
-    if (!buf || !n_frames) return HB_OK;
-    if (cap < run) return api_fail(HB_ERR_ARG, "buffer too small");
+    const uint64_t run = poff[n_frames];
+    f->last_d2h_bytes = run + 4 * n_frames;
     if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
     constexpr uint64_t kPackPiece = 64ull << 20;
     cudaError_t e = cudaSuccess;
@@ -1310,6 +1324,252 @@ int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *o
     dev_pool_free(d_poff); dev_pool_free(d_piece[0]); dev_pool_free(d_piece[1]);
     if (e != cudaSuccess) { cudaGetLastError(); return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); }
     return HB_OK;
+}
+
+
+// ---- way 2: the chunk templates cross PCIe once, per donor only the 32 header bytes and the tail; host threads put the
+// frames together in buf (template body, tail, header: three memcpy per frame).  Config 2: 2.7 GB instead of 15.2 GB over
+// PCIe; the assembly is a memory-bound copy that the host does at several times PCIe speed when it has a few cores.
+namespace {
+std::atomic<int> g_fetch_mode{0};        // 0 auto, 1 device gather, 2 host assembly
+std::atomic<int> g_host_threads{0};      // 0 = the CPUs this process may run on, at most 16
+
+int host_threads() {
+    int n = g_host_threads.load();
+    if (n > 0) return std::min(n, 64);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    n = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(n, 16));
+}
+
+// pinned staging buffers, kept between calls (cudaMallocHost of tens of MB costs milliseconds)
+struct StagePool {
+    std::mutex mu;
+    std::vector<std::pair<uint8_t *, uint64_t>> idle;
+    uint8_t *get(uint64_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i].second >= bytes) { uint8_t *p = idle[i].first; sizes[p] = idle[i].second; idle.erase(idle.begin() + (long)i); return p; }
+        }
+        uint8_t *p = nullptr;
+        if (cudaMallocHost((void **)&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        std::lock_guard<std::mutex> lk(mu);
+        sizes[p] = bytes;
+        return p;
+    }
+    void put(uint8_t *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        const uint64_t b = sizes[p];
+        if (idle.size() < 8) idle.push_back({p, b}); else { sizes.erase(p); cudaFreeHost(p); }
+    }
+    std::map<uint8_t *, uint64_t> sizes;
+} g_stage_pool;
+
+struct Piece {                            // frames [first, last) whose tails + headers sit in `stage`
+    uint64_t first = 0, last = 0, tail_base = 0, hdr_at = 0;
+    const uint8_t *stage = nullptr;
+};
+
+// fork-join over the frames of one piece at a time
+struct Assembler {
+    const hb_frames *f; uint8_t *buf; const uint64_t *poff; const uint64_t *tail_off; const uint8_t *tmpl;
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    Piece piece;
+    uint64_t gen = 0, next = 0, grain = 1;
+    int busy = 0;
+    bool quit = false;
+    // n bytes (a multiple of 16) to a 16-byte aligned destination with non-temporal stores: the image is written once and
+    // not read again here, and ordinary stores would first READ every destination line (15 GB of extra DRAM traffic)
+    static void stream16(uint8_t *dst, const uint8_t *src, size_t n) {
+        for (size_t k = 0; k < n; k += 16)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + k), _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + k)));
+    }
+    void frame(uint64_t i) const {
+        const uint64_t nc = f->n_chunks, c = i % nc;
+        const uint32_t tl = f->h_tmpl_len[c], tl16 = tl & ~15u, sz = f->h_size[i];
+        uint8_t *dst = buf + poff[i];
+        const uint8_t *tp = tmpl + c * (uint64_t)f->tmpl_cap;
+        const uint8_t *tail = piece.stage + (tail_off[i] - piece.tail_base), *hdr = piece.stage + piece.hdr_at + 32 * (i - piece.first);
+        if (tl16 >= 32 && sz >= tl16) {
+            stream16(dst, hdr, 32);                                       // header with this frame's size fields
+            stream16(dst + 32, tp + 32, tl16 - 32);                       // template body
+            stream16(dst + tl16, tail, ((size_t)(sz - tl16) + 15) & ~size_t(15));     // own tail from the template's last 16-byte boundary, zero pad included
+            return;
+        }
+        memcpy(dst, tp, std::min(tl, sz));                                // tiny templates: the same three pieces, any overlap
+        if (sz > tl16) memcpy(dst + tl16, tail, sz - tl16);
+        memcpy(dst, hdr, std::min<uint32_t>(32, sz));
+        const uint64_t pad = (16 - (sz & 15)) & 15;                       // the image is zero up to the next frame
+        if (pad) memset(dst + sz, 0, pad);
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return quit || gen != seen; });
+            if (quit) return;
+            seen = gen;
+            for (;;) {
+                const uint64_t a = next;
+                if (a >= piece.last) break;
+                next = std::min(piece.last, a + grain);
+                const uint64_t b = next;
+                lk.unlock();
+                for (uint64_t i = a; i < b; ++i) frame(i);
+                _mm_sfence();
+                lk.lock();
+            }
+            if (--busy == 0) cv_done.notify_all();
+        }
+    }
+    void start(int n) { for (int k = 0; k < n; ++k) th.emplace_back([this] { worker(); }); }
+    void run(const Piece &p) {                 // returns when the piece before has been assembled and this one is handed out
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return busy == 0; });
+        piece = p; next = p.first;
+        grain = std::max<uint64_t>(64, (p.last - p.first) / (8 * std::max<uint64_t>(1, (uint64_t)th.size())));
+        busy = (int)th.size(); ++gen;
+        cv_work.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return busy == 0; }); }
+    void stop() {
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv_work.notify_all();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+};
+}  // namespace
+
+static int fetch_packed_assemble(hb_frames *f, uint8_t *buf, const std::vector<uint64_t> &poff, int n_threads) {
+    const uint64_t nc = f->n_chunks, n_frames = nc * f->n_samples;
+    if (cudaSetDevice(f->device) != cudaSuccess) return api_fail(HB_ERR_CUDA, "cudaSetDevice failed");
+    // tails in frame order, 16-byte units
+    std::vector<uint64_t> toff(n_frames + 1);
+    {
+        uint64_t run = 0;
+        for (uint64_t i = 0; i < n_frames; ++i) {
+            toff[i] = run;
+            const uint32_t tl16 = f->h_tmpl_len[i % nc] & ~15u, sz = f->h_size[i];
+            if (sz > tl16) run += ((uint64_t)(sz - tl16) + 15) & ~15ull;
+        }
+        toff[n_frames] = run;
+    }
+    constexpr uint64_t kTailPiece = 32ull << 20;
+    // pieces: at most kTailPiece bytes of tails each
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < n_frames) {
+        const uint64_t a = cut.back();
+        uint64_t b = std::upper_bound(toff.begin() + a, toff.begin() + n_frames + 1, toff[a] + kTailPiece) - toff.begin() - 1;
+        if (b <= a) b = a + 1;
+        b = std::min(b, a + (kTailPiece >> 5));              // and at most as many headers as fit the same room
+        cut.push_back(b);
+    }
+    f->last_d2h_bytes = toff[n_frames] + 32 * n_frames + (uint64_t)nc * f->tmpl_cap + 4 * n_frames;    // tails, headers, templates, sizes
+    uint64_t stage_bytes = 0;
+    for (size_t k = 0; k + 1 < cut.size(); ++k)
+        stage_bytes = std::max<uint64_t>(stage_bytes, ((toff[cut[k + 1]] - toff[cut[k]] + 15) & ~15ull) + 32ull * (cut[k + 1] - cut[k]));
+    cudaError_t e = cudaSuccess;
+    auto ck = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    uint64_t *d_toff = nullptr;
+    uint8_t *d_piece[2] = {nullptr, nullptr}, *h_stage[2] = {nullptr, nullptr};
+    cudaStream_t copy = nullptr, packs = nullptr;
+    cudaEvent_t ev_g[2] = {nullptr, nullptr}, ev_c[2] = {nullptr, nullptr}, ev_ready = nullptr;
+    std::vector<uint8_t> tmpl((uint64_t)nc * f->tmpl_cap);
+    ck(dev_pool_alloc((void **)&d_toff, (n_frames + 1) * 8));
+    ck(dev_pool_alloc((void **)&d_piece[0], stage_bytes));
+    ck(dev_pool_alloc((void **)&d_piece[1], stage_bytes));
+    h_stage[0] = g_stage_pool.get(stage_bytes); h_stage[1] = g_stage_pool.get(stage_bytes);
+    if (!h_stage[0] || !h_stage[1]) ck(cudaErrorMemoryAllocation);
+    ck(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        ck(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ck(cudaStreamCreateWithPriority(&packs, cudaStreamNonBlocking, hi));     // see fetch_packed_gather
+        ck(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 2; ++k) { ck(cudaEventCreateWithFlags(&ev_g[k], cudaEventDisableTiming)); ck(cudaEventCreateWithFlags(&ev_c[k], cudaEventDisableTiming)); }
+    if (e == cudaSuccess) {
+        ck(cudaMemcpyAsync(d_toff, toff.data(), (n_frames + 1) * 8, cudaMemcpyHostToDevice, f->stream));
+        ck(d2h_copy(tmpl.data(), f->d_tmpl, tmpl.size(), f->stream));            // the templates, once (a few MB)
+        ck(cudaEventRecord(ev_ready, f->stream));
+        ck(cudaStreamWaitEvent(packs, ev_ready, 0));                             // the frames are complete
+    }
+    Assembler as;
+    as.f = f; as.buf = buf; as.poff = poff.data(); as.tail_off = toff.data(); as.tmpl = tmpl.data();
+    if (e == cudaSuccess) as.start(n_threads);
+    const size_t n_pieces = cut.size() - 1;
+    std::vector<Piece> pieces(n_pieces);
+    // piece k: gathered + copied into stage k & 1 while piece k - 1 is assembled; a stage is reused when the piece that
+    // used it (k - 2) is done, which as.run(k - 1) has waited for
+    for (size_t k = 0; e == cudaSuccess && k <= n_pieces; ++k) {
+        if (k < n_pieces) {
+            const int b = (int)(k & 1);
+            Piece &pc = pieces[k];
+            pc.first = cut[k]; pc.last = cut[k + 1]; pc.tail_base = toff[pc.first];
+            pc.hdr_at = (toff[pc.last] - pc.tail_base + 15) & ~15ull;
+            pc.stage = h_stage[b];
+            if (k >= 2) { as.wait(); }                                           // (run(k - 1) below already waited for k - 2; this is the k - 1 hand-out)
+            const uint64_t cnt = pc.last - pc.first;
+            pack_tails_kernel<<<(unsigned)((cnt + 7) / 8), 256, 0, packs>>>(f->d_frames, f->d_slot_off, nc, f->d_size, f->d_tmpl_len, d_toff,
+                                                                          pc.first, cnt, pc.tail_base, d_piece[b],
+                                                                          reinterpret_cast<uint4 *>(d_piece[b] + pc.hdr_at));
+            count_launch();
+            ck(cudaGetLastError());
+            ck(cudaEventRecord(ev_g[b], packs));
+            ck(cudaStreamWaitEvent(copy, ev_g[b], 0));
+            ck(cudaMemcpyAsync(h_stage[b], d_piece[b], pc.hdr_at + 32 * cnt, cudaMemcpyDeviceToHost, copy));
+            ck(cudaEventRecord(ev_c[b], copy));
+        }
+        if (k >= 1 && e == cudaSuccess) {
+            ck(cudaEventSynchronize(ev_c[(k - 1) & 1]));
+            if (e == cudaSuccess) as.run(pieces[k - 1]);
+        }
+    }
+    if (!as.th.empty()) { as.wait(); as.stop(); }
+    if (copy) cudaStreamSynchronize(copy);
+    if (packs) cudaStreamSynchronize(packs);
+    for (int q = 0; q < 2; ++q) { if (ev_g[q]) cudaEventDestroy(ev_g[q]); if (ev_c[q]) cudaEventDestroy(ev_c[q]); }
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (packs) cudaStreamDestroy(packs);
+    if (copy) cudaStreamDestroy(copy);
+    dev_pool_free(d_toff); dev_pool_free(d_piece[0]); dev_pool_free(d_piece[1]);
+    g_stage_pool.put(h_stage[0]); g_stage_pool.put(h_stage[1]);
+    if (e != cudaSuccess) { cudaGetLastError(); return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e)); }
+    return HB_OK;
+}
+
+uint64_t hb_frames_last_d2h_bytes(const hb_frames *f) { return f ? f->last_d2h_bytes : 0; }
+void hb_set_fetch_mode(int mode) { g_fetch_mode.store(mode < 0 || mode > 2 ? 0 : mode); }
+void hb_set_host_threads(int n) { g_host_threads.store(n < 0 ? 0 : n); }
+
+// All frames packed back to back (each starts on a 16-byte boundary of the image), [sample][chunk] order: what a
+// converter writes into the HDF5 file with one write.  offsets [n_samples][n_chunks] = where each frame starts in buf;
+// sizes as in hb_frames_layout; either may be NULL.  buf == NULL: only *total (bytes needed) is set.
+int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *offsets, uint32_t *sizes, uint64_t *total) {
+    if (!f) return api_fail(HB_ERR_ARG, "null handle");
+    int rc = frames_layout(f);
+    if (rc != HB_OK) return rc;
+    const uint64_t nc = f->n_chunks, n_frames = nc * f->n_samples;
+    std::vector<uint64_t> poff(n_frames + 1);
+    uint64_t run = 0;
+    for (uint64_t i = 0; i < n_frames; ++i) { poff[i] = run; run += ((uint64_t)f->h_size[i] + 15) & ~15ull; }
+    poff[n_frames] = run;
+    if (total) *total = run;
+    if (offsets && n_frames) memcpy(offsets, poff.data(), n_frames * 8);
+    if (sizes && n_frames) memcpy(sizes, f->h_size.data(), n_frames * 4);
+    if (!buf || !n_frames) return HB_OK;
+    if (cap < run) return api_fail(HB_ERR_ARG, "buffer too small");
+    // host assembly needs a template that IS the head of every frame (not so for raw chunks, cr < 6) and pays when the
+    // host has a few cores to copy with
+    const int mode = g_fetch_mode.load(), nt = host_threads();
+    const bool assemble = f->cr >= 6 && (mode == 2 || (mode == 0 && nt >= 4));
+    return assemble ? fetch_packed_assemble(f, buf, poff, nt) : fetch_packed_gather(f, buf, poff);
 }
 
 int hb_frames_fetch_sample(hb_frames *f, uint32_t s, uint64_t *sizes, uint8_t *buf, uint64_t cap, uint64_t *total) {

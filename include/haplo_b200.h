@@ -231,6 +231,17 @@ int hb_frames_fetch_all(hb_frames *f, uint8_t *buf, uint64_t cap);
  * total_bytes (+ < 16 per frame) cross PCIe instead of padded_bytes.  offsets / sizes [n_samples][n_chunks] may be
  * NULL; buf == NULL only reports *total, the bytes buf must hold.  buf should be pinned memory. */
 int hb_frames_fetch_packed(hb_frames *f, uint8_t *buf, uint64_t cap, uint64_t *offsets, uint32_t *sizes, uint64_t *total);
+/* How hb_frames_fetch_packed moves the frames.  A stored chunk is its HDF5 chunk's template (the LZ4 stream of the 33 site
+ * planes, the same for every donor) with 32 patched header bytes and the donor's own tail behind it, so by default
+ * (mode 0, when the process may run on >= 4 CPUs) the templates cross PCIe once per chunk, only headers and tails per
+ * donor (config 2: 2.7 GB instead of 15.2 GB), and host threads put the frames together in buf with memcpy.  mode 1:
+ * every frame is gathered whole on the device and copied (what r01 / r02j did); mode 2: host assembly regardless of the
+ * CPU count.  The bytes in buf are the same either way.  hb_set_host_threads: threads used for the assembly
+ * (0 = the CPUs the process may run on, at most 16). */
+void hb_set_fetch_mode(int mode);
+void hb_set_host_threads(int n);
+/* bytes the last hb_frames_fetch_packed of this handle moved device -> host (frames or tails + headers + templates, + sizes) */
+uint64_t hb_frames_last_d2h_bytes(const hb_frames *f);
 /* sizes[n_chunks] of one sample's frames; then the frames themselves, concatenated without padding */
 int hb_frames_fetch_sample(hb_frames *f, uint32_t sample_index, uint64_t *sizes, uint8_t *buf, uint64_t cap,
                            uint64_t *total);

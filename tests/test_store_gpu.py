@@ -139,6 +139,19 @@ def test_long_segments_and_layout(capi, mix, chunk_records):
         for k, f in enumerate(fr.sample(s)):
             o = int(poffs[s, k])
             assert pk[o:o + int(psizes[s, k])].tobytes() == f
+    # the two ways the packed image is made (hb_set_fetch_mode): whole frames gathered on the device, or templates once +
+    # headers and tails per donor put together by host threads: the same bytes, pad bytes included, with 1 or many threads
+    try:
+        for mode, threads in ((1, 0), (2, 1), (2, 3), (2, 0)):
+            capi.lib().hb_set_fetch_mode(mode)
+            capi.lib().hb_set_host_threads(threads)
+            pin.fill_(0xEE)
+            tot2, o2, z2 = fr.fetch_packed(out=(pin.data_ptr(), pin.numel()))
+            assert tot2 == len(pk) and np.array_equal(pin.numpy()[:tot2], pk) and (pin.numpy()[tot2:] == 0xEE).all()
+            assert np.array_equal(o2, poffs) and np.array_equal(z2, psizes)
+    finally:
+        capi.lib().hb_set_fetch_mode(0)
+        capi.lib().hb_set_host_threads(0)
     fr.rerun(p)                                                                       # deterministic: same bytes again
     assert np.array_equal(fr.fetch_all(), buf)
 

@@ -22,7 +22,13 @@ def t(fn, reps=3):
     return ts
 out["raw_d2h_ms"] = t(lambda: pin[:tot].copy_(dev, non_blocking=True))
 out["raw_d2h_GBs"] = tot / min(out["raw_d2h_ms"]) / 1e6
-out["fetch_packed_ms"] = t(lambda: fr.fetch_packed(out=(pin.data_ptr(), cap)))
-out["fetch_packed_GBs"] = tot / min(out["fetch_packed_ms"]) / 1e6
+for mode, name in ((1, "device_gather"), (2, "host_assembly")):
+    capi.lib().hb_set_fetch_mode(mode)
+    out["fetch_packed_%s_ms" % name] = t(lambda: fr.fetch_packed(out=(pin.data_ptr(), cap)))
+    out["fetch_packed_%s_GBs" % name] = tot / min(out["fetch_packed_%s_ms" % name]) / 1e6
+for th in (4, 8, 16):
+    capi.lib().hb_set_host_threads(th)
+    out["host_assembly_%d_threads_ms" % th] = t(lambda: fr.fetch_packed(out=(pin.data_ptr(), cap)))
+capi.lib().hb_set_host_threads(0); capi.lib().hb_set_fetch_mode(0)
 out["layout_only_ms"] = t(lambda: fr.layout())
 print(json.dumps(out))
