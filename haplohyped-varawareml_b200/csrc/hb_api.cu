@@ -515,6 +515,28 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
     return HB_OK;
 }
 
+// the CHROM runs of the last run_parse, on the host (needs the text: hb_parse_release_text calls it first)
+static int ensure_runs(hb_parse *p) {
+    if (p->runs_valid) return HB_OK;
+    CU(cudaSetDevice(p->device));
+    p->run_rows.clear(); p->run_names.clear();
+    const uint64_t n_runs = std::min<uint64_t>(p->h_st.n_chrom_runs, hb_parse::kMaxRuns);
+    if (n_runs && p->d_run_rows && p->d_text) {
+        p->run_rows.resize(n_runs);
+        CU(cudaMemcpy(p->run_rows.data(), p->d_run_rows, n_runs * 8, cudaMemcpyDeviceToHost));
+        std::sort(p->run_rows.begin(), p->run_rows.end());
+        for (uint64_t r : p->run_rows) {
+            uint64_t abs; uint8_t len; char name[256];
+            CU(cudaMemcpy(&abs, p->d_chrom_abs + r, 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&len, p->d_chrom_len + r, 1, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(name, p->d_text + abs, len, cudaMemcpyDeviceToHost));
+            p->run_names.emplace_back(name, name + len);
+        }
+    }
+    p->runs_valid = true;
+    return HB_OK;
+}
+
 static int run_parse(hb_parse *p) {
     CU(cudaSetDevice(p->device));
     Launch L{p->stream, p->sm_count};
@@ -598,22 +620,11 @@ static int run_parse(hb_parse *p) {
         return run_parse(p);
     }
 
-    // ---- CHROM runs -> names (a handful of tiny D2H copies)
+    // ---- CHROM runs -> names: fetched when somebody asks (ensure_runs): a handful of tiny synchronous D2H copies that a
+    // step which goes on to compress the records does not need to wait for (~60 us of idle GPU per step, r02n)
     p->run_rows.clear(); p->run_names.clear();
-    uint64_t n_runs = std::min<uint64_t>(p->h_st.n_chrom_runs, hb_parse::kMaxRuns);
+    p->runs_valid = false;
     if (p->h_st.n_chrom_runs > hb_parse::kMaxRuns) return fail(HB_ERR_FORMAT, "more than 4096 CHROM runs (unsorted VCF?)");
-    if (n_runs) {
-        p->run_rows.resize(n_runs);
-        CU(cudaMemcpy(p->run_rows.data(), p->d_run_rows, n_runs * 8, cudaMemcpyDeviceToHost));
-        std::sort(p->run_rows.begin(), p->run_rows.end());
-        for (uint64_t r : p->run_rows) {
-            uint64_t abs; uint8_t len; char name[256];
-            CU(cudaMemcpy(&abs, p->d_chrom_abs + r, 8, cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(&len, p->d_chrom_len + r, 1, cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(name, p->d_text + abs, len, cudaMemcpyDeviceToHost));
-            p->run_names.emplace_back(name, name + len);
-        }
-    }
     if (p->h_st.n_bad_cols)
         return fail(HB_ERR_FORMAT, "Number of columns does not match the number of samples (" +
                                        std::to_string(p->h_st.n_bad_cols) + " records)");
@@ -876,6 +887,7 @@ int hb_parse_stream_host(const uint8_t *text, uint64_t nbytes, const hb_parse_op
 int hb_parse_release_text(hb_parse *p) {
     if (!p) return fail(HB_ERR_ARG, "null handle");
     if (p->d_text_owned) {
+        TRY(ensure_runs(p));                     // the CHROM names are read from the text
         CU(cudaSetDevice(p->device));
         {   // the caller wants the HBM back: not into the idle pool
             std::lock_guard<std::mutex> lk(g_pool.mu);
@@ -978,6 +990,7 @@ int hb_parse_fetch_sample_errors(hb_parse *p, uint32_t *ploidy, uint32_t *badgt)
 int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint64_t max_runs, char *names,
                         uint64_t names_cap, uint64_t *names_len) {
     if (!p || !n_runs) return fail(HB_ERR_ARG, "null argument");
+    TRY(ensure_runs(p));
     *n_runs = p->run_rows.size();
     uint64_t used = 0;
     for (size_t i = 0; i < p->run_rows.size(); ++i) {
@@ -1348,6 +1361,7 @@ int build_entry(CacheEntry &ce, const char *path, const char *region, bool want_
     uint64_t n = p->h_st.n_records;
     ce.start.resize(n); ce.stop.resize(n); ce.ref.resize(n); ce.alt.resize(n); ce.chrom_off.resize(n);
     TRY(hb_parse_fetch_sites(p, ce.start.data(), ce.stop.data(), ce.ref.data(), ce.alt.data()));
+    TRY(ensure_runs(p));
     for (size_t i = 0; i < p->run_rows.size(); ++i) {
         uint32_t off = (uint32_t)ce.chrom_pool.size();
         ce.chrom_pool.append(p->run_names[i]);
@@ -1769,6 +1783,7 @@ struct ResidentSink : SlabSink {
         TRY(new_parse(&oo, &big));
         big->samples = samples;
         big->text_released = true;             // there is no text to re-run on
+        big->runs_valid = true;                // its CHROM runs are put together from the slabs'
         return HB_OK;
     }
     int grow(uint64_t need, cudaStream_t st, uint64_t R) {          // capacity for `need` rows, the R rows present are kept
@@ -1830,6 +1845,7 @@ struct ResidentSink : SlabSink {
         if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_alt + R, s.p->d_alt, n, cudaMemcpyDeviceToDevice, s.d2h);
         if (e == cudaSuccess) e = cudaMemcpyAsync(big->d_chrom5 + R, s.p->d_chrom5, n * 8, cudaMemcpyDeviceToDevice, s.d2h);
         // CHROM runs of the slab continue the file's
+        TRY(ensure_runs(s.p));
         for (size_t i = 0; i < s.p->run_rows.size(); ++i) {
             if (!big->run_names.empty() && big->run_names.back() == s.p->run_names[i]) continue;
             big->run_rows.push_back(R + s.p->run_rows[i]);

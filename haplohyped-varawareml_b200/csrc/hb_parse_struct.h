@@ -64,6 +64,7 @@ struct hb_parse {
     // chrom runs (host)
     std::vector<uint64_t> run_rows;
     std::vector<std::string> run_names;
+    bool runs_valid = false;             // run_rows / run_names hold the runs of the last parse (fetched on demand)
     std::vector<std::string> samples;   // sample names when the parse was made from a file
     void *attached_frames = nullptr;    // hb_frames whose site templates are made while the GT decoder runs (hb_store.cu)
 };

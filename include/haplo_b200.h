@@ -164,7 +164,9 @@ int hb_parse_fetch_matrix(hb_parse *p, int8_t *gt0, int8_t *gt1); /* [n_samples]
 /* per-sample counts [n_samples]: records whose GT was not diploid (the reference aborts there,
  * parse_vcf.cpp:46) and records whose GT had an unreadable allele (htslib "Couldn't read GT data") */
 int hb_parse_fetch_sample_errors(hb_parse *p, uint32_t *ploidy, uint32_t *badgt);
-/* CHROM runs: rows [row_begin[i], row_begin[i+1]) share names[i]; names are written NUL-separated */
+/* CHROM runs: rows [row_begin[i], row_begin[i+1]) share names[i]; names are written NUL-separated.  The names are read
+ * from the text on the first call after a parse: a caller that owns the text buffer (hb_parse_device_text) must ask
+ * before it overwrites the buffer. */
 int hb_parse_chrom_runs(hb_parse *p, uint64_t *n_runs, uint64_t *row_begin, uint64_t max_runs,
                         char *names, uint64_t names_cap, uint64_t *names_len);
 void hb_parse_free(hb_parse *p);
