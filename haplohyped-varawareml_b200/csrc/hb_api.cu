@@ -295,6 +295,7 @@ void hb_parse_free(hb_parse *p) {
     if (!p) return;
     const double t_free0 = getenv("HB_TRACE") ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0;
     cudaSetDevice(p->device);
+    if (p->side) cudaStreamSynchronize(p->side);
     free_dev(p->d_text_owned); free_dev(p->d_nl_after); free_dev(p->d_cta); free_dev(p->d_cbase); free_dev(p->d_cp);
     free_dev(p->d_st); free_dev(p->d_start); free_dev(p->d_stop); free_dev(p->d_ref); free_dev(p->d_alt);
     free_dev(p->d_chrom_len); free_dev(p->d_chrom_abs); free_dev(p->d_chrom5); free_dev(p->d_rowinfo); free_dev(p->d_nu_rows);
@@ -302,6 +303,8 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+    if (p->ev_runs) cudaEventDestroy(p->ev_runs);
     pin_slot_release(p->h_st_pin);
     if (t_free0 > 0) fprintf(stderr, "[hb_parse_free] %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_free0);
     delete p;
@@ -538,6 +541,7 @@ static int ensure_runs(hb_parse *p) {
 }
 
 static int run_parse(hb_parse *p) {
+    ++p->run_seq;
     CU(cudaSetDevice(p->device));
     Launch L{p->stream, p->sm_count};
     if (!p->d_st) TRY(dev_alloc(&p->d_st, 1));
@@ -573,6 +577,16 @@ static int run_parse(hb_parse *p) {
     else TRY(index_by_tokenizer(p, L));
     const uint64_t n_rec = p->h_st.n_records;
     if (p->attached_frames && n_rec) frames_early_site_pass(p->attached_frames, p);
+    {   // CHROM runs need the site columns only: on a side stream, next to the decoder; the status fetch waits for them
+        if (!p->side) CU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+        if (!p->ev_runs) CU(cudaEventCreateWithFlags(&p->ev_runs, cudaEventDisableTiming));
+        CU(cudaEventRecord(p->ev_runs, p->stream));
+        CU(cudaStreamWaitEvent(p->side, p->ev_runs, 0));
+        Launch Ls = L;
+        Ls.stream = p->side;
+        launch_chrom_runs(p->d_text, p->d_chrom_abs, p->d_chrom_len, n_rec, p->d_run_rows, hb_parse::kMaxRuns, p->d_st, Ls);
+        CU(cudaEventRecord(p->ev_runs, p->side));
+    }
 
     // ---- GT decode
     if (p->want_gt && n_rec && p->n_samples) {
@@ -606,7 +620,10 @@ static int run_parse(hb_parse *p) {
                          p->gt_stride, p->d_bits, p->bits_stride, p->d_ploidy, p->d_badgt, p->d_st, L);
     }
     CU(cudaEventRecord(p->ev[3], p->stream));
-    launch_chrom_runs(p->d_text, p->d_chrom_abs, p->d_chrom_len, n_rec, p->d_run_rows, hb_parse::kMaxRuns, p->d_st, L);
+    // frames attached to this parse: their kernel is queued right behind the decoder now (the host waits for the templates
+    // only), instead of after this function's status fetch + the caller's next call
+    if (p->attached_frames && n_rec && p->want_gt && p->n_samples) frames_early_launch(p->attached_frames, p);
+    CU(cudaStreamWaitEvent(p->stream, p->ev_runs, 0));       // the CHROM runs (side stream) are part of the status
     TRY(fetch_status(p));
     CU(cudaGetLastError());
     cudaEventElapsedTime(&p->ms_tok, p->ev[0], p->ev[1]);

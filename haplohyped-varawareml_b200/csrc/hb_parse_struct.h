@@ -59,11 +59,14 @@ struct hb_parse {
     uint64_t *d_run_rows = nullptr;
     static constexpr uint64_t kMaxRuns = 4096;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side = nullptr;         // the CHROM-run kernel runs here, next to the GT decoder
+    cudaEvent_t ev_runs = nullptr;
     float ms_tok = 0, ms_sites = 0, ms_decode = 0, ms_inflate = 0;
     uint64_t compressed_bytes = 0;      // BGZF bytes shipped over PCIe when the file was inflated on the GPU
     // chrom runs (host)
     std::vector<uint64_t> run_rows;
     std::vector<std::string> run_names;
+    uint64_t run_seq = 0;                // counts run_parse calls (frames launched early belong to one of them)
     bool runs_valid = false;             // run_rows / run_names hold the runs of the last parse (fetched on demand)
     std::vector<std::string> samples;   // sample names when the parse was made from a file
     void *attached_frames = nullptr;    // hb_frames whose site templates are made while the GT decoder runs (hb_store.cu)
@@ -73,5 +76,6 @@ struct hb_parse {
 namespace hb {
 // hb_store.cu: start the site-template kernel of the attached frames on their side stream (called by run_parse)
 void frames_early_site_pass(void *frames, hb_parse *p);
+void frames_early_launch(void *frames, hb_parse *p);
 void frames_buffer_cache_clear();       // hb_store.cu: release the kept frame buffers
 }

@@ -913,6 +913,11 @@ struct hb_frames {
     cudaEvent_t ev_sites = nullptr, ev_tmpl = nullptr, ev_side0 = nullptr;
     bool early_site = false;                     // the template pass of the current parse run is already in flight
     uint64_t last_d2h_bytes = 0;                 // bytes the last hb_frames_fetch_packed moved device -> host
+    // frames launched from inside run_parse, right behind the GT decoder (frames_early_launch): hb_frames_rerun only collects
+    bool launched = false;
+    bool totals_valid = false;                   // total_bytes is summed when somebody asks (hb_frames_get_info)
+    uint64_t launched_run = 0, pending_need = 0;
+    bool pending_was_early = false;
 };
 
 // More than 48 KB of dynamic shared memory is opt-in per function AND per device.  The ceiling is always raised to the
@@ -989,7 +994,10 @@ void frames_early_site_pass(void *frames, hb_parse *p) {
 }
 }  // namespace hb
 
-static int frames_run(hb_frames *f, hb_parse *p) {
+// everything up to the launch of the frame kernel.  early: called from inside run_parse with the template pass in flight on
+// the side stream and the GT decoder queued on the main one -- the host waits for the TEMPLATES only (their lengths size the
+// slots), then queues the frame kernel behind the decoder: no idle GPU between the two.
+static int frames_prepare(hb_frames *f, hb_parse *p, bool early) {
     cudaError_t e;
 #define CUF(x) do { e = (x); if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e) + " at " #x); } while (0)
     CUF(cudaSetDevice(f->device));
@@ -997,7 +1005,7 @@ static int frames_run(hb_frames *f, hb_parse *p) {
     const uint32_t cr = (uint32_t)f->cr;
     const uint64_t n_frames = f->n_chunks * f->n_samples;
     f->layout_valid = false;
-    CUF(cudaMemsetAsync(f->d_totals, 0, 8, f->stream));
+    f->totals_valid = false;
     const bool was_early = f->early_site;
     if (was_early) {
         CUF(cudaStreamWaitEvent(f->stream, f->ev_tmpl, 0));       // the templates were made while the decoder ran
@@ -1007,9 +1015,11 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         if (rc != HB_OK) return rc;
     }
     f->early_site = false;
+    f->launched = false;
     // the frame buffer is sized from the longest template: frame <= template + worst-case allele tail
-    CUF(cudaMemcpyAsync(f->h_tmpl_len.data(), f->d_tmpl_len, f->n_chunks * 4, cudaMemcpyDeviceToHost, f->stream));
-    CUF(cudaStreamSynchronize(f->stream));
+    cudaStream_t lens = early && was_early ? f->side : f->stream;
+    CUF(cudaMemcpyAsync(f->h_tmpl_len.data(), f->d_tmpl_len, f->n_chunks * 4, cudaMemcpyDeviceToHost, lens));
+    CUF(cudaStreamSynchronize(lens));
     CUF(cudaGetLastError());
     // slots: frame <= template + worst-case allele tail, so every address is known before the encode
     uint64_t need = 0;
@@ -1066,21 +1076,44 @@ static int frames_run(hb_frames *f, hb_parse *p) {
         case 5: launch_donor_frames<5>(fa, n_ctas, f->stream); break;
         default: launch_donor_frames<6>(fa, n_ctas, f->stream); break;
     }
-    sum_sizes_kernel<<<296, 256, 0, f->stream>>>(f->d_size, n_frames, f->d_totals);
-    count_launch(2);
+    count_launch(1);
     CUF(cudaEventRecord(f->ev[2], f->stream));
-    unsigned long long tot = 0;
-    CUF(cudaMemcpyAsync(&tot, f->d_totals, 8, cudaMemcpyDeviceToHost, f->stream));
+    f->pending_need = need;
+    f->pending_was_early = was_early;
+    f->launched = true;
+    f->launched_run = p->run_seq;
+#undef CUF
+    return HB_OK;
+}
+
+static int frames_finish(hb_frames *f) {
+    cudaError_t e;
+#define CUF(x) do { e = (x); if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e) + " at " #x); } while (0)
+    f->launched = false;
+    CUF(cudaSetDevice(f->device));
     CUF(cudaStreamSynchronize(f->stream));
     CUF(cudaGetLastError());
-    f->padded_bytes = need;
-    f->total_bytes = tot;
-    if (was_early) cudaEventElapsedTime(&f->ms_site, f->ev_side0, f->ev_tmpl);
+    f->padded_bytes = f->pending_need;
+    if (f->pending_was_early) cudaEventElapsedTime(&f->ms_site, f->ev_side0, f->ev_tmpl);
     else cudaEventElapsedTime(&f->ms_site, f->ev[0], f->ev[1]);
     cudaEventElapsedTime(&f->ms_frames, f->ev[1], f->ev[2]);
 #undef CUF
     return HB_OK;
 }
+
+static int frames_run(hb_frames *f, hb_parse *p) {
+    int rc = frames_prepare(f, p, false);
+    return rc == HB_OK ? frames_finish(f) : rc;
+}
+
+namespace hb {
+// called by run_parse (hb_api.cu) right after the GT decoder of this run was launched
+void frames_early_launch(void *frames, hb_parse *p) {
+    hb_frames *f = static_cast<hb_frames *>(frames);
+    if (!f || !f->early_site || !f->n_chunks || !f->n_samples) return;      // no template pass in flight for this run
+    if (frames_prepare(f, p, true) != HB_OK) f->launched = false;             // hb_frames_rerun will do (and report) it
+}
+}  // namespace hb
 
 static int frames_layout(hb_frames *f) {
     if (f->layout_valid) return HB_OK;
@@ -1204,6 +1237,7 @@ int hb_frames_rerun(hb_frames *f, hb_parse *p) {
         f->early_site = false;                   // an early template pass (if any) was made for the old shape
     }
     if (!f->n_chunks || !f->n_samples) return HB_OK;
+    if (f->launched && f->launched_run == p->run_seq) return frames_finish(f);     // launched behind the decoder of this very run
     return frames_run(f, p);
 }
 
@@ -1213,6 +1247,7 @@ int hb_frames_set_window(hb_frames *f, uint32_t s0, uint32_t ns) {
     f->s0 = s0;
     f->n_samples = ns;
     f->layout_valid = false;
+    f->launched = false;
     return HB_OK;
 }
 
@@ -1220,6 +1255,21 @@ int hb_frames_get_info(const hb_frames *f, hb_frames_info *info) {
     if (!f || !info) return api_fail(HB_ERR_ARG, "null argument");
     memset(info, 0, sizeof *info);
     info->n_records = f->n_records; info->n_chunks = f->n_chunks; info->chunk_records = f->cr;
+    if (!f->totals_valid && f->n_chunks && f->n_samples && f->d_size) {       // sum of the frame sizes, on demand (18 us of kernel per step otherwise)
+        hb_frames *w = const_cast<hb_frames *>(f);
+        unsigned long long tot = 0;
+        cudaError_t e = cudaSetDevice(f->device);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w->d_totals, 0, 8, w->stream);
+        if (e == cudaSuccess) {
+            sum_sizes_kernel<<<296, 256, 0, w->stream>>>(w->d_size, w->n_chunks * w->n_samples, w->d_totals);
+            count_launch();
+            e = cudaMemcpyAsync(&tot, w->d_totals, 8, cudaMemcpyDeviceToHost, w->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) return api_fail(HB_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+        w->total_bytes = tot;
+        w->totals_valid = true;
+    }
     info->n_samples = f->n_samples; info->total_bytes = f->total_bytes;
     info->raw_bytes = 35ull * f->n_records * f->n_samples;
     info->ms_site = f->ms_site; info->ms_frames = f->ms_frames;
