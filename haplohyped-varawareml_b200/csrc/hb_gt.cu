@@ -286,32 +286,31 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 if (lane >= d) inc += t;
             }
             uint32_t k = seen + inc - cnt;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t mm = m[q];
-                while (mm) {
-                    const int bit = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (k < ns) {
-                        int a0, a1, pl;
-                        const int rel = 16 * lane + 4 * q + (bit >> 3) + 1;          // first byte of the field, in `row`
-                        const uint32_t *fw = reinterpret_cast<const uint32_t *>(row + (rel & ~3));
-                        const uint32_t x = __funnelshift_r(fw[0], fw[1], (rel & 3) * 8);
-                        const uint32_t X = x & 0xffu, sep = (x >> 8) & 0xffu, Y = (x >> 16) & 0xffu, T = x >> 24;
-                        const uint32_t dx = X - '0', dy = Y - '0';
-                        if (g == 0 && (sep == '|' || sep == '/') && (T == ':' || T == '\t' || T == '\n' || T == '\r') &&
-                            (dx <= 9u || X == '.') && (dy <= 9u || Y == '.')) {
-                            a0 = X == '.' ? -9 : (int)dx;
-                            a1 = Y == '.' ? -9 : (int)dy;
-                            pl = 2;
-                        } else pl = decode_field(text, o + 4ull * q + (bit >> 3) + 1, g, a0, a1);
-                        if (pl < 0) { atomicAdd(&st->n_bad_gt, 1ull); atomicAdd(&badgt_err[s0 + k], 1u); a0 = 0; a1 = 0; }
-                        else if (pl != 2) atomicAdd(&ploidy_err[s0 + k], 1u);
-                        sm.out[0][k][r] = (uint8_t)a0;
-                        sm.out[1][k][r] = (uint8_t)a1;
-                    }
-                    ++k;
+            // one bit per byte of the lane's 16: the lane walks ITS tabs (1-2 for "a|b:GQ:DP" fields), not word by word --
+            // per-word loops ran 4 passes per piece with a third of the lanes in each
+            uint32_t mm = pack_lsb4(m[0] >> 7) | (pack_lsb4(m[1] >> 7) << 4) | (pack_lsb4(m[2] >> 7) << 8) | (pack_lsb4(m[3] >> 7) << 12);
+            while (mm) {
+                const int bit = __ffs(mm) - 1;                                   // byte of the TAB inside the lane's 16
+                mm &= mm - 1;
+                if (k < ns) {
+                    int a0, a1, pl;
+                    const int rel = 16 * lane + bit + 1;                         // first byte of the field, in `row`
+                    const uint32_t *fw = reinterpret_cast<const uint32_t *>(row + (rel & ~3));
+                    const uint32_t x = __funnelshift_r(fw[0], fw[1], (rel & 3) * 8);
+                    const uint32_t X = x & 0xffu, sep = (x >> 8) & 0xffu, Y = (x >> 16) & 0xffu, T = x >> 24;
+                    const uint32_t dx = X - '0', dy = Y - '0';
+                    if (g == 0 && (sep == '|' || sep == '/') && (T == ':' || T == '\t' || T == '\n' || T == '\r') &&
+                        (dx <= 9u || X == '.') && (dy <= 9u || Y == '.')) {
+                        a0 = X == '.' ? -9 : (int)dx;
+                        a1 = Y == '.' ? -9 : (int)dy;
+                        pl = 2;
+                    } else pl = decode_field(text, o + (uint64_t)bit + 1, g, a0, a1);
+                    if (pl < 0) { atomicAdd(&st->n_bad_gt, 1ull); atomicAdd(&badgt_err[s0 + k], 1u); a0 = 0; a1 = 0; }
+                    else if (pl != 2) atomicAdd(&ploidy_err[s0 + k], 1u);
+                    sm.out[0][k][r] = (uint8_t)a0;
+                    sm.out[1][k][r] = (uint8_t)a1;
                 }
+                ++k;
             }
             seen += __shfl_sync(0xffffffffu, inc, 31);
             __syncwarp();                                     // the row is overwritten by the next 512 bytes
