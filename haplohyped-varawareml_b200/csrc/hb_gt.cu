@@ -254,31 +254,27 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
             const uint64_t o = base + 16ull * lane;
             const uint4 v = nxt;
             nxt = make_uint4(0, 0, 0, 0);
-            if (o + 512 < e) nxt = *reinterpret_cast<const uint4 *>(text + o + 512);
+            if (o + 512 < e + 4) nxt = *reinterpret_cast<const uint4 *>(text + o + 512);     // (+ 4: the look-ahead of a field that ends the segment; the buffer has slack)
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            // the 512 bytes (+ 16 of look-ahead) also go to this record's row of the staging buffer, which the general
-            // path does not use otherwise: the common field shape "X|Y" + terminator is then decoded from shared memory
-            // with one unaligned 4-byte read instead of a byte-wise parse over global memory
+            // the 512 bytes (+ 16 of look-ahead = lane 0's next piece) also go to this record's row of the staging buffer,
+            // which the general path does not use otherwise: the common field shape "X|Y" + terminator is then decoded from
+            // shared memory with one unaligned 4-byte read instead of a byte-wise parse over global memory
             uint8_t *row = sm.text[r];
             *reinterpret_cast<uint4 *>(row + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-            if (lane == 0) {                                  // 16 bytes of look-ahead: lane 0's next piece (zeros past the segment,
-                uint4 x = nxt;                                //  except its first 4 bytes, which a field that ends the segment reads)
-                if (!(base + 512 < e) && base + 512 < e + 4) x = *reinterpret_cast<const uint4 *>(text + base + 512);
-                *reinterpret_cast<uint4 *>(row + 512) = x;
-            }
+            if (lane == 0) *reinterpret_cast<uint4 *>(row + 512) = nxt;
             __syncwarp();
-            uint32_t m[4], cnt = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                m[q] = eq_mask(w[q], kTab4);
-                const uint64_t wo = o + 4ull * q;
-                if (wo < b || wo + 4 > e) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (wo + k < b || wo + k >= e) m[q] &= ~(0x80u << (8 * k));
-                }
-                cnt += __popc(m[q]);
+            // one bit per byte of the lane's 16 that is a TAB inside [b, e): the lane walks ITS tabs (1-2 for "a|b:GQ:DP"
+            // fields) in one loop -- per-word loops ran 4 passes per piece with a third of the lanes in each, and the
+            // per-byte range test of the first / last piece (most pieces: a segment is 2-3 of them) was 22 % of the instructions
+            uint32_t mm = pack_lsb4(eq_mask(w[0], kTab4) >> 7) | (pack_lsb4(eq_mask(w[1], kTab4) >> 7) << 4) |
+                          (pack_lsb4(eq_mask(w[2], kTab4) >> 7) << 8) | (pack_lsb4(eq_mask(w[3], kTab4) >> 7) << 12);
+            {
+                const int64_t lo = (int64_t)b - (int64_t)o, hi = (int64_t)e - (int64_t)o;      // valid bytes of the lane: [lo, hi) within 0..16
+                const uint32_t below_lo = lo <= 0 ? 0u : (lo >= 16 ? 0xFFFFu : (1u << lo) - 1u);
+                const uint32_t below_hi = hi <= 0 ? 0u : (hi >= 16 ? 0xFFFFu : (1u << hi) - 1u);
+                mm &= below_hi & ~below_lo;
             }
+            const uint32_t cnt = __popc(mm);
             uint32_t inc = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -286,9 +282,6 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 if (lane >= d) inc += t;
             }
             uint32_t k = seen + inc - cnt;
-            // one bit per byte of the lane's 16: the lane walks ITS tabs (1-2 for "a|b:GQ:DP" fields), not word by word --
-            // per-word loops ran 4 passes per piece with a third of the lanes in each
-            uint32_t mm = pack_lsb4(m[0] >> 7) | (pack_lsb4(m[1] >> 7) << 4) | (pack_lsb4(m[2] >> 7) << 8) | (pack_lsb4(m[3] >> 7) << 12);
             while (mm) {
                 const int bit = __ffs(mm) - 1;                                   // byte of the TAB inside the lane's 16
                 mm &= mm - 1;
