@@ -456,6 +456,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--slab-bytes", type=int, default=1 << 30, help="slab size of the streamed e2e paths")
     ap.add_argument("--parse-only", action="store_true", help="step = kernels 1-3 only (no frames)")
+    ap.add_argument("--site-matcher", choices=["fast", "deep"], default="fast",
+                    help="deep: 4-way hash buckets in the site-plane encoder (hb_set_site_matcher): smaller chunks, slower kernel 4a")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -476,6 +478,7 @@ def main():
     # host threads of the library (frame assembly in hb_frames_fetch_packed): this rank's share of the CPUs it may run on
     host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, world)))
     capi.lib().hb_set_host_threads(host_threads)
+    capi.lib().hb_set_site_matcher(1 if args.site_matcher == "deep" else 0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # rank 0 prints ONE line on stdout: whatever libraries print there meanwhile (NCCL's version banner, when NCCL_DEBUG

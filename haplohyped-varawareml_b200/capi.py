@@ -380,14 +380,14 @@ class Frames:
         into buf, sizes uint32 [n_samples, n_chunks]).  out: a pre-allocated uint8 array / (address, capacity) to fill (e.g.
         pinned memory), else a new numpy array."""
         i = self.info
-        offs = np.zeros((i.n_samples, i.n_chunks), np.uint64)
-        sizes = np.zeros((i.n_samples, i.n_chunks), np.uint32)
+        offs = np.empty((i.n_samples, i.n_chunks), np.uint64)
+        sizes = np.empty((i.n_samples, i.n_chunks), np.uint32)
         tot = C.c_uint64()
-        check(lib().hb_frames_fetch_packed(self._h, None, 0, offs.ctypes.data, sizes.ctypes.data, C.byref(tot)))
-        if out is None:
+        if out is None:                                   # how many bytes?  then one more call for the data
+            check(lib().hb_frames_fetch_packed(self._h, None, 0, None, None, C.byref(tot)))
             out = np.empty(max(1, tot.value), np.uint8)
         addr, cap = (out.ctypes.data, out.size) if isinstance(out, np.ndarray) else (int(out[0]), int(out[1]))
-        check(lib().hb_frames_fetch_packed(self._h, addr, cap, None, None, C.byref(tot)))
+        check(lib().hb_frames_fetch_packed(self._h, addr, cap, offs.ctypes.data, sizes.ctypes.data, C.byref(tot)))
         return (out[:tot.value] if isinstance(out, np.ndarray) else tot.value), offs, sizes
 
     def sample(self, s: int):
