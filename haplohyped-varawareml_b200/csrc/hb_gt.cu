@@ -108,12 +108,12 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     extern __shared__ __align__(128) uint8_t smem_raw[];
     GtSmem &sm = *reinterpret_cast<GtSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t tile = blockIdx.x;
-    const uint32_t tile_s = (uint32_t)(tile % n_stiles);
-    const uint64_t tile_r = tile / n_stiles;
+    const uint32_t tile = blockIdx.x;                      // (32-bit on purpose: a 64-bit divide is ~100 dependent instructions
+    const uint32_t tile_r = tile / n_stiles;               //  at the head of every CTA's critical path)
+    const uint32_t tile_s = tile - tile_r * n_stiles;
     const uint32_t s0 = tile_s * kTS;
     const uint32_t ns = min((uint32_t)kTS, n_samples - s0);
-    const uint64_t r0 = tile_r * kTV;
+    const uint64_t r0 = (uint64_t)tile_r * kTV;
     const uint32_t nr = (uint32_t)min((uint64_t)kTV, n_rows - r0);
 
     if (tid == 0) {
@@ -155,10 +155,11 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         }
         // The tile that will run in this CTA's slot once it retires (pf_dist tiles ahead = resident CTAs of the whole
         // GPU): its text is pulled into L2 now (UBLKPF), so that CTA's TMA loads find it there instead of in DRAM.
-        const uint64_t tf = tile + pf_dist;
-        if (pf_dist && tf < gridDim.x) {
-            const uint32_t s0f = (uint32_t)(tf % n_stiles) * kTS;
-            const uint64_t rf = (tf / n_stiles) * kTV + tid;
+        const uint32_t tf = tile + pf_dist;
+        if (pf_dist && tf < gridDim.x && tf > tile) {
+            const uint32_t trf = tf / n_stiles;
+            const uint32_t s0f = (tf - trf * n_stiles) * kTS;
+            const uint64_t rf = (uint64_t)trf * kTV + tid;
             if (rf < n_rows) {
                 const RowInfo rif = rowinfo[rf];
                 if ((rif.misc & kRowHasSamples) && (rif.misc & kRowUniform) && (rif.misc & 0xffu) != 255u) {
