@@ -334,3 +334,32 @@ def test_two_gpus_write_the_same_datasets(mods, tmp_path):
     assert got["one"] == got["two"]
     plan = v2h.VCFtoHDF5Converter("c", str(vdir), str(tmp_path / "p"), str(tmp_path / "donors.txt"), 2, 4, devices=[0, 1]).plan_devices([1, 4, 9, 17, 22])
     assert all(plan) and sorted(c for b in plan for c in b) == [1, 4, 9, 17, 22]
+
+
+def test_general_text_full_width_parity(mods):
+    """The general path at the cohort's width: FORMAT=GT:GQ:DP text of 2,504 samples (variable-width fields, unphased and
+    missing calls, dropped sites), 4,000 records -- tokenizer with column checkpoints + tab-scanning decoder: the WHOLE
+    matrix, the site columns and every stored chunk of 4 donors against the oracle."""
+    capi = mods[0]
+    block, samples = synth.random_vcf(160, 2504, seed=91, fmt="GT:GQ:DP", kinds="mixed", site_mix=True)
+    body = synth.body_of(block)
+    text = block[:len(block) - len(body)] + body * 25
+    ora = oracle.parse_text(text, "*", "chr22")
+    p = capi.Parse.from_host(synth.body_of(text), 2504, region="chr22")
+    assert p.info.n_records == ora["n"] and ora["n"] > 3000 and p.info.tokenizer_used == 2
+    g0, g1 = p.matrix()
+    assert np.array_equal(g0, ora["gt0"]) and np.array_equal(g1, ora["gt1"])
+    start, stop, ref, alt = p.sites()
+    assert np.array_equal(start, ora["start"]) and np.array_equal(stop, ora["stop"])
+    assert np.array_equal(ref, ora["ref"]) and np.array_equal(alt, ora["alt"])
+    pe, be = p.sample_errors()
+    assert not pe.any() and not be.any()
+    fr = p.compress(0)
+    cr, nc = int(fr.info.chunk_records), int(fr.info.n_chunks)
+    pk, offs, sizes = fr.fetch_packed()
+    for s in (0, 127, 128, 2503):                              # both sides of a decode-tile seam, first and last donor
+        rec = oracle.records_from_columns(ora["chrom"], ora["start"], ora["stop"], ora["ref"], ora["alt"], ora["gt0"][s], ora["gt1"][s])
+        raw = rec.tobytes() + b"\0" * (nc * cr * 35 - rec.nbytes)
+        for c in range(nc):
+            f = pk[int(offs[s, c]):int(offs[s, c]) + int(sizes[s, c])].tobytes()
+            assert oracle.blosc_chunk_decode(f, cr * 35).tobytes() == raw[c * cr * 35:(c + 1) * cr * 35], (s, c)
