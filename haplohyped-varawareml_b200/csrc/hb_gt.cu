@@ -41,7 +41,6 @@ struct GtSmem {
     uint32_t seg_g[kTV];
     int mode[kTV];                        // 0 nothing to decode (zeros), 1 staged fast path, 2 general path
     alignas(8) uint64_t bar;
-    uint32_t tx_total;
     uint32_t any_general;                 // some record of the tile takes the general path (phase 2)
 };
 
@@ -118,9 +117,8 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     const uint32_t nr = (uint32_t)min((uint64_t)kTV, n_rows - r0);
 
     if (tid == 0) {
-        mbar_init(&sm.bar, 1);
+        mbar_init(&sm.bar, kTV);                           // every record's thread arrives, with the bytes it requested
         mbar_fence_init();
-        sm.tx_total = 0;
         sm.any_general = 0;
     }
     if (tid < kTS + 4) sm.dummy[tid] = 0x307C3009u;
@@ -155,6 +153,24 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 }
             }
         }
+        sm.seg_begin[tid] = b;
+        sm.seg_len[tid] = len;
+        sm.seg_g[tid] = g;
+        sm.mode[tid] = mode;
+        if (mode == 2) sm.any_general = 1u;
+        if (mode == 1) {
+            sm.addr[tid] = (uint32_t)tid * SEG_PITCH + ((uint32_t)(b & 15ull) & ~3u);
+            sm.shft[tid] = 8u * ((uint32_t)b & 3u);
+            // the record's segment is requested the moment its RowInfo is here (no CTA barrier, no byte total first), and
+            // BEFORE this thread reads the RowInfo of the tile it prefetches: that second load was on every tile's critical path
+            const uint32_t bytes = (uint32_t)(((b & 15ull) + len + 15ull) & ~15ull);
+            mbar_expect_tx(&sm.bar, bytes);
+            tma_load_1d(sm.text[tid], text + (b & ~15ull), bytes, &sm.bar);
+        } else {
+            sm.addr[tid] = (uint32_t)(reinterpret_cast<const uint8_t *>(sm.dummy) - &sm.text[0][0]);
+            sm.shft[tid] = 0;
+            mbar_arrive(&sm.bar);
+        }
         // The tile that will run in this CTA's slot once it retires (pf_dist tiles ahead = resident CTAs of the whole
         // GPU): its text is pulled into L2 now (UBLKPF), so that CTA's TMA loads find it there instead of in DRAM.
         const uint32_t tf = tile + pf_dist;
@@ -172,38 +188,12 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
                 }
             }
         }
-        sm.seg_begin[tid] = b;
-        sm.seg_len[tid] = len;
-        sm.seg_g[tid] = g;
-        sm.mode[tid] = mode;
-        if (mode == 2) sm.any_general = 1u;
-        if (mode == 1) {
-            sm.addr[tid] = (uint32_t)tid * SEG_PITCH + ((uint32_t)(b & 15ull) & ~3u);
-            sm.shft[tid] = 8u * ((uint32_t)b & 3u);
-        } else {
-            sm.addr[tid] = (uint32_t)(reinterpret_cast<const uint8_t *>(sm.dummy) - &sm.text[0][0]);
-            sm.shft[tid] = 0;
-        }
-        if (mode == 1) {
-            uint32_t bytes = (uint32_t)(((b & 15ull) + len + 15ull) & ~15ull);
-            atomicAdd(&sm.tx_total, bytes);
-        }
-    }
-    __syncthreads();
-    const uint32_t tx_total = sm.tx_total;
-    if (tx_total) {
-        if (tid == 0) mbar_expect_tx(&sm.bar, tx_total);
-        if (tid < kTV && sm.mode[tid] == 1) {
-            uint64_t b = sm.seg_begin[tid];
-            uint32_t bytes = (uint32_t)(((b & 15ull) + sm.seg_len[tid] + 15ull) & ~15ull);
-            tma_load_1d(sm.text[tid], text + (b & ~15ull), bytes, &sm.bar);
-        }
         if (pf_bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(text + pf_addr), "r"(pf_bytes) : "memory");
-        // ONE thread waits for the bulk copies, the CTA barrier releases the rest: 256 threads spinning on try_wait were
-        // 8.7 % of the kernel's instructions (r02a ncu), issue slots taken from the CTAs that share the SM
-        if (tid == 0) mbar_wait(&sm.bar, 0);
-        __syncthreads();
     }
+    // ONE thread waits for the bulk copies, the CTA barrier releases the rest: 256 threads spinning on try_wait were
+    // 8.7 % of the kernel's instructions (r02a ncu), issue slots taken from the CTAs that share the SM
+    if (tid == kTV) mbar_wait(&sm.bar, 0);                 // (a thread that has no record to locate first)
+    __syncthreads();
 
     // ---- phase 1: fast path.  One thread = 1 sample x 16 records; lanes run along samples, so the
     //      two 4-byte loads per call and the 16-byte transposed stores are bank-conflict free.
