@@ -1,7 +1,8 @@
 """Multi-GPU sharding of the conversion path.
 
-The path partitions into independent units -- one (chromosome file) or one BGZF-block byte range --
-so ranks never exchange genotype data.  The only collective is an all_gather of a few int64 of
+The path partitions into independent units -- chromosome files -- so ranks never exchange genotype
+data.  (Splitting ONE file over GPUs by BGZF-member range is not built: the HDF5 chunk that straddles two
+ranks' rows needs a boundary-row exchange)  The only collective is an all_gather of a few int64 of
 per-shard index metadata (record counts, first/last position, byte counts), which turns local
 record indices into global chunk ranges.  One process per GPU; `torch.distributed` is plumbing
 (NCCL on GPUs, gloo in the CPU tests).
@@ -27,20 +28,6 @@ def plan_shards(sizes: Sequence[int], world: int) -> List[List[int]]:
         bins[r].append(i)
         load[r] += sizes[i]
     return [sorted(b) for b in bins]
-
-
-def byte_ranges(total: int, world: int, align: int = 1 << 16) -> List[tuple]:
-    """Fine-grained alternative: split one file's bytes into `world` contiguous ranges aligned to
-    `align` (a BGZF block is <= 64 KiB).  A shard starts at the first record boundary at or after
-    its begin and runs past its end to finish its last record."""
-    per = -(-total // world)
-    per = -(-per // align) * align
-    out = []
-    for r in range(world):
-        b = min(total, r * per)
-        e = min(total, (r + 1) * per)
-        out.append((b, e))
-    return out
 
 
 def gather_metadata(meta: Dict[str, int], device=None) -> List[Dict[str, int]]:
