@@ -302,6 +302,8 @@ void hb_parse_free(hb_parse *p) {
     free_dev(p->d_sites_state); free_dev(p->d_gt[0]); free_dev(p->d_gt[1]); free_dev(p->d_bits); free_dev(p->d_ploidy);
     free_dev(p->d_badgt); free_dev(p->d_run_rows);
     free_dev(p->d_wstart); free_dev(p->d_wrow); free_dev(p->d_verify); free_dev(p->d_wcount);
+    free_dev(p->walk_pad.start); free_dev(p->walk_pad.stop); free_dev(p->walk_pad.ref); free_dev(p->walk_pad.alt);
+    free_dev(p->walk_pad.chrom_abs); free_dev(p->walk_pad.chrom_len); free_dev(p->walk_pad.chrom5); free_dev(p->walk_pad.rowinfo);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
     if (p->ev_runs) cudaEventDestroy(p->ev_runs);
@@ -489,9 +491,20 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
             p->walk_cap = p->n_walkers;
         }
     }
+    {   // padded rows of the walk and the list of spans to verify: sized by the walkers, known before anything runs
+        const uint64_t cap = (uint64_t)p->n_walkers * kWalkSlots;
+        hb::WalkPad &w = p->walk_pad;
+        if (w.cap < cap) {
+            TRY(dev_alloc(&w.start, cap)); TRY(dev_alloc(&w.stop, cap)); TRY(dev_alloc(&w.ref, cap)); TRY(dev_alloc(&w.alt, cap));
+            TRY(dev_alloc(&w.chrom_abs, cap)); TRY(dev_alloc(&w.chrom_len, cap)); TRY(dev_alloc(&w.chrom5, cap));
+            TRY(dev_alloc(&w.rowinfo, cap));
+            w.cap = cap;
+        }
+        if (p->verify_cap < cap || !p->d_verify) { TRY(dev_alloc(&p->d_verify, cap)); p->verify_cap = cap; }
+    }
     CU(cudaEventRecord(p->ev[0], p->stream));
-    launch_walk_count(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
-                      p->d_wstart, p->d_wcount, p->d_wrow, p->d_st, L);
+    launch_walk(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int, p->d_wstart, p->d_wcount,
+                p->d_wrow, p->walk_pad, p->d_verify, p->verify_cap, p->d_st, L);
     CU(cudaEventRecord(p->ev[1], p->stream));
     TRY(fetch_status(p));
     CU(cudaGetLastError());
@@ -506,13 +519,9 @@ static int index_by_walker(hb_parse *p, const Launch &L) {
         if (p->d_sites_state) { free_dev(p->d_sites_state); p->d_sites_state = nullptr; }
         p->row_cap = cap;
     }
-    if (p->verify_cap < n_lines || !p->d_verify) {
-        const uint64_t cap = p->d_verify ? n_lines + n_lines / 8 + 1024 : n_lines;
-        TRY(dev_alloc(&p->d_verify, cap)); p->verify_cap = cap;
-    }
-    launch_walk_write(p->d_text, p->nbytes, p->n_samples, p->walk_range, p->n_walkers, p->rg, p->end_is_int,
-                      p->d_wstart, p->d_wcount, p->d_wrow, p->d_start, p->d_stop, p->d_ref, p->d_alt, p->d_chrom_abs,
-                      p->d_chrom_len, p->d_chrom5, p->d_rowinfo, p->d_nu_rows, p->d_verify, p->verify_cap, p->d_st, L);
+    launch_walk_compact(p->d_text, p->nbytes, p->n_samples, p->n_walkers, p->d_wcount, p->d_wrow, p->walk_pad, p->d_start, p->d_stop,
+                        p->d_ref, p->d_alt, p->d_chrom_abs, p->d_chrom_len, p->d_chrom5, p->d_rowinfo, p->d_nu_rows, p->d_verify,
+                        p->verify_cap, p->d_st, L);
     CU(cudaEventRecord(p->ev[2], p->stream));
     p->index_used = 3;
     return HB_OK;

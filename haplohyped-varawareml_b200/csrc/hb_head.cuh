@@ -178,7 +178,7 @@ __device__ __forceinline__ void write_site_row(const SiteOut &o, const uint8_t *
         else if (!v.uniform) {
             const unsigned long long slot = atomicAdd(&o.st->n_nonuniform, 1ull);
             if (cp_row_by_line != kNoCpRow) ri.cp_row = cp_row_by_line;
-            else { ri.cp_row = (uint32_t)slot; o.nu_rows[slot] = (uint32_t)row; }
+            else { ri.cp_row = (uint32_t)slot; if (o.nu_rows) o.nu_rows[slot] = (uint32_t)row; }
         }
     }
     o.rowinfo[row] = ri;

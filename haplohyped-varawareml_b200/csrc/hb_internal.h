@@ -83,14 +83,22 @@ void launch_sites(const uint8_t *d_text, const LineIndex &li, uint64_t n_lines, 
                   const Launch &L);
 // index-free record location for GT-only text (hb_walk.cu)
 uint32_t walk_plan(uint64_t nbytes, uint64_t first_line_len, uint32_t lines_per_walker, uint64_t *range_bytes);
-void launch_walk_count(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
-                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
-                       uint64_t *d_wrow, DevStatus *d_st, const Launch &L);
-void launch_walk_write(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
-                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
-                       uint64_t *d_wrow, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt,
-                       uint64_t *d_chrom_abs, uint8_t *d_chrom_len, uint64_t *d_chrom5, RowInfo *d_rowinfo,
-                       uint32_t *d_nu_rows, uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L);
+// walker (hb_walk.cu): padded site rows, kWalkSlots per walker, compacted to dense rows after the prefix sum
+constexpr uint32_t kWalkSlots = 24;
+struct WalkPad {
+    uint32_t *start = nullptr, *stop = nullptr;
+    uint8_t *ref = nullptr, *alt = nullptr, *chrom_len = nullptr;
+    uint64_t *chrom_abs = nullptr, *chrom5 = nullptr;
+    RowInfo *rowinfo = nullptr;
+    uint64_t cap = 0;                        // rows
+};
+void launch_walk(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes, uint32_t n_walkers,
+                 const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount, uint64_t *d_wrow, const WalkPad &pad,
+                 uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L);
+void launch_walk_compact(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint32_t n_walkers, void *d_wcount,
+                         uint64_t *d_wrow, const WalkPad &pad, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt,
+                         uint64_t *d_chrom_abs, uint8_t *d_chrom_len, uint64_t *d_chrom5, RowInfo *d_rowinfo,
+                         uint32_t *d_nu_rows, uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L);
 void launch_chrom_runs(const uint8_t *d_text, const uint64_t *d_chrom_abs, const uint8_t *d_chrom_len,
                        uint64_t n_rows, uint64_t *d_run_rows, uint64_t max_runs, DevStatus *d_st,
                        const Launch &L);

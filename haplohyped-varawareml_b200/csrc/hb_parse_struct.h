@@ -27,6 +27,7 @@ struct hb_parse {
     uint64_t *d_wstart = nullptr, *d_wrow = nullptr, *d_verify = nullptr;
     void *d_wcount = nullptr;
     uint64_t verify_cap = 0;
+    hb::WalkPad walk_pad;                // padded site rows of the walk (compacted into d_start ... d_rowinfo)
     int walker_fallbacks = 0;
     int index_used = 0;                 // 1 newline tokenizer, 2 newline+tab tokenizer, 3 walker
     uint32_t ncp = 0;

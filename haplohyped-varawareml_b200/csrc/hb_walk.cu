@@ -18,8 +18,10 @@
 //     decoder validates every 4-byte group of the records it decodes (hb_gt.cu raises
 //     DevStatus::index_invalid on a newline), and the spans nobody decodes (records dropped by
 //     the SNP / region filter, or not plain-GT) are scanned by walk_verify_kernel.
-// Two passes over the heads (count, then write) give every walker its dense output row base with
-// one small prefix sum in between; the second pass hits L2.
+// ONE pass over the heads (r02): a walker writes the rows it keeps into its own kWalkSlots slots of padded site arrays and
+// counts them, one small prefix sum gives every walker its dense row base, and a compaction kernel moves the rows (54
+// bytes each) to their dense places -- the second head-parsing pass of r01 (0.25 ms, instruction-bound at 14 warps per SM)
+// became a 50 MB copy.
 #include <algorithm>
 #include <cstring>
 
@@ -42,7 +44,8 @@ struct WalkArgs {
     uint64_t *wstart;        // [n_walkers + 1] first record start at/after w * range_bytes; [n_walkers] = nbytes
     uint2 *wcount;           // [n_walkers] (lines, kept rows)
     uint64_t *wrow;          // [n_walkers] exclusive prefix sum of kept rows
-    SiteOut out;
+    SiteOut out;             // dense rows (compaction) 
+    SiteOut pad;             // [n_walkers * kWalkSlots] padded rows (walk)
     uint64_t *verify;        // spans (offset of their 9th tab) that the decoder will not validate
     uint64_t verify_cap;
     DevStatus *st;
@@ -161,18 +164,16 @@ __device__ __noinline__ uint64_t find_newline(const uint8_t *text, uint64_t nbyt
 }
 
 // ------------------------------------------------------------------------------------------
-// Pass 1 (kWrite = false): count lines and kept rows per walker.
-// Pass 2 (kWrite = true):  same walk, rows written at wrow[w] + local rank.
+// The walk: lines and kept rows per walker are counted, kept rows written to the walker's padded slots.
 // ------------------------------------------------------------------------------------------
-template <bool kWrite>
 __global__ void __launch_bounds__(WK_THREADS) walk_kernel(const WalkArgs a) {
     const uint32_t w = blockIdx.x * WK_THREADS + threadIdx.x;
     if (w >= a.n_walkers) return;
     uint64_t p = a.wstart[w];
     const uint64_t end = a.wstart[w + 1];
-    if (p >= end) { if (!kWrite) a.wcount[w] = make_uint2(0, 0); return; }
+    if (p >= end) { a.wcount[w] = make_uint2(0, 0); return; }
     uint32_t lines = 0, kept = 0;
-    const uint64_t row0 = kWrite ? a.wrow[w] : 0;
+    const uint64_t row0 = (uint64_t)w * kWalkSlots;
     const uint64_t span = 4ull * a.n_samples;
     ByteStream bs;
     bs.init(a.text, a.nbytes, p);
@@ -231,20 +232,21 @@ __global__ void __launch_bounds__(WK_THREADS) walk_kernel(const WalkArgs a) {
         ++lines;
         if (skip || le == ls) continue;                       // '#' line or empty line: ignored
         const HeadVerdict v = judge_head(h, le, a.n_samples, a.rg, a.end_is_int);
-        if (kWrite) {
-            if (v.malformed) atomicAdd(&a.out.st->n_bad_cols, 1ull);
-            if (v.keep) write_site_row(a.out, a.text, row0 + kept, ls, le, h, v, 1, kNoCpRow);
-            if (fast && !(v.keep && v.uniform)) {
-                const unsigned long long k = atomicAdd(&a.st->n_verify, 1ull);
-                if (k < a.verify_cap) a.verify[k] = h.samp_abs;
-                else a.st->index_invalid = 1u;               // cannot be proven: make the caller fall back
-            }
+        if (v.malformed) atomicAdd(&a.st->n_bad_cols, 1ull);
+        if (v.keep) {
+            if (kept < kWalkSlots) write_site_row(a.pad, a.text, row0 + kept, ls, le, h, v, 1, kNoCpRow);
+            else a.st->walk_broken = 1u;                     // more kept lines in a range than slots: the caller falls back
         }
-        if (!kWrite && v.keep && h.has_samples && h.g >= 0 && !v.uniform) atomicAdd(&a.st->n_nu_count, 1ull);
+        if (fast && !(v.keep && v.uniform)) {
+            const unsigned long long k = atomicAdd(&a.st->n_verify, 1ull);
+            if (k < a.verify_cap) a.verify[k] = h.samp_abs;
+            else a.st->index_invalid = 1u;                   // cannot be proven: make the caller fall back
+        }
+        if (v.keep && h.has_samples && h.g >= 0 && !v.uniform) atomicAdd(&a.st->n_nu_count, 1ull);
         if (v.keep) ++kept;
     }
     if (p != end) a.st->walk_broken = 1u;
-    if (!kWrite) a.wcount[w] = make_uint2(lines, kept);
+    a.wcount[w] = make_uint2(lines, kept < kWalkSlots ? kept : kWalkSlots);
 }
 
 // single CTA: exclusive prefix sum of kept rows over the walkers + totals.  1024 walkers per round, read coalesced (the
@@ -282,6 +284,26 @@ __global__ void __launch_bounds__(1024) walk_scan_kernel(const WalkArgs a) {
         __syncthreads();                                    // s_rows / s_lines are rewritten by the next round
     }
     if (t == 0) { a.st->n_records = carry_rows; a.st->n_lines = carry_lines; }
+}
+
+// padded rows -> dense rows: thread = (walker, slot); a row that needs the general decode path registers its dense index
+// under the checkpoint-table slot it was given during the walk
+__global__ void __launch_bounds__(256) walk_compact_kernel(const WalkArgs a) {
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t w = (uint32_t)(t / kWalkSlots), j = (uint32_t)(t - (uint64_t)w * kWalkSlots);
+    if (w >= a.n_walkers || j >= a.wcount[w].y) return;
+    const uint64_t dst = a.wrow[w] + j;
+    a.out.start[dst] = a.pad.start[t];
+    a.out.stop[dst] = a.pad.stop[t];
+    a.out.ref[dst] = a.pad.ref[t];
+    a.out.alt[dst] = a.pad.alt[t];
+    a.out.chrom_abs[dst] = a.pad.chrom_abs[t];
+    a.out.chrom_len[dst] = a.pad.chrom_len[t];
+    a.out.chrom5[dst] = a.pad.chrom5[t];
+    const RowInfo ri = a.pad.rowinfo[t];
+    a.out.rowinfo[dst] = ri;
+    const uint32_t gi = ri.misc & 0xffu;
+    if ((ri.misc & kRowHasSamples) && gi != 255u && !(ri.misc & kRowUniform)) a.out.nu_rows[ri.cp_row] = (uint32_t)dst;
 }
 
 // The jumped-over spans nobody decodes: [tab9, tab9 + 4*S) must not hold a newline.
@@ -325,29 +347,37 @@ static WalkArgs make_args(const uint8_t *d_text, uint64_t nbytes, uint32_t n_sam
     return a;
 }
 
-void launch_walk_count(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
-                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
-                       uint64_t *d_wrow, DevStatus *d_st, const Launch &L) {
+void launch_walk(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes, uint32_t n_walkers,
+                 const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount, uint64_t *d_wrow, const WalkPad &pad,
+                 uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L) {
     WalkArgs a = make_args(d_text, nbytes, n_samples, range_bytes, n_walkers, rg, end_is_int, d_wstart,
                            (uint2 *)d_wcount, d_wrow, d_st);
+    a.pad.start = pad.start; a.pad.stop = pad.stop; a.pad.ref = pad.ref; a.pad.alt = pad.alt;
+    a.pad.chrom_abs = pad.chrom_abs; a.pad.chrom_len = pad.chrom_len; a.pad.chrom5 = pad.chrom5; a.pad.rowinfo = pad.rowinfo;
+    a.pad.nu_rows = nullptr;                 // (the dense index is registered by the compaction)
+    a.pad.st = d_st;
+    a.verify = d_verify; a.verify_cap = verify_cap;
     walk_sync_kernel<<<(n_walkers + 1 + 7) / 8, 256, 0, L.stream>>>(a);
-    walk_kernel<false><<<(n_walkers + WK_THREADS - 1) / WK_THREADS, WK_THREADS, 0, L.stream>>>(a);
+    walk_kernel<<<(n_walkers + WK_THREADS - 1) / WK_THREADS, WK_THREADS, 0, L.stream>>>(a);
     walk_scan_kernel<<<1, 1024, 0, L.stream>>>(a);
     count_launch(3);
 }
 
-void launch_walk_write(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint64_t range_bytes,
-                       uint32_t n_walkers, const RegionArg &rg, int end_is_int, uint64_t *d_wstart, void *d_wcount,
-                       uint64_t *d_wrow, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt,
-                       uint64_t *d_chrom_abs, uint8_t *d_chrom_len, uint64_t *d_chrom5, RowInfo *d_rowinfo,
-                       uint32_t *d_nu_rows, uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L) {
-    WalkArgs a = make_args(d_text, nbytes, n_samples, range_bytes, n_walkers, rg, end_is_int, d_wstart,
-                           (uint2 *)d_wcount, d_wrow, d_st);
+void launch_walk_compact(const uint8_t *d_text, uint64_t nbytes, uint32_t n_samples, uint32_t n_walkers, void *d_wcount,
+                         uint64_t *d_wrow, const WalkPad &pad, uint32_t *d_start, uint32_t *d_stop, uint8_t *d_ref, uint8_t *d_alt,
+                         uint64_t *d_chrom_abs, uint8_t *d_chrom_len, uint64_t *d_chrom5, RowInfo *d_rowinfo,
+                         uint32_t *d_nu_rows, uint64_t *d_verify, uint64_t verify_cap, DevStatus *d_st, const Launch &L) {
+    RegionArg rg;
+    memset(&rg, 0, sizeof rg);
+    WalkArgs a = make_args(d_text, nbytes, n_samples, 0, n_walkers, rg, 0, nullptr, (uint2 *)d_wcount, d_wrow, d_st);
+    a.pad.start = pad.start; a.pad.stop = pad.stop; a.pad.ref = pad.ref; a.pad.alt = pad.alt;
+    a.pad.chrom_abs = pad.chrom_abs; a.pad.chrom_len = pad.chrom_len; a.pad.chrom5 = pad.chrom5; a.pad.rowinfo = pad.rowinfo;
     a.out.start = d_start; a.out.stop = d_stop; a.out.ref = d_ref; a.out.alt = d_alt;
     a.out.chrom_abs = d_chrom_abs; a.out.chrom_len = d_chrom_len; a.out.chrom5 = d_chrom5; a.out.rowinfo = d_rowinfo;
     a.out.nu_rows = d_nu_rows;
     a.verify = d_verify; a.verify_cap = verify_cap;
-    walk_kernel<true><<<(n_walkers + WK_THREADS - 1) / WK_THREADS, WK_THREADS, 0, L.stream>>>(a);
+    const uint64_t n = (uint64_t)n_walkers * kWalkSlots;
+    walk_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, L.stream>>>(a);
     const uint32_t pieces = (uint32_t)((4ull * n_samples + 4095) / 4096);
     walk_verify_kernel<<<L.sm_count * 4, 256, 0, L.stream>>>(a, pieces ? pieces : 1);
     count_launch(2);
