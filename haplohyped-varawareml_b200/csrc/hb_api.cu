@@ -480,7 +480,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
 // ---- records located by walking heads (uniform GT-only text): hb_walk.cu
 static int index_by_walker(hb_parse *p, const Launch &L) {
     {
-        const uint32_t k = 16;                         // lines per walker: 4 / 8 / 16 / 32 give 0.95 / 0.59 / 0.44 / 0.57 ms for locate and 0.20 / 0.23 / 0.27 / 0.52 ms for the site pass (r02k)
+        const uint32_t k = 16;                         // lines per walker; one-pass walker (r02u): 10 / 12 / 14 / 16 give 0.61 / 0.49 / 0.51 / 0.42 ms for locate
         p->n_walkers = walk_plan(p->nbytes, p->first_line_len, k, &p->walk_range);
         if (!p->d_wstart || p->n_walkers > p->walk_cap) {
             TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
