@@ -224,22 +224,27 @@ struct SiteArgs4 {
     int deep;                    // 4-way bucket matcher (HB_SITE_MATCHER=deep): smaller templates, slower kernel
 };
 
-constexpr int kSiteSegs = 8;                     // = warps of the CTA
+constexpr int kSiteSegs = 12;                    // = warps of the CTA
 constexpr int kSiteHashLog = 10;
 __host__ __device__ inline uint32_t site_seg_cap(uint32_t len) { return (len + len / 255 + 24 + 15) & ~15u; }
 // Segment s of the encoded part [0, 24*cr+1) of the site planes covers [site_seg_begin(s), site_seg_begin(s+1)).
-// The cuts follow where the work is: the REF plane (13) and the ALT plane (23) are random A/C/G/T -- hundreds of
-// short matches each -- and get three warps each; everything else (constant, zero, or literal-only planes) is cheap.
+// The cuts follow where the work is.  r01 gave the random REF and ALT planes three warps each and the nine planes in
+// front of them ONE: the r02v ncu capture showed 69 % of the stall samples at the barrier behind the encode -- seven
+// warps waiting for the one that walks start's byte 1 (a short run every few records) after five constant planes.
 __host__ __device__ inline uint32_t site_seg_begin(int s, uint32_t cr) {
     switch (s) {
-        case 0: return 0;
-        case 1: return 9 * cr;
-        case 2: return 13 * cr;
-        case 3: return 13 * cr + cr / 3;
-        case 4: return 13 * cr + 2 * cr / 3;
-        case 5: return 23 * cr;
-        case 6: return 23 * cr + cr / 3;
-        case 7: return 23 * cr + 2 * cr / 3;
+        case 0: return 0;                          // CHROM bytes: five constant planes
+        case 1: return 5 * cr;                     // start, byte 0: literals
+        case 2: return 6 * cr;                     // start, byte 1: a run every few records, in two halves
+        case 3: return 6 * cr + cr / 2;
+        case 4: return 7 * cr;                     // start, bytes 2-3
+        case 5: return 9 * cr;                     // stop: matches 4 * cr back
+        case 6: return 13 * cr;                    // REF in thirds (the last one runs on through the nine zero planes)
+        case 7: return 13 * cr + cr / 3;
+        case 8: return 13 * cr + 2 * cr / 3;
+        case 9: return 23 * cr;                    // ALT in thirds
+        case 10: return 23 * cr + cr / 3;
+        case 11: return 23 * cr + 2 * cr / 3;
         default: return 24 * cr + 1;
     }
 }
@@ -976,7 +981,7 @@ static int frames_site_pass(hb_frames *f, hb_parse *p, bool early) {
     }
     CUF(cudaEventRecord(early ? f->ev_side0 : f->ev[0], st));
     raise_smem_limit(reinterpret_cast<const void *>(site_template_kernel));
-    site_template_kernel<<<(unsigned)f->n_chunks, 256, f->smem_site, st>>>(sa);
+    site_template_kernel<<<(unsigned)f->n_chunks, kSiteSegs * 32, f->smem_site, st>>>(sa);
     count_launch();
     CUF(cudaEventRecord(early ? f->ev_tmpl : f->ev[1], st));
     f->early_site = early;
