@@ -224,27 +224,34 @@ struct SiteArgs4 {
     int deep;                    // 4-way bucket matcher (HB_SITE_MATCHER=deep): smaller templates, slower kernel
 };
 
-constexpr int kSiteSegs = 12;                    // = warps of the CTA
+constexpr int kSiteSegs = 18;                    // = warps of the CTA
 constexpr int kSiteHashLog = 10;
 __host__ __device__ inline uint32_t site_seg_cap(uint32_t len) { return (len + len / 255 + 24 + 15) & ~15u; }
 // Segment s of the encoded part [0, 24*cr+1) of the site planes covers [site_seg_begin(s), site_seg_begin(s+1)).
 // The cuts follow where the work is.  r01 gave the random REF and ALT planes three warps each and the nine planes in
 // front of them ONE: the r02v ncu capture showed 69 % of the stall samples at the barrier behind the encode -- seven
 // warps waiting for the one that walks start's byte 1 (a short run every few records) after five constant planes.
+// The cuts below equalise the per-segment cycle counts measured with clock64() (0.57 -> 0.23 -> 0.14 ms).
 __host__ __device__ inline uint32_t site_seg_begin(int s, uint32_t cr) {
-    switch (s) {
-        case 0: return 0;                          // CHROM bytes: five constant planes
-        case 1: return 5 * cr;                     // start, byte 0: literals
-        case 2: return 6 * cr;                     // start, byte 1: a run every few records, in two halves
-        case 3: return 6 * cr + cr / 2;
-        case 4: return 7 * cr;                     // start, bytes 2-3
-        case 5: return 9 * cr;                     // stop: matches 4 * cr back
-        case 6: return 13 * cr;                    // REF in thirds (the last one runs on through the nine zero planes)
-        case 7: return 13 * cr + cr / 3;
-        case 8: return 13 * cr + 2 * cr / 3;
-        case 9: return 23 * cr;                    // ALT in thirds
-        case 10: return 23 * cr + cr / 3;
-        case 11: return 23 * cr + 2 * cr / 3;
+    switch (s) {                                   // (cycles of a warp on its segment, r02w, at cr = 1075)
+        case 0: return 0;                          // CHROM bytes: five constant planes                           38 K
+        case 1: return 5 * cr;                     // start, byte 0: literals                                     27 K
+        case 2: return 6 * cr;                     // start, byte 1: a short run every few records -- the most
+        case 3: return 6 * cr + cr / 5;            //   expensive bytes of the block (180 cycles each): in fifths  39 K
+        case 4: return 6 * cr + 2 * cr / 5;
+        case 5: return 6 * cr + 3 * cr / 5;
+        case 6: return 6 * cr + 4 * cr / 5;
+        case 7: return 7 * cr;                     // start, bytes 2-3                                            17 K
+        case 8: return 9 * cr;                     // stop: matches 4 * cr back, in halves                        25 K
+        case 9: return 11 * cr;
+        case 10: return 13 * cr;                   // REF in thirds                                               33 K
+        case 11: return 13 * cr + cr / 3;
+        case 12: return 13 * cr + 2 * cr / 3;
+        case 13: return 14 * cr;                   // the nine zero planes behind REF, in halves                  29 K
+        case 14: return 18 * cr + cr / 2;
+        case 15: return 23 * cr;                   // ALT in thirds                                               33 K
+        case 16: return 23 * cr + cr / 3;
+        case 17: return 23 * cr + 2 * cr / 3;
         default: return 24 * cr + 1;
     }
 }
