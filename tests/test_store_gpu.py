@@ -248,3 +248,32 @@ def test_allele_plane_encoder_on_degenerate_and_hostile_planes(capi):
     text, samples = _pattern_vcf(2300, cols)
     for cr in (1075, 0, 64, 6, 2300):
         _check(capi, text, len(samples), "chr22", cr, list(range(len(samples))))
+
+
+def test_frames_launched_from_inside_the_parse_are_the_same_frames(capi):
+    """hb_parse_attach_frames: on a re-run of the parse the frame kernel is queued right behind the GT decoder from inside
+    hb_parse_rerun (the host waits for the templates only) and hb_frames_rerun just collects: byte-identical to frames made
+    the plain way, run after run, and a moved sample window falls back to the plain path."""
+    spec = capi.synth_spec(5000, 150, seed=12, mix=1 << 8)
+    text = capi.synth_header(spec) + capi.synth_host(spec)
+    body = synth.body_of(text)
+    plain = capi.Parse.from_host(body, 150, region="chr22")
+    fp = plain.compress(300)
+    want, o_want, z_want = fp.fetch_packed()
+    p = capi.Parse.from_host(body, 150, region="chr22")
+    fr = p.compress(300)
+    p.attach(fr)
+    for _ in range(3):
+        p.rerun()
+        fr.rerun(p)
+        got, o, z = fr.fetch_packed()
+        assert np.array_equal(z, z_want) and np.array_equal(o, o_want) and np.array_equal(got, want)
+        assert fr.info.total_bytes == fp.info.total_bytes == int(z_want.sum())
+    p.rerun()                                              # frames launched for all samples ...
+    fr.set_window(10, 40)                                  # ... but the caller wants a window now
+    fr.rerun(p)
+    win = plain.compress(300, 10, 40)
+    a, _, za = fr.fetch_packed()
+    b, _, zb = win.fetch_packed()
+    assert np.array_equal(za, zb) and np.array_equal(a, b)
+    p.attach(None)
