@@ -1457,7 +1457,7 @@ struct Assembler {
         uint8_t *dst = buf + poff[i];
         const uint8_t *tp = tmpl + c * (uint64_t)f->tmpl_cap;
         const uint8_t *tail = piece.stage + (tail_off[i] - piece.tail_base), *hdr = piece.stage + piece.hdr_at + 32 * (i - piece.first);
-        if (tl16 >= 32 && sz >= tl16) {
+        if (tl16 >= 32 && sz >= tl16 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0) {     // (frames start on 16-byte boundaries of buf)
             stream16(dst, hdr, 32);                                       // header with this frame's size fields
             stream16(dst + 32, tp + 32, tl16 - 32);                       // template body
             stream16(dst + tl16, tail, ((size_t)(sz - tl16) + 15) & ~size_t(15));     // own tail from the template's last 16-byte boundary, zero pad included

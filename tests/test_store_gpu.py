@@ -149,6 +149,11 @@ def test_long_segments_and_layout(capi, mix, chunk_records):
             tot2, o2, z2 = fr.fetch_packed(out=(pin.data_ptr(), pin.numel()))
             assert tot2 == len(pk) and np.array_equal(pin.numpy()[:tot2], pk) and (pin.numpy()[tot2:] == 0xEE).all()
             assert np.array_equal(o2, poffs) and np.array_equal(z2, psizes)
+        # a destination that is not 16-byte aligned (the streaming stores need alignment: plain copies then)
+        odd = np.empty(len(pk) + 64, np.uint8)
+        shift = (1 - odd.ctypes.data) % 16 or 16
+        tot3, _, _ = fr.fetch_packed(out=(odd.ctypes.data + shift, len(pk)))
+        assert tot3 == len(pk) and np.array_equal(odd[shift:shift + tot3], pk)
     finally:
         capi.lib().hb_set_fetch_mode(0)
         capi.lib().hb_set_host_threads(0)
