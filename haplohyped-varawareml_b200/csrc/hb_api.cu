@@ -31,7 +31,8 @@ namespace hb {
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<uint64_t> g_text_limit{0};      // hb_parse_set_text_limit: 0 = from free device memory
+static std::atomic<uint64_t> g_text_limit{0};
+static std::atomic<uint32_t> g_walker_lines{16};   // hb_set_walker_lines      // hb_parse_set_text_limit: 0 = from free device memory
 void count_launch(uint64_t n) { g_launches += n; }
 
 static int fail(int code, const std::string &msg) {
@@ -480,7 +481,7 @@ static int index_by_tokenizer(hb_parse *p, const Launch &L) {
 // ---- records located by walking heads (uniform GT-only text): hb_walk.cu
 static int index_by_walker(hb_parse *p, const Launch &L) {
     {
-        const uint32_t k = 16;                         // lines per walker; one-pass walker (r02u): 10 / 12 / 14 / 16 give 0.61 / 0.49 / 0.51 / 0.42 ms for locate
+        const uint32_t k = g_walker_lines.load();      // lines per walker: 16 (one-pass walker, r02u: 10 / 12 / 14 / 16 give 0.61 / 0.49 / 0.51 / 0.42 ms for locate)
         p->n_walkers = walk_plan(p->nbytes, p->first_line_len, k, &p->walk_range);
         if (!p->d_wstart || p->n_walkers > p->walk_cap) {
             TRY(dev_alloc(&p->d_wstart, (uint64_t)p->n_walkers + 1));
@@ -1530,6 +1531,7 @@ void hb_cache_set_limit(uint64_t hbm_bytes) {
 }
 
 void hb_parse_set_text_limit(uint64_t text_bytes) { g_text_limit.store(text_bytes); }
+void hb_set_walker_lines(uint32_t lines) { g_walker_lines.store(lines == 0 ? 16u : std::min(lines, 20u)); }
 
 void hb_cache_clear(void) {
     {

@@ -221,7 +221,7 @@ struct SiteArgs4 {
     uint8_t *tmpl;               // [n_chunks][tmpl_cap], 16-byte aligned rows
     uint32_t tmpl_cap;
     uint32_t *tmpl_len;          // [n_chunks] = TMPL_HDR + LZ4 bytes of the site planes
-    int deep;                    // 4-way bucket matcher (HB_SITE_MATCHER=deep): smaller templates, slower kernel
+    int deep;                    // 4-way bucket matcher (hb_set_site_matcher(1)): smaller templates, slower kernel
 };
 
 constexpr int kSiteSegs = 18;                    // = warps of the CTA

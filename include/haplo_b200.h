@@ -147,6 +147,9 @@ int hb_parse_stream_bgzf_resident(const uint8_t *bgzf, uint64_t nbytes, const ch
  * would not fit the device next to its planes (text > 0.9 x free / 1.55).  text_bytes != 0 sets the threshold explicitly
  * (bound the HBM a parse may take; tests); 0 = automatic. */
 void hb_parse_set_text_limit(uint64_t text_bytes);
+/* Lines per walker of the head walker (kernel 1a): 0 = the default (16), at most 20 (a walker has 24 row slots).  Tests
+ * use 1-3 to put a walker boundary at every line. */
+void hb_set_walker_lines(uint32_t lines);
 /* sample names of a file-level parse, NUL-separated */
 int hb_parse_samples(hb_parse *p, uint32_t *n, char *names, uint64_t cap, uint64_t *len);
 /* re-run the kernels of an existing handle on (new contents of) the same device buffer: no allocation */

@@ -175,10 +175,19 @@ def test_many_tiles_lookback(capi):
 # ------------------------------------------------------------------------------------------------
 # head walker (tokenizer 3): records located by jumping 4*S bytes from the 9th tab
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("lines_per_walker", ["1", "3", "16", "500"])
+@pytest.fixture
+def walker_lines(capi):
+    """hb_set_walker_lines for one test (1-3 lines per walker put a walker boundary at every line)."""
+    def set_lines(n):
+        capi.lib().hb_set_walker_lines(int(n))
+    yield set_lines
+    capi.lib().hb_set_walker_lines(0)
+
+
+@pytest.mark.parametrize("lines_per_walker", ["1", "3", "16", "20"])
 @pytest.mark.parametrize("mix", [0, 1])
-def test_walker_uniform_text(capi, monkeypatch, lines_per_walker, mix):
-    monkeypatch.setenv("HB_WALK_LINES", lines_per_walker)
+def test_walker_uniform_text(capi, walker_lines, lines_per_walker, mix):
+    walker_lines(lines_per_walker)
     spec = capi.synth_spec(6000, 300, seed=17 + mix, mix=mix)
     text = capi.synth_header(spec) + capi.synth_host(spec)
     p, info = _check_matrix(capi, text, spec.n_samples, "chr22", tokenizer=0)
@@ -188,10 +197,10 @@ def test_walker_uniform_text(capi, monkeypatch, lines_per_walker, mix):
     assert p.info.tokenizer_used == 3 and p.info.n_records == info.n_records
 
 
-def test_walker_odd_lines_stay_exact(capi, monkeypatch):
+def test_walker_odd_lines_stay_exact(capi, walker_lines):
     """Comment lines, empty lines, CRLF, wide records, other FORMATs and a missing final newline inside
     otherwise uniform text: the walker searches those newlines instead of jumping."""
-    monkeypatch.setenv("HB_WALK_LINES", "4")
+    walker_lines(4)
     S = synth.sample_names(260)
     rng = np.random.default_rng(0)
 
@@ -225,11 +234,11 @@ def test_walker_odd_lines_stay_exact(capi, monkeypatch):
     _check_matrix(capi, text[:-1], 260, "chr22", tokenizer=3)        # no final newline
 
 
-def test_walker_cannot_be_fooled_by_hidden_newlines(capi, monkeypatch):
+def test_walker_cannot_be_fooled_by_hidden_newlines(capi, walker_lines):
     """Two short records whose lengths add up so that (9th tab of the first) + 4*S lands exactly on the
     second one's newline: the jump is accepted by the walker and must be caught afterwards -- by the
     verify kernel when the merged record is dropped, by the GT decoder when it is kept."""
-    monkeypatch.setenv("HB_WALK_LINES", "2")
+    walker_lines(2)
     n = 300
     S = synth.sample_names(n)
     rng = np.random.default_rng(1)
