@@ -42,6 +42,7 @@ struct GtSmem {
     int mode[kTV];                        // 0 nothing to decode (zeros), 1 staged fast path, 2 general path
     alignas(8) uint64_t bar;
     uint32_t any_general;                 // some record of the tile takes the general path (phase 2)
+    uint32_t any_fast;                    // some record of the tile is staged for the fast path (phase 1)
 };
 
 // One sample column starting at p (first byte after the TAB).  Restates htslib's GT parse:
@@ -120,6 +121,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         mbar_init(&sm.bar, kTV);                           // every record's thread arrives, with the bytes it requested
         mbar_fence_init();
         sm.any_general = 0;
+        sm.any_fast = 0;
     }
     if (tid < kTS + 4) sm.dummy[tid] = 0x307C3009u;
     __syncthreads();
@@ -158,6 +160,7 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
         sm.seg_g[tid] = g;
         sm.mode[tid] = mode;
         if (mode == 2) sm.any_general = 1u;
+        if (mode == 1) sm.any_fast = 1u;
         if (mode == 1) {
             sm.addr[tid] = (uint32_t)tid * SEG_PITCH + ((uint32_t)(b & 15ull) & ~3u);
             sm.shft[tid] = 8u * ((uint32_t)b & 3u);
@@ -200,6 +203,9 @@ decode_gt_kernel(const uint8_t *__restrict__ text, const RowInfo *__restrict__ r
     //      Records that are not on the fast path read a dummy row of "\t0|0" instead (-> zeros), and
     //      anything that is not "\t[01]|[01]" only raises a flag, so the hot loop has no branches;
     //      flagged threads then redo their few odd calls one by one.
+    if (!sm.any_fast) {      // a tile of general-path records only (GT:GQ:DP text): nothing to decode here, the tile starts as zeros
+        for (int i = tid; i < (int)(sizeof(sm.out) / 16); i += GT_THREADS) reinterpret_cast<uint4 *>(&sm.out[0][0][0])[i] = make_uint4(0, 0, 0, 0);
+    } else
     for (int item = tid; item < kTS * (kTV / 16); item += GT_THREADS) {
         const int s = item % kTS, rg = item / kTS;
         uint32_t acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
