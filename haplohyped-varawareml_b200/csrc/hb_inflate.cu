@@ -34,6 +34,9 @@ namespace hb {
 constexpr int kLitBits = 10, kDistBits = 8;       // primary table widths; longer codes take the canonical slow path
 constexpr int kInfWarps = 8;
 
+// runs of period d < 32: D = d * (32 / d); lane / d == (lane * inv) >> 16 for lane < 32 with inv = 65536 / d + 1 (d = 1: lane % 1 == 0)
+__constant__ uint8_t c_runD[32] = {0, 32, 32, 30, 32, 30, 30, 28, 32, 27, 30, 22, 24, 26, 28, 30, 32, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+__constant__ uint32_t c_runInv[32] = {0, 65536, 32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4097, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115};
 __constant__ uint8_t c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 struct HuffTab {            // one canonical Huffman code, in shared memory
@@ -289,9 +292,10 @@ __global__ void __launch_bounds__(kInfWarps * 32, 6) inflate_bgzf_kernel(const I
                     for (int k = 0; k < 3; ++k) { const uint32_t i = base + 32 * k + lane; if (i < len) to[i] = v[k]; }
                 }
             } else if (d < 32) {                           // a run of period d (the "0|0\t" of genotype text is d = 4, len = 258):
-                const uint32_t D = d * (32u / d);          // a lane's byte repeats every D = the largest multiple of d <= 32
-                if ((uint32_t)lane < D) {
-                    const uint8_t b = __ldcg(from + (uint32_t)lane % d);
+                const uint32_t D = c_runD[d];              // a lane's byte repeats every D = the largest multiple of d <= 32
+                if ((uint32_t)lane < D) {                  // (D and lane % d from tables: two divisions by a variable cost ~40 instructions)
+                    const uint32_t r = (uint32_t)lane - (((uint32_t)lane * c_runInv[d]) >> 16) * d;
+                    const uint8_t b = __ldcg(from + r);
                     for (uint32_t i = lane; i < len; i += D) to[i] = b;
                 }
             } else {                                       // 32 <= d < len: each 32 bytes read what the ones before stored
